@@ -1,0 +1,214 @@
+"""aither_b200 -- B200-native hot path of the Aither structured-grid flow solver.
+
+The product is the C-ABI shared library `aither_b200/lib/libaither_b200.so` (CUDA, sm_100a; ABI in
+include/aither_gpu.h). This package is the thin Python host side used by the tests and bench:
+`GridLevel` mirrors the reference's `gridLevel` / `mgSolution::Iterate` interface (reference
+include/gridLevel.hpp:84-109, src/mgSolution.cpp:246-269) one method per phase, calling straight
+through ctypes. There is no CPU fallback: if the library or a GPU is missing, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ctypes_abi as abi
+from .problem import Block, Problem, make_cfg  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaither_b200.so")
+_LIB = None
+
+# every symbol include/aither_gpu.h declares
+ABI_SYMBOLS = (
+    "aither_gpu_create", "aither_gpu_store_old_solution", "aither_gpu_iterate",
+    "aither_gpu_get_boundary_conditions", "aither_gpu_calc_residual", "aither_gpu_calc_time_step",
+    "aither_gpu_invert_diagonal", "aither_gpu_initialize_matrix_update", "aither_gpu_relax",
+    "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
+    "aither_gpu_upload_state", "aither_gpu_download_state", "aither_gpu_download_field",
+    "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
+    "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
+    "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
+    "aither_gpu_destroy", "aither_gpu_last_error", "aither_gpu_version",
+)
+
+
+class AitherGpuError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the CUDA library and declare its prototypes. Raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise AitherGpuError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                             % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    pd = C.POINTER(C.c_double)
+    vp = C.c_void_p
+    L.aither_gpu_create.argtypes = [C.POINTER(abi.Cfg), C.c_int, C.POINTER(abi.BlockDesc), C.c_int,
+                                    C.POINTER(abi.Conn), C.c_int, C.c_int, vp, C.c_int,
+                                    C.POINTER(vp)]
+    L.aither_gpu_store_old_solution.argtypes = [vp, C.c_int]
+    L.aither_gpu_iterate.argtypes = [vp, C.c_double, C.c_int, pd, C.POINTER(abi.Linf), pd]
+    for name in ("aither_gpu_get_boundary_conditions", "aither_gpu_calc_residual",
+                 "aither_gpu_invert_diagonal", "aither_gpu_initialize_matrix_update",
+                 "aither_gpu_reset_diagonal", "aither_gpu_synchronize", "aither_gpu_timer_start",
+                 "aither_gpu_destroy"):
+        getattr(L, name).argtypes = [vp]
+    L.aither_gpu_calc_time_step.argtypes = [vp, C.c_double]
+    L.aither_gpu_relax.argtypes = [vp, C.c_int, pd]
+    L.aither_gpu_update_blocks.argtypes = [vp, C.c_int, pd, C.POINTER(abi.Linf)]
+    L.aither_gpu_run.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, pd]
+    L.aither_gpu_upload_state.argtypes = [vp, C.c_int, pd]
+    L.aither_gpu_download_state.argtypes = [vp, C.c_int, pd]
+    L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
+    L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
+    L.aither_gpu_field_size.restype = C.c_longlong
+    L.aither_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.aither_gpu_launch_count.argtypes = [vp]
+    L.aither_gpu_launch_count.restype = C.c_longlong
+    L.aither_gpu_profile_enable.argtypes = [vp, C.c_int]
+    L.aither_gpu_profile_get.argtypes = [vp, C.c_int, pd, C.POINTER(C.c_longlong)]
+    L.aither_gpu_kernel_family_name.argtypes = [C.c_int]
+    L.aither_gpu_kernel_family_name.restype = C.c_char_p
+    L.aither_gpu_last_error.restype = C.c_char_p
+    L.aither_gpu_version.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class GridLevel:
+    """Device-resident grid level + linear solver for the blocks owned by this rank."""
+
+    def __init__(self, problem, device=0, rank=0, n_ranks=1, block_ids=None, nccl_comm=None):
+        self.problem = problem
+        self.neq = problem.neq
+        self.block_ids = list(range(len(problem.blocks))) if block_ids is None else list(block_ids)
+        self._lib = load_library()
+        descs, conns, keep = problem.c_records(self.block_ids)
+        h = C.c_void_p()
+        rc = self._lib.aither_gpu_create(C.byref(problem.cfg), len(self.block_ids), descs,
+                                         len(problem.conns), conns, rank, n_ranks, nccl_comm,
+                                         device, C.byref(h))
+        self._h = h if rc == 0 else None
+        self._check(rc)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AitherGpuError(self._lib.aither_gpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.aither_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mgSolution / gridLevel interface --------------------------------------------------
+    def store_old_solution(self, it=0):
+        self._check(self._lib.aither_gpu_store_old_solution(self._h, it))
+
+    def get_boundary_conditions(self):
+        self._check(self._lib.aither_gpu_get_boundary_conditions(self._h))
+
+    def calc_residual(self):
+        self._check(self._lib.aither_gpu_calc_residual(self._h))
+
+    def calc_time_step(self, cfl):
+        self._check(self._lib.aither_gpu_calc_time_step(self._h, cfl))
+
+    def invert_diagonal(self):
+        self._check(self._lib.aither_gpu_invert_diagonal(self._h))
+
+    def initialize_matrix_update(self):
+        self._check(self._lib.aither_gpu_initialize_matrix_update(self._h))
+
+    def relax(self, sweeps=None):
+        if sweeps is None:
+            sweeps = self.problem.cfg.matrixSweeps
+        mr = C.c_double()
+        self._check(self._lib.aither_gpu_relax(self._h, sweeps, C.byref(mr)))
+        return mr.value
+
+    def update_blocks(self, mm=0):
+        l2 = np.zeros(self.neq)
+        linf = abi.Linf()
+        self._check(self._lib.aither_gpu_update_blocks(self._h, mm, _ptr(l2), C.byref(linf)))
+        return l2, linf
+
+    def reset_diagonal(self):
+        self._check(self._lib.aither_gpu_reset_diagonal(self._h))
+
+    def iterate(self, cfl, mm=0):
+        """One nonlinear iteration; returns (residL2[neq], linf, matrixResid)."""
+        l2 = np.zeros(self.neq)
+        linf = abi.Linf()
+        mr = C.c_double()
+        self._check(self._lib.aither_gpu_iterate(self._h, cfl, mm, _ptr(l2), C.byref(linf),
+                                                 C.byref(mr)))
+        return l2, linf, mr.value
+
+    def run(self, n_iter, cfl_start, cfl_step=0.0, cfl_max=None):
+        """n_iter time steps back to back; returns hist[n_iter, neq + 1]."""
+        hist = np.zeros((n_iter, self.neq + 1))
+        self._check(self._lib.aither_gpu_run(self._h, n_iter, cfl_start, cfl_step,
+                                             cfl_start if cfl_max is None else cfl_max, _ptr(hist)))
+        return hist
+
+    # ---- data movement ---------------------------------------------------------------------
+    def field(self, blk, fld):
+        n = self._lib.aither_gpu_field_size(self._h, blk, fld)
+        if n < 0:
+            raise AitherGpuError(self._lib.aither_gpu_last_error().decode())
+        out = np.empty(n)
+        self._check(self._lib.aither_gpu_download_field(self._h, blk, fld, _ptr(out)))
+        b = self.problem.blocks[self.block_ids[blk]]
+        g = self.problem.cfg.numGhosts
+        padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE)
+        shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
+        return out.reshape(shp + (-1,))
+
+    def upload_state(self, blk, state):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        self._check(self._lib.aither_gpu_upload_state(self._h, blk, _ptr(state)))
+
+    def download_state_into(self, blk, out):
+        self._check(self._lib.aither_gpu_download_state(self._h, blk, _ptr(out)))
+
+    # ---- timing ----------------------------------------------------------------------------
+    def synchronize(self):
+        self._check(self._lib.aither_gpu_synchronize(self._h))
+
+    def timer_start(self):
+        self._check(self._lib.aither_gpu_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self._lib.aither_gpu_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return self._lib.aither_gpu_launch_count(self._h)
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.aither_gpu_profile_enable(self._h, int(on)))
+
+    def profile(self):
+        """{family: (ms, launches)} accumulated since profile_enable."""
+        out = {}
+        for f in range(self._lib.aither_gpu_num_kernel_families()):
+            ms, n = C.c_double(), C.c_longlong()
+            self._check(self._lib.aither_gpu_profile_get(self._h, f, C.byref(ms), C.byref(n)))
+            out[self._lib.aither_gpu_kernel_family_name(f).decode()] = (ms.value, n.value)
+        return out

@@ -1,0 +1,876 @@
+// aither_gpu.cu -- host side of the B200 hot path and its C ABI (include/aither_gpu.h).
+//
+// This file is the device-side `gridLevel` + `linearSolver`: it owns the blocks' HBM storage,
+// sequences the kernels of one nonlinear iteration exactly as mgSolution::Iterate /
+// ImplicitUpdate / CycleAtLevel do for a single grid level (ref: src/mgSolution.cpp:160-269), and
+// returns what main.cpp's loop consumes. There is no CPU fallback: every entry point fails with an
+// error if CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/aither_gpu.h"
+#include "halo.cuh"
+#include "kernels.cuh"
+
+using namespace aither;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int Fail(const std::string &msg) {
+  g_lastError = msg;
+  return 1;
+}
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      return Fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                  ":" + std::to_string(__LINE__) + ")");                               \
+    }                                                                                  \
+  } while (0)
+
+enum Family {
+  kFamBc = 0, kFamResidual, kFamPrep, kFamDplur, kFamLusgs, kFamAxmb, kFamUpdate, kFamStore,
+  kFamReduce, kFamHalo, kFamLayout, kNumFamilies
+};
+const char *kFamilyNames[kNumFamilies] = {"bc_ghost_fill", "residual", "dt_diag_init", "dplur_sweep",
+                                          "lusgs_plane", "matrix_residual", "update_norms",
+                                          "store_time_n", "reduce_finalize", "halo_pack_unpack",
+                                          "layout_convert"};
+
+struct HostBlock {
+  BlockDev dev;
+  void *alloc = nullptr;          // one allocation holding every field
+  size_t allocBytes = 0;
+  std::vector<aither_surface> surfaces;
+  SurfDev *dSurfs = nullptr;
+  int nBcSurfs = 0;
+  long long bcThreads = 0;
+  uint8_t *dConnFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int globalPos = 0;
+  long long paddedCells = 0;
+  dim3 cellGrid, cellBlock;       // cell-parallel kernels (32 x 8 threads)
+  dim3 resGrid, resBlock;
+  int nCellBlocks = 0;
+};
+
+}  // namespace
+
+struct aither_gpu {
+  aither_cfg cfg;
+  Params params;
+  int neq = 0, ns = 0, nt = 0, asz = 1;
+  int device = 0;
+  int rank = 0, nRanks = 1;
+  cudaStream_t stream = nullptr;
+  std::vector<HostBlock> blocks;
+  std::vector<aither_conn> conns;
+  HaloPlan halo;
+  aither_bc_state *dBcStates = nullptr;
+  double *dPartials = nullptr;    // per-thread-block partial sums
+  LinfCand *dLinfPartials = nullptr;
+  size_t partialsCap = 0;
+  IterResult *dResults = nullptr;
+  IterResult *hResults = nullptr;  // pinned
+  int resultsCap = 0;
+  double *dStage = nullptr;        // layout-conversion staging
+  size_t stageBytes = 0;
+  long long launches = 0;
+  bool keepMatrixResid = false;
+  // timing
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  bool profile = false;
+  struct Ev { cudaEvent_t a, b; int fam; };
+  std::vector<Ev> evs;
+  double famMs[kNumFamilies] = {0};
+  long long famLaunches[kNumFamilies] = {0};
+};
+
+namespace {
+
+struct ScopedLaunch {
+  aither_gpu *h;
+  int fam;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ScopedLaunch(aither_gpu *h_, int fam_) : h(h_), fam(fam_) {
+    h->launches++;
+    h->famLaunches[fam]++;
+    if (h->profile) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  ~ScopedLaunch() {
+    if (h->profile) {
+      cudaEventRecord(b, h->stream);
+      h->evs.push_back({a, b, fam});
+    }
+  }
+};
+
+void DrainProfile(aither_gpu *h) {
+  for (auto &e : h->evs) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    h->famMs[e.fam] += ms;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  h->evs.clear();
+}
+
+int EnsureStage(aither_gpu *h, size_t bytes) {
+  if (bytes <= h->stageBytes) return 0;
+  if (h->dStage) cudaFree(h->dStage);
+  h->dStage = nullptr;
+  h->stageBytes = 0;
+  CK(cudaMalloc(&h->dStage, bytes));
+  h->stageBytes = bytes;
+  return 0;
+}
+
+// host AoS (reference layout, extents SI,SJ,SK with origin (oi,oj,ok) in physical index space)
+// -> device SoA field
+int UploadAos(aither_gpu *h, const HostBlock &hb, const double *src, int SI, int SJ, int SK,
+              int nc, double *dstField, int originI, int originJ, int originK) {
+  const size_t n = static_cast<size_t>(SI) * SJ * SK * nc;
+  if (EnsureStage(h, n * sizeof(double))) return 1;
+  CK(cudaMemcpyAsync(h->dStage, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const BlockDev &b = hb.dev;
+  const long long cells = static_cast<long long>(SI) * SJ * SK;
+  const int grid = static_cast<int>(std::min<long long>((cells + 255) / 256, 148 * 16));
+  {
+    ScopedLaunch sl(h, kFamLayout);
+    AosToSoaKernel<<<grid, 256, 0, h->stream>>>(h->dStage, SI, SJ, SK, nc, dstField, b.fs,
+                                                originI + b.lp, originJ + b.g, originK + b.g, b.sj,
+                                                b.sk);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int DownloadAos(aither_gpu *h, const HostBlock &hb, double *dst, int SI, int SJ, int SK, int nc,
+                const double *srcField, int originI, int originJ, int originK) {
+  const size_t n = static_cast<size_t>(SI) * SJ * SK * nc;
+  if (EnsureStage(h, n * sizeof(double))) return 1;
+  const BlockDev &b = hb.dev;
+  const long long cells = static_cast<long long>(SI) * SJ * SK;
+  const int grid = static_cast<int>(std::min<long long>((cells + 255) / 256, 148 * 16));
+  {
+    ScopedLaunch sl(h, kFamLayout);
+    SoaToAosKernel<<<grid, 256, 0, h->stream>>>(h->dStage, SI, SJ, SK, nc, srcField, b.fs,
+                                                originI + b.lp, originJ + b.g, originK + b.g, b.sj,
+                                                b.sk);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, h->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int SurfaceType(const aither_surface &s) {
+  // ref: src/boundaryConditions.cpp:2424-2452
+  if (s.imin == s.imax) return s.imax == 0 ? 1 : 2;
+  if (s.jmin == s.jmax) return s.jmax == 0 ? 3 : 4;
+  return s.kmax == 0 ? 5 : 6;
+}
+
+bool Supported(const aither_cfg &c, std::string *why) {
+  if (c.numSpecies != 1) { *why = "only single-species gas is built in this round"; return false; }
+  if (c.numTurb != 0 || c.isRANS) { *why = "RANS turbulence models are not built in this round"; return false; }
+  if (c.isViscous) { *why = "viscous fluxes are not built in this round"; return false; }
+  if (c.isBlockMatrix) { *why = "block-matrix solvers (blusgs/bdplur) are not built in this round"; return false; }
+  if (c.invFluxJac != AITHER_JAC_RUSANOV) { *why = "approximateRoe flux jacobian is not built in this round"; return false; }
+  if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
+  return true;
+}
+
+template <int NS, int NT>
+int LaunchResidual(aither_gpu *h, HostBlock &hb) {
+  const aither_cfg &c = h->cfg;
+  const int implicitScalar = 1;
+  ScopedLaunch sl(h, kFamResidual);
+#define RES(RC, LM, FX)                                                                  \
+  ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(hb.dev, \
+                                                                               h->params, \
+                                                                               implicitScalar)
+#define RES_FLUX(RC, LM)                         \
+  do {                                           \
+    if (c.invFlux == AITHER_FLUX_ROE) RES(RC, LM, AITHER_FLUX_ROE); \
+    else RES(RC, LM, AITHER_FLUX_AUSM);          \
+  } while (0)
+  if (c.recon == AITHER_RECON_CONSTANT) {
+    RES_FLUX(AITHER_RECON_CONSTANT, AITHER_LIMITER_NONE);
+  } else if (c.recon == AITHER_RECON_MUSCL) {
+    if (c.limiter == AITHER_LIMITER_NONE) RES_FLUX(AITHER_RECON_MUSCL, AITHER_LIMITER_NONE);
+    else if (c.limiter == AITHER_LIMITER_VAN_ALBADA) RES_FLUX(AITHER_RECON_MUSCL, AITHER_LIMITER_VAN_ALBADA);
+    else RES_FLUX(AITHER_RECON_MUSCL, AITHER_LIMITER_MINMOD);
+  } else {
+    RES_FLUX(AITHER_RECON_WENO, AITHER_LIMITER_NONE);
+  }
+#undef RES
+#undef RES_FLUX
+  return 0;
+}
+
+int ZeroResult(aither_gpu *h, int slot) {
+  CK(cudaMemsetAsync(h->dResults + slot, 0, sizeof(IterResult), h->stream));
+  return 0;
+}
+
+int EnsureResults(aither_gpu *h, int n) {
+  if (n <= h->resultsCap) return 0;
+  if (h->dResults) cudaFree(h->dResults);
+  if (h->hResults) cudaFreeHost(h->hResults);
+  h->dResults = nullptr;
+  h->hResults = nullptr;
+  CK(cudaMalloc(&h->dResults, sizeof(IterResult) * n));
+  CK(cudaMallocHost(&h->hResults, sizeof(IterResult) * n));
+  h->resultsCap = n;
+  return 0;
+}
+
+// ---- phases (all asynchronous on h->stream) ---------------------------------------------------
+int Exchange(aither_gpu *h, int which) {
+  if (h->halo.nConn == 0) return 0;
+  std::vector<const BlockDev *> devs;
+  for (auto &hb : h->blocks) devs.push_back(&hb.dev);
+  if (HaloExchange(h->halo, devs, which, h->stream, &h->launches)) return Fail(HaloError());
+  return 0;
+}
+
+int PhaseBoundaryConditions(aither_gpu *h) {
+  // ref: src/gridLevel.cpp:287-319
+  for (auto &hb : h->blocks) {
+    if (hb.bcThreads == 0) continue;
+    ScopedLaunch sl(h, kFamBc);
+    const int grid = static_cast<int>((hb.bcThreads + 127) / 128);
+    BcKernel<1, 0><<<grid, 128, 0, h->stream>>>(hb.dev, h->params, hb.dSurfs, hb.nBcSurfs,
+                                               h->dBcStates, hb.bcThreads);
+  }
+  CK(cudaGetLastError());
+  if (Exchange(h, kHaloState)) return 1;
+  return 0;
+}
+
+int PhaseResidual(aither_gpu *h) {
+  for (auto &hb : h->blocks) LaunchResidual<1, 0>(h, hb);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int PhasePrep(aither_gpu *h, double cfl, int bits) {
+  for (auto &hb : h->blocks) {
+    ScopedLaunch sl(h, kFamPrep);
+    PrepKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int SwapUpdate(aither_gpu *h) {
+  // ref: src/linearSolver.cpp:190-193, src/utility.cpp:400-423
+  return Exchange(h, kHaloUpdate);
+}
+
+int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
+  const bool fullGSAlways = h->cfg.matrixRequiresInit != 0;
+  for (int s = 0; s < sweeps; ++s) {
+    if (SwapUpdate(h)) return 1;
+    if (h->cfg.solver == AITHER_SOLVER_DPLUR) {
+      for (auto &hb : h->blocks) {
+        {
+          ScopedLaunch sl(h, kFamDplur);
+          DplurKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+                                                                          hb.dev.x, hb.dev.xalt);
+        }
+        std::swap(hb.dev.x, hb.dev.xalt);
+      }
+    } else {
+      const int fullGS = (s > 0 || fullGSAlways) ? 1 : 0;
+      for (auto &hb : h->blocks) {
+        const BlockDev &b = hb.dev;
+        const dim3 blk(16, 8);
+        const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
+        for (int pl = 0; pl <= b.ni + b.nj + b.nk - 3; ++pl) {
+          ScopedLaunch sl(h, kFamLusgs);
+          LusgsPlaneKernel<1, 0, true><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+        }
+      }
+      if (SwapUpdate(h)) return 1;
+      for (auto &hb : h->blocks) {
+        const BlockDev &b = hb.dev;
+        const dim3 blk(16, 8);
+        const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
+        for (int pl = b.ni + b.nj + b.nk - 3; pl >= 0; --pl) {
+          ScopedLaunch sl(h, kFamLusgs);
+          LusgsPlaneKernel<1, 0, false><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+        }
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  if (SwapUpdate(h)) return 1;
+  // matrix residual and its norm (ref: src/linearSolver.cpp:92-109, src/mgSolution.cpp:198-206)
+  for (auto &hb : h->blocks) {
+    {
+      ScopedLaunch sl(h, kFamAxmb);
+      AxmbKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, h->dPartials,
+                                                                     h->keepMatrixResid ? 1 : 0);
+    }
+    {
+      ScopedLaunch sl(h, kFamReduce);
+      FinalizeSumKernel<<<1, 32, 0, h->stream>>>(h->dPartials, hb.nCellBlocks, 1,
+                                                 &h->dResults[slot].matrixSumSq);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int PhaseUpdate(aither_gpu *h, int slot) {
+  for (auto &hb : h->blocks) {
+    {
+      ScopedLaunch sl(h, kFamUpdate);
+      UpdateKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+                                                                       h->dPartials,
+                                                                       h->dLinfPartials);
+    }
+    {
+      ScopedLaunch sl(h, kFamReduce);
+      FinalizeSumKernel<<<h->neq, 32, 0, h->stream>>>(h->dPartials, hb.nCellBlocks, h->neq,
+                                                      h->dResults[slot].l2);
+    }
+    {
+      ScopedLaunch sl(h, kFamReduce);
+      FinalizeLinfKernel<<<1, 32, 0, h->stream>>>(h->dLinfPartials, hb.nCellBlocks, hb.dev, h->neq,
+                                                  &h->dResults[slot]);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+long long TotalPaddedSize(const aither_gpu *h) {
+  long long t = 0;
+  for (auto &hb : h->blocks) t += hb.paddedCells * h->neq;
+  return t;
+}
+
+int IterateAsync(aither_gpu *h, double cfl, int slot) {
+  if (ZeroResult(h, slot)) return 1;
+  if (PhaseBoundaryConditions(h)) return 1;
+  if (PhaseResidual(h)) return 1;
+  if (PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
+  if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
+  if (PhaseUpdate(h, slot)) return 1;
+  return 0;
+}
+
+int FetchResults(aither_gpu *h, int n) {
+  CK(cudaMemcpyAsync(h->hResults, h->dResults, sizeof(IterResult) * n, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void FreeAll(aither_gpu *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto &hb : h->blocks) {
+    if (hb.alloc) cudaFree(hb.alloc);
+    if (hb.dSurfs) cudaFree(hb.dSurfs);
+    for (auto &p : hb.dConnFace)
+      if (p) cudaFree(p);
+  }
+  HaloDestroy(h->halo);
+  if (h->dBcStates) cudaFree(h->dBcStates);
+  if (h->dPartials) cudaFree(h->dPartials);
+  if (h->dLinfPartials) cudaFree(h->dLinfPartials);
+  if (h->dResults) cudaFree(h->dResults);
+  if (h->hResults) cudaFreeHost(h->hResults);
+  if (h->dStage) cudaFree(h->dStage);
+  if (h->evStart) cudaEventDestroy(h->evStart);
+  if (h->evStop) cudaEventDestroy(h->evStop);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *aither_gpu_last_error(void) { return g_lastError.c_str(); }
+const char *aither_gpu_version(void) { return "aither_b200 0.1 (sm_100a)"; }
+const char *aither_gpu_kernel_family_name(int f) {
+  return (f >= 0 && f < kNumFamilies) ? kFamilyNames[f] : "";
+}
+int aither_gpu_num_kernel_families(void) { return kNumFamilies; }
+
+int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_block_desc *blocks,
+                      int nConnections, const aither_conn *conns, int rank, int nRanks,
+                      void *ncclComm, int device, aither_gpu **out) {
+  if (!cfg || !blocks || !out || nLocalBlocks < 1) return Fail("aither_gpu_create: bad arguments");
+  std::string why;
+  if (!Supported(*cfg, &why)) return Fail("aither_gpu_create: " + why);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return Fail("aither_gpu_create: no CUDA device available (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  aither_gpu *h = new aither_gpu();
+  h->cfg = *cfg;
+  h->device = device;
+  h->rank = rank;
+  h->nRanks = nRanks;
+  h->ns = cfg->numSpecies;
+  h->nt = cfg->numTurb;
+  h->neq = h->ns + 4 + h->nt;
+  h->asz = 1;
+  Params &p = h->params;
+  for (int s = 0; s < AITHER_MAX_SPECIES; ++s) {
+    p.gas.R[s] = cfg->gasConstant[s];
+    p.gas.n[s] = cfg->n[s];
+    p.gas.hf[s] = cfg->hf[s];
+  }
+  p.kappa = cfg->kappa;
+  p.theta = cfg->theta;
+  p.zeta = cfg->zeta;
+  p.relax = cfg->matrixRelaxation;
+  p.dualTimeCFL = cfg->dualTimeCFL;
+  p.dtNondim = cfg->dtNondim;
+  p.isMultilevelTime = cfg->isMultilevelTime;
+  p.matrixRequiresInit = cfg->matrixRequiresInit;
+  p.wenoZ = cfg->recon == AITHER_RECON_WENOZ;
+#define CKH(call)        \
+  do {                   \
+    if ((call)) {        \
+      FreeAll(h);        \
+      return 1;          \
+    }                    \
+  } while (0)
+#define CKC(call)                                                      \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) {                                           \
+      Fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+      FreeAll(h);                                                      \
+      return 1;                                                        \
+    }                                                                  \
+  } while (0)
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&h->evStart));
+  CKC(cudaEventCreate(&h->evStop));
+  CKC(cudaMalloc(&h->dBcStates, sizeof(aither_bc_state) * AITHER_MAX_BC_STATES));
+  CKC(cudaMemcpy(h->dBcStates, cfg->bcStates, sizeof(aither_bc_state) * AITHER_MAX_BC_STATES,
+                 cudaMemcpyHostToDevice));
+  if (nConnections > 0 && conns) h->conns.assign(conns, conns + nConnections);
+
+  const int g = cfg->numGhosts;
+  const int neq = h->neq;
+  size_t maxCellBlocks = 0;
+  h->blocks.resize(nLocalBlocks);
+  for (int bb = 0; bb < nLocalBlocks; ++bb) {
+    HostBlock &hb = h->blocks[bb];
+    const aither_block_desc &d = blocks[bb];
+    if (d.ni < 1 || d.nj < 1 || d.nk < 1) {
+      Fail("aither_gpu_create: empty block");
+      FreeAll(h);
+      return 1;
+    }
+    BlockDev &b = hb.dev;
+    memset(&b, 0, sizeof(b));
+    b.ni = d.ni; b.nj = d.nj; b.nk = d.nk; b.g = g;
+    b.parentBlock = d.parentBlock;
+    hb.globalPos = d.globalPos;
+    b.lp = 16;  // >= g, multiple of 16 doubles: cell i = 0 sits on a 128-byte line
+    b.sj = ((b.lp + d.ni + g + 1 + 15) / 16) * 16;
+    b.sk = static_cast<long long>(b.sj) * (d.nj + 2 * g + 1);
+    b.fs = ((b.sk * (d.nk + 2 * g + 1) + 15) / 16) * 16;
+    hb.paddedCells = static_cast<long long>(d.ni + 2 * g) * (d.nj + 2 * g) * (d.nk + 2 * g);
+    // field budget (doubles per cell): state, consN, [consNm1], resid, rhs, x, xalt, [mres],
+    // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
+    const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 12 + 3;
+    hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
+    CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
+    CKC(cudaMemsetAsync(hb.alloc, 0, hb.allocBytes, h->stream));
+    double *cur = static_cast<double *>(hb.alloc);
+    auto take = [&](int n) { double *r = cur; cur += static_cast<size_t>(n) * b.fs; return r; };
+    b.state = take(neq);
+    b.consN = take(neq);
+    b.consNm1 = cfg->isMultilevelTime ? take(neq) : nullptr;
+    b.resid = take(neq);
+    b.rhs = take(neq);
+    b.x = take(neq);
+    b.xalt = take(neq);
+    b.mres = take(neq);
+    b.specRad = take(2);
+    b.dt = take(1);
+    b.diag = take(1);
+    b.dinv = take(1);
+    b.vol = take(1);
+    for (int q = 0; q < 3; ++q) b.cw[q] = take(1);
+    for (int q = 0; q < 3; ++q) b.fA[q] = take(4);
+    b.center = take(3);
+
+    const int NI = d.ni + 2 * g, NJ = d.nj + 2 * g, NK = d.nk + 2 * g;
+    if (!d.state || !d.vol || !d.fAreaI || !d.fAreaJ || !d.fAreaK || !d.cellWidthI ||
+        !d.cellWidthJ || !d.cellWidthK) {
+      Fail("aither_gpu_create: block is missing a required array");
+      FreeAll(h);
+      return 1;
+    }
+    CKH(UploadAos(h, hb, d.state, NI, NJ, NK, neq, b.state, -g, -g, -g));
+    CKH(UploadAos(h, hb, d.vol, NI, NJ, NK, 1, b.vol, -g, -g, -g));
+    CKH(UploadAos(h, hb, d.fAreaI, NI + 1, NJ, NK, 4, b.fA[0], -g, -g, -g));
+    CKH(UploadAos(h, hb, d.fAreaJ, NI, NJ + 1, NK, 4, b.fA[1], -g, -g, -g));
+    CKH(UploadAos(h, hb, d.fAreaK, NI, NJ, NK + 1, 4, b.fA[2], -g, -g, -g));
+    CKH(UploadAos(h, hb, d.cellWidthI, NI, NJ, NK, 1, b.cw[0], -g, -g, -g));
+    CKH(UploadAos(h, hb, d.cellWidthJ, NI, NJ, NK, 1, b.cw[1], -g, -g, -g));
+    CKH(UploadAos(h, hb, d.cellWidthK, NI, NJ, NK, 1, b.cw[2], -g, -g, -g));
+    if (d.center) CKH(UploadAos(h, hb, d.center, NI, NJ, NK, 3, b.center, -g, -g, -g));
+
+    // boundary surfaces
+    hb.surfaces.assign(d.surfaces, d.surfaces + d.numSurfaces);
+    std::vector<SurfDev> sd;
+    long long off = 0;
+    const int nd[3] = {d.ni, d.nj, d.nk};
+    std::vector<std::vector<uint8_t>> connMask(6);
+    for (int s = 0; s < 6; ++s) {
+      const int d3 = s / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+      connMask[s].assign(static_cast<size_t>(nd[d1]) * nd[d2], 0);
+    }
+    bool anyConn = false;
+    for (const auto &sf : hb.surfaces) {
+      const int st = SurfaceType(sf);
+      const int d3 = (st - 1) / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+      int lo[3] = {sf.imin, sf.jmin, sf.kmin}, hi[3] = {sf.imax, sf.jmax, sf.kmax};
+      if (sf.type == AITHER_BC_INTERBLOCK || sf.type == AITHER_BC_PERIODIC) {
+        anyConn = true;
+        for (int c2 = lo[d2]; c2 < hi[d2]; ++c2)
+          for (int c1 = lo[d1]; c1 < hi[d1]; ++c1)
+            connMask[st - 1][c1 + static_cast<size_t>(nd[d1]) * c2] = 1;
+        continue;
+      }
+      SurfDev v;
+      v.type = sf.type;
+      v.surfType = st;
+      v.tag = sf.tag;
+      v.bcIndex = 0;
+      const bool needsData = sf.type == AITHER_BC_CHARACTERISTIC || sf.type == AITHER_BC_INLET ||
+                             sf.type == AITHER_BC_SUPERSONIC_INFLOW ||
+                             sf.type == AITHER_BC_STAGNATION_INLET ||
+                             sf.type == AITHER_BC_PRESSURE_OUTLET;
+      bool found = false;
+      for (int q = 0; q < cfg->numBCStates; ++q)
+        if (cfg->bcStates[q].tag == sf.tag) { v.bcIndex = q; found = true; break; }
+      if (needsData && !found) {
+        Fail("aither_gpu_create: boundary surface references tag " + std::to_string(sf.tag) +
+             " with no boundary state");
+        FreeAll(h);
+        return 1;
+      }
+      if (sf.type != AITHER_BC_SLIP_WALL && sf.type != AITHER_BC_VISCOUS_WALL && !needsData &&
+          sf.type != AITHER_BC_SUPERSONIC_OUTFLOW) {
+        Fail("aither_gpu_create: unsupported boundary condition type " + std::to_string(sf.type));
+        FreeAll(h);
+        return 1;
+      }
+      for (int q = 0; q < 3; ++q) { v.lo[q] = lo[q]; v.hi[q] = hi[q]; }
+      v.hi[d3] = v.lo[d3] + 1;
+      v.faceOffset = off;
+      off += static_cast<long long>(hi[d1] - lo[d1]) * (hi[d2] - lo[d2]) * g;
+      sd.push_back(v);
+    }
+    hb.nBcSurfs = static_cast<int>(sd.size());
+    hb.bcThreads = off;
+    if (!sd.empty()) {
+      CKC(cudaMalloc(&hb.dSurfs, sizeof(SurfDev) * sd.size()));
+      CKC(cudaMemcpy(hb.dSurfs, sd.data(), sizeof(SurfDev) * sd.size(), cudaMemcpyHostToDevice));
+    }
+    if (anyConn) {
+      for (int s = 0; s < 6; ++s) {
+        CKC(cudaMalloc(&hb.dConnFace[s], connMask[s].size()));
+        CKC(cudaMemcpy(hb.dConnFace[s], connMask[s].data(), connMask[s].size(),
+                       cudaMemcpyHostToDevice));
+        b.connFace[s] = hb.dConnFace[s];
+      }
+    }
+    hb.cellBlock = dim3(32, 8, 1);
+    hb.cellGrid = dim3((d.ni + 31) / 32, (d.nj + 7) / 8, d.nk);
+    hb.nCellBlocks = hb.cellGrid.x * hb.cellGrid.y * hb.cellGrid.z;
+    hb.resBlock = dim3(kTI, kTJ, kTK);
+    hb.resGrid = dim3((d.ni + 1 + kTI - 1) / kTI, (d.nj + 1 + kTJ - 1) / kTJ,
+                      (d.nk + 1 + kTK - 1) / kTK);
+    maxCellBlocks = std::max<size_t>(maxCellBlocks, hb.nCellBlocks);
+  }
+  h->partialsCap = maxCellBlocks;
+  CKC(cudaMalloc(&h->dPartials, sizeof(double) * maxCellBlocks * (AITHER_MAX_SPECIES + 6)));
+  CKC(cudaMalloc(&h->dLinfPartials, sizeof(LinfCand) * maxCellBlocks));
+  CKH(EnsureResults(h, 64));
+  // halo plan for the connections this rank takes part in
+  {
+    std::vector<const BlockDev *> devs;
+    std::vector<int> gpos;
+    for (auto &hb : h->blocks) { devs.push_back(&hb.dev); gpos.push_back(hb.globalPos); }
+    if (HaloBuild(h->halo, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm)) {
+      Fail(HaloError());
+      FreeAll(h);
+      return 1;
+    }
+  }
+  CKC(cudaStreamSynchronize(h->stream));
+#undef CKH
+#undef CKC
+  *out = h;
+  return 0;
+}
+
+int aither_gpu_destroy(aither_gpu *h) {
+  if (h) DrainProfile(h);
+  FreeAll(h);
+  return 0;
+}
+
+int aither_gpu_store_old_solution(aither_gpu *h, int iter) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  const int copyNm1 = (h->cfg.isMultilevelTime && iter == 0) ? 1 : 0;
+  for (auto &hb : h->blocks) {
+    ScopedLaunch sl(h, kFamStore);
+    StoreOldKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, copyNm1);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int aither_gpu_iterate(aither_gpu *h, double cfl, int mm, double *residL2, aither_linf *linf,
+                       double *matrixResid) {
+  (void)mm;
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (IterateAsync(h, cfl, 0)) return 1;
+  if (FetchResults(h, 1)) return 1;
+  const IterResult &r = h->hResults[0];
+  if (residL2)
+    for (int e = 0; e < h->neq; ++e) residL2[e] += r.l2[e];
+  if (linf && r.linf > linf->linf) {
+    linf->linf = r.linf;
+    linf->block = r.linfBlock;
+    linf->i = r.linfI;
+    linf->j = r.linfJ;
+    linf->k = r.linfK;
+    linf->eqn = r.linfEqn;
+  }
+  if (matrixResid) *matrixResid = r.matrixSumSq / static_cast<double>(TotalPaddedSize(h));
+  return 0;
+}
+
+int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep, double cflMax,
+                   double *hist) {
+  if (!h) return Fail("null handle");
+  if (nIter < 1) return 0;
+  CK(cudaSetDevice(h->device));
+  if (EnsureResults(h, nIter)) return 1;
+  for (int n = 0; n < nIter; ++n) {
+    const double cfl = std::min(cflStart + n * cflStep, cflMax);  // ref: src/input.cpp:647
+    if (aither_gpu_store_old_solution(h, n)) return 1;
+    if (IterateAsync(h, cfl, n)) return 1;
+  }
+  if (FetchResults(h, nIter)) return 1;
+  if (hist) {
+    const double tot = static_cast<double>(TotalPaddedSize(h));
+    for (int n = 0; n < nIter; ++n) {
+      for (int e = 0; e < h->neq; ++e) hist[n * (h->neq + 1) + e] = h->hResults[n].l2[e];
+      hist[n * (h->neq + 1) + h->neq] = h->hResults[n].matrixSumSq / tot;
+    }
+  }
+  return 0;
+}
+
+int aither_gpu_get_boundary_conditions(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (PhaseBoundaryConditions(h)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_calc_residual(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (PhaseResidual(h)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_calc_time_step(aither_gpu *h, double cfl) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (PhasePrep(h, cfl, kPrepDt)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_invert_diagonal(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (PhasePrep(h, 0.0, kPrepDiag)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_initialize_matrix_update(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (PhasePrep(h, 0.0, kPrepInit)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_relax(aither_gpu *h, int sweeps, double *matrixResid) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  h->keepMatrixResid = true;
+  if (ZeroResult(h, 0)) return 1;
+  if (PhaseRelax(h, sweeps, 0)) return 1;
+  if (FetchResults(h, 1)) return 1;
+  h->keepMatrixResid = false;
+  if (matrixResid) *matrixResid = h->hResults[0].matrixSumSq / static_cast<double>(TotalPaddedSize(h));
+  return 0;
+}
+int aither_gpu_update_blocks(aither_gpu *h, int mm, double *residL2, aither_linf *linf) {
+  (void)mm;
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (ZeroResult(h, 0)) return 1;
+  if (PhaseUpdate(h, 0)) return 1;
+  if (FetchResults(h, 1)) return 1;
+  const IterResult &r = h->hResults[0];
+  if (residL2)
+    for (int e = 0; e < h->neq; ++e) residL2[e] += r.l2[e];
+  if (linf && r.linf > linf->linf) {
+    linf->linf = r.linf;
+    linf->block = r.linfBlock;
+    linf->i = r.linfI;
+    linf->j = r.linfJ;
+    linf->k = r.linfK;
+    linf->eqn = r.linfEqn;
+  }
+  return 0;
+}
+int aither_gpu_reset_diagonal(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  for (auto &hb : h->blocks) {
+    CK(cudaMemsetAsync(hb.dev.diag, 0, sizeof(double) * hb.dev.fs, h->stream));
+  }
+  return 0;
+}
+
+static int FieldInfo(aither_gpu *h, int blk, int field, const double **ptr, int *nc, bool *padded) {
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  const BlockDev &b = h->blocks[blk].dev;
+  switch (field) {
+    case AITHER_FIELD_STATE: *ptr = b.state; *nc = h->neq; *padded = true; break;
+    case AITHER_FIELD_RESIDUAL: *ptr = b.resid; *nc = h->neq; *padded = false; break;
+    case AITHER_FIELD_SPEC_RADIUS: *ptr = b.specRad; *nc = 2; *padded = false; break;
+    case AITHER_FIELD_DT: *ptr = b.dt; *nc = 1; *padded = false; break;
+    case AITHER_FIELD_DIAG: *ptr = b.diag; *nc = h->asz; *padded = false; break;
+    case AITHER_FIELD_DIAG_INV: *ptr = b.dinv; *nc = h->asz; *padded = false; break;
+    case AITHER_FIELD_UPDATE: *ptr = b.x; *nc = h->neq; *padded = true; break;
+    case AITHER_FIELD_CONS_N: *ptr = b.consN; *nc = h->neq; *padded = false; break;
+    case AITHER_FIELD_MATRIX_RESID: *ptr = b.mres; *nc = h->neq; *padded = false; break;
+    case AITHER_FIELD_CONS_NM1:
+      if (!b.consNm1) return Fail("consNm1 is only stored for bdf2");
+      *ptr = b.consNm1; *nc = h->neq; *padded = false; break;
+    default: return Fail("unknown or unavailable field id " + std::to_string(field));
+  }
+  return 0;
+}
+
+long long aither_gpu_field_size(aither_gpu *h, int blk, int field) {
+  if (!h) return -1;
+  const double *ptr; int nc; bool padded;
+  if (FieldInfo(h, blk, field, &ptr, &nc, &padded)) return -1;
+  const BlockDev &b = h->blocks[blk].dev;
+  const int g = padded ? b.g : 0;
+  return static_cast<long long>(b.ni + 2 * g) * (b.nj + 2 * g) * (b.nk + 2 * g) * nc;
+}
+
+int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst) {
+  if (!h || !dst) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  const double *ptr; int nc; bool padded;
+  if (FieldInfo(h, blk, field, &ptr, &nc, &padded)) return 1;
+  const HostBlock &hb = h->blocks[blk];
+  const BlockDev &b = hb.dev;
+  const int g = padded ? b.g : 0;
+  return DownloadAos(h, hb, dst, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, nc, ptr, -g, -g, -g);
+}
+int aither_gpu_download_state(aither_gpu *h, int blk, double *stateAoS) {
+  return aither_gpu_download_field(h, blk, AITHER_FIELD_STATE, stateAoS);
+}
+int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
+  if (!h || !stateAoS) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  const HostBlock &hb = h->blocks[blk];
+  const BlockDev &b = hb.dev;
+  const int g = b.g;
+  return UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g,
+                   -g, -g);
+}
+
+int aither_gpu_synchronize(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_timer_start(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->evStart, h->stream));
+  return 0;
+}
+int aither_gpu_timer_stop(aither_gpu *h, float *ms) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->evStop, h->stream));
+  CK(cudaEventSynchronize(h->evStop));
+  if (ms) CK(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+  return 0;
+}
+long long aither_gpu_launch_count(aither_gpu *h) { return h ? h->launches : -1; }
+int aither_gpu_profile_enable(aither_gpu *h, int enable) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  DrainProfile(h);
+  h->profile = enable != 0;
+  for (int f = 0; f < kNumFamilies; ++f) {
+    h->famMs[f] = 0.0;
+    h->famLaunches[f] = 0;
+  }
+  return 0;
+}
+int aither_gpu_profile_get(aither_gpu *h, int family, double *ms, long long *launches) {
+  if (!h) return Fail("null handle");
+  if (family < 0 || family >= kNumFamilies) return Fail("bad family");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  DrainProfile(h);
+  if (ms) *ms = h->famMs[family];
+  if (launches) *launches = h->famLaunches[family];
+  return 0;
+}
+
+}  // extern "C"

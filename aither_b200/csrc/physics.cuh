@@ -1,0 +1,730 @@
+// physics.cuh -- point-wise numerics of the hot path, as inlineable device functions.
+//
+// Everything here works on one cell / one face held in registers: thermodynamics, MUSCL / WENO
+// reconstruction, Roe and AUSMPW+ fluxes, spectral radii, the Rusanov off-diagonal product and the
+// boundary-condition ghost states. Formulas follow mnucci32/aither v0.10.0 (cited per function as
+// "ref: file:line"); the structure does not: no heap vectors, no virtual dispatch, no string
+// compares -- species / turbulence counts are template parameters so every loop unrolls and every
+// state lives in registers.
+//
+// AITHER_HD lets tests/hostsim compile these same functions with g++ to check them point-wise
+// against the oracle without a GPU; the shipped library only ever runs them inside kernels.
+#pragma once
+#include <math.h>
+
+#include "../../include/aither_gpu.h"
+
+#ifdef __CUDACC__
+#define AITHER_HD __host__ __device__ __forceinline__
+#else
+#define AITHER_HD inline
+#endif
+
+namespace aither {
+
+constexpr double kEps = 1.0e-30;        // ref: include/macros.hpp.in:21
+constexpr double kEntropyFix = 0.1;     // ref: include/inviscidFlux.hpp:298
+constexpr double kTurbMin = 1.0e-20;    // ref: include/turbulence.hpp:72-73
+
+// Gas model constants for <= AITHER_MAX_SPECIES calorically perfect species (nondimensional).
+struct Gas {
+  double R[AITHER_MAX_SPECIES];
+  double n[AITHER_MAX_SPECIES];
+  double hf[AITHER_MAX_SPECIES];
+};
+
+// Equation layout for NS species and NT turbulence equations
+// (ref: include/varArray.hpp:47-51): [rho_1..rho_NS, u, v, w, p, (k, omega)].
+template <int NS, int NT>
+struct Eq {
+  static constexpr int ns = NS, nt = NT, neq = NS + 4 + NT;
+  static constexpr int imx = NS, imy = NS + 1, imz = NS + 2, ie = NS + 3, it = NS + 4;
+};
+
+template <int NS>
+AITHER_HD double SpeciesSum(const double *s) {
+  double r = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) r += s[q];
+  return r;
+}
+
+// T = p / sum(rho_s R_s); ref: src/eos.cpp:100-109
+template <int NS>
+AITHER_HD double Temperature(const Gas &g, const double *s) {
+  double rhoR = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) rhoR += s[q] * g.R[q];
+  return s[NS + 3] / rhoR;
+}
+
+// mixture thermodynamic sums; ref: src/thermodynamic.cpp:62-104, include/thermodynamic.hpp:102-119
+template <int NS>
+struct Mix {
+  double cp, cv, hfm, rho;
+};
+template <int NS>
+AITHER_HD Mix<NS> Mixture(const Gas &g, const double *s) {
+  Mix<NS> m;
+  m.rho = SpeciesSum<NS>(s);
+  m.cp = 0.0;
+  m.cv = 0.0;
+  m.hfm = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    const double mf = s[q] / m.rho;
+    m.cp += mf * (g.R[q] * (g.n[q] + 1.0));
+    m.cv += mf * (g.R[q] * g.n[q]);
+    m.hfm += mf * g.hf[q];
+  }
+  return m;
+}
+
+template <int NS>
+AITHER_HD double Gamma(const Gas &g, const double *s) {
+  const Mix<NS> m = Mixture<NS>(g, s);
+  return m.cp / m.cv;
+}
+
+// a = sqrt(gamma p / rho); ref: include/arrayView.hpp:384-391
+template <int NS>
+AITHER_HD double SoS(const Gas &g, const double *s) {
+  const Mix<NS> m = Mixture<NS>(g, s);
+  return sqrt(m.cp / m.cv * s[NS + 3] / m.rho);
+}
+
+template <int NS>
+AITHER_HD double VelMagSq(const double *s) {
+  return s[NS] * s[NS] + s[NS + 1] * s[NS + 1] + s[NS + 2] * s[NS + 2];
+}
+
+// H = sum Y_s (hf_s + cp_s T) + |v|^2 / 2; ref: include/arrayView.hpp:400-408, src/eos.cpp:83-88.
+// The reference forms sum_s Y_s (hf_s + cp_s T); for one species that is hf + cp T exactly, for
+// several it differs from hfm + cp T only in rounding.
+template <int NS>
+AITHER_HD double Enthalpy(const Gas &g, const double *s) {
+  const double rho = SpeciesSum<NS>(s);
+  const double t = Temperature<NS>(g, s);
+  double h = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) h += s[q] / rho * (g.hf[q] + (g.R[q] * (g.n[q] + 1.0)) * t);
+  const double vel = sqrt(VelMagSq<NS>(s));
+  return h + 0.5 * vel * vel;
+}
+
+// E = sum Y_s (hf_s + cv_s T) + |v|^2 / 2; ref: include/arrayView.hpp:432-441
+template <int NS>
+AITHER_HD double Energy(const Gas &g, const double *s) {
+  const double rho = SpeciesSum<NS>(s);
+  const double t = Temperature<NS>(g, s);
+  double e = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) e += s[q] / rho * (g.hf[q] + (g.R[q] * g.n[q]) * t);
+  const double vel = sqrt(VelMagSq<NS>(s));
+  return e + 0.5 * vel * vel;
+}
+
+// primitive -> conserved; ref: include/primitive.hpp:181-199
+template <int NS, int NT>
+AITHER_HD void PrimToCons(const Gas &g, const double *s, double *c) {
+  using E = Eq<NS, NT>;
+  const double rho = SpeciesSum<NS>(s);
+#pragma unroll
+  for (int q = 0; q < NS; ++q) c[q] = s[q];
+  c[E::imx] = rho * s[E::imx];
+  c[E::imy] = rho * s[E::imy];
+  c[E::imz] = rho * s[E::imz];
+  c[E::ie] = rho * Energy<NS>(g, s);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) c[E::it + t] = rho * s[E::it + t];
+}
+
+// conserved -> primitive; ref: include/primitive.hpp:150-177, src/eos.cpp:40-63,
+// src/thermodynamic.cpp:107-113, src/primitive.cpp:100-106 (turbulence floor)
+template <int NS, int NT>
+AITHER_HD void ConsToPrim(const Gas &g, const double *c, double *s) {
+  using E = Eq<NS, NT>;
+  const double rho = SpeciesSum<NS>(c);
+#pragma unroll
+  for (int q = 0; q < NS; ++q) s[q] = c[q];
+  s[E::imx] = c[E::imx] / rho;
+  s[E::imy] = c[E::imy] / rho;
+  s[E::imz] = c[E::imz] / rho;
+  const double energy = c[E::ie] / rho;
+  const double vel = sqrt(VelMagSq<NS>(s));
+  const double specEnergy = energy - 0.5 * vel * vel;
+  double hfm = 0.0, cv = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    const double mf = s[q] / rho;
+    hfm += g.hf[q] * mf;
+    cv += mf * (g.R[q] * g.n[q]);
+  }
+  const double temperature = (specEnergy - hfm) / cv;
+  double p = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) p += s[q] * g.R[q] * temperature;
+  s[E::ie] = p;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) s[E::it + t] = fmax(c[E::it + t] / rho, kTurbMin);
+}
+
+// state + conserved update -> new primitive state, with the reference's mass-fraction clip and
+// renormalisation; ref: include/primitive.hpp:206-231
+template <int NS, int NT>
+AITHER_HD void UpdatePrimWithCons(const Gas &g, const double *s, const double *du, double *out) {
+  using E = Eq<NS, NT>;
+  double c[E::neq];
+  PrimToCons<NS, NT>(g, s, c);
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) c[e] += du[e];
+  const double rho = SpeciesSum<NS>(c);
+  double mf[NS];
+  double total = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    mf[q] = fmax(c[q] / rho, 0.0);
+    total += mf[q];
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) c[q] = rho * (mf[q] / total);
+  ConsToPrim<NS, NT>(g, c, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reconstruction
+template <int LIM>
+AITHER_HD double Limiter(double r) {
+  if (LIM == AITHER_LIMITER_VAN_ALBADA) {  // ref: src/limiter.cpp:37-46
+    const double r2 = r * r;
+    return fmax(0.0, (r + r2) / (1.0 + r2));
+  } else if (LIM == AITHER_LIMITER_MINMOD) {  // ref: src/limiter.cpp:24-34
+    return fmax(0.0, fmin(1.0, r));
+  }
+  return 1.0;
+}
+
+// kappa-scheme MUSCL on a non-uniform grid, one component;
+// ref: include/reconstruction.hpp:110-154 (FaceReconMUSCL)
+template <int LIM>
+AITHER_HD double Muscl1(double u2, double u1, double d1, double kappa, double dPlus,
+                        double dMinus) {
+  const double dm = (u1 - u2) * dMinus;
+  const double r = (kEps + (d1 - u1) * dPlus) / (kEps + dm);
+  double lim = 1.0, invLim = 1.0;
+  if (LIM != AITHER_LIMITER_NONE) {
+    lim = Limiter<LIM>(r);
+    invLim = Limiter<LIM>(1.0 / r);
+  }
+  return u1 + 0.25 * dm * ((1.0 - kappa) * lim + (1.0 + kappa) * r * invLim);
+}
+
+template <int NEQ, int LIM>
+AITHER_HD void Muscl(const double *u2, const double *u1, const double *d1, double kappa,
+                     double w2, double w1, double wd, double *face) {
+  const double dPlus = (w1 + w1) / (w1 + wd);
+  const double dMinus = (w1 + w1) / (w1 + w2);
+#pragma unroll
+  for (int e = 0; e < NEQ; ++e) face[e] = Muscl1<LIM>(u2[e], u1[e], d1[e], kappa, dPlus, dMinus);
+}
+
+// ref: include/utility.hpp:103-114 (StencilWidth)
+AITHER_HD double StencilWidth(const double *w, int start, int end) {
+  double width = 0.0;
+  if (end > start) {
+    for (int q = start; q < end; ++q) width += w[q];
+  } else if (start > end) {
+    for (int q = end; q < start; ++q) width += w[q];
+    width = -1.0 * width;
+  }
+  return width;
+}
+
+// Lagrange reconstruction coefficients on a non-uniform stencil;
+// ref: src/utility.cpp:449-483 (LagrangeCoeff; Shu ICASE 97-65 eq. 2.20)
+template <int DEGREE>
+AITHER_HD void LagrangeCoeff(const double *w, int rr, int ii, double *coeffs) {
+#pragma unroll
+  for (int jj = 0; jj <= DEGREE; ++jj) {
+    double cj = 0.0;
+#pragma unroll
+    for (int mm = jj + 1; mm <= DEGREE + 1; ++mm) {
+      double numer = 0.0, denom = 1.0;
+#pragma unroll
+      for (int ll = 0; ll <= DEGREE + 1; ++ll) {
+        if (ll != mm) {
+          double numProd = 1.0;
+#pragma unroll
+          for (int qq = 0; qq <= DEGREE + 1; ++qq) {
+            if (qq != mm && qq != ll) numProd *= StencilWidth(w, ii - rr + qq, ii + 1);
+          }
+          numer += numProd;
+          denom *= StencilWidth(w, ii - rr + ll, ii - rr + mm);
+        }
+      }
+      cj += numer / denom;
+    }
+    coeffs[jj] = cj * w[ii - rr + jj];
+  }
+}
+
+AITHER_HD double Deriv2nd(double x0, double x1, double x2, double y0, double y1, double y2) {
+  // ref: include/utility.hpp:116-122
+  const double fwd = (y2 - y1) / (0.5 * (x2 + x1));
+  const double bck = (y1 - y0) / (0.5 * (x1 + x0));
+  return (fwd - bck) / (0.25 * (x2 + x0) + 0.5 * x1);
+}
+AITHER_HD double BetaIntegral1(double d1, double d2, double dx, double x) {
+  // ref: include/reconstruction.hpp:157-170
+  return ((d1 * d1) * x + d1 * d2 * x * x + (d2 * d2) * (x * x * x) / 3.0) * dx +
+         (d2 * d2) * x * (dx * dx * dx);
+}
+AITHER_HD double BetaIntegral(double d1, double d2, double dx, double xl, double xh) {
+  return BetaIntegral1(d1, d2, dx, xh) - BetaIntegral1(d1, d2, dx, xl);
+}
+
+// WENO5 / WENO-Z weights that depend only on the five cell widths.
+struct WenoGeom {
+  double c0[3], c1[3], c2[3];
+  double lw0, lw1, lw2;
+  double w[5];
+};
+AITHER_HD WenoGeom WenoSetup(const double *w) {
+  // ref: include/reconstruction.hpp:256-282
+  WenoGeom g;
+  double fc[5];
+  LagrangeCoeff<2>(w, 2, 2, g.c0);
+  LagrangeCoeff<2>(w, 1, 2, g.c1);
+  LagrangeCoeff<2>(w, 0, 2, g.c2);
+  LagrangeCoeff<4>(w, 2, 2, fc);
+  g.lw0 = fc[0] / g.c0[0];
+  g.lw1 = fc[4] / g.c2[2];
+  g.lw2 = 1.0 - g.lw0 - g.lw1;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) g.w[q] = w[q];
+  return g;
+}
+// one component; y = {upwind3, upwind2, upwind1, downwind1, downwind2};
+// ref: include/reconstruction.hpp:185-240 (Beta0/1/2), :284-310
+template <bool WENOZ>
+AITHER_HD double Weno1(const WenoGeom &g, double y0, double y1, double y2, double y3, double y4) {
+  const double *w = g.w;
+  const double st0 = g.c0[0] * y0 + g.c0[1] * y1 + g.c0[2] * y2;
+  const double st1 = g.c1[0] * y1 + g.c1[1] * y2 + g.c1[2] * y3;
+  const double st2 = g.c2[0] * y2 + g.c2[1] * y3 + g.c2[2] * y4;
+  double d2 = Deriv2nd(w[0], w[1], w[2], y0, y1, y2);
+  double d1 = (y2 - y1) / (0.5 * (w[2] + w[1])) + 0.5 * w[2] * d2;
+  const double b0 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+  d2 = Deriv2nd(w[1], w[2], w[3], y1, y2, y3);
+  d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
+  const double b1 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+  d2 = Deriv2nd(w[2], w[3], w[4], y2, y3, y4);
+  d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
+  const double b2 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+  double n0, n1, n2;
+  if (WENOZ) {
+    const double tau5 = fabs(b0 - b2);
+    const double eps = 1.0e-40;
+    double t = tau5 / (eps + b0);
+    n0 = g.lw0 * (1.0 + t * t);
+    t = tau5 / (eps + b1);
+    n1 = g.lw1 * (1.0 + t * t);
+    t = tau5 / (eps + b2);
+    n2 = g.lw2 * (1.0 + t * t);
+  } else {
+    const double eps = 1.0e-6;
+    n0 = g.lw0 / ((eps + b0) * (eps + b0));
+    n1 = g.lw1 / ((eps + b1) * (eps + b1));
+    n2 = g.lw2 / ((eps + b2) * (eps + b2));
+  }
+  const double sum = n0 + n1 + n2;
+  n0 /= sum;
+  n1 /= sum;
+  n2 /= sum;
+  return n0 * st0 + n1 * st1 + n2 * st2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inviscid fluxes (unit normal n)
+// ref: include/inviscidFlux.hpp:128-159 (ConstructFromPrim)
+template <int NS, int NT>
+AITHER_HD void PhysicalFlux(const Gas &g, const double *s, const double *n, double *f) {
+  using E = Eq<NS, NT>;
+  const double velNorm = s[E::imx] * n[0] + s[E::imy] * n[1] + s[E::imz] * n[2];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) f[q] = s[q] * velNorm;
+  const double rho = SpeciesSum<NS>(s);
+  const double p = s[E::ie];
+  f[E::imx] = rho * velNorm * s[E::imx] + p * n[0];
+  f[E::imy] = rho * velNorm * s[E::imy] + p * n[1];
+  f[E::imz] = rho * velNorm * s[E::imz] + p * n[2];
+  f[E::ie] = rho * velNorm * Enthalpy<NS>(g, s);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) f[E::it + t] = rho * velNorm * s[E::it + t];
+}
+
+// Roe flux-difference splitting with Harten's entropy fix;
+// ref: include/inviscidFlux.hpp:260-382 (RoeFlux), include/primitive.hpp:245-280 (Roe average:
+// density-weighted primitive state including *pressure*), src/inviscidFlux.cpp:27-33
+template <int NS, int NT>
+AITHER_HD void RoeFlux(const Gas &g, const double *l, const double *r, const double *n,
+                       double *flux) {
+  using E = Eq<NS, NT>;
+  double roe[E::neq];
+  const double denRatio = sqrt(SpeciesSum<NS>(r) / SpeciesSum<NS>(l));
+#pragma unroll
+  for (int q = 0; q < NS; ++q) roe[q] = l[q] * denRatio;
+#pragma unroll
+  for (int e = NS; e < E::neq; ++e) roe[e] = (l[e] + denRatio * r[e]) / (1.0 + denRatio);
+
+  const double hR = Enthalpy<NS>(g, roe);
+  const double aR = SoS<NS>(g, roe);
+  const double rhoR = SpeciesSum<NS>(roe);
+  const double velNormR = roe[E::imx] * n[0] + roe[E::imy] * n[1] + roe[E::imz] * n[2];
+  double delta[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) delta[e] = r[e] - l[e];
+  const double deltaRho = SpeciesSum<NS>(delta);
+  const double normVelDiff = delta[E::imx] * n[0] + delta[E::imy] * n[1] + delta[E::imz] * n[2];
+  const double dP = delta[E::ie];
+
+  double diss[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) diss[e] = 0.0;
+
+  // left-moving acoustic wave
+  double waveSpeed = fabs(velNormR - aR);
+  if (waveSpeed < kEntropyFix) waveSpeed = 0.5 * (waveSpeed * waveSpeed / kEntropyFix + kEntropyFix);
+  double waveStrength = (dP - rhoR * aR * normVelDiff) / (2.0 * aR * aR);
+  double wss = waveSpeed * waveStrength;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) diss[q] += wss * (roe[q] / rhoR);
+  diss[E::imx] += wss * (roe[E::imx] - aR * n[0]);
+  diss[E::imy] += wss * (roe[E::imy] - aR * n[1]);
+  diss[E::imz] += wss * (roe[E::imz] - aR * n[2]);
+  diss[E::ie] += wss * (hR - aR * velNormR);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) diss[E::it + t] += wss * roe[E::it + t];
+
+  // entropy wave
+  waveSpeed = fabs(velNormR);
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    waveStrength = -dP / (aR * aR);
+    wss = waveSpeed * waveStrength;
+    diss[q] += wss * (roe[q] / rhoR) + waveSpeed * delta[q];
+  }
+  waveStrength = deltaRho - dP / (aR * aR);
+  wss = waveSpeed * waveStrength;
+  diss[E::imx] += wss * roe[E::imx];
+  diss[E::imy] += wss * roe[E::imy];
+  diss[E::imz] += wss * roe[E::imz];
+  diss[E::ie] += wss * 0.5 * VelMagSq<NS>(roe);
+
+  // shear wave
+  wss = waveSpeed * rhoR;
+  diss[E::imx] += wss * (delta[E::imx] - normVelDiff * n[0]);
+  diss[E::imy] += wss * (delta[E::imy] - normVelDiff * n[1]);
+  diss[E::imz] += wss * (delta[E::imz] - normVelDiff * n[2]);
+  diss[E::ie] += wss * ((roe[E::imx] * delta[E::imx] + roe[E::imy] * delta[E::imy] +
+                         roe[E::imz] * delta[E::imz]) -
+                        velNormR * normVelDiff);
+
+  // right-moving acoustic wave
+  waveSpeed = fabs(velNormR + aR);
+  if (waveSpeed < kEntropyFix) waveSpeed = 0.5 * (waveSpeed * waveSpeed / kEntropyFix + kEntropyFix);
+  waveStrength = (dP + rhoR * aR * normVelDiff) / (2.0 * aR * aR);
+  wss = waveSpeed * waveStrength;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) diss[q] += wss * (roe[q] / rhoR);
+  diss[E::imx] += wss * (roe[E::imx] + aR * n[0]);
+  diss[E::imy] += wss * (roe[E::imy] + aR * n[1]);
+  diss[E::imz] += wss * (roe[E::imz] + aR * n[2]);
+  diss[E::ie] += wss * (hR + aR * velNormR);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) diss[E::it + t] += wss * roe[E::it + t];
+
+  // turbulence waves
+  if (NT > 0) {
+    waveSpeed = fabs(velNormR);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      waveStrength = rhoR * delta[E::it + t] + roe[E::it + t] * deltaRho -
+                     dP * roe[E::it + t] / (aR * aR);
+      diss[E::it + t] += waveSpeed * waveStrength * 1.0;
+    }
+  }
+
+  double fl[E::neq], fr[E::neq];
+  PhysicalFlux<NS, NT>(g, l, n, fl);
+  PhysicalFlux<NS, NT>(g, r, n, fr);
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) flux[e] = (fl[e] + (fr[e] - diss[e])) * 0.5;
+}
+
+AITHER_HD double Sign(double v) { return static_cast<double>((0.0 < v) - (v < 0.0)); }
+
+// AUSMPW+ (Kim, Kim & Rho 1998); ref: include/inviscidFlux.hpp:396-481, :161-208
+template <int NS, int NT>
+AITHER_HD void AusmFlux(const Gas &g, const double *l, const double *r, const double *n,
+                        double *f) {
+  using E = Eq<NS, NT>;
+  const double velNormL = l[E::imx] * n[0] + l[E::imy] * n[1] + l[E::imz] * n[2];
+  const double velNormR = r[E::imx] * n[0] + r[E::imy] * n[1] + r[E::imz] * n[2];
+  const double sosL = SoS<NS>(g, l);
+  const double sosR = SoS<NS>(g, r);
+  const double sosStar = sqrt(sosL * sosR);
+  const double vel = 0.5 * (velNormL + velNormR);
+  double sos = sosStar;
+  if (vel < 0.0) {
+    sos = sosStar * sosStar / fmax(velNormR, sosStar);
+  } else if (vel > 0.0) {
+    sos = sosStar * sosStar / fmax(velNormL, sosStar);
+  }
+  const double ml = velNormL / sos;
+  const double mr = velNormR / sos;
+  const double mPlusL = fabs(ml) <= 1.0 ? 0.25 * ((ml + 1.0) * (ml + 1.0)) : 0.5 * (ml + fabs(ml));
+  const double mMinusR =
+      fabs(mr) <= 1.0 ? -0.25 * ((mr - 1.0) * (mr - 1.0)) : 0.5 * (mr - fabs(mr));
+  const double pPlus = fabs(ml) <= 1.0 ? 0.25 * ((ml + 1.0) * (ml + 1.0)) * (2.0 - ml)
+                                       : 0.5 * (1.0 + Sign(ml));
+  const double pMinus = fabs(mr) <= 1.0 ? 0.25 * ((mr - 1.0) * (mr - 1.0)) * (2.0 + mr)
+                                        : 0.5 * (1.0 - Sign(mr));
+  const double pl = l[E::ie], pr = r[E::ie];
+  const double ps = pPlus * pl + pMinus * pr;
+  const double ratio = fmin(pl / pr, pr / pl);
+  const double w = 1.0 - ratio * ratio * ratio;
+  const double fl = fabs(ml) < 1.0 ? pl / ps - 1.0 : 0.0;
+  const double fr = fabs(mr) < 1.0 ? pr / ps - 1.0 : 0.0;
+  const double mavg = mPlusL + mMinusR;
+  const double mPlusLBar = mavg >= 0.0 ? mPlusL + mMinusR * ((1.0 - w) * (1.0 + fr) - fl)
+                                       : mPlusL * w * (1.0 + fl);
+  const double mMinusRBar = mavg >= 0.0 ? mMinusR * w * (1.0 + fr)
+                                        : mMinusR + mPlusL * ((1.0 - w) * (1.0 + fl) - fr);
+  const double vl = mPlusLBar * sos;
+  const double vr = mMinusRBar * sos;
+  const double rhoL = SpeciesSum<NS>(l);
+  const double rhoR = SpeciesSum<NS>(r);
+#pragma unroll
+  for (int q = 0; q < NS; ++q) f[q] = l[q] * vl + r[q] * vr;
+  f[E::imx] = (rhoL * vl * l[E::imx] + pPlus * pl * n[0]) +
+              (rhoR * vr * r[E::imx] + pMinus * pr * n[0]);
+  f[E::imy] = (rhoL * vl * l[E::imy] + pPlus * pl * n[1]) +
+              (rhoR * vr * r[E::imy] + pMinus * pr * n[1]);
+  f[E::imz] = (rhoL * vl * l[E::imz] + pPlus * pl * n[2]) +
+              (rhoR * vr * r[E::imz] + pMinus * pr * n[2]);
+  f[E::ie] = rhoL * vl * Enthalpy<NS>(g, l) + rhoR * vr * Enthalpy<NS>(g, r);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) f[E::it + t] = rhoL * vl * l[E::it + t] + rhoR * vr * r[E::it + t];
+}
+
+template <int NS, int NT, int FLUX>
+AITHER_HD void InviscidFlux(const Gas &g, const double *l, const double *r, const double *n,
+                            double *f) {
+  if (FLUX == AITHER_FLUX_ROE) RoeFlux<NS, NT>(g, l, r, n, f);
+  else AusmFlux<NS, NT>(g, l, r, n, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectral radii; ref: include/spectralRadius.hpp:44-80
+template <int NS>
+AITHER_HD double InvCellSpectralRadius(const double *s, double sos, const double *fL,
+                                       const double *fR) {
+  double a0 = 0.5 * (fL[0] + fR[0]), a1 = 0.5 * (fL[1] + fR[1]), a2 = 0.5 * (fL[2] + fR[2]);
+  const double mag = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  a0 /= mag;
+  a1 /= mag;
+  a2 /= mag;
+  const double fMag = 0.5 * (fL[3] + fR[3]);
+  return (fabs(s[NS] * a0 + s[NS + 1] * a1 + s[NS + 2] * a2) + sos) * fMag;
+}
+template <int NS>
+AITHER_HD double InvFaceSpectralRadius(const double *s, double sos, const double *fA) {
+  return 0.5 * fA[3] * (fabs(s[NS] * fA[0] + s[NS + 1] * fA[1] + s[NS + 2] * fA[2]) + sos);
+}
+
+// Scalar (LU-SGS / DPLUR) off-diagonal product for one neighbour, inviscid:
+// 0.5 |A| (F(U + dU) - F(U)) +- lambda_face dU, turbulence rows of the flux change zeroed;
+// ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal)
+template <int NS, int NT>
+AITHER_HD void OffDiagScalar(const Gas &g, const double *state, const double *du,
+                             const double *fArea, bool positive, double *out) {
+  using E = Eq<NS, NT>;
+  double su[E::neq], fo[E::neq], fn[E::neq];
+  UpdatePrimWithCons<NS, NT>(g, state, du, su);
+  PhysicalFlux<NS, NT>(g, state, fArea, fo);
+  PhysicalFlux<NS, NT>(g, su, fArea, fn);
+  const double sr = InvFaceSpectralRadius<NS>(state, SoS<NS>(g, state), fArea);
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) {
+    const double fc = e < NS + 4 ? 0.5 * fArea[3] * (fn[e] - fo[e]) : 0.0;
+    const double srd = (e < NS + 4 ? sr : 0.0) * du[e];
+    out[e] = positive ? fc + srd : fc - srd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary-condition ghost states; ref: src/ghostStates.cpp:62-708
+template <int NS, int NT>
+AITHER_HD void ExtrapolateHoldMixture(const double *bnd, double factor, const double *interior,
+                                      double *out) {
+  // ref: src/ghostStates.cpp:691-708
+  using E = Eq<NS, NT>;
+  const double bndRho = SpeciesSum<NS>(bnd);
+  const double intRho = SpeciesSum<NS>(interior);
+  const double ghostRho = factor * bndRho - intRho;
+  double tmp[E::neq];
+  if (ghostRho <= 0.0) {
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) tmp[e] = bnd[e];
+  } else {
+#pragma unroll
+    for (int e = NS; e < E::neq; ++e) tmp[e] = factor * bnd[e] - interior[e];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) tmp[q] = fmax(ghostRho * (bnd[q] / bndRho), 0.0);
+  }
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) out[e] = tmp[e];
+}
+
+template <int NS, int NT>
+AITHER_HD void FreeStateFromBC(const aither_bc_state &bc, double *fs) {
+  using E = Eq<NS, NT>;
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) fs[e] = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) fs[q] = bc.density * bc.massFractions[q];
+  fs[E::imx] = bc.velocity[0];
+  fs[E::imy] = bc.velocity[1];
+  fs[E::imz] = bc.velocity[2];
+  fs[E::ie] = bc.pressure;
+}
+
+// Ghost state for one boundary face. `interior` is the reflected cell for walls and the
+// boundary-adjacent cell otherwise (ref: src/procBlock.cpp:2512-2514); `areaVec` is the unit
+// normal of the boundary face; surf 1..6; layer 1..g.
+template <int NS, int NT>
+AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
+                          const double *areaVec, int surf, const aither_bc_state &bc, int layer,
+                          double *ghost) {
+  using E = Eq<NS, NT>;
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
+  const bool isLower = surf % 2 == 1;
+  double nA[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) nA[d] = isLower ? -1.0 * areaVec[d] : areaVec[d];
+  const double vn = interior[E::imx] * nA[0] + interior[E::imy] * nA[1] + interior[E::imz] * nA[2];
+
+  if (bcType == AITHER_BC_SLIP_WALL) {  // ref: :118-133
+    ghost[E::imx] = interior[E::imx] - 2.0 * nA[0] * vn;
+    ghost[E::imy] = interior[E::imy] - 2.0 * nA[1] * vn;
+    ghost[E::imz] = interior[E::imz] - 2.0 * nA[2] * vn;
+  } else if (bcType == AITHER_BC_CHARACTERISTIC || bcType == AITHER_BC_INLET) {
+    // ref: :289-386 (characteristic), :391-484 (inlet, reflecting form)
+    double fs[E::neq];
+    FreeStateFromBC<NS, NT>(bc, fs);
+    const double SoSInt = SoS<NS>(g, interior);
+    const double machInt = fabs(vn) / SoSInt;
+    const bool isInlet = bcType == AITHER_BC_INLET;
+    bool extrapolate = true;
+    if (machInt >= 1.0 && (vn < 0.0 || isInlet)) {  // supersonic inflow
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) ghost[e] = fs[e];
+      if (isInlet) extrapolate = false;
+    } else if (machInt >= 1.0) {  // supersonic outflow: interior
+    } else if (vn < 0.0 || isInlet) {  // subsonic inflow
+      const double rhoSoSInt = SpeciesSum<NS>(interior) * SoSInt;
+      const double vd0 = fs[E::imx] - interior[E::imx], vd1 = fs[E::imy] - interior[E::imy],
+                   vd2 = fs[E::imz] - interior[E::imz];
+      ghost[E::ie] = 0.5 * (fs[E::ie] + interior[E::ie] -
+                            rhoSoSInt * (nA[0] * vd0 + nA[1] * vd1 + nA[2] * vd2));
+      const double deltaPressure = fs[E::ie] - ghost[E::ie];
+      const double fsRho = SpeciesSum<NS>(fs);
+      const double rho = fsRho - deltaPressure / (SoSInt * SoSInt);
+#pragma unroll
+      for (int q = 0; q < NS; ++q) ghost[q] = rho * (fs[q] / fsRho);
+      ghost[E::imx] = fs[E::imx] - nA[0] * deltaPressure / rhoSoSInt;
+      ghost[E::imy] = fs[E::imy] - nA[1] * deltaPressure / rhoSoSInt;
+      ghost[E::imz] = fs[E::imz] - nA[2] * deltaPressure / rhoSoSInt;
+    } else {  // subsonic outflow
+      const double intRho = SpeciesSum<NS>(interior);
+      const double rhoSoSInt = intRho * SoSInt;
+      const double deltaPressure = interior[E::ie] - fs[E::ie];
+      const double rho = intRho - deltaPressure / (SoSInt * SoSInt);
+#pragma unroll
+      for (int q = 0; q < NS; ++q) ghost[q] = rho * (interior[q] / intRho);
+      ghost[E::imx] = interior[E::imx] + nA[0] * deltaPressure / rhoSoSInt;
+      ghost[E::imy] = interior[E::imy] + nA[1] * deltaPressure / rhoSoSInt;
+      ghost[E::imz] = interior[E::imz] + nA[2] * deltaPressure / rhoSoSInt;
+      ghost[E::ie] = fs[E::ie];
+    }
+    if (extrapolate) {
+      ExtrapolateHoldMixture<NS, NT>(ghost, 2.0, interior, ghost);
+      if (layer > 1) ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+    }
+  } else if (bcType == AITHER_BC_SUPERSONIC_INFLOW) {  // ref: :490-515
+    double fs[E::neq];
+    FreeStateFromBC<NS, NT>(bc, fs);
+#pragma unroll
+    for (int e = 0; e < NS + 4; ++e) ghost[e] = fs[e];
+  } else if (bcType == AITHER_BC_SUPERSONIC_OUTFLOW) {  // ref: :522-527
+    if (layer > 1) {
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) ghost[e] = layer * ghost[e] - interior[e];
+    }
+  } else if (bcType == AITHER_BC_STAGNATION_INLET) {  // ref: :533-598 (Blazek)
+    const double gam = Gamma<NS>(g, interior);
+    const double gm1 = gam - 1.0;
+    const double sosI = SoS<NS>(g, interior);
+    const double rNeg = vn - 2.0 * sosI / gm1;
+    const double magSq = VelMagSq<NS>(interior);
+    const double cosTheta = -1.0 * vn / sqrt(magSq);
+    const double stagSoSsq = sosI * sosI + 0.5 * gm1 * magSq;
+    const double sosB = -1.0 * rNeg * gm1 / (gm1 * cosTheta * cosTheta + 2.0) *
+                        (1.0 + cosTheta * sqrt((gm1 * cosTheta * cosTheta + 2.0) * stagSoSsq /
+                                                   (gm1 * rNeg * rNeg) -
+                                               0.5 * gm1));
+    const double tb = bc.stagnationTemperature * (sosB * sosB / stagSoSsq);
+    const double pb = bc.stagnationPressure * pow(sosB * sosB / stagSoSsq, gam / gm1);
+    const double vbMag = sqrt(2.0 / gm1 * (bc.stagnationTemperature - tb));
+    double Rmix = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Rmix += bc.massFractions[q] * g.R[q];
+    const double rhoGhost = pb / (Rmix * tb);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) ghost[q] = rhoGhost * bc.massFractions[q];
+    ghost[E::imx] = vbMag * bc.direction[0];
+    ghost[E::imy] = vbMag * bc.direction[1];
+    ghost[E::imz] = vbMag * bc.direction[2];
+    ghost[E::ie] = pb;
+    ExtrapolateHoldMixture<NS, NT>(ghost, 2.0, interior, ghost);
+    if (layer > 1) ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+  } else if (bcType == AITHER_BC_PRESSURE_OUTLET) {  // ref: :604-664 (reflecting form)
+    const double SoSInt = SoS<NS>(g, interior);
+    const double intRho = SpeciesSum<NS>(interior);
+    const double rhoSoSInt = intRho * SoSInt;
+    ghost[E::ie] = bc.pressure;
+    const double deltaPressure = interior[E::ie] - ghost[E::ie];
+    const double rho = intRho - deltaPressure / (SoSInt * SoSInt);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) ghost[q] = rho * (interior[q] / intRho);
+    ghost[E::imx] = interior[E::imx] + nA[0] * deltaPressure / rhoSoSInt;
+    ghost[E::imy] = interior[E::imy] + nA[1] * deltaPressure / rhoSoSInt;
+    ghost[E::imz] = interior[E::imz] + nA[2] * deltaPressure / rhoSoSInt;
+    const double gvn = ghost[E::imx] * nA[0] + ghost[E::imy] * nA[1] + ghost[E::imz] * nA[2];
+    if (gvn / SoS<NS>(g, ghost) >= 1.0) {
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
+    }
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) ghost[e] = 2.0 * ghost[e] - interior[e];
+    if (layer > 1) {
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) ghost[e] = layer * ghost[e] - interior[e];
+    }
+  }
+  // interblock / periodic: filled by the halo exchange
+}
+
+}  // namespace aither

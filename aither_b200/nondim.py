@@ -1,0 +1,72 @@
+"""Nondimensionalisation and `aither_cfg` construction (host set-up, mirrors `.inp` semantics).
+
+Follows reference src/input.cpp:600-621 (reference speed of sound), src/fluid.cpp:89-103
+(fluid::Nondimensionalize) and src/inputStates.cpp:464-473,590-599,674-681 (state data):
+lengths / lRef, velocities / aRef, rho / rhoRef, p / (rhoRef aRef^2), T / TRef.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import ctypes_abi as abi
+from .problem import make_cfg
+
+UNIVERSAL_GAS_CONSTANT = 8.3144598  # J / mol-K, reference include/fluid.hpp:44
+
+
+@dataclass
+class Fluid:
+    """One calorically perfect species, nondimensional (reference include/fluid.hpp)."""
+    n: float
+    gas_constant: float     # nondimensional R = 1/gamma for a single species
+    hf: float
+    a_ref: float
+    rho_ref: float
+    t_ref: float
+    l_ref: float
+
+
+def air(rho_ref, t_ref, l_ref=1.0, n=2.5, molar_mass_g=28.97, hf=0.0):
+    """fluidDatabase/air.dat constants -> nondimensional fluid (src/fluid.cpp:89-103)."""
+    molar_mass = molar_mass_g / 1000.0
+    gamma = (n + 1.0) / n
+    r_dim = UNIVERSAL_GAS_CONSTANT / molar_mass
+    a_ref = np.sqrt(1.0 * gamma * r_dim * t_ref)  # src/input.cpp:616-621
+    mm_nd = molar_mass / (rho_ref / l_ref ** 3.0)
+    ru_nd = UNIVERSAL_GAS_CONSTANT / (a_ref * a_ref * rho_ref / (t_ref * l_ref ** 3.0))
+    hf_nd = hf / (molar_mass * (a_ref * a_ref))
+    return Fluid(n=n, gas_constant=ru_nd / mm_nd, hf=hf_nd, a_ref=float(a_ref), rho_ref=rho_ref,
+                 t_ref=t_ref, l_ref=l_ref)
+
+
+def nondim_primitive(density, velocity, pressure, rho_ref, t_ref, fluid=None):
+    fl = fluid or air(rho_ref, t_ref)
+    return np.array([density / rho_ref, velocity[0] / fl.a_ref, velocity[1] / fl.a_ref,
+                     velocity[2] / fl.a_ref, pressure / (rho_ref * fl.a_ref * fl.a_ref)])
+
+
+_RECON = {"constant": (abi.RECON_CONSTANT, -2.0), "upwind": (abi.RECON_MUSCL, -1.0),
+          "fromm": (abi.RECON_MUSCL, 0.0), "quick": (abi.RECON_MUSCL, 0.5),
+          "central": (abi.RECON_MUSCL, 1.0), "thirdOrder": (abi.RECON_MUSCL, 1.0 / 3.0),
+          "weno": (abi.RECON_WENO, 0.0), "wenoZ": (abi.RECON_WENOZ, 0.0)}
+_LIMITER = {"none": abi.LIMITER_NONE, "vanAlbada": abi.LIMITER_VAN_ALBADA,
+            "minmod": abi.LIMITER_MINMOD}
+
+
+def euler_cfg(fluid, *, g=2, solver="dplur", sweeps=4, limiter="none", flux="roe",
+              recon="thirdOrder", relaxation=1.0, bc_states=()):
+    """`aither_cfg` for `equationSet: euler`, `timeIntegration: implicitEuler` (theta=1, zeta=0;
+    src/input.cpp:256-270), scalar diagonal (lusgs / dplur)."""
+    rc, kappa = _RECON[recon]
+    is_dplur = solver in ("dplur", "bdplur")
+    return make_cfg(
+        numSpecies=1, numTurb=0, numGhosts=g, isViscous=0, isRANS=0,
+        isBlockMatrix=int(solver in ("blusgs", "bdplur")), isMultilevelTime=0,
+        recon=rc, limiter=_LIMITER[limiter], invFlux=abi.FLUX_ROE if flux == "roe" else abi.FLUX_AUSM,
+        invFluxJac=abi.JAC_RUSANOV, viscRecon=0, turbModel=abi.TURB_NONE,
+        solver=abi.SOLVER_DPLUR if is_dplur else abi.SOLVER_LUSGS,
+        matrixSweeps=sweeps, matrixRequiresInit=int(is_dplur or sweeps > 1),  # input.cpp:1120
+        kappa=kappa, theta=1.0, zeta=0.0, matrixRelaxation=relaxation, dualTimeCFL=-1.0,
+        dtNondim=-1.0, viscousCFLCoeff=1.0,
+        gasConstant=[fluid.gas_constant], n=[fluid.n], hf=[fluid.hf],
+        bcStates=list(bc_states))

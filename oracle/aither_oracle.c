@@ -1,0 +1,1483 @@
+/* aither_oracle.c -- plain-C CPU restatement of the reference hot path.
+ * TEST INFRASTRUCTURE ONLY; see aither_oracle.h for the rules and the pinning.
+ *
+ * Sequential, array-of-structs, the reference's own loop and accumulation
+ * order. "ref:" comments cite mnucci32/aither v0.10.0 file:line.
+ */
+#include "aither_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_EPS 1.0e-30 /* ref: include/macros.hpp.in:21 */
+#define MAXEQ (AITHER_MAX_SPECIES + 6)
+
+typedef struct {
+  int ni, nj, nk, g;
+  int NI, NJ, NK; /* padded extents */
+  int parentBlock;
+  int nsurf;
+  aither_surface *surf;
+  double *state;     /* padded, neq */
+  double *residual;  /* ni nj nk neq */
+  double *specRad;   /* ni nj nk 2 */
+  double *dt;        /* ni nj nk */
+  double *a, *ainv;  /* ni nj nk asz */
+  double *x;         /* padded, neq */
+  double *xold;      /* padded, neq (scratch for DPLUR) */
+  double *consN;     /* ni nj nk neq */
+  double *consNm1;   /* ni nj nk neq */
+  double *mresid;    /* ni nj nk neq: matrix residual */
+  double *temperature; /* padded */
+  const double *vol, *fAI, *fAJ, *fAK, *center, *cwI, *cwJ, *cwK, *wallDist;
+  int *order; /* hyperplane ordering: 3 ints per cell */
+} orc_block;
+
+struct orc_level {
+  aither_cfg cfg;
+  int neq, ns, nt, asz;
+  int nblk;
+  orc_block *blk;
+  int nconn;
+  aither_conn *conn;
+};
+
+/* ------------------------------------------------------------------------ */
+/* indexing (ref: include/multiArray3d.hpp:96-126)                           */
+static inline long cidx(const orc_block *b, int i, int j, int k) {
+  return (long)(i + b->g) + (long)(j + b->g) * b->NI +
+         (long)(k + b->g) * b->NI * b->NJ;
+}
+static inline long pidx(const orc_block *b, int i, int j, int k) {
+  return (long)i + (long)j * b->ni + (long)k * b->ni * b->nj;
+}
+/* face arrays have one more entry in their own direction */
+static inline long fidxI(const orc_block *b, int i, int j, int k) {
+  return (long)(i + b->g) + (long)(j + b->g) * (b->NI + 1) +
+         (long)(k + b->g) * (b->NI + 1) * b->NJ;
+}
+static inline long fidxJ(const orc_block *b, int i, int j, int k) {
+  return (long)(i + b->g) + (long)(j + b->g) * b->NI +
+         (long)(k + b->g) * b->NI * (b->NJ + 1);
+}
+static inline long fidxK(const orc_block *b, int i, int j, int k) {
+  return (long)(i + b->g) + (long)(j + b->g) * b->NI +
+         (long)(k + b->g) * b->NI * b->NJ;
+}
+
+/* ------------------------------------------------------------------------ */
+/* thermodynamics of a primitive state [rho_s.., u, v, w, p, (k, w)]          */
+static double rho_of(const orc_level *h, const double *s) {
+  double r = 0.0; /* ref: varArray SpeciesSum, std::accumulate from 0 */
+  for (int ss = 0; ss < h->ns; ++ss) r += s[ss];
+  return r;
+}
+/* ref: src/eos.cpp:100-109 */
+static double temperature_of(const orc_level *h, const double *s) {
+  double rhoR = 0.0;
+  for (int ss = 0; ss < h->ns; ++ss) rhoR += s[ss] * h->cfg.gasConstant[ss];
+  return s[h->ns + 3] / rhoR;
+}
+static void mass_fractions(const orc_level *h, const double *s, double *mf) {
+  const double rho = rho_of(h, s);
+  for (int ss = 0; ss < h->ns; ++ss) mf[ss] = s[ss] / rho;
+}
+/* ref: src/thermodynamic.cpp:62-82, include/thermodynamic.hpp:55-57,112-119 */
+static double cp_mix(const orc_level *h, const double *mf) {
+  double cp = 0.0;
+  for (int ss = 0; ss < h->ns; ++ss)
+    cp += mf[ss] * (h->cfg.gasConstant[ss] * (h->cfg.n[ss] + 1.0));
+  return cp;
+}
+static double cv_mix(const orc_level *h, const double *mf) {
+  double cv = 0.0;
+  for (int ss = 0; ss < h->ns; ++ss)
+    cv += mf[ss] * (h->cfg.gasConstant[ss] * h->cfg.n[ss]);
+  return cv;
+}
+static double gamma_of(const orc_level *h, const double *s) {
+  double mf[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  return cp_mix(h, mf) / cv_mix(h, mf);
+}
+/* ref: include/arrayView.hpp:384-391 */
+static double sos_of(const orc_level *h, const double *s) {
+  return sqrt(gamma_of(h, s) * s[h->ns + 3] / rho_of(h, s));
+}
+static double vel_mag(const orc_level *h, const double *s) {
+  const double *v = s + h->ns;
+  return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+}
+/* ref: include/arrayView.hpp:400-408, src/eos.cpp:83-88,
+ * src/thermodynamic.cpp:95-104 */
+static double enthalpy_of(const orc_level *h, const double *s) {
+  double mf[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  const double t = temperature_of(h, s);
+  double hs = 0.0;
+  for (int ss = 0; ss < h->ns; ++ss)
+    hs += mf[ss] * (h->cfg.hf[ss] +
+                    (h->cfg.gasConstant[ss] * (h->cfg.n[ss] + 1.0)) * t);
+  const double vel = vel_mag(h, s);
+  return hs + 0.5 * vel * vel;
+}
+/* ref: include/arrayView.hpp:432-441 */
+static double energy_of(const orc_level *h, const double *s) {
+  double mf[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  const double t = temperature_of(h, s);
+  double e = 0.0;
+  for (int ss = 0; ss < h->ns; ++ss)
+    e += mf[ss] *
+         (h->cfg.hf[ss] + (h->cfg.gasConstant[ss] * h->cfg.n[ss]) * t);
+  const double vel = vel_mag(h, s);
+  return e + 0.5 * vel * vel;
+}
+/* ref: include/primitive.hpp:181-199 (PrimToCons) */
+static void prim_to_cons(const orc_level *h, const double *s, double *c) {
+  const int ns = h->ns;
+  for (int ss = 0; ss < ns; ++ss) c[ss] = s[ss];
+  const double rho = rho_of(h, s);
+  c[ns] = rho * s[ns];
+  c[ns + 1] = rho * s[ns + 1];
+  c[ns + 2] = rho * s[ns + 2];
+  c[ns + 3] = rho * energy_of(h, s);
+  for (int tt = 0; tt < h->nt; ++tt) c[ns + 4 + tt] = rho * s[ns + 4 + tt];
+}
+/* ref: include/primitive.hpp:150-177 (primitive(cons, phys)),
+ * src/eos.cpp:40-63, src/thermodynamic.cpp:107-113 */
+static void cons_to_prim(const orc_level *h, const double *c, double *s) {
+  const int ns = h->ns;
+  for (int ss = 0; ss < ns; ++ss) s[ss] = c[ss];
+  double rho = 0.0;
+  for (int ss = 0; ss < ns; ++ss) rho += c[ss];
+  s[ns] = c[ns] / rho;
+  s[ns + 1] = c[ns + 1] / rho;
+  s[ns + 2] = c[ns + 2] / rho;
+  const double energy = c[ns + 3] / rho;
+  const double vel = sqrt(s[ns] * s[ns] + s[ns + 1] * s[ns + 1] +
+                          s[ns + 2] * s[ns + 2]);
+  const double specEnergy = energy - 0.5 * vel * vel;
+  double rhoSum = 0.0;
+  for (int ss = 0; ss < ns; ++ss) rhoSum += s[ss];
+  double mf[AITHER_MAX_SPECIES];
+  for (int ss = 0; ss < ns; ++ss) mf[ss] = s[ss] / rhoSum;
+  double hf = 0.0;
+  for (int ss = 0; ss < ns; ++ss) hf += h->cfg.hf[ss] * mf[ss];
+  const double temperature = (specEnergy - hf) / cv_mix(h, mf);
+  double p = 0.0;
+  for (int ss = 0; ss < ns; ++ss)
+    p += s[ss] * h->cfg.gasConstant[ss] * temperature;
+  s[ns + 3] = p;
+  for (int tt = 0; tt < h->nt; ++tt) {
+    const double v = c[ns + 4 + tt] / rho;
+    s[ns + 4 + tt] = v > 1.0e-20 ? v : 1.0e-20; /* ref: turbulence.hpp:72-73 */
+  }
+}
+/* ref: include/primitive.hpp:206-231 (UpdatePrimWithCons) */
+static void update_prim_with_cons(const orc_level *h, const double *s,
+                                  const double *du, double *out) {
+  const int ns = h->ns;
+  double c[MAXEQ];
+  prim_to_cons(h, s, c);
+  for (int e = 0; e < h->neq; ++e) c[e] += du[e];
+  double rho = 0.0;
+  for (int ss = 0; ss < ns; ++ss) rho += c[ss];
+  double mf[AITHER_MAX_SPECIES];
+  double total = 0.0;
+  for (int ss = 0; ss < ns; ++ss) {
+    mf[ss] = c[ss] / rho;
+    mf[ss] = mf[ss] > 0.0 ? mf[ss] : 0.0;
+    total += mf[ss];
+  }
+  for (int ss = 0; ss < ns; ++ss) mf[ss] /= total;
+  for (int ss = 0; ss < ns; ++ss) c[ss] = rho * mf[ss];
+  cons_to_prim(h, c, out);
+}
+
+/* ------------------------------------------------------------------------ */
+/* reconstruction                                                             */
+static double limiter_fn(int lim, double r) {
+  if (lim == AITHER_LIMITER_VAN_ALBADA) { /* ref: src/limiter.cpp:37-46 */
+    const double r2 = r * r;
+    const double l = (r + r2) / (1.0 + r2);
+    return l > 0.0 ? l : 0.0;
+  } else if (lim == AITHER_LIMITER_MINMOD) { /* ref: src/limiter.cpp:24-34 */
+    const double m = 1.0 < r ? 1.0 : r;
+    return 0.0 > m ? 0.0 : m;
+  }
+  return 1.0;
+}
+/* ref: include/reconstruction.hpp:110-154 (FaceReconMUSCL) */
+void orc_muscl(const double *uw2, const double *uw1, const double *dw1, int n,
+               double kappa, int limiter, double w2, double w1, double wd,
+               double *face) {
+  const double dPlus = (w1 + w1) / (w1 + wd);
+  const double dMinus = (w1 + w1) / (w1 + w2);
+  for (int e = 0; e < n; ++e) {
+    const double r = (ORC_EPS + (dw1[e] - uw1[e]) * dPlus) /
+                     (ORC_EPS + (uw1[e] - uw2[e]) * dMinus);
+    double lim = 1.0, invLim = 1.0;
+    if (limiter != AITHER_LIMITER_NONE) {
+      lim = limiter_fn(limiter, r);
+      invLim = limiter_fn(limiter, 1.0 / r);
+    }
+    face[e] = uw1[e] + 0.25 * ((uw1[e] - uw2[e]) * dMinus) *
+                           ((1.0 - kappa) * lim + (1.0 + kappa) * r * invLim);
+  }
+}
+
+/* ref: include/utility.hpp:103-114 */
+static double stencil_width(const double *w, int start, int end) {
+  double width = 0.0;
+  if (end > start) {
+    for (int q = start; q < end; ++q) width += w[q];
+  } else if (start > end) {
+    for (int q = end; q < start; ++q) width += w[q];
+    width = -1.0 * width;
+  }
+  return width;
+}
+/* ref: src/utility.cpp:449-483 (LagrangeCoeff) */
+static void lagrange_coeff(const double *w, int degree, int rr, int ii,
+                           double *coeffs) {
+  for (int jj = 0; jj <= degree; ++jj) {
+    coeffs[jj] = 0.0;
+    for (int mm = jj + 1; mm <= degree + 1; ++mm) {
+      double numer = 0.0, denom = 1.0;
+      for (int ll = 0; ll <= degree + 1; ++ll) {
+        if (ll != mm) {
+          double numProd = 1.0;
+          for (int qq = 0; qq <= degree + 1; ++qq) {
+            if (qq != mm && qq != ll)
+              numProd *= stencil_width(w, ii - rr + qq, ii + 1);
+          }
+          numer += numProd;
+          denom *= stencil_width(w, ii - rr + ll, ii - rr + mm);
+        }
+      }
+      coeffs[jj] += numer / denom;
+    }
+    coeffs[jj] *= w[ii - rr + jj];
+  }
+}
+/* ref: include/utility.hpp:116-122 */
+static double deriv2nd(double x0, double x1, double x2, double y0, double y1,
+                       double y2) {
+  const double fwd = (y2 - y1) / (0.5 * (x2 + x1));
+  const double bck = (y1 - y0) / (0.5 * (x1 + x0));
+  return (fwd - bck) / (0.25 * (x2 + x0) + 0.5 * x1);
+}
+/* ref: include/reconstruction.hpp:157-183 */
+static double beta_integral1(double d1, double d2, double dx, double x) {
+  return ((d1 * d1) * x + d1 * d2 * x * x + (d2 * d2) * pow(x, 3.0) / 3.0) *
+             dx +
+         (d2 * d2) * x * pow(dx, 3.0);
+}
+static double beta_integral(double d1, double d2, double dx, double xl,
+                            double xh) {
+  return beta_integral1(d1, d2, dx, xh) - beta_integral1(d1, d2, dx, xl);
+}
+/* ref: include/reconstruction.hpp:244-310 (FaceReconWENO); u[0..4] =
+ * upwind3, upwind2, upwind1, downwind1, downwind2 */
+void orc_weno(const double *u[5], const double w[5], int n, int isWenoZ,
+              double *face) {
+  double c0[3], c1[3], c2[3], fc[5];
+  lagrange_coeff(w, 2, 2, 2, c0);
+  lagrange_coeff(w, 2, 1, 2, c1);
+  lagrange_coeff(w, 2, 0, 2, c2);
+  lagrange_coeff(w, 4, 2, 2, fc);
+  const double lw0 = fc[0] / c0[0];
+  const double lw1 = fc[4] / c2[2];
+  const double lw2 = 1.0 - lw0 - lw1;
+  for (int e = 0; e < n; ++e) {
+    const double y0 = u[0][e], y1 = u[1][e], y2 = u[2][e], y3 = u[3][e],
+                 y4 = u[4][e];
+    const double st0 = c0[0] * y0 + c0[1] * y1 + c0[2] * y2;
+    const double st1 = c1[0] * y1 + c1[1] * y2 + c1[2] * y3;
+    const double st2 = c2[0] * y2 + c2[1] * y3 + c2[2] * y4;
+    /* Beta0(uw3, uw2, uw1, ...) ref: reconstruction.hpp:185-202 */
+    double d2 = deriv2nd(w[0], w[1], w[2], y0, y1, y2);
+    double d1 = (y2 - y1) / (0.5 * (w[2] + w[1])) + 0.5 * w[2] * d2;
+    const double b0 = beta_integral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+    /* Beta1(uw2, uw1, dw1, ...) ref: :204-221 */
+    d2 = deriv2nd(w[1], w[2], w[3], y1, y2, y3);
+    d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
+    const double b1 = beta_integral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+    /* Beta2(uw1, dw1, dw2, ...) ref: :223-240 */
+    d2 = deriv2nd(w[2], w[3], w[4], y2, y3, y4);
+    d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
+    const double b2 = beta_integral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+    double n0, n1, n2;
+    if (isWenoZ) {
+      const double tau5 = fabs(b0 - b2);
+      const double eps = 1.0e-40;
+      double t = tau5 / (eps + b0);
+      n0 = lw0 * (1.0 + t * t);
+      t = tau5 / (eps + b1);
+      n1 = lw1 * (1.0 + t * t);
+      t = tau5 / (eps + b2);
+      n2 = lw2 * (1.0 + t * t);
+    } else {
+      const double eps = 1.0e-6;
+      n0 = lw0 / ((eps + b0) * (eps + b0));
+      n1 = lw1 / ((eps + b1) * (eps + b1));
+      n2 = lw2 / ((eps + b2) * (eps + b2));
+    }
+    const double sum = n0 + n1 + n2;
+    n0 /= sum;
+    n1 /= sum;
+    n2 /= sum;
+    face[e] = n0 * st0 + n1 * st1 + n2 * st2;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* inviscid fluxes                                                            */
+/* ref: include/inviscidFlux.hpp:128-159 (ConstructFromPrim) */
+static void physical_flux(const orc_level *h, const double *s,
+                          const double n[3], double *f) {
+  const int ns = h->ns;
+  const double *v = s + ns;
+  const double velNorm = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
+  for (int ss = 0; ss < ns; ++ss) f[ss] = s[ss] * velNorm;
+  const double rho = rho_of(h, s);
+  const double p = s[ns + 3];
+  f[ns] = rho * velNorm * v[0] + p * n[0];
+  f[ns + 1] = rho * velNorm * v[1] + p * n[1];
+  f[ns + 2] = rho * velNorm * v[2] + p * n[2];
+  f[ns + 3] = rho * velNorm * enthalpy_of(h, s);
+  for (int tt = 0; tt < h->nt; ++tt)
+    f[ns + 4 + tt] = rho * velNorm * s[ns + 4 + tt];
+}
+/* ref: include/inviscidFlux.hpp:260-382 (RoeFlux),
+ * include/primitive.hpp:245-280 (RoeAveragedState) */
+static void roe_flux(const orc_level *h, const double *l, const double *r,
+                     const double n[3], double *flux) {
+  const int ns = h->ns, nt = h->nt, neq = h->neq;
+  const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3, it = ns + 4;
+  double roe[MAXEQ];
+  const double denRatio = sqrt(rho_of(h, r) / rho_of(h, l));
+  for (int ss = 0; ss < ns; ++ss) roe[ss] = l[ss] * denRatio;
+  roe[imx] = (l[imx] + denRatio * r[imx]) / (1.0 + denRatio);
+  roe[imy] = (l[imy] + denRatio * r[imy]) / (1.0 + denRatio);
+  roe[imz] = (l[imz] + denRatio * r[imz]) / (1.0 + denRatio);
+  roe[ie] = (l[ie] + denRatio * r[ie]) / (1.0 + denRatio);
+  for (int tt = 0; tt < nt; ++tt)
+    roe[it + tt] = (l[it + tt] + denRatio * r[it + tt]) / (1.0 + denRatio);
+
+  const double hR = enthalpy_of(h, roe);
+  const double aR = sos_of(h, roe);
+  const double rhoR = rho_of(h, roe);
+  const double velNormR = roe[imx] * n[0] + roe[imy] * n[1] + roe[imz] * n[2];
+  double mfR[AITHER_MAX_SPECIES];
+  mass_fractions(h, roe, mfR);
+  double delta[MAXEQ];
+  for (int e = 0; e < neq; ++e) delta[e] = r[e] - l[e];
+  double deltaRho = 0.0;
+  for (int ss = 0; ss < ns; ++ss) deltaRho += delta[ss];
+  const double normVelDiff =
+      delta[imx] * n[0] + delta[imy] * n[1] + delta[imz] * n[2];
+
+  double diss[MAXEQ];
+  for (int e = 0; e < neq; ++e) diss[e] = 0.0;
+
+  /* left moving acoustic wave */
+  double waveSpeed = fabs(velNormR - aR);
+  const double entropyFix = 0.1;
+  if (waveSpeed < entropyFix)
+    waveSpeed = 0.5 * (waveSpeed * waveSpeed / entropyFix + entropyFix);
+  double waveStrength = (delta[ie] - rhoR * aR * normVelDiff) / (2.0 * aR * aR);
+  double wss = waveSpeed * waveStrength;
+  for (int ss = 0; ss < ns; ++ss) diss[ss] += wss * mfR[ss];
+  diss[imx] += wss * (roe[imx] - aR * n[0]);
+  diss[imy] += wss * (roe[imy] - aR * n[1]);
+  diss[imz] += wss * (roe[imz] - aR * n[2]);
+  diss[ie] += wss * (hR - aR * velNormR);
+  for (int tt = 0; tt < nt; ++tt) diss[it + tt] += wss * roe[it + tt];
+
+  /* entropy wave */
+  waveSpeed = fabs(velNormR);
+  for (int ss = 0; ss < ns; ++ss) {
+    waveStrength = -delta[ie] / (aR * aR);
+    wss = waveSpeed * waveStrength;
+    diss[ss] += wss * mfR[ss] + waveSpeed * delta[ss];
+  }
+  waveStrength = deltaRho - delta[ie] / (aR * aR);
+  wss = waveSpeed * waveStrength;
+  diss[imx] += wss * roe[imx];
+  diss[imy] += wss * roe[imy];
+  diss[imz] += wss * roe[imz];
+  diss[ie] += wss * 0.5 *
+              (roe[imx] * roe[imx] + roe[imy] * roe[imy] + roe[imz] * roe[imz]);
+
+  /* shear wave */
+  waveStrength = rhoR;
+  wss = waveSpeed * waveStrength;
+  diss[imx] += wss * (delta[imx] - normVelDiff * n[0]);
+  diss[imy] += wss * (delta[imy] - normVelDiff * n[1]);
+  diss[imz] += wss * (delta[imz] - normVelDiff * n[2]);
+  diss[ie] += wss * ((roe[imx] * delta[imx] + roe[imy] * delta[imy] +
+                      roe[imz] * delta[imz]) -
+                     velNormR * normVelDiff);
+
+  /* right moving acoustic wave */
+  waveSpeed = fabs(velNormR + aR);
+  if (waveSpeed < entropyFix)
+    waveSpeed = 0.5 * (waveSpeed * waveSpeed / entropyFix + entropyFix);
+  waveStrength = (delta[ie] + rhoR * aR * normVelDiff) / (2.0 * aR * aR);
+  wss = waveSpeed * waveStrength;
+  for (int ss = 0; ss < ns; ++ss) diss[ss] += wss * mfR[ss];
+  diss[imx] += wss * (roe[imx] + aR * n[0]);
+  diss[imy] += wss * (roe[imy] + aR * n[1]);
+  diss[imz] += wss * (roe[imz] + aR * n[2]);
+  diss[ie] += wss * (hR + aR * velNormR);
+  for (int tt = 0; tt < nt; ++tt) diss[it + tt] += wss * roe[it + tt];
+
+  /* turbulence waves */
+  if (nt > 0) {
+    waveSpeed = fabs(velNormR);
+    for (int tt = 0; tt < nt; ++tt) {
+      waveStrength = rhoR * delta[it + tt] + roe[it + tt] * deltaRho -
+                     delta[ie] * roe[it + tt] / (aR * aR);
+      wss = waveSpeed * waveStrength;
+      diss[it + tt] += wss * 1.0;
+    }
+  }
+
+  double fl[MAXEQ], fr[MAXEQ];
+  physical_flux(h, l, n, fl);
+  physical_flux(h, r, n, fr);
+  /* ref: src/inviscidFlux.cpp:27-33: left += right - diss; left *= 0.5 */
+  for (int e = 0; e < neq; ++e) flux[e] = (fl[e] + (fr[e] - diss[e])) * 0.5;
+}
+
+static double sign_of(double v) { return (double)((0.0 < v) - (v < 0.0)); }
+
+/* ref: include/inviscidFlux.hpp:396-481 (AUSMFlux), :161-208 */
+static void ausm_flux(const orc_level *h, const double *l, const double *r,
+                      const double n[3], double *f) {
+  const int ns = h->ns, nt = h->nt;
+  const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3, it = ns + 4;
+  const double velNormL = l[imx] * n[0] + l[imy] * n[1] + l[imz] * n[2];
+  const double velNormR = r[imx] * n[0] + r[imy] * n[1] + r[imz] * n[2];
+  const double sosL = sos_of(h, l);
+  const double sosR = sos_of(h, r);
+  const double sosStar = sqrt(sosL * sosR);
+  const double vel = 0.5 * (velNormL + velNormR);
+  double sos = sosStar;
+  if (vel < 0.0) {
+    sos = sosStar * sosStar / (velNormR > sosStar ? velNormR : sosStar);
+  } else if (vel > 0.0) {
+    sos = sosStar * sosStar / (velNormL > sosStar ? velNormL : sosStar);
+  }
+  const double ml = velNormL / sos;
+  const double mr = velNormR / sos;
+  const double mPlusL = fabs(ml) <= 1.0 ? 0.25 * pow(ml + 1.0, 2.0)
+                                        : 0.5 * (ml + fabs(ml));
+  const double mMinusR = fabs(mr) <= 1.0 ? -0.25 * pow(mr - 1.0, 2.0)
+                                         : 0.5 * (mr - fabs(mr));
+  const double pPlus = fabs(ml) <= 1.0
+                           ? 0.25 * pow(ml + 1.0, 2.0) * (2.0 - ml)
+                           : 0.5 * (1.0 + sign_of(ml));
+  const double pMinus = fabs(mr) <= 1.0
+                            ? 0.25 * pow(mr - 1.0, 2.0) * (2.0 + mr)
+                            : 0.5 * (1.0 - sign_of(mr));
+  const double pl = l[ie], pr = r[ie];
+  const double ps = pPlus * pl + pMinus * pr;
+  const double ratio = pl / pr < pr / pl ? pl / pr : pr / pl;
+  const double w = 1.0 - pow(ratio, 3.0);
+  const double fl = fabs(ml) < 1.0 ? pl / ps - 1.0 : 0.0;
+  const double fr = fabs(mr) < 1.0 ? pr / ps - 1.0 : 0.0;
+  const double mavg = mPlusL + mMinusR;
+  const double mPlusLBar =
+      mavg >= 0.0 ? mPlusL + mMinusR * ((1.0 - w) * (1.0 + fr) - fl)
+                  : mPlusL * w * (1.0 + fl);
+  const double mMinusRBar =
+      mavg >= 0.0 ? mMinusR * w * (1.0 + fr)
+                  : mMinusR + mPlusL * ((1.0 - w) * (1.0 + fl) - fr);
+
+  const double vl = mPlusLBar * sos;
+  for (int ss = 0; ss < ns; ++ss) f[ss] = l[ss] * vl;
+  const double rhoL = rho_of(h, l);
+  f[imx] = rhoL * vl * l[imx] + pPlus * pl * n[0];
+  f[imy] = rhoL * vl * l[imy] + pPlus * pl * n[1];
+  f[imz] = rhoL * vl * l[imz] + pPlus * pl * n[2];
+  f[ie] = rhoL * vl * enthalpy_of(h, l);
+  for (int tt = 0; tt < nt; ++tt) f[it + tt] = rhoL * vl * l[it + tt];
+  const double vr = mMinusRBar * sos;
+  for (int ss = 0; ss < ns; ++ss) f[ss] += r[ss] * vr;
+  const double rhoR = rho_of(h, r);
+  f[imx] += rhoR * vr * r[imx] + pMinus * pr * n[0];
+  f[imy] += rhoR * vr * r[imy] + pMinus * pr * n[1];
+  f[imz] += rhoR * vr * r[imz] + pMinus * pr * n[2];
+  f[ie] += rhoR * vr * enthalpy_of(h, r);
+  for (int tt = 0; tt < nt; ++tt) f[it + tt] += rhoR * vr * r[it + tt];
+}
+
+static void inviscid_flux(const orc_level *h, const double *l, const double *r,
+                          const double n[3], double *f) {
+  if (h->cfg.invFlux == AITHER_FLUX_ROE) roe_flux(h, l, r, n, f);
+  else ausm_flux(h, l, r, n, f);
+}
+
+/* ref: include/spectralRadius.hpp:44-65 (InvCellSpectralRadius) */
+static double inv_cell_spec_rad(const orc_level *h, const double *s,
+                                const double *fL, const double *fR) {
+  double a[3] = {0.5 * (fL[0] + fR[0]), 0.5 * (fL[1] + fR[1]),
+                 0.5 * (fL[2] + fR[2])};
+  const double mag = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  a[0] /= mag;
+  a[1] /= mag;
+  a[2] /= mag;
+  const double fMag = 0.5 * (fL[3] + fR[3]);
+  const double *v = s + h->ns;
+  return (fabs(v[0] * a[0] + v[1] * a[1] + v[2] * a[2]) + sos_of(h, s)) * fMag;
+}
+/* ref: include/spectralRadius.hpp:67-80 (InvFaceSpectralRadius) */
+static double inv_face_spec_rad(const orc_level *h, const double *s,
+                                const double *fA) {
+  const double *v = s + h->ns;
+  return 0.5 * fA[3] *
+         (fabs(v[0] * fA[0] + v[1] * fA[1] + v[2] * fA[2]) + sos_of(h, s));
+}
+
+/* ------------------------------------------------------------------------ */
+/* boundary conditions                                                        */
+static const aither_bc_state *bc_data(const orc_level *h, int tag) {
+  for (int b = 0; b < h->cfg.numBCStates; ++b)
+    if (h->cfg.bcStates[b].tag == tag) return &h->cfg.bcStates[b];
+  fprintf(stderr, "oracle: no BC state with tag %d\n", tag);
+  abort();
+  return NULL;
+}
+/* ref: src/ghostStates.cpp:691-708 (ExtrapolateHoldMixture) */
+static void extrapolate_hold_mixture(const orc_level *h, const double *bnd,
+                                     double factor, const double *interior,
+                                     double *out) {
+  const int ns = h->ns;
+  const double bndRho = rho_of(h, bnd);
+  double bndMf[AITHER_MAX_SPECIES];
+  mass_fractions(h, bnd, bndMf);
+  const double intRho = rho_of(h, interior);
+  const double ghostRho = factor * bndRho - intRho;
+  if (ghostRho <= 0.0) {
+    for (int e = 0; e < h->neq; ++e) out[e] = bnd[e];
+    return;
+  }
+  double tmp[MAXEQ];
+  for (int e = 0; e < h->neq; ++e) tmp[e] = factor * bnd[e] - interior[e];
+  for (int ss = 0; ss < ns; ++ss) {
+    const double v = ghostRho * bndMf[ss];
+    tmp[ss] = v > 0.0 ? v : 0.0;
+  }
+  for (int e = 0; e < h->neq; ++e) out[e] = tmp[e];
+}
+
+/* ref: src/ghostStates.cpp:62-689 (GetGhostState), inviscid / low-Re subset */
+static void ghost_state(const orc_level *h, const double *interior, int bcType,
+                        const double areaVec[3], int surf, int tag, int layer,
+                        double *ghost) {
+  const int ns = h->ns, neq = h->neq;
+  const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3;
+  for (int e = 0; e < neq; ++e) ghost[e] = interior[e];
+  const int isLower = surf % 2 == 1;
+  double nA[3];
+  for (int d = 0; d < 3; ++d) nA[d] = isLower ? -1.0 * areaVec[d] : areaVec[d];
+
+  if (bcType == AITHER_BC_SLIP_WALL) { /* ref: :118-133 */
+    const double vn =
+        interior[imx] * nA[0] + interior[imy] * nA[1] + interior[imz] * nA[2];
+    ghost[imx] = interior[imx] - 2.0 * nA[0] * vn;
+    ghost[imy] = interior[imy] - 2.0 * nA[1] * vn;
+    ghost[imz] = interior[imz] - 2.0 * nA[2] * vn;
+  } else if (bcType == AITHER_BC_CHARACTERISTIC) { /* ref: :289-386 */
+    const aither_bc_state *bc = bc_data(h, tag);
+    double freeState[MAXEQ];
+    for (int e = 0; e < neq; ++e) freeState[e] = 0.0;
+    for (int ss = 0; ss < ns; ++ss)
+      freeState[ss] = bc->density * bc->massFractions[ss];
+    freeState[imx] = bc->velocity[0];
+    freeState[imy] = bc->velocity[1];
+    freeState[imz] = bc->velocity[2];
+    freeState[ie] = bc->pressure;
+    const double velIntNorm =
+        interior[imx] * nA[0] + interior[imy] * nA[1] + interior[imz] * nA[2];
+    const double SoSInt = sos_of(h, interior);
+    const double machInt = fabs(velIntNorm) / SoSInt;
+    if (machInt >= 1.0 && velIntNorm < 0.0) {
+      for (int e = 0; e < neq; ++e) ghost[e] = freeState[e];
+    } else if (machInt >= 1.0 && velIntNorm >= 0.0) {
+      /* supersonic outflow: interior */
+    } else if (machInt < 1.0 && velIntNorm < 0.0) {
+      const double rhoSoSInt = rho_of(h, interior) * SoSInt;
+      const double vd[3] = {freeState[imx] - interior[imx],
+                            freeState[imy] - interior[imy],
+                            freeState[imz] - interior[imz]};
+      ghost[ie] = 0.5 * (freeState[ie] + interior[ie] -
+                         rhoSoSInt * (nA[0] * vd[0] + nA[1] * vd[1] +
+                                      nA[2] * vd[2]));
+      const double deltaPressure = freeState[ie] - ghost[ie];
+      const double rho = rho_of(h, freeState) - deltaPressure / (SoSInt * SoSInt);
+      double fmf[AITHER_MAX_SPECIES];
+      mass_fractions(h, freeState, fmf);
+      for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * fmf[ss];
+      ghost[imx] = freeState[imx] - nA[0] * deltaPressure / rhoSoSInt;
+      ghost[imy] = freeState[imy] - nA[1] * deltaPressure / rhoSoSInt;
+      ghost[imz] = freeState[imz] - nA[2] * deltaPressure / rhoSoSInt;
+    } else if (machInt < 1.0 && velIntNorm >= 0.0) {
+      const double rhoSoSInt = rho_of(h, interior) * SoSInt;
+      const double deltaPressure = interior[ie] - freeState[ie];
+      const double rho = rho_of(h, interior) - deltaPressure / (SoSInt * SoSInt);
+      double imf[AITHER_MAX_SPECIES];
+      mass_fractions(h, interior, imf);
+      for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * imf[ss];
+      ghost[imx] = interior[imx] + nA[0] * deltaPressure / rhoSoSInt;
+      ghost[imy] = interior[imy] + nA[1] * deltaPressure / rhoSoSInt;
+      ghost[imz] = interior[imz] + nA[2] * deltaPressure / rhoSoSInt;
+      ghost[ie] = freeState[ie];
+    }
+    double tmp[MAXEQ];
+    extrapolate_hold_mixture(h, ghost, 2.0, interior, tmp);
+    for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+    if (layer > 1) {
+      extrapolate_hold_mixture(h, ghost, (double)layer, interior, tmp);
+      for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+    }
+  } else if (bcType == AITHER_BC_INLET) { /* ref: :391-484, reflecting */
+    const aither_bc_state *bc = bc_data(h, tag);
+    double freeState[MAXEQ];
+    for (int e = 0; e < neq; ++e) freeState[e] = 0.0;
+    for (int ss = 0; ss < ns; ++ss)
+      freeState[ss] = bc->density * bc->massFractions[ss];
+    freeState[imx] = bc->velocity[0];
+    freeState[imy] = bc->velocity[1];
+    freeState[imz] = bc->velocity[2];
+    freeState[ie] = bc->pressure;
+    const double velIntNorm =
+        interior[imx] * nA[0] + interior[imy] * nA[1] + interior[imz] * nA[2];
+    const double SoSInt = sos_of(h, interior);
+    const double machInt = fabs(velIntNorm) / SoSInt;
+    if (machInt >= 1.0) {
+      for (int e = 0; e < neq; ++e) ghost[e] = freeState[e];
+    } else {
+      const double rhoSoSInt = rho_of(h, interior) * SoSInt;
+      const double vd[3] = {freeState[imx] - interior[imx],
+                            freeState[imy] - interior[imy],
+                            freeState[imz] - interior[imz]};
+      ghost[ie] = 0.5 * (freeState[ie] + interior[ie] -
+                         rhoSoSInt * (nA[0] * vd[0] + nA[1] * vd[1] +
+                                      nA[2] * vd[2]));
+      const double deltaPressure = freeState[ie] - ghost[ie];
+      const double rho = rho_of(h, freeState) - deltaPressure / (SoSInt * SoSInt);
+      double fmf[AITHER_MAX_SPECIES];
+      mass_fractions(h, freeState, fmf);
+      for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * fmf[ss];
+      ghost[imx] = freeState[imx] - nA[0] * deltaPressure / rhoSoSInt;
+      ghost[imy] = freeState[imy] - nA[1] * deltaPressure / rhoSoSInt;
+      ghost[imz] = freeState[imz] - nA[2] * deltaPressure / rhoSoSInt;
+      double tmp[MAXEQ];
+      extrapolate_hold_mixture(h, ghost, 2.0, interior, tmp);
+      for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+      if (layer > 1) {
+        extrapolate_hold_mixture(h, ghost, (double)layer, interior, tmp);
+        for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+      }
+    }
+  } else if (bcType == AITHER_BC_SUPERSONIC_INFLOW) { /* ref: :490-515 */
+    const aither_bc_state *bc = bc_data(h, tag);
+    for (int ss = 0; ss < ns; ++ss)
+      ghost[ss] = bc->density * bc->massFractions[ss];
+    ghost[imx] = bc->velocity[0];
+    ghost[imy] = bc->velocity[1];
+    ghost[imz] = bc->velocity[2];
+    ghost[ie] = bc->pressure;
+  } else if (bcType == AITHER_BC_SUPERSONIC_OUTFLOW) { /* ref: :522-527 */
+    if (layer > 1)
+      for (int e = 0; e < neq; ++e) ghost[e] = layer * ghost[e] - interior[e];
+  } else if (bcType == AITHER_BC_STAGNATION_INLET) { /* ref: :533-598 */
+    const aither_bc_state *bc = bc_data(h, tag);
+    const double gam = gamma_of(h, interior);
+    const double g = gam - 1.0;
+    const double vn =
+        interior[imx] * nA[0] + interior[imy] * nA[1] + interior[imz] * nA[2];
+    const double sosI = sos_of(h, interior);
+    const double rNeg = vn - 2.0 * sosI / g;
+    const double vmag = vel_mag(h, interior);
+    const double cosTheta = -1.0 * vn / vmag;
+    const double magSq = interior[imx] * interior[imx] +
+                         interior[imy] * interior[imy] +
+                         interior[imz] * interior[imz];
+    const double stagSoSsq = pow(sosI, 2.0) + 0.5 * g * magSq;
+    const double sosB =
+        -1.0 * rNeg * g / (g * cosTheta * cosTheta + 2.0) *
+        (1.0 + cosTheta * sqrt((g * cosTheta * cosTheta + 2.0) * stagSoSsq /
+                                   (g * rNeg * rNeg) -
+                               0.5 * g));
+    const double tb = bc->stagnationTemperature * (sosB * sosB / stagSoSsq);
+    const double pb =
+        bc->stagnationPressure * pow(sosB * sosB / stagSoSsq, gam / g);
+    const double vbMag = sqrt(2.0 / g * (bc->stagnationTemperature - tb));
+    /* ref: src/eos.cpp:111-115 DensityTP with MixtureGasConstant (inner
+     * product from 0) */
+    double Rmix = 0.0;
+    for (int ss = 0; ss < ns; ++ss)
+      Rmix += bc->massFractions[ss] * h->cfg.gasConstant[ss];
+    const double rhoGhost = pb / (Rmix * tb);
+    for (int ss = 0; ss < ns; ++ss) ghost[ss] = rhoGhost * bc->massFractions[ss];
+    ghost[imx] = vbMag * bc->direction[0];
+    ghost[imy] = vbMag * bc->direction[1];
+    ghost[imz] = vbMag * bc->direction[2];
+    ghost[ie] = pb;
+    double tmp[MAXEQ];
+    extrapolate_hold_mixture(h, ghost, 2.0, interior, tmp);
+    for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+    if (layer > 1) {
+      extrapolate_hold_mixture(h, ghost, (double)layer, interior, tmp);
+      for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+    }
+  } else if (bcType == AITHER_BC_PRESSURE_OUTLET) { /* ref: :604-664 */
+    const aither_bc_state *bc = bc_data(h, tag);
+    const double pb = bc->pressure;
+    const double SoSInt = sos_of(h, interior);
+    const double rhoSoSInt = rho_of(h, interior) * SoSInt;
+    ghost[ie] = pb;
+    const double deltaPressure = interior[ie] - ghost[ie];
+    const double rho = rho_of(h, interior) - deltaPressure / (SoSInt * SoSInt);
+    double imf[AITHER_MAX_SPECIES];
+    mass_fractions(h, interior, imf);
+    for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * imf[ss];
+    ghost[imx] = interior[imx] + nA[0] * deltaPressure / rhoSoSInt;
+    ghost[imy] = interior[imy] + nA[1] * deltaPressure / rhoSoSInt;
+    ghost[imz] = interior[imz] + nA[2] * deltaPressure / rhoSoSInt;
+    const double gvn = ghost[imx] * nA[0] + ghost[imy] * nA[1] + ghost[imz] * nA[2];
+    if (gvn / sos_of(h, ghost) >= 1.0)
+      for (int e = 0; e < neq; ++e) ghost[e] = interior[e];
+    for (int e = 0; e < neq; ++e) ghost[e] = 2.0 * ghost[e] - interior[e];
+    if (layer > 1)
+      for (int e = 0; e < neq; ++e) ghost[e] = layer * ghost[e] - interior[e];
+  } else if (bcType == AITHER_BC_INTERBLOCK || bcType == AITHER_BC_PERIODIC) {
+    /* filled by the halo swap */
+  } else {
+    fprintf(stderr, "oracle: BC type %d not supported\n", bcType);
+    abort();
+  }
+}
+
+static void surface_dirs(int surfType, int *d3) {
+  *d3 = (surfType - 1) / 2; /* 0 = i, 1 = j, 2 = k */
+}
+static int surface_type(const aither_surface *s) {
+  /* ref: src/boundaryConditions.cpp:2424-2452 */
+  if (s->imin == s->imax) return s->imax == 0 ? 1 : 2;
+  if (s->jmin == s->jmax) return s->jmax == 0 ? 3 : 4;
+  return s->kmax == 0 ? 5 : 6;
+}
+
+/* ref: src/procBlock.cpp:2449-2530 (AssignInviscidGhostCells) */
+static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
+  const int neq = h->neq;
+  for (int layer = 1; layer <= b->g; ++layer) {
+    for (int s = 0; s < b->nsurf; ++s) {
+      const aither_surface *sf = &b->surf[s];
+      if (sf->type == AITHER_BC_INTERBLOCK || sf->type == AITHER_BC_PERIODIC)
+        continue;
+      const int st = surface_type(sf);
+      int d3;
+      surface_dirs(st, &d3);
+      const int nd[3] = {b->ni, b->nj, b->nk};
+      const int r3 = d3 == 0 ? sf->imin : (d3 == 1 ? sf->jmin : sf->kmin);
+      int gCell, iCell, aCell;
+      const int bnd = r3;
+      if (st % 2 == 0) {
+        gCell = r3 + layer - 1;
+        iCell = r3 - layer;
+        aCell = r3 - 1;
+        if (iCell < 0) iCell = 0;
+      } else {
+        gCell = r3 - layer;
+        iCell = r3 + layer - 1;
+        aCell = r3;
+        if (iCell >= nd[d3]) iCell = nd[d3] - 1;
+      }
+      int bcType = sf->type;
+      if (bcType == AITHER_BC_VISCOUS_WALL) bcType = AITHER_BC_SLIP_WALL;
+      const int src = bcType == AITHER_BC_SLIP_WALL ? iCell : aCell;
+      /* tangential cell ranges */
+      int lo[3] = {sf->imin, sf->jmin, sf->kmin};
+      int hi[3] = {sf->imax, sf->jmax, sf->kmax};
+      lo[d3] = 0;
+      hi[d3] = 1;
+      for (int kk = lo[2]; kk < hi[2]; ++kk) {
+        for (int jj = lo[1]; jj < hi[1]; ++jj) {
+          for (int ii = lo[0]; ii < hi[0]; ++ii) {
+            int ci[3] = {ii, jj, kk}, cg[3] = {ii, jj, kk}, cf[3] = {ii, jj, kk};
+            ci[d3] = src;
+            cg[d3] = gCell;
+            cf[d3] = bnd;
+            const double *fa =
+                d3 == 0 ? b->fAI + 4 * fidxI(b, cf[0], cf[1], cf[2])
+                        : (d3 == 1 ? b->fAJ + 4 * fidxJ(b, cf[0], cf[1], cf[2])
+                                   : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
+            double ghost[MAXEQ];
+            ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]), bcType,
+                        fa, st, sf->tag, layer, ghost);
+            memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
+                   sizeof(double) * neq);
+          }
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* residual                                                                   */
+static void face_states(const orc_level *h, const orc_block *b, int d, int i,
+                        int j, int k, double *fl, double *fr) {
+  /* face (i,j,k) of direction d lies between cells (..-1) and (..) */
+  const int neq = h->neq;
+  const int di = d == 0, dj = d == 1, dk = d == 2;
+  const double *cw = d == 0 ? b->cwI : (d == 1 ? b->cwJ : b->cwK);
+#define ST(o) (b->state + neq * cidx(b, i + (o)*di, j + (o)*dj, k + (o)*dk))
+#define CW(o) (cw[cidx(b, i + (o)*di, j + (o)*dj, k + (o)*dk)])
+  if (h->cfg.recon == AITHER_RECON_CONSTANT) {
+    memcpy(fl, ST(-1), sizeof(double) * neq);
+    memcpy(fr, ST(0), sizeof(double) * neq);
+  } else if (h->cfg.recon == AITHER_RECON_MUSCL) {
+    /* ref: src/procBlock.cpp:406-418 */
+    orc_muscl(ST(-2), ST(-1), ST(0), neq, h->cfg.kappa, h->cfg.limiter, CW(-2),
+              CW(-1), CW(0), fl);
+    orc_muscl(ST(1), ST(0), ST(-1), neq, h->cfg.kappa, h->cfg.limiter, CW(1),
+              CW(0), CW(-1), fr);
+  } else {
+    /* ref: src/procBlock.cpp:420-436 */
+    const double *ul[5] = {ST(-3), ST(-2), ST(-1), ST(0), ST(1)};
+    const double wl[5] = {CW(-3), CW(-2), CW(-1), CW(0), CW(1)};
+    orc_weno(ul, wl, neq, h->cfg.recon == AITHER_RECON_WENOZ, fl);
+    const double *ur[5] = {ST(2), ST(1), ST(0), ST(-1), ST(-2)};
+    const double wr[5] = {CW(2), CW(1), CW(0), CW(-1), CW(-2)};
+    orc_weno(ur, wr, neq, h->cfg.recon == AITHER_RECON_WENOZ, fr);
+  }
+#undef ST
+#undef CW
+}
+
+/* ref: src/procBlock.cpp:384-491, :522-629, :660-767 (CalcInvFluxI/J/K) */
+static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
+  const int neq = h->neq;
+  const int ni = b->ni + (d == 0), nj = b->nj + (d == 1), nk = b->nk + (d == 2);
+  const int nd = d == 0 ? b->ni : (d == 1 ? b->nj : b->nk);
+  const double *fA = d == 0 ? b->fAI : (d == 1 ? b->fAJ : b->fAK);
+  for (int kk = 0; kk < nk; ++kk) {
+    for (int jj = 0; jj < nj; ++jj) {
+      for (int ii = 0; ii < ni; ++ii) {
+        const int fi = d == 0 ? ii : (d == 1 ? jj : kk); /* face index along d */
+        double fl[MAXEQ], fr[MAXEQ], flux[MAXEQ];
+        face_states(h, b, d, ii, jj, kk, fl, fr);
+        const long f0 = d == 0 ? fidxI(b, ii, jj, kk)
+                               : (d == 1 ? fidxJ(b, ii, jj, kk)
+                                         : fidxK(b, ii, jj, kk));
+        const double *area = fA + 4 * f0;
+        inviscid_flux(h, fl, fr, area, flux);
+        if (fi > 0) {
+          double *r = b->residual +
+                      neq * pidx(b, ii - (d == 0), jj - (d == 1), kk - (d == 2));
+          for (int e = 0; e < neq; ++e) r[e] += flux[e] * area[3];
+        }
+        if (fi < nd) {
+          double *r = b->residual + neq * pidx(b, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) r[e] -= flux[e] * area[3];
+          const long f1 = d == 0 ? fidxI(b, ii + 1, jj, kk)
+                                 : (d == 1 ? fidxJ(b, ii, jj + 1, kk)
+                                           : fidxK(b, ii, jj, kk + 1));
+          const double sr = inv_cell_spec_rad(
+              h, b->state + neq * cidx(b, ii, jj, kk), area, fA + 4 * f1);
+          double *sp = b->specRad + 2 * pidx(b, ii, jj, kk);
+          sp[0] += sr;
+          sp[1] += 0.0;
+          if (!h->cfg.isBlockMatrix) {
+            double *a = b->a + h->asz * pidx(b, ii, jj, kk);
+            a[0] += sr;
+          }
+        }
+      }
+    }
+  }
+}
+
+/* ref: src/procBlock.cpp:6171-6190 (UpdateAuxillaryVariables) */
+static void update_aux(orc_level *h, orc_block *b) {
+  for (int kk = -b->g; kk < b->nk + b->g; ++kk)
+    for (int jj = -b->g; jj < b->nj + b->g; ++jj)
+      for (int ii = -b->g; ii < b->ni + b->g; ++ii) {
+        const int oi = ii < 0 || ii >= b->ni, oj = jj < 0 || jj >= b->nj,
+                  ok = kk < 0 || kk >= b->nk;
+        if (oi + oj + ok == 3) continue; /* corner */
+        b->temperature[cidx(b, ii, jj, kk)] =
+            temperature_of(h, b->state + h->neq * cidx(b, ii, jj, kk));
+      }
+}
+
+/* ------------------------------------------------------------------------ */
+void orc_get_boundary_conditions(orc_level *h) {
+  /* ref: src/gridLevel.cpp:287-319 */
+  for (int bb = 0; bb < h->nblk; ++bb) assign_inviscid_ghosts(h, &h->blk[bb]);
+  /* connection swaps and edge ghosts: not needed by the single-block inviscid
+   * path (edge ghosts are read only by viscous / gradient stencils) */
+}
+
+void orc_calc_residual(orc_level *h) {
+  /* ref: src/procBlock.cpp:6111-6147, src/gridLevel.cpp:372-400 */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    const long nc = (long)b->ni * b->nj * b->nk;
+    memset(b->residual, 0, sizeof(double) * nc * h->neq);
+    memset(b->specRad, 0, sizeof(double) * nc * 2);
+    calc_inv_flux(h, b, 0);
+    calc_inv_flux(h, b, 1);
+    calc_inv_flux(h, b, 2);
+    update_aux(h, b);
+  }
+}
+
+void orc_calc_time_step(orc_level *h, double cfl) {
+  /* ref: src/procBlock.cpp:782-821 */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii) {
+          const long p = pidx(b, ii, jj, kk);
+          if (h->cfg.dtNondim > 0.0) {
+            b->dt[p] = h->cfg.dtNondim;
+          } else {
+            const double *sp = b->specRad + 2 * p;
+            const double mx = sp[0] > sp[1] ? sp[0] : sp[1];
+            b->dt[p] = cfl * (b->vol[cidx(b, ii, jj, kk)] / mx);
+          }
+        }
+  }
+}
+
+/* ref: src/procBlock.cpp:1010-1012 */
+static double sol_delta_n_coeff(const orc_level *h, const orc_block *b, int ii,
+                                int jj, int kk) {
+  return (b->vol[cidx(b, ii, jj, kk)] * (1.0 + h->cfg.zeta)) /
+         (b->dt[pidx(b, ii, jj, kk)] * h->cfg.theta);
+}
+
+void orc_invert_diagonal(orc_level *h) {
+  /* ref: src/linearSolver.cpp:146-188 (scalar diagonal) */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii) {
+          const long p = pidx(b, ii, jj, kk);
+          double diagVolTime = sol_delta_n_coeff(h, b, ii, jj, kk);
+          if (h->cfg.dualTimeCFL > 0.0) {
+            const double *sp = b->specRad + 2 * p;
+            diagVolTime += (sp[0] > sp[1] ? sp[0] : sp[1]) / h->cfg.dualTimeCFL;
+          }
+          for (int q = 0; q < h->asz; ++q) {
+            b->a[h->asz * p + q] *= h->cfg.matrixRelaxation;
+            b->a[h->asz * p + q] += diagVolTime;
+            b->ainv[h->asz * p + q] = 1.0 * (1.0 / b->a[h->asz * p + q]);
+          }
+        }
+  }
+}
+
+/* b = -R/theta + SolDeltaNm1 - SolDeltaMmN; ref: src/procBlock.cpp:1014-1034,
+ * src/linearSolver.cpp:124-129 */
+static void rhs_b(const orc_level *h, const orc_block *b, int ii, int jj,
+                  int kk, double *out) {
+  const int neq = h->neq;
+  const long p = pidx(b, ii, jj, kk);
+  const double thetaInv = 1.0 / h->cfg.theta;
+  double cons[MAXEQ];
+  prim_to_cons(h, b->state + neq * cidx(b, ii, jj, kk), cons);
+  const double coeff = sol_delta_n_coeff(h, b, ii, jj, kk);
+  for (int e = 0; e < neq; ++e) {
+    double nm1 = 0.0;
+    if (h->cfg.isMultilevelTime) {
+      const double c1 = (b->vol[cidx(b, ii, jj, kk)] * h->cfg.zeta) /
+                        (b->dt[p] * h->cfg.theta);
+      nm1 = c1 * (b->consN[neq * p + e] - b->consNm1[neq * p + e]);
+    }
+    const double mmn = coeff * (cons[e] - b->consN[neq * p + e]);
+    out[e] = -thetaInv * b->residual[neq * p + e] + nm1 - mmn;
+  }
+}
+
+static void diag_mult(const orc_level *h, const double *a, const double *v,
+                      double *out) {
+  /* scalar: ref include/fluxJacobian.hpp:67-73 */
+  for (int e = 0; e < h->ns + 4; ++e) out[e] = v[e] * a[0];
+  for (int e = h->ns + 4; e < h->neq; ++e) out[e] = v[e] * a[1];
+}
+
+void orc_initialize_matrix_update(orc_level *h) {
+  /* ref: src/linearSolver.cpp:111-144 */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    const long np = (long)b->NI * b->NJ * b->NK * h->neq;
+    if (!h->cfg.matrixRequiresInit) {
+      memset(b->x, 0, sizeof(double) * np);
+      continue;
+    }
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii) {
+          double rb[MAXEQ];
+          rhs_b(h, b, ii, jj, kk, rb);
+          diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rb,
+                    b->x + h->neq * cidx(b, ii, jj, kk));
+        }
+  }
+}
+
+/* ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal), inviscid */
+static void offdiag_scalar(const orc_level *h, const double *state,
+                           const double *du, const double *fArea, int positive,
+                           double *out) {
+  const int neq = h->neq;
+  double su[MAXEQ], fo[MAXEQ], fn[MAXEQ];
+  update_prim_with_cons(h, state, du, su);
+  physical_flux(h, state, fArea, fo);
+  physical_flux(h, su, fArea, fn);
+  const double sr = inv_face_spec_rad(h, state, fArea);
+  for (int e = 0; e < neq; ++e) {
+    double fc = 0.5 * fArea[3] * (fn[e] - fo[e]);
+    if (e >= h->ns + 4) fc = 0.0;
+    const double srd = (e < h->ns + 4 ? sr : 0.0) * du[e];
+    out[e] = positive ? fc + srd : fc - srd;
+  }
+}
+
+static int is_physical(const orc_block *b, int i, int j, int k) {
+  return i >= 0 && i < b->ni && j >= 0 && j < b->nj && k >= 0 && k < b->nk;
+}
+/* ref: include/boundaryConditions.hpp:287-293, src/boundaryConditions.cpp
+ * GetBCSurface: is the boundary face (i,j,k) of surface type `surf` covered by
+ * a connection BC? */
+static int bc_is_connection(const orc_block *b, int i, int j, int k, int surf) {
+  for (int s = 0; s < b->nsurf; ++s) {
+    const aither_surface *sf = &b->surf[s];
+    if (surface_type(sf) != surf) continue;
+    int in = 0;
+    if (surf <= 2) in = i == sf->imin && j >= sf->jmin && j < sf->jmax &&
+                        k >= sf->kmin && k < sf->kmax;
+    else if (surf <= 4) in = j == sf->jmin && i >= sf->imin && i < sf->imax &&
+                             k >= sf->kmin && k < sf->kmax;
+    else in = k == sf->kmin && i >= sf->imin && i < sf->imax &&
+              j >= sf->jmin && j < sf->jmax;
+    if (in) return sf->type == AITHER_BC_INTERBLOCK ||
+                   sf->type == AITHER_BC_PERIODIC;
+  }
+  return 0;
+}
+
+/* ref: src/procBlock.cpp:1056-1104 (ImplicitLower) */
+static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
+                           int jj, int kk, const double *x, double *L) {
+  const int neq = h->neq;
+  double od[MAXEQ];
+  for (int e = 0; e < neq; ++e) L[e] = 0.0;
+  if (is_physical(b, ii - 1, jj, kk) || bc_is_connection(b, ii, jj, kk, 1)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii - 1, jj, kk),
+                   x + neq * cidx(b, ii - 1, jj, kk),
+                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, od);
+    for (int e = 0; e < neq; ++e) L[e] += od[e];
+  }
+  if (is_physical(b, ii, jj - 1, kk) || bc_is_connection(b, ii, jj, kk, 3)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj - 1, kk),
+                   x + neq * cidx(b, ii, jj - 1, kk),
+                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, od);
+    for (int e = 0; e < neq; ++e) L[e] += od[e];
+  }
+  if (is_physical(b, ii, jj, kk - 1) || bc_is_connection(b, ii, jj, kk, 5)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk - 1),
+                   x + neq * cidx(b, ii, jj, kk - 1),
+                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, od);
+    for (int e = 0; e < neq; ++e) L[e] += od[e];
+  }
+}
+/* ref: src/procBlock.cpp:1106-1170 (ImplicitUpper) */
+static void implicit_upper(const orc_level *h, const orc_block *b, int ii,
+                           int jj, int kk, const double *x, double *U) {
+  const int neq = h->neq;
+  double od[MAXEQ];
+  for (int e = 0; e < neq; ++e) U[e] = 0.0;
+  if (is_physical(b, ii + 1, jj, kk) || bc_is_connection(b, ii + 1, jj, kk, 2)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii + 1, jj, kk),
+                   x + neq * cidx(b, ii + 1, jj, kk),
+                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, od);
+    for (int e = 0; e < neq; ++e) U[e] += od[e];
+  }
+  if (is_physical(b, ii, jj + 1, kk) || bc_is_connection(b, ii, jj + 1, kk, 4)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj + 1, kk),
+                   x + neq * cidx(b, ii, jj + 1, kk),
+                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, od);
+    for (int e = 0; e < neq; ++e) U[e] += od[e];
+  }
+  if (is_physical(b, ii, jj, kk + 1) || bc_is_connection(b, ii, jj, kk + 1, 6)) {
+    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk + 1),
+                   x + neq * cidx(b, ii, jj, kk + 1),
+                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, od);
+    for (int e = 0; e < neq; ++e) U[e] += od[e];
+  }
+}
+
+/* ref: src/linearSolver.cpp:473-507 (dplur::DPLUR) */
+static void dplur_sweep(orc_level *h, orc_block *b) {
+  const int neq = h->neq;
+  const long np = (long)b->NI * b->NJ * b->NK * neq;
+  memcpy(b->xold, b->x, sizeof(double) * np);
+  for (int kk = 0; kk < b->nk; ++kk)
+    for (int jj = 0; jj < b->nj; ++jj)
+      for (int ii = 0; ii < b->ni; ++ii) {
+        double L[MAXEQ], U[MAXEQ], rb[MAXEQ], rhs[MAXEQ];
+        implicit_lower(h, b, ii, jj, kk, b->xold, L);
+        implicit_upper(h, b, ii, jj, kk, b->xold, U);
+        rhs_b(h, b, ii, jj, kk, rb);
+        /* b + forcing(=0) + offDiagonal, offDiagonal = L - U */
+        for (int e = 0; e < neq; ++e) rhs[e] = rb[e] + 0.0 + (L[e] - U[e]);
+        diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs,
+                  b->x + neq * cidx(b, ii, jj, kk));
+      }
+}
+
+/* ref: src/linearSolver.cpp:341-383 (LUSGS_Forward) */
+static void lusgs_forward(orc_level *h, orc_block *b, int sweep) {
+  const int neq = h->neq;
+  const long nc = (long)b->ni * b->nj * b->nk;
+  for (long nn = 0; nn < nc; ++nn) {
+    const int ii = b->order[3 * nn], jj = b->order[3 * nn + 1],
+              kk = b->order[3 * nn + 2];
+    double L[MAXEQ], U[MAXEQ], rb[MAXEQ], rhs[MAXEQ];
+    implicit_lower(h, b, ii, jj, kk, b->x, L);
+    if (sweep > 0 || h->cfg.matrixRequiresInit) {
+      implicit_upper(h, b, ii, jj, kk, b->x, U);
+      for (int e = 0; e < neq; ++e) L[e] -= U[e];
+    }
+    rhs_b(h, b, ii, jj, kk, rb);
+    /* b = -R/theta + forcing + nm1 - mmn ; forcing = 0 */
+    for (int e = 0; e < neq; ++e) rhs[e] = rb[e] + L[e];
+    diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs,
+              b->x + neq * cidx(b, ii, jj, kk));
+  }
+}
+/* ref: src/linearSolver.cpp:385-428 (LUSGS_Backward) */
+static void lusgs_backward(orc_level *h, orc_block *b, int sweep) {
+  const int neq = h->neq;
+  const long nc = (long)b->ni * b->nj * b->nk;
+  for (long nn = nc - 1; nn >= 0; --nn) {
+    const int ii = b->order[3 * nn], jj = b->order[3 * nn + 1],
+              kk = b->order[3 * nn + 2];
+    double L[MAXEQ], U[MAXEQ], rb[MAXEQ], rhs[MAXEQ], tmp[MAXEQ];
+    implicit_upper(h, b, ii, jj, kk, b->x, U);
+    double *xc = b->x + neq * cidx(b, ii, jj, kk);
+    if (sweep > 0 || h->cfg.matrixRequiresInit) {
+      implicit_lower(h, b, ii, jj, kk, b->x, L);
+      rhs_b(h, b, ii, jj, kk, rb);
+      for (int e = 0; e < neq; ++e) rhs[e] = (rb[e] + L[e]) - U[e];
+      diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs, xc);
+    } else {
+      diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), U, tmp);
+      for (int e = 0; e < neq; ++e) xc[e] = xc[e] - tmp[e];
+    }
+  }
+}
+
+/* ref: src/linearSolver.cpp:58-109 (AXmB, Residual): f - (A x - offDiag - b) */
+static void matrix_residual(orc_level *h, orc_block *b) {
+  const int neq = h->neq;
+  for (int kk = 0; kk < b->nk; ++kk)
+    for (int jj = 0; jj < b->nj; ++jj)
+      for (int ii = 0; ii < b->ni; ++ii) {
+        double L[MAXEQ], U[MAXEQ], rb[MAXEQ], ax[MAXEQ];
+        implicit_lower(h, b, ii, jj, kk, b->x, L);
+        implicit_upper(h, b, ii, jj, kk, b->x, U);
+        rhs_b(h, b, ii, jj, kk, rb);
+        diag_mult(h, b->a + h->asz * pidx(b, ii, jj, kk),
+                  b->x + neq * cidx(b, ii, jj, kk), ax);
+        double *mr = b->mresid + neq * pidx(b, ii, jj, kk);
+        for (int e = 0; e < neq; ++e)
+          mr[e] = 0.0 - ((ax[e] - (L[e] - U[e])) - rb[e]);
+      }
+}
+
+double orc_relax(orc_level *h, int sweeps) {
+  /* ref: src/linearSolver.cpp:430-471 (lusgs::Relax), :509-535 (dplur::Relax),
+   * src/mgSolution.cpp:198-206 (norm of the matrix residual) */
+  for (int s = 0; s < sweeps; ++s) {
+    if (h->cfg.solver == AITHER_SOLVER_DPLUR) {
+      for (int bb = 0; bb < h->nblk; ++bb) dplur_sweep(h, &h->blk[bb]);
+    } else {
+      for (int bb = 0; bb < h->nblk; ++bb) lusgs_forward(h, &h->blk[bb], s);
+      for (int bb = 0; bb < h->nblk; ++bb) lusgs_backward(h, &h->blk[bb], s);
+    }
+  }
+  double l2 = 0.0;
+  long total = 0;
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    matrix_residual(h, b);
+    /* the reference sums the squares over the ghost-padded array in storage
+     * order (ghost entries are zero) */
+    double sum = 0.0;
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii)
+          for (int e = 0; e < h->neq; ++e) {
+            const double v = b->mresid[h->neq * pidx(b, ii, jj, kk) + e];
+            sum += v * v;
+          }
+    l2 += sum;
+    total += (long)b->NI * b->NJ * b->NK * h->neq;
+  }
+  return l2 / (double)total;
+}
+
+void orc_update_blocks(orc_level *h, int mm, double *residL2,
+                       aither_linf *linf) {
+  /* ref: src/procBlock.cpp:826-871, :902-915 */
+  (void)mm;
+  const int neq = h->neq;
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii) {
+          double *s = b->state + neq * cidx(b, ii, jj, kk);
+          double ns_[MAXEQ];
+          update_prim_with_cons(h, s, b->x + neq * cidx(b, ii, jj, kk), ns_);
+          memcpy(s, ns_, sizeof(double) * neq);
+          const double *r = b->residual + neq * pidx(b, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) residL2[e] += r[e] * r[e];
+          for (int e = 0; e < neq; ++e) {
+            if (r[e] > linf->linf) {
+              linf->linf = r[e];
+              linf->block = b->parentBlock;
+              linf->i = ii;
+              linf->j = jj;
+              linf->k = kk;
+              linf->eqn = e + 1;
+            }
+          }
+        }
+    if (h->cfg.isMultilevelTime) {
+      /* handled by the caller on the last nonlinear iteration */
+    }
+  }
+}
+
+void orc_reset_diagonal(orc_level *h) {
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    memset(b->a, 0, sizeof(double) * (long)b->ni * b->nj * b->nk * h->asz);
+  }
+}
+
+void orc_store_old_solution(orc_level *h, int iter) {
+  /* ref: src/mgSolution.cpp:103-114, src/procBlock.cpp:1037-1053 */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii)
+          prim_to_cons(h, b->state + h->neq * cidx(b, ii, jj, kk),
+                       b->consN + h->neq * pidx(b, ii, jj, kk));
+    if (h->cfg.isMultilevelTime && iter == 0)
+      memcpy(b->consNm1, b->consN,
+             sizeof(double) * (long)b->ni * b->nj * b->nk * h->neq);
+  }
+}
+
+double orc_iterate(orc_level *h, double cfl, int mm, double *residL2,
+                   aither_linf *linf) {
+  /* ref: src/mgSolution.cpp:246-269, :209-244 */
+  orc_get_boundary_conditions(h);
+  orc_calc_residual(h);
+  orc_calc_time_step(h, cfl);
+  orc_invert_diagonal(h);
+  orc_initialize_matrix_update(h);
+  const double mr = orc_relax(h, h->cfg.matrixSweeps);
+  orc_update_blocks(h, mm, residL2, linf);
+  orc_reset_diagonal(h);
+  return mr;
+}
+
+/* ------------------------------------------------------------------------ */
+static int cmp_plane(const void *a, const void *b) {
+  const int *x = (const int *)a, *y = (const int *)b;
+  const int sx = x[0] + x[1] + x[2], sy = y[0] + y[1] + y[2];
+  if (sx != sy) return sx - sy;
+  /* within a hyperplane the order is immaterial (no intra-plane coupling) */
+  if (x[2] != y[2]) return x[2] - y[2];
+  if (x[1] != y[1]) return x[1] - y[1];
+  return x[0] - y[0];
+}
+
+orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
+                      const aither_block_desc *blocks, int nConnections,
+                      const aither_conn *conns) {
+  orc_level *h = (orc_level *)calloc(1, sizeof(orc_level));
+  h->cfg = *cfg;
+  h->ns = cfg->numSpecies;
+  h->nt = cfg->numTurb;
+  h->neq = h->ns + 4 + h->nt;
+  h->asz = 1 + (h->nt > 0 ? 1 : 0); /* scalar diagonal: {flow, turb} */
+  h->nblk = nBlocks;
+  h->blk = (orc_block *)calloc(nBlocks, sizeof(orc_block));
+  h->nconn = nConnections;
+  h->conn = (aither_conn *)calloc(nConnections > 0 ? nConnections : 1,
+                                  sizeof(aither_conn));
+  if (nConnections > 0)
+    memcpy(h->conn, conns, sizeof(aither_conn) * nConnections);
+  for (int bb = 0; bb < nBlocks; ++bb) {
+    orc_block *b = &h->blk[bb];
+    const aither_block_desc *d = &blocks[bb];
+    b->ni = d->ni;
+    b->nj = d->nj;
+    b->nk = d->nk;
+    b->g = cfg->numGhosts;
+    b->NI = b->ni + 2 * b->g;
+    b->NJ = b->nj + 2 * b->g;
+    b->NK = b->nk + 2 * b->g;
+    b->parentBlock = d->parentBlock;
+    b->nsurf = d->numSurfaces;
+    b->surf = (aither_surface *)malloc(sizeof(aither_surface) * b->nsurf);
+    memcpy(b->surf, d->surfaces, sizeof(aither_surface) * b->nsurf);
+    const long np = (long)b->NI * b->NJ * b->NK;
+    const long nc = (long)b->ni * b->nj * b->nk;
+    b->state = (double *)malloc(sizeof(double) * np * h->neq);
+    memcpy(b->state, d->state, sizeof(double) * np * h->neq);
+    b->residual = (double *)calloc(nc * h->neq, sizeof(double));
+    b->specRad = (double *)calloc(nc * 2, sizeof(double));
+    b->dt = (double *)calloc(nc, sizeof(double));
+    b->a = (double *)calloc(nc * h->asz, sizeof(double));
+    b->ainv = (double *)calloc(nc * h->asz, sizeof(double));
+    b->x = (double *)calloc(np * h->neq, sizeof(double));
+    b->xold = (double *)calloc(np * h->neq, sizeof(double));
+    b->consN = (double *)calloc(nc * h->neq, sizeof(double));
+    b->consNm1 = (double *)calloc(nc * h->neq, sizeof(double));
+    b->mresid = (double *)calloc(nc * h->neq, sizeof(double));
+    b->temperature = (double *)calloc(np, sizeof(double));
+    b->vol = d->vol;
+    b->fAI = d->fAreaI;
+    b->fAJ = d->fAreaJ;
+    b->fAK = d->fAreaK;
+    b->center = d->center;
+    b->cwI = d->cellWidthI;
+    b->cwJ = d->cellWidthJ;
+    b->cwK = d->cellWidthK;
+    b->wallDist = d->wallDist;
+    /* ref: src/utility.cpp:377-398 (HyperplaneReorder) */
+    b->order = (int *)malloc(sizeof(int) * 3 * nc);
+    long q = 0;
+    for (int kk = 0; kk < b->nk; ++kk)
+      for (int jj = 0; jj < b->nj; ++jj)
+        for (int ii = 0; ii < b->ni; ++ii) {
+          b->order[3 * q] = ii;
+          b->order[3 * q + 1] = jj;
+          b->order[3 * q + 2] = kk;
+          ++q;
+        }
+    qsort(b->order, nc, 3 * sizeof(int), cmp_plane);
+  }
+  return h;
+}
+
+void orc_destroy(orc_level *h) {
+  if (!h) return;
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    free(b->surf); free(b->state); free(b->residual); free(b->specRad);
+    free(b->dt); free(b->a); free(b->ainv); free(b->x); free(b->xold);
+    free(b->consN); free(b->consNm1); free(b->mresid); free(b->temperature);
+    free(b->order);
+  }
+  free(h->blk);
+  free(h->conn);
+  free(h);
+}
+
+long long orc_field_size(orc_level *h, int blk, int field) {
+  const orc_block *b = &h->blk[blk];
+  const long long np = (long long)b->NI * b->NJ * b->NK;
+  const long long nc = (long long)b->ni * b->nj * b->nk;
+  switch (field) {
+    case AITHER_FIELD_STATE: return np * h->neq;
+    case AITHER_FIELD_RESIDUAL: return nc * h->neq;
+    case AITHER_FIELD_SPEC_RADIUS: return nc * 2;
+    case AITHER_FIELD_DT: return nc;
+    case AITHER_FIELD_DIAG: return nc * h->asz;
+    case AITHER_FIELD_DIAG_INV: return nc * h->asz;
+    case AITHER_FIELD_UPDATE: return np * h->neq;
+    case AITHER_FIELD_CONS_N: return nc * h->neq;
+    case AITHER_FIELD_MATRIX_RESID: return nc * h->neq;
+    case AITHER_FIELD_TEMPERATURE: return np;
+    case AITHER_FIELD_CONS_NM1: return nc * h->neq;
+  }
+  return 0;
+}
+
+void orc_get_field(orc_level *h, int blk, int field, double *dst) {
+  const orc_block *b = &h->blk[blk];
+  const double *src = NULL;
+  switch (field) {
+    case AITHER_FIELD_STATE: src = b->state; break;
+    case AITHER_FIELD_RESIDUAL: src = b->residual; break;
+    case AITHER_FIELD_SPEC_RADIUS: src = b->specRad; break;
+    case AITHER_FIELD_DT: src = b->dt; break;
+    case AITHER_FIELD_DIAG: src = b->a; break;
+    case AITHER_FIELD_DIAG_INV: src = b->ainv; break;
+    case AITHER_FIELD_UPDATE: src = b->x; break;
+    case AITHER_FIELD_CONS_N: src = b->consN; break;
+    case AITHER_FIELD_MATRIX_RESID: src = b->mresid; break;
+    case AITHER_FIELD_TEMPERATURE: src = b->temperature; break;
+    case AITHER_FIELD_CONS_NM1: src = b->consNm1; break;
+  }
+  if (src) memcpy(dst, src, sizeof(double) * orc_field_size(h, blk, field));
+}
+
+void orc_set_state(orc_level *h, int blk, const double *stateAoS) {
+  memcpy(h->blk[blk].state, stateAoS,
+         sizeof(double) * orc_field_size(h, blk, AITHER_FIELD_STATE));
+}
+
+/* ------------------------------------------------------------------------ */
+/* point-function exports                                                     */
+static void level_from_cfg(orc_level *h, const aither_cfg *cfg) {
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->ns = cfg->numSpecies;
+  h->nt = cfg->numTurb;
+  h->neq = h->ns + 4 + h->nt;
+  h->asz = 1 + (h->nt > 0 ? 1 : 0);
+}
+void orc_inviscid_flux(const aither_cfg *cfg, const double *left,
+                       const double *right, const double nrm[3], double *flux) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  inviscid_flux(&h, left, right, nrm, flux);
+}
+void orc_ghost_state(const aither_cfg *cfg, const double *interior, int bcType,
+                     const double areaUnit[3], int surfType, int tag, int layer,
+                     double *ghost) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, ghost);
+}
+void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
+                        const double *duNb, const double fArea[4], int positive,
+                        double *out) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  offdiag_scalar(&h, stateNb, duNb, fArea, positive, out);
+}

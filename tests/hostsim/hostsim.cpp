@@ -1,0 +1,58 @@
+// hostsim.cpp -- TEST-ONLY host build of the device point functions in
+// aither_b200/csrc/physics.cuh, so they can be checked against the oracle on a machine without a
+// GPU. Never part of libaither_b200.so; built on demand by tests/test_physics_host.py.
+#include "../../aither_b200/csrc/physics.cuh"
+
+using namespace aither;
+
+static Gas GasFromCfg(const aither_cfg *c) {
+  Gas g;
+  for (int s = 0; s < AITHER_MAX_SPECIES; ++s) {
+    g.R[s] = c->gasConstant[s];
+    g.n[s] = c->n[s];
+    g.hf[s] = c->hf[s];
+  }
+  return g;
+}
+static const aither_bc_state *Find(const aither_cfg *c, int tag) {
+  for (int b = 0; b < c->numBCStates; ++b)
+    if (c->bcStates[b].tag == tag) return &c->bcStates[b];
+  return &c->bcStates[0];
+}
+
+extern "C" {
+void hs_muscl(const double *u2, const double *u1, const double *d1, double kappa, int lim,
+              double w2, double w1, double wd, double *face) {
+  if (lim == 0) Muscl<5, 0>(u2, u1, d1, kappa, w2, w1, wd, face);
+  else if (lim == 1) Muscl<5, 1>(u2, u1, d1, kappa, w2, w1, wd, face);
+  else Muscl<5, 2>(u2, u1, d1, kappa, w2, w1, wd, face);
+}
+void hs_weno(const double *y, const double *w, int n, int wenoz, double *face) {
+  // y: 5 x n row-major (stencil-major)
+  const WenoGeom g = WenoSetup(w);
+  for (int e = 0; e < n; ++e) {
+    face[e] = wenoz ? Weno1<true>(g, y[e], y[n + e], y[2 * n + e], y[3 * n + e], y[4 * n + e])
+                    : Weno1<false>(g, y[e], y[n + e], y[2 * n + e], y[3 * n + e], y[4 * n + e]);
+  }
+}
+void hs_inviscid_flux(const aither_cfg *c, const double *l, const double *r, const double *n,
+                      double *f) {
+  const Gas g = GasFromCfg(c);
+  if (c->invFlux == AITHER_FLUX_ROE) RoeFlux<1, 0>(g, l, r, n, f);
+  else AusmFlux<1, 0>(g, l, r, n, f);
+}
+void hs_ghost_state(const aither_cfg *c, const double *interior, int bcType, const double *area,
+                    int surf, int tag, int layer, double *ghost) {
+  const Gas g = GasFromCfg(c);
+  GhostState<1, 0>(g, interior, bcType, area, surf, *Find(c, tag), layer, ghost);
+}
+void hs_offdiag_scalar(const aither_cfg *c, const double *s, const double *du, const double *fa,
+                       int positive, double *out) {
+  const Gas g = GasFromCfg(c);
+  OffDiagScalar<1, 0>(g, s, du, fa, positive != 0, out);
+}
+void hs_update_prim(const aither_cfg *c, const double *s, const double *du, double *out) {
+  const Gas g = GasFromCfg(c);
+  UpdatePrimWithCons<1, 0>(g, s, du, out);
+}
+}

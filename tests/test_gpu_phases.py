@@ -1,0 +1,124 @@
+"""GPU hot path vs the CPU oracle, phase by phase, through the C ABI (-m gpu).
+
+Seeded synthetic blocks at sizes the oracle finishes in seconds. Bars: per-cell residual relative
+error <= 1e-12 (relative to the largest residual magnitude of that equation in the block; residuals
+are sums of cancelling fluxes, so a per-cell denominator is ill-conditioned where R ~ 0);
+everything else to the same bar against the field's own scale.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from aither_b200 import ctypes_abi as abi
+from aither_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+RES_TOL = 1e-12
+
+
+def rel(a, b):
+    """max |a-b| per trailing component, relative to that component's max |b|."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    ax = tuple(range(a.ndim - 1))
+    scale = np.abs(b).max(axis=ax)
+    scale = np.where(scale > 0, scale, 1.0)
+    return (np.abs(a - b).max(axis=ax) / scale).max()
+
+
+def non_edge_mask(shape, g):
+    K, J, I = shape
+    kk, jj, ii = np.meshgrid(np.arange(K), np.arange(J), np.arange(I), indexing="ij")
+    out = (((kk < g) | (kk >= K - g)).astype(int) + ((jj < g) | (jj >= J - g)).astype(int) +
+           ((ii < g) | (ii >= I - g)).astype(int))
+    return out <= 1
+
+
+CASES = [
+    dict(solver="dplur", sweeps=4, limiter="none", flux="roe", recon="thirdOrder"),
+    dict(solver="dplur", sweeps=2, limiter="vanAlbada", flux="roe", recon="thirdOrder"),
+    dict(solver="dplur", sweeps=1, limiter="minmod", flux="ausm", recon="upwind"),
+    dict(solver="lusgs", sweeps=1, limiter="none", flux="roe", recon="thirdOrder"),
+    dict(solver="lusgs", sweeps=2, limiter="vanAlbada", flux="ausm", recon="fromm"),
+    dict(solver="dplur", sweeps=2, limiter="none", flux="roe", recon="constant"),
+    dict(solver="dplur", sweeps=2, limiter="none", flux="roe", recon="weno"),
+    dict(solver="lusgs", sweeps=1, limiter="none", flux="ausm", recon="wenoZ"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(v) for v in c.values()))
+@pytest.mark.parametrize("dims", [(33, 9, 7), (16, 12, 10)], ids=lambda d: "x".join(map(str, d)))
+def test_phases_match_oracle(case, dims):
+    import aither_b200
+    ni, nj, nk = dims
+    prob = synthetic.box_problem(ni, nj, nk, seed=3, amplitude=0.02, **case)
+    g = prob.cfg.numGhosts
+    gpu = aither_b200.GridLevel(prob)
+    ref = oracle.OracleLevel(prob)
+    cfl = 25.0
+    for lvl in (gpu, ref):
+        lvl.store_old_solution(0)
+        lvl.get_boundary_conditions()
+    sg, sr = gpu.field(0, abi.FIELD_STATE), ref.field(0, abi.FIELD_STATE)
+    m = non_edge_mask(sg.shape[:3], g)
+    assert rel(sg[m], sr[m]) <= 1e-13
+    for lvl in (gpu, ref):
+        lvl.calc_residual()
+    assert rel(gpu.field(0, abi.FIELD_RESIDUAL), ref.field(0, abi.FIELD_RESIDUAL)) <= RES_TOL
+    assert rel(gpu.field(0, abi.FIELD_SPEC_RADIUS)[..., :1],
+               ref.field(0, abi.FIELD_SPEC_RADIUS)[..., :1]) <= 1e-13
+    for lvl in (gpu, ref):
+        lvl.calc_time_step(cfl)
+        lvl.invert_diagonal()
+        lvl.initialize_matrix_update()
+    for f in (abi.FIELD_DT, abi.FIELD_DIAG, abi.FIELD_DIAG_INV):
+        assert rel(gpu.field(0, f), ref.field(0, f)) <= 1e-13
+    assert rel(gpu.field(0, abi.FIELD_UPDATE), ref.field(0, abi.FIELD_UPDATE)) <= 1e-12
+    mg, mr = gpu.relax(), ref.relax()
+    xg, xr = gpu.field(0, abi.FIELD_UPDATE), ref.field(0, abi.FIELD_UPDATE)
+    assert rel(xg, xr) <= 1e-11
+    assert rel(gpu.field(0, abi.FIELD_MATRIX_RESID), ref.field(0, abi.FIELD_MATRIX_RESID)) <= 1e-9
+    assert abs(mg - mr) <= 1e-9 * abs(mr)
+    (l2g, linfg), (l2r, linfr) = gpu.update_blocks(), ref.update_blocks()
+    assert np.all(np.abs(l2g - l2r) <= 1e-12 * np.abs(l2r))
+    assert abs(linfg.linf - linfr.linf) <= 1e-12 * abs(linfr.linf)
+    assert (linfg.i, linfg.j, linfg.k, linfg.eqn) == (linfr.i, linfr.j, linfr.k, linfr.eqn)
+    sg, sr = gpu.field(0, abi.FIELD_STATE), ref.field(0, abi.FIELD_STATE)
+    assert rel(sg[g:-g, g:-g, g:-g], sr[g:-g, g:-g, g:-g]) <= 1e-12
+    gpu.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("solver,sweeps", [("dplur", 4), ("lusgs", 1)])
+def test_history_matches_oracle(solver, sweeps):
+    """L2 residual history over 30 iterations within 1e-9 (north_star tolerance)."""
+    import aither_b200
+    prob = synthetic.box_problem(24, 16, 12, seed=5, solver=solver, sweeps=sweeps)
+    gpu = aither_b200.GridLevel(prob)
+    ref = oracle.OracleLevel(prob)
+    for it in range(30):
+        gpu.store_old_solution(it)
+        ref.store_old_solution(it)
+        l2g, _, mrg = gpu.iterate(50.0)
+        l2r, _, mrr = ref.iterate(50.0)
+        assert np.all(np.abs(l2g - l2r) <= 1e-9 * np.abs(l2r)), (it, l2g, l2r)
+        assert abs(mrg - mrr) <= 1e-9 * abs(mrr)
+    gpu.close()
+    ref.close()
+
+
+def test_run_equals_iterate():
+    """aither_gpu_run (no host sync between iterations) gives the same history as iterate()."""
+    import aither_b200
+    prob = synthetic.box_problem(20, 12, 8, seed=7)
+    a = aither_b200.GridLevel(prob)
+    b = aither_b200.GridLevel(prob)
+    hist = a.run(6, 40.0)
+    for it in range(6):
+        b.store_old_solution(it)
+        l2, _, mr = b.iterate(40.0)
+        assert np.array_equal(hist[it, :-1], l2)
+        assert hist[it, -1] == mr
+    a.close()
+    b.close()
