@@ -77,9 +77,30 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         ""])
 
 
-def write_case(case_dir, name, ni, nj, nk, **kw):
+def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air"):
+    """Initial-condition cloud file (reference src/utility.cpp:513-520: `numberOfPoints`, species
+    line, then `x y z rho u v w p tke omega mf...` per point), one point per cell centroid, with
+    seed-fixed +-amplitude noise on rho, u, v, w, p. The reference assigns each cell the state of
+    its nearest cloud point."""
+    x = np.asarray(nodes)
+    cen = 0.125 * (x[:-1, :-1, :-1] + x[:-1, :-1, 1:] + x[:-1, 1:, :-1] + x[:-1, 1:, 1:] +
+                   x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:]).reshape(-1, 3)
+    rng = np.random.default_rng(seed)
+    base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
+    vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((cen.shape[0], 5)) - 1.0))
+    with open(path, "w") as f:
+        f.write("%d\n%s\n" % (cen.shape[0], species))
+        for c, v in zip(cen, vals):
+            f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
+
+
+def write_case(case_dir, name, ni, nj, nk, perturb=None, **kw):
+    """Write `<name>.xyz` + `<name>.inp` (+ `ic.dat` when perturb=(seed, amplitude))."""
     os.makedirs(case_dir, exist_ok=True)
     write_plot3d(os.path.join(case_dir, name + ".xyz"), [box_nodes(ni, nj, nk)])
+    if perturb is not None:
+        write_cloud(os.path.join(case_dir, "ic.dat"), box_nodes(ni, nj, nk), *perturb)
+        kw["ic_file"] = "ic.dat"
     with open(os.path.join(case_dir, name + ".inp"), "w") as f:
         f.write(inp_text(name, ni, nj, nk, **kw))
     return name + ".inp"

@@ -1,0 +1,80 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference (oracle/_ref/aither_dump).
+
+TEST INFRASTRUCTURE ONLY. Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py [case ...]
+
+Each fixture is one compressed .npz holding, for a small case, the reference's set-up (config,
+grid metrics, initial state, connections), its arrays after every phase of selected iterations
+(`--full`), and its full-precision residual history. The tests (tests/test_oracle_pinned.py on
+CPU, tests/test_gpu_golden.py on the GPU box) read only these files: /root/reference does not
+exist on the GPU box.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import refcase  # noqa: E402
+from aither_b200 import synthetic  # noqa: E402
+
+REF_CASES = "/root/reference/testCases"
+
+# name -> (how to stage, iterations, iterations dumped phase by phase)
+CASES = {
+    # reference regression case (testCases/regressionTests.py:233-249): Euler, Roe, MUSCL k=1/3,
+    # LU-SGS x1, slipWall + stagnationInlet + pressureOutlet, 33x2x41 nodes
+    "subsonicCylinder": dict(src="subsonicCylinder", iters=100, full=(0, 50), edits={}),
+    # supersonic wedge: supersonicInflow / supersonicOutflow BCs, vanAlbada; the shipped .inp is
+    # explicit Euler, which is not on the hot path -> edited to implicit Euler + DPLUR x3
+    "supersonicWedge": dict(src="supersonicWedge", iters=30, full=(0, 10),
+                            edits={"timeIntegration": "implicitEuler", "cflStart": "5.0",
+                                   "cflMax": "5.0", "matrixSolver": "dplur",
+                                   "matrixSweeps": "3", "matrixRelaxation": "1.0"}),
+    # synthetic box of SURVEY 8d (the bench workload, small): DPLUR x4
+    "box_dplur": dict(synthetic=dict(ni=14, nj=10, nk=8, solver="dplur", sweeps=4), iters=30,
+                      full=(0, 5)),
+    "box_lusgs_va": dict(synthetic=dict(ni=12, nj=9, nk=7, solver="lusgs", sweeps=2,
+                                        limiter="vanAlbada", flux="ausm"), iters=20, full=(0, 5)),
+    "box_weno": dict(synthetic=dict(ni=12, nj=8, nk=8, solver="dplur", sweeps=2, recon="weno"),
+                     iters=12, full=(0, 4)),
+    # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
+    "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
+}
+
+DROP = ("nodes", "fCenterI", "fCenterJ", "fCenterK")
+
+
+def generate(name):
+    spec = CASES[name]
+    with tempfile.TemporaryDirectory() as tmp:
+        if "synthetic" in spec:
+            kw = dict(spec["synthetic"])
+            ni, nj, nk = kw.pop("ni"), kw.pop("nj"), kw.pop("nk")
+            # perturbed initial state: a uniform start leaves cells that are equal to the last
+            # bit, where the reference's eps-regularised MUSCL ratio (reconstruction.hpp:128-153)
+            # is discontinuous and a 1-ulp difference moves the residual by 1e-6
+            inp = synthetic.write_case(tmp, name, ni, nj, nk, iterations=spec["iters"],
+                                       perturb=(11, 0.01), **kw)
+        else:
+            inp = refcase.stage_case(os.path.join(REF_CASES, spec["src"]), tmp, spec["edits"],
+                                     iterations=spec["iters"])
+        d = refcase.run_harness(tmp, inp, spec["iters"], full=spec["full"], geom=True)
+    out = {k: np.asarray(v) for k, v in d.items()
+           if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time"}
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%s: %d records, %.1f kB" % (name, len(out), os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    if not refcase.have_harness():
+        sys.exit("oracle/_ref/aither_dump is not built (make -C oracle ref)")
+    for nm in (sys.argv[1:] or list(CASES)):
+        generate(nm)

@@ -1,0 +1,36 @@
+"""GPU hot path (through the C ABI) against the committed golden fixtures of the UNMODIFIED
+reference (tests/golden/*.npz) -- no oracle in between. north_star bars: per-cell residual
+relative error <= 1e-12 after one evaluation; L2 residual history within 1e-9 relative over 100
+iterations. /root/reference is not needed at run time.
+"""
+import pytest
+
+import goldencheck as gc
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-13, dt=1e-13, diag=1e-13, x0=1e-12,
+           x=1e-11, matrixResid=1e-9, state=1e-12, l2=1e-12)
+
+SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno"]
+
+
+def make_gpu_level(prob):
+    import aither_b200
+    return aither_b200.GridLevel(prob)
+
+
+@pytest.mark.parametrize("name", SINGLE_BLOCK)
+def test_gpu_phases_match_reference(name):
+    d = gc.load(name)
+    for it in gc.full_iterations(d):
+        gc.check_phases(make_gpu_level, d, it, TOL)
+
+
+@pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30),
+                                        ("box_dplur", 30), ("box_lusgs_va", 20),
+                                        ("box_weno", 12)])
+def test_gpu_history_matches_reference(name, iters):
+    d = gc.load(name)
+    worst = gc.check_history(make_gpu_level, d, iters, 1e-9, name=name)
+    assert worst <= 1e-9
