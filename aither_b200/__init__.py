@@ -29,6 +29,7 @@ ABI_SYMBOLS = (
     "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
     "aither_gpu_destroy", "aither_gpu_last_error", "aither_gpu_version",
+    "aither_gpu_alloc_host", "aither_gpu_free_host",
 )
 
 
@@ -74,6 +75,8 @@ def load_library():
     L.aither_gpu_kernel_family_name.argtypes = [C.c_int]
     L.aither_gpu_kernel_family_name.restype = C.c_char_p
     L.aither_gpu_last_error.restype = C.c_char_p
+    L.aither_gpu_alloc_host.argtypes = [C.c_longlong, C.POINTER(vp)]
+    L.aither_gpu_free_host.argtypes = [vp]
     L.aither_gpu_version.restype = C.c_char_p
     _LIB = L
     return L
@@ -81,6 +84,18 @@ def load_library():
 
 def _ptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pinned_array(shape):
+    """float64 numpy array in page-locked host memory (aither_gpu_alloc_host); keeps itself alive
+    through the array's base object and is freed with the library when the process exits."""
+    L = load_library()
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    if L.aither_gpu_alloc_host(n * 8, C.byref(p)) != 0:
+        raise AitherGpuError(L.aither_gpu_last_error().decode())
+    buf = (C.c_double * n).from_address(p.value)
+    return np.ctypeslib.as_array(buf).reshape(shape)
 
 
 class GridLevel:

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -18,6 +19,7 @@
 #include "../../include/aither_gpu.h"
 #include "halo.cuh"
 #include "kernels.cuh"
+#include "march.cuh"
 
 using namespace aither;
 
@@ -62,6 +64,10 @@ struct HostBlock {
   dim3 cellGrid, cellBlock;       // cell-parallel kernels (32 x 8 threads)
   dim3 resGrid, resBlock;
   int nCellBlocks = 0;
+  // plane-marching kernels (march.cuh)
+  dim3 marchGrid;
+  int kChunk = 1;
+  int nMarchBlocks = 0;
 };
 
 }  // namespace
@@ -87,6 +93,7 @@ struct aither_gpu {
   size_t stageBytes = 0;
   long long launches = 0;
   bool keepMatrixResid = false;
+  bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
   // timing
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   bool profile = false;
@@ -197,15 +204,31 @@ bool Supported(const aither_cfg &c, std::string *why) {
   return true;
 }
 
+template <int NS, int NT, int RC, int LM, int FX>
+void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar) {
+  if (h->legacyKernels) {
+    ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(
+        hb.dev, h->params, implicitScalar);
+    return;
+  }
+  using S = ResSmem<NS, NT, RC>;
+  auto kern = ResidualMarchKernel<NS, NT, RC, LM, FX>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(S::bytes));
+    configured = true;
+  }
+  kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), S::bytes, h->stream>>>(hb.dev, h->params, hb.kChunk,
+                                                                 implicitScalar);
+}
+
 template <int NS, int NT>
 int LaunchResidual(aither_gpu *h, HostBlock &hb) {
   const aither_cfg &c = h->cfg;
   const int implicitScalar = 1;
   ScopedLaunch sl(h, kFamResidual);
-#define RES(RC, LM, FX)                                                                  \
-  ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(hb.dev, \
-                                                                               h->params, \
-                                                                               implicitScalar)
+#define RES(RC, LM, FX) LaunchResidualOne<NS, NT, RC, LM, FX>(h, hb, implicitScalar)
 #define RES_FLUX(RC, LM)                         \
   do {                                           \
     if (c.invFlux == AITHER_FLUX_ROE) RES(RC, LM, AITHER_FLUX_ROE); \
@@ -223,6 +246,21 @@ int LaunchResidual(aither_gpu *h, HostBlock &hb) {
 #undef RES
 #undef RES_FLUX
   return 0;
+}
+
+template <int NS, int NT, int MODE>
+void LaunchImplicitMarch(aither_gpu *h, HostBlock &hb, const double *xin, double *xout,
+                         int storeField) {
+  constexpr size_t bytes = sizeof(double) * 2 * Ingr<NS, NT>::n * kIPC;
+  auto kern = ImplicitMarchKernel<NS, NT, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(bytes));
+    configured = true;
+  }
+  kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), bytes, h->stream>>>(hb.dev, h->params, xin, xout,
+                                                             hb.kChunk, h->dPartials, storeField);
 }
 
 int ZeroResult(aither_gpu *h, int slot) {
@@ -293,8 +331,12 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
       for (auto &hb : h->blocks) {
         {
           ScopedLaunch sl(h, kFamDplur);
-          DplurKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
-                                                                          hb.dev.x, hb.dev.xalt);
+          if (h->legacyKernels) {
+            DplurKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+                                                                            hb.dev.x, hb.dev.xalt);
+          } else {
+            LaunchImplicitMarch<1, 0, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
+          }
         }
         std::swap(hb.dev.x, hb.dev.xalt);
       }
@@ -325,15 +367,21 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
   if (SwapUpdate(h)) return 1;
   // matrix residual and its norm (ref: src/linearSolver.cpp:92-109, src/mgSolution.cpp:198-206)
   for (auto &hb : h->blocks) {
+    int nPartials = hb.nCellBlocks;
     {
       ScopedLaunch sl(h, kFamAxmb);
-      AxmbKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, h->dPartials,
-                                                                     h->keepMatrixResid ? 1 : 0);
+      if (h->legacyKernels) {
+        AxmbKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
+            hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
+      } else {
+        LaunchImplicitMarch<1, 0, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+        nPartials = hb.nMarchBlocks;
+      }
     }
     {
       ScopedLaunch sl(h, kFamReduce);
-      FinalizeSumKernel<<<1, 32, 0, h->stream>>>(h->dPartials, hb.nCellBlocks, 1,
-                                                 &h->dResults[slot].matrixSumSq);
+      FinalizeSumKernel<<<1, kFinalThreads, 0, h->stream>>>(h->dPartials, nPartials, 1,
+                                                            &h->dResults[slot].matrixSumSq);
     }
   }
   CK(cudaGetLastError());
@@ -350,13 +398,13 @@ int PhaseUpdate(aither_gpu *h, int slot) {
     }
     {
       ScopedLaunch sl(h, kFamReduce);
-      FinalizeSumKernel<<<h->neq, 32, 0, h->stream>>>(h->dPartials, hb.nCellBlocks, h->neq,
-                                                      h->dResults[slot].l2);
+      FinalizeSumKernel<<<h->neq, kFinalThreads, 0, h->stream>>>(h->dPartials, hb.nCellBlocks,
+                                                                 h->neq, h->dResults[slot].l2);
     }
     {
       ScopedLaunch sl(h, kFamReduce);
-      FinalizeLinfKernel<<<1, 32, 0, h->stream>>>(h->dLinfPartials, hb.nCellBlocks, hb.dev, h->neq,
-                                                  &h->dResults[slot]);
+      FinalizeLinfKernel<<<1, kFinalThreads, 0, h->stream>>>(h->dLinfPartials, hb.nCellBlocks,
+                                                             hb.dev, h->neq, &h->dResults[slot]);
     }
   }
   CK(cudaGetLastError());
@@ -454,6 +502,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.isMultilevelTime = cfg->isMultilevelTime;
   p.matrixRequiresInit = cfg->matrixRequiresInit;
   p.wenoZ = cfg->recon == AITHER_RECON_WENOZ;
+  GasFinalize(&p.gas);
+  {
+    const char *kv = getenv("AITHER_B200_KERNELS");
+    h->legacyKernels = kv != nullptr && std::string(kv) == "legacy";
+  }
 #define CKH(call)        \
   do {                   \
     if ((call)) {        \
@@ -502,7 +555,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.paddedCells = static_cast<long long>(d.ni + 2 * g) * (d.nj + 2 * g) * (d.nk + 2 * g);
     // field budget (doubles per cell): state, consN, [consNm1], resid, rhs, x, xalt, [mres],
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
-    const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 12 + 3;
+    const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
+                        12 + 3;
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
     CKC(cudaMemsetAsync(hb.alloc, 0, hb.allocBytes, h->stream));
@@ -522,6 +576,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     b.dinv = take(1);
     b.vol = take(1);
     for (int q = 0; q < 3; ++q) b.cw[q] = take(1);
+    for (int q = 0; q < 3; ++q) b.mc[q] = take(2);
     for (int q = 0; q < 3; ++q) b.fA[q] = take(4);
     b.center = take(3);
 
@@ -541,6 +596,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     CKH(UploadAos(h, hb, d.cellWidthJ, NI, NJ, NK, 1, b.cw[1], -g, -g, -g));
     CKH(UploadAos(h, hb, d.cellWidthK, NI, NJ, NK, 1, b.cw[2], -g, -g, -g));
     if (d.center) CKH(UploadAos(h, hb, d.center, NI, NJ, NK, 3, b.center, -g, -g, -g));
+    for (int q = 0; q < 3; ++q) {
+      ScopedLaunch sl(h, kFamLayout);
+      MusclCoefKernel<<<148 * 8, 256, 0, h->stream>>>(b, q);
+    }
+    CKC(cudaGetLastError());
 
     // boundary surfaces
     hb.surfaces.assign(d.surfaces, d.surfaces + d.numSurfaces);
@@ -614,6 +674,18 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.resBlock = dim3(kTI, kTJ, kTK);
     hb.resGrid = dim3((d.ni + 1 + kTI - 1) / kTI, (d.nj + 1 + kTJ - 1) / kTJ,
                       (d.nk + 1 + kTK - 1) / kTK);
+    {
+      // k-chunks of the marching kernels: enough blocks to fill 148 SMs x 2 resident blocks a few
+      // times over, but chunks of at least 8 planes so the per-chunk prologue stays small
+      const int cols = ((d.ni + kMI - 1) / kMI) * ((d.nj + kMJ - 1) / kMJ);
+      int nChunks = std::max(1, (148 * 2 * 4 + cols - 1) / cols);
+      int chunk = std::max(std::min(8, d.nk), (d.nk + nChunks - 1) / nChunks);
+      chunk = std::min(chunk, 64);
+      nChunks = (d.nk + chunk - 1) / chunk;
+      hb.kChunk = chunk;
+      hb.marchGrid = dim3((d.ni + kMI - 1) / kMI, (d.nj + kMJ - 1) / kMJ, nChunks);
+      hb.nMarchBlocks = hb.marchGrid.x * hb.marchGrid.y * hb.marchGrid.z;
+    }
     maxCellBlocks = std::max<size_t>(maxCellBlocks, hb.nCellBlocks);
   }
   h->partialsCap = maxCellBlocks;
@@ -827,6 +899,16 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   const int g = b.g;
   return UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g,
                    -g, -g);
+}
+
+int aither_gpu_alloc_host(long long bytes, void **out) {
+  if (!out || bytes <= 0) return Fail("aither_gpu_alloc_host: bad arguments");
+  CK(cudaMallocHost(out, static_cast<size_t>(bytes)));
+  return 0;
+}
+int aither_gpu_free_host(void *p) {
+  if (p) CK(cudaFreeHost(p));
+  return 0;
 }
 
 int aither_gpu_synchronize(aither_gpu *h) {

@@ -627,27 +627,44 @@ __global__ void __launch_bounds__(256)
 
 // final pass over the per-block partials of one procBlock, accumulating into the iteration's
 // result record in a fixed order (deterministic run to run)
-__global__ void FinalizeSumKernel(const double *__restrict__ partials, int nPartials, int nv,
-                                  double *__restrict__ out) {
-  // one warp per value; each lane strides the partial list, then a shuffle tree
+constexpr int kFinalThreads = 512;
+__global__ void __launch_bounds__(kFinalThreads)
+    FinalizeSumKernel(const double *__restrict__ partials, int nPartials, int nv,
+                      double *__restrict__ out) {
+  // one block per value; each thread strides the partial list, then a fixed shuffle/shared tree
+  __shared__ double sh[kFinalThreads / 32];
   const int v = blockIdx.x;
   double acc = 0.0;
-  for (int q = threadIdx.x; q < nPartials; q += 32) acc += partials[static_cast<long long>(q) * nv + v];
+  for (int q = threadIdx.x; q < nPartials; q += kFinalThreads)
+    acc += partials[static_cast<long long>(q) * nv + v];
   acc = WarpSum(acc);
-  if (threadIdx.x == 0) out[v] += acc;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double w = threadIdx.x < kFinalThreads / 32 ? sh[threadIdx.x] : 0.0;
+    w = WarpSum(w);
+    if (threadIdx.x == 0) out[v] += w;
+  }
 }
-__global__ void FinalizeLinfKernel(const LinfCand *__restrict__ cands, int n, BlockDev b, int neq,
-                                   IterResult *__restrict__ res) {
+__global__ void __launch_bounds__(kFinalThreads)
+    FinalizeLinfKernel(const LinfCand *__restrict__ cands, int n, BlockDev b, int neq,
+                       IterResult *__restrict__ res) {
+  __shared__ LinfCand sh[kFinalThreads / 32];
   LinfCand best;
   best.v = 0.0;
   best.key = 0x7fffffffffffffffLL;
-  for (int q = threadIdx.x; q < n; q += 32) best = LinfBetter(best, cands[q]);
+  for (int q = threadIdx.x; q < n; q += kFinalThreads) best = LinfBetter(best, cands[q]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     LinfCand c;
     c.v = __shfl_down_sync(0xffffffffu, best.v, o);
     c.key = __shfl_down_sync(0xffffffffu, best.key, o);
     best = LinfBetter(best, c);
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kFinalThreads / 32; ++w) best = LinfBetter(best, sh[w]);
   }
   if (threadIdx.x == 0 && best.v > res->linf) {  // strict: earlier blocks win ties
     long long key = best.key;

@@ -37,6 +37,7 @@ struct BlockDev {
   double *dinv;      // asz   D^-1
   double *vol;       // 1
   double *cw[3];     // 1     cell widths along i, j, k
+  double *mc[3];     // 2     MUSCL grid ratios along i, j, k: {2w/(w+w_lower), 2w/(w+w_upper)}
   double *fA[3];     // 4     face areas {nx, ny, nz, |A|} for i-, j-, k-faces
   double *center;    // 3
   // per boundary face: 1 if the neighbour across that block face contributes to the implicit

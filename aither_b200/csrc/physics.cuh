@@ -31,7 +31,14 @@ struct Gas {
   double R[AITHER_MAX_SPECIES];
   double n[AITHER_MAX_SPECIES];
   double hf[AITHER_MAX_SPECIES];
+  // single-species constants used by the marching kernels (march.cuh): 1/R, 1/cv, cp/cv
+  double rInv0, cvInv0, gamma0;
 };
+inline void GasFinalize(Gas *g) {
+  g->rInv0 = 1.0 / g->R[0];
+  g->cvInv0 = 1.0 / (g->R[0] * g->n[0]);
+  g->gamma0 = (g->R[0] * (g->n[0] + 1.0)) / (g->R[0] * g->n[0]);
+}
 
 // Equation layout for NS species and NT turbulence equations
 // (ref: include/varArray.hpp:47-51): [rho_1..rho_NS, u, v, w, p, (k, omega)].
@@ -561,6 +568,270 @@ AITHER_HD void OffDiagScalar(const Gas &g, const double *state, const double *du
     const double srd = (e < NS + 4 ? sr : 0.0) * du[e];
     out[e] = positive ? fc + srd : fc - srd;
   }
+}
+
+// =============================================================================================
+// Restructured point functions used by the plane-marching kernels (march.cuh). Same formulas as
+// above with shared reciprocals; each differs from its twin by rounding only (tests/hostsim).
+// ---------------------------------------------------------------------------------------------
+// cheap thermodynamics. cp/cv sums follow src/thermodynamic.cpp:62-104; for one species the mass
+// fraction is exactly 1 and the sums collapse to constants.
+template <int NS>
+struct MixK {
+  double rho, rhoInv, cp, cv, cvInv, hf;
+  double tFac;    // T = p * tFac          (ref src/eos.cpp:100-109: T = p / sum(rho_s R_s))
+  double gamma;   // cp / cv
+};
+template <int NS>
+AITHER_HD MixK<NS> MixOf(const Gas &g, const double *s) {
+  MixK<NS> m;
+  if (NS == 1) {
+    m.rho = s[0];
+    m.rhoInv = 1.0 / s[0];
+    m.cp = g.R[0] * (g.n[0] + 1.0);
+    m.cv = g.R[0] * g.n[0];
+    m.cvInv = g.cvInv0;
+    m.hf = g.hf[0];
+    m.tFac = m.rhoInv * g.rInv0;
+    m.gamma = g.gamma0;
+  } else {
+    m.rho = SpeciesSum<NS>(s);
+    m.rhoInv = 1.0 / m.rho;
+    m.cp = 0.0; m.cv = 0.0; m.hf = 0.0;
+    double rhoR = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const double mf = s[q] * m.rhoInv;
+      m.cp += mf * (g.R[q] * (g.n[q] + 1.0));
+      m.cv += mf * (g.R[q] * g.n[q]);
+      m.hf += mf * g.hf[q];
+      rhoR += s[q] * g.R[q];
+    }
+    m.cvInv = 1.0 / m.cv;
+    m.tFac = 1.0 / rhoR;
+    m.gamma = m.cp * m.cvInv;
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roe flux, same wave decomposition as RoeFlux (physics.cuh; ref include/inviscidFlux.hpp:260-382)
+// with shared reciprocals. Returns flux * 1 (unit normal n), not yet times area.
+template <int NS, int NT>
+AITHER_HD void RoeFluxFast(const Gas &g, const double *l, const double *r,
+                                            const double *n, double *flux) {
+  using E = Eq<NS, NT>;
+  const MixK<NS> ml = MixOf<NS>(g, l);
+  const MixK<NS> mr = MixOf<NS>(g, r);
+  const double denRatio = sqrt(mr.rho * ml.rhoInv);
+  const double inv1p = 1.0 / (1.0 + denRatio);
+  double roe[E::neq];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) roe[q] = l[q] * denRatio;
+#pragma unroll
+  for (int e = NS; e < E::neq; ++e) roe[e] = (l[e] + denRatio * r[e]) * inv1p;
+  const MixK<NS> mm = MixOf<NS>(g, roe);
+  const double q2 = VelMagSq<NS>(roe);
+  const double tR = roe[E::ie] * mm.tFac;
+  const double hR = mm.hf + mm.cp * tR + 0.5 * q2;
+  const double a2 = mm.gamma * roe[E::ie] * mm.rhoInv;
+  const double aR = sqrt(a2);
+  const double a2inv = 1.0 / (aR * aR);
+  const double rhoR = mm.rho;
+  const double velNormR = roe[E::imx] * n[0] + roe[E::imy] * n[1] + roe[E::imz] * n[2];
+  double delta[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) delta[e] = r[e] - l[e];
+  const double deltaRho = SpeciesSum<NS>(delta);
+  const double nvd = delta[E::imx] * n[0] + delta[E::imy] * n[1] + delta[E::imz] * n[2];
+  const double dP = delta[E::ie];
+  double diss[E::neq];
+  double mfR[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) mfR[q] = NS == 1 ? 1.0 : roe[q] * mm.rhoInv;
+
+  // left-moving acoustic wave
+  double ws = fabs(velNormR - aR);
+  if (ws < kEntropyFix) ws = 0.5 * (ws * ws / kEntropyFix + kEntropyFix);
+  double wss = ws * ((dP - rhoR * aR * nvd) * (0.5 * a2inv));
+#pragma unroll
+  for (int q = 0; q < NS; ++q) diss[q] = wss * mfR[q];
+  diss[E::imx] = wss * (roe[E::imx] - aR * n[0]);
+  diss[E::imy] = wss * (roe[E::imy] - aR * n[1]);
+  diss[E::imz] = wss * (roe[E::imz] - aR * n[2]);
+  diss[E::ie] = wss * (hR - aR * velNormR);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) diss[E::it + t] = wss * roe[E::it + t];
+  // entropy wave
+  ws = fabs(velNormR);
+  const double dPa2 = dP * a2inv;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) diss[q] += (ws * (-dPa2)) * mfR[q] + ws * delta[q];
+  wss = ws * (deltaRho - dPa2);
+  diss[E::imx] += wss * roe[E::imx];
+  diss[E::imy] += wss * roe[E::imy];
+  diss[E::imz] += wss * roe[E::imz];
+  diss[E::ie] += wss * 0.5 * q2;
+  // shear wave
+  wss = ws * rhoR;
+  diss[E::imx] += wss * (delta[E::imx] - nvd * n[0]);
+  diss[E::imy] += wss * (delta[E::imy] - nvd * n[1]);
+  diss[E::imz] += wss * (delta[E::imz] - nvd * n[2]);
+  diss[E::ie] += wss * ((roe[E::imx] * delta[E::imx] + roe[E::imy] * delta[E::imy] +
+                         roe[E::imz] * delta[E::imz]) -
+                        velNormR * nvd);
+  // right-moving acoustic wave
+  ws = fabs(velNormR + aR);
+  if (ws < kEntropyFix) ws = 0.5 * (ws * ws / kEntropyFix + kEntropyFix);
+  wss = ws * ((dP + rhoR * aR * nvd) * (0.5 * a2inv));
+#pragma unroll
+  for (int q = 0; q < NS; ++q) diss[q] += wss * mfR[q];
+  diss[E::imx] += wss * (roe[E::imx] + aR * n[0]);
+  diss[E::imy] += wss * (roe[E::imy] + aR * n[1]);
+  diss[E::imz] += wss * (roe[E::imz] + aR * n[2]);
+  diss[E::ie] += wss * (hR + aR * velNormR);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) diss[E::it + t] += wss * roe[E::it + t];
+  if (NT > 0) {
+    ws = fabs(velNormR);
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      diss[E::it + t] += ws * (rhoR * delta[E::it + t] + roe[E::it + t] * deltaRho -
+                               dPa2 * roe[E::it + t]);
+  }
+  // physical fluxes of the two states (ref include/inviscidFlux.hpp:128-159)
+  const double vnL = l[E::imx] * n[0] + l[E::imy] * n[1] + l[E::imz] * n[2];
+  const double vnR = r[E::imx] * n[0] + r[E::imy] * n[1] + r[E::imz] * n[2];
+  const double hL = ml.hf + ml.cp * (l[E::ie] * ml.tFac) + 0.5 * VelMagSq<NS>(l);
+  const double hRt = mr.hf + mr.cp * (r[E::ie] * mr.tFac) + 0.5 * VelMagSq<NS>(r);
+  const double mL = ml.rho * vnL, mR = mr.rho * vnR;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) flux[q] = (l[q] * vnL + (r[q] * vnR - diss[q])) * 0.5;
+  flux[E::imx] = ((mL * l[E::imx] + l[E::ie] * n[0]) +
+                  ((mR * r[E::imx] + r[E::ie] * n[0]) - diss[E::imx])) * 0.5;
+  flux[E::imy] = ((mL * l[E::imy] + l[E::ie] * n[1]) +
+                  ((mR * r[E::imy] + r[E::ie] * n[1]) - diss[E::imy])) * 0.5;
+  flux[E::imz] = ((mL * l[E::imz] + l[E::ie] * n[2]) +
+                  ((mR * r[E::imz] + r[E::ie] * n[2]) - diss[E::imz])) * 0.5;
+  flux[E::ie] = (mL * hL + (mR * hRt - diss[E::ie])) * 0.5;
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+    flux[E::it + t] = (mL * l[E::it + t] + (mR * r[E::it + t] - diss[E::it + t])) * 0.5;
+}
+
+template <int NS, int NT, int FLUX>
+AITHER_HD void InviscidFluxFast(const Gas &g, const double *l, const double *r,
+                                                 const double *n, double *f) {
+  if (FLUX == AITHER_FLUX_ROE) RoeFluxFast<NS, NT>(g, l, r, n, f);
+  else AusmFlux<NS, NT>(g, l, r, n, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// implicit sweep. Ingredients of one cell, as the off-diagonal product of every neighbour needs
+// them (ref src/fluxJacobian.cpp:122-162 RusanovScalarOffDiagonal): old primitive state, its
+// enthalpy and sound speed, the conserved update, and the updated primitive state + enthalpy.
+template <int NS, int NT>
+struct Ingr {
+  static constexpr int neq = NS + 4 + NT;
+  static constexpr int n = 3 * neq + 3;  // s[neq] H a | du[neq] | sn[neq] Hn
+};
+
+// state + dU -> Ingr; ref include/primitive.hpp:206-231 (UpdatePrimWithCons), :150-177
+template <int NS, int NT>
+AITHER_HD void MakeIngr(const Gas &g, const double *s, const double *du,
+                                         double *H, double *a, double *sn, double *Hn) {
+  using E = Eq<NS, NT>;
+  const MixK<NS> m = MixOf<NS>(g, s);
+  const double q2 = VelMagSq<NS>(s);
+  const double t = s[E::ie] * m.tFac;
+  *H = m.hf + m.cp * t + 0.5 * q2;
+  *a = sqrt(m.gamma * s[E::ie] * m.rhoInv);
+  // conserved + update
+  double c[E::neq];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) c[q] = s[q] + du[q];
+  c[E::imx] = m.rho * s[E::imx] + du[E::imx];
+  c[E::imy] = m.rho * s[E::imy] + du[E::imy];
+  c[E::imz] = m.rho * s[E::imz] + du[E::imz];
+  c[E::ie] = m.rho * (m.hf + m.cv * t + 0.5 * q2) + du[E::ie];
+#pragma unroll
+  for (int tq = 0; tq < NT; ++tq) c[E::it + tq] = m.rho * s[E::it + tq] + du[E::it + tq];
+  double rho = SpeciesSum<NS>(c);
+  double rhoInv = 1.0 / rho;
+  if (NS > 1) {
+    double mf[NS], total = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      mf[q] = fmax(c[q] * rhoInv, 0.0);
+      total += mf[q];
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) c[q] = rho * (mf[q] / total);
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) sn[q] = c[q];
+  sn[E::imx] = c[E::imx] * rhoInv;
+  sn[E::imy] = c[E::imy] * rhoInv;
+  sn[E::imz] = c[E::imz] * rhoInv;
+  const MixK<NS> mn = MixOf<NS>(g, sn);
+  const double q2n = VelMagSq<NS>(sn);
+  const double tn = ((c[E::ie] * rhoInv - 0.5 * q2n) - mn.hf) * mn.cvInv;
+  double rhoRn = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) rhoRn += sn[q] * g.R[q];
+  sn[E::ie] = rhoRn * tn;
+#pragma unroll
+  for (int tq = 0; tq < NT; ++tq) sn[E::it + tq] = fmax(c[E::it + tq] * rhoInv, kTurbMin);
+  *Hn = mn.hf + mn.cp * tn + 0.5 * q2n;
+}
+
+// off-diagonal product of one neighbour from its ingredients and the shared face's area
+template <int NS, int NT, typename LD>
+AITHER_HD void OffDiagFromIngr(LD ld, const double *fA, bool positive,
+                                                double *acc) {
+  using E = Eq<NS, NT>;
+  constexpr int neq = E::neq;
+  // layout: [0,neq) s | neq H | neq+1 a | [neq+2, 2neq+2) du | [2neq+2, 3neq+2) sn | 3neq+2 Hn
+  const double u = ld(E::imx), v = ld(E::imy), w = ld(E::imz), pr = ld(E::ie);
+  const double un = ld(2 * neq + 2 + E::imx), vn_ = ld(2 * neq + 2 + E::imy),
+               wn = ld(2 * neq + 2 + E::imz), pn = ld(2 * neq + 2 + E::ie);
+  const double vo = u * fA[0] + v * fA[1] + w * fA[2];
+  const double vnw = un * fA[0] + vn_ * fA[1] + wn * fA[2];
+  double rho = 0.0, rhon = 0.0;
+  const double half = 0.5 * fA[3];
+  const double sr = half * (fabs(vo) + ld(neq + 1));
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    const double r0 = ld(q), r1 = ld(2 * neq + 2 + q);
+    rho += r0;
+    rhon += r1;
+    const double fc = half * (r1 * vnw - r0 * vo);
+    const double srd = sr * ld(neq + 2 + q);
+    acc[q] += positive ? fc + srd : fc - srd;
+  }
+  const double mo = rho * vo, mn = rhon * vnw;
+  {
+    const double fc = half * ((mn * un + pn * fA[0]) - (mo * u + pr * fA[0]));
+    const double srd = sr * ld(neq + 2 + E::imx);
+    acc[E::imx] += positive ? fc + srd : fc - srd;
+  }
+  {
+    const double fc = half * ((mn * vn_ + pn * fA[1]) - (mo * v + pr * fA[1]));
+    const double srd = sr * ld(neq + 2 + E::imy);
+    acc[E::imy] += positive ? fc + srd : fc - srd;
+  }
+  {
+    const double fc = half * ((mn * wn + pn * fA[2]) - (mo * w + pr * fA[2]));
+    const double srd = sr * ld(neq + 2 + E::imz);
+    acc[E::imz] += positive ? fc + srd : fc - srd;
+  }
+  {
+    const double fc = half * (mn * ld(3 * neq + 2) - mo * ld(neq));
+    const double srd = sr * ld(neq + 2 + E::ie);
+    acc[E::ie] += positive ? fc + srd : fc - srd;
+  }
+  // turbulence rows: flux change zeroed and the flow spectral radius does not act on them
+  // (ref src/fluxJacobian.cpp:146-149; the turbulence spectral radius is 0 for inviscid flow)
 }
 
 // ---------------------------------------------------------------------------------------------

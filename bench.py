@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: Mcell-iter/s of one full nonlinear iteration
+(BC fill + residual + time step + implicit DPLUR solve + update + norms; the body of the
+reference's mgSolution::Iterate, src/mgSolution.cpp:246-269).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference on host cores
+
+Workload (BASELINE.json configs[1]): synthetic 256^3 single block per GPU, Euler,
+Roe + MUSCL (kappa = 1/3, no limiter), implicit Euler, DPLUR x4, CFL 50, characteristic i-faces,
+slip-wall j/k faces, seed-fixed +-1 % perturbed state. fp64 throughout.
+
+A "step" is one nonlinear iteration over the whole block. `value` times K steps back to back
+with everything resident in HBM (CUDA events on the library's stream). `e2e` times the same K
+steps through the C-ABI entry points a host solver would call when it owns the state: every step
+uploads the state from pinned host memory (aither_gpu_upload_state), runs aither_gpu_iterate and
+reads the residual norms back. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEPS = 4
+CFL = 50.0
+NEQ = 5
+# algorithmic (compulsory) doubles per cell, per kernel family of one iteration
+ALG_DOUBLES = {"residual": 27, "dt_diag_init": 13, "dplur_sweep": 34, "matrix_residual": 30,
+               "update_norms": 20, "store_time_n": 10}
+
+
+def bytes_per_cell_iter(sweeps):
+    return 8 * (100 + 34 * sweeps)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons, sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([t.strip() for t in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2.0)
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        # samples under load = the upper half (the sampler also sees idle gaps)
+        sm.sort()
+        med = float(np.median(sm[len(sm) // 2:])) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+AIR_DAT = """n: 2.5
+molarMass: 28.97
+vibrationalTemperature: [3056.0]
+heatOfFormation: 0
+referencePressure: 101325
+referenceTemperature: 298.15
+referenceEntropy: 0
+sutherlandViscosityC1: 1.458e-6
+sutherlandViscosityS: 110.4
+sutherlandConductivityC1: 2.495e-3
+sutherlandConductivityS: 194.0
+"""
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "aither_dump")
+
+
+def _run_reference_sample(n, iters, procs):
+    """Time the UNMODIFIED reference (oracle/_ref/aither_dump, built from /root/reference against
+    a single-rank MPI stub) on the bench workload at n^3 cells: `procs` independent single-rank
+    processes, one per host core, each on its own n^3 block (no halo cost). Returns the list of
+    per-iteration wall times of the slowest process (first iteration dropped by the caller)."""
+    from aither_b200 import synthetic
+    tmp = tempfile.mkdtemp(prefix="aither_ref_")
+    try:
+        dirs = []
+        for p in range(procs):
+            d = os.path.join(tmp, "p%d" % p)
+            synthetic.write_case(d, "box", n, n, n, iterations=iters, solver="dplur",
+                                 sweeps=SWEEPS, cfl=CFL, perturb=(p, 0.01))
+            open(os.path.join(d, "air.dat"), "w").write(AIR_DAT)
+            dirs.append(d)
+        running = []
+        for d in dirs:
+            env = dict(os.environ, AITHER_INSTALL_DIRECTORY=d)
+            running.append(subprocess.Popen(
+                [HARNESS, "box.inp", os.path.join(d, "dump.bin"), "--iters", str(iters), "--time"],
+                cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        times = []
+        for pr in running:
+            out, _ = pr.communicate()
+            if pr.returncode != 0:
+                raise RuntimeError("reference harness failed:\n" + out[-2000:])
+            times.append([float(m) for m in re.findall(r"time_s ([0-9.eE+-]+)", out)])
+        return [max(t[i] for t in times) for i in range(iters)]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _oracle_port_sample(n, iters):
+    """Fallback when oracle/_ref is absent: the plain-C restatement, 1 core."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from aither_b200 import synthetic
+    prob = synthetic.box_problem(n, n, n, solver="dplur", sweeps=SWEEPS)
+    lvl = oracle.OracleLevel(prob)
+    out = []
+    for it in range(iters):
+        t0 = time.perf_counter()
+        lvl.store_old_solution(it)
+        lvl.iterate(CFL)
+        out.append(time.perf_counter() - t0)
+    lvl.close()
+    return out
+
+
+def cpu_baseline(n=40, iters=4):
+    """Bounded CPU sample for the GPU arm's JSON line: 1 core, n^3 cells, `iters` iterations
+    (first dropped). ~10-20 s of CPU work."""
+    if os.path.exists(HARNESS):
+        t = _run_reference_sample(n, iters, 1)
+        kind = "reference"
+    else:
+        t = _oracle_port_sample(n, iters)
+        kind = "port"
+    per = float(np.mean(t[1:])) if len(t) > 1 else float(t[0])
+    return {"value": n ** 3 / per / 1e6, "unit": "Mcell-iter/s", "cores": 1, "kind": kind,
+            "sample": "same workload at %d^3 cells, %d iterations (first dropped), 1 process on "
+                      "1 host core, %.2f s/iter" % (n, iters, per)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU code on all host cores of the box."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    procs = max(1, min(cores, 64))
+    n = 32
+    iters = args.warmup + args.steps
+    if os.path.exists(HARNESS):
+        t = _run_reference_sample(n, iters, procs)
+        kind = "reference"
+    else:
+        t = _oracle_port_sample(n, iters)
+        kind, procs = "port", 1
+    timed = t[args.warmup:]
+    per = float(np.mean(timed))
+    value = procs * n ** 3 / per / 1e6
+    line = {
+        "impl": "reference", "metric": "Mcell-iter/s (residual+implicit)", "value": value,
+        "unit": "Mcell-iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_cells_note="%d independent %d^3 blocks, one per host core" %
+                                  (procs, n)),
+        "cpu_baseline": {"value": value, "unit": "Mcell-iter/s", "cores": procs, "kind": kind,
+                         "sample": "each step = one iteration of %d single-rank reference "
+                                   "processes (one per core, no MPI on the box so no halo cost), "
+                                   "each on the bench workload at %d^3 cells" % (procs, n)},
+        "e2e": {"value": value, "unit": "Mcell-iter/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n=256, n_cells_note=None, gpus=1):
+    cfg = {"workload": "synthetic %d^3 single block per GPU, inviscid Roe+MUSCL(kappa=1/3), "
+                       "implicit Euler, DPLUR x%d, CFL %g" % (n, SWEEPS, CFL),
+           "cells_per_gpu": n ** 3, "matrix_sweeps": SWEEPS,
+           "l2": "inputs larger than L2 (each field %.0f MB, ~40 fields)" % (n ** 3 * 8 / 1e6),
+           "parallelism": "blocks%d" % gpus}
+    if n_cells_note:
+        cfg["sample"] = n_cells_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import aither_b200
+    from aither_b200 import ctypes_abi as abi
+    from aither_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.n
+    t_setup = time.perf_counter()
+    prob = synthetic.box_problem(n, n, n, solver="dplur", sweeps=SWEEPS, seed=rank)
+    lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world)
+    cells = prob.num_cells
+    g = prob.cfg.numGhosts
+    state_shape = prob.blocks[0].padded_shape(g) + (NEQ,)
+    host_state = aither_b200.pinned_array(state_shape)
+    host_state[...] = prob.blocks[0].arrays["state"]
+    for b in prob.blocks:          # host copies of the metrics are no longer needed
+        b.arrays = {"state": None}
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        lvl.synchronize()
+        if dist is not None:
+            dist.barrier()
+        lvl.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident: K iterations back to back, no host sync in between ----------------------
+    lvl.run(args.warmup, CFL)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lvl.profile_enable(True)
+    barrier()
+    launches0 = lvl.launch_count
+    lvl.timer_start()
+    hist = lvl.run(args.steps, CFL)
+    ms = lvl.timer_stop()
+    barrier()
+    launches = lvl.launch_count - launches0
+    ms = max_over_ranks(ms)
+    prof = lvl.profile()
+    lvl.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.isfinite(hist).all(), "non-finite residual history"
+
+    # ---- e2e: host-owned state, H2D every step, norms D2H every step -------------------------
+    h2d = host_state.nbytes
+    d2h = (NEQ + 1) * 8 + 32
+    for it in range(2):
+        lvl.upload_state(0, host_state)
+        lvl.store_old_solution(it)
+        lvl.iterate(CFL)
+    barrier()
+    t0 = time.perf_counter()
+    lvl.timer_start()
+    for it in range(args.steps):
+        lvl.upload_state(0, host_state)
+        lvl.store_old_solution(it)
+        l2, linf, mr = lvl.iterate(CFL)
+    ms_e2e = lvl.timer_stop()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
+    # a round trip that also brings the state back to the host (output / restart iterations)
+    lvl.download_state_into(0, host_state)
+
+    if rank != 0:
+        lvl.close()
+        return
+    total_cells = cells * world
+    value = total_cells * args.steps / (ms * 1e-3) / 1e6
+    e2e = total_cells * args.steps / (ms_e2e * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    # dominant kernel family of the timed region
+    fam = {k: v for k, v in prof.items() if v[1] > 0 and k in ALG_DOUBLES}
+    top = max(fam, key=lambda k: fam[k][0])
+    top_ms, top_n = fam[top]
+    alg_bytes = ALG_DOUBLES[top] * 8 * cells
+    achieved = alg_bytes / (top_ms / top_n * 1e-3) / 1e9
+    total_fam_ms = sum(v[0] for v in prof.values())
+    bpc = bytes_per_cell_iter(SWEEPS)
+    iter_gbs = cells * bpc / (ms / args.steps * 1e-3) / 1e9
+    line = {
+        "metric": "Mcell-iter/s (residual+implicit)", "value": value, "unit": "Mcell-iter/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, gpus=world),
+        "e2e": {"value": e2e, "unit": "Mcell-iter/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "what": "per step: aither_gpu_upload_state from pinned host memory + "
+                        "store_old_solution + aither_gpu_iterate (norms copied back)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_ms": top_ms / top_n,
+                     "share_of_step": top_ms / total_fam_ms},
+        "roofline_iteration": {"bytes_per_cell_iter": bpc, "achieved": iter_gbs,
+                               "frac": iter_gbs / peak, "unit": "GB/s"},
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]},
+        "setup_s": round(t_setup, 1),
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu_traffic):
+        tr = json.load(open(ncu_traffic))
+        if top in tr and tr[top].get("cells") == cells:
+            line["roofline"]["traffic"] = tr[top]["dram_bytes_per_launch"]
+    print(json.dumps(line))
+    lvl.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per side of the block (256)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -238,6 +238,12 @@ int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst);
 /* number of doubles aither_gpu_download_field writes for `field` */
 long long aither_gpu_field_size(aither_gpu *h, int blk, int field);
 
+/* page-locked host buffers for the state transfers above (cudaMallocHost /
+ * cudaFreeHost): a caller that wants the copies at full PCIe rate allocates its
+ * staging arrays here. Usable before any handle exists. */
+int aither_gpu_alloc_host(long long bytes, void **out);
+int aither_gpu_free_host(void *p);
+
 /* device synchronisation + CUDA-event timing helpers for bench.py (the
  * launching stream is the library's own, which torch.cuda.Event cannot see). */
 int aither_gpu_synchronize(aither_gpu *h);

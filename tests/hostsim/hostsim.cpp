@@ -12,6 +12,7 @@ static Gas GasFromCfg(const aither_cfg *c) {
     g.n[s] = c->n[s];
     g.hf[s] = c->hf[s];
   }
+  GasFinalize(&g);
   return g;
 }
 static const aither_bc_state *Find(const aither_cfg *c, int tag) {
@@ -54,5 +55,29 @@ void hs_offdiag_scalar(const aither_cfg *c, const double *s, const double *du, c
 void hs_update_prim(const aither_cfg *c, const double *s, const double *du, double *out) {
   const Gas g = GasFromCfg(c);
   UpdatePrimWithCons<1, 0>(g, s, du, out);
+}
+}
+
+// ---- restructured twins used by the marching kernels ----------------------------------------
+extern "C" {
+void hs_roe_flux_fast(const aither_cfg *c, const double *l, const double *r, const double *n,
+                      double *f) {
+  const Gas g = GasFromCfg(c);
+  RoeFluxFast<1, 0>(g, l, r, n, f);
+}
+// the off-diagonal product of one neighbour, through MakeIngr + OffDiagFromIngr
+void hs_offdiag_fast(const aither_cfg *c, const double *s, const double *du, const double *fa,
+                     int positive, double *out) {
+  const Gas g = GasFromCfg(c);
+  constexpr int neq = 5;
+  double ing[Ingr<1, 0>::n];
+  MakeIngr<1, 0>(g, s, du, &ing[neq], &ing[neq + 1], &ing[2 * neq + 2], &ing[3 * neq + 2]);
+  for (int e = 0; e < neq; ++e) {
+    ing[e] = s[e];
+    ing[neq + 2 + e] = du[e];
+    out[e] = 0.0;
+  }
+  auto ld = [&](int q) { return ing[q]; };
+  OffDiagFromIngr<1, 0>(ld, fa, positive != 0, out);
 }
 }

@@ -152,3 +152,35 @@ def test_offdiag(hs):
             L.orc_offdiag_scalar(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(a))
             hs.hs_offdiag_scalar(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(b))
             close(b, a)
+
+
+@pytest.mark.parametrize("mach", [0.3, 1.5, 0.02])
+def test_roe_flux_fast_twin(hs, mach):
+    """RoeFluxFast (shared reciprocals; used by ResidualMarchKernel) vs the oracle's Roe flux."""
+    rng = np.random.default_rng(23)
+    cfg = cfg_for("roe")
+    L = oracle.lib()
+    for _ in range(500):
+        l, r, n = rand_state(rng, mach), rand_state(rng, mach), unit(rng)
+        a, b = np.empty(5), np.empty(5)
+        L.orc_inviscid_flux(C.byref(cfg), ptr(l), ptr(r), ptr(n), ptr(a))
+        hs.hs_roe_flux_fast(C.byref(cfg), ptr(l), ptr(r), ptr(n), ptr(b))
+        close(b, a, 2e-14)
+
+
+def test_offdiag_fast_twin(hs):
+    """MakeIngr + OffDiagFromIngr (ImplicitMarchKernel) vs the oracle's scalar off-diagonal."""
+    rng = np.random.default_rng(29)
+    cfg = cfg_for()
+    L = oracle.lib()
+    for trial in range(500):
+        s, n = rand_state(rng), unit(rng)
+        du = rng.normal(size=5) * (1e-2 if trial % 2 else 1e-6)
+        fa = np.concatenate([n, [rng.uniform(0.1, 2.0)]])
+        for pos in (0, 1):
+            a, b = np.empty(5), np.empty(5)
+            L.orc_offdiag_scalar(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(a))
+            hs.hs_offdiag_fast(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(b))
+            # absolute bar against the flux magnitude: both compute F(U+dU) - F(U) by cancellation
+            scale = fa[3] * (np.abs(s).max() + 1.0)
+            assert np.abs(a - b).max() <= 1e-14 * scale + 1e-12 * np.abs(a).max(), (a, b)
