@@ -30,6 +30,8 @@ ABI_SYMBOLS = (
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
     "aither_gpu_destroy", "aither_gpu_last_error", "aither_gpu_version",
     "aither_gpu_alloc_host", "aither_gpu_free_host",
+    "aither_gpu_comm_unique_id", "aither_gpu_comm_create", "aither_gpu_comm_destroy",
+    "aither_gpu_halo_info",
 )
 
 
@@ -78,6 +80,10 @@ def load_library():
     L.aither_gpu_alloc_host.argtypes = [C.c_longlong, C.POINTER(vp)]
     L.aither_gpu_free_host.argtypes = [vp]
     L.aither_gpu_version.restype = C.c_char_p
+    L.aither_gpu_comm_unique_id.argtypes = [C.c_char_p]
+    L.aither_gpu_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.aither_gpu_comm_destroy.argtypes = [vp]
+    L.aither_gpu_halo_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     _LIB = L
     return L
 

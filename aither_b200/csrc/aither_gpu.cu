@@ -282,10 +282,19 @@ int EnsureResults(aither_gpu *h, int n) {
 
 // ---- phases (all asynchronous on h->stream) ---------------------------------------------------
 int Exchange(aither_gpu *h, int which) {
+  // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update)
   if (h->halo.nConn == 0) return 0;
-  std::vector<const BlockDev *> devs;
-  for (auto &hb : h->blocks) devs.push_back(&hb.dev);
-  if (HaloExchange(h->halo, devs, which, h->stream, &h->launches)) return Fail(HaloError());
+  HaloFields f;
+  for (size_t bb = 0; bb < h->blocks.size(); ++bb) {
+    const BlockDev &b = h->blocks[bb].dev;
+    f.base[bb] = which == kHaloState ? b.state : b.x;
+    f.fs[bb] = b.fs;
+  }
+  ScopedLaunch sl(h, kFamHalo);
+  h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
+  h->famLaunches[kFamHalo]--;
+  if (HaloExchange(h->halo, f, h->neq, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
+    return Fail(HaloError());
   return 0;
 }
 
@@ -908,6 +917,42 @@ int aither_gpu_alloc_host(long long bytes, void **out) {
 }
 int aither_gpu_free_host(void *p) {
   if (p) CK(cudaFreeHost(p));
+  return 0;
+}
+
+int aither_gpu_comm_unique_id(char id[128]) {
+  if (!id) return Fail("null argument");
+  NcclApi *api = Nccl();
+  if (!api) return Fail(HaloError());
+  NcclUniqueId u;
+  const int rc = api->GetUniqueId(&u);
+  if (rc != 0) return Fail(std::string("ncclGetUniqueId: ") + api->GetErrorString(rc));
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+int aither_gpu_comm_create(const char id[128], int rank, int nRanks, int device, void **comm) {
+  if (!id || !comm) return Fail("null argument");
+  NcclApi *api = Nccl();
+  if (!api) return Fail(HaloError());
+  CK(cudaSetDevice(device));
+  NcclUniqueId u;
+  memcpy(u.internal, id, 128);
+  const int rc = api->CommInitRank(comm, nRanks, u, rank);
+  if (rc != 0) return Fail(std::string("ncclCommInitRank: ") + api->GetErrorString(rc));
+  return 0;
+}
+int aither_gpu_comm_destroy(void *comm) {
+  if (!comm) return 0;
+  NcclApi *api = Nccl();
+  if (!api) return Fail(HaloError());
+  const int rc = api->CommDestroy(comm);
+  if (rc != 0) return Fail(std::string("ncclCommDestroy: ") + api->GetErrorString(rc));
+  return 0;
+}
+int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells) {
+  if (!h) return Fail("null handle");
+  if (levels) *levels = static_cast<int>(h->halo.levels.size());
+  if (remoteCells) *remoteCells = h->halo.bytesPerExchangeRemote;
   return 0;
 }
 

@@ -140,3 +140,143 @@ def box_problem(ni, nj, nk, *, solver="dplur", sweeps=4, limiter="none", flux="r
     arrays["state"] = state
     arrays["wallDist"] = None
     return Problem(cfg, [Block(ni, nj, nk, surfaces, arrays)])
+
+
+# ---- multi-block decomposition of a single-block problem ---------------------------------------
+def _cuts(n, parts):
+    """cell index of the cuts that split n cells into `parts` nearly equal pieces"""
+    return [(n * p) // parts for p in range(parts + 1)]
+
+
+def split_problem(prob, splits):
+    """Cut the single block of `prob` into splits = (pi, pj, pk) sub-blocks joined by `interblock`
+    connections, the way the reference's decomposition presents them to the solver (reference
+    src/parallel.cpp:95-178 splits blocks; src/boundaryConditions.cpp:2458-2497 names the joins;
+    include/boundaryConditions.hpp:324-336 is the connection record).
+
+    Every sub-block's ghost-padded geometry is cut out of the parent's, so geometry ghosts across a
+    join equal the neighbour's cells exactly as after the reference's geometry swap
+    (src/procBlock.cpp:3149-3330). Block order: i fastest, then j, then k. Connections: all i-joins,
+    then j-joins, then k-joins; first side = lower block's upper surface, orientation 1."""
+    assert len(prob.blocks) == 1
+    parent = prob.blocks[0]
+    g = prob.cfg.numGhosts
+    pi, pj, pk = splits
+    ci, cj, ck = _cuts(parent.ni, pi), _cuts(parent.nj, pj), _cuts(parent.nk, pk)
+    n_of = (parent.ni, parent.nj, parent.nk)
+
+    def parent_surface(surf_type, lo, hi):
+        """the parent's boundary surface of that side (one surface must cover the sub-face)"""
+        for row in parent.surfaces:
+            t, imin, imax, jmin, jmax, kmin, kmax, tag = row
+            mn, mx = (imin, jmin, kmin), (imax, jmax, kmax)
+            d3 = (surf_type - 1) // 2
+            if mn[d3] != mx[d3] or mn[d3] != (0 if surf_type % 2 else n_of[d3]):
+                continue
+            ok = all(mn[d] <= lo[d] and hi[d] <= mx[d] for d in range(3) if d != d3)
+            if ok:
+                return t, tag
+        raise ValueError("no single parent surface covers the sub-block face")
+
+    blocks, index = [], {}
+    for c in range(pk):
+        for b in range(pj):
+            for a in range(pi):
+                lo = (ci[a], cj[b], ck[c])
+                hi = (ci[a + 1], cj[b + 1], ck[c + 1])
+                n = tuple(hi[d] - lo[d] for d in range(3))
+                arrays = {}
+                for name, arr in parent.arrays.items():
+                    if arr is None:
+                        arrays[name] = None
+                        continue
+                    ext = [n[2] + 2 * g, n[1] + 2 * g, n[0] + 2 * g]
+                    if name == "fAreaI":
+                        ext[2] += 1
+                    elif name == "fAreaJ":
+                        ext[1] += 1
+                    elif name == "fAreaK":
+                        ext[0] += 1
+                    arrays[name] = np.ascontiguousarray(
+                        arr[lo[2]:lo[2] + ext[0], lo[1]:lo[1] + ext[1], lo[0]:lo[0] + ext[2]])
+                surfaces = []
+                pos = (a, b, c)
+                parts = (pi, pj, pk)
+                for d3 in range(3):
+                    for upper in (0, 1):
+                        st = 2 * d3 + 1 + upper
+                        rng = [[0, n[0]], [0, n[1]], [0, n[2]]]
+                        rng[d3] = [n[d3], n[d3]] if upper else [0, 0]
+                        at_edge = pos[d3] == (parts[d3] - 1 if upper else 0)
+                        if at_edge:
+                            t, tag = parent_surface(st, lo, hi)
+                        else:
+                            nb = list(pos)
+                            nb[d3] += 1 if upper else -1
+                            nb_id = nb[0] + pi * (nb[1] + pj * nb[2])
+                            partner_surface = st - 1 if upper else st + 1
+                            t, tag = abi.BC_INTERBLOCK, partner_surface * 1000 + nb_id
+                        surfaces.append((t, rng[0][0], rng[0][1], rng[1][0], rng[1][1], rng[2][0],
+                                         rng[2][1], tag))
+                bid = len(blocks)
+                index[pos] = bid
+                blocks.append(Block(n[0], n[1], n[2], surfaces, arrays, parent_block=0,
+                                    global_pos=bid))
+    conns = []
+    for d3 in range(3):
+        d1, d2 = (d3 + 1) % 3, (d3 + 2) % 3
+        for c in range(pk):
+            for b in range(pj):
+                for a in range(pi):
+                    pos = [a, b, c]
+                    if pos[d3] + 1 >= (pi, pj, pk)[d3]:
+                        continue
+                    up = list(pos)
+                    up[d3] += 1
+                    lo_id, up_id = index[tuple(pos)], index[tuple(up)]
+                    lb = blocks[lo_id]
+                    nlo = (lb.ni, lb.nj, lb.nk)
+                    cn = abi.Conn()
+                    cn.rank[0] = cn.rank[1] = 0
+                    cn.block[0], cn.block[1] = lo_id, up_id
+                    cn.localBlock[0], cn.localBlock[1] = lo_id, up_id
+                    cn.boundary[0], cn.boundary[1] = 2 * d3 + 2, 2 * d3 + 1
+                    for s in range(2):
+                        cn.d1Start[s], cn.d1End[s] = 0, nlo[d1]
+                        cn.d2Start[s], cn.d2End[s] = 0, nlo[d2]
+                    cn.constSurf[0], cn.constSurf[1] = nlo[d3], 0
+                    cn.orientation, cn.isInterblock = 1, 1
+                    conns.append(cn)
+    return Problem(prob.cfg, blocks, conns)
+
+
+def assign_ranks(prob, n_ranks):
+    """Place block b on rank b % ... in contiguous groups (the reference's `manual` decomposition:
+    one input block per rank, src/parallel.cpp:44-66) and fill the rank / localBlock fields of
+    every connection. Returns block ids per rank."""
+    nb = len(prob.blocks)
+    per = [[] for _ in range(n_ranks)]
+    owner, local = {}, {}
+    for b in range(nb):
+        r = (b * n_ranks) // nb
+        owner[b], local[b] = r, len(per[r])
+        per[r].append(b)
+    for cn in prob.conns:
+        for s in range(2):
+            gb = cn.block[s]
+            cn.rank[s], cn.localBlock[s] = owner[gb], local[gb]
+    return per
+
+
+def reassemble(prob_split, splits, fields):
+    """Stitch per-block interior arrays (k, j, i, c) of a split problem back into the parent's
+    (nk, nj, ni, c) array."""
+    pi, pj, pk = splits
+    rows_k = []
+    for c in range(pk):
+        rows_j = []
+        for b in range(pj):
+            rows_j.append(np.concatenate([fields[a + pi * (b + pj * c)] for a in range(pi)],
+                                         axis=2))
+        rows_k.append(np.concatenate(rows_j, axis=1))
+    return np.concatenate(rows_k, axis=0)

@@ -258,6 +258,22 @@ int aither_gpu_profile_get(aither_gpu *h, int family, double *ms, long long *lau
 const char *aither_gpu_kernel_family_name(int family);
 int aither_gpu_num_kernel_families(void);
 
+/* Multi-GPU: one process (reference "rank") per GPU. Connections whose two sides
+ * live on different ranks exchange their ghost layers with ncclSend/ncclRecv
+ * (replacing MPI_Sendrecv_replace, reference include/multiArray3d.hpp:1440-1508).
+ * The host program makes the communicator the way it would an MPI one: rank 0
+ * calls aither_gpu_comm_unique_id, broadcasts the 128 bytes with whatever it has
+ * (MPI_Bcast in the reference's main.cpp, torch.distributed in bench.py), every
+ * rank calls aither_gpu_comm_create and passes the result to aither_gpu_create.
+ * libnccl.so.2 is bound with dlopen on first use; single-GPU runs never load it. */
+int aither_gpu_comm_unique_id(char id[128]);
+int aither_gpu_comm_create(const char id[128], int rank, int nRanks, int device,
+                           void **comm);
+int aither_gpu_comm_destroy(void *comm);
+/* number of halo levels (pack/unpack launch pairs per exchange) and doubles this
+ * rank sends to other ranks per component per exchange; for reports and tests */
+int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells);
+
 int aither_gpu_destroy(aither_gpu *h);
 const char *aither_gpu_last_error(void);
 const char *aither_gpu_version(void);

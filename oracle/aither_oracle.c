@@ -921,12 +921,187 @@ static void update_aux(orc_level *h, orc_block *b) {
       }
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* connection (interblock / periodic) ghost swaps                            */
+typedef struct {
+  int boundary[2], d1s[2], d1e[2], d2s[2], d2e[2], cs[2], border[8], orient;
+} orc_conn;
+static void conn_load(const aither_conn *c, orc_conn *o) {
+  for (int s = 0; s < 2; ++s) {
+    o->boundary[s] = c->boundary[s];
+    o->d1s[s] = c->d1Start[s];
+    o->d1e[s] = c->d1End[s];
+    o->d2s[s] = c->d2Start[s];
+    o->d2e[s] = c->d2End[s];
+    o->cs[s] = c->constSurf[s];
+  }
+  for (int q = 0; q < 8; ++q) o->border[q] = c->patchBorder[q];
+  o->orient = c->orientation;
+}
+#define ISWAP(a, b) do { int t_ = (a); (a) = (b); (b) = t_; } while (0)
+/* ref: src/boundaryConditions.cpp:341-364 */
+static void conn_swap_order(orc_conn *o) {
+  ISWAP(o->boundary[0], o->boundary[1]);
+  ISWAP(o->d1s[0], o->d1s[1]);
+  ISWAP(o->d1e[0], o->d1e[1]);
+  ISWAP(o->d2s[0], o->d2s[1]);
+  ISWAP(o->d2e[0], o->d2e[1]);
+  ISWAP(o->cs[0], o->cs[1]);
+  for (int q = 0; q < 4; ++q) ISWAP(o->border[q], o->border[q + 4]);
+  if (o->orient == 4) o->orient = 5;
+  else if (o->orient == 5) o->orient = 4;
+}
+/* ref: src/boundaryConditions.cpp:833-858 */
+static void conn_adjust_for_slice(orc_conn *o, int blkFirst, int numG) {
+  if (!blkFirst) conn_swap_order(o);
+  const int blkStart = (o->boundary[0] % 2 == 0) ? o->cs[0] : -numG;
+  o->cs[1] = 0;
+  o->cs[0] = blkStart;
+  o->d1e[1] = o->d1e[1] - o->d1s[1] + 2 * numG;
+  o->d1e[0] = o->d1e[0] + numG;
+  o->d1s[1] = 0;
+  o->d1s[0] = o->d1s[0] - numG;
+  o->d2e[1] = o->d2e[1] - o->d2s[1] + 2 * numG;
+  o->d2e[0] = o->d2e[0] + numG;
+  o->d2s[1] = 0;
+  o->d2s[0] = o->d2s[0] - numG;
+}
+/* ref: src/boundaryConditions.cpp:1016-1150; side s, lo/hi in (i, j, k) */
+static void conn_slice_indices(const orc_conn *o, int s, int numG, int *lo,
+                               int *hi) {
+  const int upLowFac = (o->boundary[s] % 2 == 0) ? -numG : 0;
+  int d3, d1, d2;
+  if (o->boundary[s] <= 2) { d3 = 0; d1 = 1; d2 = 2; }
+  else if (o->boundary[s] <= 4) { d3 = 1; d1 = 2; d2 = 0; }
+  else { d3 = 2; d1 = 0; d2 = 1; }
+  lo[d3] = o->cs[s] + upLowFac;
+  hi[d3] = lo[d3] + numG;
+  lo[d1] = o->d1s[s] - numG;
+  hi[d1] = o->d1e[s] + numG;
+  lo[d2] = o->d2s[s] - numG;
+  hi[d2] = o->d2e[s] + numG;
+}
+/* ref: src/boundaryConditions.cpp:3006-3181 (GetSwapLoc) */
+static void get_swap_loc(int l1, int l2, int l3, int numGhosts,
+                         const orc_conn *o, int d3, int first, int *loc) {
+  const int ot = o->orient;
+  if (first) {
+    const int lower = o->cs[0] == 0; /* IsLowerFirst */
+    const int n3 = lower ? l3 - numGhosts : o->cs[0] + l3;
+    if (o->boundary[0] <= 2) {
+      loc[1] = o->d1s[0] + l1; loc[2] = o->d2s[0] + l2; loc[0] = n3;
+    } else if (o->boundary[0] <= 4) {
+      loc[2] = o->d1s[0] + l1; loc[0] = o->d2s[0] + l2; loc[1] = n3;
+    } else {
+      loc[0] = o->d1s[0] + l1; loc[1] = o->d2s[0] + l2; loc[2] = n3;
+    }
+    return;
+  }
+  const int lowerSecond = o->cs[1] == 0; /* IsLowerSecond */
+  const int llOrUu = (o->boundary[0] + o->boundary[1]) % 2 == 0;
+  int n3;
+  if (llOrUu)
+    n3 = lowerSecond ? d3 - l3 - 1 : o->cs[1] + d3 - l3 - 1;
+  else
+    n3 = lowerSecond ? l3 - numGhosts : o->cs[1] + l3;
+  const int swapped = ot == 2 || ot == 4 || ot == 5 || ot == 7;
+  if (o->boundary[1] <= 2) { /* i-patch: dir 1 = j, dir 2 = k */
+    if (swapped) {
+      loc[2] = (ot == 5 || ot == 7) ? o->d2e[1] - 1 - l1 : o->d2s[1] + l1;
+      loc[1] = (ot == 4 || ot == 7) ? o->d1e[1] - 1 - l2 : o->d1s[1] + l2;
+    } else {
+      loc[1] = (ot == 6 || ot == 8) ? o->d1e[1] - 1 - l1 : o->d1s[1] + l1;
+      loc[2] = (ot == 3 || ot == 8) ? o->d2e[1] - 1 - l2 : o->d2s[1] + l2;
+    }
+    loc[0] = n3;
+  } else if (o->boundary[1] <= 4) { /* j-patch: dir 1 = k, dir 2 = i */
+    if (swapped) {
+      loc[0] = (ot == 5 || ot == 7) ? o->d2e[1] - 1 - l1 : o->d2s[1] + l1;
+      loc[2] = (ot == 4 || ot == 7) ? o->d1e[1] - 1 - l2 : o->d1s[1] + l2;
+    } else {
+      loc[2] = (ot == 3 || ot == 8) ? o->d1e[1] - 1 - l1 : o->d1s[1] + l1;
+      loc[0] = (ot == 6 || ot == 8) ? o->d2e[1] - 1 - l2 : o->d2s[1] + l2;
+    }
+    loc[1] = n3;
+  } else { /* k-patch: dir 1 = i, dir 2 = j */
+    if (swapped) {
+      loc[1] = (ot == 5 || ot == 7) ? o->d2e[1] - 1 - l1 : o->d2s[1] + l1;
+      loc[0] = (ot == 4 || ot == 7) ? o->d1e[1] - 1 - l2 : o->d1s[1] + l2;
+    } else {
+      loc[0] = (ot == 3 || ot == 8) ? o->d1e[1] - 1 - l1 : o->d1s[1] + l1;
+      loc[1] = (ot == 6 || ot == 8) ? o->d2e[1] - 1 - l2 : o->d2s[1] + l2;
+    }
+    loc[2] = n3;
+  }
+}
+/* copy of a box of a padded array (multiArray3d::Slice) */
+static double *take_slice(const orc_block *b, const double *arr, int nc,
+                          const int *lo, const int *hi) {
+  const int n0 = hi[0] - lo[0], n1 = hi[1] - lo[1], n2 = hi[2] - lo[2];
+  double *s = (double *)malloc(sizeof(double) * (size_t)n0 * n1 * n2 * nc);
+  for (int k = 0; k < n2; ++k)
+    for (int j = 0; j < n1; ++j)
+      for (int i = 0; i < n0; ++i)
+        memcpy(s + (size_t)nc * (i + (size_t)n0 * (j + (size_t)n1 * k)),
+               arr + nc * cidx(b, lo[0] + i, lo[1] + j, lo[2] + k),
+               sizeof(double) * nc);
+  return s;
+}
+/* ref: include/multiArray3d.hpp:876-926 (InsertSlice); `o` already adjusted */
+static void insert_slice(const orc_block *b, double *arr, int nc,
+                         const double *slice, const int *sn,
+                         const orc_conn *o, int d3) {
+  const int adjS1 = o->border[0] ? b->g : 0, adjE1 = o->border[1] ? b->g : 0;
+  const int adjS2 = o->border[2] ? b->g : 0, adjE2 = o->border[3] ? b->g : 0;
+  const int len1 = o->d1e[0] - o->d1s[0], len2 = o->d2e[0] - o->d2s[0];
+  for (int l3 = 0; l3 < d3; ++l3)
+    for (int l2 = adjS2; l2 < len2 - adjE2; ++l2)
+      for (int l1 = adjS1; l1 < len1 - adjE1; ++l1) {
+        int a[3], s[3];
+        get_swap_loc(l1, l2, l3, b->g, o, d3, 1, a);
+        get_swap_loc(l1, l2, l3, 0, o, d3, 0, s);
+        memcpy(arr + nc * cidx(b, a[0], a[1], a[2]),
+               slice + (size_t)nc * (s[0] + (size_t)sn[0] *
+                                                (s[1] + (size_t)sn[1] * s[2])),
+               sizeof(double) * nc);
+      }
+}
+/* ref: include/multiArray3d.hpp:790-823 (SwapSliceLocal), connection by
+ * connection in list order (src/gridLevel.cpp:297-312, src/utility.cpp:400-423);
+ * which = 0: state, 1: implicit update x */
+static void swap_connections(orc_level *h, int which) {
+  const int nc = h->neq;
+  for (int c = 0; c < h->nconn; ++c) {
+    orc_conn o;
+    conn_load(&h->conn[c], &o);
+    orc_block *b1 = &h->blk[h->conn[c].localBlock[0]];
+    orc_block *b2 = &h->blk[h->conn[c].localBlock[1]];
+    double *a1 = which == 0 ? b1->state : b1->x;
+    double *a2 = which == 0 ? b2->state : b2->x;
+    int lo1[3], hi1[3], lo2[3], hi2[3], sn1[3], sn2[3];
+    conn_slice_indices(&o, 0, b1->g, lo1, hi1);
+    conn_slice_indices(&o, 1, b2->g, lo2, hi2);
+    for (int q = 0; q < 3; ++q) { sn1[q] = hi1[q] - lo1[q]; sn2[q] = hi2[q] - lo2[q]; }
+    double *s1 = take_slice(b1, a1, nc, lo1, hi1);
+    double *s2 = take_slice(b2, a2, nc, lo2, hi2);
+    orc_conn c1 = o, c2 = o;
+    conn_adjust_for_slice(&c1, 0, b1->g);
+    conn_adjust_for_slice(&c2, 1, b2->g);
+    insert_slice(b1, a1, nc, s2, sn2, &c2, b2->g);
+    insert_slice(b2, a2, nc, s1, sn1, &c1, b1->g);
+    free(s1);
+    free(s2);
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 void orc_get_boundary_conditions(orc_level *h) {
   /* ref: src/gridLevel.cpp:287-319 */
   for (int bb = 0; bb < h->nblk; ++bb) assign_inviscid_ghosts(h, &h->blk[bb]);
-  /* connection swaps and edge ghosts: not needed by the single-block inviscid
-   * path (edge ghosts are read only by viscous / gradient stencils) */
+  swap_connections(h, 0);
+  /* edge ghosts (AssignInviscidGhostCellsEdge) are read only by viscous /
+   * gradient stencils: not needed by the inviscid path */
 }
 
 void orc_calc_residual(orc_level *h) {
@@ -1215,13 +1390,16 @@ double orc_relax(orc_level *h, int sweeps) {
   /* ref: src/linearSolver.cpp:430-471 (lusgs::Relax), :509-535 (dplur::Relax),
    * src/mgSolution.cpp:198-206 (norm of the matrix residual) */
   for (int s = 0; s < sweeps; ++s) {
+    swap_connections(h, 1);
     if (h->cfg.solver == AITHER_SOLVER_DPLUR) {
       for (int bb = 0; bb < h->nblk; ++bb) dplur_sweep(h, &h->blk[bb]);
     } else {
       for (int bb = 0; bb < h->nblk; ++bb) lusgs_forward(h, &h->blk[bb], s);
+      swap_connections(h, 1);
       for (int bb = 0; bb < h->nblk; ++bb) lusgs_backward(h, &h->blk[bb], s);
     }
   }
+  swap_connections(h, 1);
   double l2 = 0.0;
   long total = 0;
   for (int bb = 0; bb < h->nblk; ++bb) {

@@ -1,0 +1,109 @@
+"""Block connections on the GPU (-m gpu): ghost-layer exchange for the state and for the implicit
+update, through the C ABI.
+
+* against the UNMODIFIED reference's dumps of testCases/multiblockCylinder (tests/golden/),
+  phase by phase and over its 100-iteration history;
+* against the CPU oracle on split synthetic boxes (LU-SGS depends on the decomposition, reference
+  src/linearSolver.cpp:444-462, so the oracle runs the same decomposition);
+* the size-independent property the domain offers: Jacobi (DPLUR) is decomposition invariant, so
+  a box cut into 2x2x2 connected blocks must reproduce the uncut box.
+"""
+import numpy as np
+import pytest
+
+import goldencheck as gc
+import oracle
+from aither_b200 import ctypes_abi as abi
+from aither_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-13, dt=1e-13, diag=1e-13, x0=1e-12,
+           x=1e-11, matrixResid=1e-9, state=1e-12, l2=1e-12)
+
+
+def make_gpu_level(prob):
+    import aither_b200
+    return aither_b200.GridLevel(prob)
+
+
+def test_multiblock_cylinder_phases_match_reference():
+    # thin O-grid around the cylinder with strong stretching: the residual is a sum of cancelling
+    # fluxes and the CPU oracle, which follows the reference operation for operation, is itself
+    # 2.9e-13 from the reference here (tests/test_oracle_multiblock.py); the restructured device
+    # maths lands at 1.3e-12, so this one case is held to 2.5e-12 like subsonicCylinder
+    d = gc.load("multiblockCylinder")
+    for it in gc.full_iterations(d):
+        gc.check_phases(make_gpu_level, d, it, dict(TOL, residual=2.5e-12, ghosts=2.5e-12))
+
+
+def test_multiblock_cylinder_history_matches_reference():
+    d = gc.load("multiblockCylinder")
+    assert gc.check_history(make_gpu_level, d, 100, 1e-9, name="multiblockCylinder") <= 1e-9
+
+
+@pytest.mark.parametrize("splits", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 2), (3, 2, 1)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("recon", ["thirdOrder", "weno"])
+def test_dplur_is_decomposition_invariant(splits, recon):
+    import aither_b200
+    prob = synthetic.box_problem(24, 16, 12, seed=11, amplitude=0.02, sweeps=3, recon=recon)
+    sp = synthetic.split_problem(prob, splits)
+    g = prob.cfg.numGhosts
+    one, many = aither_b200.GridLevel(prob), aither_b200.GridLevel(sp)
+    nb = len(sp.blocks)
+    for it in range(4):
+        one.store_old_solution(it)
+        many.store_old_solution(it)
+        l2a, linfa, _ = one.iterate(30.0)
+        l2b, linfb, _ = many.iterate(30.0)
+        assert np.all(np.abs(l2a - l2b) <= 1e-12 * np.abs(l2a)), (it, l2a, l2b)
+        assert abs(linfa.linf - linfb.linf) <= 1e-12 * abs(linfa.linf)
+    for fld, pad in ((abi.FIELD_STATE, g), (abi.FIELD_RESIDUAL, 0), (abi.FIELD_UPDATE, g)):
+        cut = lambda a: a[pad:a.shape[0] - pad, pad:a.shape[1] - pad, pad:a.shape[2] - pad]
+        whole = cut(one.field(0, fld))
+        parts = synthetic.reassemble(sp, splits, [cut(many.field(b, fld)) for b in range(nb)])
+        scale = np.abs(whole).max(axis=(0, 1, 2))
+        assert (np.abs(whole - parts).max(axis=(0, 1, 2)) / scale).max() <= 1e-12, fld
+    one.close()
+    many.close()
+
+
+@pytest.mark.parametrize("solver,sweeps", [("lusgs", 2), ("dplur", 2)])
+def test_split_box_matches_oracle(solver, sweeps):
+    import aither_b200
+    prob = synthetic.box_problem(20, 14, 10, seed=13, amplitude=0.02, solver=solver, sweeps=sweeps,
+                                 limiter="vanAlbada")
+    sp = synthetic.split_problem(prob, (2, 2, 2))
+    g = prob.cfg.numGhosts
+    gpu, ref = aither_b200.GridLevel(sp), oracle.OracleLevel(sp)
+    for it in range(5):
+        gpu.store_old_solution(it)
+        ref.store_old_solution(it)
+        l2g, _, mrg = gpu.iterate(40.0)
+        l2r, _, mrr = ref.iterate(40.0)
+        assert np.all(np.abs(l2g - l2r) <= 1e-10 * np.abs(l2r)), (it, l2g, l2r)
+        assert abs(mrg - mrr) <= 1e-9 * abs(mrr)
+    for b in range(len(sp.blocks)):
+        sg = gpu.field(b, abi.FIELD_STATE)[g:-g, g:-g, g:-g]
+        sr = ref.field(b, abi.FIELD_STATE)[g:-g, g:-g, g:-g]
+        assert np.abs(sg - sr).max() <= 1e-12 * np.abs(sr).max()
+        # ghost layers filled by the exchange (edges excluded: never read by the inviscid path)
+        m = gc.non_edge_mask(gpu.field(b, abi.FIELD_STATE).shape[:3], g)
+        xg, xr = gpu.field(b, abi.FIELD_UPDATE), ref.field(b, abi.FIELD_UPDATE)
+        assert np.abs(xg[m] - xr[m]).max() <= 1e-11 * np.abs(xr).max()
+    gpu.close()
+    ref.close()
+
+
+def test_halo_levels_cartesian():
+    """A 2x2x2 Cartesian decomposition needs one pack/unpack level per direction."""
+    import ctypes as C
+    import aither_b200
+    prob = synthetic.box_problem(8, 8, 8, seed=1)
+    sp = synthetic.split_problem(prob, (2, 2, 2))
+    lvl = aither_b200.GridLevel(sp)
+    levels, cells = C.c_int(), C.c_longlong()
+    assert lvl._lib.aither_gpu_halo_info(lvl._h, C.byref(levels), C.byref(cells)) == 0
+    assert levels.value == 3 and cells.value == 0
+    lvl.close()

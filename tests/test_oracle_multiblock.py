@@ -1,0 +1,41 @@
+"""CPU: the oracle's connection swaps against the UNMODIFIED reference (multiblockCylinder golden)
+and its decomposition invariance on a split synthetic box."""
+import numpy as np
+
+import goldencheck as gc
+import oracle
+from aither_b200 import ctypes_abi as abi
+from aither_b200 import synthetic
+
+TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-14, dt=1e-14, diag=1e-14, x0=1e-13,
+           x=1e-12, matrixResid=1e-10, state=1e-13, l2=1e-13)
+
+
+def test_oracle_multiblock_phases_match_reference():
+    d = gc.load("multiblockCylinder")
+    for it in gc.full_iterations(d):
+        gc.check_phases(oracle.OracleLevel, d, it, TOL)
+
+
+def test_oracle_multiblock_history_matches_reference():
+    d = gc.load("multiblockCylinder")
+    assert gc.check_history(oracle.OracleLevel, d, 100, 1e-9, name="multiblockCylinder") <= 1e-9
+
+
+def test_oracle_split_box_equals_whole_box():
+    prob = synthetic.box_problem(12, 10, 8, seed=3, amplitude=0.02, sweeps=3)
+    sp = synthetic.split_problem(prob, (2, 2, 2))
+    a, b = oracle.OracleLevel(prob), oracle.OracleLevel(sp)
+    for it in range(3):
+        a.store_old_solution(it)
+        b.store_old_solution(it)
+        la, _, _ = a.iterate(30.0)
+        lb, _, _ = b.iterate(30.0)
+        assert np.all(np.abs(la - lb) <= 1e-13 * np.abs(la))
+    g = 2
+    sa = a.field(0, abi.FIELD_STATE)[g:-g, g:-g, g:-g]
+    sb = synthetic.reassemble(sp, (2, 2, 2), [b.field(i, abi.FIELD_STATE)[g:-g, g:-g, g:-g]
+                                              for i in range(8)])
+    assert np.abs(sa - sb).max() <= 1e-14 * np.abs(sa).max()
+    a.close()
+    b.close()
