@@ -222,6 +222,15 @@ def split_problem(prob, splits):
                 index[pos] = bid
                 blocks.append(Block(n[0], n[1], n[2], surfaces, arrays, parent_block=0,
                                     global_pos=bid))
+    conns = lattice_connections([(b.ni, b.nj, b.nk) for b in blocks], splits)
+    return Problem(prob.cfg, blocks, conns)
+
+
+def lattice_connections(dims, splits):
+    """`interblock` connections of a pi x pj x pk lattice of blocks (block id = a + pi (b + pj c),
+    dims[id] = (ni, nj, nk)): all i-joins, then j-joins, then k-joins; first side = lower block's
+    upper surface, second = upper block's lower surface, orientation 1."""
+    pi, pj, pk = splits
     conns = []
     for d3 in range(3):
         d1, d2 = (d3 + 1) % 3, (d3 + 2) % 3
@@ -229,13 +238,13 @@ def split_problem(prob, splits):
             for b in range(pj):
                 for a in range(pi):
                     pos = [a, b, c]
-                    if pos[d3] + 1 >= (pi, pj, pk)[d3]:
+                    if pos[d3] + 1 >= splits[d3]:
                         continue
                     up = list(pos)
                     up[d3] += 1
-                    lo_id, up_id = index[tuple(pos)], index[tuple(up)]
-                    lb = blocks[lo_id]
-                    nlo = (lb.ni, lb.nj, lb.nk)
+                    lo_id = pos[0] + pi * (pos[1] + pj * pos[2])
+                    up_id = up[0] + pi * (up[1] + pj * up[2])
+                    nlo = dims[lo_id]
                     cn = abi.Conn()
                     cn.rank[0] = cn.rank[1] = 0
                     cn.block[0], cn.block[1] = lo_id, up_id
@@ -247,7 +256,72 @@ def split_problem(prob, splits):
                     cn.constSurf[0], cn.constSurf[1] = nlo[d3], 0
                     cn.orientation, cn.isInterblock = 1, 1
                     conns.append(cn)
-    return Problem(prob.cfg, blocks, conns)
+    return conns
+
+
+def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="none", flux="roe",
+                    recon="thirdOrder", seed=0, amplitude=0.01):
+    """A pi x pj x pk lattice of n^3-cell blocks (each a unit cube of the warped box, so every block
+    is the benchmark's block) joined by `interblock` connections -- the weak-scaling workload.
+    `only`: block ids to materialise (default all); the others are dimension-only placeholders so
+    that a rank builds just the blocks it owns. Each block's ghost geometry on a joined face is its
+    neighbour's real geometry: the block's nodes are generated g cells beyond those faces from the
+    same analytic node function, metrics computed, and the extra layers cropped."""
+    pi, pj, pk = splits
+    nb = pi * pj * pk
+    g = {"constant": 1, "weno": 3, "wenoZ": 3}.get(recon, 2)
+    fluid = nondim.air(REF_RHO, REF_T)
+    free = nondim.nondim_primitive(IC["density"], IC["velocity"], IC["pressure"], REF_RHO, REF_T)
+    cfg = nondim.euler_cfg(fluid, g=g, solver=solver, sweeps=sweeps, limiter=limiter, flux=flux,
+                           recon=recon,
+                           bc_states=[dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
+                                           velocity=list(free[1:4]), pressure=free[4],
+                                           massFractions=[1.0])])
+    want = set(range(nb) if only is None else only)
+    blocks = []
+    for bid in range(nb):
+        a, b, c = bid % pi, (bid // pi) % pj, bid // (pi * pj)
+        pos = (a, b, c)
+        surfaces = []
+        ext_lo, ext_hi = [0, 0, 0], [0, 0, 0]
+        for d3 in range(3):
+            for upper in (0, 1):
+                st = 2 * d3 + 1 + upper
+                rng = [[0, n], [0, n], [0, n]]
+                rng[d3] = [n, n] if upper else [0, 0]
+                at_edge = pos[d3] == (splits[d3] - 1 if upper else 0)
+                if at_edge:
+                    t, tag = (abi.BC_CHARACTERISTIC, 1) if d3 == 0 else (abi.BC_SLIP_WALL, 0)
+                else:
+                    nbp = list(pos)
+                    nbp[d3] += 1 if upper else -1
+                    t = abi.BC_INTERBLOCK
+                    tag = (st - 1 if upper else st + 1) * 1000 + nbp[0] + pi * (nbp[1] + pj * nbp[2])
+                    (ext_hi if upper else ext_lo)[d3] = g
+                surfaces.append((t, rng[0][0], rng[0][1], rng[1][0], rng[1][1], rng[2][0],
+                                 rng[2][1], tag))
+        arrays = {"state": None}
+        if bid in want:
+            ne = [n + ext_lo[d] + ext_hi[d] for d in range(3)]
+            h = 1.0 / n
+            nodes = box_nodes(ne[0], ne[1], ne[2],
+                              lengths=tuple(ne[d] * h for d in range(3)),
+                              origin=tuple(pos[d] - ext_lo[d] * h for d in range(3)))
+            m = block_metrics(nodes, g)
+            arrays = {}
+            for name in ("vol", "fAreaI", "fAreaJ", "fAreaK", "center", "cellWidthI", "cellWidthJ",
+                         "cellWidthK"):
+                arr = m[name]
+                sl = []
+                for ax, d in ((0, 2), (1, 1), (2, 0)):
+                    extra = 1 if name == "fArea" + "IJK"[d] else 0
+                    sl.append(slice(ext_lo[d], ext_lo[d] + n + 2 * g + extra))
+                arrays[name] = np.ascontiguousarray(arr[tuple(sl)])
+            arrays["state"] = perturbed_state((n + 2 * g,) * 3, 5, seed + bid, amplitude)
+            arrays["wallDist"] = None
+        blocks.append(Block(n, n, n, surfaces, arrays, parent_block=bid, global_pos=bid))
+    conns = lattice_connections([(n, n, n)] * nb, splits)
+    return Problem(cfg, blocks, conns)
 
 
 def assign_ranks(prob, n_ranks):

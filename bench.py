@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 
 SWEEPS = 4
 CFL = 50.0
+# block lattice of the multi-GPU runs: one n^3 block per GPU, joined by interblock connections
+LATTICE = {2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
 NEQ = 5
 # algorithmic (compulsory) doubles per cell, per kernel family of one iteration
 ALG_DOUBLES = {"residual": 27, "dt_diag_init": 13, "dplur_sweep": 34, "matrix_residual": 30,
@@ -218,6 +220,10 @@ def workload_config(n=256, n_cells_note=None, gpus=1):
            "cells_per_gpu": n ** 3, "matrix_sweeps": SWEEPS,
            "l2": "inputs larger than L2 (each field %.0f MB, ~40 fields)" % (n ** 3 * 8 / 1e6),
            "parallelism": "blocks%d" % gpus}
+    if gpus > 1 and gpus in LATTICE:
+        cfg["parallelism"] = ("%dx%dx%d lattice of connected blocks, one per GPU; ghost layers of "
+                              "state and implicit update exchanged with ncclSend/ncclRecv "
+                              "(%d exchanges per iteration)" % (*LATTICE[gpus], SWEEPS + 2))
     if n_cells_note:
         cfg["sample"] = n_cells_note
     return cfg
@@ -233,20 +239,34 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = None
     n = args.n
     t_setup = time.perf_counter()
-    prob = synthetic.box_problem(n, n, n, solver="dplur", sweeps=SWEEPS, seed=rank)
-    lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world)
-    cells = prob.num_cells
+    if world > 1:
+        # weak scaling WITH halo exchange: a lattice of `world` connected n^3 blocks, one per GPU
+        # (reference `manual` decomposition, one block per rank); ghost layers of the state and of
+        # the implicit update travel with ncclSend/ncclRecv inside the library every iteration
+        import torch
+        import torch.distributed as dist
+        from aither_b200 import distributed as adist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = adist.make_comm(local)
+        splits = LATTICE[world]
+        prob = synthetic.lattice_problem(n, splits, only=[rank], solver="dplur", sweeps=SWEEPS)
+        synthetic.assign_ranks(prob, world)
+        mine = rank
+        lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world,
+                                    block_ids=[mine], nccl_comm=comm)
+    else:
+        prob = synthetic.box_problem(n, n, n, solver="dplur", sweeps=SWEEPS, seed=rank)
+        mine = 0
+        lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world)
+    cells = n ** 3
     g = prob.cfg.numGhosts
-    state_shape = prob.blocks[0].padded_shape(g) + (NEQ,)
+    state_shape = prob.blocks[mine].padded_shape(g) + (NEQ,)
     host_state = aither_b200.pinned_array(state_shape)
-    host_state[...] = prob.blocks[0].arrays["state"]
+    host_state[...] = prob.blocks[mine].arrays["state"]
     for b in prob.blocks:          # host copies of the metrics are no longer needed
         b.arrays = {"state": None}
     t_setup = time.perf_counter() - t_setup
@@ -306,8 +326,17 @@ def run_gpu_arm(args):
     # a round trip that also brings the state back to the host (output / restart iterations)
     lvl.download_state_into(0, host_state)
 
-    if rank != 0:
+    def shutdown():
         lvl.close()
+        if comm is not None:
+            from aither_b200 import distributed as adist
+            adist.destroy_comm(comm)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
     total_cells = cells * world
     value = total_cells * args.steps / (ms * 1e-3) / 1e6
@@ -352,8 +381,8 @@ def run_gpu_arm(args):
         tr = json.load(open(ncu_traffic))
         if top in tr and tr[top].get("cells") == cells:
             line["roofline"]["traffic"] = tr[top]["dram_bytes_per_launch"]
-    print(json.dumps(line))
-    lvl.close()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 def main():

@@ -1,0 +1,30 @@
+"""Cross-GPU ghost-layer exchange (ncclSend/ncclRecv inside the library), -m gpu; needs >= 2 GPUs
+on the box, otherwise skipped. One process per GPU under torch.distributed.run; the check itself
+is in tests/multigpu_worker.py (multi-process NCCL == single-process same-GPU halo == CPU oracle).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("solver", ["dplur", "lusgs"])
+def test_two_ranks_match_one_rank_and_oracle(solver):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29600 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "multigpu_worker.py"), solver]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "MULTIGPU_OK" in res.stdout, res.stdout[-4000:]
