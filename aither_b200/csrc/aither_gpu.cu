@@ -20,6 +20,7 @@
 #include "halo.cuh"
 #include "kernels.cuh"
 #include "march.cuh"
+#include "implicit_tma.cuh"
 
 using namespace aither;
 
@@ -68,6 +69,12 @@ struct HostBlock {
   dim3 marchGrid;
   int kChunk = 1;
   int nMarchBlocks = 0;
+  // TMA-fed implicit sweep (implicit_tma.cuh)
+  ImplMaps tmaMaps;
+  dim3 tmaGrid;
+  int tmaChunk = 1;
+  int nTmaBlocks = 0;
+  int nFields = 0;
 };
 
 }  // namespace
@@ -94,6 +101,8 @@ struct aither_gpu {
   long long launches = 0;
   bool keepMatrixResid = false;
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
+  bool tmaImplicit = true;         // AITHER_B200_KERNELS=march: register-fed implicit sweep
+  bool fusePrep = true;            // AITHER_B200_FUSE_PREP=0: separate PrepKernel (A/B runs)
   // timing
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   bool profile = false;
@@ -205,7 +214,7 @@ bool Supported(const aither_cfg &c, std::string *why) {
 }
 
 template <int NS, int NT, int RC, int LM, int FX>
-void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar) {
+void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fusePrep, double cfl) {
   if (h->legacyKernels) {
     ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(
         hb.dev, h->params, implicitScalar);
@@ -220,15 +229,16 @@ void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar) {
     configured = true;
   }
   kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), S::bytes, h->stream>>>(hb.dev, h->params, hb.kChunk,
-                                                                 implicitScalar);
+                                                                 implicitScalar, fusePrep, cfl);
 }
 
 template <int NS, int NT>
-int LaunchResidual(aither_gpu *h, HostBlock &hb) {
+int LaunchResidual(aither_gpu *h, HostBlock &hb, int fusePrep, double cfl) {
   const aither_cfg &c = h->cfg;
   const int implicitScalar = 1;
+  if (h->legacyKernels) fusePrep = 0;
   ScopedLaunch sl(h, kFamResidual);
-#define RES(RC, LM, FX) LaunchResidualOne<NS, NT, RC, LM, FX>(h, hb, implicitScalar)
+#define RES(RC, LM, FX) LaunchResidualOne<NS, NT, RC, LM, FX>(h, hb, implicitScalar, fusePrep, cfl)
 #define RES_FLUX(RC, LM)                         \
   do {                                           \
     if (c.invFlux == AITHER_FLUX_ROE) RES(RC, LM, AITHER_FLUX_ROE); \
@@ -261,6 +271,26 @@ void LaunchImplicitMarch(aither_gpu *h, HostBlock &hb, const double *xin, double
   }
   kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), bytes, h->stream>>>(hb.dev, h->params, xin, xout,
                                                              hb.kChunk, h->dPartials, storeField);
+}
+
+template <int NS, int NT, int MODE>
+void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *xout,
+                       int storeField) {
+  using T = ImplTma<NS, NT>;
+  auto kern = ImplicitTmaKernel<NS, NT, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(T::bytes));
+    configured = true;
+  }
+  const BlockDev &b = hb.dev;
+  const double *base = static_cast<const double *>(hb.alloc);
+  const int fX = static_cast<int>((xin - base) / b.fs);
+  const int fAi = static_cast<int>((b.fA[0] - base) / b.fs);
+  const int fAj = static_cast<int>((b.fA[1] - base) / b.fs);
+  kern<<<hb.tmaGrid, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
+      hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField);
 }
 
 int ZeroResult(aither_gpu *h, int slot) {
@@ -312,8 +342,8 @@ int PhaseBoundaryConditions(aither_gpu *h) {
   return 0;
 }
 
-int PhaseResidual(aither_gpu *h) {
-  for (auto &hb : h->blocks) LaunchResidual<1, 0>(h, hb);
+int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
+  for (auto &hb : h->blocks) LaunchResidual<1, 0>(h, hb, fusePrep, cfl);
   CK(cudaGetLastError());
   return 0;
 }
@@ -343,6 +373,8 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
           if (h->legacyKernels) {
             DplurKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
                                                                             hb.dev.x, hb.dev.xalt);
+          } else if (h->tmaImplicit) {
+            LaunchImplicitTma<1, 0, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           } else {
             LaunchImplicitMarch<1, 0, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           }
@@ -382,6 +414,9 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
       if (h->legacyKernels) {
         AxmbKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
             hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
+      } else if (h->tmaImplicit) {
+        LaunchImplicitTma<1, 0, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+        nPartials = hb.nTmaBlocks;
       } else {
         LaunchImplicitMarch<1, 0, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
         nPartials = hb.nMarchBlocks;
@@ -429,8 +464,10 @@ long long TotalPaddedSize(const aither_gpu *h) {
 int IterateAsync(aither_gpu *h, double cfl, int slot) {
   if (ZeroResult(h, slot)) return 1;
   if (PhaseBoundaryConditions(h)) return 1;
-  if (PhaseResidual(h)) return 1;
-  if (PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
+  // inviscid: time step, diagonal, right-hand side and x0 ride in the residual kernel's epilogue
+  const bool fuse = !h->legacyKernels && h->fusePrep;
+  if (PhaseResidual(h, fuse ? 1 : 0, cfl)) return 1;
+  if (!fuse && PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
   if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
   if (PhaseUpdate(h, slot)) return 1;
   return 0;
@@ -515,6 +552,9 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   {
     const char *kv = getenv("AITHER_B200_KERNELS");
     h->legacyKernels = kv != nullptr && std::string(kv) == "legacy";
+    h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march");
+    const char *fp = getenv("AITHER_B200_FUSE_PREP");
+    h->fusePrep = !(fp != nullptr && std::string(fp) == "0");
   }
 #define CKH(call)        \
   do {                   \
@@ -567,6 +607,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3;
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
+    hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
     CKC(cudaMemsetAsync(hb.alloc, 0, hb.allocBytes, h->stream));
     double *cur = static_cast<double *>(hb.alloc);
@@ -695,7 +736,26 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       hb.marchGrid = dim3((d.ni + kMI - 1) / kMI, (d.nj + kMJ - 1) / kMJ, nChunks);
       hb.nMarchBlocks = hb.marchGrid.x * hb.marchGrid.y * hb.marchGrid.z;
     }
-    maxCellBlocks = std::max<size_t>(maxCellBlocks, hb.nCellBlocks);
+    {
+      // TMA-fed implicit sweep: 32 x 16 columns, chunks of ~32 planes (2 extra end planes each)
+      const int cols = ((d.ni + kQI - 1) / kQI) * ((d.nj + kQJ - 1) / kQJ);
+      int nChunks = std::max(1, (148 * 4 + cols - 1) / cols);
+      int chunk = std::max(std::min(16, d.nk), (d.nk + nChunks - 1) / nChunks);
+      chunk = std::min(chunk, 64);
+      nChunks = (d.nk + chunk - 1) / chunk;
+      hb.tmaChunk = chunk;
+      hb.tmaGrid = dim3((d.ni + kQI - 1) / kQI, (d.nj + kQJ - 1) / kQJ, nChunks);
+      hb.nTmaBlocks = hb.tmaGrid.x * hb.tmaGrid.y * hb.tmaGrid.z;
+      std::string err;
+      if (EncodeBlockMap(&hb.tmaMaps.cell, b, hb.alloc, nFields, kQPI, kQPJ, neq, &err) ||
+          EncodeBlockMap(&hb.tmaMaps.faceI, b, hb.alloc, nFields, kQAI, kQJ, 4, &err) ||
+          EncodeBlockMap(&hb.tmaMaps.faceJ, b, hb.alloc, nFields, kQI, kQJ + 1, 4, &err)) {
+        Fail("aither_gpu_create: " + err);
+        FreeAll(h);
+        return 1;
+      }
+    }
+    maxCellBlocks = std::max<size_t>(maxCellBlocks, std::max(hb.nCellBlocks, hb.nTmaBlocks));
   }
   h->partialsCap = maxCellBlocks;
   CKC(cudaMalloc(&h->dPartials, sizeof(double) * maxCellBlocks * (AITHER_MAX_SPECIES + 6)));

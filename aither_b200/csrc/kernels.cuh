@@ -320,9 +320,10 @@ __global__ void __launch_bounds__(kResThreads)
 // K5 time step, diagonal, inverse, right-hand side b and initial update x0.
 enum PrepBits { kPrepDt = 1, kPrepDiag = 2, kPrepInit = 4 };
 
-template <int NS, int NT>
+template <int NS, int NT, bool LOCAL_RES = false>
 __device__ __forceinline__ void RhsB(const BlockDev &b, const Params &p, long long idx,
-                                     const double *s, double vol, double dt, double *out) {
+                                     const double *s, double vol, double dt, double *out,
+                                     const double *resLocal = nullptr) {
   // b = -R/theta + SolDeltaNm1 - SolDeltaMmN; ref: src/procBlock.cpp:1010-1034,
   // src/linearSolver.cpp:124-129
   using E = Eq<NS, NT>;
@@ -339,7 +340,8 @@ __device__ __forceinline__ void RhsB(const BlockDev &b, const Params &p, long lo
       nm1 = c1 * (cn - __ldg(b.consNm1 + e * b.fs + idx));
     }
     const double mmn = coeff * (cons[e] - cn);
-    out[e] = -thetaInv * __ldg(b.resid + e * b.fs + idx) + nm1 - mmn;
+    const double r = LOCAL_RES ? resLocal[e] : __ldg(b.resid + e * b.fs + idx);
+    out[e] = -thetaInv * r + nm1 - mmn;
   }
 }
 

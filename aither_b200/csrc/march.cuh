@@ -154,7 +154,8 @@ __device__ __forceinline__ void FaceFluxSmem(const BlockDev &b, const Params &p,
 
 template <int NS, int NT, int RECON, int LIM, int FLUX>
 __global__ void __launch_bounds__(kMThreads, 2)
-    ResidualMarchKernel(BlockDev b, Params p, int kChunk, int implicitScalar) {
+    ResidualMarchKernel(BlockDev b, Params p, int kChunk, int implicitScalar, int fusePrep,
+                        double cfl) {
   using E = Eq<NS, NT>;
   using S = ResSmem<NS, NT, RECON>;
   constexpr int H = S::H, PI = S::PI, PC = S::PC, NSLOT = S::NSLOT;
@@ -277,12 +278,42 @@ __global__ void __launch_bounds__(kMThreads, 2)
     // finalise the cell below (k-1): add its upper k-face flux, k-direction spectral radius
     if (colValid && k > k0) {
       const long long idxm = idx - b.sk;
+      double res[E::neq];
 #pragma unroll
-      for (int e = 0; e < E::neq; ++e) b.resid[e * b.fs + idxm] = pend[e] + fk[e];
+      for (int e = 0; e < E::neq; ++e) {
+        res[e] = pend[e] + fk[e];
+        b.resid[e * b.fs + idxm] = res[e];
+      }
       const double sr = pendSpec + InvCellSpectralRadius<NS>(sPrev, sosPrev, fAkLo, fAk);
       b.specRad[idxm] = sr;
       b.specRad[b.fs + idxm] = 0.0;
-      if (implicitScalar) b.diag[idxm] = sr;
+      if (!fusePrep) {
+        if (implicitScalar) b.diag[idxm] = sr;
+      } else {
+        // the cell's residual and spectral radius are final here, so the time step, the scalar
+        // diagonal and its inverse, the right-hand side and x0 = D^-1 b follow in the same pass
+        // (PrepKernel's arithmetic, kernels.cuh; ref src/procBlock.cpp:782-821,
+        // src/linearSolver.cpp:111-188) instead of re-reading residual and spectral radius
+        const double vol = __ldg(b.vol + idxm);
+        const double srMax = fmax(sr, 0.0);
+        const double dt = p.dtNondim > 0.0 ? p.dtNondim : cfl * (vol / srMax);
+        b.dt[idxm] = dt;
+        double diagVolTime = (vol * (1.0 + p.zeta)) / (dt * p.theta);
+        if (p.dualTimeCFL > 0.0) diagVolTime += srMax / p.dualTimeCFL;
+        double a = sr;
+        a *= p.relax;
+        a += diagVolTime;
+        b.diag[idxm] = a;
+        const double dinv = 1.0 / a;
+        b.dinv[idxm] = dinv;
+        double rb[E::neq];
+        RhsB<NS, NT, true>(b, p, idxm, sPrev, vol, dt, rb, res);
+#pragma unroll
+        for (int e = 0; e < E::neq; ++e) {
+          b.rhs[e * b.fs + idxm] = rb[e];
+          b.x[e * b.fs + idxm] = p.matrixRequiresInit ? rb[e] * dinv : 0.0;
+        }
+      }
     }
     if (k == k1) break;
     __syncthreads();

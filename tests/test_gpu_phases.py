@@ -122,3 +122,25 @@ def test_run_equals_iterate():
         assert hist[it, -1] == mr
     a.close()
     b.close()
+
+
+def test_fused_prep_equals_separate_prep(monkeypatch):
+    """iterate() folds time step / diagonal / right-hand side / x0 into the residual kernel's
+    epilogue; same formulas as the separate PrepKernel, so the histories agree to rounding (the
+    compiler contracts multiply-adds differently in the two kernels: not bit-identical)."""
+    import aither_b200
+    prob = synthetic.box_problem(40, 18, 9, seed=9, sweeps=2, limiter="vanAlbada")
+    a = aither_b200.GridLevel(prob)
+    monkeypatch.setenv("AITHER_B200_FUSE_PREP", "0")
+    b = aither_b200.GridLevel(prob)
+    monkeypatch.delenv("AITHER_B200_FUSE_PREP")
+    for it in range(4):
+        a.store_old_solution(it)
+        b.store_old_solution(it)
+        l2a, _, mra = a.iterate(35.0)
+        l2b, _, mrb = b.iterate(35.0)
+        assert np.all(np.abs(l2a - l2b) <= 1e-12 * np.abs(l2b)) and abs(mra - mrb) <= 1e-11 * mrb
+    for f in (abi.FIELD_STATE, abi.FIELD_DT, abi.FIELD_DIAG_INV, abi.FIELD_UPDATE):
+        assert rel(a.field(0, f), b.field(0, f)) <= 1e-12
+    a.close()
+    b.close()
