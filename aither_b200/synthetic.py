@@ -20,13 +20,13 @@ REF_RHO = 1.2256
 IC = dict(pressure=101300.0, density=1.2256, velocity=(100.0, 20.0, 10.0))
 
 
-def box_nodes(ni, nj, nk, lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), warp=0.02):
+def box_nodes(ni, nj, nk, lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), warp=0.02, period=1.0):
     """Node coordinates (nk+1, nj+1, ni+1, 3) of a warped box."""
     X = origin[0] + lengths[0] * np.arange(ni + 1) / ni
     Y = origin[1] + lengths[1] * np.arange(nj + 1) / nj
     Z = origin[2] + lengths[2] * np.arange(nk + 1) / nk
     zz, yy, xx = np.meshgrid(Z, Y, X, indexing="ij")
-    x = xx + warp * np.sin(2 * np.pi * yy) * np.sin(2 * np.pi * zz)
+    x = xx + warp * np.sin(2 * np.pi * yy / period) * np.sin(2 * np.pi * zz / period)
     return np.stack([x, yy, zz], axis=-1)
 
 
@@ -44,13 +44,21 @@ def write_plot3d(path, blocks_nodes):
 
 
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
-             recon="thirdOrder", flux="roe", iterations=10, ic_file=None):
+             recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
+             visc_recon="central", wall=None):
+    """`viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
+    ("isothermal", T) or ("heatFlux", q))."""
     vel = "[%g, %g, %g]" % IC["velocity"]
     state = "pressure=%g; density=%g; velocity=%s" % (IC["pressure"], IC["density"], vel)
     ic = "icState(tag=-1; %s)" % state if ic_file is None else "icState(tag=-1; file=%s)" % ic_file
+    wall_state = "viscousWall(tag=2)"
+    if wall is not None and wall[0] == "isothermal":
+        wall_state = "viscousWall(tag=2; temperature=%g)" % wall[1]
+    elif wall is not None and wall[0] == "heatFlux":
+        wall_state = "viscousWall(tag=2; heatFlux=%g)" % wall[1]
     return "\n".join([
         "gridName: %s" % name,
-        "equationSet: euler",
+        "equationSet: %s" % ("navierStokes" if viscous else "euler"),
         "timeIntegration: implicitEuler",
         "cflStart: %g" % cfl, "cflMax: %g" % cfl,
         "faceReconstruction: %s" % recon,
@@ -65,12 +73,15 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "matrixSolver: %s" % solver,
         "matrixSweeps: %d" % sweeps,
         "matrixRelaxation: 1.0",
-        "boundaryStates: <characteristic(tag=1; %s)>" % state,
+        "viscousFaceReconstruction: %s" % visc_recon,
+        ("boundaryStates: <characteristic(tag=1; %s), %s>" % (state, wall_state)) if viscous
+        else ("boundaryStates: <characteristic(tag=1; %s)>" % state),
         "boundaryConditions: 1",
         "2 2 2",
         "characteristic %d %d %d %d %d %d 1" % (0, 0, 0, nj, 0, nk),
         "characteristic %d %d %d %d %d %d 1" % (ni, ni, 0, nj, 0, nk),
-        "slipWall %d %d %d %d %d %d 0" % (0, ni, 0, 0, 0, nk),
+        ("viscousWall %d %d %d %d %d %d 2" if viscous else "slipWall %d %d %d %d %d %d 0")
+        % (0, ni, 0, 0, 0, nk),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, nj, nj, 0, nk),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, 0, nj, 0, 0),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, 0, nj, nk, nk),
@@ -94,12 +105,15 @@ def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air"):
             f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
 
 
-def write_case(case_dir, name, ni, nj, nk, perturb=None, **kw):
-    """Write `<name>.xyz` + `<name>.inp` (+ `ic.dat` when perturb=(seed, amplitude))."""
+def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
+    """Write `<name>.xyz` + `<name>.inp` (+ `ic.dat` when perturb=(seed, amplitude)). `size`: edge
+    length of the box in metres (a small box lowers the cell Reynolds number so that the viscous
+    fluxes weigh in the residual)."""
     os.makedirs(case_dir, exist_ok=True)
-    write_plot3d(os.path.join(case_dir, name + ".xyz"), [box_nodes(ni, nj, nk)])
+    nodes = box_nodes(ni, nj, nk, lengths=(size, size, size), warp=0.02 * size, period=size)
+    write_plot3d(os.path.join(case_dir, name + ".xyz"), [nodes])
     if perturb is not None:
-        write_cloud(os.path.join(case_dir, "ic.dat"), box_nodes(ni, nj, nk), *perturb)
+        write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb)
         kw["ic_file"] = "ic.dat"
     with open(os.path.join(case_dir, name + ".inp"), "w") as f:
         f.write(inp_text(name, ni, nj, nk, **kw))

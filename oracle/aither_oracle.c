@@ -31,6 +31,7 @@ typedef struct {
   double *consNm1;   /* ni nj nk neq */
   double *mresid;    /* ni nj nk neq: matrix residual */
   double *temperature; /* padded */
+  double *viscosity;   /* padded (viscous only) */
   const double *vol, *fAI, *fAJ, *fAK, *center, *cwI, *cwJ, *cwK, *wallDist;
   int *order; /* hyperplane ordering: 3 ints per cell */
 } orc_block;
@@ -577,9 +578,10 @@ static void extrapolate_hold_mixture(const orc_level *h, const double *bnd,
 }
 
 /* ref: src/ghostStates.cpp:62-689 (GetGhostState), inviscid / low-Re subset */
+static double eff_conductivity(const orc_level *h, double t);
 static void ghost_state(const orc_level *h, const double *interior, int bcType,
                         const double areaVec[3], int surf, int tag, int layer,
-                        double *ghost) {
+                        double wallDist, double *ghost) {
   const int ns = h->ns, neq = h->neq;
   const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3;
   for (int e = 0; e < neq; ++e) ghost[e] = interior[e];
@@ -593,6 +595,30 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     ghost[imx] = interior[imx] - 2.0 * nA[0] * vn;
     ghost[imy] = interior[imy] - 2.0 * nA[1] * vn;
     ghost[imz] = interior[imz] - 2.0 * nA[2] * vn;
+  } else if (bcType == AITHER_BC_VISCOUS_WALL) { /* ref: :134-258, low-Re */
+    const aither_bc_state *bc = bc_data(h, tag);
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    const double *velWall = bc ? bc->velocity : zero3;
+    ghost[imx] = 2.0 * velWall[0] - interior[imx];
+    ghost[imy] = 2.0 * velWall[1] - interior[imy];
+    ghost[imz] = 2.0 * velWall[2] - interior[imz];
+    if (bc && (bc->isIsothermal || bc->isConstantHeatFlux)) {
+      double mf[AITHER_MAX_SPECIES];
+      mass_fractions(h, interior, mf);
+      double tGhost;
+      if (bc->isIsothermal) { /* ref: :183-189 */
+        tGhost = 2.0 * bc->temperature - temperature_of(h, interior);
+      } else { /* ref: :226-236 */
+        const double t = temperature_of(h, interior);
+        const double kappa = eff_conductivity(h, t);
+        tGhost = temperature_of(h, interior) -
+                 bc->heatFlux / kappa * 2.0 * wallDist;
+      }
+      double R = 0.0; /* ref: src/eos.cpp:111-115 (DensityTP) */
+      for (int ss = 0; ss < ns; ++ss) R += mf[ss] * h->cfg.gasConstant[ss];
+      const double rho = ghost[ie] / (R * tGhost);
+      for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * mf[ss];
+    }
   } else if (bcType == AITHER_BC_CHARACTERISTIC) { /* ref: :289-386 */
     const aither_bc_state *bc = bc_data(h, tag);
     double freeState[MAXEQ];
@@ -823,7 +849,7 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
                                    : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
             double ghost[MAXEQ];
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]), bcType,
-                        fa, st, sf->tag, layer, ghost);
+                        fa, st, sf->tag, layer, 0.0, ghost);
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -908,6 +934,35 @@ static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* transport: Sutherland (ref: src/transport.cpp:113-196); single species     */
+static double species_viscosity(const orc_level *h, double t, int ss) {
+  const double temp = t * h->cfg.tRef;
+  const double mu =
+      (h->cfg.suthViscC1[ss] * pow(temp, 1.5)) / (temp + h->cfg.suthViscS[ss]);
+  return mu / h->cfg.muMixRef;
+}
+static double viscosity_of(const orc_level *h, double t) {
+  if (h->ns != 1) {
+    fprintf(stderr, "oracle: Wilke mixing rule is not restated (ns > 1)\n");
+    abort();
+  }
+  return species_viscosity(h, t, 0);
+}
+static double conductivity_of(const orc_level *h, double t) {
+  const double temp = t * h->cfg.tRef;
+  const double k =
+      (h->cfg.suthCondC1[0] * pow(temp, 1.5)) / (temp + h->cfg.suthCondS[0]);
+  return k / h->cfg.kMixRef;
+}
+static double eff_conductivity(const orc_level *h, double t) {
+  return conductivity_of(h, t) * h->cfg.nondimScaling;
+}
+/* ref: include/thermodynamic.hpp:61-64 */
+static double prandtl_of(double gamma) {
+  return (4.0 * gamma) / (9.0 * gamma - 5.0);
+}
+
 /* ref: src/procBlock.cpp:6171-6190 (UpdateAuxillaryVariables) */
 static void update_aux(orc_level *h, orc_block *b) {
   for (int kk = -b->g; kk < b->nk + b->g; ++kk)
@@ -916,11 +971,343 @@ static void update_aux(orc_level *h, orc_block *b) {
         const int oi = ii < 0 || ii >= b->ni, oj = jj < 0 || jj >= b->nj,
                   ok = kk < 0 || kk >= b->nk;
         if (oi + oj + ok == 3) continue; /* corner */
-        b->temperature[cidx(b, ii, jj, kk)] =
-            temperature_of(h, b->state + h->neq * cidx(b, ii, jj, kk));
+        const long c = cidx(b, ii, jj, kk);
+        b->temperature[c] = temperature_of(h, b->state + h->neq * c);
+        if (h->cfg.isViscous)
+          b->viscosity[c] = viscosity_of(h, b->temperature[c]);
       }
 }
 
+/* ------------------------------------------------------------------------ */
+/* edge ghost cells and viscous-wall ghost cells                              */
+/* multiArray3d::operator()(dir, d1, d2, d3): include/multiArray3d.hpp:231-243 */
+static void dir_ijk(int dd, int d1, int d2, int d3, int *c) {
+  if (dd == 0) { c[0] = d1; c[1] = d2; c[2] = d3; }
+  else if (dd == 1) { c[0] = d3; c[1] = d1; c[2] = d2; }
+  else { c[0] = d2; c[1] = d3; c[2] = d1; }
+}
+/* ref: src/boundaryConditions.cpp:109-185 (GetBCSurface) */
+static const aither_surface *find_surface(const orc_block *b, int i, int j,
+                                          int k, int surf) {
+  for (int s = 0; s < b->nsurf; ++s) {
+    const aither_surface *sf = &b->surf[s];
+    const int st = surface_type(sf);
+    if ((st - 1) / 2 != (surf - 1) / 2) continue;
+    int in;
+    if (surf <= 2)
+      in = i >= sf->imin && i <= sf->imax && j >= sf->jmin && j < sf->jmax &&
+           k >= sf->kmin && k < sf->kmax;
+    else if (surf <= 4)
+      in = i >= sf->imin && i < sf->imax && j >= sf->jmin && j <= sf->jmax &&
+           k >= sf->kmin && k < sf->kmax;
+    else
+      in = i >= sf->imin && i < sf->imax && j >= sf->jmin && j < sf->jmax &&
+           k >= sf->kmin && k <= sf->kmax;
+    if (in) return sf;
+  }
+  fprintf(stderr, "oracle: no boundary surface at %d %d %d (surf %d)\n", i, j, k,
+          surf);
+  abort();
+  return NULL;
+}
+static const double *face_area_dir(const orc_block *b, int faceDir, int dd,
+                                   int d1, int d2, int d3) {
+  int c[3];
+  dir_ijk(dd, d1, d2, d3, c);
+  return faceDir == 0 ? b->fAI + 4 * fidxI(b, c[0], c[1], c[2])
+                      : (faceDir == 1 ? b->fAJ + 4 * fidxJ(b, c[0], c[1], c[2])
+                                      : b->fAK + 4 * fidxK(b, c[0], c[1], c[2]));
+}
+/* ref: src/procBlock.cpp:2565-2703 (AssignInviscidGhostCellsEdge, viscous = 0)
+ * and :2873-3025 (AssignViscousGhostCellsEdge, viscous = 1) */
+static void assign_ghost_edges(orc_level *h, orc_block *b, int viscous) {
+  const int neq = h->neq, g = b->g;
+  const int nd[3] = {b->ni, b->nj, b->nk};
+  for (int dd = 0; dd < 3; ++dd) {
+    const int max1 = nd[dd], max2 = nd[(dd + 1) % 3], max3 = nd[(dd + 2) % 3];
+    const int surfStart2 = 2 * ((dd + 1) % 3) + 1, surfStart3 = 2 * ((dd + 2) % 3) + 1;
+    const int fd2 = (dd + 1) % 3, fd3 = (dd + 2) % 3; /* face arrays of dirs 2, 3 */
+    for (int layer3 = 1; layer3 <= g; ++layer3)
+      for (int layer2 = 1; layer2 <= g; ++layer2)
+        for (int cc = 0; cc < 4; ++cc) {
+          const int upper2 = cc > 1, upper3 = cc % 2 == 1;
+          const int pCellD2 = upper2 ? max2 + layer2 - 2 : 1 - layer2;
+          const int gCellD2 = upper2 ? pCellD2 + 1 : pCellD2 - 1;
+          const int pCellD3 = upper3 ? max3 + layer3 - 2 : 1 - layer3;
+          const int gCellD3 = upper3 ? pCellD3 + 1 : pCellD3 - 1;
+          const int surf2 = upper2 ? surfStart2 + 1 : surfStart2;
+          const int surf3 = upper3 ? surfStart3 + 1 : surfStart3;
+          const int cFaceD2_2 = upper2 ? max2 : 0, cFaceD2_3 = upper3 ? max3 - 1 : 0;
+          const int cFaceD3_2 = upper2 ? max2 - 1 : 0, cFaceD3_3 = upper3 ? max3 : 0;
+          for (int d1 = 0; d1 < max1; ++d1) {
+            int c2[3], c3[3], cg[3], cp2[3], cp3[3];
+            dir_ijk(dd, d1, cFaceD2_2, cFaceD2_3, c2);
+            dir_ijk(dd, d1, cFaceD3_2, cFaceD3_3, c3);
+            const aither_surface *s2 = find_surface(b, c2[0], c2[1], c2[2], surf2);
+            const aither_surface *s3 = find_surface(b, c3[0], c3[1], c3[2], surf3);
+            const double *fArea2 = face_area_dir(b, fd2, dd, d1, cFaceD2_2, gCellD3);
+            const double *fArea3 = face_area_dir(b, fd3, dd, d1, gCellD2, cFaceD3_3);
+            int bc2 = s2->type, bc3 = s3->type;
+            if (!viscous) {
+              if (bc2 == AITHER_BC_VISCOUS_WALL) bc2 = AITHER_BC_SLIP_WALL;
+              if (bc3 == AITHER_BC_VISCOUS_WALL) bc3 = AITHER_BC_SLIP_WALL;
+            }
+            int cw2[3], cw3[3];
+            dir_ijk(dd, d1, cFaceD3_2, gCellD3, cw2);
+            dir_ijk(dd, d1, gCellD2, cFaceD2_3, cw3);
+            const double wDist2 = b->wallDist ? b->wallDist[cidx(b, cw2[0], cw2[1], cw2[2])] : 0.0;
+            const double wDist3 = b->wallDist ? b->wallDist[cidx(b, cw3[0], cw3[1], cw3[2])] : 0.0;
+            dir_ijk(dd, d1, gCellD2, gCellD3, cg);
+            dir_ijk(dd, d1, pCellD2, gCellD3, cp2);
+            dir_ijk(dd, d1, gCellD2, pCellD3, cp3);
+            double *dst = b->state + neq * cidx(b, cg[0], cg[1], cg[2]);
+            const double *from2 = b->state + neq * cidx(b, cp2[0], cp2[1], cp2[2]);
+            const double *from3 = b->state + neq * cidx(b, cp3[0], cp3[1], cp3[2]);
+            double ghost[MAXEQ];
+            /* the viscous variant tests the literal string "slipWall" while the
+             * types are unmapped there (:2994-3005), so in it a viscous wall is
+             * never extended by this branch pair -- only the both-viscousWall
+             * averaging below applies */
+            if (bc2 == AITHER_BC_SLIP_WALL && bc3 != AITHER_BC_SLIP_WALL) {
+              ghost_state(h, from2, bc2, fArea2, surf2, s2->tag, layer2, wDist2, ghost);
+              memcpy(dst, ghost, sizeof(double) * neq);
+            } else if (bc2 != AITHER_BC_SLIP_WALL && bc3 == AITHER_BC_SLIP_WALL) {
+              ghost_state(h, from3, bc3, fArea3, surf3, s3->tag, layer3, wDist3, ghost);
+              memcpy(dst, ghost, sizeof(double) * neq);
+            } else if (!viscous || (bc2 == AITHER_BC_VISCOUS_WALL &&
+                                    bc3 == AITHER_BC_VISCOUS_WALL)) {
+              if (layer2 == layer3) {
+                for (int e = 0; e < neq; ++e) ghost[e] = 0.5 * (from2[e] + from3[e]);
+                memcpy(dst, ghost, sizeof(double) * neq);
+              } else if (layer2 > layer3) {
+                memcpy(ghost, from3, sizeof(double) * neq);
+                memcpy(dst, ghost, sizeof(double) * neq);
+              } else {
+                memcpy(ghost, from2, sizeof(double) * neq);
+                memcpy(dst, ghost, sizeof(double) * neq);
+              }
+            }
+          }
+        }
+  }
+}
+
+/* ref: src/procBlock.cpp:2760-2836 (AssignViscousGhostCells) */
+static void assign_viscous_ghosts(orc_level *h, orc_block *b) {
+  const int neq = h->neq;
+  for (int layer = 1; layer <= b->g; ++layer) {
+    for (int s = 0; s < b->nsurf; ++s) {
+      const aither_surface *sf = &b->surf[s];
+      if (sf->type != AITHER_BC_VISCOUS_WALL) continue;
+      const int st = surface_type(sf);
+      const int d3 = (st - 1) / 2;
+      const int nd[3] = {b->ni, b->nj, b->nk};
+      const int r3 = d3 == 0 ? sf->imin : (d3 == 1 ? sf->jmin : sf->kmin);
+      int gCell, iCell, aCell;
+      if (st % 2 == 0) {
+        gCell = r3 + layer - 1;
+        iCell = r3 - layer;
+        aCell = r3 - 1;
+        if (iCell < 0) iCell = 0;
+      } else {
+        gCell = r3 - layer;
+        iCell = r3 + layer - 1;
+        aCell = r3;
+        if (iCell >= nd[d3]) iCell = nd[d3] - 1;
+      }
+      int lo[3] = {sf->imin, sf->jmin, sf->kmin};
+      int hi[3] = {sf->imax, sf->jmax, sf->kmax};
+      lo[d3] = 0;
+      hi[d3] = 1;
+      for (int kk = lo[2]; kk < hi[2]; ++kk)
+        for (int jj = lo[1]; jj < hi[1]; ++jj)
+          for (int ii = lo[0]; ii < hi[0]; ++ii) {
+            int ci[3] = {ii, jj, kk}, cg[3] = {ii, jj, kk}, cf[3] = {ii, jj, kk},
+                ca[3] = {ii, jj, kk};
+            ci[d3] = iCell;
+            cg[d3] = gCell;
+            cf[d3] = r3;
+            ca[d3] = aCell;
+            const double *fa =
+                d3 == 0 ? b->fAI + 4 * fidxI(b, cf[0], cf[1], cf[2])
+                        : (d3 == 1 ? b->fAJ + 4 * fidxJ(b, cf[0], cf[1], cf[2])
+                                   : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
+            const double wd = b->wallDist ? b->wallDist[cidx(b, ca[0], ca[1], ca[2])] : 0.0;
+            double ghost[MAXEQ];
+            ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]),
+                        AITHER_BC_VISCOUS_WALL, fa, st, sf->tag, layer, wd, ghost);
+            memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
+                   sizeof(double) * neq);
+          }
+    }
+  }
+  assign_ghost_edges(h, b, 1);
+}
+
+/* ------------------------------------------------------------------------ */
+/* viscous fluxes                                                             */
+static void area_vec(const double *fa, double *v) {
+  v[0] = fa[0] * fa[3]; /* unitVec3dMag::Vector(): unit * mag */
+  v[1] = fa[1] * fa[3];
+  v[2] = fa[2] * fa[3];
+}
+static const double *farea(const orc_block *b, int d, int i, int j, int k) {
+  return d == 0 ? b->fAI + 4 * fidxI(b, i, j, k)
+                : (d == 1 ? b->fAJ + 4 * fidxJ(b, i, j, k)
+                          : b->fAK + 4 * fidxK(b, i, j, k));
+}
+/* Green-Gauss gradients of velocity and temperature on the control volume
+ * centred on face (i,j,k) of direction d; ref: src/procBlock.cpp:5173-5303
+ * (I), :5378-5508 (J), :5584-5714 (K); src/utility.cpp:59-175 */
+static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
+                           int j, int k, double vg[9], double tg[3]) {
+  const int ns = h->ns, neq = h->neq;
+  const int e3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const int *ed = e3[d];
+  /* areas of the alternate control volume, per direction q: lower, upper */
+  double al[3][3], au[3][3];
+  for (int q = 0; q < 3; ++q) {
+    double a0[3], a1[3];
+    if (q == d) {
+      area_vec(farea(b, d, i, j, k), a0);
+      area_vec(farea(b, d, i + ed[0], j + ed[1], k + ed[2]), a1);
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      area_vec(farea(b, d, i - ed[0], j - ed[1], k - ed[2]), a1);
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    } else {
+      const int *eq = e3[q];
+      area_vec(farea(b, q, i + eq[0], j + eq[1], k + eq[2]), a0);
+      area_vec(farea(b, q, i + eq[0] - ed[0], j + eq[1] - ed[1], k + eq[2] - ed[2]), a1);
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      area_vec(farea(b, q, i, j, k), a0);
+      area_vec(farea(b, q, i - ed[0], j - ed[1], k - ed[2]), a1);
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    }
+  }
+  const double vol = 0.5 * (b->vol[cidx(b, i - ed[0], j - ed[1], k - ed[2])] +
+                            b->vol[cidx(b, i, j, k)]);
+  /* values on the faces of the control volume: 3 velocity components + T */
+  double vl[3][4], vu[3][4];
+  const long cLo = cidx(b, i - ed[0], j - ed[1], k - ed[2]), cHi = cidx(b, i, j, k);
+  for (int c = 0; c < 4; ++c) {
+#define VAL(cell) (c < 3 ? b->state[neq * (cell) + ns + c] : b->temperature[(cell)])
+    for (int q = 0; q < 3; ++q) {
+      if (q == d) {
+        vl[q][c] = VAL(cLo);
+        vu[q][c] = VAL(cHi);
+      } else {
+        const int *eq = e3[q];
+        const long up0 = cidx(b, i + eq[0], j + eq[1], k + eq[2]);
+        const long up1 = cidx(b, i + eq[0] - ed[0], j + eq[1] - ed[1], k + eq[2] - ed[2]);
+        const long lo0 = cidx(b, i - eq[0], j - eq[1], k - eq[2]);
+        const long lo1 = cidx(b, i - eq[0] - ed[0], j - eq[1] - ed[1], k - eq[2] - ed[2]);
+        vu[q][c] = 0.25 * (VAL(cLo) + VAL(cHi) + VAL(up0) + VAL(up1));
+        vl[q][c] = 0.25 * (VAL(cLo) + VAL(cHi) + VAL(lo0) + VAL(lo1));
+      }
+    }
+#undef VAL
+  }
+  const double invVol = 1.0 / vol;
+  /* velGrad(r, c) = d u_c / d x_r */
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double t = vu[0][c] * au[0][r] - vl[0][c] * al[0][r] +
+                       vu[1][c] * au[1][r] - vl[1][c] * al[1][r] +
+                       vu[2][c] * au[2][r] - vl[2][c] * al[2][r];
+      vg[3 * r + c] = t * invVol;
+    }
+  for (int r = 0; r < 3; ++r) {
+    const double t = vu[0][3] * au[0][r] - vl[0][3] * al[0][r] +
+                     vu[1][3] * au[1][r] - vl[1][3] * al[1][r] +
+                     vu[2][3] * au[2][r] - vl[2][3] * al[2][r];
+    tg[r] = t * invVol;
+  }
+}
+/* ref: src/utility.cpp:425-437 (TauNormal), src/transport.cpp:173-176 (Lambda) */
+static void tau_normal(const double vg[9], const double n[3], double mu,
+                       double mut, double tau[3]) {
+  const double lambda = 0.0 - (2.0 / 3.0) * (mu + mut);
+  const double trace = vg[0] + vg[4] + vg[8];
+  for (int r = 0; r < 3; ++r) {
+    double mm = 0.0; /* ((G + G^T) n)_r */
+    for (int c = 0; c < 3; ++c) mm += (vg[3 * r + c] + vg[3 * c + r]) * n[c];
+    tau[r] = lambda * trace * n[r] + (mu + mut) * mm;
+  }
+}
+/* ref: src/procBlock.cpp:1233-1497 (CalcViscFluxI; J, K alike), laminar */
+static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
+  const int neq = h->neq, ns = h->ns;
+  const int nd[3] = {b->ni, b->nj, b->nk};
+  const int di = d == 0, dj = d == 1, dk = d == 2;
+  const double *cw = d == 0 ? b->cwI : (d == 1 ? b->cwJ : b->cwK);
+  const double viscCoeff = h->cfg.viscousCFLCoeff;
+  for (int kk = 0; kk < b->nk + dk; ++kk)
+    for (int jj = 0; jj < b->nj + dj; ++jj)
+      for (int ii = 0; ii < b->ni + di; ++ii) {
+        const int fi = d == 0 ? ii : (d == 1 ? jj : kk);
+        double vg[9], tg[3];
+        face_gradients(h, b, d, ii, jj, kk, vg, tg);
+        double state[MAXEQ], mu;
+#define CL(o) cidx(b, ii + (o)*di, jj + (o)*dj, kk + (o)*dk)
+        if (h->cfg.viscRecon == 0) { /* central; ref: :1305-1321 */
+          const double w[2] = {cw[CL(-1)], cw[CL(0)]};
+          double c[2];
+          lagrange_coeff(w, 1, 0, 0, c);
+          for (int e = 0; e < neq; ++e)
+            state[e] = c[0] * b->state[neq * CL(0) + e] + c[1] * b->state[neq * CL(-1) + e];
+          mu = c[0] * b->viscosity[CL(0)] + c[1] * b->viscosity[CL(-1)];
+        } else { /* centralFourth; ref: :1323-1346 */
+          const double w[4] = {cw[CL(-2)], cw[CL(-1)], cw[CL(0)], cw[CL(1)]};
+          double c[4];
+          lagrange_coeff(w, 3, 1, 1, c);
+          for (int e = 0; e < neq; ++e)
+            state[e] = c[0] * b->state[neq * CL(-2) + e] + c[1] * b->state[neq * CL(-1) + e] +
+                       c[2] * b->state[neq * CL(0) + e] + c[3] * b->state[neq * CL(1) + e];
+          mu = c[0] * b->viscosity[CL(-2)] + c[1] * b->viscosity[CL(-1)] +
+               c[2] * b->viscosity[CL(0)] + c[3] * b->viscosity[CL(1)];
+        }
+        /* viscousFlux::CalcFlux; ref: src/viscousFlux.cpp:58-135 */
+        const double *fa = farea(b, d, ii, jj, kk);
+        const double mus = h->cfg.nondimScaling * mu;
+        const double muts = h->cfg.nondimScaling * 0.0;
+        double tau[3], flux[MAXEQ];
+        for (int e = 0; e < neq; ++e) flux[e] = 0.0;
+        tau_normal(vg, fa, mus, muts, tau);
+        flux[ns] = tau[0];
+        flux[ns + 1] = tau[1];
+        flux[ns + 2] = tau[2];
+        const double t = temperature_of(h, state);
+        const double kcond = eff_conductivity(h, t);
+        const double kt = 0.0;
+        flux[ns + 3] = (tau[0] * state[ns] + tau[1] * state[ns + 1] + tau[2] * state[ns + 2]) +
+                       (kcond + kt) * (tg[0] * fa[0] + tg[1] * fa[1] + tg[2] * fa[2]) + 0.0;
+        /* residual: opposite sign to the inviscid flux; ref: :1392-1429 */
+        if (fi > 0) {
+          double *r = b->residual + neq * pidx(b, ii - di, jj - dj, kk - dk);
+          for (int e = 0; e < neq; ++e) r[e] -= flux[e] * fa[3];
+        }
+        if (fi < nd[d]) {
+          double *r = b->residual + neq * pidx(b, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) r[e] += flux[e] * fa[3];
+          /* ViscCellSpectralRadius; ref: include/spectralRadius.hpp:94-124 */
+          const double *s = b->state + neq * CL(0);
+          const double *fu = farea(b, d, ii + di, jj + dj, kk + dk);
+          const double fMag = 0.5 * (fa[3] + fu[3]);
+          const double rho = rho_of(h, s);
+          const double gam = gamma_of(h, s);
+          const double a43 = 4.0 / (3.0 * rho), gr = gam / rho;
+          const double maxTerm = a43 > gr ? a43 : gr;
+          const double viscTerm =
+              h->cfg.nondimScaling * (b->viscosity[CL(0)] / prandtl_of(gam) + 0.0 / 0.9);
+          const double vsr = maxTerm * viscTerm * fMag * fMag / b->vol[CL(0)];
+          double *sp = b->specRad + 2 * pidx(b, ii, jj, kk);
+          sp[0] += vsr * viscCoeff;
+          sp[1] += 0.0 * viscCoeff;
+          if (!h->cfg.isBlockMatrix) b->a[h->asz * pidx(b, ii, jj, kk)] += 2.0 * vsr;
+        }
+#undef CL
+      }
+}
 
 /* ------------------------------------------------------------------------ */
 /* connection (interblock / periodic) ghost swaps                            */
@@ -1100,8 +1487,7 @@ void orc_get_boundary_conditions(orc_level *h) {
   /* ref: src/gridLevel.cpp:287-319 */
   for (int bb = 0; bb < h->nblk; ++bb) assign_inviscid_ghosts(h, &h->blk[bb]);
   swap_connections(h, 0);
-  /* edge ghosts (AssignInviscidGhostCellsEdge) are read only by viscous /
-   * gradient stencils: not needed by the inviscid path */
+  for (int bb = 0; bb < h->nblk; ++bb) assign_ghost_edges(h, &h->blk[bb], 0);
 }
 
 void orc_calc_residual(orc_level *h) {
@@ -1114,7 +1500,15 @@ void orc_calc_residual(orc_level *h) {
     calc_inv_flux(h, b, 0);
     calc_inv_flux(h, b, 1);
     calc_inv_flux(h, b, 2);
-    update_aux(h, b);
+    if (h->cfg.isViscous) { /* ref: src/procBlock.cpp:6125-6137 */
+      assign_viscous_ghosts(h, b);
+      update_aux(h, b);
+      calc_visc_flux(h, b, 0);
+      calc_visc_flux(h, b, 1);
+      calc_visc_flux(h, b, 2);
+    } else {
+      update_aux(h, b);
+    }
   }
 }
 
@@ -1218,13 +1612,23 @@ void orc_initialize_matrix_update(orc_level *h) {
 /* ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal), inviscid */
 static void offdiag_scalar(const orc_level *h, const double *state,
                            const double *du, const double *fArea, int positive,
-                           double *out) {
+                           double mu, double dist, double *out) {
   const int neq = h->neq;
   double su[MAXEQ], fo[MAXEQ], fn[MAXEQ];
   update_prim_with_cons(h, state, du, su);
   physical_flux(h, state, fArea, fo);
   physical_flux(h, su, fArea, fn);
-  const double sr = inv_face_spec_rad(h, state, fArea);
+  double sr = inv_face_spec_rad(h, state, fArea);
+  if (h->cfg.isViscous) {
+    /* ref: include/spectralRadius.hpp:126-151,180-200 (Visc/FaceSpectralRadius) */
+    const double rho = rho_of(h, state);
+    const double gam = gamma_of(h, state);
+    const double a43 = 4.0 / (3.0 * rho), gr = gam / rho;
+    const double maxTerm = a43 > gr ? a43 : gr;
+    const double viscTerm =
+        h->cfg.nondimScaling * (mu / prandtl_of(gam) + 0.0 / 0.9);
+    sr += fArea[3] / dist * maxTerm * viscTerm;
+  }
   for (int e = 0; e < neq; ++e) {
     double fc = 0.5 * fArea[3] * (fn[e] - fo[e]);
     if (e >= h->ns + 4) fc = 0.0;
@@ -1256,6 +1660,19 @@ static int bc_is_connection(const orc_block *b, int i, int j, int k, int surf) {
   return 0;
 }
 
+/* ref: src/procBlock.cpp:6316-6341 (ProjC2CDist): face (ii,jj,kk) of direction d */
+static double proj_c2c_dist(const orc_block *b, int d, int ii, int jj, int kk) {
+  if (!b->center) return 1.0;
+  const double *cu = b->center + 3 * cidx(b, ii, jj, kk);
+  const double *cl = b->center + 3 * cidx(b, ii - (d == 0), jj - (d == 1), kk - (d == 2));
+  const double *fa = d == 0 ? b->fAI + 4 * fidxI(b, ii, jj, kk)
+                            : (d == 1 ? b->fAJ + 4 * fidxJ(b, ii, jj, kk)
+                                      : b->fAK + 4 * fidxK(b, ii, jj, kk));
+  return (cu[0] - cl[0]) * fa[0] + (cu[1] - cl[1]) * fa[1] + (cu[2] - cl[2]) * fa[2];
+}
+static double visc_at(const orc_level *h, const orc_block *b, int ii, int jj, int kk) {
+  return h->cfg.isViscous ? b->viscosity[cidx(b, ii, jj, kk)] : 0.0;
+}
 /* ref: src/procBlock.cpp:1056-1104 (ImplicitLower) */
 static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
                            int jj, int kk, const double *x, double *L) {
@@ -1265,19 +1682,22 @@ static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
   if (is_physical(b, ii - 1, jj, kk) || bc_is_connection(b, ii, jj, kk, 1)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii - 1, jj, kk),
                    x + neq * cidx(b, ii - 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, od);
+                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, visc_at(h, b, ii - 1, jj, kk),
+                   proj_c2c_dist(b, 0, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj - 1, kk) || bc_is_connection(b, ii, jj, kk, 3)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj - 1, kk),
                    x + neq * cidx(b, ii, jj - 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, od);
+                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, visc_at(h, b, ii, jj - 1, kk),
+                   proj_c2c_dist(b, 1, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk - 1) || bc_is_connection(b, ii, jj, kk, 5)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk - 1),
                    x + neq * cidx(b, ii, jj, kk - 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, od);
+                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, visc_at(h, b, ii, jj, kk - 1),
+                   proj_c2c_dist(b, 2, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
 }
@@ -1290,19 +1710,22 @@ static void implicit_upper(const orc_level *h, const orc_block *b, int ii,
   if (is_physical(b, ii + 1, jj, kk) || bc_is_connection(b, ii + 1, jj, kk, 2)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii + 1, jj, kk),
                    x + neq * cidx(b, ii + 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, od);
+                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, visc_at(h, b, ii + 1, jj, kk),
+                   proj_c2c_dist(b, 0, ii + 1, jj, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj + 1, kk) || bc_is_connection(b, ii, jj + 1, kk, 4)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj + 1, kk),
                    x + neq * cidx(b, ii, jj + 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, od);
+                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, visc_at(h, b, ii, jj + 1, kk),
+                   proj_c2c_dist(b, 1, ii, jj + 1, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk + 1) || bc_is_connection(b, ii, jj, kk + 1, 6)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk + 1),
                    x + neq * cidx(b, ii, jj, kk + 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, od);
+                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, visc_at(h, b, ii, jj, kk + 1),
+                   proj_c2c_dist(b, 2, ii, jj, kk + 1), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
 }
@@ -1546,6 +1969,7 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
     b->consNm1 = (double *)calloc(nc * h->neq, sizeof(double));
     b->mresid = (double *)calloc(nc * h->neq, sizeof(double));
     b->temperature = (double *)calloc(np, sizeof(double));
+    b->viscosity = (double *)calloc(np, sizeof(double));
     b->vol = d->vol;
     b->fAI = d->fAreaI;
     b->fAJ = d->fAreaJ;
@@ -1578,7 +2002,7 @@ void orc_destroy(orc_level *h) {
     free(b->surf); free(b->state); free(b->residual); free(b->specRad);
     free(b->dt); free(b->a); free(b->ainv); free(b->x); free(b->xold);
     free(b->consN); free(b->consNm1); free(b->mresid); free(b->temperature);
-    free(b->order);
+    free(b->viscosity); free(b->order);
   }
   free(h->blk);
   free(h->conn);
@@ -1650,12 +2074,12 @@ void orc_ghost_state(const aither_cfg *cfg, const double *interior, int bcType,
                      double *ghost) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, ghost);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, ghost);
 }
 void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
                         const double *duNb, const double fArea[4], int positive,
                         double *out) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  offdiag_scalar(&h, stateNb, duNb, fArea, positive, out);
+  offdiag_scalar(&h, stateNb, duNb, fArea, positive, 0.0, 1.0, out);
 }

@@ -209,6 +209,7 @@ void DumpConfig(Dump &d, const input &inp, const physics &phys) {
   d.vec("cfg/hf", hf);
   d.vec("cfg/mixtureRef", inp.MixtureRef());
   d.scalar("cfg/nondimScaling", phys.Transport()->NondimScaling());
+  d.scalar("cfg/muMixRef", phys.Transport()->MuRef());
   // transport (sutherland) coefficients, per species
   {
     std::vector<double> vc1(ns), vs(ns), kc1(ns), ks(ns), mm(ns);

@@ -44,6 +44,19 @@ CASES = {
                                         limiter="vanAlbada", flux="ausm"), iters=20, full=(0, 5)),
     "box_weno": dict(synthetic=dict(ni=12, nj=8, nk=8, solver="dplur", sweeps=2, recon="weno"),
                      iters=12, full=(0, 4)),
+    # laminar Navier-Stokes (regressionTests.py:340-358): viscous wall (adiabatic), central
+    # viscous reconstruction, LU-SGS, CFL 1e4; 65x65x2 nodes
+    "viscousFlatPlate": dict(src="viscousFlatPlate", iters=100, full=(0, 1), edits={},
+                             drop=("velocityGrad@", "diagRaw@", "temperature@")),
+    # synthetic viscous boxes, 20 micron wide so that the viscous fluxes are ~10 % of the
+    # inviscid ones: WENO + 4th-order central viscous reconstruction, adiabatic wall, DPLUR
+    "box_visc4": dict(synthetic=dict(ni=12, nj=10, nk=8, solver="dplur", sweeps=3, recon="weno",
+                                     viscous=True, visc_recon="centralFourth", size=2e-5),
+                      iters=12, full=(0, 4)),
+    # MUSCL + 2nd-order central, isothermal wall, LU-SGS
+    "box_visc_iso": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                        limiter="vanAlbada", viscous=True, size=2e-5,
+                                        wall=("isothermal", 300.0)), iters=12, full=(0, 4)),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
 }
@@ -67,7 +80,8 @@ def generate(name):
                                      iterations=spec["iters"])
         d = refcase.run_harness(tmp, inp, spec["iters"], full=spec["full"], geom=True)
     out = {k: np.asarray(v) for k, v in d.items()
-           if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time"}
+           if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time" and
+           not any(k.split("/")[-1].startswith(p) for p in spec.get("drop", ()))}
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("%s: %d records, %.1f kB" % (name, len(out), os.path.getsize(path) / 1e3))

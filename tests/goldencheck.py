@@ -16,6 +16,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REGRESSION_GOLDENS = {
     "subsonicCylinder": (100, [1.8751e-01, 2.6727e-01, 3.1217e-01, None, 1.8639e-01]),
     "multiblockCylinder": (100, [2.0529e-01, 3.4540e-01, 5.0153e-01, None, 1.9997e-01]),
+    # :356-357
+    "viscousFlatPlate": (100, [7.4673e-02, 2.4711e-01, 3.8960e-02, None, 7.7683e-02]),
 }
 
 
@@ -33,6 +35,10 @@ def rel(a, b):
     b = np.asarray(b, dtype=np.float64).reshape(a.shape)
     ax = tuple(range(a.ndim - 1))
     scale = np.abs(b).max(axis=ax)
+    # a component that is rounding noise next to the others (the out-of-plane momentum of a 2-D
+    # case: 1e-22 noise against 1e-7; the reference's regression suite ignores that index too,
+    # testCases/regressionTests.py SetIgnoreIndices) is measured against the field's scale
+    scale = np.maximum(scale, 1e-2 * scale.max()) if scale.size else scale
     scale = np.where(scale > 0, scale, 1.0)
     return float((np.abs(a - b).max(axis=ax) / scale).max())
 
@@ -43,6 +49,15 @@ def non_edge_mask(shape, g):
     out = (((kk < g) | (kk >= K - g)).astype(int) + ((jj < g) | (jj >= J - g)).astype(int) +
            ((ii < g) | (ii >= I - g)).astype(int))
     return out <= 1
+
+
+def non_corner_mask(shape, g):
+    """everything but the 8 corner blocks of the ghost shell (never assigned by the solver)"""
+    K, J, I = shape
+    kk, jj, ii = np.meshgrid(np.arange(K), np.arange(J), np.arange(I), indexing="ij")
+    out = (((kk < g) | (kk >= K - g)).astype(int) + ((jj < g) | (jj >= J - g)).astype(int) +
+           ((ii < g) | (ii >= I - g)).astype(int))
+    return out <= 2
 
 
 def interior(a, g):
@@ -68,6 +83,8 @@ def check_phases(make_level, d, it, tol):
     cfl = float(d[tag + "/cfl"][0])
     out = {}
 
+    viscous = bool(prob.cfg.isViscous)
+
     def cmp(field, key, what, mask_edges=False, inner=False, comps=None):
         worst = 0.0
         for bb in range(nb):
@@ -79,7 +96,8 @@ def check_phases(make_level, d, it, tol):
             if comps is not None:
                 a, b = a[..., comps], b[..., comps]
             if mask_edges:
-                m = non_edge_mask(a.shape[:3], g)
+                # edge ghost cells are read by the viscous gradient stencils only
+                m = (non_corner_mask if viscous else non_edge_mask)(a.shape[:3], g)
                 a, b = a[m], b[m]
             if inner:
                 a, b = interior(a, g), interior(b, g)
@@ -91,6 +109,8 @@ def check_phases(make_level, d, it, tol):
     lvl.get_boundary_conditions()
     cmp(abi.FIELD_STATE, "state@%s.bc" % tag, "ghosts", mask_edges=True)
     lvl.calc_residual()
+    if viscous:  # ghost cells as the viscous fluxes saw them (viscous-wall + edge refill)
+        cmp(abi.FIELD_STATE, "state@%s.viscbc" % tag, "ghosts", mask_edges=True)
     cmp(abi.FIELD_RESIDUAL, "residual@" + tag, "residual")
     cmp(abi.FIELD_SPEC_RADIUS, "specRadius@" + tag, "specRadius", comps=slice(0, 1))
     lvl.calc_time_step(cfl)
@@ -107,7 +127,8 @@ def check_phases(make_level, d, it, tol):
     lvl.reset_diagonal()
     cmp(abi.FIELD_STATE, "state@%s.end" % tag, "state", inner=True)
     h = d["hist/residL2"][it]
-    l2err = float(np.max(np.abs(l2 - h) / np.where(h > 0, h, 1.0)))
+    # equations whose residual is rounding noise are not compared (as in check_history)
+    l2err = float(np.max(np.abs(l2 - h) / np.where(h > 1e-20 * h.max(), h, np.inf)))
     out["l2"] = l2err
     assert l2err <= tol["l2"], (tag, l2, h)
     # L-infinity: the reference takes the largest *signed* residual (src/procBlock.cpp:862-867);

@@ -92,6 +92,10 @@ def cfg_from_dump(d):
         suthViscC1=list(g("suthViscC1")), suthViscS=list(g("suthViscS")),
         suthCondC1=list(g("suthCondC1")), suthCondS=list(g("suthCondS")),
         molarMass=list(g("molarMass")), tRef=float(g("tRef")[0]), schmidt=float(g("schmidt")[0]),
+        # sutherland::sutherland (reference src/transport.cpp:65-68): kNonDim = aRef^2 muRef / tRef
+        muMixRef=float(d["cfg/muMixRef"][0]) if "cfg/muMixRef" in d else 0.0,
+        kMixRef=(float(g("aRef")[0]) ** 2 * float(d["cfg/muMixRef"][0]) / float(g("tRef")[0])
+                 if "cfg/muMixRef" in d else 0.0),
         bcStates=bcs)
 
 

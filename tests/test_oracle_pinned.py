@@ -18,19 +18,28 @@ import oracle
 TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-14, dt=1e-14, diag=1e-14, x0=1e-13,
            x=1e-12, matrixResid=1e-10, state=1e-13, l2=1e-13)
 
-SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno"]
+SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno",
+                # laminar Navier-Stokes: Green-Gauss face gradients, viscous fluxes, Sutherland,
+                # viscous-wall + edge ghost cells, viscous spectral radii (diagonal and faces)
+                "viscousFlatPlate", "box_visc4", "box_visc_iso"]
+
+
+# viscousFlatPlate runs at CFL 1e4 from a uniform start: the implicit update is the solution of a
+# nearly singular system and amplifies the 1e-13 residual differences to 6e-12 in x
+CASE_TOL = {"viscousFlatPlate": dict(TOL, x=1e-10)}
 
 
 @pytest.mark.parametrize("name", SINGLE_BLOCK)
 def test_oracle_phases_match_reference(name):
     d = gc.load(name)
     for it in gc.full_iterations(d):
-        gc.check_phases(oracle.OracleLevel, d, it, TOL)
+        gc.check_phases(oracle.OracleLevel, d, it, CASE_TOL.get(name, TOL))
 
 
 @pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30),
                                         ("box_dplur", 30), ("box_lusgs_va", 20),
-                                        ("box_weno", 12)])
+                                        ("box_weno", 12), ("viscousFlatPlate", 100),
+                                        ("box_visc4", 12), ("box_visc_iso", 12)])
 def test_oracle_history_matches_reference(name, iters):
     """L2 history within 1e-9 relative (north_star bar) + the reference's regression goldens."""
     d = gc.load(name)
