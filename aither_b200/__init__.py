@@ -195,7 +195,8 @@ class GridLevel:
         self._check(self._lib.aither_gpu_download_field(self._h, blk, fld, _ptr(out)))
         b = self.problem.blocks[self.block_ids[blk]]
         g = self.problem.cfg.numGhosts
-        padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE)
+        padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE,
+                         abi.FIELD_VISCOSITY)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
 

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "march.cuh"
 #include "implicit_tma.cuh"
+#include "viscous.cuh"
 
 using namespace aither;
 
@@ -44,12 +45,12 @@ int Fail(const std::string &msg) {
 
 enum Family {
   kFamBc = 0, kFamResidual, kFamPrep, kFamDplur, kFamLusgs, kFamAxmb, kFamUpdate, kFamStore,
-  kFamReduce, kFamHalo, kFamLayout, kNumFamilies
+  kFamReduce, kFamHalo, kFamLayout, kFamViscGhost, kFamViscFlux, kNumFamilies
 };
 const char *kFamilyNames[kNumFamilies] = {"bc_ghost_fill", "residual", "dt_diag_init", "dplur_sweep",
                                           "lusgs_plane", "matrix_residual", "update_norms",
                                           "store_time_n", "reduce_finalize", "halo_pack_unpack",
-                                          "layout_convert"};
+                                          "layout_convert", "viscous_ghosts_aux", "viscous_flux"};
 
 struct HostBlock {
   BlockDev dev;
@@ -58,6 +59,8 @@ struct HostBlock {
   std::vector<aither_surface> surfaces;
   SurfDev *dSurfs = nullptr;
   int nBcSurfs = 0;
+  EdgeSurf *dEdgeSurfs = nullptr;  // every surface of the block, connections included
+  int nEdgeSurfs = 0;
   long long bcThreads = 0;
   uint8_t *dConnFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int globalPos = 0;
@@ -206,7 +209,8 @@ int SurfaceType(const aither_surface &s) {
 bool Supported(const aither_cfg &c, std::string *why) {
   if (c.numSpecies != 1) { *why = "only single-species gas is built in this round"; return false; }
   if (c.numTurb != 0 || c.isRANS) { *why = "RANS turbulence models are not built in this round"; return false; }
-  if (c.isViscous) { *why = "viscous fluxes are not built in this round"; return false; }
+  if (c.isViscous && c.viscRecon != 0 && c.viscRecon != 1) { *why = "unknown viscous face reconstruction"; return false; }
+  if (c.isViscous && c.numGhosts < 2) { *why = "viscous fluxes need at least 2 ghost layers"; return false; }
   if (c.isBlockMatrix) { *why = "block-matrix solvers (blusgs/bdplur) are not built in this round"; return false; }
   if (c.invFluxJac != AITHER_JAC_RUSANOV) { *why = "approximateRoe flux jacobian is not built in this round"; return false; }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
@@ -339,11 +343,54 @@ int PhaseBoundaryConditions(aither_gpu *h) {
   }
   CK(cudaGetLastError());
   if (Exchange(h, kHaloState)) return 1;
+  if (h->cfg.isViscous) {
+    // edge ghost cells: read by the viscous gradient stencils only (ref src/gridLevel.cpp:314-318)
+    for (auto &hb : h->blocks) {
+      ScopedLaunch sl(h, kFamViscGhost);
+      const int n = 4 * (hb.dev.ni + hb.dev.nj + hb.dev.nk);
+      EdgeKernel<1, 0, false><<<(n + 127) / 128, 128, 0, h->stream>>>(
+          hb.dev, h->params, hb.dEdgeSurfs, hb.nEdgeSurfs, h->dBcStates);
+    }
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 
 int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
   for (auto &hb : h->blocks) LaunchResidual<1, 0>(h, hb, fusePrep, cfl);
+  CK(cudaGetLastError());
+  if (!h->cfg.isViscous) return 0;
+  // ref: src/procBlock.cpp:6125-6137
+  for (auto &hb : h->blocks) {
+    const BlockDev &b = hb.dev;
+    if (hb.bcThreads > 0) {
+      ScopedLaunch sl(h, kFamViscGhost);
+      const int grid = static_cast<int>((hb.bcThreads + 127) / 128);
+      ViscousWallKernel<1, 0><<<grid, 128, 0, h->stream>>>(b, h->params, hb.dSurfs, hb.nBcSurfs,
+                                                          h->dBcStates, hb.bcThreads);
+    }
+    {
+      ScopedLaunch sl(h, kFamViscGhost);
+      const int n = 4 * (b.ni + b.nj + b.nk);
+      EdgeKernel<1, 0, true><<<(n + 127) / 128, 128, 0, h->stream>>>(
+          b, h->params, hb.dEdgeSurfs, hb.nEdgeSurfs, h->dBcStates);
+    }
+    {
+      ScopedLaunch sl(h, kFamViscGhost);
+      const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
+      AuxKernel<1, 0><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
+    }
+    {
+      ScopedLaunch sl(h, kFamViscFlux);
+      const dim3 grid((b.ni + 1 + 31) / 32, (b.nj + 1 + 7) / 8, b.nk + 1);
+      ViscFaceKernel<1, 0><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params, b.xalt, b.x);
+    }
+    {
+      ScopedLaunch sl(h, kFamViscFlux);
+      ViscAccumKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(b, h->params, b.xalt, b.x,
+                                                                         1);
+    }
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -465,7 +512,7 @@ int IterateAsync(aither_gpu *h, double cfl, int slot) {
   if (ZeroResult(h, slot)) return 1;
   if (PhaseBoundaryConditions(h)) return 1;
   // inviscid: time step, diagonal, right-hand side and x0 ride in the residual kernel's epilogue
-  const bool fuse = !h->legacyKernels && h->fusePrep;
+  const bool fuse = !h->legacyKernels && h->fusePrep && !h->cfg.isViscous;
   if (PhaseResidual(h, fuse ? 1 : 0, cfl)) return 1;
   if (!fuse && PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
   if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
@@ -486,6 +533,7 @@ void FreeAll(aither_gpu *h) {
   for (auto &hb : h->blocks) {
     if (hb.alloc) cudaFree(hb.alloc);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
+    if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     for (auto &p : hb.dConnFace)
       if (p) cudaFree(p);
   }
@@ -548,11 +596,28 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.isMultilevelTime = cfg->isMultilevelTime;
   p.matrixRequiresInit = cfg->matrixRequiresInit;
   p.wenoZ = cfg->recon == AITHER_RECON_WENOZ;
+  p.isViscous = cfg->isViscous;
+  p.viscRecon = cfg->viscRecon;
+  p.viscCFLCoeff = cfg->viscousCFLCoeff;
+  p.tr.tRef = cfg->tRef;
+  p.tr.viscC1 = cfg->suthViscC1[0];
+  p.tr.viscS = cfg->suthViscS[0];
+  p.tr.muRef = cfg->muMixRef;
+  p.tr.condC1 = cfg->suthCondC1[0];
+  p.tr.condS = cfg->suthCondS[0];
+  p.tr.kRef = cfg->kMixRef;
+  p.tr.scaling = cfg->nondimScaling;
+  if (cfg->isViscous && !(cfg->muMixRef > 0.0 && cfg->kMixRef > 0.0 && cfg->tRef > 0.0)) {
+    delete h;
+    return Fail("aither_gpu_create: viscous run without transport reference values "
+                "(tRef, muMixRef, kMixRef)");
+  }
   GasFinalize(&p.gas);
   {
     const char *kv = getenv("AITHER_B200_KERNELS");
     h->legacyKernels = kv != nullptr && std::string(kv) == "legacy";
-    h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march");
+    // the TMA-fed sweep is inviscid-only so far; viscous runs take the register-fed march kernel
+    h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march") && !cfg->isViscous;
     const char *fp = getenv("AITHER_B200_FUSE_PREP");
     h->fusePrep = !(fp != nullptr && std::string(fp) == "0");
   }
@@ -605,7 +670,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // field budget (doubles per cell): state, consN, [consNm1], resid, rhs, x, xalt, [mres],
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
-                        12 + 3;
+                        12 + 3 + (cfg->isViscous ? 6 : 0);
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
@@ -629,6 +694,12 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     for (int q = 0; q < 3; ++q) b.mc[q] = take(2);
     for (int q = 0; q < 3; ++q) b.fA[q] = take(4);
     b.center = take(3);
+    if (cfg->isViscous) {
+      b.temperature = take(1);
+      b.viscosity = take(1);
+      b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
+      for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
+    }
 
     const int NI = d.ni + 2 * g, NJ = d.nj + 2 * g, NK = d.nk + 2 * g;
     if (!d.state || !d.vol || !d.fAreaI || !d.fAreaJ || !d.fAreaK || !d.cellWidthI ||
@@ -646,6 +717,16 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     CKH(UploadAos(h, hb, d.cellWidthJ, NI, NJ, NK, 1, b.cw[1], -g, -g, -g));
     CKH(UploadAos(h, hb, d.cellWidthK, NI, NJ, NK, 1, b.cw[2], -g, -g, -g));
     if (d.center) CKH(UploadAos(h, hb, d.center, NI, NJ, NK, 3, b.center, -g, -g, -g));
+    if (cfg->isViscous) {
+      if (!d.center) {
+        Fail("aither_gpu_create: viscous runs need the cell centres");
+        FreeAll(h);
+        return 1;
+      }
+      if (d.wallDist) CKH(UploadAos(h, hb, d.wallDist, NI, NJ, NK, 1, b.wallDist, -g, -g, -g));
+      ScopedLaunch sl(h, kFamLayout);
+      DistKernel<<<148 * 8, 256, 0, h->stream>>>(b);
+    }
     for (int q = 0; q < 3; ++q) {
       ScopedLaunch sl(h, kFamLayout);
       MusclCoefKernel<<<148 * 8, 256, 0, h->stream>>>(b, q);
@@ -679,7 +760,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       v.surfType = st;
       v.tag = sf.tag;
       v.bcIndex = 0;
-      const bool needsData = sf.type == AITHER_BC_CHARACTERISTIC || sf.type == AITHER_BC_INLET ||
+      const bool needsData = (sf.type == AITHER_BC_VISCOUS_WALL && cfg->isViscous) ||
+                             sf.type == AITHER_BC_CHARACTERISTIC || sf.type == AITHER_BC_INLET ||
                              sf.type == AITHER_BC_SUPERSONIC_INFLOW ||
                              sf.type == AITHER_BC_STAGNATION_INLET ||
                              sf.type == AITHER_BC_PRESSURE_OUTLET;
@@ -703,6 +785,27 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       v.faceOffset = off;
       off += static_cast<long long>(hi[d1] - lo[d1]) * (hi[d2] - lo[d2]) * g;
       sd.push_back(v);
+    }
+    {
+      std::vector<EdgeSurf> es;
+      for (const auto &sf : hb.surfaces) {
+        EdgeSurf e;
+        e.type = sf.type;
+        e.surfType = SurfaceType(sf);
+        e.tag = sf.tag;
+        e.bcIndex = 0;
+        for (int q = 0; q < cfg->numBCStates; ++q)
+          if (cfg->bcStates[q].tag == sf.tag) { e.bcIndex = q; break; }
+        e.lo[0] = sf.imin; e.lo[1] = sf.jmin; e.lo[2] = sf.kmin;
+        e.hi[0] = sf.imax; e.hi[1] = sf.jmax; e.hi[2] = sf.kmax;
+        es.push_back(e);
+      }
+      hb.nEdgeSurfs = static_cast<int>(es.size());
+      if (!es.empty()) {
+        CKC(cudaMalloc(&hb.dEdgeSurfs, sizeof(EdgeSurf) * es.size()));
+        CKC(cudaMemcpy(hb.dEdgeSurfs, es.data(), sizeof(EdgeSurf) * es.size(),
+                       cudaMemcpyHostToDevice));
+      }
     }
     hb.nBcSurfs = static_cast<int>(sd.size());
     hb.bcThreads = off;
@@ -932,6 +1035,12 @@ static int FieldInfo(aither_gpu *h, int blk, int field, const double **ptr, int 
     case AITHER_FIELD_CONS_NM1:
       if (!b.consNm1) return Fail("consNm1 is only stored for bdf2");
       *ptr = b.consNm1; *nc = h->neq; *padded = false; break;
+    case AITHER_FIELD_TEMPERATURE:
+      if (!b.temperature) return Fail("temperature is only stored for viscous runs");
+      *ptr = b.temperature; *nc = 1; *padded = true; break;
+    case AITHER_FIELD_VISCOSITY:
+      if (!b.viscosity) return Fail("viscosity is only stored for viscous runs");
+      *ptr = b.viscosity; *nc = 1; *padded = true; break;
     default: return Fail("unknown or unavailable field id " + std::to_string(field));
   }
   return 0;

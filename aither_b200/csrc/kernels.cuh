@@ -25,10 +25,13 @@ namespace aither {
 // scalar solver parameters, passed by value
 struct Params {
   Gas gas;
-  double kappa, theta, zeta, relax, dualTimeCFL, dtNondim;
+  Transport tr;
+  double kappa, theta, zeta, relax, dualTimeCFL, dtNondim, viscCFLCoeff;
   int isMultilevelTime;
   int matrixRequiresInit;
   int wenoZ;
+  int isViscous;
+  int viscRecon;   // 0 central, 1 centralFourth
 };
 
 // per-iteration reduction results (device + pinned host mirror)
@@ -419,7 +422,12 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx - st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx);
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, true, od);
+        double extra = 0.0;
+        if (p.isViscous)
+          extra = fa[3] / __ldg(b.dist[d] + idx) *
+                  ViscSpecFactor(p.tr, SpeciesSum<NS>(sn), Gamma<NS>(p.gas, sn),
+                                 __ldg(b.viscosity + idx - st));
+        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, true, od, extra);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) L[e] += od[e];
       }
@@ -431,7 +439,12 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx + st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx + st);
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, false, od);
+        double extra = 0.0;
+        if (p.isViscous)
+          extra = fa[3] / __ldg(b.dist[d] + idx + st) *
+                  ViscSpecFactor(p.tr, SpeciesSum<NS>(sn), Gamma<NS>(p.gas, sn),
+                                 __ldg(b.viscosity + idx + st));
+        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, false, od, extra);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) U[e] += od[e];
       }

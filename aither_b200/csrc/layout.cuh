@@ -40,6 +40,11 @@ struct BlockDev {
   double *mc[3];     // 2     MUSCL grid ratios along i, j, k: {2w/(w+w_lower), 2w/(w+w_upper)}
   double *fA[3];     // 4     face areas {nx, ny, nz, |A|} for i-, j-, k-faces
   double *center;    // 3
+  // viscous runs only (else null)
+  double *temperature;  // 1   ghosts valid (all but corner cells)
+  double *viscosity;    // 1   laminar viscosity, normalised by mu_ref; ghosts valid
+  double *wallDist;     // 1   (null when the caller gave none)
+  double *dist[3];      // 1   projected centre-to-centre distance across i-, j-, k-faces
   // per boundary face: 1 if the neighbour across that block face contributes to the implicit
   // off-diagonals, i.e. the face belongs to a connection (interblock / periodic) boundary
   // (ref: src/procBlock.cpp:1064,1115; include/boundaryConditions.hpp:287-293).

@@ -432,6 +432,9 @@ __global__ void __launch_bounds__(kMThreads, 2)
           ing[e] = s[e];
           ing[neq + 2 + e] = du[e];
         }
+        ing[G::ivt] = p.isViscous ? ViscSpecFactor(p.tr, SpeciesSum<NS>(s), Gamma<NS>(p.gas, s),
+                                                   __ldg(b.viscosity + idx))
+                                  : 0.0;
       }
       if (planeInterior) {
 #pragma unroll
@@ -445,7 +448,8 @@ __global__ void __launch_bounds__(kMThreads, 2)
           double fa[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[2] + q * b.fs + idx);
-          OffDiagFromIngr<NS, NT>(ldOwn, fa, false, accUp);
+          OffDiagFromIngr<NS, NT>(ldOwn, fa, false, accUp,
+                                  p.isViscous ? fa[3] / __ldg(b.dist[2] + idx) * ing[G::ivt] : 0.0);
         }
         const long long idxm = idx - b.sk;
         if (MODE == kModeDplur) {
@@ -472,7 +476,9 @@ __global__ void __launch_bounds__(kMThreads, 2)
         double fa[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[2] + q * b.fs + idx + b.sk);
-        OffDiagFromIngr<NS, NT>(ldOwn, fa, true, newCarry);
+        OffDiagFromIngr<NS, NT>(ldOwn, fa, true, newCarry,
+                                p.isViscous ? fa[3] / __ldg(b.dist[2] + idx + b.sk) * ing[G::ivt]
+                                            : 0.0);
       }
     }
     if (planeInterior && hpi >= 0) {
@@ -487,6 +493,9 @@ __global__ void __launch_bounds__(kMThreads, 2)
         hing[e] = s[e];
         hing[neq + 2 + e] = du[e];
       }
+      hing[G::ivt] = p.isViscous ? ViscSpecFactor(p.tr, SpeciesSum<NS>(s), Gamma<NS>(p.gas, s),
+                                                  __ldg(b.viscosity + hidx))
+                                 : 0.0;
       const int hc = hpi + kIPI * hpj;
 #pragma unroll
       for (int q = 0; q < G::n; ++q) cur[q * kIPC + hc] = hing[q];
@@ -510,13 +519,15 @@ __global__ void __launch_bounds__(kMThreads, 2)
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[0] + q * b.fs + idx);
         auto ld = [&](int q) { return cur[q * kIPC + pc - 1]; };
-        OffDiagFromIngr<NS, NT>(ld, fa, true, accLp);
+        OffDiagFromIngr<NS, NT>(ld, fa, true, accLp,
+                                p.isViscous ? fa[3] / __ldg(b.dist[0] + idx) * ld(G::ivt) : 0.0);
       }
       if (useJlo) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[1] + q * b.fs + idx);
         auto ld = [&](int q) { return cur[q * kIPC + pc - kIPI]; };
-        OffDiagFromIngr<NS, NT>(ld, fa, true, accLp);
+        OffDiagFromIngr<NS, NT>(ld, fa, true, accLp,
+                                p.isViscous ? fa[3] / __ldg(b.dist[1] + idx) * ld(G::ivt) : 0.0);
       }
       if (useKlo) {  // produced from the cell below at the previous plane
 #pragma unroll
@@ -526,13 +537,16 @@ __global__ void __launch_bounds__(kMThreads, 2)
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[0] + q * b.fs + idx + 1);
         auto ld = [&](int q) { return cur[q * kIPC + pc + 1]; };
-        OffDiagFromIngr<NS, NT>(ld, fa, false, accUp);
+        OffDiagFromIngr<NS, NT>(ld, fa, false, accUp,
+                                p.isViscous ? fa[3] / __ldg(b.dist[0] + idx + 1) * ld(G::ivt) : 0.0);
       }
       if (useJhi) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[1] + q * b.fs + idx + b.sj);
         auto ld = [&](int q) { return cur[q * kIPC + pc + kIPI]; };
-        OffDiagFromIngr<NS, NT>(ld, fa, false, accUp);
+        OffDiagFromIngr<NS, NT>(ld, fa, false, accUp,
+                                p.isViscous ? fa[3] / __ldg(b.dist[1] + idx + b.sj) * ld(G::ivt)
+                                            : 0.0);
       }
     }
 #pragma unroll

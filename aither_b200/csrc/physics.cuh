@@ -27,6 +27,21 @@ constexpr double kEntropyFix = 0.1;     // ref: include/inviscidFlux.hpp:298
 constexpr double kTurbMin = 1.0e-20;    // ref: include/turbulence.hpp:72-73
 
 // Gas model constants for <= AITHER_MAX_SPECIES calorically perfect species (nondimensional).
+// Sutherland transport of the (single) species; ref: src/transport.cpp:50-68,113-131
+struct Transport {
+  double tRef, viscC1, viscS, muRef, condC1, condS, kRef, scaling;
+};
+
+// max(4/(3 rho), gamma/rho) * scaling * mu / Pr: the state-dependent factor shared by
+// ViscCellSpectralRadius and ViscFaceSpectralRadius (include/spectralRadius.hpp:94-151);
+// Pr = 4 gamma / (9 gamma - 5) (include/thermodynamic.hpp:61-64)
+AITHER_HD double ViscSpecFactor(const Transport &tr, double rho, double gamma, double mu) {
+  const double maxTerm = fmax(4.0 / (3.0 * rho), gamma / rho);
+  const double pr = (4.0 * gamma) / (9.0 * gamma - 5.0);
+  const double viscTerm = tr.scaling * (mu / pr + 0.0);
+  return maxTerm * viscTerm;
+}
+
 struct Gas {
   double R[AITHER_MAX_SPECIES];
   double n[AITHER_MAX_SPECIES];
@@ -555,13 +570,14 @@ AITHER_HD double InvFaceSpectralRadius(const double *s, double sos, const double
 // ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal)
 template <int NS, int NT>
 AITHER_HD void OffDiagScalar(const Gas &g, const double *state, const double *du,
-                             const double *fArea, bool positive, double *out) {
+                             const double *fArea, bool positive, double *out,
+                             double srExtra = 0.0) {
   using E = Eq<NS, NT>;
   double su[E::neq], fo[E::neq], fn[E::neq];
   UpdatePrimWithCons<NS, NT>(g, state, du, su);
   PhysicalFlux<NS, NT>(g, state, fArea, fo);
   PhysicalFlux<NS, NT>(g, su, fArea, fn);
-  const double sr = InvFaceSpectralRadius<NS>(state, SoS<NS>(g, state), fArea);
+  const double sr = InvFaceSpectralRadius<NS>(state, SoS<NS>(g, state), fArea) + srExtra;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) {
     const double fc = e < NS + 4 ? 0.5 * fArea[3] * (fn[e] - fo[e]) : 0.0;
@@ -733,7 +749,9 @@ AITHER_HD void InviscidFluxFast(const Gas &g, const double *l, const double *r,
 template <int NS, int NT>
 struct Ingr {
   static constexpr int neq = NS + 4 + NT;
-  static constexpr int n = 3 * neq + 3;  // s[neq] H a | du[neq] | sn[neq] Hn
+  // s[neq] H a | du[neq] | sn[neq] Hn | vt (viscous spectral factor, 0 when inviscid)
+  static constexpr int n = 3 * neq + 4;
+  static constexpr int ivt = 3 * neq + 3;
 };
 
 // state + dU -> Ingr; ref include/primitive.hpp:206-231 (UpdatePrimWithCons), :150-177
@@ -786,9 +804,11 @@ AITHER_HD void MakeIngr(const Gas &g, const double *s, const double *du,
 }
 
 // off-diagonal product of one neighbour from its ingredients and the shared face's area
+// `srExtra`: viscous part of the face spectral radius, |A| / dist * max(4/(3 rho), gamma/rho) *
+// scaling * mu / Pr of the neighbour (ref include/spectralRadius.hpp:126-151,180-200)
 template <int NS, int NT, typename LD>
 AITHER_HD void OffDiagFromIngr(LD ld, const double *fA, bool positive,
-                                                double *acc) {
+                                                double *acc, double srExtra = 0.0) {
   using E = Eq<NS, NT>;
   constexpr int neq = E::neq;
   // layout: [0,neq) s | neq H | neq+1 a | [neq+2, 2neq+2) du | [2neq+2, 3neq+2) sn | 3neq+2 Hn
@@ -799,7 +819,7 @@ AITHER_HD void OffDiagFromIngr(LD ld, const double *fA, bool positive,
   const double vnw = un * fA[0] + vn_ * fA[1] + wn * fA[2];
   double rho = 0.0, rhon = 0.0;
   const double half = 0.5 * fA[3];
-  const double sr = half * (fabs(vo) + ld(neq + 1));
+  const double sr = half * (fabs(vo) + ld(neq + 1)) + srExtra;
 #pragma unroll
   for (int q = 0; q < NS; ++q) {
     const double r0 = ld(q), r1 = ld(2 * neq + 2 + q);

@@ -1,0 +1,465 @@
+// viscous.cuh -- laminar Navier-Stokes terms of the residual (K2/K3) and what they need around
+// them: Sutherland transport, viscous-wall and edge ghost cells, viscous spectral radii.
+//
+// Reference path (mnucci32/aither v0.10.0): procBlock::CalcResidualNoSource viscous branch
+// (src/procBlock.cpp:6125-6137) = AssignViscousGhostCells (:2760-3025) -> UpdateAuxillaryVariables
+// (:6171-6190) -> CalcViscFluxI/J/K (:1233-2200) with CalcGradsI/J/K (:5173-5780),
+// viscousFlux::CalcFlux (src/viscousFlux.cpp:58-135), ViscCellSpectralRadius
+// (include/spectralRadius.hpp:94-124).
+//
+// Device design: a face's viscous flux is computed ONCE, by the thread of the cell above it
+// (ViscFaceKernel, all three directions in one pass over the block, 10-cell Green-Gauss stencil
+// served by L1/L2), and parked in scratch fields that are idle during the residual phase (the
+// implicit update's ping-pong buffer and the matrix-residual field); ViscAccumKernel then adds
+// the six face fluxes of every cell to its residual in the reference's order (+lower, -upper for
+// i, j, k) together with the viscous spectral radius and its share of the scalar
+// diagonal. Owner-writes, no atomics, run-to-run identical.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace aither {
+
+// ---- transport: Sutherland, single species (ref: src/transport.cpp:113-131,173-196) ------------
+AITHER_HD double SutherlandViscosity(const Transport &tr, double t) {
+  const double temp = t * tr.tRef;
+  const double mu = (tr.viscC1 * (temp * sqrt(temp))) / (temp + tr.viscS);
+  return mu / tr.muRef;
+}
+AITHER_HD double EffectiveConductivity(const Transport &tr, double t) {
+  const double temp = t * tr.tRef;
+  const double k = (tr.condC1 * (temp * sqrt(temp))) / (temp + tr.condS);
+  return (k / tr.kRef) * tr.scaling;
+}
+// viscous-wall ghost state, low-Re treatment (ref: src/ghostStates.cpp:134-258): velocity
+// mirrored about the wall velocity; adiabatic keeps rho and p, isothermal / heat-flux walls set
+// the ghost temperature and take rho from p = rho R T
+template <int NS, int NT>
+AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double *interior,
+                                const aither_bc_state &bc, double wallDist, double *ghost) {
+  using E = Eq<NS, NT>;
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
+  ghost[E::imx] = 2.0 * bc.velocity[0] - interior[E::imx];
+  ghost[E::imy] = 2.0 * bc.velocity[1] - interior[E::imy];
+  ghost[E::imz] = 2.0 * bc.velocity[2] - interior[E::imz];
+  if (bc.isIsothermal || bc.isConstantHeatFlux) {
+    const double tInt = Temperature<NS>(g, interior);
+    double tGhost;
+    if (bc.isIsothermal) {
+      tGhost = 2.0 * bc.temperature - tInt;
+    } else {
+      const double kappa = EffectiveConductivity(tr, tInt);
+      tGhost = tInt - bc.heatFlux / kappa * 2.0 * wallDist;
+    }
+    const double rhoInt = SpeciesSum<NS>(interior);
+    double R = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) R += interior[q] / rhoInt * g.R[q];
+    const double rho = ghost[E::ie] / (R * tGhost);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) ghost[q] = rho * (interior[q] / rhoInt);
+  }
+}
+
+// ---- K11b: viscous-wall ghost cells (ref: src/procBlock.cpp:2760-2833) -------------------------
+template <int NS, int NT>
+__global__ void ViscousWallKernel(BlockDev b, Params p, const SurfDev *__restrict__ surfs, int nsurf,
+                                  const aither_bc_state *__restrict__ bcs, long long total) {
+  using E = Eq<NS, NT>;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t >= total) return;
+  int s = 0;
+  while (s + 1 < nsurf && surfs[s + 1].faceOffset <= t) ++s;
+  const SurfDev sf = surfs[s];
+  if (sf.type != AITHER_BC_VISCOUS_WALL) return;
+  const int d3 = (sf.surfType - 1) / 2;
+  const int d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+  const int n1 = sf.hi[d1] - sf.lo[d1], n2 = sf.hi[d2] - sf.lo[d2];
+  long long r = t - sf.faceOffset;
+  const int a1 = static_cast<int>(r % n1);
+  r /= n1;
+  const int a2 = static_cast<int>(r % n2);
+  const int layer = static_cast<int>(r / n2) + 1;
+  const int nd[3] = {b.ni, b.nj, b.nk};
+  const int r3 = sf.lo[d3];
+  int gCell, iCell, aCell;
+  if (sf.surfType % 2 == 0) {
+    gCell = r3 + layer - 1;
+    iCell = max(r3 - layer, 0);
+    aCell = r3 - 1;
+  } else {
+    gCell = r3 - layer;
+    iCell = min(r3 + layer - 1, nd[d3] - 1);
+    aCell = r3;
+  }
+  int c[3];
+  c[d1] = sf.lo[d1] + a1;
+  c[d2] = sf.lo[d2] + a2;
+  c[d3] = iCell;
+  double interior[E::neq], ghost[E::neq];
+  LoadCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), interior);
+  c[d3] = aCell;
+  const double wd = b.wallDist ? b.wallDist[CellIdx(b, c[0], c[1], c[2])] : 0.0;
+  ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bcs[sf.bcIndex], wd, ghost);
+  c[d3] = gCell;
+  StoreCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), ghost);
+}
+
+// ---- K11c: edge ghost cells --------------------------------------------------------------------
+// ref: src/procBlock.cpp:2565-2703 (AssignInviscidGhostCellsEdge; VISCOUS = false) and
+// :2873-3025 (AssignViscousGhostCellsEdge; VISCOUS = true). One thread per (edge direction, one of
+// its 4 edges, position along the edge); the g x g cells of that position are filled in the
+// reference's layer order because later layers read earlier ones.
+struct EdgeSurf {
+  int type, surfType, tag, bcIndex;
+  int lo[3], hi[3];  // node-index ranges of the surface as given (imin..kmax)
+};
+__device__ __forceinline__ void DirIjk(int dd, int d1, int d2, int d3, int *c) {
+  // multiArray3d::operator()(dir, d1, d2, d3): include/multiArray3d.hpp:231-243
+  if (dd == 0) { c[0] = d1; c[1] = d2; c[2] = d3; }
+  else if (dd == 1) { c[0] = d3; c[1] = d1; c[2] = d2; }
+  else { c[0] = d2; c[1] = d3; c[2] = d1; }
+}
+__device__ __forceinline__ int FindSurface(const EdgeSurf *surfs, int nsurf, const int *c, int surf) {
+  // ref: src/boundaryConditions.cpp:109-185 (GetBCSurface)
+  const int sd = (surf - 1) / 2;
+  for (int s = 0; s < nsurf; ++s) {
+    if ((surfs[s].surfType - 1) / 2 != sd) continue;
+    bool in = true;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q == sd) in = in && c[q] >= surfs[s].lo[q] && c[q] <= surfs[s].hi[q];
+      else in = in && c[q] >= surfs[s].lo[q] && c[q] < surfs[s].hi[q];
+    }
+    if (in) return s;
+  }
+  return -1;
+}
+template <int NS, int NT, bool VISCOUS>
+__global__ void EdgeKernel(BlockDev b, Params p, const EdgeSurf *__restrict__ surfs, int nsurf,
+                           const aither_bc_state *__restrict__ bcs) {
+  using E = Eq<NS, NT>;
+  const int nd[3] = {b.ni, b.nj, b.nk};
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int dd = 0;
+  for (; dd < 3; ++dd) {
+    if (t < 4 * nd[dd]) break;
+    t -= 4 * nd[dd];
+  }
+  if (dd == 3) return;
+  const int cc = t / nd[dd], d1 = t % nd[dd];
+  const int max2 = nd[(dd + 1) % 3], max3 = nd[(dd + 2) % 3];
+  const int surfStart2 = 2 * ((dd + 1) % 3) + 1, surfStart3 = 2 * ((dd + 2) % 3) + 1;
+  const int fd2 = (dd + 1) % 3, fd3 = (dd + 2) % 3;
+  const bool upper2 = cc > 1, upper3 = cc % 2 == 1;
+  const int surf2 = upper2 ? surfStart2 + 1 : surfStart2;
+  const int surf3 = upper3 ? surfStart3 + 1 : surfStart3;
+  const int cFaceD2_2 = upper2 ? max2 : 0, cFaceD2_3 = upper3 ? max3 - 1 : 0;
+  const int cFaceD3_2 = upper2 ? max2 - 1 : 0, cFaceD3_3 = upper3 ? max3 : 0;
+  int c2[3], c3[3];
+  DirIjk(dd, d1, cFaceD2_2, cFaceD2_3, c2);
+  DirIjk(dd, d1, cFaceD3_2, cFaceD3_3, c3);
+  const int s2 = FindSurface(surfs, nsurf, c2, surf2), s3 = FindSurface(surfs, nsurf, c3, surf3);
+  if (s2 < 0 || s3 < 0) return;
+  int bc2 = surfs[s2].type, bc3 = surfs[s3].type;
+  if (!VISCOUS) {
+    if (bc2 == AITHER_BC_VISCOUS_WALL) bc2 = AITHER_BC_SLIP_WALL;
+    if (bc3 == AITHER_BC_VISCOUS_WALL) bc3 = AITHER_BC_SLIP_WALL;
+  }
+  for (int layer3 = 1; layer3 <= b.g; ++layer3) {
+    for (int layer2 = 1; layer2 <= b.g; ++layer2) {
+      const int pCellD2 = upper2 ? max2 + layer2 - 2 : 1 - layer2;
+      const int gCellD2 = upper2 ? pCellD2 + 1 : pCellD2 - 1;
+      const int pCellD3 = upper3 ? max3 + layer3 - 2 : 1 - layer3;
+      const int gCellD3 = upper3 ? pCellD3 + 1 : pCellD3 - 1;
+      int cg[3], cp2[3], cp3[3];
+      DirIjk(dd, d1, gCellD2, gCellD3, cg);
+      DirIjk(dd, d1, pCellD2, gCellD3, cp2);
+      DirIjk(dd, d1, gCellD2, pCellD3, cp3);
+      const long long ig = CellIdx(b, cg[0], cg[1], cg[2]);
+      double from2[E::neq], from3[E::neq], ghost[E::neq];
+      // plain loads: these cells may have been written earlier in this very loop
+      for (int e = 0; e < E::neq; ++e) {
+        from2[e] = b.state[e * b.fs + CellIdx(b, cp2[0], cp2[1], cp2[2])];
+        from3[e] = b.state[e * b.fs + CellIdx(b, cp3[0], cp3[1], cp3[2])];
+      }
+      const bool wall2 = bc2 == AITHER_BC_SLIP_WALL && bc3 != AITHER_BC_SLIP_WALL;
+      const bool wall3 = bc2 != AITHER_BC_SLIP_WALL && bc3 == AITHER_BC_SLIP_WALL;
+      if (wall2 || wall3) {
+        // the wall is extended into the edge cell: slip-wall reflection about the corner face
+        int cf[3];
+        if (wall2) DirIjk(dd, d1, cFaceD2_2, gCellD3, cf);
+        else DirIjk(dd, d1, gCellD2, cFaceD3_3, cf);
+        const int fd = wall2 ? fd2 : fd3;
+        const long long fidx = CellIdx(b, cf[0], cf[1], cf[2]);
+        double area[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) area[q] = b.fA[fd][q * b.fs + fidx];
+        const int sx = wall2 ? s2 : s3;
+        GhostState<NS, NT>(p.gas, wall2 ? from2 : from3, AITHER_BC_SLIP_WALL, area,
+                           wall2 ? surf2 : surf3, bcs[surfs[sx].bcIndex], wall2 ? layer2 : layer3,
+                           ghost);
+      } else if (!VISCOUS || (bc2 == AITHER_BC_VISCOUS_WALL && bc3 == AITHER_BC_VISCOUS_WALL)) {
+        if (layer2 == layer3) {
+#pragma unroll
+          for (int e = 0; e < E::neq; ++e) ghost[e] = 0.5 * (from2[e] + from3[e]);
+        } else if (layer2 > layer3) {
+#pragma unroll
+          for (int e = 0; e < E::neq; ++e) ghost[e] = from3[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < E::neq; ++e) ghost[e] = from2[e];
+        }
+      } else {
+        continue;
+      }
+      for (int e = 0; e < E::neq; ++e) b.state[e * b.fs + ig] = ghost[e];
+    }
+  }
+}
+
+// ---- temperature and viscosity of every cell the stencils read (all but the corner ghosts) -----
+// ref: src/procBlock.cpp:6171-6190 (UpdateAuxillaryVariables)
+template <int NS, int NT>
+__global__ void __launch_bounds__(256) AuxKernel(BlockDev b, Params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x - b.g;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y - b.g;
+  const int k = static_cast<int>(blockIdx.z) - b.g;
+  if (i >= b.ni + b.g || j >= b.nj + b.g) return;
+  const int out = (i < 0 || i >= b.ni) + (j < 0 || j >= b.nj) + (k < 0 || k >= b.nk);
+  if (out == 3) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double s[NS + 4 + NT];
+  LoadCell<NS + 4 + NT>(b.state, b.fs, idx, s);
+  const double t = Temperature<NS>(p.gas, s);
+  b.temperature[idx] = t;
+  b.viscosity[idx] = SutherlandViscosity(p.tr, t);
+}
+
+// projected centre-to-centre distance across every face (geometry only; built once):
+// ref: src/procBlock.cpp:6316-6341 (ProjC2CDist)
+__global__ void DistKernel(BlockDev b) {
+  const int NI = b.ni + 2 * b.g, NJ = b.nj + 2 * b.g, NK = b.nk + 2 * b.g;
+  const long long n = static_cast<long long>(NI) * NJ * NK;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c[3] = {static_cast<int>(t % NI) - b.g, static_cast<int>((t / NI) % NJ) - b.g,
+                      static_cast<int>(t / (static_cast<long long>(NI) * NJ)) - b.g};
+    const long long idx = CellIdx(b, c[0], c[1], c[2]);
+    for (int d = 0; d < 3; ++d) {
+      double dist = 1.0;
+      if (c[d] > -b.g) {
+        const long long lo = idx - Stride(b, d);
+        double acc = 0.0;
+        for (int q = 0; q < 3; ++q)
+          acc += (b.center[q * b.fs + idx] - b.center[q * b.fs + lo]) * b.fA[d][q * b.fs + idx];
+        dist = acc;
+      }
+      b.dist[d][idx] = dist;
+    }
+  }
+}
+
+// ---- K2/K3: face gradients + viscous flux ------------------------------------------------------
+__device__ __forceinline__ void AreaVec(const BlockDev &b, int d, long long idx, double *v) {
+  const double m = __ldg(b.fA[d] + 3 * b.fs + idx);
+  v[0] = __ldg(b.fA[d] + idx) * m;  // unitVec3dMag::Vector(): unit * mag (vector3d.hpp:178)
+  v[1] = __ldg(b.fA[d] + b.fs + idx) * m;
+  v[2] = __ldg(b.fA[d] + 2 * b.fs + idx) * m;
+}
+
+// viscous flux times face area through face (idx = cell above the face) of direction D:
+// out = {tau_x, tau_y, tau_z, tau.v + k grad T.n} |A|
+template <int NS, int NT, int D>
+__device__ __forceinline__ void ViscFaceFlux(const BlockDev &b, const Params &p, long long idx,
+                                             double *out) {
+  using E = Eq<NS, NT>;
+  const long long sd = Stride(b, D);
+  const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
+  // areas of the control volume centred on the face (ref: src/procBlock.cpp:5190-5206)
+  double al[3][3], au[3][3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double a0[3], a1[3];
+    if (q == D) {
+      AreaVec(b, D, idx, a0);
+      AreaVec(b, D, idx + sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, D, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    } else {
+      AreaVec(b, q, idx + st[q], a0);
+      AreaVec(b, q, idx + st[q] - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, q, idx, a0);
+      AreaVec(b, q, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    }
+  }
+  const double vol = 0.5 * (__ldg(b.vol + idx - sd) + __ldg(b.vol + idx));
+  const double invVol = 1.0 / vol;
+  // velocity (3) and temperature on the six faces of the control volume, then Green-Gauss
+  // (ref: src/utility.cpp:59-175): grad(r, c) = sum_faces value_c * area_r / vol, i-, j-, k-pairs
+  double grad[4][3];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double *f = c < 3 ? b.state + (NS + c) * b.fs : b.temperature;
+    const double lo = __ldg(f + idx - sd), hi = __ldg(f + idx);
+    double vl[3], vu[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q == D) {
+        vl[q] = lo;
+        vu[q] = hi;
+      } else {
+        vu[q] = 0.25 * (lo + hi + __ldg(f + idx + st[q]) + __ldg(f + idx + st[q] - sd));
+        vl[q] = 0.25 * (lo + hi + __ldg(f + idx - st[q]) + __ldg(f + idx - st[q] - sd));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double t = vu[0] * au[0][r] - vl[0] * al[0][r] + vu[1] * au[1][r] - vl[1] * al[1][r] +
+                       vu[2] * au[2][r] - vl[2] * al[2][r];
+      grad[c][r] = t * invVol;
+    }
+  }
+  // face state and viscosity: central or 4th-order central (ref: src/procBlock.cpp:1305-1346,
+  // include/reconstruction.hpp:315-379)
+  double fs_[E::neq], mu;
+  if (p.viscRecon == 0) {
+    const double w[2] = {__ldg(b.cw[D] + idx - sd), __ldg(b.cw[D] + idx)};
+    double c[2];
+    LagrangeCoeff<1>(w, 0, 0, c);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e)
+      fs_[e] = c[0] * __ldg(b.state + e * b.fs + idx) + c[1] * __ldg(b.state + e * b.fs + idx - sd);
+    mu = c[0] * __ldg(b.viscosity + idx) + c[1] * __ldg(b.viscosity + idx - sd);
+  } else {
+    const double w[4] = {__ldg(b.cw[D] + idx - 2 * sd), __ldg(b.cw[D] + idx - sd),
+                         __ldg(b.cw[D] + idx), __ldg(b.cw[D] + idx + sd)};
+    double c[4];
+    LagrangeCoeff<3>(w, 1, 1, c);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e)
+      fs_[e] = c[0] * __ldg(b.state + e * b.fs + idx - 2 * sd) +
+               c[1] * __ldg(b.state + e * b.fs + idx - sd) + c[2] * __ldg(b.state + e * b.fs + idx) +
+               c[3] * __ldg(b.state + e * b.fs + idx + sd);
+    mu = c[0] * __ldg(b.viscosity + idx - 2 * sd) + c[1] * __ldg(b.viscosity + idx - sd) +
+         c[2] * __ldg(b.viscosity + idx) + c[3] * __ldg(b.viscosity + idx + sd);
+  }
+  // viscousFlux::CalcFlux (src/viscousFlux.cpp:58-135), TauNormal (src/utility.cpp:425-437)
+  double n[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) n[q] = __ldg(b.fA[D] + q * b.fs + idx);
+  const double mag = __ldg(b.fA[D] + 3 * b.fs + idx);
+  const double mus = p.tr.scaling * mu;
+  const double lambda = 0.0 - (2.0 / 3.0) * (mus + 0.0);
+  const double trace = grad[0][0] + grad[1][1] + grad[2][2];
+  double tau[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    // velGrad(r, c) = d u_c / d x_r = grad[c][r]; ((G + G^T) n)_r
+    double mm = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mm += (grad[c][r] + grad[r][c]) * n[c];
+    tau[r] = lambda * trace * n[r] + (mus + 0.0) * mm;
+  }
+  const double t = Temperature<NS>(p.gas, fs_);
+  const double kcond = EffectiveConductivity(p.tr, t);
+  const double fe = (tau[0] * fs_[E::imx] + tau[1] * fs_[E::imy] + tau[2] * fs_[E::imz]) +
+                    (kcond + 0.0) * (grad[3][0] * n[0] + grad[3][1] * n[1] + grad[3][2] * n[2]) + 0.0;
+  out[0] = tau[0] * mag;
+  out[1] = tau[1] * mag;
+  out[2] = tau[2] * mag;
+  out[3] = fe * mag;
+}
+
+// scratch: 4 doubles per face and direction. i-faces in vscr[0..3], j in [4..7], k in [8..11]
+// (field stride fs, face indexed like its upper cell)
+template <int NS, int NT>
+__global__ void __launch_bounds__(256) ViscFaceKernel(BlockDev b, Params p, double *__restrict__ scrA,
+                                                      double *__restrict__ scrB) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i > b.ni || j > b.nj || k > b.nk) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double f[4];
+  if (j < b.nj && k < b.nk) {
+    ViscFaceFlux<NS, NT, 0>(b, p, idx, f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) scrA[q * b.fs + idx] = f[q];
+  }
+  if (i < b.ni && k < b.nk) {
+    ViscFaceFlux<NS, NT, 1>(b, p, idx, f);
+    scrA[4 * b.fs + idx] = f[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) scrB[(q - 1) * b.fs + idx] = f[q];
+  }
+  if (i < b.ni && j < b.nj) {
+    ViscFaceFlux<NS, NT, 2>(b, p, idx, f);
+    scrB[3 * b.fs + idx] = f[0];
+    scrB[4 * b.fs + idx] = f[1];
+    // the last two ride in the (otherwise idle) second half of the MUSCL-coefficient-free
+    // matrix-residual field
+    b.mres[0 * b.fs + idx] = f[2];
+    b.mres[1 * b.fs + idx] = f[3];
+  }
+}
+
+// per cell: residual += viscous fluxes (+lower, -upper; i, j, k), spectral radius and diagonal
+// (ref: src/procBlock.cpp:1392-1493 and the J/K twins)
+template <int NS, int NT>
+__global__ void __launch_bounds__(256)
+    ViscAccumKernel(BlockDev b, Params p, const double *__restrict__ scrA,
+                    const double *__restrict__ scrB, int implicitScalar) {
+  using E = Eq<NS, NT>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
+  double s[E::neq];
+  LoadCell<E::neq>(b.state, b.fs, idx, s);
+  const double rho = SpeciesSum<NS>(s);
+  const double gam = Gamma<NS>(p.gas, s);
+  const double fac = ViscSpecFactor(p.tr, rho, gam, __ldg(b.viscosity + idx));
+  const double vol = __ldg(b.vol + idx);
+  double r[4], sr = b.specRad[idx], dg = implicitScalar ? b.diag[idx] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r[q] = b.resid[(NS + q) * b.fs + idx];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double lo[4], hi[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int slot = 4 * d + q;  // 0..4 scrA, 5..9 scrB, 10..11 mres
+      const double *f = slot < 5 ? scrA + slot * b.fs
+                                 : (slot < 10 ? scrB + (slot - 5) * b.fs : b.mres + (slot - 10) * b.fs);
+      lo[q] = f[idx];
+      hi[q] = f[idx + st[d]];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r[q] += lo[q];
+      r[q] -= hi[q];
+    }
+    const double fMag = 0.5 * (__ldg(b.fA[d] + 3 * b.fs + idx) + __ldg(b.fA[d] + 3 * b.fs + idx + st[d]));
+    const double vsr = fac * fMag * fMag / vol;
+    sr += vsr * p.viscCFLCoeff;
+    dg += 2.0 * vsr;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) b.resid[(NS + q) * b.fs + idx] = r[q];
+  b.specRad[idx] = sr;
+  if (implicitScalar) b.diag[idx] = dg;
+}
+
+}  // namespace aither

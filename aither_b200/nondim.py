@@ -48,25 +48,48 @@ def nondim_primitive(density, velocity, pressure, rho_ref, t_ref, fluid=None):
 _RECON = {"constant": (abi.RECON_CONSTANT, -2.0), "upwind": (abi.RECON_MUSCL, -1.0),
           "fromm": (abi.RECON_MUSCL, 0.0), "quick": (abi.RECON_MUSCL, 0.5),
           "central": (abi.RECON_MUSCL, 1.0), "thirdOrder": (abi.RECON_MUSCL, 1.0 / 3.0),
-          "weno": (abi.RECON_WENO, 0.0), "wenoZ": (abi.RECON_WENOZ, 0.0)}
+          # weno / wenoZ leave kappa at its out-of-range default (src/input.cpp:67,288-300)
+          "weno": (abi.RECON_WENO, -2.0), "wenoZ": (abi.RECON_WENOZ, -2.0)}
 _LIMITER = {"none": abi.LIMITER_NONE, "vanAlbada": abi.LIMITER_VAN_ALBADA,
             "minmod": abi.LIMITER_MINMOD}
 
 
+# fluidDatabase/air.dat Sutherland coefficients (viscosity C1, S; conductivity C1, S)
+AIR_SUTHERLAND = (1.458e-6, 110.4, 2.495e-3, 194.0)
+
+
+def viscous_terms(fluid, recon_kappa, visc_recon="central", sutherland=AIR_SUTHERLAND):
+    """cfg entries of `equationSet: navierStokes`: Sutherland reference values and scaling
+    (reference src/transport.cpp:50-68, include/transport.hpp:33-37) and the viscous CFL
+    coefficient (src/input.cpp:1110-1118)."""
+    c1, s_, k1, ks = sutherland
+    mu_ref = c1 * fluid.t_ref ** 1.5 / (fluid.t_ref + s_)
+    k_ref = fluid.a_ref * fluid.a_ref * mu_ref / fluid.t_ref
+    coeff = 4.0 if recon_kappa == 1.0 else (2.0 if recon_kappa == -2.0 else 1.0)
+    return dict(isViscous=1, viscRecon=0 if visc_recon == "central" else 1,
+                viscousCFLCoeff=coeff, nondimScaling=mu_ref / (fluid.rho_ref * fluid.a_ref *
+                                                               fluid.l_ref),
+                suthViscC1=[c1], suthViscS=[s_], suthCondC1=[k1], suthCondS=[ks],
+                tRef=fluid.t_ref, muMixRef=mu_ref, kMixRef=k_ref)
+
+
 def euler_cfg(fluid, *, g=2, solver="dplur", sweeps=4, limiter="none", flux="roe",
-              recon="thirdOrder", relaxation=1.0, bc_states=()):
+              recon="thirdOrder", relaxation=1.0, bc_states=(), viscous=False,
+              visc_recon="central"):
     """`aither_cfg` for `equationSet: euler`, `timeIntegration: implicitEuler` (theta=1, zeta=0;
     src/input.cpp:256-270), scalar diagonal (lusgs / dplur)."""
     rc, kappa = _RECON[recon]
     is_dplur = solver in ("dplur", "bdplur")
+    extra = viscous_terms(fluid, kappa, visc_recon) if viscous else dict(isViscous=0, viscRecon=0,
+                                                                         viscousCFLCoeff=1.0)
     return make_cfg(
-        numSpecies=1, numTurb=0, numGhosts=g, isViscous=0, isRANS=0,
+        numSpecies=1, numTurb=0, numGhosts=g, isRANS=0,
         isBlockMatrix=int(solver in ("blusgs", "bdplur")), isMultilevelTime=0,
         recon=rc, limiter=_LIMITER[limiter], invFlux=abi.FLUX_ROE if flux == "roe" else abi.FLUX_AUSM,
-        invFluxJac=abi.JAC_RUSANOV, viscRecon=0, turbModel=abi.TURB_NONE,
+        invFluxJac=abi.JAC_RUSANOV, turbModel=abi.TURB_NONE,
         solver=abi.SOLVER_DPLUR if is_dplur else abi.SOLVER_LUSGS,
         matrixSweeps=sweeps, matrixRequiresInit=int(is_dplur or sweeps > 1),  # input.cpp:1120
         kappa=kappa, theta=1.0, zeta=0.0, matrixRelaxation=relaxation, dualTimeCFL=-1.0,
-        dtNondim=-1.0, viscousCFLCoeff=1.0,
+        dtNondim=-1.0,
         gasConstant=[fluid.gas_constant], n=[fluid.n], hf=[fluid.hf],
-        bcStates=list(bc_states))
+        bcStates=list(bc_states), **extra)

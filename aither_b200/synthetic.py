@@ -129,22 +129,33 @@ def perturbed_state(shape_kji, neq_state, seed=0, amplitude=0.01):
 
 
 def box_problem(ni, nj, nk, *, solver="dplur", sweeps=4, limiter="none", flux="roe",
-                recon="thirdOrder", seed=0, amplitude=0.01):
-    """The synthetic single-block Euler case as a `Problem` (product-side set-up, no reference)."""
+                recon="thirdOrder", seed=0, amplitude=0.01, viscous=False, visc_recon="central",
+                wall=None, size=1.0):
+    """The synthetic single-block case as a `Problem` (product-side set-up, no reference): Euler,
+    or with `viscous` laminar Navier-Stokes with a viscous wall on the j-lo face (`wall`: None =
+    adiabatic, ("isothermal", T [K]), ("heatFlux", q)) on a box `size` metres wide."""
     g = {"constant": 1, "weno": 3, "wenoZ": 3}.get(recon, 2)  # input.cpp:1127-1144
-    m = block_metrics(box_nodes(ni, nj, nk), g)
+    m = block_metrics(box_nodes(ni, nj, nk, lengths=(size,) * 3, warp=0.02 * size, period=size), g)
     fluid = nondim.air(REF_RHO, REF_T)
     free = nondim.nondim_primitive(IC["density"], IC["velocity"], IC["pressure"], REF_RHO, REF_T)
+    bc_states = [dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
+                      velocity=list(free[1:4]), pressure=free[4], massFractions=[1.0])]
+    if viscous:
+        ws = dict(tag=2, type=abi.BC_VISCOUS_WALL, velocity=[0.0, 0.0, 0.0], massFractions=[1.0])
+        if wall is not None and wall[0] == "isothermal":
+            ws.update(isIsothermal=1, temperature=wall[1] / REF_T)
+        elif wall is not None and wall[0] == "heatFlux":
+            raise ValueError("heat-flux walls need the wall distance: use a reference dump")
+        bc_states.append(ws)
     cfg = nondim.euler_cfg(fluid, g=g, solver=solver, sweeps=sweeps, limiter=limiter, flux=flux,
-                           recon=recon,
-                           bc_states=[dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
-                                           velocity=list(free[1:4]), pressure=free[4],
-                                           massFractions=[1.0])])
+                           recon=recon, bc_states=bc_states, viscous=viscous,
+                           visc_recon=visc_recon)
     state = perturbed_state((nk + 2 * g, nj + 2 * g, ni + 2 * g), 5, seed, amplitude)
     surfaces = [
         (abi.BC_CHARACTERISTIC, 0, 0, 0, nj, 0, nk, 1),
         (abi.BC_CHARACTERISTIC, ni, ni, 0, nj, 0, nk, 1),
-        (abi.BC_SLIP_WALL, 0, ni, 0, 0, 0, nk, 0),
+        (abi.BC_VISCOUS_WALL, 0, ni, 0, 0, 0, nk, 2) if viscous
+        else (abi.BC_SLIP_WALL, 0, ni, 0, 0, 0, nk, 0),
         (abi.BC_SLIP_WALL, 0, ni, nj, nj, 0, nk, 0),
         (abi.BC_SLIP_WALL, 0, ni, 0, nj, 0, 0, 0),
         (abi.BC_SLIP_WALL, 0, ni, 0, nj, nk, nk, 0),

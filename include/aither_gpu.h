@@ -185,7 +185,8 @@ enum aither_field {
   AITHER_FIELD_CONS_N = 7,       /* no ghosts, neq */
   AITHER_FIELD_MATRIX_RESID = 8, /* no ghosts, neq: f - (Ax - b) */
   AITHER_FIELD_TEMPERATURE = 9,  /* ghost padded, 1 */
-  AITHER_FIELD_CONS_NM1 = 10     /* no ghosts, neq */
+  AITHER_FIELD_CONS_NM1 = 10,    /* no ghosts, neq */
+  AITHER_FIELD_VISCOSITY = 11    /* ghost padded, 1 (viscous runs) */
 };
 
 typedef struct aither_gpu aither_gpu;   /* opaque handle */

@@ -2024,6 +2024,7 @@ long long orc_field_size(orc_level *h, int blk, int field) {
     case AITHER_FIELD_CONS_N: return nc * h->neq;
     case AITHER_FIELD_MATRIX_RESID: return nc * h->neq;
     case AITHER_FIELD_TEMPERATURE: return np;
+    case AITHER_FIELD_VISCOSITY: return np;
     case AITHER_FIELD_CONS_NM1: return nc * h->neq;
   }
   return 0;
@@ -2043,6 +2044,7 @@ void orc_get_field(orc_level *h, int blk, int field, double *dst) {
     case AITHER_FIELD_CONS_N: src = b->consN; break;
     case AITHER_FIELD_MATRIX_RESID: src = b->mresid; break;
     case AITHER_FIELD_TEMPERATURE: src = b->temperature; break;
+    case AITHER_FIELD_VISCOSITY: src = b->viscosity; break;
     case AITHER_FIELD_CONS_NM1: src = b->consNm1; break;
   }
   if (src) memcpy(dst, src, sizeof(double) * orc_field_size(h, blk, field));

@@ -111,6 +111,7 @@ def check_phases(make_level, d, it, tol):
     lvl.calc_residual()
     if viscous:  # ghost cells as the viscous fluxes saw them (viscous-wall + edge refill)
         cmp(abi.FIELD_STATE, "state@%s.viscbc" % tag, "ghosts", mask_edges=True)
+        cmp(abi.FIELD_VISCOSITY, "viscosity@" + tag, "ghosts", mask_edges=True)
     cmp(abi.FIELD_RESIDUAL, "residual@" + tag, "residual")
     cmp(abi.FIELD_SPEC_RADIUS, "specRadius@" + tag, "specRadius", comps=slice(0, 1))
     lvl.calc_time_step(cfl)

@@ -117,6 +117,7 @@ class OracleLevel:
         lib().orc_get_field(self._h, blk, fld, out.ctypes.data_as(C.POINTER(C.c_double)))
         b = self.problem.blocks[blk]
         g = self.problem.cfg.numGhosts
-        padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE)
+        padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE,
+                         abi.FIELD_VISCOSITY)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
