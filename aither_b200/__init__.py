@@ -181,7 +181,7 @@ class GridLevel:
 
     def run(self, n_iter, cfl_start, cfl_step=0.0, cfl_max=None):
         """n_iter time steps back to back; returns hist[n_iter, neq + 1]."""
-        hist = np.zeros((n_iter, self.neq + 1))
+        hist = np.zeros((n_iter * max(1, self.problem.cfg.nonlinearIterations), self.neq + 1))
         self._check(self._lib.aither_gpu_run(self._h, n_iter, cfl_start, cfl_step,
                                              cfl_start if cfl_max is None else cfl_max, _ptr(hist)))
         return hist

@@ -219,11 +219,13 @@ bool Supported(const aither_cfg &c, std::string *why) {
 
 template <int NS, int NT, int RC, int LM, int FX>
 void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fusePrep, double cfl) {
+#ifdef AITHER_B200_LEGACY_RESIDUAL  // first-generation gather kernel, A/B builds only
   if (h->legacyKernels) {
     ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(
         hb.dev, h->params, implicitScalar);
     return;
   }
+#endif
   using S = ResSmem<NS, NT, RC>;
   auto kern = ResidualMarchKernel<NS, NT, RC, LM, FX>;
   static bool configured = false;  // per template instantiation
@@ -479,7 +481,8 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
   return 0;
 }
 
-int PhaseUpdate(aither_gpu *h, int slot) {
+int PhaseUpdate(aither_gpu *h, int slot, int mm) {
+  const int nl = std::max(1, h->cfg.nonlinearIterations);
   for (auto &hb : h->blocks) {
     {
       ScopedLaunch sl(h, kFamUpdate);
@@ -497,6 +500,12 @@ int PhaseUpdate(aither_gpu *h, int slot) {
       FinalizeLinfKernel<<<1, kFinalThreads, 0, h->stream>>>(h->dLinfPartials, hb.nCellBlocks,
                                                              hb.dev, h->neq, &h->dResults[slot]);
     }
+    // U^(n-1) <- U^n after the last nonlinear iteration of a multilevel scheme
+    // (ref: src/gridLevel.cpp:427-430)
+    if (h->cfg.isMultilevelTime && mm == nl - 1) {
+      CK(cudaMemcpyAsync(hb.dev.consNm1, hb.dev.consN, sizeof(double) * h->neq * hb.dev.fs,
+                         cudaMemcpyDeviceToDevice, h->stream));
+    }
   }
   CK(cudaGetLastError());
   return 0;
@@ -508,7 +517,7 @@ long long TotalPaddedSize(const aither_gpu *h) {
   return t;
 }
 
-int IterateAsync(aither_gpu *h, double cfl, int slot) {
+int IterateAsync(aither_gpu *h, double cfl, int slot, int mm) {
   if (ZeroResult(h, slot)) return 1;
   if (PhaseBoundaryConditions(h)) return 1;
   // inviscid: time step, diagonal, right-hand side and x0 ride in the residual kernel's epilogue
@@ -516,7 +525,7 @@ int IterateAsync(aither_gpu *h, double cfl, int slot) {
   if (PhaseResidual(h, fuse ? 1 : 0, cfl)) return 1;
   if (!fuse && PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
   if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
-  if (PhaseUpdate(h, slot)) return 1;
+  if (PhaseUpdate(h, slot, mm)) return 1;
   return 0;
 }
 
@@ -902,10 +911,9 @@ int aither_gpu_store_old_solution(aither_gpu *h, int iter) {
 
 int aither_gpu_iterate(aither_gpu *h, double cfl, int mm, double *residL2, aither_linf *linf,
                        double *matrixResid) {
-  (void)mm;
   if (!h) return Fail("null handle");
   CK(cudaSetDevice(h->device));
-  if (IterateAsync(h, cfl, 0)) return 1;
+  if (IterateAsync(h, cfl, 0, mm)) return 1;
   if (FetchResults(h, 1)) return 1;
   const IterResult &r = h->hResults[0];
   if (residL2)
@@ -927,12 +935,15 @@ int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep, do
   if (!h) return Fail("null handle");
   if (nIter < 1) return 0;
   CK(cudaSetDevice(h->device));
-  if (EnsureResults(h, nIter)) return 1;
+  const int nl = std::max(1, h->cfg.nonlinearIterations);
+  if (EnsureResults(h, nIter * nl)) return 1;
   for (int n = 0; n < nIter; ++n) {
     const double cfl = std::min(cflStart + n * cflStep, cflMax);  // ref: src/input.cpp:647
     if (aither_gpu_store_old_solution(h, n)) return 1;
-    if (IterateAsync(h, cfl, n)) return 1;
+    for (int mm = 0; mm < nl; ++mm)
+      if (IterateAsync(h, cfl, n * nl + mm, mm)) return 1;
   }
+  nIter *= nl;
   if (FetchResults(h, nIter)) return 1;
   if (hist) {
     const double tot = static_cast<double>(TotalPaddedSize(h));
@@ -991,11 +1002,10 @@ int aither_gpu_relax(aither_gpu *h, int sweeps, double *matrixResid) {
   return 0;
 }
 int aither_gpu_update_blocks(aither_gpu *h, int mm, double *residL2, aither_linf *linf) {
-  (void)mm;
   if (!h) return Fail("null handle");
   CK(cudaSetDevice(h->device));
   if (ZeroResult(h, 0)) return 1;
-  if (PhaseUpdate(h, 0)) return 1;
+  if (PhaseUpdate(h, 0, mm)) return 1;
   if (FetchResults(h, 1)) return 1;
   const IterResult &r = h->hResults[0];
   if (residL2)

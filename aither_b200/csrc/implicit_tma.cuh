@@ -118,17 +118,11 @@ __global__ void __launch_bounds__(kQThreads, 1)
     carryL[e] = 0.0;
     duPrev[e] = 0.0;
   }
-  // register prefetch, one plane ahead: k-face area above the current plane's cell, and what
-  // finishing the pending cell needs (rhs, D^-1 or D)
+  // what has no in-plane reuse comes through registers: the k-face area above this plane's cell
+  // (kept one plane, it is the next plane's lower face), right-hand side and D^-1 / D of the
+  // pending cell; the loads are issued at the top of a plane, before the wait on its tiles
   const long long idxCol = CellIdx(b, min(i, b.ni - 1), min(j, b.nj - 1), 0);
-  double faUp[4], faCur[4], rhsN[neq], dN = 0.0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    faCur[q] = 0.0;
-    faUp[q] = __ldg(b.fA[2] + q * b.fs + idxCol + static_cast<long long>(k0) * b.sk);
-  }
-#pragma unroll
-  for (int e = 0; e < neq; ++e) rhsN[e] = 0.0;
+  double faCur[4] = {0.0, 0.0, 0.0, 0.0};
 
   for (int it = 0; it < nIter; ++it) {
     const int k = k0 - 1 + it;
@@ -138,22 +132,22 @@ __global__ void __launch_bounds__(kQThreads, 1)
     const bool planeInterior = it > 0 && it < nIter - 1;
     const long long idx = idxCol + static_cast<long long>(k) * b.sk;
 
-    // issue next plane's register loads before waiting on this plane's tiles
-    double faNext[4], rhsNext[neq], dNext = 0.0;
-    if (it + 1 < nIter - 1) {  // next plane is interior: its face above is k + 2
+    // this plane's register operands, issued before waiting on its tiles
+    double faUp[4], rhsN[neq], dN = 0.0;
+    if (it < nIter - 1) {  // face k + 1: upper face of this plane's cell
 #pragma unroll
-      for (int q = 0; q < 4; ++q) faNext[q] = __ldg(b.fA[2] + q * b.fs + idx + 2 * b.sk);
+      for (int q = 0; q < 4; ++q) faUp[q] = __ldg(b.fA[2] + q * b.fs + idx + b.sk);
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) faNext[q] = 0.0;
+      for (int q = 0; q < 4; ++q) faUp[q] = 0.0;
     }
-    if (planeInterior) {  // this plane's cell is finished at the next plane
+    if (it >= 2) {  // the pending cell (k - 1) is finished in this plane
 #pragma unroll
-      for (int e = 0; e < neq; ++e) rhsNext[e] = __ldg(b.rhs + e * b.fs + idx);
-      dNext = __ldg((MODE == kModeDplur ? b.dinv : b.diag) + idx);
+      for (int e = 0; e < neq; ++e) rhsN[e] = __ldg(b.rhs + e * b.fs + idx - b.sk);
+      dN = __ldg((MODE == kModeDplur ? b.dinv : b.diag) + idx - b.sk);
     } else {
 #pragma unroll
-      for (int e = 0; e < neq; ++e) rhsNext[e] = 0.0;
+      for (int e = 0; e < neq; ++e) rhsN[e] = 0.0;
     }
 
     MbarWait(full + (it & 1), (it >> 1) & 1);
@@ -275,15 +269,10 @@ __global__ void __launch_bounds__(kQThreads, 1)
 #pragma unroll
     for (int e = 0; e < neq; ++e) {
       carryL[e] = newCarry[e];
-      rhsN[e] = rhsNext[e];
-      duPrev[e] = du[e];
+      if (MODE == kModeAxmb) duPrev[e] = du[e];
     }
-    dN = dNext;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      faCur[q] = faUp[q];
-      faUp[q] = faNext[q];
-    }
+    for (int q = 0; q < 4; ++q) faCur[q] = faUp[q];
     __syncthreads();  // every reader of this stage and of sG is done
     if (tid == 0 && it + 2 < nIter) issue(it + 2);
   }

@@ -58,6 +58,7 @@ class Cfg(C.Structure):
         ("recon", C.c_int), ("limiter", C.c_int), ("invFlux", C.c_int), ("invFluxJac", C.c_int),
         ("viscRecon", C.c_int), ("turbModel", C.c_int), ("solver", C.c_int),
         ("matrixSweeps", C.c_int), ("matrixRequiresInit", C.c_int),
+        ("nonlinearIterations", C.c_int),
         ("kappa", C.c_double), ("theta", C.c_double), ("zeta", C.c_double),
         ("matrixRelaxation", C.c_double), ("dualTimeCFL", C.c_double),
         ("dtNondim", C.c_double), ("viscousCFLCoeff", C.c_double),

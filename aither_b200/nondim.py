@@ -89,6 +89,7 @@ def euler_cfg(fluid, *, g=2, solver="dplur", sweeps=4, limiter="none", flux="roe
         invFluxJac=abi.JAC_RUSANOV, turbModel=abi.TURB_NONE,
         solver=abi.SOLVER_DPLUR if is_dplur else abi.SOLVER_LUSGS,
         matrixSweeps=sweeps, matrixRequiresInit=int(is_dplur or sweeps > 1),  # input.cpp:1120
+        nonlinearIterations=1,
         kappa=kappa, theta=1.0, zeta=0.0, matrixRelaxation=relaxation, dualTimeCFL=-1.0,
         dtNondim=-1.0,
         gasConstant=[fluid.gas_constant], n=[fluid.n], hf=[fluid.hf],

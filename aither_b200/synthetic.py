@@ -88,6 +88,35 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         ""])
 
 
+def read_plot3d(path):
+    """Blocks of a raw-binary multi-block Plot3D file as (nk+1, nj+1, ni+1, 3) node arrays."""
+    with open(path, "rb") as f:
+        nb = int(np.fromfile(f, dtype="<i4", count=1)[0])
+        dims = np.fromfile(f, dtype="<i4", count=3 * nb).reshape(nb, 3)
+        out = []
+        for ni1, nj1, nk1 in dims:
+            n = int(ni1) * int(nj1) * int(nk1)
+            xyz = np.fromfile(f, dtype="<f8", count=3 * n).reshape(3, nk1, nj1, ni1)
+            out.append(np.moveaxis(xyz, 0, -1))
+    return out
+
+
+def centroids(x):
+    return 0.125 * (x[:-1, :-1, :-1] + x[:-1, :-1, 1:] + x[:-1, 1:, :-1] + x[:-1, 1:, 1:] +
+                    x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:])
+
+
+def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air"):
+    """cloud file with seed-fixed noise on the IC state at the given points (see write_cloud)"""
+    rng = np.random.default_rng(seed)
+    base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
+    vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((cen.shape[0], 5)) - 1.0))
+    with open(path, "w") as f:
+        f.write("%d\n%s\n" % (cen.shape[0], species))
+        for c, v in zip(cen, vals):
+            f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
+
+
 def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air"):
     """Initial-condition cloud file (reference src/utility.cpp:513-520: `numberOfPoints`, species
     line, then `x y z rho u v w p tke omega mf...` per point), one point per cell centroid, with

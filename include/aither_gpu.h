@@ -99,6 +99,8 @@ typedef struct aither_cfg {
   int solver;                    /* aither_solver */
   int matrixSweeps;
   int matrixRequiresInit;        /* input::MatrixRequiresInitialization */
+  int nonlinearIterations;       /* per time step (>= 1); U^(n-1) <- U^n after the last one
+                                    of a multilevel scheme (src/gridLevel.cpp:418-431) */
   double kappa;
   double theta;                  /* Beam-Warming theta (input.cpp:256-270) */
   double zeta;
@@ -224,9 +226,10 @@ int aither_gpu_update_blocks(aither_gpu *h, int mm, double *residL2,
                              aither_linf *linf);
 int aither_gpu_reset_diagonal(aither_gpu *h);
 
-/* `nIter` iterations back to back without host synchronisation in between
- * (residual norms of every iteration land in hist: nIter x (neq + 1), the last
- * column being the matrix residual). Same arithmetic as aither_gpu_iterate;
+/* `nIter` time steps back to back without host synchronisation in between,
+ * each of cfg.nonlinearIterations nonlinear iterations (residual norms of every
+ * nonlinear iteration land in hist: (nIter * nonlinearIterations) x (neq + 1),
+ * the last column being the matrix residual). Same arithmetic as aither_gpu_iterate;
  * the call main.cpp's loop would make when the log is only read at the end. */
 int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep,
                    double cflMax, double *hist);

@@ -1847,7 +1847,6 @@ double orc_relax(orc_level *h, int sweeps) {
 void orc_update_blocks(orc_level *h, int mm, double *residL2,
                        aither_linf *linf) {
   /* ref: src/procBlock.cpp:826-871, :902-915 */
-  (void)mm;
   const int neq = h->neq;
   for (int bb = 0; bb < h->nblk; ++bb) {
     orc_block *b = &h->blk[bb];
@@ -1871,9 +1870,11 @@ void orc_update_blocks(orc_level *h, int mm, double *residL2,
             }
           }
         }
-    if (h->cfg.isMultilevelTime) {
-      /* handled by the caller on the last nonlinear iteration */
-    }
+    /* ref: src/gridLevel.cpp:427-430: U^(n-1) <- U^n at the end of the nonlinear iterations */
+    const int nl = h->cfg.nonlinearIterations > 0 ? h->cfg.nonlinearIterations : 1;
+    if (h->cfg.isMultilevelTime && mm == nl - 1)
+      memcpy(b->consNm1, b->consN,
+             sizeof(double) * (long)b->ni * b->nj * b->nk * h->neq);
   }
 }
 

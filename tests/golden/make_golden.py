@@ -57,6 +57,16 @@ CASES = {
     "box_visc_iso": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2,
                                         limiter="vanAlbada", viscous=True, size=2e-5,
                                         wall=("isothermal", 300.0)), iters=12, full=(0, 4)),
+    # reference regression case (regressionTests.py:271-287): two blocks, WENO, BDF2 with dual
+    # time stepping (5 nonlinear iterations per time step), LU-SGS
+    "shockTube": dict(src="shockTube", iters=40, full=(0,), edits={}),
+    # testCases/uniformFlow: 10 blocks joined through all 8 patch orientations. The shipped case is
+    # RANS (run-only check, regressionTests.py:482-496); here it runs as Euler from a perturbed
+    # state so that every orientation of the ghost exchange carries non-trivial data
+    "uniformFlow_euler": dict(src="uniformFlow", iters=20, full=(0, 5), cloud=(17, 0.01),
+                              edits={"equationSet": "euler", "turbulenceModel": "none",
+                                     "iterations": "20",
+                                     "initialConditions": "<icState(tag=-1; file=ic.dat)>"}),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
 }
@@ -78,6 +88,10 @@ def generate(name):
         else:
             inp = refcase.stage_case(os.path.join(REF_CASES, spec["src"]), tmp, spec["edits"],
                                      iterations=spec["iters"])
+            if "cloud" in spec:  # perturbed initial state at every cell centroid of the grid
+                blocks = synthetic.read_plot3d(os.path.join(tmp, inp[:-4] + ".xyz"))
+                nodes = np.concatenate([synthetic.centroids(b).reshape(-1, 3) for b in blocks])
+                synthetic.write_cloud_points(os.path.join(tmp, "ic.dat"), nodes, *spec["cloud"])
         d = refcase.run_harness(tmp, inp, spec["iters"], full=spec["full"], geom=True)
     out = {k: np.asarray(v) for k, v in d.items()
            if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time" and

@@ -84,6 +84,7 @@ def cfg_from_dump(d):
         invFluxJac=int(g("invFluxJac")[0]), viscRecon=int(g("viscRecon")[0]),
         turbModel=int(g("turbModel")[0]), solver=int(g("solver")[0]),
         matrixSweeps=int(g("matrixSweeps")[0]), matrixRequiresInit=int(g("matrixRequiresInit")[0]),
+        nonlinearIterations=int(g("nonlinearIterations")[0]),
         kappa=float(g("kappa")[0]), theta=float(g("theta")[0]), zeta=float(g("zeta")[0]),
         matrixRelaxation=float(g("matrixRelaxation")[0]), dualTimeCFL=float(g("dualTimeCFL")[0]),
         dtNondim=float(g("dtNondim")[0]), viscousCFLCoeff=float(g("viscousCFLCoeff")[0]),

@@ -39,3 +39,22 @@ def test_oracle_split_box_equals_whole_box():
     assert np.abs(sa - sb).max() <= 1e-14 * np.abs(sa).max()
     a.close()
     b.close()
+
+
+def test_oracle_uniform_flow_all_orientations():
+    """testCases/uniformFlow joins its 10 blocks through all 8 patch orientations (as Euler, from
+    a perturbed state): ghost cells after the swap are bit-identical to the reference's."""
+    d = gc.load("uniformFlow_euler")
+    assert sorted(set(int(c[26]) for c in d["connections"])) == [1, 2, 3, 4, 5, 6, 7, 8]
+    for it in gc.full_iterations(d):
+        out = gc.check_phases(oracle.OracleLevel, d, it, TOL)
+        assert out["ghosts"] == 0.0
+    assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
+
+
+def test_oracle_shock_tube_bdf2_dual_time():
+    """testCases/shockTube (regressionTests.py:271-287): two blocks, WENO, BDF2 with dual time
+    stepping, 5 nonlinear iterations per step -- 40 steps = 200 history records."""
+    d = gc.load("shockTube")
+    gc.check_phases(oracle.OracleLevel, d, 0, TOL)
+    assert gc.check_history(oracle.OracleLevel, d, 200, 1e-9) <= 1e-9

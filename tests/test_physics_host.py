@@ -25,9 +25,9 @@ def ptr(a):
 def hs():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
     out = os.path.join(HERE, "hostsim", "libhostsim.so")
-    hdr = os.path.join(HERE, "..", "aither_b200", "csrc", "physics.cuh")
-    if (not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src),
-                                                               os.path.getmtime(hdr))):
+    deps = [src, os.path.join(HERE, "..", "aither_b200", "csrc", "physics.cuh"),
+            os.path.join(HERE, "..", "include", "aither_gpu.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared",
                                "-o", out, src])
     return C.CDLL(out)
