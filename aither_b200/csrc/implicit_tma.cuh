@@ -160,26 +160,12 @@ __global__ void __launch_bounds__(kQThreads, 1)
       du[e] = sX[e * kQPC + pc];
     }
     MakeIngr<NS, NT>(p.gas, s, du, &H, &a, sn, &Hn);
-    if (planeInterior) {
+    if (it < nIter - 1) {  // every plane that has a cell above it in the chunk
       sG[pc] = H;
       sG[kQPC + pc] = a;
 #pragma unroll
       for (int e = 0; e < neq; ++e) sG[(2 + e) * kQPC + pc] = sn[e];
       sG[(2 + neq) * kQPC + pc] = Hn;
-      if (hc >= 0) {
-        double hs[neq], hdu[neq], hH, ha, hsn[neq], hHn;
-#pragma unroll
-        for (int e = 0; e < neq; ++e) {
-          hs[e] = sS[e * kQPC + hc];
-          hdu[e] = sX[e * kQPC + hc];
-        }
-        MakeIngr<NS, NT>(p.gas, hs, hdu, &hH, &ha, hsn, &hHn);
-        sG[hc] = hH;
-        sG[kQPC + hc] = ha;
-#pragma unroll
-        for (int e = 0; e < neq; ++e) sG[(2 + e) * kQPC + hc] = hsn[e];
-        sG[(2 + neq) * kQPC + hc] = hHn;
-      }
     }
     // own ingredients in the OffDiagFromIngr layout: s | H a | du | sn | Hn
     auto ldOwn = [&](int q) {
@@ -191,9 +177,6 @@ __global__ void __launch_bounds__(kQThreads, 1)
                                                                            ? sn[q - 2 * neq - 2]
                                                                            : Hn))));
     };
-    double newCarry[neq];
-#pragma unroll
-    for (int e = 0; e < neq; ++e) newCarry[e] = 0.0;
     if (colValid && it >= 2) {
       // U-term of the cell below (k-1) across face k, then finish that cell
       const bool useKhi = k < b.nk || ConnAcross(b, 6, i, b.ni, j);
@@ -213,9 +196,21 @@ __global__ void __launch_bounds__(kQThreads, 1)
         }
       }
     }
-    if (colValid && it + 1 < nIter - 1) {
-      // L-term this cell contributes to the cell above (k+1), across face k+1
-      OffDiagFromIngr<NS, NT>(ldOwn, faUp, true, newCarry);
+    // ring of halo cells (threads 0..95), after the pending cell has been finished so that this
+    // thread's own ingredients no longer occupy registers
+    if (planeInterior && hc >= 0) {
+      double hs[neq], hdu[neq], hH, ha, hsn[neq], hHn;
+#pragma unroll
+      for (int e = 0; e < neq; ++e) {
+        hs[e] = sS[e * kQPC + hc];
+        hdu[e] = sX[e * kQPC + hc];
+      }
+      MakeIngr<NS, NT>(p.gas, hs, hdu, &hH, &ha, hsn, &hHn);
+      sG[hc] = hH;
+      sG[kQPC + hc] = ha;
+#pragma unroll
+      for (int e = 0; e < neq; ++e) sG[(2 + e) * kQPC + hc] = hsn[e];
+      sG[(2 + neq) * kQPC + hc] = hHn;
     }
     __syncthreads();  // sG of this plane is complete
     if (colValid && planeInterior) {
@@ -266,10 +261,23 @@ __global__ void __launch_bounds__(kQThreads, 1)
         OffDiagFromIngr<NS, NT>(nb(pc + kQPI), fa, false, accUp);
       }
     }
+    // L-term this cell contributes to the cell above (k+1), across face k+1. Its ingredients are
+    // read back from shared memory so that they need not stay in registers through the
+    // neighbour phase; the previous carry has been consumed above.
 #pragma unroll
-    for (int e = 0; e < neq; ++e) {
-      carryL[e] = newCarry[e];
-      if (MODE == kModeAxmb) duPrev[e] = du[e];
+    for (int e = 0; e < neq; ++e) carryL[e] = 0.0;
+    if (colValid && it + 1 < nIter - 1) {
+      auto own = [=](int q) {
+        return q < neq ? sS[q * kQPC + pc]
+                       : (q < neq + 2 ? sG[(q - neq) * kQPC + pc]
+                                      : (q < 2 * neq + 2 ? sX[(q - neq - 2) * kQPC + pc]
+                                                         : sG[(q - 2 * neq) * kQPC + pc]));
+      };
+      OffDiagFromIngr<NS, NT>(own, faUp, true, carryL);
+    }
+    if (MODE == kModeAxmb) {
+#pragma unroll
+      for (int e = 0; e < neq; ++e) duPrev[e] = sX[e * kQPC + pc];
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) faCur[q] = faUp[q];

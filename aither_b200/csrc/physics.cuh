@@ -55,6 +55,23 @@ inline void GasFinalize(Gas *g) {
   g->gamma0 = (g->R[0] * (g->n[0] + 1.0)) / (g->R[0] * g->n[0]);
 }
 
+// 1/x for the hot loops. The compiler's IEEE fp64 reciprocal / division is ~12 instructions plus
+// a guarded slow-path call (a BSSY/BSYNC region per division: 14 % of the residual kernel's stall
+// samples, profiles/r01c_*); this is the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton
+// steps: 5 instructions, no branch, <= 1 ulp for normal-range arguments (all we feed it:
+// densities, 1 + sqrt(rho_R / rho_L), a^2, eps + slope). Host builds (tests/hostsim) divide.
+AITHER_HD double FastRcp(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(y, fma(-x, y, 1.0), y);
+  y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Equation layout for NS species and NT turbulence equations
 // (ref: include/varArray.hpp:47-51): [rho_1..rho_NS, u, v, w, p, (k, omega)].
 template <int NS, int NT>
@@ -232,7 +249,7 @@ template <int LIM>
 AITHER_HD double Muscl1(double u2, double u1, double d1, double kappa, double dPlus,
                         double dMinus) {
   const double dm = (u1 - u2) * dMinus;
-  const double r = (kEps + (d1 - u1) * dPlus) / (kEps + dm);
+  const double r = (kEps + (d1 - u1) * dPlus) * FastRcp(kEps + dm);
   double lim = 1.0, invLim = 1.0;
   if (LIM != AITHER_LIMITER_NONE) {
     lim = Limiter<LIM>(r);
@@ -603,7 +620,7 @@ AITHER_HD MixK<NS> MixOf(const Gas &g, const double *s) {
   MixK<NS> m;
   if (NS == 1) {
     m.rho = s[0];
-    m.rhoInv = 1.0 / s[0];
+    m.rhoInv = FastRcp(s[0]);
     m.cp = g.R[0] * (g.n[0] + 1.0);
     m.cv = g.R[0] * g.n[0];
     m.cvInv = g.cvInv0;
@@ -640,7 +657,7 @@ AITHER_HD void RoeFluxFast(const Gas &g, const double *l, const double *r,
   const MixK<NS> ml = MixOf<NS>(g, l);
   const MixK<NS> mr = MixOf<NS>(g, r);
   const double denRatio = sqrt(mr.rho * ml.rhoInv);
-  const double inv1p = 1.0 / (1.0 + denRatio);
+  const double inv1p = FastRcp(1.0 + denRatio);
   double roe[E::neq];
 #pragma unroll
   for (int q = 0; q < NS; ++q) roe[q] = l[q] * denRatio;
@@ -652,7 +669,7 @@ AITHER_HD void RoeFluxFast(const Gas &g, const double *l, const double *r,
   const double hR = mm.hf + mm.cp * tR + 0.5 * q2;
   const double a2 = mm.gamma * roe[E::ie] * mm.rhoInv;
   const double aR = sqrt(a2);
-  const double a2inv = 1.0 / (aR * aR);
+  const double a2inv = FastRcp(aR * aR);
   const double rhoR = mm.rho;
   const double velNormR = roe[E::imx] * n[0] + roe[E::imy] * n[1] + roe[E::imz] * n[2];
   double delta[E::neq];
@@ -775,7 +792,7 @@ AITHER_HD void MakeIngr(const Gas &g, const double *s, const double *du,
 #pragma unroll
   for (int tq = 0; tq < NT; ++tq) c[E::it + tq] = m.rho * s[E::it + tq] + du[E::it + tq];
   double rho = SpeciesSum<NS>(c);
-  double rhoInv = 1.0 / rho;
+  double rhoInv = FastRcp(rho);  // the same reciprocal MixOf(sn) forms below (one species)
   if (NS > 1) {
     double mf[NS], total = 0.0;
 #pragma unroll
