@@ -198,13 +198,8 @@ __global__ void __launch_bounds__(kMThreads, 2)
   const int fIlo = tx + (kMI + 1) * ty, fJlo = S::FI + tx + kMI * ty;
   double pend[E::neq];                       // residual of the cell one plane below, k-hi missing
   double pendSpec = 0.0, sosPrev = 0.0;
-  double fAkLo[4] = {0.0, 0.0, 0.0, 0.0};    // k-face area at plane k (lower face of cell k)
-  double sPrev[E::neq];
 #pragma unroll
-  for (int e = 0; e < E::neq; ++e) {
-    pend[e] = 0.0;
-    sPrev[e] = 0.0;
-  }
+  for (int e = 0; e < E::neq; ++e) pend[e] = 0.0;
 
   for (int k = k0; k <= k1; ++k) {
     CpAsyncWaitAll();
@@ -278,6 +273,14 @@ __global__ void __launch_bounds__(kMThreads, 2)
     // finalise the cell below (k-1): add its upper k-face flux, k-direction spectral radius
     if (colValid && k > k0) {
       const long long idxm = idx - b.sk;
+      // the pending cell's state is still in the ring (plane k-1) and its lower k-face area in
+      // L1: re-read both instead of carrying nine doubles through the face loop
+      double sPrev[E::neq], fAkLo[4];
+      const int prevBase = slotOf(k - 1) * SLOTSZ;
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) sPrev[e] = ring[prevBase + e * PC + pc];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) fAkLo[q] = __ldg(b.fA[2] + q * b.fs + idxm);
       double res[E::neq];
 #pragma unroll
       for (int e = 0; e < E::neq; ++e) {
@@ -335,7 +338,6 @@ __global__ void __launch_bounds__(kMThreads, 2)
         r += sfl[e * FTOT + fJlo + kMI];
         r -= fk[e];
         pend[e] = r;
-        sPrev[e] = s[e];
       }
       double sr = 0.0;
 #pragma unroll
@@ -352,8 +354,6 @@ __global__ void __launch_bounds__(kMThreads, 2)
       sr += InvCellSpectralRadius<NS>(s, sos, aLo, aHi);
       pendSpec = sr;
       sosPrev = sos;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) fAkLo[q] = fAk[q];
     }
   }
   CpAsyncWaitAll();

@@ -301,7 +301,7 @@ AITHER_HD void LagrangeCoeff(const double *w, int rr, int ii, double *coeffs) {
           denom *= StencilWidth(w, ii - rr + ll, ii - rr + mm);
         }
       }
-      cj += numer / denom;
+      cj += numer * FastRcp(denom);
     }
     coeffs[jj] = cj * w[ii - rr + jj];
   }
@@ -322,11 +322,18 @@ AITHER_HD double BetaIntegral(double d1, double d2, double dx, double xl, double
   return BetaIntegral1(d1, d2, dx, xh) - BetaIntegral1(d1, d2, dx, xl);
 }
 
-// WENO5 / WENO-Z weights that depend only on the five cell widths.
+// WENO5 / WENO-Z quantities that depend only on the five cell widths. Besides the Lagrange
+// coefficients and linear weights this holds the reciprocals of every width combination the
+// smoothness indicators divide by (the reference re-divides per variable: Deriv2nd,
+// include/utility.hpp:116-122, and the d1 terms of include/reconstruction.hpp:185-240 -- 12
+// divisions per variable per side) and the two width factors of the closed-form beta integral.
 struct WenoGeom {
   double c0[3], c1[3], c2[3];
   double lw0, lw1, lw2;
-  double w[5];
+  double rA, rB, rC, rD;  // 1 / (0.5 (w1 + w0)), ... (w2 + w1), (w3 + w2), (w4 + w3)
+  double q0, q1, q2;      // 1 / (0.25 (w2 + w0) + 0.5 w1), ... (w3 + w1) .. w2, (w4 + w2) .. w3
+  double hw;              // 0.5 w2
+  double bA1, bA2;        // beta = d1^2 bA1 + d2^2 bA2
 };
 AITHER_HD WenoGeom WenoSetup(const double *w) {
   // ref: include/reconstruction.hpp:256-282
@@ -336,51 +343,59 @@ AITHER_HD WenoGeom WenoSetup(const double *w) {
   LagrangeCoeff<2>(w, 1, 2, g.c1);
   LagrangeCoeff<2>(w, 0, 2, g.c2);
   LagrangeCoeff<4>(w, 2, 2, fc);
-  g.lw0 = fc[0] / g.c0[0];
-  g.lw1 = fc[4] / g.c2[2];
+  g.lw0 = fc[0] * FastRcp(g.c0[0]);
+  g.lw1 = fc[4] * FastRcp(g.c2[2]);
   g.lw2 = 1.0 - g.lw0 - g.lw1;
-#pragma unroll
-  for (int q = 0; q < 5; ++q) g.w[q] = w[q];
+  g.rA = FastRcp(0.5 * (w[1] + w[0]));
+  g.rB = FastRcp(0.5 * (w[2] + w[1]));
+  g.rC = FastRcp(0.5 * (w[3] + w[2]));
+  g.rD = FastRcp(0.5 * (w[4] + w[3]));
+  g.q0 = FastRcp(0.25 * (w[2] + w[0]) + 0.5 * w[1]);
+  g.q1 = FastRcp(0.25 * (w[3] + w[1]) + 0.5 * w[2]);
+  g.q2 = FastRcp(0.25 * (w[4] + w[2]) + 0.5 * w[3]);
+  g.hw = 0.5 * w[2];
+  // BetaIntegral(d1, d2, dx = w2, -w2/2, +w2/2) (include/reconstruction.hpp:157-183): the terms odd
+  // in x double, the even one cancels: d1^2 (2 h dx) + d2^2 (2 h^3 dx / 3 + 2 h dx^3), h = w2 / 2
+  const double dx = w[2], h = g.hw;
+  g.bA1 = 2.0 * h * dx;
+  g.bA2 = 2.0 * (h * h * h) * dx / 3.0 + 2.0 * h * (dx * dx * dx);
   return g;
 }
 // one component; y = {upwind3, upwind2, upwind1, downwind1, downwind2};
 // ref: include/reconstruction.hpp:185-240 (Beta0/1/2), :284-310
 template <bool WENOZ>
 AITHER_HD double Weno1(const WenoGeom &g, double y0, double y1, double y2, double y3, double y4) {
-  const double *w = g.w;
   const double st0 = g.c0[0] * y0 + g.c0[1] * y1 + g.c0[2] * y2;
   const double st1 = g.c1[0] * y1 + g.c1[1] * y2 + g.c1[2] * y3;
   const double st2 = g.c2[0] * y2 + g.c2[1] * y3 + g.c2[2] * y4;
-  double d2 = Deriv2nd(w[0], w[1], w[2], y0, y1, y2);
-  double d1 = (y2 - y1) / (0.5 * (w[2] + w[1])) + 0.5 * w[2] * d2;
-  const double b0 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
-  d2 = Deriv2nd(w[1], w[2], w[3], y1, y2, y3);
-  d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
-  const double b1 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
-  d2 = Deriv2nd(w[2], w[3], w[4], y2, y3, y4);
-  d1 = (y3 - y2) / (0.5 * (w[3] + w[2])) - 0.5 * w[2] * d2;
-  const double b2 = BetaIntegral(d1, d2, w[2], -0.5 * w[2], 0.5 * w[2]);
+  const double e1 = (y1 - y0) * g.rA, e2 = (y2 - y1) * g.rB, e3 = (y3 - y2) * g.rC,
+               e4 = (y4 - y3) * g.rD;
+  double d2 = (e2 - e1) * g.q0;
+  double d1 = e2 + g.hw * d2;
+  const double b0 = (d1 * d1) * g.bA1 + (d2 * d2) * g.bA2;
+  d2 = (e3 - e2) * g.q1;
+  d1 = e3 - g.hw * d2;
+  const double b1 = (d1 * d1) * g.bA1 + (d2 * d2) * g.bA2;
+  d2 = (e4 - e3) * g.q2;
+  d1 = e3 - g.hw * d2;
+  const double b2 = (d1 * d1) * g.bA1 + (d2 * d2) * g.bA2;
   double n0, n1, n2;
   if (WENOZ) {
     const double tau5 = fabs(b0 - b2);
     const double eps = 1.0e-40;
-    double t = tau5 / (eps + b0);
+    double t = tau5 * FastRcp(eps + b0);
     n0 = g.lw0 * (1.0 + t * t);
-    t = tau5 / (eps + b1);
+    t = tau5 * FastRcp(eps + b1);
     n1 = g.lw1 * (1.0 + t * t);
-    t = tau5 / (eps + b2);
+    t = tau5 * FastRcp(eps + b2);
     n2 = g.lw2 * (1.0 + t * t);
   } else {
     const double eps = 1.0e-6;
-    n0 = g.lw0 / ((eps + b0) * (eps + b0));
-    n1 = g.lw1 / ((eps + b1) * (eps + b1));
-    n2 = g.lw2 / ((eps + b2) * (eps + b2));
+    n0 = g.lw0 * FastRcp((eps + b0) * (eps + b0));
+    n1 = g.lw1 * FastRcp((eps + b1) * (eps + b1));
+    n2 = g.lw2 * FastRcp((eps + b2) * (eps + b2));
   }
-  const double sum = n0 + n1 + n2;
-  n0 /= sum;
-  n1 /= sum;
-  n2 /= sum;
-  return n0 * st0 + n1 * st1 + n2 * st2;
+  return (n0 * st0 + n1 * st1 + n2 * st2) * FastRcp(n0 + n1 + n2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -570,10 +585,10 @@ template <int NS>
 AITHER_HD double InvCellSpectralRadius(const double *s, double sos, const double *fL,
                                        const double *fR) {
   double a0 = 0.5 * (fL[0] + fR[0]), a1 = 0.5 * (fL[1] + fR[1]), a2 = 0.5 * (fL[2] + fR[2]);
-  const double mag = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-  a0 /= mag;
-  a1 /= mag;
-  a2 /= mag;
+  const double rmag = FastRcp(sqrt(a0 * a0 + a1 * a1 + a2 * a2));
+  a0 *= rmag;
+  a1 *= rmag;
+  a2 *= rmag;
   const double fMag = 0.5 * (fL[3] + fR[3]);
   return (fabs(s[NS] * a0 + s[NS + 1] * a1 + s[NS + 2] * a2) + sos) * fMag;
 }
