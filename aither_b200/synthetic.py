@@ -45,11 +45,15 @@ def write_plot3d(path, blocks_nodes):
 
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
-             visc_recon="central", wall=None):
+             visc_recon="central", wall=None, turb=None):
     """`viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
-    ("isothermal", T) or ("heatFlux", q))."""
+    ("isothermal", T) or ("heatFlux", q)). `turb`: None, "kOmegaWilcox2006" or "sst2003" (RANS,
+    implies viscous; farfield turbulence intensity 1 %, eddy viscosity ratio 10)."""
+    viscous = viscous or turb is not None
     vel = "[%g, %g, %g]" % IC["velocity"]
     state = "pressure=%g; density=%g; velocity=%s" % (IC["pressure"], IC["density"], vel)
+    if turb is not None:
+        state += "; turbulenceIntensity=0.01; eddyViscosityRatio=10"
     ic = "icState(tag=-1; %s)" % state if ic_file is None else "icState(tag=-1; file=%s)" % ic_file
     wall_state = "viscousWall(tag=2)"
     if wall is not None and wall[0] == "isothermal":
@@ -58,7 +62,8 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         wall_state = "viscousWall(tag=2; heatFlux=%g)" % wall[1]
     return "\n".join([
         "gridName: %s" % name,
-        "equationSet: %s" % ("navierStokes" if viscous else "euler"),
+        "equationSet: %s" % ("rans" if turb else ("navierStokes" if viscous else "euler")),
+        "turbulenceModel: %s" % (turb or "none"),
         "timeIntegration: implicitEuler",
         "cflStart: %g" % cfl, "cflMax: %g" % cfl,
         "faceReconstruction: %s" % recon,
@@ -117,7 +122,7 @@ def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air"):
             f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
 
 
-def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air"):
+def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None):
     """Initial-condition cloud file (reference src/utility.cpp:513-520: `numberOfPoints`, species
     line, then `x y z rho u v w p tke omega mf...` per point), one point per cell centroid, with
     seed-fixed +-amplitude noise on rho, u, v, w, p. The reference assigns each cell the state of
@@ -128,10 +133,19 @@ def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air"):
     rng = np.random.default_rng(seed)
     base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
     vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((cen.shape[0], 5)) - 1.0))
+    kw = np.zeros((cen.shape[0], 2))
+    if turb is not None:
+        # farfield-like turbulence: k = 1.5 (0.01 |v|)^2, omega = rho k / (10 mu), +- noise
+        vmag = np.linalg.norm(IC["velocity"])
+        k0 = 1.5 * (0.01 * vmag) ** 2
+        mu0 = 1.458e-6 * REF_T ** 1.5 / (REF_T + 110.4)
+        w0 = IC["density"] * k0 / (10.0 * mu0)
+        kw = np.array([k0, w0])[None, :] * (1.0 + amplitude *
+                                            (2.0 * rng.random((cen.shape[0], 2)) - 1.0))
     with open(path, "w") as f:
         f.write("%d\n%s\n" % (cen.shape[0], species))
-        for c, v in zip(cen, vals):
-            f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
+        for c, v, t in zip(cen, vals, kw):
+            f.write(" ".join("%.17g" % x for x in (*c, *v, *t, 1.0)) + "\n")
 
 
 def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
@@ -142,7 +156,7 @@ def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
     nodes = box_nodes(ni, nj, nk, lengths=(size, size, size), warp=0.02 * size, period=size)
     write_plot3d(os.path.join(case_dir, name + ".xyz"), [nodes])
     if perturb is not None:
-        write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb)
+        write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb, turb=kw.get("turb"))
         kw["ic_file"] = "ic.dat"
     with open(os.path.join(case_dir, name + ".inp"), "w") as f:
         f.write(inp_text(name, ni, nj, nk, **kw))

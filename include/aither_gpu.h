@@ -188,7 +188,14 @@ enum aither_field {
   AITHER_FIELD_MATRIX_RESID = 8, /* no ghosts, neq: f - (Ax - b) */
   AITHER_FIELD_TEMPERATURE = 9,  /* ghost padded, 1 */
   AITHER_FIELD_CONS_NM1 = 10,    /* no ghosts, neq */
-  AITHER_FIELD_VISCOSITY = 11    /* ghost padded, 1 (viscous runs) */
+  AITHER_FIELD_VISCOSITY = 11,   /* ghost padded, 1 (viscous runs) */
+  /* RANS runs: cell averages of the six face values (procBlock.cpp:1396-1452) */
+  AITHER_FIELD_EDDY_VISCOSITY = 12, /* ghost padded, 1 */
+  AITHER_FIELD_F1 = 13,          /* ghost padded, 1 */
+  AITHER_FIELD_F2 = 14,          /* ghost padded, 1 */
+  AITHER_FIELD_VELOCITY_GRAD = 15, /* ghost padded, 9: (r,c) = d u_c / d x_r */
+  AITHER_FIELD_TKE_GRAD = 16,    /* no ghosts, 3 */
+  AITHER_FIELD_OMEGA_GRAD = 17   /* no ghosts, 3 */
 };
 
 typedef struct aither_gpu aither_gpu;   /* opaque handle */

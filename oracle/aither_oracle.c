@@ -32,6 +32,11 @@ typedef struct {
   double *mresid;    /* ni nj nk neq: matrix residual */
   double *temperature; /* padded */
   double *viscosity;   /* padded (viscous only) */
+  /* RANS: cell values accumulated as 1/6 of the six face values
+   * (ref: src/procBlock.cpp:1396-1452) */
+  double *eddyVisc, *f1, *f2; /* padded; ghosts only across connections */
+  double *velGrad;            /* padded, 9: velGrad(r,c) = d u_c / d x_r */
+  double *tkeGrad, *omegaGrad; /* ni nj nk 3 */
   const double *vol, *fAI, *fAJ, *fAK, *center, *cwI, *cwJ, *cwK, *wallDist;
   int *order; /* hyperplane ordering: 3 ints per cell */
 } orc_block;
@@ -579,9 +584,21 @@ static void extrapolate_hold_mixture(const orc_level *h, const double *bnd,
 
 /* ref: src/ghostStates.cpp:62-689 (GetGhostState), inviscid / low-Re subset */
 static double eff_conductivity(const orc_level *h, double t);
+static double viscosity_of(const orc_level *h, double t);
+/* primitive::ApplyFarfieldTurbBC; ref: src/primitive.cpp:83-98 */
+static void apply_farfield_turb(const orc_level *h, double *s, const double vel[3],
+                                double turbInten, double viscRatio) {
+  const int it = h->ns + 4;
+  const double vmag = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  s[it] = 1.5 * pow(turbInten * vmag, 2.0);
+  s[it + 1] = rho_of(h, s) * s[it] / (viscRatio * viscosity_of(h, temperature_of(h, s)));
+  for (int tt = 0; tt < h->nt; ++tt)
+    s[it + tt] = s[it + tt] > 1.0e-20 ? s[it + tt] : 1.0e-20;
+}
 static void ghost_state(const orc_level *h, const double *interior, int bcType,
                         const double areaVec[3], int surf, int tag, int layer,
-                        double wallDist, double *ghost) {
+                        double wallDist, double nuW, double *ghost) {
+  const int rans = h->nt > 0, it = h->ns + 4;
   const int ns = h->ns, neq = h->neq;
   const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3;
   for (int e = 0; e < neq; ++e) ghost[e] = interior[e];
@@ -619,6 +636,15 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
       const double rho = ghost[ie] / (R * tGhost);
       for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * mf[ss];
     }
+    if (rans) { /* ref: :262-281 (low-Re wall) */
+      ghost[it] = -1.0 * interior[it];
+      const double scaling = h->cfg.nondimScaling;
+      const double wWall = scaling * scaling * 60.0 * nuW /
+                           (wallDist * wallDist * (h->cfg.turbModel == AITHER_TURB_SST
+                                                       ? 0.075 : 0.0708));
+      ghost[it + 1] = 2.0 * wWall - interior[it + 1];
+      if (layer > 1) ghost[it + 1] = layer * ghost[it + 1] - wWall;
+    }
   } else if (bcType == AITHER_BC_CHARACTERISTIC) { /* ref: :289-386 */
     const aither_bc_state *bc = bc_data(h, tag);
     double freeState[MAXEQ];
@@ -635,6 +661,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     const double machInt = fabs(velIntNorm) / SoSInt;
     if (machInt >= 1.0 && velIntNorm < 0.0) {
       for (int e = 0; e < neq; ++e) ghost[e] = freeState[e];
+      if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                    bc->eddyViscosityRatio);
     } else if (machInt >= 1.0 && velIntNorm >= 0.0) {
       /* supersonic outflow: interior */
     } else if (machInt < 1.0 && velIntNorm < 0.0) {
@@ -653,6 +681,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
       ghost[imx] = freeState[imx] - nA[0] * deltaPressure / rhoSoSInt;
       ghost[imy] = freeState[imy] - nA[1] * deltaPressure / rhoSoSInt;
       ghost[imz] = freeState[imz] - nA[2] * deltaPressure / rhoSoSInt;
+      if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                    bc->eddyViscosityRatio);
     } else if (machInt < 1.0 && velIntNorm >= 0.0) {
       const double rhoSoSInt = rho_of(h, interior) * SoSInt;
       const double deltaPressure = interior[ie] - freeState[ie];
@@ -671,6 +701,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     if (layer > 1) {
       extrapolate_hold_mixture(h, ghost, (double)layer, interior, tmp);
       for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+      if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                    bc->eddyViscosityRatio);
     }
   } else if (bcType == AITHER_BC_INLET) { /* ref: :391-484, reflecting */
     const aither_bc_state *bc = bc_data(h, tag);
@@ -688,6 +720,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     const double machInt = fabs(velIntNorm) / SoSInt;
     if (machInt >= 1.0) {
       for (int e = 0; e < neq; ++e) ghost[e] = freeState[e];
+      if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                    bc->eddyViscosityRatio);
     } else {
       const double rhoSoSInt = rho_of(h, interior) * SoSInt;
       const double vd[3] = {freeState[imx] - interior[imx],
@@ -704,6 +738,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
       ghost[imx] = freeState[imx] - nA[0] * deltaPressure / rhoSoSInt;
       ghost[imy] = freeState[imy] - nA[1] * deltaPressure / rhoSoSInt;
       ghost[imz] = freeState[imz] - nA[2] * deltaPressure / rhoSoSInt;
+      if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                    bc->eddyViscosityRatio);
       double tmp[MAXEQ];
       extrapolate_hold_mixture(h, ghost, 2.0, interior, tmp);
       for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
@@ -720,6 +756,8 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     ghost[imy] = bc->velocity[1];
     ghost[imz] = bc->velocity[2];
     ghost[ie] = bc->pressure;
+    if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
+                                  bc->eddyViscosityRatio);
   } else if (bcType == AITHER_BC_SUPERSONIC_OUTFLOW) { /* ref: :522-527 */
     if (layer > 1)
       for (int e = 0; e < neq; ++e) ghost[e] = layer * ghost[e] - interior[e];
@@ -757,12 +795,18 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     ghost[imy] = vbMag * bc->direction[1];
     ghost[imz] = vbMag * bc->direction[2];
     ghost[ie] = pb;
+    if (rans) apply_farfield_turb(h, ghost, ghost + imx, bc->turbulenceIntensity,
+                                  bc->eddyViscosityRatio);
     double tmp[MAXEQ];
     extrapolate_hold_mixture(h, ghost, 2.0, interior, tmp);
     for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
     if (layer > 1) {
       extrapolate_hold_mixture(h, ghost, (double)layer, interior, tmp);
       for (int e = 0; e < neq; ++e) ghost[e] = tmp[e];
+      if (rans) {
+        const double gv[3] = {ghost[imx], ghost[imy], ghost[imz]};
+        apply_farfield_turb(h, ghost, gv, bc->turbulenceIntensity, bc->eddyViscosityRatio);
+      }
     }
   } else if (bcType == AITHER_BC_PRESSURE_OUTLET) { /* ref: :604-664 */
     const aither_bc_state *bc = bc_data(h, tag);
@@ -849,7 +893,7 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
                                    : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
             double ghost[MAXEQ];
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]), bcType,
-                        fa, st, sf->tag, layer, 0.0, ghost);
+                        fa, st, sf->tag, layer, 0.0, 0.0, ghost);
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -892,6 +936,8 @@ static void face_states(const orc_level *h, const orc_block *b, int d, int i,
 }
 
 /* ref: src/procBlock.cpp:384-491, :522-629, :660-767 (CalcInvFluxI/J/K) */
+static double turb_inv_cell_spec_rad(const orc_level *h, const double *s,
+                                     const double *fL, const double *fR);
 static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
   const int neq = h->neq;
   const int ni = b->ni + (d == 0), nj = b->nj + (d == 1), nk = b->nk + (d == 2);
@@ -922,11 +968,17 @@ static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
           const double sr = inv_cell_spec_rad(
               h, b->state + neq * cidx(b, ii, jj, kk), area, fA + 4 * f1);
           double *sp = b->specRad + 2 * pidx(b, ii, jj, kk);
+          /* turbModel::InviscidCellSpecRad; ref: src/procBlock.cpp:473-478 */
+          const double tsr =
+              h->nt > 0 ? turb_inv_cell_spec_rad(h, b->state + neq * cidx(b, ii, jj, kk),
+                                                 area, fA + 4 * f1)
+                        : 0.0;
           sp[0] += sr;
-          sp[1] += 0.0;
+          sp[1] += tsr;
           if (!h->cfg.isBlockMatrix) {
             double *a = b->a + h->asz * pidx(b, ii, jj, kk);
             a[0] += sr;
+            if (h->nt > 0) a[1] += tsr;
           }
         }
       }
@@ -1069,10 +1121,10 @@ static void assign_ghost_edges(orc_level *h, orc_block *b, int viscous) {
              * never extended by this branch pair -- only the both-viscousWall
              * averaging below applies */
             if (bc2 == AITHER_BC_SLIP_WALL && bc3 != AITHER_BC_SLIP_WALL) {
-              ghost_state(h, from2, bc2, fArea2, surf2, s2->tag, layer2, wDist2, ghost);
+              ghost_state(h, from2, bc2, fArea2, surf2, s2->tag, layer2, wDist2, 0.0, ghost);
               memcpy(dst, ghost, sizeof(double) * neq);
             } else if (bc2 != AITHER_BC_SLIP_WALL && bc3 == AITHER_BC_SLIP_WALL) {
-              ghost_state(h, from3, bc3, fArea3, surf3, s3->tag, layer3, wDist3, ghost);
+              ghost_state(h, from3, bc3, fArea3, surf3, s3->tag, layer3, wDist3, 0.0, ghost);
               memcpy(dst, ghost, sizeof(double) * neq);
             } else if (!viscous || (bc2 == AITHER_BC_VISCOUS_WALL &&
                                     bc3 == AITHER_BC_VISCOUS_WALL)) {
@@ -1133,9 +1185,13 @@ static void assign_viscous_ghosts(orc_level *h, orc_block *b) {
                         : (d3 == 1 ? b->fAJ + 4 * fidxJ(b, cf[0], cf[1], cf[2])
                                    : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
             const double wd = b->wallDist ? b->wallDist[cidx(b, ca[0], ca[1], ca[2])] : 0.0;
+            /* nu at the wall-adjacent cell from the stored (previous evaluation's)
+             * viscosity; ref: src/procBlock.cpp:2814-2822 */
+            const long ac = cidx(b, ca[0], ca[1], ca[2]);
+            const double nuW = b->viscosity[ac] / rho_of(h, b->state + neq * ac);
             double ghost[MAXEQ];
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]),
-                        AITHER_BC_VISCOUS_WALL, fa, st, sf->tag, layer, wd, ghost);
+                        AITHER_BC_VISCOUS_WALL, fa, st, sf->tag, layer, wd, nuW, ghost);
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -1160,7 +1216,8 @@ static const double *farea(const orc_block *b, int d, int i, int j, int k) {
  * centred on face (i,j,k) of direction d; ref: src/procBlock.cpp:5173-5303
  * (I), :5378-5508 (J), :5584-5714 (K); src/utility.cpp:59-175 */
 static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
-                           int j, int k, double vg[9], double tg[3]) {
+                           int j, int k, double vg[9], double tg[3],
+                           double kg[3], double wg[3]) {
   const int ns = h->ns, neq = h->neq;
   const int e3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   const int *ed = e3[d];
@@ -1186,11 +1243,15 @@ static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
   }
   const double vol = 0.5 * (b->vol[cidx(b, i - ed[0], j - ed[1], k - ed[2])] +
                             b->vol[cidx(b, i, j, k)]);
-  /* values on the faces of the control volume: 3 velocity components + T */
-  double vl[3][4], vu[3][4];
+  /* values on the faces of the control volume: 3 velocity components + T
+   * (+ k, omega for RANS; ref: src/procBlock.cpp:5305-5352) */
+  double vl[3][6], vu[3][6];
+  const int nval = h->nt > 0 ? 6 : 4;
   const long cLo = cidx(b, i - ed[0], j - ed[1], k - ed[2]), cHi = cidx(b, i, j, k);
-  for (int c = 0; c < 4; ++c) {
-#define VAL(cell) (c < 3 ? b->state[neq * (cell) + ns + c] : b->temperature[(cell)])
+  for (int c = 0; c < nval; ++c) {
+#define VAL(cell)                                                       \
+  (c < 3 ? b->state[neq * (cell) + ns + c]                              \
+         : (c == 3 ? b->temperature[(cell)] : b->state[neq * (cell) + ns + c]))
     for (int q = 0; q < 3; ++q) {
       if (q == d) {
         vl[q][c] = VAL(cLo);
@@ -1222,6 +1283,212 @@ static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
                      vu[2][3] * au[2][r] - vl[2][3] * al[2][r];
     tg[r] = t * invVol;
   }
+  for (int c = 4; c < nval; ++c) {
+    double *out = c == 4 ? kg : wg;
+    for (int r = 0; r < 3; ++r) {
+      const double t = vu[0][c] * au[0][r] - vl[0][c] * al[0][r] +
+                       vu[1][c] * au[1][r] - vl[1][c] * al[1][r] +
+                       vu[2][c] * au[2][r] - vl[2][c] * al[2][r];
+      out[r] = t * invVol;
+    }
+  }
+  if (nval == 4) {
+    for (int r = 0; r < 3; ++r) kg[r] = wg[r] = 0.0;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* turbulence models: k-omega Wilcox 2006 and Menter SST 2003                 */
+/* constants: include/turbulence.hpp:391-398 (Wilcox), :489-501 (SST) */
+#define KW_GAMMA 0.52
+#define KW_BETASTAR 0.09
+#define KW_SIGMA 0.5
+#define KW_SIGMASTAR 0.6
+#define KW_SIGMAD0 0.125
+#define KW_BETA0 0.0708
+#define KW_CLIM 0.875
+#define SST_BETASTAR 0.09
+#define SST_SIGMAK1 0.85
+#define SST_SIGMAK2 1.0
+#define SST_SIGMAW1 0.5
+#define SST_SIGMAW2 0.856
+#define SST_BETA1 0.075
+#define SST_BETA2 0.0828
+#define SST_GAMMA1 (5.0 / 9.0)
+#define SST_GAMMA2 0.44
+#define SST_A1 0.31
+#define SST_KPROD2DEST 10.0
+static int is_sst(const orc_level *h) { return h->cfg.turbModel == AITHER_TURB_SST; }
+static int is_rans(const orc_level *h) { return h->nt > 0; }
+/* ref: include/turbulence.hpp:70 (0.9), :462 (Wilcox 8/9), :578 (SST 0.9) */
+static double turb_prandtl(const orc_level *h) {
+  return h->cfg.turbModel == AITHER_TURB_KW_WILCOX ? 8.0 / 9.0 : 0.9;
+}
+static double blended(double c1, double c2, double f1) { /* turbulence.cpp:592-595 */
+  return f1 * c1 + (1.0 - f1) * c2;
+}
+static double sigma_k(const orc_level *h, double f1) { /* turbulence.hpp:476,599 */
+  return is_sst(h) ? blended(SST_SIGMAK1, SST_SIGMAK2, f1) : KW_SIGMASTAR;
+}
+static double sigma_w(const orc_level *h, double f1) { /* turbulence.hpp:477,602 */
+  return is_sst(h) ? blended(SST_SIGMAW1, SST_SIGMAW2, f1) : KW_SIGMA;
+}
+static double wall_beta(const orc_level *h) { /* turbulence.hpp:463,577 */
+  return is_sst(h) ? SST_BETA1 : KW_BETA0;
+}
+static double tke_of(const orc_level *h, const double *s) { return s[h->ns + 4]; }
+static double omega_of(const orc_level *h, const double *s) { return s[h->ns + 5]; }
+/* ref: src/turbulence.cpp:38-40 */
+static double eddy_visc_no_lim(const orc_level *h, const double *s) {
+  return rho_of(h, s) * tke_of(h, s) / omega_of(h, s);
+}
+/* primitive::LimitTurb; ref: src/primitive.cpp:100-106, turbulence.hpp:72-73 */
+static void limit_turb(const orc_level *h, double *s) {
+  for (int tt = 0; tt < h->nt; ++tt)
+    s[h->ns + 4 + tt] = s[h->ns + 4 + tt] > 1.0e-20 ? s[h->ns + 4 + tt] : 1.0e-20;
+}
+static double ddot_trans(const double a[9], const double b[9]) {
+  /* tensor::DoubleDotTrans: sum of the elementwise product, flat order;
+   * ref: include/tensor.hpp:353-356 */
+  double sum = 0.0;
+  for (int q = 0; q < 9; ++q) sum += a[q] * b[q];
+  return sum;
+}
+static double dot3(const double a[3], const double b[3]) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+/* SST cross diffusion; ref: include/turbulence.hpp:528-537 */
+static double sst_cdkw(const orc_level *h, const double *s, const double kg[3],
+                       const double wg[3]) {
+  const double v = 2.0 * rho_of(h, s) * SST_SIGMAW2 / omega_of(h, s) * dot3(kg, wg);
+  return v > 1.0e-10 ? v : 1.0e-10;
+}
+/* turbModel::EddyViscAndBlending; ref: src/turbulence.cpp:405-423 (Wilcox,
+ * OmegaTilda :329-342), :663-684 (SST, EddyVisc :570-580, F1/F2 :582-590,
+ * Alpha1-3 :597-615) */
+static void eddy_visc_and_blending(const orc_level *h, const double *s,
+                                   const double vg[9], const double kg[3],
+                                   const double wg[3], double mu, double wallDist,
+                                   double *mut, double *f1, double *f2) {
+  const double scaling = h->cfg.nondimScaling;
+  const double rho = rho_of(h, s), tke = tke_of(h, s), omg = omega_of(h, s);
+  const double trace = vg[0] + vg[4] + vg[8];
+  if (!is_sst(h)) {
+    *f1 = 1.0;
+    *f2 = 0.0;
+    double sHat[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        sHat[3 * r + c] = 0.5 * (vg[3 * r + c] + vg[3 * c + r]) -
+                          1.0 / 3.0 * trace * (r == c ? 1.0 : 0.0);
+    const double lim = scaling * KW_CLIM * sqrt(2.0 * ddot_trans(sHat, sHat) / KW_BETASTAR);
+    const double omegaTilda = omg > lim ? omg : lim;
+    *mut = rho * tke / omegaTilda;
+    return;
+  }
+  const double dE = wallDist + ORC_EPS;
+  const double alpha1 = scaling * sqrt(tke) / (SST_BETASTAR * omg * dE);
+  const double alpha2 = scaling * scaling * 500.0 * mu / (dE * dE * rho * omg);
+  const double cdkw = sst_cdkw(h, s, kg, wg);
+  const double alpha3 = 4.0 * rho * SST_SIGMAW2 * tke / (cdkw * dE * dE);
+  const double m12 = alpha1 > alpha2 ? alpha1 : alpha2;
+  const double arg1 = m12 < alpha3 ? m12 : alpha3;
+  *f1 = tanh(pow(arg1, 4.0));
+  const double arg2 = 2.0 * alpha1 > alpha2 ? 2.0 * alpha1 : alpha2;
+  *f2 = tanh(arg2 * arg2);
+  double sr[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) sr[3 * r + c] = 0.5 * (vg[3 * r + c] + vg[3 * c + r]);
+  const double meanStrainRate = sqrt(2.0 * ddot_trans(sr, sr));
+  const double d1 = SST_A1 * omg, d2 = scaling * meanStrainRate * (*f2);
+  *mut = rho * SST_A1 * tke / (d1 > d2 ? d1 : d2);
+}
+/* turbulence-equation spectral radii; ref: src/turbulence.cpp:152-171
+ * (inviscid), :500-527 (Wilcox viscous: unlimited eddy viscosity), :783-808 (SST) */
+static double turb_inv_cell_spec_rad(const orc_level *h, const double *s,
+                                     const double *fL, const double *fR) {
+  double na[3];
+  for (int q = 0; q < 3; ++q) na[q] = 0.5 * (fL[q] + fR[q]);
+  const double mag = sqrt(na[0] * na[0] + na[1] * na[1] + na[2] * na[2]);
+  for (int q = 0; q < 3; ++q) na[q] /= mag;
+  const double fMag = 0.5 * (fL[3] + fR[3]);
+  return fabs(dot3(s + h->ns, na)) * fMag;
+}
+static double turb_inv_face_spec_rad(const orc_level *h, const double *s,
+                                     const double *fA, int positive) {
+  const double velNorm = dot3(s + h->ns, fA);
+  return positive ? 0.5 * fA[3] * fabs(velNorm + fabs(velNorm))
+                  : 0.5 * fA[3] * fabs(velNorm - fabs(velNorm));
+}
+static double turb_visc_spec_rad(const orc_level *h, const double *s, double length,
+                                 double mu, double mut, double f1) {
+  const double mt = is_sst(h) ? mut : eddy_visc_no_lim(h, s);
+  return h->cfg.nondimScaling * length / rho_of(h, s) * (mu + sigma_k(h, f1) * mt);
+}
+/* turbModel::SrcSpecRad; ref: src/turbulence.cpp:438-443, :699-704 */
+static double turb_src_spec_rad(const orc_level *h, const double *s, double vol) {
+  const double invScaling = 1.0 / h->cfg.nondimScaling;
+  return -2.0 * KW_BETASTAR * omega_of(h, s) * vol * invScaling;
+}
+/* turbModel::CalcTurbSrc; ref: src/turbulence.cpp:344-384 (Wilcox; Beta/FBeta/Xw
+ * :291-319), :617-661 (SST); BoussinesqReynoldsStress :55-70 */
+static void calc_turb_src(const orc_level *h, const double *s, const double vg[9],
+                          const double kg[3], const double wg[3], double mut,
+                          double f1, double src[2]) {
+  const double scaling = h->cfg.nondimScaling, invScaling = 1.0 / scaling;
+  const double rho = rho_of(h, s), tke = tke_of(h, s), omg = omega_of(h, s);
+  const double trace = vg[0] + vg[4] + vg[8];
+  /* tau = lambda tr(G) I + mut (G + G^T) - 2/3 rho k I; lambda = -2/3 mut */
+  const double lambda = 0.0 - (2.0 / 3.0) * mut;
+  double tau[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double I = r == c ? 1.0 : 0.0;
+      tau[3 * r + c] = lambda * trace * I + mut * (vg[3 * r + c] + vg[3 * c + r]) -
+                       2.0 / 3.0 * rho * tke * I;
+    }
+  const double prodRaw = scaling * ddot_trans(tau, vg);
+  if (!is_sst(h)) {
+    const double tkeDest = invScaling * KW_BETASTAR * (rho * tke * omg * 1.0);
+    /* Xw = |Omega_ij Omega_jk S^_ki / (betaStar w)^3| scaling^3 */
+    double vort[9], ski[9], vv[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        vort[3 * r + c] = 0.5 * (vg[3 * r + c] - vg[3 * c + r]);
+        ski[3 * r + c] =
+            0.5 * (vg[3 * r + c] + vg[3 * c + r] - trace * (r == c ? 1.0 : 0.0));
+      }
+    for (int q = 0; q < 9; ++q) vv[q] = 0.0;
+    for (int cc = 0; cc < 3; ++cc) /* tensor::MatMult, include/tensor.hpp:272-282 */
+      for (int rr = 0; rr < 3; ++rr)
+        for (int ii = 0; ii < 3; ++ii) vv[3 * rr + ii] += vort[3 * rr + cc] * vort[3 * cc + ii];
+    const double xw = fabs(ddot_trans(vv, ski) / pow(KW_BETASTAR * omg, 3.0)) *
+                      pow(scaling, 3.0);
+    const double beta = KW_BETA0 * ((1.0 + 85.0 * xw) / (1.0 + 100.0 * xw));
+    const double omgDest = invScaling * beta * (rho * omg * omg);
+    double tkeProd = prodRaw > 0.0 ? prodRaw : 0.0;
+    double omgProd = KW_GAMMA * omg / tke * tkeProd;
+    omgProd = omgProd > 0.0 ? omgProd : 0.0;
+    const double kw = dot3(kg, wg);
+    const double sigmaD = kw <= 0.0 ? 0.0 : KW_SIGMAD0;
+    const double omgCd = scaling * sigmaD * (rho / omg * kw);
+    src[0] = tkeProd - tkeDest;
+    src[1] = omgProd - omgDest + omgCd;
+    return;
+  }
+  const double cdkw = sst_cdkw(h, s, kg, wg);
+  const double gamma = blended(SST_GAMMA1, SST_GAMMA2, f1);
+  const double beta = blended(SST_BETA1, SST_BETA2, f1);
+  const double tkeDest = invScaling * SST_BETASTAR * (rho * tke * omg * 1.0);
+  const double omgDest = invScaling * beta * (rho * omg * omg);
+  const double lim = SST_KPROD2DEST * tkeDest;
+  double tkeProd = prodRaw < lim ? prodRaw : lim;
+  tkeProd = tkeProd > 0.0 ? tkeProd : 0.0;
+  double omgProd = gamma * rho / mut * tkeProd;
+  omgProd = omgProd > 0.0 ? omgProd : 0.0;
+  const double omgCd = scaling * (1.0 - f1) * cdkw;
+  src[0] = tkeProd - tkeDest;
+  src[1] = omgProd - omgDest + omgCd;
 }
 /* ref: src/utility.cpp:425-437 (TauNormal), src/transport.cpp:173-176 (Lambda) */
 static void tau_normal(const double vg[9], const double n[3], double mu,
@@ -1234,20 +1501,22 @@ static void tau_normal(const double vg[9], const double n[3], double mu,
     tau[r] = lambda * trace * n[r] + (mu + mut) * mm;
   }
 }
-/* ref: src/procBlock.cpp:1233-1497 (CalcViscFluxI; J, K alike), laminar */
+/* ref: src/procBlock.cpp:1233-1497 (CalcViscFluxI; J, K alike); low-Re walls */
 static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
   const int neq = h->neq, ns = h->ns;
   const int nd[3] = {b->ni, b->nj, b->nk};
   const int di = d == 0, dj = d == 1, dk = d == 2;
   const double *cw = d == 0 ? b->cwI : (d == 1 ? b->cwJ : b->cwK);
   const double viscCoeff = h->cfg.viscousCFLCoeff;
+  const double sixth = 1.0 / 6.0;
+  const int rans = is_rans(h);
   for (int kk = 0; kk < b->nk + dk; ++kk)
     for (int jj = 0; jj < b->nj + dj; ++jj)
       for (int ii = 0; ii < b->ni + di; ++ii) {
         const int fi = d == 0 ? ii : (d == 1 ? jj : kk);
-        double vg[9], tg[3];
-        face_gradients(h, b, d, ii, jj, kk, vg, tg);
-        double state[MAXEQ], mu;
+        double vg[9], tg[3], kg[3], wg[3];
+        face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg);
+        double state[MAXEQ], mu, wDist = 0.0;
 #define CL(o) cidx(b, ii + (o)*di, jj + (o)*dj, kk + (o)*dk)
         if (h->cfg.viscRecon == 0) { /* central; ref: :1305-1321 */
           const double w[2] = {cw[CL(-1)], cw[CL(0)]};
@@ -1256,7 +1525,8 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           for (int e = 0; e < neq; ++e)
             state[e] = c[0] * b->state[neq * CL(0) + e] + c[1] * b->state[neq * CL(-1) + e];
           mu = c[0] * b->viscosity[CL(0)] + c[1] * b->viscosity[CL(-1)];
-        } else { /* centralFourth; ref: :1323-1346 */
+          if (b->wallDist) wDist = c[0] * b->wallDist[CL(0)] + c[1] * b->wallDist[CL(-1)];
+        } else { /* centralFourth; ref: :1323-1346, include/reconstruction.hpp:359-379 */
           const double w[4] = {cw[CL(-2)], cw[CL(-1)], cw[CL(0)], cw[CL(1)]};
           double c[4];
           lagrange_coeff(w, 3, 1, 1, c);
@@ -1265,11 +1535,22 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
                        c[2] * b->state[neq * CL(0) + e] + c[3] * b->state[neq * CL(1) + e];
           mu = c[0] * b->viscosity[CL(-2)] + c[1] * b->viscosity[CL(-1)] +
                c[2] * b->viscosity[CL(0)] + c[3] * b->viscosity[CL(1)];
+          const double w2[2] = {w[1], w[2]};
+          double c2[2];
+          lagrange_coeff(w2, 1, 0, 0, c2);
+          /* turbulence variables stay second order (reconstruction.hpp:366-376) */
+          for (int e = ns + 4; e < neq; ++e)
+            state[e] = c2[0] * b->state[neq * CL(0) + e] + c2[1] * b->state[neq * CL(-1) + e];
+          if (b->wallDist) wDist = c2[0] * b->wallDist[CL(0)] + c2[1] * b->wallDist[CL(-1)];
         }
-        /* viscousFlux::CalcFlux; ref: src/viscousFlux.cpp:58-135 */
+        limit_turb(h, state);
+        if (wDist < 0.0 && wDist > -1.0e-10) wDist = 0.0; /* WALL_DIST_NEG_TOL, :1349-1351 */
+        double mut = 0.0, f1 = 0.0, f2 = 0.0;
+        if (rans) eddy_visc_and_blending(h, state, vg, kg, wg, mu, wDist, &mut, &f1, &f2);
+        /* viscousFlux::CalcFlux / CalcWallFlux; ref: src/viscousFlux.cpp:58-135,137-196 */
         const double *fa = farea(b, d, ii, jj, kk);
         const double mus = h->cfg.nondimScaling * mu;
-        const double muts = h->cfg.nondimScaling * 0.0;
+        const double muts = h->cfg.nondimScaling * mut;
         double tau[3], flux[MAXEQ];
         for (int e = 0; e < neq; ++e) flux[e] = 0.0;
         tau_normal(vg, fa, mus, muts, tau);
@@ -1278,17 +1559,50 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         flux[ns + 2] = tau[2];
         const double t = temperature_of(h, state);
         const double kcond = eff_conductivity(h, t);
-        const double kt = 0.0;
+        double kt = 0.0;
+        if (rans) { /* sutherland::TurbConductivity: mut cp / Prt, include/transport.hpp:132-137 */
+          double mf[AITHER_MAX_SPECIES];
+          mass_fractions(h, state, mf);
+          kt = muts * cp_mix(h, mf) / turb_prandtl(h);
+        }
         flux[ns + 3] = (tau[0] * state[ns] + tau[1] * state[ns + 1] + tau[2] * state[ns + 2]) +
                        (kcond + kt) * (tg[0] * fa[0] + tg[1] * fa[1] + tg[2] * fa[2]) + 0.0;
+        if (rans) {
+          const double mutt = is_sst(h) ? muts
+                                        : h->cfg.nondimScaling * eddy_visc_no_lim(h, state);
+          flux[ns + 4] = (mus + sigma_k(h, f1) * mutt) * dot3(kg, fa);
+          flux[ns + 5] = (mus + sigma_w(h, f1) * mutt) * dot3(wg, fa);
+        }
         /* residual: opposite sign to the inviscid flux; ref: :1392-1429 */
         if (fi > 0) {
           double *r = b->residual + neq * pidx(b, ii - di, jj - dj, kk - dk);
           for (int e = 0; e < neq; ++e) r[e] -= flux[e] * fa[3];
+          if (rans) {
+            const long c = CL(-1), pp = pidx(b, ii - di, jj - dj, kk - dk);
+            for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
+            b->eddyVisc[c] += sixth * mut;
+            for (int q = 0; q < 3; ++q) {
+              b->tkeGrad[3 * pp + q] += sixth * kg[q];
+              b->omegaGrad[3 * pp + q] += sixth * wg[q];
+            }
+            b->f1[c] += sixth * f1;
+            b->f2[c] += sixth * f2;
+          }
         }
         if (fi < nd[d]) {
           double *r = b->residual + neq * pidx(b, ii, jj, kk);
           for (int e = 0; e < neq; ++e) r[e] += flux[e] * fa[3];
+          if (rans) {
+            const long c = CL(0), pp = pidx(b, ii, jj, kk);
+            for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
+            b->eddyVisc[c] += sixth * mut;
+            for (int q = 0; q < 3; ++q) {
+              b->tkeGrad[3 * pp + q] += sixth * kg[q];
+              b->omegaGrad[3 * pp + q] += sixth * wg[q];
+            }
+            b->f1[c] += sixth * f1;
+            b->f2[c] += sixth * f2;
+          }
           /* ViscCellSpectralRadius; ref: include/spectralRadius.hpp:94-124 */
           const double *s = b->state + neq * CL(0);
           const double *fu = farea(b, d, ii + di, jj + dj, kk + dk);
@@ -1298,14 +1612,46 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           const double a43 = 4.0 / (3.0 * rho), gr = gam / rho;
           const double maxTerm = a43 > gr ? a43 : gr;
           const double viscTerm =
-              h->cfg.nondimScaling * (b->viscosity[CL(0)] / prandtl_of(gam) + 0.0 / 0.9);
+              h->cfg.nondimScaling * (b->viscosity[CL(0)] / prandtl_of(gam) + mut / turb_prandtl(h));
           const double vsr = maxTerm * viscTerm * fMag * fMag / b->vol[CL(0)];
+          /* turbModel::ViscCellSpecRad; ref: src/turbulence.cpp:500-511,783-794 */
+          const double tvsr =
+              rans ? turb_visc_spec_rad(h, s, fMag * fMag / b->vol[CL(0)], b->viscosity[CL(0)],
+                                        mut, f1)
+                   : 0.0;
           double *sp = b->specRad + 2 * pidx(b, ii, jj, kk);
           sp[0] += vsr * viscCoeff;
-          sp[1] += 0.0 * viscCoeff;
-          if (!h->cfg.isBlockMatrix) b->a[h->asz * pidx(b, ii, jj, kk)] += 2.0 * vsr;
+          sp[1] += tvsr * viscCoeff;
+          if (!h->cfg.isBlockMatrix) {
+            double *a = b->a + h->asz * pidx(b, ii, jj, kk);
+            a[0] += 2.0 * vsr;
+            if (rans) a[1] += 2.0 * tvsr;
+          }
         }
 #undef CL
+      }
+}
+
+/* procBlock::CalcSrcTerms (RANS part); ref: src/procBlock.cpp:5956-6025,
+ * src/source.cpp:64-82 */
+static void calc_src_terms(orc_level *h, orc_block *b) {
+  const int neq = h->neq, ns = h->ns;
+  for (int kk = 0; kk < b->nk; ++kk)
+    for (int jj = 0; jj < b->nj; ++jj)
+      for (int ii = 0; ii < b->ni; ++ii) {
+        const long c = cidx(b, ii, jj, kk), pp = pidx(b, ii, jj, kk);
+        const double *s = b->state + neq * c;
+        double src[2];
+        calc_turb_src(h, s, b->velGrad + 9 * c, b->tkeGrad + 3 * pp, b->omegaGrad + 3 * pp,
+                      b->eddyVisc[c], b->f1[c], src);
+        const double turbSpecRad = turb_src_spec_rad(h, s, b->vol[c]);
+        b->specRad[2 * pp + 1] -= turbSpecRad;
+        if (!h->cfg.isBlockMatrix) b->a[h->asz * pp + 1] -= turbSpecRad;
+        double *r = b->residual + neq * pp;
+        for (int e = 0; e < neq; ++e) {
+          const double sv = e >= ns + 4 ? src[e - ns - 4] : 0.0;
+          r[e] -= sv * b->vol[c];
+        }
       }
 }
 
@@ -1458,14 +1804,23 @@ static void insert_slice(const orc_block *b, double *arr, int nc,
  * connection in list order (src/gridLevel.cpp:297-312, src/utility.cpp:400-423);
  * which = 0: state, 1: implicit update x */
 static void swap_connections(orc_level *h, int which) {
-  const int nc = h->neq;
+  /* 2..5: eddy viscosity, f1, f2, velocity gradient
+   * (ref: src/procBlock.cpp:3064-3085, src/gridLevel.cpp:321-370) */
+  const int nc = which <= 1 ? h->neq : (which == 5 ? 9 : 1);
   for (int c = 0; c < h->nconn; ++c) {
     orc_conn o;
     conn_load(&h->conn[c], &o);
     orc_block *b1 = &h->blk[h->conn[c].localBlock[0]];
     orc_block *b2 = &h->blk[h->conn[c].localBlock[1]];
-    double *a1 = which == 0 ? b1->state : b1->x;
-    double *a2 = which == 0 ? b2->state : b2->x;
+#define SWAP_ARR(bp)                                                       \
+  (which == 0 ? (bp)->state                                                \
+              : (which == 1 ? (bp)->x                                      \
+                            : (which == 2 ? (bp)->eddyVisc                 \
+                                          : (which == 3 ? (bp)->f1         \
+                                                        : (which == 4 ? (bp)->f2 : (bp)->velGrad)))))
+    double *a1 = SWAP_ARR(b1);
+    double *a2 = SWAP_ARR(b2);
+#undef SWAP_ARR
     int lo1[3], hi1[3], lo2[3], hi2[3], sn1[3], sn2[3];
     conn_slice_indices(&o, 0, b1->g, lo1, hi1);
     conn_slice_indices(&o, 1, b2->g, lo2, hi2);
@@ -1495,8 +1850,17 @@ void orc_calc_residual(orc_level *h) {
   for (int bb = 0; bb < h->nblk; ++bb) {
     orc_block *b = &h->blk[bb];
     const long nc = (long)b->ni * b->nj * b->nk;
+    const long np = (long)b->NI * b->NJ * b->NK;
     memset(b->residual, 0, sizeof(double) * nc * h->neq);
     memset(b->specRad, 0, sizeof(double) * nc * 2);
+    if (is_rans(h)) { /* ResetGradients, ResetTurbVars; ref: src/procBlock.cpp:961-981 */
+      memset(b->velGrad, 0, sizeof(double) * np * 9);
+      memset(b->tkeGrad, 0, sizeof(double) * nc * 3);
+      memset(b->omegaGrad, 0, sizeof(double) * nc * 3);
+      memset(b->eddyVisc, 0, sizeof(double) * np);
+      memset(b->f1, 0, sizeof(double) * np);
+      memset(b->f2, 0, sizeof(double) * np);
+    }
     calc_inv_flux(h, b, 0);
     calc_inv_flux(h, b, 1);
     calc_inv_flux(h, b, 2);
@@ -1509,6 +1873,15 @@ void orc_calc_residual(orc_level *h) {
     } else {
       update_aux(h, b);
     }
+  }
+  if (is_rans(h)) {
+    /* SwapEddyViscAndGradients, SwapTurbVars, then the source terms;
+     * ref: src/gridLevel.cpp:386-399 */
+    swap_connections(h, 5);
+    swap_connections(h, 2);
+    swap_connections(h, 3);
+    swap_connections(h, 4);
+    for (int bb = 0; bb < h->nblk; ++bb) calc_src_terms(h, &h->blk[bb]);
   }
 }
 
@@ -1609,10 +1982,11 @@ void orc_initialize_matrix_update(orc_level *h) {
   }
 }
 
-/* ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal), inviscid */
+/* ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal) */
 static void offdiag_scalar(const orc_level *h, const double *state,
                            const double *du, const double *fArea, int positive,
-                           double mu, double dist, double *out) {
+                           double mu, double mut, double f1, double dist,
+                           double *out) {
   const int neq = h->neq;
   double su[MAXEQ], fo[MAXEQ], fn[MAXEQ];
   update_prim_with_cons(h, state, du, su);
@@ -1626,13 +2000,19 @@ static void offdiag_scalar(const orc_level *h, const double *state,
     const double a43 = 4.0 / (3.0 * rho), gr = gam / rho;
     const double maxTerm = a43 > gr ? a43 : gr;
     const double viscTerm =
-        h->cfg.nondimScaling * (mu / prandtl_of(gam) + 0.0 / 0.9);
+        h->cfg.nondimScaling * (mu / prandtl_of(gam) + mut / turb_prandtl(h));
     sr += fArea[3] / dist * maxTerm * viscTerm;
+  }
+  /* turbModel::FaceSpectralRadius; ref: include/turbulence.hpp:308-329 */
+  double tsr = 0.0;
+  if (h->nt > 0) {
+    tsr = turb_inv_face_spec_rad(h, state, fArea, positive);
+    tsr += turb_visc_spec_rad(h, state, fArea[3] / dist, mu, mut, f1);
   }
   for (int e = 0; e < neq; ++e) {
     double fc = 0.5 * fArea[3] * (fn[e] - fo[e]);
     if (e >= h->ns + 4) fc = 0.0;
-    const double srd = (e < h->ns + 4 ? sr : 0.0) * du[e];
+    const double srd = (e < h->ns + 4 ? sr : tsr) * du[e];
     out[e] = positive ? fc + srd : fc - srd;
   }
 }
@@ -1682,21 +2062,21 @@ static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
   if (is_physical(b, ii - 1, jj, kk) || bc_is_connection(b, ii, jj, kk, 1)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii - 1, jj, kk),
                    x + neq * cidx(b, ii - 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, visc_at(h, b, ii - 1, jj, kk),
+                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, visc_at(h, b, ii - 1, jj, kk), b->eddyVisc[cidx(b, ii - 1, jj, kk)], b->f1[cidx(b, ii - 1, jj, kk)],
                    proj_c2c_dist(b, 0, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj - 1, kk) || bc_is_connection(b, ii, jj, kk, 3)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj - 1, kk),
                    x + neq * cidx(b, ii, jj - 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, visc_at(h, b, ii, jj - 1, kk),
+                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, visc_at(h, b, ii, jj - 1, kk), b->eddyVisc[cidx(b, ii, jj - 1, kk)], b->f1[cidx(b, ii, jj - 1, kk)],
                    proj_c2c_dist(b, 1, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk - 1) || bc_is_connection(b, ii, jj, kk, 5)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk - 1),
                    x + neq * cidx(b, ii, jj, kk - 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, visc_at(h, b, ii, jj, kk - 1),
+                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, visc_at(h, b, ii, jj, kk - 1), b->eddyVisc[cidx(b, ii, jj, kk - 1)], b->f1[cidx(b, ii, jj, kk - 1)],
                    proj_c2c_dist(b, 2, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
@@ -1710,21 +2090,21 @@ static void implicit_upper(const orc_level *h, const orc_block *b, int ii,
   if (is_physical(b, ii + 1, jj, kk) || bc_is_connection(b, ii + 1, jj, kk, 2)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii + 1, jj, kk),
                    x + neq * cidx(b, ii + 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, visc_at(h, b, ii + 1, jj, kk),
+                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, visc_at(h, b, ii + 1, jj, kk), b->eddyVisc[cidx(b, ii + 1, jj, kk)], b->f1[cidx(b, ii + 1, jj, kk)],
                    proj_c2c_dist(b, 0, ii + 1, jj, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj + 1, kk) || bc_is_connection(b, ii, jj + 1, kk, 4)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj + 1, kk),
                    x + neq * cidx(b, ii, jj + 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, visc_at(h, b, ii, jj + 1, kk),
+                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, visc_at(h, b, ii, jj + 1, kk), b->eddyVisc[cidx(b, ii, jj + 1, kk)], b->f1[cidx(b, ii, jj + 1, kk)],
                    proj_c2c_dist(b, 1, ii, jj + 1, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk + 1) || bc_is_connection(b, ii, jj, kk + 1, 6)) {
     offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk + 1),
                    x + neq * cidx(b, ii, jj, kk + 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, visc_at(h, b, ii, jj, kk + 1),
+                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, visc_at(h, b, ii, jj, kk + 1), b->eddyVisc[cidx(b, ii, jj, kk + 1)], b->f1[cidx(b, ii, jj, kk + 1)],
                    proj_c2c_dist(b, 2, ii, jj, kk + 1), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
@@ -1925,6 +2305,19 @@ static int cmp_plane(const void *a, const void *b) {
   return x[0] - y[0];
 }
 
+/* gridLevel::AuxillaryAndWidths -> UpdateAuxillaryVariables(phys, false): temperature
+ * and viscosity of the physical cells before the first iteration (the viscous-wall
+ * omega BC reads the stored viscosity); ref: src/gridLevel.cpp:433-438 */
+static void init_aux(orc_level *h, orc_block *b) {
+  for (int kk = 0; kk < b->nk; ++kk)
+    for (int jj = 0; jj < b->nj; ++jj)
+      for (int ii = 0; ii < b->ni; ++ii) {
+        const long c = cidx(b, ii, jj, kk);
+        b->temperature[c] = temperature_of(h, b->state + h->neq * c);
+        if (h->cfg.isViscous) b->viscosity[c] = viscosity_of(h, b->temperature[c]);
+      }
+}
+
 orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
                       const aither_block_desc *blocks, int nConnections,
                       const aither_conn *conns) {
@@ -1971,6 +2364,12 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
     b->mresid = (double *)calloc(nc * h->neq, sizeof(double));
     b->temperature = (double *)calloc(np, sizeof(double));
     b->viscosity = (double *)calloc(np, sizeof(double));
+    b->eddyVisc = (double *)calloc(np, sizeof(double));
+    b->f1 = (double *)calloc(np, sizeof(double));
+    b->f2 = (double *)calloc(np, sizeof(double));
+    b->velGrad = (double *)calloc(np * 9, sizeof(double));
+    b->tkeGrad = (double *)calloc(nc * 3, sizeof(double));
+    b->omegaGrad = (double *)calloc(nc * 3, sizeof(double));
     b->vol = d->vol;
     b->fAI = d->fAreaI;
     b->fAJ = d->fAreaJ;
@@ -1992,6 +2391,7 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
           ++q;
         }
     qsort(b->order, nc, 3 * sizeof(int), cmp_plane);
+    init_aux(h, b);
   }
   return h;
 }
@@ -2004,6 +2404,8 @@ void orc_destroy(orc_level *h) {
     free(b->dt); free(b->a); free(b->ainv); free(b->x); free(b->xold);
     free(b->consN); free(b->consNm1); free(b->mresid); free(b->temperature);
     free(b->viscosity); free(b->order);
+    free(b->eddyVisc); free(b->f1); free(b->f2); free(b->velGrad);
+    free(b->tkeGrad); free(b->omegaGrad);
   }
   free(h->blk);
   free(h->conn);
@@ -2027,6 +2429,12 @@ long long orc_field_size(orc_level *h, int blk, int field) {
     case AITHER_FIELD_TEMPERATURE: return np;
     case AITHER_FIELD_VISCOSITY: return np;
     case AITHER_FIELD_CONS_NM1: return nc * h->neq;
+    case AITHER_FIELD_EDDY_VISCOSITY: return np;
+    case AITHER_FIELD_F1: return np;
+    case AITHER_FIELD_F2: return np;
+    case AITHER_FIELD_VELOCITY_GRAD: return np * 9;
+    case AITHER_FIELD_TKE_GRAD: return nc * 3;
+    case AITHER_FIELD_OMEGA_GRAD: return nc * 3;
   }
   return 0;
 }
@@ -2047,6 +2455,12 @@ void orc_get_field(orc_level *h, int blk, int field, double *dst) {
     case AITHER_FIELD_TEMPERATURE: src = b->temperature; break;
     case AITHER_FIELD_VISCOSITY: src = b->viscosity; break;
     case AITHER_FIELD_CONS_NM1: src = b->consNm1; break;
+    case AITHER_FIELD_EDDY_VISCOSITY: src = b->eddyVisc; break;
+    case AITHER_FIELD_F1: src = b->f1; break;
+    case AITHER_FIELD_F2: src = b->f2; break;
+    case AITHER_FIELD_VELOCITY_GRAD: src = b->velGrad; break;
+    case AITHER_FIELD_TKE_GRAD: src = b->tkeGrad; break;
+    case AITHER_FIELD_OMEGA_GRAD: src = b->omegaGrad; break;
   }
   if (src) memcpy(dst, src, sizeof(double) * orc_field_size(h, blk, field));
 }
@@ -2054,6 +2468,7 @@ void orc_get_field(orc_level *h, int blk, int field, double *dst) {
 void orc_set_state(orc_level *h, int blk, const double *stateAoS) {
   memcpy(h->blk[blk].state, stateAoS,
          sizeof(double) * orc_field_size(h, blk, AITHER_FIELD_STATE));
+  init_aux(h, &h->blk[blk]);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -2077,12 +2492,12 @@ void orc_ghost_state(const aither_cfg *cfg, const double *interior, int bcType,
                      double *ghost) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, ghost);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, 0.0, ghost);
 }
 void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
                         const double *duNb, const double fArea[4], int positive,
                         double *out) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  offdiag_scalar(&h, stateNb, duNb, fArea, positive, 0.0, 1.0, out);
+  offdiag_scalar(&h, stateNb, duNb, fArea, positive, 0.0, 0.0, 0.0, 1.0, out);
 }

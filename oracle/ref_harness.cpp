@@ -438,6 +438,8 @@ int main(int argc, char *argv[]) {
           if (inp.IsRANS()) {
             d.field(p + "f1@" + it, lvl.Block(bb).f1_);
             d.field(p + "f2@" + it, lvl.Block(bb).f2_);
+            d.field(p + "tkeGrad@" + it, lvl.Block(bb).tkeGrad_);
+            d.field(p + "omegaGrad@" + it, lvl.Block(bb).omegaGrad_);
           }
           d.field(p + "diagRaw@" + it, lvl.solver_->a_[bb]);
         }

@@ -69,6 +69,20 @@ CASES = {
                                      "initialConditions": "<icState(tag=-1; file=ic.dat)>"}),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
+    # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,
+    # CFL 1e5, viscous wall with the omega wall BC, stagnation inlet / pressure outlet with
+    # farfield turbulence; 136x96 cells. Phases only at iteration 0: the wall omega BC reads the
+    # viscosity stored by the previous evaluation, which a restart cannot reproduce
+    "turbFlatPlate": dict(src="turbFlatPlate", iters=20, full=(0,), edits={},
+                          drop=("diagRaw@", "temperature@", "state@it0.start", "x0@")),
+    # synthetic RANS boxes (1 mm, viscous wall on j-lo): SST 2003 + DPLUR + 4th-order
+    # viscous reconstruction, and k-omega Wilcox 2006 + LU-SGS + AUSMPW+ + minmod at CFL 5
+    "box_sst": dict(synthetic=dict(ni=12, nj=10, nk=8, solver="dplur", sweeps=3, turb="sst2003",
+                                   limiter="vanAlbada", visc_recon="centralFourth", size=1e-3),
+                    iters=12, full=(0,)),
+    "box_kw": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2, flux="ausm",
+                                  limiter="minmod", cfl=5.0, turb="kOmegaWilcox2006",
+                                  size=1e-3), iters=12, full=(0,)),
 }
 
 DROP = ("nodes", "fCenterI", "fCenterJ", "fCenterK")

@@ -118,6 +118,7 @@ class OracleLevel:
         b = self.problem.blocks[blk]
         g = self.problem.cfg.numGhosts
         padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE,
-                         abi.FIELD_VISCOSITY)
+                         abi.FIELD_VISCOSITY, abi.FIELD_EDDY_VISCOSITY, abi.FIELD_F1,
+                         abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))

@@ -16,17 +16,22 @@ import oracle
 # state, src/ghostStates.cpp:574: libm's and the reference build's pow differ in the last bits and
 # the formula amplifies that to 4e-13 on subsonicCylinder; every other case is at ~1e-14.)
 TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-14, dt=1e-14, diag=1e-14, x0=1e-13,
-           x=1e-12, matrixResid=1e-10, state=1e-13, l2=1e-13)
+           x=1e-12, matrixResid=1e-10, state=1e-13, l2=1e-13, turb=1e-12)
 
 SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno",
                 # laminar Navier-Stokes: Green-Gauss face gradients, viscous fluxes, Sutherland,
                 # viscous-wall + edge ghost cells, viscous spectral radii (diagonal and faces)
-                "viscousFlatPlate", "box_visc4", "box_visc_iso"]
+                "viscousFlatPlate", "box_visc4", "box_visc_iso",
+                # RANS: k-omega Wilcox 2006 and SST 2003 (eddy viscosity, blending functions,
+                # k / omega face fluxes and source terms, turbulent spectral radii, wall omega BC)
+                "turbFlatPlate", "box_sst", "box_kw"]
 
 
 # viscousFlatPlate runs at CFL 1e4 from a uniform start: the implicit update is the solution of a
 # nearly singular system and amplifies the 1e-13 residual differences to 6e-12 in x
-CASE_TOL = {"viscousFlatPlate": dict(TOL, x=1e-10)}
+CASE_TOL = {"viscousFlatPlate": dict(TOL, x=1e-10),
+            # CFL 1e5 from a uniform start, as above
+            "turbFlatPlate": dict(TOL, x=1e-10, matrixResid=1e-9)}
 
 
 @pytest.mark.parametrize("name", SINGLE_BLOCK)
@@ -39,7 +44,8 @@ def test_oracle_phases_match_reference(name):
 @pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30),
                                         ("box_dplur", 30), ("box_lusgs_va", 20),
                                         ("box_weno", 12), ("viscousFlatPlate", 100),
-                                        ("box_visc4", 12), ("box_visc_iso", 12)])
+                                        ("box_visc4", 12), ("box_visc_iso", 12),
+                                        ("turbFlatPlate", 20), ("box_sst", 12), ("box_kw", 12)])
 def test_oracle_history_matches_reference(name, iters):
     """L2 history within 1e-9 relative (north_star bar) + the reference's regression goldens."""
     d = gc.load(name)
