@@ -208,7 +208,12 @@ int SurfaceType(const aither_surface &s) {
 
 bool Supported(const aither_cfg &c, std::string *why) {
   if (c.numSpecies != 1) { *why = "only single-species gas is built in this round"; return false; }
-  if (c.numTurb != 0 || c.isRANS) { *why = "RANS turbulence models are not built in this round"; return false; }
+  if (c.numTurb != 0 || c.isRANS) {
+    if (c.numTurb != 2 || !c.isRANS || !c.isViscous) { *why = "RANS needs numTurb = 2 and isViscous"; return false; }
+    if (c.turbModel != AITHER_TURB_KW_WILCOX && c.turbModel != AITHER_TURB_SST) {
+      *why = "turbulence model must be kOmegaWilcox2006 or sst2003"; return false;
+    }
+  }
   if (c.isViscous && c.viscRecon != 0 && c.viscRecon != 1) { *why = "unknown viscous face reconstruction"; return false; }
   if (c.isViscous && c.numGhosts < 2) { *why = "viscous fluxes need at least 2 ghost layers"; return false; }
   if (c.isBlockMatrix) { *why = "block-matrix solvers (blusgs/bdplur) are not built in this round"; return false; }
@@ -299,6 +304,13 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
       hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField);
 }
 
+template <int NS, int NT>
+void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t stream) {
+  if constexpr (NT > 0) {
+    RansCellKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1);
+  }
+}
+
 int ZeroResult(aither_gpu *h, int slot) {
   CK(cudaMemsetAsync(h->dResults + slot, 0, sizeof(IterResult), h->stream));
   return 0;
@@ -323,24 +335,27 @@ int Exchange(aither_gpu *h, int which) {
   HaloFields f;
   for (size_t bb = 0; bb < h->blocks.size(); ++bb) {
     const BlockDev &b = h->blocks[bb].dev;
-    f.base[bb] = which == kHaloState ? b.state : b.x;
+    f.base[bb] = which == kHaloState ? b.state : (which == kHaloUpdate ? b.x : b.eddyVisc);
     f.fs[bb] = b.fs;
   }
   ScopedLaunch sl(h, kFamHalo);
   h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
   h->famLaunches[kFamHalo]--;
-  if (HaloExchange(h->halo, f, h->neq, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
+  // kHaloTurb: eddy viscosity, f1, f2 (three contiguous fields; ref src/procBlock.cpp:3064-3085)
+  const int nc = which == kHaloTurb ? 3 : h->neq;
+  if (HaloExchange(h->halo, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
     return Fail(HaloError());
   return 0;
 }
 
-int PhaseBoundaryConditions(aither_gpu *h) {
+template <int NS, int NT>
+int PhaseBoundaryConditionsT(aither_gpu *h) {
   // ref: src/gridLevel.cpp:287-319
   for (auto &hb : h->blocks) {
     if (hb.bcThreads == 0) continue;
     ScopedLaunch sl(h, kFamBc);
     const int grid = static_cast<int>((hb.bcThreads + 127) / 128);
-    BcKernel<1, 0><<<grid, 128, 0, h->stream>>>(hb.dev, h->params, hb.dSurfs, hb.nBcSurfs,
+    BcKernel<NS, NT><<<grid, 128, 0, h->stream>>>(hb.dev, h->params, hb.dSurfs, hb.nBcSurfs,
                                                h->dBcStates, hb.bcThreads);
   }
   CK(cudaGetLastError());
@@ -350,7 +365,7 @@ int PhaseBoundaryConditions(aither_gpu *h) {
     for (auto &hb : h->blocks) {
       ScopedLaunch sl(h, kFamViscGhost);
       const int n = 4 * (hb.dev.ni + hb.dev.nj + hb.dev.nk);
-      EdgeKernel<1, 0, false><<<(n + 127) / 128, 128, 0, h->stream>>>(
+      EdgeKernel<NS, NT, false><<<(n + 127) / 128, 128, 0, h->stream>>>(
           hb.dev, h->params, hb.dEdgeSurfs, hb.nEdgeSurfs, h->dBcStates);
     }
     CK(cudaGetLastError());
@@ -358,8 +373,9 @@ int PhaseBoundaryConditions(aither_gpu *h) {
   return 0;
 }
 
-int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
-  for (auto &hb : h->blocks) LaunchResidual<1, 0>(h, hb, fusePrep, cfl);
+template <int NS, int NT>
+int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
+  for (auto &hb : h->blocks) LaunchResidual<NS, NT>(h, hb, fusePrep, cfl);
   CK(cudaGetLastError());
   if (!h->cfg.isViscous) return 0;
   // ref: src/procBlock.cpp:6125-6137
@@ -368,39 +384,50 @@ int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
     if (hb.bcThreads > 0) {
       ScopedLaunch sl(h, kFamViscGhost);
       const int grid = static_cast<int>((hb.bcThreads + 127) / 128);
-      ViscousWallKernel<1, 0><<<grid, 128, 0, h->stream>>>(b, h->params, hb.dSurfs, hb.nBcSurfs,
+      ViscousWallKernel<NS, NT><<<grid, 128, 0, h->stream>>>(b, h->params, hb.dSurfs, hb.nBcSurfs,
                                                           h->dBcStates, hb.bcThreads);
     }
     {
       ScopedLaunch sl(h, kFamViscGhost);
       const int n = 4 * (b.ni + b.nj + b.nk);
-      EdgeKernel<1, 0, true><<<(n + 127) / 128, 128, 0, h->stream>>>(
+      EdgeKernel<NS, NT, true><<<(n + 127) / 128, 128, 0, h->stream>>>(
           b, h->params, hb.dEdgeSurfs, hb.nEdgeSurfs, h->dBcStates);
     }
     {
       ScopedLaunch sl(h, kFamViscGhost);
       const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
-      AuxKernel<1, 0><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
+      AuxKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
+    }
+    if (NT > 0) {
+      // RANS: viscous + turbulent fluxes, cell averages, spectral radii and source terms per cell
+      ScopedLaunch sl(h, kFamViscFlux);
+      const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
+      LaunchRansCell<NS, NT>(b, h->params, grid, h->stream);
+      continue;
     }
     {
       ScopedLaunch sl(h, kFamViscFlux);
       const dim3 grid((b.ni + 1 + 31) / 32, (b.nj + 1 + 7) / 8, b.nk + 1);
-      ViscFaceKernel<1, 0><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params, b.xalt, b.x);
+      ViscFaceKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params, b.xalt, b.x);
     }
     {
       ScopedLaunch sl(h, kFamViscFlux);
-      ViscAccumKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(b, h->params, b.xalt, b.x,
+      ViscAccumKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(b, h->params, b.xalt, b.x,
                                                                          1);
     }
   }
   CK(cudaGetLastError());
+  // eddy viscosity and blending functions of the cells across connections
+  // (gridLevel::SwapEddyViscAndGradients / SwapTurbVars, ref src/gridLevel.cpp:386-392)
+  if (NT > 0 && Exchange(h, kHaloTurb)) return 1;
   return 0;
 }
 
-int PhasePrep(aither_gpu *h, double cfl, int bits) {
+template <int NS, int NT>
+int PhasePrepT(aither_gpu *h, double cfl, int bits) {
   for (auto &hb : h->blocks) {
     ScopedLaunch sl(h, kFamPrep);
-    PrepKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
+    PrepKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
   }
   CK(cudaGetLastError());
   return 0;
@@ -411,7 +438,8 @@ int SwapUpdate(aither_gpu *h) {
   return Exchange(h, kHaloUpdate);
 }
 
-int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
+template <int NS, int NT>
+int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
   const bool fullGSAlways = h->cfg.matrixRequiresInit != 0;
   for (int s = 0; s < sweeps; ++s) {
     if (SwapUpdate(h)) return 1;
@@ -419,13 +447,13 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
       for (auto &hb : h->blocks) {
         {
           ScopedLaunch sl(h, kFamDplur);
-          if (h->legacyKernels) {
-            DplurKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+          if (h->legacyKernels || NT > 0) {
+            DplurKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
                                                                             hb.dev.x, hb.dev.xalt);
           } else if (h->tmaImplicit) {
-            LaunchImplicitTma<1, 0, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
+            LaunchImplicitTma<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           } else {
-            LaunchImplicitMarch<1, 0, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
+            LaunchImplicitMarch<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           }
         }
         std::swap(hb.dev.x, hb.dev.xalt);
@@ -438,7 +466,7 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
         const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
         for (int pl = 0; pl <= b.ni + b.nj + b.nk - 3; ++pl) {
           ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<1, 0, true><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+          LusgsPlaneKernel<NS, NT, true><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
         }
       }
       if (SwapUpdate(h)) return 1;
@@ -448,7 +476,7 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
         const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
         for (int pl = b.ni + b.nj + b.nk - 3; pl >= 0; --pl) {
           ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<1, 0, false><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+          LusgsPlaneKernel<NS, NT, false><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
         }
       }
     }
@@ -460,14 +488,14 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
     int nPartials = hb.nCellBlocks;
     {
       ScopedLaunch sl(h, kFamAxmb);
-      if (h->legacyKernels) {
-        AxmbKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
+      if (h->legacyKernels || NT > 0) {
+        AxmbKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
             hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
       } else if (h->tmaImplicit) {
-        LaunchImplicitTma<1, 0, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+        LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
         nPartials = hb.nTmaBlocks;
       } else {
-        LaunchImplicitMarch<1, 0, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+        LaunchImplicitMarch<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
         nPartials = hb.nMarchBlocks;
       }
     }
@@ -481,12 +509,13 @@ int PhaseRelax(aither_gpu *h, int sweeps, int slot) {
   return 0;
 }
 
-int PhaseUpdate(aither_gpu *h, int slot, int mm) {
+template <int NS, int NT>
+int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
   const int nl = std::max(1, h->cfg.nonlinearIterations);
   for (auto &hb : h->blocks) {
     {
       ScopedLaunch sl(h, kFamUpdate);
-      UpdateKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+      UpdateKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
                                                                        h->dPartials,
                                                                        h->dLinfPartials);
     }
@@ -508,6 +537,36 @@ int PhaseUpdate(aither_gpu *h, int slot, int mm) {
     }
   }
   CK(cudaGetLastError());
+  return 0;
+}
+
+// equation-set dispatch: one species, laminar / Euler (NT = 0) or two-equation RANS (NT = 2)
+#define EQ_DISPATCH(h, FN, ...) ((h)->nt == 0 ? FN<1, 0>(__VA_ARGS__) : FN<1, 2>(__VA_ARGS__))
+int PhaseBoundaryConditions(aither_gpu *h) { return EQ_DISPATCH(h, PhaseBoundaryConditionsT, h); }
+int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
+  return EQ_DISPATCH(h, PhaseResidualT, h, fusePrep, cfl);
+}
+int PhasePrep(aither_gpu *h, double cfl, int bits) { return EQ_DISPATCH(h, PhasePrepT, h, cfl, bits); }
+int PhaseRelax(aither_gpu *h, int sweeps, int slot) { return EQ_DISPATCH(h, PhaseRelaxT, h, sweeps, slot); }
+int PhaseUpdate(aither_gpu *h, int slot, int mm) { return EQ_DISPATCH(h, PhaseUpdateT, h, slot, mm); }
+
+template <int NS, int NT>
+int StoreOldT(aither_gpu *h, int copyNm1) {
+  for (auto &hb : h->blocks) {
+    ScopedLaunch sl(h, kFamStore);
+    StoreOldKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, copyNm1);
+  }
+  return 0;
+}
+// temperature and viscosity from the current state (gridLevel::AuxillaryAndWidths before the first
+// iteration, ref src/gridLevel.cpp:433-438: the viscous-wall omega BC reads the stored viscosity)
+template <int NS, int NT>
+int InitAuxT(aither_gpu *h, int blk) {
+  HostBlock &hb = h->blocks[blk];
+  const BlockDev &b = hb.dev;
+  ScopedLaunch sl(h, kFamViscGhost);
+  const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
+  AuxKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
   return 0;
 }
 
@@ -589,7 +648,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   h->ns = cfg->numSpecies;
   h->nt = cfg->numTurb;
   h->neq = h->ns + 4 + h->nt;
-  h->asz = 1;
+  h->asz = 1 + (h->nt > 0 ? 1 : 0);  // scalar diagonal {flow, turbulence}
   Params &p = h->params;
   for (int s = 0; s < AITHER_MAX_SPECIES; ++s) {
     p.gas.R[s] = cfg->gasConstant[s];
@@ -616,6 +675,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.tr.condS = cfg->suthCondS[0];
   p.tr.kRef = cfg->kMixRef;
   p.tr.scaling = cfg->nondimScaling;
+  p.tr.turbModel = cfg->turbModel;
   if (cfg->isViscous && !(cfg->muMixRef > 0.0 && cfg->kMixRef > 0.0 && cfg->tRef > 0.0)) {
     delete h;
     return Fail("aither_gpu_create: viscous run without transport reference values "
@@ -679,7 +739,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // field budget (doubles per cell): state, consN, [consNm1], resid, rhs, x, xalt, [mres],
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
-                        12 + 3 + (cfg->isViscous ? 6 : 0);
+                        12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
+                        (h->nt > 0 ? 18 : 0);
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
@@ -696,8 +757,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     b.mres = take(neq);
     b.specRad = take(2);
     b.dt = take(1);
-    b.diag = take(1);
-    b.dinv = take(1);
+    b.diag = take(h->asz);
+    b.dinv = take(h->asz);
     b.vol = take(1);
     for (int q = 0; q < 3; ++q) b.cw[q] = take(1);
     for (int q = 0; q < 3; ++q) b.mc[q] = take(2);
@@ -708,6 +769,19 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       b.viscosity = take(1);
       b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
+    }
+    if (h->nt > 0) {
+      b.eddyVisc = take(1);
+      b.f1 = take(1);
+      b.f2 = take(1);
+      b.velGrad = take(9);
+      b.tkeGrad = take(3);
+      b.omegaGrad = take(3);
+      if (!d.wallDist) {
+        Fail("aither_gpu_create: RANS runs need the wall distance");
+        FreeAll(h);
+        return 1;
+      }
     }
 
     const int NI = d.ni + 2 * g, NJ = d.nj + 2 * g, NK = d.nk + 2 * g;
@@ -733,8 +807,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
         return 1;
       }
       if (d.wallDist) CKH(UploadAos(h, hb, d.wallDist, NI, NJ, NK, 1, b.wallDist, -g, -g, -g));
-      ScopedLaunch sl(h, kFamLayout);
-      DistKernel<<<148 * 8, 256, 0, h->stream>>>(b);
+      {
+        ScopedLaunch sl(h, kFamLayout);
+        DistKernel<<<148 * 8, 256, 0, h->stream>>>(b);
+      }
+      EQ_DISPATCH(h, InitAuxT, h, bb);
     }
     for (int q = 0; q < 3; ++q) {
       ScopedLaunch sl(h, kFamLayout);
@@ -859,9 +936,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       hb.tmaGrid = dim3((d.ni + kQI - 1) / kQI, (d.nj + kQJ - 1) / kQJ, nChunks);
       hb.nTmaBlocks = hb.tmaGrid.x * hb.tmaGrid.y * hb.tmaGrid.z;
       std::string err;
-      if (EncodeBlockMap(&hb.tmaMaps.cell, b, hb.alloc, nFields, kQPI, kQPJ, neq, &err) ||
+      if (h->tmaImplicit && h->nt == 0 &&
+          (EncodeBlockMap(&hb.tmaMaps.cell, b, hb.alloc, nFields, kQPI, kQPJ, neq, &err) ||
           EncodeBlockMap(&hb.tmaMaps.faceI, b, hb.alloc, nFields, kQAI, kQJ, 4, &err) ||
-          EncodeBlockMap(&hb.tmaMaps.faceJ, b, hb.alloc, nFields, kQI, kQJ + 1, 4, &err)) {
+          EncodeBlockMap(&hb.tmaMaps.faceJ, b, hb.alloc, nFields, kQI, kQJ + 1, 4, &err))) {
         Fail("aither_gpu_create: " + err);
         FreeAll(h);
         return 1;
@@ -901,10 +979,7 @@ int aither_gpu_store_old_solution(aither_gpu *h, int iter) {
   if (!h) return Fail("null handle");
   CK(cudaSetDevice(h->device));
   const int copyNm1 = (h->cfg.isMultilevelTime && iter == 0) ? 1 : 0;
-  for (auto &hb : h->blocks) {
-    ScopedLaunch sl(h, kFamStore);
-    StoreOldKernel<1, 0><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, copyNm1);
-  }
+  EQ_DISPATCH(h, StoreOldT, h, copyNm1);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1024,7 +1099,7 @@ int aither_gpu_reset_diagonal(aither_gpu *h) {
   if (!h) return Fail("null handle");
   CK(cudaSetDevice(h->device));
   for (auto &hb : h->blocks) {
-    CK(cudaMemsetAsync(hb.dev.diag, 0, sizeof(double) * hb.dev.fs, h->stream));
+    CK(cudaMemsetAsync(hb.dev.diag, 0, sizeof(double) * hb.dev.fs * h->asz, h->stream));
   }
   return 0;
 }
@@ -1051,6 +1126,17 @@ static int FieldInfo(aither_gpu *h, int blk, int field, const double **ptr, int 
     case AITHER_FIELD_VISCOSITY:
       if (!b.viscosity) return Fail("viscosity is only stored for viscous runs");
       *ptr = b.viscosity; *nc = 1; *padded = true; break;
+    case AITHER_FIELD_EDDY_VISCOSITY: case AITHER_FIELD_F1: case AITHER_FIELD_F2:
+    case AITHER_FIELD_VELOCITY_GRAD: case AITHER_FIELD_TKE_GRAD: case AITHER_FIELD_OMEGA_GRAD:
+      if (!b.eddyVisc) return Fail("turbulence fields are only stored for RANS runs");
+      *padded = field != AITHER_FIELD_TKE_GRAD && field != AITHER_FIELD_OMEGA_GRAD;
+      *nc = field == AITHER_FIELD_VELOCITY_GRAD ? 9 : (*padded ? 1 : 3);
+      *ptr = field == AITHER_FIELD_EDDY_VISCOSITY ? b.eddyVisc
+             : field == AITHER_FIELD_F1 ? b.f1
+             : field == AITHER_FIELD_F2 ? b.f2
+             : field == AITHER_FIELD_VELOCITY_GRAD ? b.velGrad
+             : field == AITHER_FIELD_TKE_GRAD ? b.tkeGrad : b.omegaGrad;
+      break;
     default: return Fail("unknown or unavailable field id " + std::to_string(field));
   }
   return 0;
@@ -1085,8 +1171,14 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   const HostBlock &hb = h->blocks[blk];
   const BlockDev &b = hb.dev;
   const int g = b.g;
-  return UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g,
-                   -g, -g);
+  if (UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g, -g,
+                -g))
+    return 1;
+  if (h->nt > 0) {  // the wall omega BC reads the stored viscosity: make it the new state's
+    EQ_DISPATCH(h, InitAuxT, h, blk);
+    CK(cudaGetLastError());
+  }
+  return 0;
 }
 
 int aither_gpu_alloc_host(long long bytes, void **out) {

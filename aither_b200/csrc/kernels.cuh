@@ -19,6 +19,7 @@
 
 #include "layout.cuh"
 #include "physics.cuh"
+#include "turbulence.cuh"
 
 namespace aither {
 
@@ -137,7 +138,8 @@ __global__ void BcKernel(BlockDev b, Params p, const SurfDev *__restrict__ surfs
   const long long fidx = CellIdx(b, c[0], c[1], c[2]);
 #pragma unroll
   for (int q = 0; q < 3; ++q) area[q] = __ldg(b.fA[d3] + q * b.fs + fidx);
-  GhostState<NS, NT>(p.gas, interior, bcType, area, sf.surfType, bcs[sf.bcIndex], layer, ghost);
+  GhostState<NS, NT>(p.gas, interior, bcType, area, sf.surfType, bcs[sf.bcIndex], layer, ghost,
+                     &p.tr);
   c[d3] = gCell;
   StoreCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), ghost);
 }
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(256) PrepKernel(BlockDev b, Params p, double c
   } else {
     dt = b.dt[idx];
   }
-  double dinv;
+  double dinv, dinvT = 0.0;
   if (bits & kPrepDiag) {
     // ref: src/linearSolver.cpp:146-188
     double diagVolTime = (vol * (1.0 + p.zeta)) / (dt * p.theta);
@@ -378,8 +380,17 @@ __global__ void __launch_bounds__(256) PrepKernel(BlockDev b, Params p, double c
     b.diag[idx] = a;
     dinv = 1.0 / a;
     b.dinv[idx] = dinv;
+    if (NT > 0) {  // uncoupled scalar diagonal {flow, turbulence}
+      double at = b.diag[b.fs + idx];
+      at *= p.relax;
+      at += diagVolTime;
+      b.diag[b.fs + idx] = at;
+      dinvT = 1.0 / at;
+      b.dinv[b.fs + idx] = dinvT;
+    }
   } else {
     dinv = b.dinv[idx];
+    if (NT > 0) dinvT = b.dinv[b.fs + idx];
   }
   if (bits & kPrepInit) {
     double s[E::neq], rb[E::neq];
@@ -388,7 +399,8 @@ __global__ void __launch_bounds__(256) PrepKernel(BlockDev b, Params p, double c
     StoreCell<E::neq>(b.rhs, b.fs, idx, rb);
     // ref: src/linearSolver.cpp:111-144 (x = D^-1 b when the solver needs initialisation, else 0)
 #pragma unroll
-    for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = p.matrixRequiresInit ? rb[e] * dinv : 0.0;
+    for (int e = 0; e < E::neq; ++e)
+      b.x[e * b.fs + idx] = p.matrixRequiresInit ? rb[e] * (e < NS + 4 ? dinv : dinvT) : 0.0;
   }
 }
 
@@ -397,6 +409,24 @@ __global__ void __launch_bounds__(256) PrepKernel(BlockDev b, Params p, double c
 __device__ __forceinline__ bool ConnAcross(const BlockDev &b, int surf, int c1, int n1, int c2) {
   const uint8_t *m = b.connFace[surf - 1];
   return m != nullptr && m[c1 + n1 * c2] != 0;
+}
+
+// viscous parts of the face spectral radii of neighbour cell `nidx` (state sn): flow
+// (ViscFaceSpectralRadius, include/spectralRadius.hpp:126-151) and turbulence equations
+// (turbModel::ViscousFaceSpectralRadius, src/turbulence.cpp:513-527,796-808), from the neighbour's
+// stored viscosity, eddy viscosity and blending function (ref: src/procBlock.cpp:1069-1076)
+template <int NS, int NT>
+__device__ __forceinline__ void NeighbourViscTerms(const BlockDev &b, const Params &p,
+                                                   const double *sn, long long nidx, double length,
+                                                   double *extra, double *extraT) {
+  const double rho = SpeciesSum<NS>(sn);
+  const double mu = __ldg(b.viscosity + nidx);
+  const double mut = NT > 0 ? __ldg(b.eddyVisc + nidx) : 0.0;
+  *extra = length * ViscSpecFactor(p.tr, rho, Gamma<NS>(p.gas, sn), mu, mut);
+  if (NT > 0)
+    *extraT = length * TurbViscSpecFactor(p.tr.turbModel, p.tr.scaling, rho, sn[NS + 4],
+                                          sn[NS + 4 + (NT > 1 ? 1 : 0)], mu, mut,
+                                          __ldg(b.f1 + nidx));
 }
 
 template <int NS, int NT, bool LOWER, bool UPPER>
@@ -422,12 +452,11 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx - st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx);
-        double extra = 0.0;
+        double extra = 0.0, extraT = 0.0;
         if (p.isViscous)
-          extra = fa[3] / __ldg(b.dist[d] + idx) *
-                  ViscSpecFactor(p.tr, SpeciesSum<NS>(sn), Gamma<NS>(p.gas, sn),
-                                 __ldg(b.viscosity + idx - st));
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, true, od, extra);
+          NeighbourViscTerms<NS, NT>(b, p, sn, idx - st, fa[3] / __ldg(b.dist[d] + idx), &extra,
+                                     &extraT);
+        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, true, od, extra, extraT);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) L[e] += od[e];
       }
@@ -439,12 +468,11 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx + st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx + st);
-        double extra = 0.0;
+        double extra = 0.0, extraT = 0.0;
         if (p.isViscous)
-          extra = fa[3] / __ldg(b.dist[d] + idx + st) *
-                  ViscSpecFactor(p.tr, SpeciesSum<NS>(sn), Gamma<NS>(p.gas, sn),
-                                 __ldg(b.viscosity + idx + st));
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, false, od, extra);
+          NeighbourViscTerms<NS, NT>(b, p, sn, idx + st, fa[3] / __ldg(b.dist[d] + idx + st),
+                                     &extra, &extraT);
+        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, false, od, extra, extraT);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) U[e] += od[e];
       }
@@ -464,11 +492,12 @@ __global__ void __launch_bounds__(256)
   const long long idx = CellIdx(b, i, j, k);
   double L[E::neq], U[E::neq];
   OffDiagonals<NS, NT, true, true>(b, p, xin, i, j, k, idx, L, U);
-  const double dinv = __ldg(b.dinv + idx);
+  const double dinvF = __ldg(b.dinv + idx);
+  const double dinvT = NT > 0 ? __ldg(b.dinv + b.fs + idx) : 0.0;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) {
     const double rb = __ldg(b.rhs + e * b.fs + idx);
-    xout[e * b.fs + idx] = ((rb + 0.0) + (L[e] - U[e])) * dinv;
+    xout[e * b.fs + idx] = ((rb + 0.0) + (L[e] - U[e])) * (e < NS + 4 ? dinvF : dinvT);
   }
 }
 
@@ -484,7 +513,9 @@ __global__ void __launch_bounds__(128)
   const int i = plane - j - k;
   if (i < 0 || i >= b.ni) return;
   const long long idx = CellIdx(b, i, j, k);
-  const double dinv = __ldg(b.dinv + idx);
+  const double dinvF = __ldg(b.dinv + idx);
+  const double dinvT = NT > 0 ? __ldg(b.dinv + b.fs + idx) : 0.0;
+#define dinv (e < NS + 4 ? dinvF : dinvT)
   double L[E::neq], U[E::neq];
   if (FORWARD) {
     if (fullGS) {
@@ -514,6 +545,7 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
+#undef dinv
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -560,11 +592,12 @@ __global__ void __launch_bounds__(256)
     const long long idx = CellIdx(b, i, j, k);
     double L[E::neq], U[E::neq];
     OffDiagonals<NS, NT, true, true>(b, p, b.x, i, j, k, idx, L, U);
-    const double a = __ldg(b.diag + idx);
+    const double aF = __ldg(b.diag + idx);
+    const double aT = NT > 0 ? __ldg(b.diag + b.fs + idx) : 0.0;
 #pragma unroll
     for (int e = 0; e < E::neq; ++e) {
       const double rb = __ldg(b.rhs + e * b.fs + idx);
-      const double ax = b.x[e * b.fs + idx] * a;
+      const double ax = b.x[e * b.fs + idx] * (e < NS + 4 ? aF : aT);
       const double mr = 0.0 - ((ax - (L[e] - U[e])) - rb);
       if (storeField) b.mres[e * b.fs + idx] = mr;
       sq += mr * mr;

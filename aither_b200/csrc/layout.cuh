@@ -45,6 +45,13 @@ struct BlockDev {
   double *viscosity;    // 1   laminar viscosity, normalised by mu_ref; ghosts valid
   double *wallDist;     // 1   (null when the caller gave none)
   double *dist[3];      // 1   projected centre-to-centre distance across i-, j-, k-faces
+  // RANS runs only (else null): cell averages of the six face values
+  // (ref: src/procBlock.cpp:1396-1452); eddyVisc, f1, f2 are contiguous fields (one halo exchange)
+  double *eddyVisc;     // 1   ghosts valid across connections only
+  double *f1, *f2;      // 1
+  double *velGrad;      // 9   velGrad[3 r + c] = d u_c / d x_r
+  double *tkeGrad;      // 3
+  double *omegaGrad;    // 3
   // per boundary face: 1 if the neighbour across that block face contributes to the implicit
   // off-diagonals, i.e. the face belongs to a connection (interblock / periodic) boundary
   // (ref: src/procBlock.cpp:1064,1115; include/boundaryConditions.hpp:287-293).

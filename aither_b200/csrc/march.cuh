@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kMThreads, 2)
   // flux slots of this thread's cell: lower / upper i-face, lower / upper j-face
   const int fIlo = tx + (kMI + 1) * ty, fJlo = S::FI + tx + kMI * ty;
   double pend[E::neq];                       // residual of the cell one plane below, k-hi missing
-  double pendSpec = 0.0, sosPrev = 0.0;
+  double pendSpec = 0.0, pendSpecT = 0.0, sosPrev = 0.0;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) pend[e] = 0.0;
 
@@ -287,11 +287,16 @@ __global__ void __launch_bounds__(kMThreads, 2)
         res[e] = pend[e] + fk[e];
         b.resid[e * b.fs + idxm] = res[e];
       }
-      const double sr = pendSpec + InvCellSpectralRadius<NS>(sPrev, sosPrev, fAkLo, fAk);
+      double srTk = 0.0;
+      const double sr = pendSpec + InvCellSpectralRadii<NS>(sPrev, sosPrev, fAkLo, fAk, &srTk);
+      const double srT = NT > 0 ? pendSpecT + srTk : 0.0;
       b.specRad[idxm] = sr;
-      b.specRad[b.fs + idxm] = 0.0;
+      b.specRad[b.fs + idxm] = srT;
       if (!fusePrep) {
-        if (implicitScalar) b.diag[idxm] = sr;
+        if (implicitScalar) {
+          b.diag[idxm] = sr;
+          if (NT > 0) b.diag[b.fs + idxm] = srT;
+        }
       } else {
         // the cell's residual and spectral radius are final here, so the time step, the scalar
         // diagonal and its inverse, the right-hand side and x0 = D^-1 b follow in the same pass
@@ -339,20 +344,23 @@ __global__ void __launch_bounds__(kMThreads, 2)
         r -= fk[e];
         pend[e] = r;
       }
-      double sr = 0.0;
+      double sr = 0.0, srT = 0.0, st1 = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         aLo[q] = __ldg(b.fA[0] + q * b.fs + idx);
         aHi[q] = __ldg(b.fA[0] + q * b.fs + idx + 1);
       }
-      sr += InvCellSpectralRadius<NS>(s, sos, aLo, aHi);
+      sr += InvCellSpectralRadii<NS>(s, sos, aLo, aHi, &st1);
+      srT += st1;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         aLo[q] = __ldg(b.fA[1] + q * b.fs + idx);
         aHi[q] = __ldg(b.fA[1] + q * b.fs + idx + b.sj);
       }
-      sr += InvCellSpectralRadius<NS>(s, sos, aLo, aHi);
+      sr += InvCellSpectralRadii<NS>(s, sos, aLo, aHi, &st1);
+      srT += st1;
       pendSpec = sr;
+      pendSpecT = srT;
       sosPrev = sos;
     }
   }

@@ -30,15 +30,32 @@ constexpr double kTurbMin = 1.0e-20;    // ref: include/turbulence.hpp:72-73
 // Sutherland transport of the (single) species; ref: src/transport.cpp:50-68,113-131
 struct Transport {
   double tRef, viscC1, viscS, muRef, condC1, condS, kRef, scaling;
+  int turbModel;  // aither_turb
 };
+// ref: src/transport.cpp:113-131,173-196
+AITHER_HD double SutherlandViscosity(const Transport &tr, double t) {
+  const double temp = t * tr.tRef;
+  const double mu = (tr.viscC1 * (temp * sqrt(temp))) / (temp + tr.viscS);
+  return mu / tr.muRef;
+}
+AITHER_HD double EffectiveConductivity(const Transport &tr, double t) {
+  const double temp = t * tr.tRef;
+  const double k = (tr.condC1 * (temp * sqrt(temp))) / (temp + tr.condS);
+  return (k / tr.kRef) * tr.scaling;
+}
+// turbulent Prandtl number: 0.9 (include/turbulence.hpp:70), k-omega 2006 8/9 (:398), SST 0.9 (:500)
+AITHER_HD double TurbPrandtl(int turbModel) {
+  return turbModel == AITHER_TURB_KW_WILCOX ? 8.0 / 9.0 : 0.9;
+}
 
 // max(4/(3 rho), gamma/rho) * scaling * mu / Pr: the state-dependent factor shared by
 // ViscCellSpectralRadius and ViscFaceSpectralRadius (include/spectralRadius.hpp:94-151);
 // Pr = 4 gamma / (9 gamma - 5) (include/thermodynamic.hpp:61-64)
-AITHER_HD double ViscSpecFactor(const Transport &tr, double rho, double gamma, double mu) {
+AITHER_HD double ViscSpecFactor(const Transport &tr, double rho, double gamma, double mu,
+                                double mut = 0.0) {
   const double maxTerm = fmax(4.0 / (3.0 * rho), gamma / rho);
   const double pr = (4.0 * gamma) / (9.0 * gamma - 5.0);
-  const double viscTerm = tr.scaling * (mu / pr + 0.0);
+  const double viscTerm = tr.scaling * (mu / pr + mut / TurbPrandtl(tr.turbModel));
   return maxTerm * viscTerm;
 }
 
@@ -592,6 +609,21 @@ AITHER_HD double InvCellSpectralRadius(const double *s, double sos, const double
   const double fMag = 0.5 * (fL[3] + fR[3]);
   return (fabs(s[NS] * a0 + s[NS + 1] * a1 + s[NS + 2] * a2) + sos) * fMag;
 }
+// the same with the turbulence-equation convective part |v.n| A beside it
+// (turbModel::InviscidCellSpectralRadius, ref: src/turbulence.cpp:152-160)
+template <int NS>
+AITHER_HD double InvCellSpectralRadii(const double *s, double sos, const double *fL,
+                                      const double *fR, double *turb) {
+  double a0 = 0.5 * (fL[0] + fR[0]), a1 = 0.5 * (fL[1] + fR[1]), a2 = 0.5 * (fL[2] + fR[2]);
+  const double rmag = FastRcp(sqrt(a0 * a0 + a1 * a1 + a2 * a2));
+  a0 *= rmag;
+  a1 *= rmag;
+  a2 *= rmag;
+  const double fMag = 0.5 * (fL[3] + fR[3]);
+  const double vn = fabs(s[NS] * a0 + s[NS + 1] * a1 + s[NS + 2] * a2);
+  *turb = vn * fMag;
+  return (vn + sos) * fMag;
+}
 template <int NS>
 AITHER_HD double InvFaceSpectralRadius(const double *s, double sos, const double *fA) {
   return 0.5 * fA[3] * (fabs(s[NS] * fA[0] + s[NS + 1] * fA[1] + s[NS + 2] * fA[2]) + sos);
@@ -603,17 +635,25 @@ AITHER_HD double InvFaceSpectralRadius(const double *s, double sos, const double
 template <int NS, int NT>
 AITHER_HD void OffDiagScalar(const Gas &g, const double *state, const double *du,
                              const double *fArea, bool positive, double *out,
-                             double srExtra = 0.0) {
+                             double srExtra = 0.0, double srTurbVisc = 0.0) {
   using E = Eq<NS, NT>;
   double su[E::neq], fo[E::neq], fn[E::neq];
   UpdatePrimWithCons<NS, NT>(g, state, du, su);
   PhysicalFlux<NS, NT>(g, state, fArea, fo);
   PhysicalFlux<NS, NT>(g, su, fArea, fn);
   const double sr = InvFaceSpectralRadius<NS>(state, SoS<NS>(g, state), fArea) + srExtra;
+  // turbulence equations: turbModel::FaceSpectralRadius = 0.5 |A| |vn +- |vn|| + viscous part
+  // (ref: src/turbulence.cpp:162-171, include/turbulence.hpp:308-329)
+  double srT = 0.0;
+  if (NT > 0) {
+    const double velNorm = state[NS] * fArea[0] + state[NS + 1] * fArea[1] + state[NS + 2] * fArea[2];
+    srT = (positive ? 0.5 * fArea[3] * fabs(velNorm + fabs(velNorm))
+                    : 0.5 * fArea[3] * fabs(velNorm - fabs(velNorm))) + srTurbVisc;
+  }
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) {
     const double fc = e < NS + 4 ? 0.5 * fArea[3] * (fn[e] - fo[e]) : 0.0;
-    const double srd = (e < NS + 4 ? sr : 0.0) * du[e];
+    const double srd = (e < NS + 4 ? sr : srT) * du[e];
     out[e] = positive ? fc + srd : fc - srd;
   }
 }
@@ -926,10 +966,25 @@ AITHER_HD void FreeStateFromBC(const aither_bc_state &bc, double *fs) {
 // Ghost state for one boundary face. `interior` is the reflected cell for walls and the
 // boundary-adjacent cell otherwise (ref: src/procBlock.cpp:2512-2514); `areaVec` is the unit
 // normal of the boundary face; surf 1..6; layer 1..g.
+// primitive::ApplyFarfieldTurbBC; ref: src/primitive.cpp:83-98
+template <int NS, int NT>
+AITHER_HD void ApplyFarfieldTurb(const Gas &g, const Transport *tr, double *s, double vx, double vy,
+                                 double vz, const aither_bc_state &bc) {
+  if (NT < 2 || tr == nullptr) return;
+  using E = Eq<NS, NT>;
+  const double vmag = sqrt(vx * vx + vy * vy + vz * vz);
+  const double tv = bc.turbulenceIntensity * vmag;
+  s[E::it] = 1.5 * (tv * tv);
+  const double mu = SutherlandViscosity(*tr, Temperature<NS>(g, s));
+  s[E::it + (NT > 1 ? 1 : 0)] = SpeciesSum<NS>(s) * s[E::it] / (bc.eddyViscosityRatio * mu);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) s[E::it + t] = fmax(s[E::it + t], kTurbMin);
+}
+
 template <int NS, int NT>
 AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
                           const double *areaVec, int surf, const aither_bc_state &bc, int layer,
-                          double *ghost) {
+                          double *ghost, const Transport *tr = nullptr) {
   using E = Eq<NS, NT>;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
@@ -954,6 +1009,7 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
     if (machInt >= 1.0 && (vn < 0.0 || isInlet)) {  // supersonic inflow
 #pragma unroll
       for (int e = 0; e < E::neq; ++e) ghost[e] = fs[e];
+      ApplyFarfieldTurb<NS, NT>(g, tr, ghost, bc.velocity[0], bc.velocity[1], bc.velocity[2], bc);
       if (isInlet) extrapolate = false;
     } else if (machInt >= 1.0) {  // supersonic outflow: interior
     } else if (vn < 0.0 || isInlet) {  // subsonic inflow
@@ -970,6 +1026,7 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
       ghost[E::imx] = fs[E::imx] - nA[0] * deltaPressure / rhoSoSInt;
       ghost[E::imy] = fs[E::imy] - nA[1] * deltaPressure / rhoSoSInt;
       ghost[E::imz] = fs[E::imz] - nA[2] * deltaPressure / rhoSoSInt;
+      ApplyFarfieldTurb<NS, NT>(g, tr, ghost, bc.velocity[0], bc.velocity[1], bc.velocity[2], bc);
     } else {  // subsonic outflow
       const double intRho = SpeciesSum<NS>(interior);
       const double rhoSoSInt = intRho * SoSInt;
@@ -984,13 +1041,20 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
     }
     if (extrapolate) {
       ExtrapolateHoldMixture<NS, NT>(ghost, 2.0, interior, ghost);
-      if (layer > 1) ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+      if (layer > 1) {
+        ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+        // the characteristic BC re-applies the farfield turbulence to the deeper layers, the
+        // inlet BC does not (ref: :375-385 vs :484-486)
+        if (!isInlet)
+          ApplyFarfieldTurb<NS, NT>(g, tr, ghost, bc.velocity[0], bc.velocity[1], bc.velocity[2], bc);
+      }
     }
   } else if (bcType == AITHER_BC_SUPERSONIC_INFLOW) {  // ref: :490-515
     double fs[E::neq];
     FreeStateFromBC<NS, NT>(bc, fs);
 #pragma unroll
     for (int e = 0; e < NS + 4; ++e) ghost[e] = fs[e];
+    ApplyFarfieldTurb<NS, NT>(g, tr, ghost, bc.velocity[0], bc.velocity[1], bc.velocity[2], bc);
   } else if (bcType == AITHER_BC_SUPERSONIC_OUTFLOW) {  // ref: :522-527
     if (layer > 1) {
 #pragma unroll
@@ -1021,8 +1085,12 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
     ghost[E::imy] = vbMag * bc.direction[1];
     ghost[E::imz] = vbMag * bc.direction[2];
     ghost[E::ie] = pb;
+    ApplyFarfieldTurb<NS, NT>(g, tr, ghost, ghost[E::imx], ghost[E::imy], ghost[E::imz], bc);
     ExtrapolateHoldMixture<NS, NT>(ghost, 2.0, interior, ghost);
-    if (layer > 1) ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+    if (layer > 1) {
+      ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
+      ApplyFarfieldTurb<NS, NT>(g, tr, ghost, ghost[E::imx], ghost[E::imy], ghost[E::imz], bc);
+    }
   } else if (bcType == AITHER_BC_PRESSURE_OUTLET) {  // ref: :604-664 (reflecting form)
     const double SoSInt = SoS<NS>(g, interior);
     const double intRho = SpeciesSum<NS>(interior);

@@ -21,23 +21,13 @@
 
 namespace aither {
 
-// ---- transport: Sutherland, single species (ref: src/transport.cpp:113-131,173-196) ------------
-AITHER_HD double SutherlandViscosity(const Transport &tr, double t) {
-  const double temp = t * tr.tRef;
-  const double mu = (tr.viscC1 * (temp * sqrt(temp))) / (temp + tr.viscS);
-  return mu / tr.muRef;
-}
-AITHER_HD double EffectiveConductivity(const Transport &tr, double t) {
-  const double temp = t * tr.tRef;
-  const double k = (tr.condC1 * (temp * sqrt(temp))) / (temp + tr.condS);
-  return (k / tr.kRef) * tr.scaling;
-}
 // viscous-wall ghost state, low-Re treatment (ref: src/ghostStates.cpp:134-258): velocity
 // mirrored about the wall velocity; adiabatic keeps rho and p, isothermal / heat-flux walls set
 // the ghost temperature and take rho from p = rho R T
 template <int NS, int NT>
 AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double *interior,
-                                const aither_bc_state &bc, double wallDist, double *ghost) {
+                                const aither_bc_state &bc, double wallDist, double *ghost,
+                                double nuW = 0.0, int layer = 1) {
   using E = Eq<NS, NT>;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
@@ -60,6 +50,15 @@ AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double 
     const double rho = ghost[E::ie] / (R * tGhost);
 #pragma unroll
     for (int q = 0; q < NS; ++q) ghost[q] = rho * (interior[q] / rhoInt);
+  }
+  if (NT > 1) {
+    // k = 0 at the wall; omega_wall = scaling^2 60 nu_w / (beta d^2) (ref: :262-281)
+    ghost[E::it] = -1.0 * interior[E::it];
+    const double wWall = tr.scaling * tr.scaling * 60.0 * nuW /
+                         (wallDist * wallDist * TurbWallBeta(tr.turbModel));
+    constexpr int iw = E::it + (NT > 1 ? 1 : 0);
+    ghost[iw] = 2.0 * wWall - interior[iw];
+    if (layer > 1) ghost[iw] = layer * ghost[iw] - wWall;
   }
 }
 
@@ -101,8 +100,18 @@ __global__ void ViscousWallKernel(BlockDev b, Params p, const SurfDev *__restric
   double interior[E::neq], ghost[E::neq];
   LoadCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), interior);
   c[d3] = aCell;
-  const double wd = b.wallDist ? b.wallDist[CellIdx(b, c[0], c[1], c[2])] : 0.0;
-  ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bcs[sf.bcIndex], wd, ghost);
+  const long long aidx = CellIdx(b, c[0], c[1], c[2]);
+  const double wd = b.wallDist ? b.wallDist[aidx] : 0.0;
+  // nu of the wall-adjacent cell from the STORED viscosity, i.e. the previous evaluation's
+  // (AssignViscousGhostCells runs before UpdateAuxillaryVariables; ref src/procBlock.cpp:2814-2822)
+  double nuW = 0.0;
+  if (NT > 0) {
+    double rhoA = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) rhoA += __ldg(b.state + q * b.fs + aidx);
+    nuW = b.viscosity[aidx] / rhoA;
+  }
+  ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bcs[sf.bcIndex], wd, ghost, nuW, layer);
   c[d3] = gCell;
   StoreCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), ghost);
 }
@@ -460,6 +469,275 @@ __global__ void __launch_bounds__(256)
   for (int q = 0; q < 4; ++q) b.resid[(NS + q) * b.fs + idx] = r[q];
   b.specRad[idx] = sr;
   if (implicitScalar) b.diag[idx] = dg;
+}
+
+// =============================================================================================
+// RANS (k-omega Wilcox 2006 / SST 2003): viscous + turbulent face fluxes, cell averages of the
+// face gradients / eddy viscosity / blending functions, turbulent spectral radii and the
+// turbulence source terms, in ONE pass: a thread owns a cell and evaluates its six faces (each
+// interior face is therefore evaluated twice, from identical inputs with identical code, so both
+// owners see the same bits: owner-writes, no atomics, no scratch fields). Accumulation order per
+// cell as the reference: i-lo, i-hi, j-lo, j-hi, k-lo, k-hi, then the source terms
+// (ref: src/procBlock.cpp:1233-1497 and the J/K twins; CalcSrcTerms :5956-6025).
+template <int NEQ>
+struct FaceOut {
+  double flux[NEQ];  // viscous flux * |A| (species rows are 0 for one species)
+  double mut, f1, f2;
+  double vg[9], kg[3], wg[3];
+};
+
+template <int NS, int NT, int D>
+__device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, long long idx,
+                                         FaceOut<NS + 4 + NT> &o) {
+  using E = Eq<NS, NT>;
+  constexpr int iw = E::it + (NT > 1 ? 1 : 0);
+  const long long sd = Stride(b, D);
+  const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
+  double al[3][3], au[3][3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double a0[3], a1[3];
+    if (q == D) {
+      AreaVec(b, D, idx, a0);
+      AreaVec(b, D, idx + sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, D, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    } else {
+      AreaVec(b, q, idx + st[q], a0);
+      AreaVec(b, q, idx + st[q] - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, q, idx, a0);
+      AreaVec(b, q, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    }
+  }
+  const double vol = 0.5 * (__ldg(b.vol + idx - sd) + __ldg(b.vol + idx));
+  const double invVol = 1.0 / vol;
+  // u, v, w, T, k, omega on the six faces of the control volume, then Green-Gauss
+  // (ref: src/procBlock.cpp:5190-5352, src/utility.cpp:59-175)
+  double grad[6][3];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const double *f = c < 3 ? b.state + (NS + c) * b.fs
+                            : (c == 3 ? b.temperature : b.state + (E::it + c - 4) * b.fs);
+    const double lo = __ldg(f + idx - sd), hi = __ldg(f + idx);
+    double vl[3], vu[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q == D) {
+        vl[q] = lo;
+        vu[q] = hi;
+      } else {
+        vu[q] = 0.25 * (lo + hi + __ldg(f + idx + st[q]) + __ldg(f + idx + st[q] - sd));
+        vl[q] = 0.25 * (lo + hi + __ldg(f + idx - st[q]) + __ldg(f + idx - st[q] - sd));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double t = vu[0] * au[0][r] - vl[0] * al[0][r] + vu[1] * au[1][r] - vl[1] * al[1][r] +
+                       vu[2] * au[2][r] - vl[2] * al[2][r];
+      grad[c][r] = t * invVol;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.vg[3 * r + c] = grad[c][r];
+    o.kg[r] = grad[4][r];
+    o.wg[r] = grad[5][r];
+  }
+  // face state, viscosity and wall distance (ref: src/procBlock.cpp:1305-1351; turbulence
+  // variables and the wall distance stay second order, include/reconstruction.hpp:359-379)
+  double fs_[E::neq], mu, wDist = 0.0;
+  {
+    const double w2[2] = {__ldg(b.cw[D] + idx - sd), __ldg(b.cw[D] + idx)};
+    double c2[2];
+    LagrangeCoeff<1>(w2, 0, 0, c2);
+    if (p.viscRecon == 0) {
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e)
+        fs_[e] = c2[0] * __ldg(b.state + e * b.fs + idx) + c2[1] * __ldg(b.state + e * b.fs + idx - sd);
+      mu = c2[0] * __ldg(b.viscosity + idx) + c2[1] * __ldg(b.viscosity + idx - sd);
+    } else {
+      const double w[4] = {__ldg(b.cw[D] + idx - 2 * sd), w2[0], w2[1], __ldg(b.cw[D] + idx + sd)};
+      double c[4];
+      LagrangeCoeff<3>(w, 1, 1, c);
+#pragma unroll
+      for (int e = 0; e < NS + 4; ++e)
+        fs_[e] = c[0] * __ldg(b.state + e * b.fs + idx - 2 * sd) +
+                 c[1] * __ldg(b.state + e * b.fs + idx - sd) + c[2] * __ldg(b.state + e * b.fs + idx) +
+                 c[3] * __ldg(b.state + e * b.fs + idx + sd);
+#pragma unroll
+      for (int e = NS + 4; e < E::neq; ++e)
+        fs_[e] = c2[0] * __ldg(b.state + e * b.fs + idx) + c2[1] * __ldg(b.state + e * b.fs + idx - sd);
+      mu = c[0] * __ldg(b.viscosity + idx - 2 * sd) + c[1] * __ldg(b.viscosity + idx - sd) +
+           c[2] * __ldg(b.viscosity + idx) + c[3] * __ldg(b.viscosity + idx + sd);
+    }
+    if (b.wallDist) wDist = c2[0] * __ldg(b.wallDist + idx) + c2[1] * __ldg(b.wallDist + idx - sd);
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) fs_[E::it + t] = fmax(fs_[E::it + t], kTurbMin);  // LimitTurb
+  if (wDist < 0.0 && wDist > -1.0e-10) wDist = 0.0;  // WALL_DIST_NEG_TOL
+  const double rho = SpeciesSum<NS>(fs_);
+  EddyViscAndBlending(p.tr.turbModel, p.tr.scaling, rho, fs_[E::it], fs_[iw], o.vg, o.kg, o.wg, mu,
+                      wDist, &o.mut, &o.f1, &o.f2);
+  // viscousFlux::CalcFlux (src/viscousFlux.cpp:58-135), TauNormal (src/utility.cpp:425-437)
+  double n[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) n[q] = __ldg(b.fA[D] + q * b.fs + idx);
+  const double mag = __ldg(b.fA[D] + 3 * b.fs + idx);
+  const double mus = p.tr.scaling * mu, muts = p.tr.scaling * o.mut;
+  const double lambda = 0.0 - (2.0 / 3.0) * (mus + muts);
+  const double trace = grad[0][0] + grad[1][1] + grad[2][2];
+  double tau[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double mm = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mm += (grad[c][r] + grad[r][c]) * n[c];
+    tau[r] = lambda * trace * n[r] + (mus + muts) * mm;
+  }
+  const double t = Temperature<NS>(p.gas, fs_);
+  const double kcond = EffectiveConductivity(p.tr, t);
+  // sutherland::TurbConductivity: mu_t cp / Pr_t (include/transport.hpp:132-137)
+  const double kt = muts * Mixture<NS>(p.gas, fs_).cp / TurbPrandtl(p.tr.turbModel);
+  const double fe = (tau[0] * fs_[E::imx] + tau[1] * fs_[E::imy] + tau[2] * fs_[E::imz]) +
+                    (kcond + kt) * (grad[3][0] * n[0] + grad[3][1] * n[1] + grad[3][2] * n[2]) + 0.0;
+  // k and omega diffusion; k-omega 2006 uses the unlimited eddy viscosity here
+  // (ref: src/viscousFlux.cpp:117-134, include/turbulence.hpp:439)
+  const double mutt = IsSst(p.tr.turbModel) ? muts : p.tr.scaling * (rho * fs_[E::it] / fs_[iw]);
+  const double fk = (mus + TurbSigmaK(p.tr.turbModel, o.f1) * mutt) * Dot3(o.kg, n);
+  const double fw = (mus + TurbSigmaW(p.tr.turbModel, o.f1) * mutt) * Dot3(o.wg, n);
+#pragma unroll
+  for (int q = 0; q < NS; ++q) o.flux[q] = 0.0;
+  o.flux[E::imx] = tau[0] * mag;
+  o.flux[E::imy] = tau[1] * mag;
+  o.flux[E::imz] = tau[2] * mag;
+  o.flux[E::ie] = fe * mag;
+  o.flux[E::it] = fk * mag;
+  o.flux[iw] = fw * mag;
+}
+
+template <int NS, int NT>
+struct RansAcc {
+  double r[NS + 4 + NT];
+  double sr, srT, dg, dgT;
+  double mut, f1, f2, vg[9], kg[3], wg[3];
+};
+
+template <int NS, int NT, int D>
+__device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Params &p, long long idx,
+                                                  const double *s, double visc, double vol,
+                                                  RansAcc<NS, NT> &a) {
+  using E = Eq<NS, NT>;
+  constexpr double sixth = 1.0 / 6.0;
+  constexpr int iw = E::it + (NT > 1 ? 1 : 0);
+  const long long sd = Stride(b, D);
+  FaceOut<E::neq> f;
+  // lower face: this cell is the face's upper cell (ref: :1432-1493)
+  RansFace<NS, NT, D>(b, p, idx, f);
+#pragma unroll
+  for (int e = NS; e < E::neq; ++e) a.r[e] += f.flux[e];
+  const double mutLo = f.mut, f1Lo = f.f1;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) a.vg[q] += sixth * f.vg[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    a.kg[q] += sixth * f.kg[q];
+    a.wg[q] += sixth * f.wg[q];
+  }
+  a.mut += sixth * f.mut;
+  a.f1 += sixth * f.f1;
+  a.f2 += sixth * f.f2;
+  {
+    const double fMag = 0.5 * (__ldg(b.fA[D] + 3 * b.fs + idx) + __ldg(b.fA[D] + 3 * b.fs + idx + sd));
+    const double rho = SpeciesSum<NS>(s);
+    const double length = fMag * fMag / vol;
+    const double vsr = ViscSpecFactor(p.tr, rho, Gamma<NS>(p.gas, s), visc, mutLo) * length;
+    const double tvsr = TurbViscSpecFactor(p.tr.turbModel, p.tr.scaling, rho, s[E::it], s[iw], visc,
+                                           mutLo, f1Lo) * length;
+    a.sr += vsr * p.viscCFLCoeff;
+    a.srT += tvsr * p.viscCFLCoeff;
+    a.dg += 2.0 * vsr;
+    a.dgT += 2.0 * tvsr;
+  }
+  // upper face: this cell is the face's lower cell (ref: :1392-1429)
+  RansFace<NS, NT, D>(b, p, idx + sd, f);
+#pragma unroll
+  for (int e = NS; e < E::neq; ++e) a.r[e] -= f.flux[e];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) a.vg[q] += sixth * f.vg[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    a.kg[q] += sixth * f.kg[q];
+    a.wg[q] += sixth * f.wg[q];
+  }
+  a.mut += sixth * f.mut;
+  a.f1 += sixth * f.f1;
+  a.f2 += sixth * f.f2;
+}
+
+template <int NS, int NT>
+__global__ void __launch_bounds__(128)
+    RansCellKernel(BlockDev b, Params p, int implicitScalar) {
+  using E = Eq<NS, NT>;
+  constexpr int iw = E::it + (NT > 1 ? 1 : 0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double s[E::neq];
+  LoadCell<E::neq>(b.state, b.fs, idx, s);
+  const double visc = __ldg(b.viscosity + idx);
+  const double vol = __ldg(b.vol + idx);
+  RansAcc<NS, NT> a;
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) a.r[e] = b.resid[e * b.fs + idx];
+  a.sr = b.specRad[idx];
+  a.srT = b.specRad[b.fs + idx];
+  a.dg = implicitScalar ? b.diag[idx] : 0.0;
+  a.dgT = implicitScalar ? b.diag[b.fs + idx] : 0.0;
+  a.mut = a.f1 = a.f2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) a.vg[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) a.kg[q] = a.wg[q] = 0.0;
+  RansAccumulateDir<NS, NT, 0>(b, p, idx, s, visc, vol, a);
+  RansAccumulateDir<NS, NT, 1>(b, p, idx, s, visc, vol, a);
+  RansAccumulateDir<NS, NT, 2>(b, p, idx, s, visc, vol, a);
+  // source terms (ref: src/procBlock.cpp:5956-6025, src/source.cpp:64-82)
+  double src[2];
+  const double rho = SpeciesSum<NS>(s);
+  TurbSource(p.tr.turbModel, p.tr.scaling, rho, s[E::it], s[iw], a.vg, a.kg, a.wg, a.mut, a.f1, src);
+  const double turbSpecRad = TurbSrcSpecRad(p.tr.scaling, s[iw], vol);
+  a.srT -= turbSpecRad;
+  a.dgT -= turbSpecRad;
+  a.r[E::it] -= src[0] * vol;
+  a.r[iw] -= src[1] * vol;
+#pragma unroll
+  for (int e = NS; e < E::neq; ++e) b.resid[e * b.fs + idx] = a.r[e];
+  b.specRad[idx] = a.sr;
+  b.specRad[b.fs + idx] = a.srT;
+  if (implicitScalar) {
+    b.diag[idx] = a.dg;
+    b.diag[b.fs + idx] = a.dgT;
+  }
+  b.eddyVisc[idx] = a.mut;
+  b.f1[idx] = a.f1;
+  b.f2[idx] = a.f2;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) b.velGrad[q * b.fs + idx] = a.vg[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    b.tkeGrad[q * b.fs + idx] = a.kg[q];
+    b.omegaGrad[q * b.fs + idx] = a.wg[q];
+  }
 }
 
 }  // namespace aither

@@ -2501,3 +2501,33 @@ void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
   level_from_cfg(&h, cfg);
   offdiag_scalar(&h, stateNb, duNb, fArea, positive, 0.0, 0.0, 0.0, 1.0, out);
 }
+
+/* turbulence point functions (tests/test_physics_host.py) */
+void orc_eddy_visc(const aither_cfg *cfg, const double *state, const double vg[9],
+                   const double kg[3], const double wg[3], double mu, double wallDist,
+                   double out[3]) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  eddy_visc_and_blending(&h, state, vg, kg, wg, mu, wallDist, &out[0], &out[1], &out[2]);
+}
+void orc_turb_source(const aither_cfg *cfg, const double *state, const double vg[9],
+                     const double kg[3], const double wg[3], double mut, double f1,
+                     double src[2]) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  calc_turb_src(&h, state, vg, kg, wg, mut, f1, src);
+}
+void orc_offdiag_scalar_visc(const aither_cfg *cfg, const double *stateNb, const double *duNb,
+                             const double fArea[4], int positive, double mu, double mut,
+                             double f1, double dist, double *out) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  offdiag_scalar(&h, stateNb, duNb, fArea, positive, mu, mut, f1, dist, out);
+}
+void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcType,
+                          const double areaUnit[3], int surfType, int tag, int layer,
+                          double wallDist, double nuW, double *ghost) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, wallDist, nuW, ghost);
+}

@@ -63,6 +63,20 @@ void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
                         const double *duNb, const double fArea[4], int positive,
                         double *out);
 
+/* turbulence / viscous variants */
+void orc_eddy_visc(const aither_cfg *cfg, const double *state, const double vg[9],
+                   const double kg[3], const double wg[3], double mu, double wallDist,
+                   double out[3] /* mut, f1, f2 */);
+void orc_turb_source(const aither_cfg *cfg, const double *state, const double vg[9],
+                     const double kg[3], const double wg[3], double mut, double f1,
+                     double src[2]);
+void orc_offdiag_scalar_visc(const aither_cfg *cfg, const double *stateNb, const double *duNb,
+                             const double fArea[4], int positive, double mu, double mut,
+                             double f1, double dist, double *out);
+void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcType,
+                          const double areaUnit[3], int surfType, int tag, int layer,
+                          double wallDist, double nuW, double *ghost);
+
 #ifdef __cplusplus
 }
 #endif

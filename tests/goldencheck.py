@@ -146,7 +146,7 @@ def check_phases(make_level, d, it, tol):
     # equations whose residual is rounding noise are not compared (as in check_history)
     l2err = float(np.max(np.abs(l2 - h) / np.where(h > 1e-20 * h.max(), h, np.inf)))
     out["l2"] = l2err
-    assert l2err <= tol["l2"], (tag, l2, h)
+    assert l2err <= tol["l2"], (tag, l2err, np.abs(l2 - h) / h, out)
     # L-infinity: the reference takes the largest *signed* residual (src/procBlock.cpp:862-867);
     # when every residual of a uniform flow is <= rounding noise its location is noise too
     loc, lref = d["hist/linfLoc"][it], float(d["hist/linf"][it])

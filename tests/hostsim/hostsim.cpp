@@ -2,6 +2,7 @@
 // aither_b200/csrc/physics.cuh, so they can be checked against the oracle on a machine without a
 // GPU. Never part of libaither_b200.so; built on demand by tests/test_physics_host.py.
 #include "../../aither_b200/csrc/physics.cuh"
+#include "../../aither_b200/csrc/turbulence.cuh"
 
 using namespace aither;
 
@@ -79,5 +80,53 @@ void hs_offdiag_fast(const aither_cfg *c, const double *s, const double *du, con
   }
   auto ld = [&](int q) { return ing[q]; };
   OffDiagFromIngr<1, 0>(ld, fa, positive != 0, out);
+}
+}
+
+// ---- RANS point functions (turbulence.cuh) and the NT = 2 variants ---------------------------
+static Transport TransportFromCfg(const aither_cfg *c) {
+  Transport t;
+  t.tRef = c->tRef; t.viscC1 = c->suthViscC1[0]; t.viscS = c->suthViscS[0]; t.muRef = c->muMixRef;
+  t.condC1 = c->suthCondC1[0]; t.condS = c->suthCondS[0]; t.kRef = c->kMixRef;
+  t.scaling = c->nondimScaling; t.turbModel = c->turbModel;
+  return t;
+}
+extern "C" {
+void hs_eddy_visc(const aither_cfg *c, const double *s, const double *vg, const double *kg,
+                  const double *wg, double mu, double wallDist, double *out) {
+  EddyViscAndBlending(c->turbModel, c->nondimScaling, s[0], s[5], s[6], vg, kg, wg, mu, wallDist,
+                      &out[0], &out[1], &out[2]);
+}
+void hs_turb_source(const aither_cfg *c, const double *s, const double *vg, const double *kg,
+                    const double *wg, double mut, double f1, double *src) {
+  TurbSource(c->turbModel, c->nondimScaling, s[0], s[5], s[6], vg, kg, wg, mut, f1, src);
+}
+void hs_offdiag_scalar_rans(const aither_cfg *c, const double *s, const double *du,
+                            const double *fa, int positive, double mu, double mut, double f1,
+                            double dist, double *out) {
+  const Gas g = GasFromCfg(c);
+  const Transport tr = TransportFromCfg(c);
+  const double length = fa[3] / dist;
+  const double extra = length * ViscSpecFactor(tr, s[0], Gamma<1>(g, s), mu, mut);
+  const double extraT =
+      length * TurbViscSpecFactor(tr.turbModel, tr.scaling, s[0], s[5], s[6], mu, mut, f1);
+  OffDiagScalar<1, 2>(g, s, du, fa, positive != 0, out, extra, extraT);
+}
+void hs_ghost_state_rans(const aither_cfg *c, const double *interior, int bcType,
+                         const double *area, int surf, int tag, int layer, double *ghost) {
+  const Gas g = GasFromCfg(c);
+  const Transport tr = TransportFromCfg(c);
+  GhostState<1, 2>(g, interior, bcType, area, surf, *Find(c, tag), layer, ghost, &tr);
+}
+void hs_inviscid_flux_rans(const aither_cfg *c, const double *l, const double *r, const double *n,
+                           int fast, double *f) {
+  const Gas g = GasFromCfg(c);
+  if (c->invFlux == AITHER_FLUX_ROE) {
+    if (fast) RoeFluxFast<1, 2>(g, l, r, n, f);
+    else RoeFlux<1, 2>(g, l, r, n, f);
+  } else {
+    if (fast) InviscidFluxFast<1, 2, AITHER_FLUX_AUSM>(g, l, r, n, f);
+    else AusmFlux<1, 2>(g, l, r, n, f);
+  }
 }
 }

@@ -26,6 +26,7 @@ def hs():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
     out = os.path.join(HERE, "hostsim", "libhostsim.so")
     deps = [src, os.path.join(HERE, "..", "aither_b200", "csrc", "physics.cuh"),
+            os.path.join(HERE, "..", "aither_b200", "csrc", "turbulence.cuh"),
             os.path.join(HERE, "..", "include", "aither_gpu.h")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared",
@@ -184,3 +185,123 @@ def test_offdiag_fast_twin(hs):
             # absolute bar against the flux magnitude: both compute F(U+dU) - F(U) by cancellation
             scale = fa[3] * (np.abs(s).max() + 1.0)
             assert np.abs(a - b).max() <= 1e-14 * scale + 1e-12 * np.abs(a).max(), (a, b)
+
+
+# ---- RANS point functions (turbulence.cuh, NT = 2 variants of physics.cuh) ----------------------
+def rans_cfg(model):
+    """configuration of a committed RANS fixture (transport reference values included)"""
+    import goldencheck as gc
+    import refcase
+    cfg = refcase.cfg_from_dump(gc.load("box_sst"))
+    cfg.turbModel = model
+    return cfg
+
+
+def rand_rans_state(rng, mach=0.3):
+    s = np.empty(7)
+    s[:5] = rand_state(rng, mach)
+    s[5] = 10.0 ** rng.uniform(-8, -3)   # k / a_ref^2
+    s[6] = 10.0 ** rng.uniform(-4, 0)    # omega mu_ref / (rho_ref a_ref^2)
+    return s
+
+
+def declare_rans(hs, L):
+    D = C.c_double
+    hs.hs_eddy_visc.argtypes = [C.c_void_p, PD, PD, PD, PD, D, D, PD]
+    hs.hs_turb_source.argtypes = [C.c_void_p, PD, PD, PD, PD, D, D, PD]
+    hs.hs_offdiag_scalar_rans.argtypes = [C.c_void_p, PD, PD, PD, C.c_int, D, D, D, D, PD]
+    L.orc_eddy_visc.argtypes = [C.c_void_p, PD, PD, PD, PD, D, D, PD]
+    L.orc_turb_source.argtypes = [C.c_void_p, PD, PD, PD, PD, D, D, PD]
+    L.orc_offdiag_scalar_visc.argtypes = [C.c_void_p, PD, PD, PD, C.c_int, D, D, D, D, PD]
+    L.orc_ghost_state_visc.argtypes = [C.c_void_p, PD, C.c_int, PD, C.c_int, C.c_int, C.c_int, D, D,
+                                       PD]
+    for f in (hs.hs_eddy_visc, hs.hs_turb_source, hs.hs_offdiag_scalar_rans, L.orc_eddy_visc,
+              L.orc_turb_source, L.orc_offdiag_scalar_visc, L.orc_ghost_state_visc):
+        f.restype = None
+
+
+@pytest.mark.parametrize("model", [abi.TURB_KW_WILCOX, abi.TURB_SST])
+def test_eddy_viscosity_and_source(hs, model):
+    rng = np.random.default_rng(31 + model)
+    cfg = rans_cfg(model)
+    L = oracle.lib()
+    declare_rans(hs, L)
+    for trial in range(400):
+        s = rand_rans_state(rng)
+        vg = rng.normal(size=9) * 10.0 ** rng.uniform(-2, 3)
+        kg = rng.normal(size=3) * s[5] * 1e2
+        wg = rng.normal(size=3) * s[6] * 1e2
+        mu, wd = rng.uniform(0.5, 1.5), 10.0 ** rng.uniform(-5, 0)
+        a, b = np.empty(3), np.empty(3)
+        L.orc_eddy_visc(C.byref(cfg), ptr(s), ptr(vg), ptr(kg), ptr(wg), mu, wd, ptr(a))
+        hs.hs_eddy_visc(C.byref(cfg), ptr(s), ptr(vg), ptr(kg), ptr(wg), mu, wd, ptr(b))
+        assert np.all(np.abs(a - b) <= 1e-12 * np.maximum(np.abs(a), 1e-300) + 1e-15), (a, b)
+        sa, sb = np.empty(2), np.empty(2)
+        f1 = a[1]
+        L.orc_turb_source(C.byref(cfg), ptr(s), ptr(vg), ptr(kg), ptr(wg), a[0], f1, ptr(sa))
+        hs.hs_turb_source(C.byref(cfg), ptr(s), ptr(vg), ptr(kg), ptr(wg), a[0], f1, ptr(sb))
+        # production and destruction cancel: compare against the larger of the two magnitudes
+        scale = abs(sa) + s[0] * s[6] * np.array([s[5], s[6]]) / cfg.nondimScaling
+        assert np.all(np.abs(sa - sb) <= 1e-12 * scale), (trial, sa, sb)
+
+
+@pytest.mark.parametrize("model", [abi.TURB_KW_WILCOX, abi.TURB_SST])
+def test_offdiag_rans(hs, model):
+    rng = np.random.default_rng(41 + model)
+    cfg = rans_cfg(model)
+    L = oracle.lib()
+    declare_rans(hs, L)
+    for _ in range(300):
+        s, n = rand_rans_state(rng), unit(rng)
+        du = rng.normal(size=7) * 1e-2 * np.array([1, 1, 1, 1, 1, s[5], s[6]])
+        fa = np.concatenate([n, [rng.uniform(0.1, 2.0)]])
+        mu, mut, f1, dist = rng.uniform(0.5, 1.5), rng.uniform(0, 50), rng.uniform(0, 1), \
+            rng.uniform(1e-3, 1.0)
+        for pos in (0, 1):
+            a, b = np.empty(7), np.empty(7)
+            L.orc_offdiag_scalar_visc(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, mu, mut, f1, dist,
+                                      ptr(a))
+            hs.hs_offdiag_scalar_rans(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, mu, mut, f1, dist,
+                                      ptr(b))
+            assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a).max() + 1e-13 * np.abs(a)), (a, b)
+
+
+@pytest.mark.parametrize("bc,tag", [(abi.BC_SLIP_WALL, 0), (abi.BC_CHARACTERISTIC, 1),
+                                    (abi.BC_INLET, 1), (abi.BC_SUPERSONIC_INFLOW, 1),
+                                    (abi.BC_PRESSURE_OUTLET, 1), (abi.BC_SUPERSONIC_OUTFLOW, 0)])
+def test_ghost_state_rans(hs, bc, tag):
+    """farfield turbulence (turbulence intensity / eddy viscosity ratio) in the ghost states"""
+    rng = np.random.default_rng(43)
+    cfg = rans_cfg(abi.TURB_SST)
+    L = oracle.lib()
+    declare_rans(hs, L)
+    for trial in range(200):
+        mach = 0.3 if trial % 2 == 0 else 1.6
+        s, n = rand_rans_state(rng, mach), unit(rng)
+        for surf in (1, 2, 5):
+            for layer in (1, 2, 3):
+                a, b = np.empty(7), np.empty(7)
+                L.orc_ghost_state_visc(C.byref(cfg), ptr(s), bc, ptr(n), surf, tag, layer, 0.0, 0.0,
+                                       ptr(a))
+                hs.hs_ghost_state_rans(C.byref(cfg), ptr(s), bc, ptr(n), surf, tag, layer, ptr(b))
+                if not np.isfinite(a).all():
+                    continue
+                assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a) + 1e-14 * np.abs(a[:5]).max()), (a, b)
+
+
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_inviscid_flux_rans(hs, flux, fast):
+    rng = np.random.default_rng(47)
+    cfg = rans_cfg(abi.TURB_SST)
+    cfg.invFlux = abi.FLUX_ROE if flux == "roe" else abi.FLUX_AUSM
+    L = oracle.lib()
+    for trial in range(300):
+        mach = 0.3 if trial % 2 == 0 else 1.5
+        l, r, n = rand_rans_state(rng, mach), rand_rans_state(rng, mach), unit(rng)
+        a, b = np.empty(7), np.empty(7)
+        L.orc_inviscid_flux(C.byref(cfg), ptr(l), ptr(r), ptr(n), ptr(a))
+        hs.hs_inviscid_flux_rans(C.byref(cfg), ptr(l), ptr(r), ptr(n), fast, ptr(b))
+        assert np.all(np.abs(a[:5] - b[:5]) <= 3e-14 * np.abs(a[:5]).max()), (a, b)
+        tscale = np.maximum(np.abs(a[5:]), np.abs(a[0]) * np.maximum(l[5:], r[5:]))
+        assert np.all(np.abs(a[5:] - b[5:]) <= 1e-12 * tscale), (a, b)
