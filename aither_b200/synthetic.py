@@ -111,15 +111,29 @@ def centroids(x):
                     x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:])
 
 
-def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air"):
-    """cloud file with seed-fixed noise on the IC state at the given points (see write_cloud)"""
+def _cloud_values(n, seed, amplitude, turb):
+    """seed-fixed +-amplitude noise on rho, u, v, w, p (+ k, omega for RANS: farfield-like
+    k = 1.5 (0.01 |v|)^2, omega = rho k / (10 mu))"""
     rng = np.random.default_rng(seed)
     base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
-    vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((cen.shape[0], 5)) - 1.0))
+    vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((n, 5)) - 1.0))
+    kw = np.zeros((n, 2))
+    if turb is not None:
+        vmag = np.linalg.norm(IC["velocity"])
+        k0 = 1.5 * (0.01 * vmag) ** 2
+        mu0 = 1.458e-6 * REF_T ** 1.5 / (REF_T + 110.4)
+        w0 = IC["density"] * k0 / (10.0 * mu0)
+        kw = np.array([k0, w0])[None, :] * (1.0 + amplitude * (2.0 * rng.random((n, 2)) - 1.0))
+    return vals, kw
+
+
+def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air", turb=None):
+    """cloud file with seed-fixed noise on the IC state at the given points (see write_cloud)"""
+    vals, kw = _cloud_values(cen.shape[0], seed, amplitude, turb)
     with open(path, "w") as f:
         f.write("%d\n%s\n" % (cen.shape[0], species))
-        for c, v in zip(cen, vals):
-            f.write(" ".join("%.17g" % t for t in (*c, *v, 0.0, 0.0, 1.0)) + "\n")
+        for c, v, t in zip(cen, vals, kw):
+            f.write(" ".join("%.17g" % x for x in (*c, *v, *t, 1.0)) + "\n")
 
 
 def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None):
@@ -130,18 +144,7 @@ def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None):
     x = np.asarray(nodes)
     cen = 0.125 * (x[:-1, :-1, :-1] + x[:-1, :-1, 1:] + x[:-1, 1:, :-1] + x[:-1, 1:, 1:] +
                    x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:]).reshape(-1, 3)
-    rng = np.random.default_rng(seed)
-    base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
-    vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((cen.shape[0], 5)) - 1.0))
-    kw = np.zeros((cen.shape[0], 2))
-    if turb is not None:
-        # farfield-like turbulence: k = 1.5 (0.01 |v|)^2, omega = rho k / (10 mu), +- noise
-        vmag = np.linalg.norm(IC["velocity"])
-        k0 = 1.5 * (0.01 * vmag) ** 2
-        mu0 = 1.458e-6 * REF_T ** 1.5 / (REF_T + 110.4)
-        w0 = IC["density"] * k0 / (10.0 * mu0)
-        kw = np.array([k0, w0])[None, :] * (1.0 + amplitude *
-                                            (2.0 * rng.random((cen.shape[0], 2)) - 1.0))
+    vals, kw = _cloud_values(cen.shape[0], seed, amplitude, turb)
     with open(path, "w") as f:
         f.write("%d\n%s\n" % (cen.shape[0], species))
         for c, v, t in zip(cen, vals, kw):

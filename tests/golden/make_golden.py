@@ -67,6 +67,16 @@ CASES = {
                               edits={"equationSet": "euler", "turbulenceModel": "none",
                                      "iterations": "20",
                                      "initialConditions": "<icState(tag=-1; file=ic.dat)>"}),
+    # the shipped uniformFlow case itself: SST 2003, LU-SGS x2, 10 blocks / 8 orientations, from
+    # a perturbed state (turbulence included; CFL 20 instead of 1000, which diverges from such a
+    # state): pins the exchange of eddy viscosity and blending
+    # functions across connections (gridLevel::SwapEddyViscAndGradients, SwapTurbVars)
+    "uniformFlow_rans": dict(src="uniformFlow", iters=20, full=(0,), cloud=(19, 0.01),
+                             turb="sst2003",
+                             edits={"iterations": "20", "cflStart": "20", "cflMax": "20",
+                                    "initialConditions": "<icState(tag=-1; file=ic.dat)>"},
+                             drop=("diagRaw@", "temperature@", "state@it0.start", "x0@",
+                                   "velocityGrad@")),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
     # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,
@@ -105,7 +115,8 @@ def generate(name):
             if "cloud" in spec:  # perturbed initial state at every cell centroid of the grid
                 blocks = synthetic.read_plot3d(os.path.join(tmp, inp[:-4] + ".xyz"))
                 nodes = np.concatenate([synthetic.centroids(b).reshape(-1, 3) for b in blocks])
-                synthetic.write_cloud_points(os.path.join(tmp, "ic.dat"), nodes, *spec["cloud"])
+                synthetic.write_cloud_points(os.path.join(tmp, "ic.dat"), nodes, *spec["cloud"],
+                                             turb=spec.get("turb"))
         d = refcase.run_harness(tmp, inp, spec["iters"], full=spec["full"], geom=True)
     out = {k: np.asarray(v) for k, v in d.items()
            if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time" and

@@ -58,3 +58,12 @@ def test_oracle_shock_tube_bdf2_dual_time():
     d = gc.load("shockTube")
     gc.check_phases(oracle.OracleLevel, d, 0, TOL)
     assert gc.check_history(oracle.OracleLevel, d, 200, 1e-9) <= 1e-9
+
+
+def test_oracle_uniform_flow_rans():
+    """The shipped testCases/uniformFlow (SST 2003, LU-SGS x2, 10 blocks through all 8 patch
+    orientations) from a perturbed state: eddy viscosity / blending functions swapped across
+    connections and used by the implicit off-diagonals of the neighbouring block."""
+    d = gc.load("uniformFlow_rans")
+    gc.check_phases(oracle.OracleLevel, d, 0, dict(TOL, turb=1e-12))
+    assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
