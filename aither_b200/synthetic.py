@@ -45,7 +45,7 @@ def write_plot3d(path, blocks_nodes):
 
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
-             visc_recon="central", wall=None, turb=None):
+             visc_recon="central", wall=None, turb=None, jac="rusanov"):
     """`viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
     ("isothermal", T) or ("heatFlux", q)). `turb`: None, "kOmegaWilcox2006" or "sst2003" (RANS,
     implies viscous; farfield turbulence intensity 1 %, eddy viscosity ratio 10)."""
@@ -69,6 +69,7 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "faceReconstruction: %s" % recon,
         "limiter: %s" % limiter,
         "inviscidFlux: %s" % flux,
+        "inviscidFluxJacobian: %s" % jac,
         "iterations: %d" % iterations,
         "outputFrequency: 1000000",
         "outputVariables: <density, vel_x, vel_y, vel_z, pressure>",

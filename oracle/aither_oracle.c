@@ -13,6 +13,8 @@
 
 #define ORC_EPS 1.0e-30 /* ref: include/macros.hpp.in:21 */
 #define MAXEQ (AITHER_MAX_SPECIES + 6)
+#define MAXFS (AITHER_MAX_SPECIES + 4)
+#define MAXJAC (MAXFS * MAXFS + 4)
 
 typedef struct {
   int ni, nj, nk, g;
@@ -936,6 +938,8 @@ static void face_states(const orc_level *h, const orc_block *b, int d, int i,
 }
 
 /* ref: src/procBlock.cpp:384-491, :522-629, :660-767 (CalcInvFluxI/J/K) */
+static void rusanov_flux_jacobian(const orc_level *h, const double *s,
+                                  const double *area, int positive, double *J);
 static double turb_inv_cell_spec_rad(const orc_level *h, const double *s,
                                      const double *fL, const double *fR);
 static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
@@ -958,6 +962,12 @@ static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
           double *r = b->residual +
                       neq * pidx(b, ii - (d == 0), jj - (d == 1), kk - (d == 2));
           for (int e = 0; e < neq; ++e) r[e] += flux[e] * area[3];
+          if (h->cfg.isBlockMatrix) { /* ref: src/procBlock.cpp:452-457 */
+            double J[MAXJAC];
+            rusanov_flux_jacobian(h, fl, area, 1, J);
+            double *a = b->a + h->asz * pidx(b, ii - (d == 0), jj - (d == 1), kk - (d == 2));
+            for (int q = 0; q < h->asz; ++q) a[q] += J[q];
+          }
         }
         if (fi < nd) {
           double *r = b->residual + neq * pidx(b, ii, jj, kk);
@@ -979,6 +989,11 @@ static void calc_inv_flux(orc_level *h, orc_block *b, int d) {
             double *a = b->a + h->asz * pidx(b, ii, jj, kk);
             a[0] += sr;
             if (h->nt > 0) a[1] += tsr;
+          } else { /* ref: src/procBlock.cpp:481-486 */
+            double J[MAXJAC];
+            rusanov_flux_jacobian(h, fr, area, 0, J);
+            double *a = b->a + h->asz * pidx(b, ii, jj, kk);
+            for (int q = 0; q < h->asz; ++q) a[q] -= J[q];
           }
         }
       }
@@ -1434,7 +1449,7 @@ static double turb_src_spec_rad(const orc_level *h, const double *s, double vol)
  * :291-319), :617-661 (SST); BoussinesqReynoldsStress :55-70 */
 static void calc_turb_src(const orc_level *h, const double *s, const double vg[9],
                           const double kg[3], const double wg[3], double mut,
-                          double f1, double src[2]) {
+                          double f1, double src[2], double *betaOut) {
   const double scaling = h->cfg.nondimScaling, invScaling = 1.0 / scaling;
   const double rho = rho_of(h, s), tke = tke_of(h, s), omg = omega_of(h, s);
   const double trace = vg[0] + vg[4] + vg[8];
@@ -1465,6 +1480,7 @@ static void calc_turb_src(const orc_level *h, const double *s, const double vg[9
     const double xw = fabs(ddot_trans(vv, ski) / pow(KW_BETASTAR * omg, 3.0)) *
                       pow(scaling, 3.0);
     const double beta = KW_BETA0 * ((1.0 + 85.0 * xw) / (1.0 + 100.0 * xw));
+    *betaOut = beta;
     const double omgDest = invScaling * beta * (rho * omg * omg);
     double tkeProd = prodRaw > 0.0 ? prodRaw : 0.0;
     double omgProd = KW_GAMMA * omg / tke * tkeProd;
@@ -1479,6 +1495,7 @@ static void calc_turb_src(const orc_level *h, const double *s, const double vg[9
   const double cdkw = sst_cdkw(h, s, kg, wg);
   const double gamma = blended(SST_GAMMA1, SST_GAMMA2, f1);
   const double beta = blended(SST_BETA1, SST_BETA2, f1);
+  *betaOut = beta;
   const double tkeDest = invScaling * SST_BETASTAR * (rho * tke * omg * 1.0);
   const double omgDest = invScaling * beta * (rho * omg * omg);
   const double lim = SST_KPROD2DEST * tkeDest;
@@ -1501,6 +1518,11 @@ static void tau_normal(const double vg[9], const double n[3], double mu,
     tau[r] = lambda * trace * n[r] + (mu + mut) * mm;
   }
 }
+static double proj_c2c_dist(const orc_block *b, int d, int ii, int jj, int kk);
+static void approx_tsl_jacobian(const orc_level *h, const double *s, double lamVisc,
+                                double turbVisc, double f1, const double *area,
+                                double dist, int left, const double vGrad[9],
+                                double *J);
 /* ref: src/procBlock.cpp:1233-1497 (CalcViscFluxI; J, K alike); low-Re walls */
 static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
   const int neq = h->neq, ns = h->ns;
@@ -1577,6 +1599,15 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         if (fi > 0) {
           double *r = b->residual + neq * pidx(b, ii - di, jj - dj, kk - dk);
           for (int e = 0; e < neq; ++e) r[e] -= flux[e] * fa[3];
+          if (!rans)
+            for (int q = 0; q < 9; ++q) b->velGrad[9 * CL(-1) + q] += sixth * vg[q];
+          if (h->cfg.isBlockMatrix) { /* ref: src/procBlock.cpp:1420-1428 */
+            double J[MAXJAC];
+            approx_tsl_jacobian(h, state, mu, mut, f1, fa, proj_c2c_dist(b, d, ii, jj, kk), 1,
+                                vg, J);
+            double *a = b->a + h->asz * pidx(b, ii - di, jj - dj, kk - dk);
+            for (int q = 0; q < h->asz; ++q) a[q] -= J[q];
+          }
           if (rans) {
             const long c = CL(-1), pp = pidx(b, ii - di, jj - dj, kk - dk);
             for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
@@ -1592,6 +1623,8 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         if (fi < nd[d]) {
           double *r = b->residual + neq * pidx(b, ii, jj, kk);
           for (int e = 0; e < neq; ++e) r[e] += flux[e] * fa[3];
+          if (!rans)
+            for (int q = 0; q < 9; ++q) b->velGrad[9 * CL(0) + q] += sixth * vg[q];
           if (rans) {
             const long c = CL(0), pp = pidx(b, ii, jj, kk);
             for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
@@ -1626,6 +1659,12 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
             double *a = b->a + h->asz * pidx(b, ii, jj, kk);
             a[0] += 2.0 * vsr;
             if (rans) a[1] += 2.0 * tvsr;
+          } else { /* ref: src/procBlock.cpp:1481-1489 */
+            double J[MAXJAC];
+            approx_tsl_jacobian(h, state, mu, mut, f1, fa, proj_c2c_dist(b, d, ii, jj, kk), 0,
+                                vg, J);
+            double *a = b->a + h->asz * pidx(b, ii, jj, kk);
+            for (int q = 0; q < h->asz; ++q) a[q] += J[q];
           }
         }
 #undef CL
@@ -1641,12 +1680,26 @@ static void calc_src_terms(orc_level *h, orc_block *b) {
       for (int ii = 0; ii < b->ni; ++ii) {
         const long c = cidx(b, ii, jj, kk), pp = pidx(b, ii, jj, kk);
         const double *s = b->state + neq * c;
-        double src[2];
+        double src[2], beta = 0.0;
         calc_turb_src(h, s, b->velGrad + 9 * c, b->tkeGrad + 3 * pp, b->omegaGrad + 3 * pp,
-                      b->eddyVisc[c], b->f1[c], src);
+                      b->eddyVisc[c], b->f1[c], src, &beta);
         const double turbSpecRad = turb_src_spec_rad(h, s, b->vol[c]);
         b->specRad[2 * pp + 1] -= turbSpecRad;
-        if (!h->cfg.isBlockMatrix) b->a[h->asz * pp + 1] -= turbSpecRad;
+        if (!h->cfg.isBlockMatrix) {
+          b->a[h->asz * pp + 1] -= turbSpecRad;
+        } else { /* TurbSrcJac; ref: src/turbulence.cpp:445-458,706-720 */
+          const int fs = ns + 4;
+          const double invScaling = 1.0 / h->cfg.nondimScaling;
+          double *a = b->a + h->asz * pp + fs * fs;
+          const double j00 = is_sst(h)
+                                 ? -2.0 * SST_BETASTAR * omega_of(h, s) * 1.0 * b->vol[c] * invScaling
+                                 : -2.0 * KW_BETASTAR * omega_of(h, s) * b->vol[c] * invScaling;
+          const double j11 = -2.0 * beta * omega_of(h, s) * b->vol[c] * invScaling;
+          a[0] -= j00;
+          a[1] -= 0.0;
+          a[2] -= 0.0;
+          a[3] -= j11;
+        }
         double *r = b->residual + neq * pp;
         for (int e = 0; e < neq; ++e) {
           const double sv = e >= ns + 4 ? src[e - ns - 4] : 0.0;
@@ -1853,8 +1906,8 @@ void orc_calc_residual(orc_level *h) {
     const long np = (long)b->NI * b->NJ * b->NK;
     memset(b->residual, 0, sizeof(double) * nc * h->neq);
     memset(b->specRad, 0, sizeof(double) * nc * 2);
+    if (h->cfg.isViscous) memset(b->velGrad, 0, sizeof(double) * np * 9);
     if (is_rans(h)) { /* ResetGradients, ResetTurbVars; ref: src/procBlock.cpp:961-981 */
-      memset(b->velGrad, 0, sizeof(double) * np * 9);
       memset(b->tkeGrad, 0, sizeof(double) * nc * 3);
       memset(b->omegaGrad, 0, sizeof(double) * nc * 3);
       memset(b->eddyVisc, 0, sizeof(double) * np);
@@ -1874,6 +1927,7 @@ void orc_calc_residual(orc_level *h) {
       update_aux(h, b);
     }
   }
+  if (h->cfg.isViscous && !is_rans(h)) swap_connections(h, 5);
   if (is_rans(h)) {
     /* SwapEddyViscAndGradients, SwapTurbVars, then the source terms;
      * ref: src/gridLevel.cpp:386-399 */
@@ -1911,6 +1965,7 @@ static double sol_delta_n_coeff(const orc_level *h, const orc_block *b, int ii,
          (b->dt[pidx(b, ii, jj, kk)] * h->cfg.theta);
 }
 
+static void matrix_inverse(double *mat, int size);
 void orc_invert_diagonal(orc_level *h) {
   /* ref: src/linearSolver.cpp:146-188 (scalar diagonal) */
   for (int bb = 0; bb < h->nblk; ++bb) {
@@ -1923,6 +1978,20 @@ void orc_invert_diagonal(orc_level *h) {
           if (h->cfg.dualTimeCFL > 0.0) {
             const double *sp = b->specRad + 2 * p;
             diagVolTime += (sp[0] > sp[1] ? sp[0] : sp[1]) / h->cfg.dualTimeCFL;
+          }
+          if (h->cfg.isBlockMatrix) {
+            /* MultiplyOnDiagonal / AddOnDiagonal / Inverse of the flow and turbulence
+             * blocks; ref: include/matMultiArray3d.hpp:109-122 */
+            const int fs = h->ns + 4, nt = h->nt;
+            double *a = b->a + h->asz * p, *ai = b->ainv + h->asz * p;
+            for (int r = 0; r < fs; ++r) a[r * fs + r] *= h->cfg.matrixRelaxation;
+            for (int r = 0; r < nt; ++r) a[fs * fs + r * nt + r] *= h->cfg.matrixRelaxation;
+            for (int r = 0; r < fs; ++r) a[r * fs + r] += diagVolTime;
+            for (int r = 0; r < nt; ++r) a[fs * fs + r * nt + r] += diagVolTime;
+            memcpy(ai, a, sizeof(double) * h->asz);
+            matrix_inverse(ai, fs);
+            if (nt > 0) matrix_inverse(ai + fs * fs, nt);
+            continue;
           }
           for (int q = 0; q < h->asz; ++q) {
             b->a[h->asz * p + q] *= h->cfg.matrixRelaxation;
@@ -1955,8 +2024,15 @@ static void rhs_b(const orc_level *h, const orc_block *b, int ii, int jj,
   }
 }
 
+static void block_mult(const orc_level *h, const double *a, const double *v, double *out);
 static void diag_mult(const orc_level *h, const double *a, const double *v,
                       double *out) {
+  if (h->cfg.isBlockMatrix) {
+    double tmp[MAXEQ];
+    block_mult(h, a, v, tmp);
+    for (int e = 0; e < h->neq; ++e) out[e] = tmp[e];
+    return;
+  }
   /* scalar: ref include/fluxJacobian.hpp:67-73 */
   for (int e = 0; e < h->ns + 4; ++e) out[e] = v[e] * a[0];
   for (int e = h->ns + 4; e < h->neq; ++e) out[e] = v[e] * a[1];
@@ -1980,6 +2056,217 @@ void orc_initialize_matrix_update(orc_level *h) {
                     b->x + h->neq * cidx(b, ii, jj, kk));
         }
   }
+}
+
+/* ------------------------------------------------------------------------ */
+/* block flux Jacobians (blusgs / bdplur): flow block fs x fs row-major, then  */
+/* the turbulence block nt x nt (ref: include/fluxJacobian.hpp:62-75)          */
+static double energy_of(const orc_level *h, const double *s);
+/* fluxJacobian::InvFluxJacobian; ref: include/fluxJacobian.hpp:486-562 */
+static void inv_flux_jacobian(const orc_level *h, const double *s,
+                              const double *area, double *J) {
+  const int ns = h->ns, fs = ns + 4, nt = h->nt;
+  for (int q = 0; q < fs * fs + nt * nt; ++q) J[q] = 0.0;
+  const double *n = area;
+  const double u = s[ns], v = s[ns + 1], w = s[ns + 2];
+  const double velNorm = u * n[0] + v * n[1] + w * n[2];
+  double mf[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  const double gamma = gamma_of(h, s);
+  const double gm1 = gamma - 1.0;
+  const double phi = 0.5 * gm1 * (u * u + v * v + w * w);
+  const double a1 = gamma * energy_of(h, s) - phi;
+  const double a3 = gamma - 2.0;
+#define FJ(r, c) J[(r)*fs + (c)]
+  for (int ii = 0; ii < ns; ++ii) {
+    for (int jj = 0; jj < ns; ++jj)
+      FJ(ii, jj) = velNorm * ((ii == jj ? 1.0 : 0.0) - mf[ii]);
+    FJ(ii, ns + 0) = mf[ii] * n[0];
+    FJ(ii, ns + 1) = mf[ii] * n[1];
+    FJ(ii, ns + 2) = mf[ii] * n[2];
+    FJ(ns + 0, ii) = phi * n[0] - u * velNorm;
+    FJ(ns + 1, ii) = phi * n[1] - v * velNorm;
+    FJ(ns + 2, ii) = phi * n[2] - w * velNorm;
+    FJ(ns + 3, ii) = velNorm * (phi - a1);
+  }
+  FJ(ns + 0, ns) = velNorm - a3 * n[0] * u;
+  FJ(ns + 1, ns) = v * n[0] - gm1 * u * n[1];
+  FJ(ns + 2, ns) = w * n[0] - gm1 * u * n[2];
+  FJ(ns + 3, ns) = a1 * n[0] - gm1 * u * velNorm;
+  FJ(ns + 0, ns + 1) = u * n[1] - gm1 * v * n[0];
+  FJ(ns + 1, ns + 1) = velNorm - a3 * n[1] * v;
+  FJ(ns + 2, ns + 1) = w * n[1] - gm1 * v * n[2];
+  FJ(ns + 3, ns + 1) = a1 * n[1] - gm1 * v * velNorm;
+  FJ(ns + 0, ns + 2) = u * n[2] - gm1 * w * n[0];
+  FJ(ns + 1, ns + 2) = v * n[2] - gm1 * w * n[1];
+  FJ(ns + 2, ns + 2) = velNorm - a3 * n[2] * w;
+  FJ(ns + 3, ns + 2) = a1 * n[2] - gm1 * w * velNorm;
+  FJ(ns + 0, ns + 3) = gm1 * n[0];
+  FJ(ns + 1, ns + 3) = gm1 * n[1];
+  FJ(ns + 2, ns + 3) = gm1 * n[2];
+  FJ(ns + 3, ns + 3) = gamma * velNorm;
+#undef FJ
+  for (int q = 0; q < fs * fs; ++q) J[q] *= 0.5 * area[3];
+  if (nt > 0) { /* 0.5 * InviscidConvJacobian; ref: src/turbulence.cpp:126-136 */
+    const double diag = velNorm * area[3];
+    J[fs * fs + 0] = 0.5 * diag;
+    J[fs * fs + 3] = 0.5 * diag;
+  }
+}
+/* fluxJacobian::RusanovFluxJacobian; ref: include/fluxJacobian.hpp:446-483 */
+static void rusanov_flux_jacobian(const orc_level *h, const double *s,
+                                  const double *area, int positive, double *J) {
+  const int fs = h->ns + 4, nt = h->nt;
+  const double specRad = inv_face_spec_rad(h, s, area);
+  inv_flux_jacobian(h, s, area, J);
+  double D[MAXJAC];
+  for (int q = 0; q < fs * fs + nt * nt; ++q) D[q] = 0.0;
+  for (int r = 0; r < fs; ++r) D[r * fs + r] = 1.0 * specRad;
+  if (nt > 0) { /* 0.5 * InviscidDissJacobian; ref: src/turbulence.cpp:138-148 */
+    const double velNorm = dot3(s + h->ns, area);
+    const double diag = fabs(velNorm) * area[3];
+    D[fs * fs + 0] = 0.5 * diag;
+    D[fs * fs + 3] = 0.5 * diag;
+  }
+  for (int q = 0; q < fs * fs + nt * nt; ++q) J[q] = positive ? J[q] + D[q] : J[q] - D[q];
+}
+/* fluxJacobian::ApproxTSLJacobian; ref: include/fluxJacobian.hpp:664-758
+ * (DelprimitiveDelConservative :610-661, MatrixMultiply src/matrix.cpp:197-212) */
+static void approx_tsl_jacobian(const orc_level *h, const double *s, double lamVisc,
+                                double turbVisc, double f1, const double *area,
+                                double dist, int left, const double vGrad[9],
+                                double *J) {
+  const int ns = h->ns, fs = ns + 4, nt = h->nt;
+  double A[MAXFS * MAXFS], P[MAXFS * MAXFS];
+  for (int q = 0; q < fs * fs; ++q) A[q] = P[q] = 0.0;
+  for (int q = 0; q < fs * fs + nt * nt; ++q) J[q] = 0.0;
+  const double t = temperature_of(h, s);
+  const double mu = h->cfg.nondimScaling * lamVisc;
+  const double mut = h->cfg.nondimScaling * turbVisc;
+  const double *n = area;
+  const double u = s[ns], v = s[ns + 1], w = s[ns + 2];
+  const double velNorm = u * n[0] + v * n[1] + w * n[2];
+  double mf[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  const double rho = rho_of(h, s);
+  const double k = eff_conductivity(h, t);
+  const double kt = mut * cp_mix(h, mf) / turb_prandtl(h);
+  double tauNorm[3];
+  tau_normal(vGrad, n, mu, mut, tauNorm);
+  const double fac = left ? -1.0 : 1.0;
+  const double third = 1.0 / 3.0;
+  if (ns != 1) {
+    fprintf(stderr, "oracle: species diffusion jacobian is not restated (ns > 1)\n");
+    abort();
+  }
+#define FA(r, c) A[(r)*fs + (c)]
+  for (int ii = 0; ii < ns; ++ii) {
+    for (int jj = 0; jj < ns; ++jj)
+      FA(ii, jj) = 0.0 * ((ii == jj ? 1.0 : 0.0) - mf[ii]) / ((mu + mut) * rho);
+    const double speciesEnthalpy = FA(ii, ii) * 0.0;
+    FA(ns + 3, ii) = -(k + kt) * t / ((mu + mut) * rho) + speciesEnthalpy;
+  }
+  FA(ns + 0, ns) = third * n[0] * n[0] + 1.0;
+  FA(ns + 1, ns) = third * n[0] * n[1];
+  FA(ns + 2, ns) = third * n[0] * n[2];
+  FA(ns + 3, ns) = fac * 0.5 * dist / (mu + mut) * tauNorm[0] + third * n[0] * velNorm + u;
+  FA(ns + 0, ns + 1) = third * n[1] * n[0];
+  FA(ns + 1, ns + 1) = third * n[1] * n[1] + 1.0;
+  FA(ns + 2, ns + 1) = third * n[1] * n[2];
+  FA(ns + 3, ns + 1) = fac * 0.5 * dist / (mu + mut) * tauNorm[1] + third * n[1] * velNorm + v;
+  FA(ns + 0, ns + 2) = third * n[2] * n[0];
+  FA(ns + 1, ns + 2) = third * n[2] * n[1];
+  FA(ns + 2, ns + 2) = third * n[2] * n[2] + 1.0;
+  FA(ns + 3, ns + 2) = fac * 0.5 * dist / (mu + mut) * tauNorm[2] + third * n[2] * velNorm + w;
+  FA(ns + 3, ns + 3) = (k + kt) / ((mu + mut) * rho);
+#undef FA
+  for (int q = 0; q < fs * fs; ++q) A[q] *= area[3] * (mu + mut) / dist;
+  /* prim2Cons */
+  const double gm1 = gamma_of(h, s) - 1.0;
+  const double invRho = 1.0 / rho;
+#define FP(r, c) P[(r)*fs + (c)]
+  for (int ii = 0; ii < ns; ++ii) {
+    FP(ii, ii) = 1.0;
+    FP(ns + 0, ii) = -invRho * u;
+    FP(ns + 1, ii) = -invRho * v;
+    FP(ns + 2, ii) = -invRho * w;
+    FP(ns + 3, ii) = 0.5 * gm1 * (u * u + v * v + w * w);
+  }
+  FP(ns, ns) = invRho;
+  FP(ns + 3, ns) = -gm1 * u;
+  FP(ns + 1, ns + 1) = invRho;
+  FP(ns + 3, ns + 1) = -gm1 * v;
+  FP(ns + 2, ns + 2) = invRho;
+  FP(ns + 3, ns + 2) = -gm1 * w;
+  FP(ns + 3, ns + 3) = gm1;
+#undef FP
+  for (int cc = 0; cc < fs; ++cc)
+    for (int rr = 0; rr < fs; ++rr)
+      for (int ii = 0; ii < fs; ++ii) J[rr * fs + ii] += A[rr * fs + cc] * P[cc * fs + ii];
+  if (nt > 0) { /* fac * turbModel::ViscJac; ref: src/turbulence.cpp:485-498,768-781 */
+    const double length = area[3] / dist;
+    const double mt = is_sst(h) ? turbVisc : eddy_visc_no_lim(h, s);
+    J[fs * fs + 0] = fac * (h->cfg.nondimScaling * length / rho * (lamVisc + sigma_k(h, f1) * mt));
+    J[fs * fs + 3] = fac * (h->cfg.nondimScaling * length / rho * (lamVisc + sigma_w(h, f1) * mt));
+  }
+}
+/* squareMatrix inverse by Gauss-Jordan elimination with partial pivoting, the
+ * reference's operation order; ref: src/matrix.cpp:57-107 */
+static void matrix_inverse(double *mat, int size) {
+  double I[MAXFS * MAXFS];
+  for (int r = 0; r < size; ++r)
+    for (int c = 0; c < size; ++c) I[r * size + c] = r == c ? 1.0 : 0.0;
+  for (int cPivot = 0, r = 0; r < size; ++r, ++cPivot) {
+    double maxVal = 0.0;
+    int rPivot = 0;
+    for (int ii = r; ii <= size - 1; ++ii)
+      if (fabs(mat[ii * size + cPivot]) > maxVal) {
+        maxVal = fabs(mat[ii * size + cPivot]);
+        rPivot = ii;
+      }
+    if (r != rPivot)
+      for (int c = 0; c < size; ++c) {
+        double tmp = mat[r * size + c];
+        mat[r * size + c] = mat[rPivot * size + c];
+        mat[rPivot * size + c] = tmp;
+        tmp = I[r * size + c];
+        I[r * size + c] = I[rPivot * size + c];
+        I[rPivot * size + c] = tmp;
+      }
+    if (r != 0)
+      for (int ii = 0; ii < cPivot; ++ii) {
+        const double factor = mat[r * size + ii] / mat[ii * size + ii];
+        for (int c = 0; c < size; ++c) {
+          mat[r * size + c] = mat[r * size + c] - factor * mat[ii * size + c];
+          I[r * size + c] = I[r * size + c] - factor * I[ii * size + c];
+        }
+      }
+    if (mat[r * size + cPivot] == 0.0) {
+      fprintf(stderr, "oracle: singular matrix in Gauss-Jordan elimination\n");
+      abort();
+    }
+    const double normFactor = 1.0 / mat[r * size + cPivot];
+    for (int c = cPivot; c < size; ++c) mat[r * size + c] *= normFactor;
+    for (int c = 0; c < size; ++c) I[r * size + c] *= normFactor;
+  }
+  for (int cPivot = size - 2, r = size - 2; r >= 0; --r, --cPivot)
+    for (int ii = size - 1; ii > cPivot; --ii) {
+      const double factor = mat[r * size + ii];
+      for (int c = 0; c < size; ++c) {
+        mat[r * size + c] = mat[r * size + c] - factor * mat[ii * size + c];
+        I[r * size + c] = I[r * size + c] - factor * I[ii * size + c];
+      }
+    }
+  for (int q = 0; q < size * size; ++q) mat[q] = I[q];
+}
+/* block ArrayMult; ref: include/fluxJacobian.hpp:76-88 */
+static void block_mult(const orc_level *h, const double *a, const double *v, double *out) {
+  const int fs = h->ns + 4, nt = h->nt;
+  for (int e = 0; e < h->neq; ++e) out[e] = 0.0;
+  for (int rr = 0; rr < fs; ++rr)
+    for (int cc = 0; cc < fs; ++cc) out[rr] += a[rr * fs + cc] * v[cc];
+  for (int rr = 0; rr < nt; ++rr)
+    for (int cc = 0; cc < nt; ++cc) out[fs + rr] += a[fs * fs + rr * nt + cc] * v[fs + cc];
 }
 
 /* ref: src/fluxJacobian.cpp:122-162 (RusanovScalarOffDiagonal) */
@@ -2053,31 +2340,79 @@ static double proj_c2c_dist(const orc_block *b, int d, int ii, int jj, int kk) {
 static double visc_at(const orc_level *h, const orc_block *b, int ii, int jj, int kk) {
   return h->cfg.isViscous ? b->viscosity[cidx(b, ii, jj, kk)] : 0.0;
 }
+/* fluxJacobian.cpp OffDiagonal (:196-238): the product of one neighbour's off-diagonal block
+ * with its update, by the configured method */
+static void roe_flux(const orc_level *h, const double *l, const double *r,
+                     const double n[3], double *flux);
+static void offdiag_cell(const orc_level *h, const orc_block *b, long nb, long own,
+                         const double *x, const double *fArea, int positive, double dist,
+                         double *out) {
+  const int neq = h->neq;
+  const double *state = b->state + neq * nb, *du = x + neq * nb;
+  const double mu = h->cfg.isViscous ? b->viscosity[nb] : 0.0;
+  const double mut = b->eddyVisc[nb], f1 = b->f1[nb];
+  if (h->cfg.invFluxJac == AITHER_JAC_APPROX_ROE) {
+    /* RoeOffDiagonal; ref: src/fluxJacobian.cpp:240-296. The caller passes (.., f1, dist, ..)
+     * into parameters declared (.., dist, f1, ..) (:226-228 vs :243-244): inside, `dist` holds
+     * f1 and `f1` holds dist. Restated as is. */
+    const double distIn = f1, f1In = dist;
+    const double *diag = b->state + neq * own;
+    double oldFlux[MAXEQ], newFlux[MAXEQ], su[MAXEQ];
+    roe_flux(h, state, diag, fArea, oldFlux);
+    update_prim_with_cons(h, state, du, su);
+    if (positive) roe_flux(h, su, diag, fArea, newFlux);
+    else roe_flux(h, diag, su, fArea, newFlux);
+    double sr = 0.0, tsr = 0.0;
+    if (h->cfg.isViscous) {
+      const double rho = rho_of(h, state);
+      const double gam = gamma_of(h, state);
+      const double a43 = 4.0 / (3.0 * rho), gr = gam / rho;
+      const double maxTerm = a43 > gr ? a43 : gr;
+      const double viscTerm =
+          h->cfg.nondimScaling * (mu / prandtl_of(gam) + mut / turb_prandtl(h));
+      sr += fArea[3] / distIn * maxTerm * viscTerm;
+      if (h->nt > 0) tsr += turb_visc_spec_rad(h, state, fArea[3] / distIn, mu, mut, f1In);
+    }
+    for (int e = 0; e < neq; ++e) {
+      const double fc = fArea[3] * (newFlux[e] - oldFlux[e]);
+      const double srd = (e < h->ns + 4 ? sr : tsr) * du[e];
+      out[e] = positive ? fc + srd : fc - srd;
+    }
+    return;
+  }
+  if (h->cfg.isBlockMatrix) {
+    /* RusanovBlockOffDiagonal; ref: src/fluxJacobian.cpp:164-194 */
+    double J[MAXJAC], V[MAXJAC];
+    rusanov_flux_jacobian(h, state, fArea, positive, J);
+    if (h->cfg.isViscous) {
+      approx_tsl_jacobian(h, state, mu, mut, f1, fArea, dist, positive, b->velGrad + 9 * nb, V);
+      for (int q = 0; q < h->asz; ++q) J[q] = positive ? J[q] - V[q] : J[q] + V[q];
+    }
+    block_mult(h, J, du, out);
+    return;
+  }
+  offdiag_scalar(h, state, du, fArea, positive, mu, mut, f1, dist, out);
+}
 /* ref: src/procBlock.cpp:1056-1104 (ImplicitLower) */
 static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
                            int jj, int kk, const double *x, double *L) {
   const int neq = h->neq;
+  const long own = cidx(b, ii, jj, kk);
   double od[MAXEQ];
   for (int e = 0; e < neq; ++e) L[e] = 0.0;
   if (is_physical(b, ii - 1, jj, kk) || bc_is_connection(b, ii, jj, kk, 1)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii - 1, jj, kk),
-                   x + neq * cidx(b, ii - 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii, jj, kk), 1, visc_at(h, b, ii - 1, jj, kk), b->eddyVisc[cidx(b, ii - 1, jj, kk)], b->f1[cidx(b, ii - 1, jj, kk)],
-                   proj_c2c_dist(b, 0, ii, jj, kk), od);
+    offdiag_cell(h, b, cidx(b, ii - 1, jj, kk), own, x, b->fAI + 4 * fidxI(b, ii, jj, kk), 1,
+                 proj_c2c_dist(b, 0, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj - 1, kk) || bc_is_connection(b, ii, jj, kk, 3)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj - 1, kk),
-                   x + neq * cidx(b, ii, jj - 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1, visc_at(h, b, ii, jj - 1, kk), b->eddyVisc[cidx(b, ii, jj - 1, kk)], b->f1[cidx(b, ii, jj - 1, kk)],
-                   proj_c2c_dist(b, 1, ii, jj, kk), od);
+    offdiag_cell(h, b, cidx(b, ii, jj - 1, kk), own, x, b->fAJ + 4 * fidxJ(b, ii, jj, kk), 1,
+                 proj_c2c_dist(b, 1, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk - 1) || bc_is_connection(b, ii, jj, kk, 5)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk - 1),
-                   x + neq * cidx(b, ii, jj, kk - 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk), 1, visc_at(h, b, ii, jj, kk - 1), b->eddyVisc[cidx(b, ii, jj, kk - 1)], b->f1[cidx(b, ii, jj, kk - 1)],
-                   proj_c2c_dist(b, 2, ii, jj, kk), od);
+    offdiag_cell(h, b, cidx(b, ii, jj, kk - 1), own, x, b->fAK + 4 * fidxK(b, ii, jj, kk), 1,
+                 proj_c2c_dist(b, 2, ii, jj, kk), od);
     for (int e = 0; e < neq; ++e) L[e] += od[e];
   }
 }
@@ -2085,27 +2420,22 @@ static void implicit_lower(const orc_level *h, const orc_block *b, int ii,
 static void implicit_upper(const orc_level *h, const orc_block *b, int ii,
                            int jj, int kk, const double *x, double *U) {
   const int neq = h->neq;
+  const long own = cidx(b, ii, jj, kk);
   double od[MAXEQ];
   for (int e = 0; e < neq; ++e) U[e] = 0.0;
   if (is_physical(b, ii + 1, jj, kk) || bc_is_connection(b, ii + 1, jj, kk, 2)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii + 1, jj, kk),
-                   x + neq * cidx(b, ii + 1, jj, kk),
-                   b->fAI + 4 * fidxI(b, ii + 1, jj, kk), 0, visc_at(h, b, ii + 1, jj, kk), b->eddyVisc[cidx(b, ii + 1, jj, kk)], b->f1[cidx(b, ii + 1, jj, kk)],
-                   proj_c2c_dist(b, 0, ii + 1, jj, kk), od);
+    offdiag_cell(h, b, cidx(b, ii + 1, jj, kk), own, x, b->fAI + 4 * fidxI(b, ii + 1, jj, kk),
+                 0, proj_c2c_dist(b, 0, ii + 1, jj, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj + 1, kk) || bc_is_connection(b, ii, jj + 1, kk, 4)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj + 1, kk),
-                   x + neq * cidx(b, ii, jj + 1, kk),
-                   b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk), 0, visc_at(h, b, ii, jj + 1, kk), b->eddyVisc[cidx(b, ii, jj + 1, kk)], b->f1[cidx(b, ii, jj + 1, kk)],
-                   proj_c2c_dist(b, 1, ii, jj + 1, kk), od);
+    offdiag_cell(h, b, cidx(b, ii, jj + 1, kk), own, x, b->fAJ + 4 * fidxJ(b, ii, jj + 1, kk),
+                 0, proj_c2c_dist(b, 1, ii, jj + 1, kk), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
   if (is_physical(b, ii, jj, kk + 1) || bc_is_connection(b, ii, jj, kk + 1, 6)) {
-    offdiag_scalar(h, b->state + neq * cidx(b, ii, jj, kk + 1),
-                   x + neq * cidx(b, ii, jj, kk + 1),
-                   b->fAK + 4 * fidxK(b, ii, jj, kk + 1), 0, visc_at(h, b, ii, jj, kk + 1), b->eddyVisc[cidx(b, ii, jj, kk + 1)], b->f1[cidx(b, ii, jj, kk + 1)],
-                   proj_c2c_dist(b, 2, ii, jj, kk + 1), od);
+    offdiag_cell(h, b, cidx(b, ii, jj, kk + 1), own, x, b->fAK + 4 * fidxK(b, ii, jj, kk + 1),
+                 0, proj_c2c_dist(b, 2, ii, jj, kk + 1), od);
     for (int e = 0; e < neq; ++e) U[e] += od[e];
   }
 }
@@ -2326,7 +2656,8 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
   h->ns = cfg->numSpecies;
   h->nt = cfg->numTurb;
   h->neq = h->ns + 4 + h->nt;
-  h->asz = 1 + (h->nt > 0 ? 1 : 0); /* scalar diagonal: {flow, turb} */
+  h->asz = cfg->isBlockMatrix ? (h->ns + 4) * (h->ns + 4) + h->nt * h->nt
+                              : 1 + (h->nt > 0 ? 1 : 0); /* scalar: {flow, turb} */
   h->nblk = nBlocks;
   h->blk = (orc_block *)calloc(nBlocks, sizeof(orc_block));
   h->nconn = nConnections;
@@ -2479,7 +2810,8 @@ static void level_from_cfg(orc_level *h, const aither_cfg *cfg) {
   h->ns = cfg->numSpecies;
   h->nt = cfg->numTurb;
   h->neq = h->ns + 4 + h->nt;
-  h->asz = 1 + (h->nt > 0 ? 1 : 0);
+  h->asz = cfg->isBlockMatrix ? (h->ns + 4) * (h->ns + 4) + h->nt * h->nt
+                              : 1 + (h->nt > 0 ? 1 : 0);
 }
 void orc_inviscid_flux(const aither_cfg *cfg, const double *left,
                        const double *right, const double nrm[3], double *flux) {
@@ -2514,8 +2846,9 @@ void orc_turb_source(const aither_cfg *cfg, const double *state, const double vg
                      const double kg[3], const double wg[3], double mut, double f1,
                      double src[2]) {
   orc_level h;
+  double beta;
   level_from_cfg(&h, cfg);
-  calc_turb_src(&h, state, vg, kg, wg, mut, f1, src);
+  calc_turb_src(&h, state, vg, kg, wg, mut, f1, src, &beta);
 }
 void orc_offdiag_scalar_visc(const aither_cfg *cfg, const double *stateNb, const double *duNb,
                              const double fArea[4], int positive, double mu, double mut,

@@ -67,6 +67,20 @@ CASES = {
                               edits={"equationSet": "euler", "turbulenceModel": "none",
                                      "iterations": "20",
                                      "initialConditions": "<icState(tag=-1; file=ic.dat)>"}),
+    # block-matrix solvers (full flux Jacobians on the diagonal, Gauss-Jordan inverse, block
+    # off-diagonals): BDPLUR on the Euler box, BLU-SGS on a laminar box (thin-shear-layer viscous
+    # Jacobian) and on the SST box (2x2 turbulence blocks, source Jacobian)
+    "box_bdplur": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="bdplur", sweeps=3), iters=12,
+                       full=(0, 4)),
+    "box_blusgs_visc": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="blusgs", sweeps=2,
+                                           limiter="vanAlbada", viscous=True, size=2e-5),
+                            iters=12, full=(0, 4)),
+    "box_sst_blusgs": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="blusgs", sweeps=2,
+                                          turb="sst2003", limiter="vanAlbada", size=1e-3),
+                           iters=12, full=(0,)),
+    # approximateRoe flux Jacobian (off-diagonals as Roe-flux changes), Euler, LU-SGS x2
+    "box_roe_jac": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                       jac="approximateRoe"), iters=12, full=(0, 4)),
     # the shipped uniformFlow case itself: SST 2003, LU-SGS x2, 10 blocks / 8 orientations, from
     # a perturbed state (turbulence included; CFL 20 instead of 1000, which diverges from such a
     # state): pins the exchange of eddy viscosity and blending
