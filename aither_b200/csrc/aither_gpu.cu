@@ -66,6 +66,7 @@ struct HostBlock {
   int globalPos = 0;
   long long paddedCells = 0;
   dim3 cellGrid, cellBlock;       // cell-parallel kernels (32 x 8 threads)
+  dim3 cell128Grid;               // register-heavy cell-parallel kernels (32 x 4 threads)
   dim3 resGrid, resBlock;
   int nCellBlocks = 0;
   // plane-marching kernels (march.cuh)
@@ -103,6 +104,8 @@ struct aither_gpu {
   size_t stageBytes = 0;
   long long launches = 0;
   bool keepMatrixResid = false;
+  int jac = kJacScalar;            // JacKind of the implicit matrix
+  int *dFlag = nullptr;            // set by PrepBlockKernel on a singular diagonal block
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
   bool tmaImplicit = true;         // AITHER_B200_KERNELS=march: register-fed implicit sweep
   bool fusePrep = true;            // AITHER_B200_FUSE_PREP=0: separate PrepKernel (A/B runs)
@@ -216,8 +219,14 @@ bool Supported(const aither_cfg &c, std::string *why) {
   }
   if (c.isViscous && c.viscRecon != 0 && c.viscRecon != 1) { *why = "unknown viscous face reconstruction"; return false; }
   if (c.isViscous && c.numGhosts < 2) { *why = "viscous fluxes need at least 2 ghost layers"; return false; }
-  if (c.isBlockMatrix) { *why = "block-matrix solvers (blusgs/bdplur) are not built in this round"; return false; }
-  if (c.invFluxJac != AITHER_JAC_RUSANOV) { *why = "approximateRoe flux jacobian is not built in this round"; return false; }
+  if (c.invFluxJac != AITHER_JAC_RUSANOV && c.invFluxJac != AITHER_JAC_APPROX_ROE) { *why = "unknown inviscid flux jacobian"; return false; }
+  if (c.invFluxJac == AITHER_JAC_APPROX_ROE && (c.isViscous || c.isBlockMatrix)) {
+    // RoeOffDiagonal receives (f1, dist) in swapped positions (reference src/fluxJacobian.cpp:226-228
+    // vs :243-244) and divides the viscous spectral radius by f1 = 0 for laminar flow
+    *why = "approximateRoe is built for inviscid runs with a scalar diagonal only (the reference's "
+           "viscous branch divides by zero)";
+    return false;
+  }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
   return true;
 }
@@ -246,8 +255,8 @@ void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fus
 template <int NS, int NT>
 int LaunchResidual(aither_gpu *h, HostBlock &hb, int fusePrep, double cfl) {
   const aither_cfg &c = h->cfg;
-  const int implicitScalar = 1;
-  if (h->legacyKernels) fusePrep = 0;
+  const int implicitScalar = h->jac == kJacBlock ? 0 : 1;
+  if (h->legacyKernels || h->jac == kJacBlock) fusePrep = 0;
   ScopedLaunch sl(h, kFamResidual);
 #define RES(RC, LM, FX) LaunchResidualOne<NS, NT, RC, LM, FX>(h, hb, implicitScalar, fusePrep, cfl)
 #define RES_FLUX(RC, LM)                         \
@@ -305,10 +314,30 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
 }
 
 template <int NS, int NT>
-void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t stream) {
-  if constexpr (NT > 0) {
-    RansCellKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1);
+void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t stream, bool block) {
+  if (block) {
+    RansCellKernel<NS, NT, true><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 0);
+  } else {
+    if constexpr (NT > 0) {
+      RansCellKernel<NS, NT, false><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1);
+    }
   }
+}
+
+// inviscid part of the block diagonal, same reconstruction as the residual
+template <int NS, int NT>
+void LaunchBlockDiagInv(aither_gpu *h, HostBlock &hb) {
+  const aither_cfg &c = h->cfg;
+  const BlockDev &b = hb.dev;
+  const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk), blk(32, 4, 1);
+#define BDI(RC, LM) BlockDiagInvKernel<NS, NT, RC, LM><<<grid, blk, 0, h->stream>>>(b, h->params)
+  if (c.recon == AITHER_RECON_CONSTANT) BDI(AITHER_RECON_CONSTANT, AITHER_LIMITER_NONE);
+  else if (c.recon == AITHER_RECON_MUSCL) {
+    if (c.limiter == AITHER_LIMITER_NONE) BDI(AITHER_RECON_MUSCL, AITHER_LIMITER_NONE);
+    else if (c.limiter == AITHER_LIMITER_VAN_ALBADA) BDI(AITHER_RECON_MUSCL, AITHER_LIMITER_VAN_ALBADA);
+    else BDI(AITHER_RECON_MUSCL, AITHER_LIMITER_MINMOD);
+  } else BDI(AITHER_RECON_WENO, AITHER_LIMITER_NONE);
+#undef BDI
 }
 
 int ZeroResult(aither_gpu *h, int slot) {
@@ -330,21 +359,28 @@ int EnsureResults(aither_gpu *h, int n) {
 
 // ---- phases (all asynchronous on h->stream) ---------------------------------------------------
 int Exchange(aither_gpu *h, int which) {
-  // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update)
+  // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update),
+  // src/procBlock.cpp:3064-3085 (eddy viscosity + f1 + f2: three contiguous fields; velocity gradient)
   if (h->halo.nConn == 0) return 0;
-  HaloFields f;
-  for (size_t bb = 0; bb < h->blocks.size(); ++bb) {
-    const BlockDev &b = h->blocks[bb].dev;
-    f.base[bb] = which == kHaloState ? b.state : (which == kHaloUpdate ? b.x : b.eddyVisc);
-    f.fs[bb] = b.fs;
+  const int total = which == kHaloTurb ? 3 : (which == kHaloVelGrad ? 9 : h->neq);
+  for (int done = 0; done < total;) {
+    const int nc = std::min(total - done, h->neq);  // the plan's buffers hold neq components
+    HaloFields f;
+    for (size_t bb = 0; bb < h->blocks.size(); ++bb) {
+      const BlockDev &b = h->blocks[bb].dev;
+      double *base = which == kHaloState ? b.state
+                     : which == kHaloUpdate ? b.x
+                     : which == kHaloTurb ? b.eddyVisc : b.velGrad;
+      f.base[bb] = base + static_cast<long long>(done) * b.fs;
+      f.fs[bb] = b.fs;
+    }
+    ScopedLaunch sl(h, kFamHalo);
+    h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
+    h->famLaunches[kFamHalo]--;
+    if (HaloExchange(h->halo, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
+      return Fail(HaloError());
+    done += nc;
   }
-  ScopedLaunch sl(h, kFamHalo);
-  h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
-  h->famLaunches[kFamHalo]--;
-  // kHaloTurb: eddy viscosity, f1, f2 (three contiguous fields; ref src/procBlock.cpp:3064-3085)
-  const int nc = which == kHaloTurb ? 3 : h->neq;
-  if (HaloExchange(h->halo, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
-    return Fail(HaloError());
   return 0;
 }
 
@@ -375,7 +411,14 @@ int PhaseBoundaryConditionsT(aither_gpu *h) {
 
 template <int NS, int NT>
 int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
-  for (auto &hb : h->blocks) LaunchResidual<NS, NT>(h, hb, fusePrep, cfl);
+  const bool block = h->jac == kJacBlock;
+  for (auto &hb : h->blocks) {
+    LaunchResidual<NS, NT>(h, hb, fusePrep, cfl);
+    if (block) {
+      ScopedLaunch sl(h, kFamResidual);
+      LaunchBlockDiagInv<NS, NT>(h, hb);
+    }
+  }
   CK(cudaGetLastError());
   if (!h->cfg.isViscous) return 0;
   // ref: src/procBlock.cpp:6125-6137
@@ -398,11 +441,12 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
       const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
       AuxKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
     }
-    if (NT > 0) {
-      // RANS: viscous + turbulent fluxes, cell averages, spectral radii and source terms per cell
+    if (NT > 0 || block) {
+      // RANS and / or block matrix: viscous (+ turbulent) fluxes, cell averages, spectral radii,
+      // source terms and the thin-shear-layer Jacobians, per cell
       ScopedLaunch sl(h, kFamViscFlux);
       const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
-      LaunchRansCell<NS, NT>(b, h->params, grid, h->stream);
+      LaunchRansCell<NS, NT>(b, h->params, grid, h->stream, block);
       continue;
     }
     {
@@ -420,6 +464,8 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
   // eddy viscosity and blending functions of the cells across connections
   // (gridLevel::SwapEddyViscAndGradients / SwapTurbVars, ref src/gridLevel.cpp:386-392)
   if (NT > 0 && Exchange(h, kHaloTurb)) return 1;
+  // the block off-diagonals read the neighbour's velocity gradient (SwapEddyViscAndGradientSlice)
+  if (block && Exchange(h, kHaloVelGrad)) return 1;
   return 0;
 }
 
@@ -427,7 +473,14 @@ template <int NS, int NT>
 int PhasePrepT(aither_gpu *h, double cfl, int bits) {
   for (auto &hb : h->blocks) {
     ScopedLaunch sl(h, kFamPrep);
-    PrepKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
+    if (h->jac == kJacBlock) {
+      const BlockDev &b = hb.dev;
+      const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
+      PrepBlockKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, h->params, cfl, bits,
+                                                                     h->dFlag);
+    } else {
+      PrepKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
+    }
   }
   CK(cudaGetLastError());
   return 0;
@@ -438,8 +491,9 @@ int SwapUpdate(aither_gpu *h) {
   return Exchange(h, kHaloUpdate);
 }
 
-template <int NS, int NT>
-int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
+template <int NS, int NT, int JAC>
+int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
+  constexpr bool kCell = NT > 0 || JAC != kJacScalar;  // cell-parallel implicit kernels
   const bool fullGSAlways = h->cfg.matrixRequiresInit != 0;
   for (int s = 0; s < sweeps; ++s) {
     if (SwapUpdate(h)) return 1;
@@ -447,9 +501,13 @@ int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
       for (auto &hb : h->blocks) {
         {
           ScopedLaunch sl(h, kFamDplur);
-          if (h->legacyKernels || NT > 0) {
-            DplurKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
-                                                                            hb.dev.x, hb.dev.xalt);
+          if (h->legacyKernels || kCell) {
+            if (JAC == kJacScalar)
+              DplurKernel<NS, NT, JAC><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
+                  hb.dev, h->params, hb.dev.x, hb.dev.xalt);
+            else
+              DplurKernel<NS, NT, JAC><<<hb.cell128Grid, dim3(32, 4, 1), 0, h->stream>>>(
+                  hb.dev, h->params, hb.dev.x, hb.dev.xalt);
           } else if (h->tmaImplicit) {
             LaunchImplicitTma<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           } else {
@@ -466,7 +524,7 @@ int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
         const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
         for (int pl = 0; pl <= b.ni + b.nj + b.nk - 3; ++pl) {
           ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<NS, NT, true><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+          LusgsPlaneKernel<NS, NT, true, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
         }
       }
       if (SwapUpdate(h)) return 1;
@@ -476,7 +534,7 @@ int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
         const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
         for (int pl = b.ni + b.nj + b.nk - 3; pl >= 0; --pl) {
           ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<NS, NT, false><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+          LusgsPlaneKernel<NS, NT, false, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
         }
       }
     }
@@ -488,9 +546,15 @@ int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
     int nPartials = hb.nCellBlocks;
     {
       ScopedLaunch sl(h, kFamAxmb);
-      if (h->legacyKernels || NT > 0) {
-        AxmbKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
-            hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
+      if (h->legacyKernels || kCell) {
+        if (JAC == kJacScalar) {
+          AxmbKernel<NS, NT, JAC><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(
+              hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
+        } else {
+          AxmbKernel<NS, NT, JAC><<<hb.cell128Grid, dim3(32, 4, 1), 0, h->stream>>>(
+              hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
+          nPartials = hb.cell128Grid.x * hb.cell128Grid.y * hb.cell128Grid.z;
+        }
       } else if (h->tmaImplicit) {
         LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
         nPartials = hb.nTmaBlocks;
@@ -507,6 +571,15 @@ int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
   }
   CK(cudaGetLastError());
   return 0;
+}
+
+template <int NS, int NT>
+int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
+  if (h->jac == kJacBlock) return PhaseRelaxJ<NS, NT, kJacBlock>(h, sweeps, slot);
+  if constexpr (NT == 0) {
+    if (h->jac == kJacRoe) return PhaseRelaxJ<NS, NT, kJacRoe>(h, sweeps, slot);
+  }
+  return PhaseRelaxJ<NS, NT, kJacScalar>(h, sweeps, slot);
 }
 
 template <int NS, int NT>
@@ -580,7 +653,7 @@ int IterateAsync(aither_gpu *h, double cfl, int slot, int mm) {
   if (ZeroResult(h, slot)) return 1;
   if (PhaseBoundaryConditions(h)) return 1;
   // inviscid: time step, diagonal, right-hand side and x0 ride in the residual kernel's epilogue
-  const bool fuse = !h->legacyKernels && h->fusePrep && !h->cfg.isViscous;
+  const bool fuse = !h->legacyKernels && h->fusePrep && !h->cfg.isViscous && h->jac != kJacBlock;
   if (PhaseResidual(h, fuse ? 1 : 0, cfl)) return 1;
   if (!fuse && PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
   if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
@@ -588,11 +661,21 @@ int IterateAsync(aither_gpu *h, double cfl, int slot, int mm) {
   return 0;
 }
 
+int CheckFlag(aither_gpu *h) {
+  if (h->jac != kJacBlock) return 0;
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, h->dFlag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (flag != 0)  // the reference exits (src/matrix.cpp:83-86); here the call fails
+    return Fail("singular diagonal block in the Gauss-Jordan inverse");
+  return 0;
+}
+
 int FetchResults(aither_gpu *h, int n) {
   CK(cudaMemcpyAsync(h->hResults, h->dResults, sizeof(IterResult) * n, cudaMemcpyDeviceToHost,
                      h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return CheckFlag(h);
 }
 
 void FreeAll(aither_gpu *h) {
@@ -607,6 +690,7 @@ void FreeAll(aither_gpu *h) {
   }
   HaloDestroy(h->halo);
   if (h->dBcStates) cudaFree(h->dBcStates);
+  if (h->dFlag) cudaFree(h->dFlag);
   if (h->dPartials) cudaFree(h->dPartials);
   if (h->dLinfPartials) cudaFree(h->dLinfPartials);
   if (h->dResults) cudaFree(h->dResults);
@@ -648,7 +732,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   h->ns = cfg->numSpecies;
   h->nt = cfg->numTurb;
   h->neq = h->ns + 4 + h->nt;
-  h->asz = 1 + (h->nt > 0 ? 1 : 0);  // scalar diagonal {flow, turbulence}
+  h->jac = cfg->isBlockMatrix ? kJacBlock
+                              : (cfg->invFluxJac == AITHER_JAC_APPROX_ROE ? kJacRoe : kJacScalar);
+  // scalar diagonal {flow, turbulence}, or the (ns + 4)^2 flow block + nt^2 turbulence block
+  h->asz = cfg->isBlockMatrix ? (h->ns + 4) * (h->ns + 4) + h->nt * h->nt : 1 + (h->nt > 0 ? 1 : 0);
   Params &p = h->params;
   for (int s = 0; s < AITHER_MAX_SPECIES; ++s) {
     p.gas.R[s] = cfg->gasConstant[s];
@@ -709,6 +796,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->evStart));
   CKC(cudaEventCreate(&h->evStop));
+  CKC(cudaMalloc(&h->dFlag, sizeof(int)));
+  CKC(cudaMemset(h->dFlag, 0, sizeof(int)));
   CKC(cudaMalloc(&h->dBcStates, sizeof(aither_bc_state) * AITHER_MAX_BC_STATES));
   CKC(cudaMemcpy(h->dBcStates, cfg->bcStates, sizeof(aither_bc_state) * AITHER_MAX_BC_STATES,
                  cudaMemcpyHostToDevice));
@@ -740,7 +829,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
-                        (h->nt > 0 ? 18 : 0);
+                        (h->nt > 0 ? 18 : ((cfg->isViscous && cfg->isBlockMatrix) ? 9 : 0));
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
@@ -770,6 +859,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
     }
+    if (h->nt == 0 && cfg->isViscous && cfg->isBlockMatrix) b.velGrad = take(9);
     if (h->nt > 0) {
       b.eddyVisc = take(1);
       b.f1 = take(1);
@@ -910,6 +1000,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.cellBlock = dim3(32, 8, 1);
     hb.cellGrid = dim3((d.ni + 31) / 32, (d.nj + 7) / 8, d.nk);
     hb.nCellBlocks = hb.cellGrid.x * hb.cellGrid.y * hb.cellGrid.z;
+    hb.cell128Grid = dim3((d.ni + 31) / 32, (d.nj + 3) / 4, d.nk);
     hb.resBlock = dim3(kTI, kTJ, kTK);
     hb.resGrid = dim3((d.ni + 1 + kTI - 1) / kTI, (d.nj + 1 + kTJ - 1) / kTJ,
                       (d.nk + 1 + kTK - 1) / kTK);
@@ -945,7 +1036,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
         return 1;
       }
     }
-    maxCellBlocks = std::max<size_t>(maxCellBlocks, std::max(hb.nCellBlocks, hb.nTmaBlocks));
+    maxCellBlocks = std::max<size_t>(
+        maxCellBlocks, std::max<size_t>(std::max(hb.nCellBlocks, hb.nTmaBlocks),
+                                        static_cast<size_t>(hb.cell128Grid.x) * hb.cell128Grid.y *
+                                            hb.cell128Grid.z));
   }
   h->partialsCap = maxCellBlocks;
   CKC(cudaMalloc(&h->dPartials, sizeof(double) * maxCellBlocks * (AITHER_MAX_SPECIES + 6)));
@@ -1056,7 +1150,7 @@ int aither_gpu_invert_diagonal(aither_gpu *h) {
   CK(cudaSetDevice(h->device));
   if (PhasePrep(h, 0.0, kPrepDiag)) return 1;
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return CheckFlag(h);
 }
 int aither_gpu_initialize_matrix_update(aither_gpu *h) {
   if (!h) return Fail("null handle");

@@ -20,6 +20,7 @@
 #include "layout.cuh"
 #include "physics.cuh"
 #include "turbulence.cuh"
+#include "blockjac.cuh"
 
 namespace aither {
 
@@ -429,11 +430,59 @@ __device__ __forceinline__ void NeighbourViscTerms(const BlockDev &b, const Para
                                           __ldg(b.f1 + nidx));
 }
 
-template <int NS, int NT, bool LOWER, bool UPPER>
+// implicit-matrix flavour: scalar diagonal + Rusanov flux-change off-diagonals (lusgs / dplur),
+// full block Jacobians (blusgs / bdplur), or scalar diagonal + Roe flux-change off-diagonals
+// (inviscidFluxJacobian: approximateRoe); ref: src/fluxJacobian.cpp:196-238 (OffDiagonal)
+enum JacKind { kJacScalar = 0, kJacBlock = 1, kJacRoe = 2 };
+
+// one neighbour's off-diagonal product; `own` = state of the cell being updated (Roe only)
+template <int NS, int NT, int JAC>
+__device__ __forceinline__ void OffDiagOne(const BlockDev &b, const Params &p, const double *sn,
+                                           const double *dun, const double *own, const double *fa,
+                                           bool positive, long long nidx, double dist,
+                                           double *od) {
+  using E = Eq<NS, NT>;
+  if (JAC == kJacBlock) {
+    // RusanovBlockOffDiagonal; ref: src/fluxJacobian.cpp:164-194
+    double J[Blk<NS, NT>::n];
+    RusanovFluxJacobian<NS, NT>(p.gas, sn, fa, positive, J);
+    if (p.isViscous) {
+      double V[Blk<NS, NT>::n], vg[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) vg[q] = __ldg(b.velGrad + q * b.fs + nidx);
+      const double mut = NT > 0 ? __ldg(b.eddyVisc + nidx) : 0.0;
+      const double f1 = NT > 0 ? __ldg(b.f1 + nidx) : 0.0;
+      ApproxTslJacobian<NS, NT>(p.gas, p.tr, sn, __ldg(b.viscosity + nidx), mut, f1, fa, dist,
+                                positive, vg, V);
+#pragma unroll
+      for (int q = 0; q < Blk<NS, NT>::n; ++q) J[q] = positive ? J[q] - V[q] : J[q] + V[q];
+    }
+    BlockMult<NS, NT>(J, dun, od);
+  } else if (JAC == kJacRoe) {
+    // RoeOffDiagonal; ref: src/fluxJacobian.cpp:240-296. Its caller passes (.., f1, dist, ..) into
+    // parameters declared (.., dist, f1, ..), so for viscous flow the reference divides by f1 = 0;
+    // only the inviscid use is built (aither_gpu_create refuses approximateRoe + viscous).
+    double oldFlux[E::neq], newFlux[E::neq], su[E::neq];
+    RoeFlux<NS, NT>(p.gas, sn, own, fa, oldFlux);
+    UpdatePrimWithCons<NS, NT>(p.gas, sn, dun, su);
+    if (positive) RoeFlux<NS, NT>(p.gas, su, own, fa, newFlux);
+    else RoeFlux<NS, NT>(p.gas, own, su, fa, newFlux);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) od[e] = fa[3] * (newFlux[e] - oldFlux[e]);
+  } else {
+    double extra = 0.0, extraT = 0.0;
+    if (p.isViscous) NeighbourViscTerms<NS, NT>(b, p, sn, nidx, fa[3] / dist, &extra, &extraT);
+    OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, positive, od, extra, extraT);
+  }
+}
+
+template <int NS, int NT, bool LOWER, bool UPPER, int JAC = kJacScalar>
 __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
                                              const double *__restrict__ x, int i, int j, int k,
                                              long long idx, double *L, double *U) {
   using E = Eq<NS, NT>;
+  double own[E::neq];
+  if (JAC == kJacRoe) LoadCell<E::neq>(b.state, b.fs, idx, own);
   const int c[3] = {i, j, k};
   const int nd[3] = {b.ni, b.nj, b.nk};
 #pragma unroll
@@ -452,11 +501,8 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx - st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx);
-        double extra = 0.0, extraT = 0.0;
-        if (p.isViscous)
-          NeighbourViscTerms<NS, NT>(b, p, sn, idx - st, fa[3] / __ldg(b.dist[d] + idx), &extra,
-                                     &extraT);
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, true, od, extra, extraT);
+        OffDiagOne<NS, NT, JAC>(b, p, sn, dun, own, fa, true, idx - st,
+                                p.isViscous ? __ldg(b.dist[d] + idx) : 1.0, od);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) L[e] += od[e];
       }
@@ -468,11 +514,8 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
         LoadCell<E::neq>(x, b.fs, idx + st, dun);
 #pragma unroll
         for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx + st);
-        double extra = 0.0, extraT = 0.0;
-        if (p.isViscous)
-          NeighbourViscTerms<NS, NT>(b, p, sn, idx + st, fa[3] / __ldg(b.dist[d] + idx + st),
-                                     &extra, &extraT);
-        OffDiagScalar<NS, NT>(p.gas, sn, dun, fa, false, od, extra, extraT);
+        OffDiagOne<NS, NT, JAC>(b, p, sn, dun, own, fa, false, idx + st,
+                                p.isViscous ? __ldg(b.dist[d] + idx + st) : 1.0, od);
 #pragma unroll
         for (int e = 0; e < E::neq; ++e) U[e] += od[e];
       }
@@ -480,9 +523,41 @@ __device__ __forceinline__ void OffDiagonals(const BlockDev &b, const Params &p,
   }
 }
 
+// out = M v with M the cell's diagonal (or inverse) in `field`: {flow, turbulence} scalars, or
+// the flow block fs x fs followed by the turbulence block NT x NT
+// (ArrayMultiplication, ref: include/fluxJacobian.hpp:50-88)
+template <int NS, int NT, int JAC>
+__device__ __forceinline__ void DiagMult(const double *__restrict__ field, long long fs,
+                                         long long idx, const double *v, double *out) {
+  using E = Eq<NS, NT>;
+  if (JAC == kJacBlock) {
+    constexpr int nf = Blk<NS, NT>::fs;
+#pragma unroll
+    for (int rr = 0; rr < nf; ++rr) {
+      double acc = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < nf; ++cc) acc += __ldg(field + (rr * nf + cc) * fs + idx) * v[cc];
+      out[rr] = acc;
+    }
+#pragma unroll
+    for (int rr = 0; rr < NT; ++rr) {
+      double acc = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NT; ++cc)
+        acc += __ldg(field + (nf * nf + rr * NT + cc) * fs + idx) * v[nf + cc];
+      out[nf + rr] = acc;
+    }
+  } else {
+    const double dF = __ldg(field + idx);
+    const double dT = NT > 0 ? __ldg(field + fs + idx) : 0.0;
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) out[e] = v[e] * (e < NS + 4 ? dF : dT);
+  }
+}
+
 // K6 DPLUR (Jacobi) sweep: xout = D^-1 (b + L(xin) - U(xin)); ref: src/linearSolver.cpp:473-507
-template <int NS, int NT>
-__global__ void __launch_bounds__(256)
+template <int NS, int NT, int JAC = kJacScalar>
+__global__ void __launch_bounds__(JAC == kJacScalar ? 256 : 128)
     DplurKernel(BlockDev b, Params p, const double *__restrict__ xin, double *__restrict__ xout) {
   using E = Eq<NS, NT>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,20 +565,18 @@ __global__ void __launch_bounds__(256)
   const int k = blockIdx.z;
   if (i >= b.ni || j >= b.nj) return;
   const long long idx = CellIdx(b, i, j, k);
-  double L[E::neq], U[E::neq];
-  OffDiagonals<NS, NT, true, true>(b, p, xin, i, j, k, idx, L, U);
-  const double dinvF = __ldg(b.dinv + idx);
-  const double dinvT = NT > 0 ? __ldg(b.dinv + b.fs + idx) : 0.0;
+  double L[E::neq], U[E::neq], rhs[E::neq], xn[E::neq];
+  OffDiagonals<NS, NT, true, true, JAC>(b, p, xin, i, j, k, idx, L, U);
 #pragma unroll
-  for (int e = 0; e < E::neq; ++e) {
-    const double rb = __ldg(b.rhs + e * b.fs + idx);
-    xout[e * b.fs + idx] = ((rb + 0.0) + (L[e] - U[e])) * (e < NS + 4 ? dinvF : dinvT);
-  }
+  for (int e = 0; e < E::neq; ++e) rhs[e] = (__ldg(b.rhs + e * b.fs + idx) + 0.0) + (L[e] - U[e]);
+  DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, rhs, xn);
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) xout[e * b.fs + idx] = xn[e];
 }
 
 // K7 LU-SGS along one i+j+k hyperplane; ref: src/linearSolver.cpp:341-428. Cells of a plane do
 // not couple, so any order inside the plane reproduces the reference's lexicographic result.
-template <int NS, int NT, bool FORWARD>
+template <int NS, int NT, bool FORWARD, int JAC = kJacScalar>
 __global__ void __launch_bounds__(128)
     LusgsPlaneKernel(BlockDev b, Params p, int plane, int fullGS) {
   using E = Eq<NS, NT>;
@@ -513,39 +586,166 @@ __global__ void __launch_bounds__(128)
   const int i = plane - j - k;
   if (i < 0 || i >= b.ni) return;
   const long long idx = CellIdx(b, i, j, k);
-  const double dinvF = __ldg(b.dinv + idx);
-  const double dinvT = NT > 0 ? __ldg(b.dinv + b.fs + idx) : 0.0;
-#define dinv (e < NS + 4 ? dinvF : dinvT)
-  double L[E::neq], U[E::neq];
+  double L[E::neq], U[E::neq], rhs[E::neq], xn[E::neq];
   if (FORWARD) {
     if (fullGS) {
-      OffDiagonals<NS, NT, true, true>(b, p, b.x, i, j, k, idx, L, U);
+      OffDiagonals<NS, NT, true, true, JAC>(b, p, b.x, i, j, k, idx, L, U);
     } else {
-      OffDiagonals<NS, NT, true, false>(b, p, b.x, i, j, k, idx, L, U);
+      OffDiagonals<NS, NT, true, false, JAC>(b, p, b.x, i, j, k, idx, L, U);
     }
 #pragma unroll
-    for (int e = 0; e < E::neq; ++e) {
-      const double rb = __ldg(b.rhs + e * b.fs + idx);
-      b.x[e * b.fs + idx] = (rb + (L[e] - U[e])) * dinv;
-    }
+    for (int e = 0; e < E::neq; ++e) rhs[e] = __ldg(b.rhs + e * b.fs + idx) + (L[e] - U[e]);
+    DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, rhs, xn);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = xn[e];
   } else {
     if (fullGS) {
-      OffDiagonals<NS, NT, true, true>(b, p, b.x, i, j, k, idx, L, U);
+      OffDiagonals<NS, NT, true, true, JAC>(b, p, b.x, i, j, k, idx, L, U);
 #pragma unroll
-      for (int e = 0; e < E::neq; ++e) {
-        const double rb = __ldg(b.rhs + e * b.fs + idx);
-        b.x[e * b.fs + idx] = ((rb + L[e]) - U[e]) * dinv;
-      }
+      for (int e = 0; e < E::neq; ++e) rhs[e] = (__ldg(b.rhs + e * b.fs + idx) + L[e]) - U[e];
+      DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, rhs, xn);
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = xn[e];
     } else {
-      OffDiagonals<NS, NT, false, true>(b, p, b.x, i, j, k, idx, L, U);
+      OffDiagonals<NS, NT, false, true, JAC>(b, p, b.x, i, j, k, idx, L, U);
+      DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, U, xn);
 #pragma unroll
       for (int e = 0; e < E::neq; ++e) {
         const double xo = b.x[e * b.fs + idx];
-        b.x[e * b.fs + idx] = xo - U[e] * dinv;
+        b.x[e * b.fs + idx] = xo - xn[e];
       }
     }
   }
-#undef dinv
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-matrix diagonal (blusgs / bdplur).
+// face state reconstructed from this cell's side towards its lower (UPPER_FACE = false: the
+// face's "upper" state) or upper face (the face's "lower" state) -- the very expressions of
+// FaceStates (march.cuh), one side only; ref: src/procBlock.cpp:399-431
+template <int NS, int NT, int RECON, int LIM, bool UPPER_FACE>
+__device__ __forceinline__ void OneSidedFaceState(const BlockDev &b, const Params &p, int d,
+                                                  long long idx, double *out) {
+  using E = Eq<NS, NT>;
+  const long long st = Stride(b, d);
+  if (RECON == AITHER_RECON_CONSTANT) {
+    LoadCell<E::neq>(b.state, b.fs, idx, out);
+  } else if (RECON == AITHER_RECON_MUSCL) {
+    const double cLo = __ldg(b.mc[d] + idx), cHi = __ldg(b.mc[d] + b.fs + idx);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) {
+      const double um = __ldg(b.state + e * b.fs + idx - st), u0 = __ldg(b.state + e * b.fs + idx),
+                   up = __ldg(b.state + e * b.fs + idx + st);
+      out[e] = UPPER_FACE ? Muscl1<LIM>(um, u0, up, p.kappa, cHi, cLo)
+                          : Muscl1<LIM>(up, u0, um, p.kappa, cLo, cHi);
+    }
+  } else {
+    double w[5];
+#pragma unroll
+    for (int o = 0; o < 5; ++o)
+      w[o] = __ldg(b.cw[d] + idx + (UPPER_FACE ? (o - 2) : (2 - o)) * st);
+    const WenoGeom g = WenoSetup(w);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) {
+      double y[5];
+#pragma unroll
+      for (int o = 0; o < 5; ++o)
+        y[o] = __ldg(b.state + e * b.fs + idx + (UPPER_FACE ? (o - 2) : (2 - o)) * st);
+      out[e] = p.wenoZ ? Weno1<true>(g, y[0], y[1], y[2], y[3], y[4])
+                       : Weno1<false>(g, y[0], y[1], y[2], y[3], y[4]);
+    }
+  }
+}
+
+// inviscid part of the block diagonal: for i, j, k: A -= dF_Ur(upper state of the lower face),
+// A += dF_Ul(lower state of the upper face); ref: src/procBlock.cpp:447-486
+template <int NS, int NT, int RECON, int LIM>
+__global__ void __launch_bounds__(128) BlockDiagInvKernel(BlockDev b, Params p) {
+  using B = Blk<NS, NT>;
+  using E = Eq<NS, NT>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double A[B::n], J[B::n], fsd[E::neq], fa[4];
+#pragma unroll
+  for (int q = 0; q < B::n; ++q) A[q] = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const long long st = Stride(b, d);
+    OneSidedFaceState<NS, NT, RECON, LIM, false>(b, p, d, idx, fsd);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx);
+    RusanovFluxJacobian<NS, NT>(p.gas, fsd, fa, false, J);
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) A[q] -= J[q];
+    OneSidedFaceState<NS, NT, RECON, LIM, true>(b, p, d, idx, fsd);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + idx + st);
+    RusanovFluxJacobian<NS, NT>(p.gas, fsd, fa, true, J);
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) A[q] += J[q];
+  }
+#pragma unroll
+  for (int q = 0; q < B::n; ++q) b.diag[q * b.fs + idx] = A[q];
+}
+
+// K5 for the block diagonal: time step; D <- relax on the diagonal entries + V(1+zeta)/(dt theta)
+// [+ max(lambda)/CFL_dual]; D^-1 by the reference's Gauss-Jordan; b and x0 = D^-1 b
+// (ref: src/linearSolver.cpp:111-188, include/matMultiArray3d.hpp:109-122)
+template <int NS, int NT>
+__global__ void __launch_bounds__(128)
+    PrepBlockKernel(BlockDev b, Params p, double cfl, int bits, int *__restrict__ singular) {
+  using B = Blk<NS, NT>;
+  using E = Eq<NS, NT>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  const double vol = __ldg(b.vol + idx);
+  const double srMax = fmax(b.specRad[idx], b.specRad[b.fs + idx]);
+  double dt;
+  if (bits & kPrepDt) {
+    dt = p.dtNondim > 0.0 ? p.dtNondim : cfl * (vol / srMax);
+    b.dt[idx] = dt;
+  } else {
+    dt = b.dt[idx];
+  }
+  if (bits & kPrepDiag) {
+    double diagVolTime = (vol * (1.0 + p.zeta)) / (dt * p.theta);
+    if (p.dualTimeCFL > 0.0) diagVolTime += srMax / p.dualTimeCFL;
+    double A[B::n];
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) A[q] = b.diag[q * b.fs + idx];
+#pragma unroll
+    for (int r = 0; r < B::fs; ++r) {
+      A[r * B::fs + r] *= p.relax;
+      A[r * B::fs + r] += diagVolTime;
+    }
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      A[B::nf + r * NT + r] *= p.relax;
+      A[B::nf + r * NT + r] += diagVolTime;
+    }
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) b.diag[q * b.fs + idx] = A[q];
+    bool ok = MatrixInverse<B::fs>(A);
+    if (NT > 0) ok = MatrixInverse<(NT > 0 ? NT : 1)>(A + B::nf) && ok;
+    if (!ok) *singular = 1;  // the reference exits here (src/matrix.cpp:83-86)
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) b.dinv[q * b.fs + idx] = A[q];
+  }
+  if (bits & kPrepInit) {
+    double s[E::neq], rb[E::neq], x0[E::neq];
+    LoadCell<E::neq>(b.state, b.fs, idx, s);
+    RhsB<NS, NT>(b, p, idx, s, vol, dt, rb);
+    StoreCell<E::neq>(b.rhs, b.fs, idx, rb);
+    DiagMult<NS, NT, kJacBlock>(b.dinv, b.fs, idx, rb, x0);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = p.matrixRequiresInit ? x0[e] : 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -580,8 +780,8 @@ __device__ __forceinline__ void BlockSumToPartials(double *vals, double *partial
 
 // K8 matrix residual f - (A x - (L - U) - b) and its sum of squares;
 // ref: src/linearSolver.cpp:58-109, src/mgSolution.cpp:198-206
-template <int NS, int NT>
-__global__ void __launch_bounds__(256)
+template <int NS, int NT, int JAC = kJacScalar>
+__global__ void __launch_bounds__(JAC == kJacScalar ? 256 : 128)
     AxmbKernel(BlockDev b, Params p, double *__restrict__ partials, int storeField) {
   using E = Eq<NS, NT>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,15 +790,15 @@ __global__ void __launch_bounds__(256)
   double sq = 0.0;
   if (i < b.ni && j < b.nj) {
     const long long idx = CellIdx(b, i, j, k);
-    double L[E::neq], U[E::neq];
-    OffDiagonals<NS, NT, true, true>(b, p, b.x, i, j, k, idx, L, U);
-    const double aF = __ldg(b.diag + idx);
-    const double aT = NT > 0 ? __ldg(b.diag + b.fs + idx) : 0.0;
+    double L[E::neq], U[E::neq], xc[E::neq], ax[E::neq];
+    OffDiagonals<NS, NT, true, true, JAC>(b, p, b.x, i, j, k, idx, L, U);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) xc[e] = b.x[e * b.fs + idx];
+    DiagMult<NS, NT, JAC>(b.diag, b.fs, idx, xc, ax);
 #pragma unroll
     for (int e = 0; e < E::neq; ++e) {
       const double rb = __ldg(b.rhs + e * b.fs + idx);
-      const double ax = b.x[e * b.fs + idx] * (e < NS + 4 ? aF : aT);
-      const double mr = 0.0 - ((ax - (L[e] - U[e])) - rb);
+      const double mr = 0.0 - ((ax[e] - (L[e] - U[e])) - rb);
       if (storeField) b.mres[e * b.fs + idx] = mr;
       sq += mr * mr;
     }

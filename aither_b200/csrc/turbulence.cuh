@@ -112,7 +112,7 @@ AITHER_HD double TurbSrcSpecRad(double scaling, double omega, double vol) {
 // FBeta, Xw :291-319), :617-661 (SST); BoussinesqReynoldsStress :55-70
 AITHER_HD void TurbSource(int turbModel, double scaling, double rho, double tke, double omega,
                           const double *vg, const double *kg, const double *wg, double mut,
-                          double f1, double *src) {
+                          double f1, double *src, double *betaOut = nullptr) {
   const double invScaling = 1.0 / scaling;
   const double trace = vg[0] + vg[4] + vg[8];
   const double lambda = 0.0 - (2.0 / 3.0) * mut;
@@ -147,6 +147,7 @@ AITHER_HD void TurbSource(int turbModel, double scaling, double rho, double tke,
     const double bw = kw::betaStar * omega;
     const double xw = fabs(DDotTrans(vv, ski) / (bw * bw * bw)) * (scaling * scaling * scaling);
     const double beta = kw::beta0 * ((1.0 + 85.0 * xw) / (1.0 + 100.0 * xw));
+    if (betaOut) *betaOut = beta;
     const double omgDest = invScaling * beta * (rho * omega * omega);
     const double tkeProd = fmax(prodRaw, 0.0);
     const double omgProd = fmax(kw::gamma * omega / tke * tkeProd, 0.0);
@@ -160,6 +161,7 @@ AITHER_HD void TurbSource(int turbModel, double scaling, double rho, double tke,
   const double cdkw = SstCdkw(rho, omega, kg, wg);
   const double gamma = Blended(sst::gamma1, sst::gamma2, f1);
   const double beta = Blended(sst::beta1, sst::beta2, f1);
+  if (betaOut) *betaOut = beta;
   const double tkeDest = invScaling * sst::betaStar * (rho * tke * omega);
   const double omgDest = invScaling * beta * (rho * omega * omega);
   const double tkeProd = fmax(fmin(prodRaw, sst::kProd2Dest * tkeDest), 0.0);

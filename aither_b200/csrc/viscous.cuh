@@ -484,6 +484,7 @@ struct FaceOut {
   double flux[NEQ];  // viscous flux * |A| (species rows are 0 for one species)
   double mut, f1, f2;
   double vg[9], kg[3], wg[3];
+  double st[NEQ], mu;  // face state and laminar viscosity (thin-shear-layer Jacobian)
 };
 
 template <int NS, int NT, int D>
@@ -491,6 +492,7 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
                                          FaceOut<NS + 4 + NT> &o) {
   using E = Eq<NS, NT>;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
+  constexpr int NG = NT > 0 ? 6 : 4;
   const long long sd = Stride(b, D);
   const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
   double al[3][3], au[3][3];
@@ -518,11 +520,13 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
   }
   const double vol = 0.5 * (__ldg(b.vol + idx - sd) + __ldg(b.vol + idx));
   const double invVol = 1.0 / vol;
-  // u, v, w, T, k, omega on the six faces of the control volume, then Green-Gauss
+  // u, v, w, T (, k, omega) on the six faces of the control volume, then Green-Gauss
   // (ref: src/procBlock.cpp:5190-5352, src/utility.cpp:59-175)
   double grad[6][3];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
+  for (int r = 0; r < 3; ++r) grad[4][r] = grad[5][r] = 0.0;
+#pragma unroll
+  for (int c = 0; c < NG; ++c) {
     const double *f = c < 3 ? b.state + (NS + c) * b.fs
                             : (c == 3 ? b.temperature : b.state + (E::it + c - 4) * b.fs);
     const double lo = __ldg(f + idx - sd), hi = __ldg(f + idx);
@@ -584,8 +588,13 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
   for (int t = 0; t < NT; ++t) fs_[E::it + t] = fmax(fs_[E::it + t], kTurbMin);  // LimitTurb
   if (wDist < 0.0 && wDist > -1.0e-10) wDist = 0.0;  // WALL_DIST_NEG_TOL
   const double rho = SpeciesSum<NS>(fs_);
-  EddyViscAndBlending(p.tr.turbModel, p.tr.scaling, rho, fs_[E::it], fs_[iw], o.vg, o.kg, o.wg, mu,
-                      wDist, &o.mut, &o.f1, &o.f2);
+  o.mut = o.f1 = o.f2 = 0.0;
+  if (NT > 0)
+    EddyViscAndBlending(p.tr.turbModel, p.tr.scaling, rho, fs_[E::it], fs_[iw], o.vg, o.kg, o.wg,
+                        mu, wDist, &o.mut, &o.f1, &o.f2);
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) o.st[e] = fs_[e];
+  o.mu = mu;
   // viscousFlux::CalcFlux (src/viscousFlux.cpp:58-135), TauNormal (src/utility.cpp:425-437)
   double n[3];
 #pragma unroll
@@ -610,17 +619,19 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
                     (kcond + kt) * (grad[3][0] * n[0] + grad[3][1] * n[1] + grad[3][2] * n[2]) + 0.0;
   // k and omega diffusion; k-omega 2006 uses the unlimited eddy viscosity here
   // (ref: src/viscousFlux.cpp:117-134, include/turbulence.hpp:439)
-  const double mutt = IsSst(p.tr.turbModel) ? muts : p.tr.scaling * (rho * fs_[E::it] / fs_[iw]);
-  const double fk = (mus + TurbSigmaK(p.tr.turbModel, o.f1) * mutt) * Dot3(o.kg, n);
-  const double fw = (mus + TurbSigmaW(p.tr.turbModel, o.f1) * mutt) * Dot3(o.wg, n);
 #pragma unroll
   for (int q = 0; q < NS; ++q) o.flux[q] = 0.0;
   o.flux[E::imx] = tau[0] * mag;
   o.flux[E::imy] = tau[1] * mag;
   o.flux[E::imz] = tau[2] * mag;
   o.flux[E::ie] = fe * mag;
-  o.flux[E::it] = fk * mag;
-  o.flux[iw] = fw * mag;
+  if (NT > 0) {
+    const double mutt = IsSst(p.tr.turbModel) ? muts : p.tr.scaling * (rho * fs_[E::it] / fs_[iw]);
+    const double fk = (mus + TurbSigmaK(p.tr.turbModel, o.f1) * mutt) * Dot3(o.kg, n);
+    const double fw = (mus + TurbSigmaW(p.tr.turbModel, o.f1) * mutt) * Dot3(o.wg, n);
+    o.flux[E::it] = fk * mag;
+    o.flux[iw] = fw * mag;
+  }
 }
 
 template <int NS, int NT>
@@ -630,10 +641,10 @@ struct RansAcc {
   double mut, f1, f2, vg[9], kg[3], wg[3];
 };
 
-template <int NS, int NT, int D>
+template <int NS, int NT, int D, bool BLOCK>
 __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Params &p, long long idx,
                                                   const double *s, double visc, double vol,
-                                                  RansAcc<NS, NT> &a) {
+                                                  RansAcc<NS, NT> &a, double *dblk) {
   using E = Eq<NS, NT>;
   constexpr double sixth = 1.0 / 6.0;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
@@ -659,17 +670,36 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
     const double rho = SpeciesSum<NS>(s);
     const double length = fMag * fMag / vol;
     const double vsr = ViscSpecFactor(p.tr, rho, Gamma<NS>(p.gas, s), visc, mutLo) * length;
-    const double tvsr = TurbViscSpecFactor(p.tr.turbModel, p.tr.scaling, rho, s[E::it], s[iw], visc,
-                                           mutLo, f1Lo) * length;
+    const double tvsr = NT > 0 ? TurbViscSpecFactor(p.tr.turbModel, p.tr.scaling, rho, s[E::it],
+                                                    s[iw], visc, mutLo, f1Lo) * length
+                               : 0.0;
     a.sr += vsr * p.viscCFLCoeff;
     a.srT += tvsr * p.viscCFLCoeff;
     a.dg += 2.0 * vsr;
     a.dgT += 2.0 * tvsr;
   }
+  if (BLOCK) {  // + dFv/dU of the lower face (left = false); ref: src/procBlock.cpp:1481-1489
+    double fa[4], J[Blk<NS, NT>::n];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[D] + q * b.fs + idx);
+    ApproxTslJacobian<NS, NT>(p.gas, p.tr, f.st, f.mu, f.mut, f.f1, fa, __ldg(b.dist[D] + idx), false,
+                              f.vg, J);
+#pragma unroll
+    for (int q = 0; q < Blk<NS, NT>::n; ++q) dblk[q] += J[q];
+  }
   // upper face: this cell is the face's lower cell (ref: :1392-1429)
   RansFace<NS, NT, D>(b, p, idx + sd, f);
 #pragma unroll
   for (int e = NS; e < E::neq; ++e) a.r[e] -= f.flux[e];
+  if (BLOCK) {  // - dFv/dU of the upper face (left = true); ref: src/procBlock.cpp:1420-1428
+    double fa[4], J[Blk<NS, NT>::n];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[D] + q * b.fs + idx + sd);
+    ApproxTslJacobian<NS, NT>(p.gas, p.tr, f.st, f.mu, f.mut, f.f1, fa, __ldg(b.dist[D] + idx + sd),
+                              true, f.vg, J);
+#pragma unroll
+    for (int q = 0; q < Blk<NS, NT>::n; ++q) dblk[q] -= J[q];
+  }
 #pragma unroll
   for (int q = 0; q < 9; ++q) a.vg[q] += sixth * f.vg[q];
 #pragma unroll
@@ -682,10 +712,11 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
   a.f2 += sixth * f.f2;
 }
 
-template <int NS, int NT>
+template <int NS, int NT, bool BLOCK>
 __global__ void __launch_bounds__(128)
     RansCellKernel(BlockDev b, Params p, int implicitScalar) {
   using E = Eq<NS, NT>;
+  using B = Blk<NS, NT>;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -697,47 +728,66 @@ __global__ void __launch_bounds__(128)
   const double visc = __ldg(b.viscosity + idx);
   const double vol = __ldg(b.vol + idx);
   RansAcc<NS, NT> a;
+  double dblk[BLOCK ? B::n : 1];
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) a.r[e] = b.resid[e * b.fs + idx];
   a.sr = b.specRad[idx];
   a.srT = b.specRad[b.fs + idx];
   a.dg = implicitScalar ? b.diag[idx] : 0.0;
-  a.dgT = implicitScalar ? b.diag[b.fs + idx] : 0.0;
+  a.dgT = (implicitScalar && NT > 0) ? b.diag[b.fs + idx] : 0.0;
+  if (BLOCK) {
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) dblk[q] = b.diag[q * b.fs + idx];
+  }
   a.mut = a.f1 = a.f2 = 0.0;
 #pragma unroll
   for (int q = 0; q < 9; ++q) a.vg[q] = 0.0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) a.kg[q] = a.wg[q] = 0.0;
-  RansAccumulateDir<NS, NT, 0>(b, p, idx, s, visc, vol, a);
-  RansAccumulateDir<NS, NT, 1>(b, p, idx, s, visc, vol, a);
-  RansAccumulateDir<NS, NT, 2>(b, p, idx, s, visc, vol, a);
-  // source terms (ref: src/procBlock.cpp:5956-6025, src/source.cpp:64-82)
-  double src[2];
-  const double rho = SpeciesSum<NS>(s);
-  TurbSource(p.tr.turbModel, p.tr.scaling, rho, s[E::it], s[iw], a.vg, a.kg, a.wg, a.mut, a.f1, src);
-  const double turbSpecRad = TurbSrcSpecRad(p.tr.scaling, s[iw], vol);
-  a.srT -= turbSpecRad;
-  a.dgT -= turbSpecRad;
-  a.r[E::it] -= src[0] * vol;
-  a.r[iw] -= src[1] * vol;
+  RansAccumulateDir<NS, NT, 0, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
+  RansAccumulateDir<NS, NT, 1, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
+  RansAccumulateDir<NS, NT, 2, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
+  if (NT > 0) {
+    // source terms (ref: src/procBlock.cpp:5956-6025, src/source.cpp:64-82)
+    double src[2], beta = 0.0;
+    const double rho = SpeciesSum<NS>(s);
+    TurbSource(p.tr.turbModel, p.tr.scaling, rho, s[E::it], s[iw], a.vg, a.kg, a.wg, a.mut, a.f1,
+               src, &beta);
+    const double turbSpecRad = TurbSrcSpecRad(p.tr.scaling, s[iw], vol);
+    a.srT -= turbSpecRad;
+    a.dgT -= turbSpecRad;
+    a.r[E::it] -= src[0] * vol;
+    a.r[iw] -= src[1] * vol;
+    if (BLOCK) {  // TurbSrcJac (src/turbulence.cpp:445-458, :706-720)
+      const double invScaling = 1.0 / p.tr.scaling;
+      dblk[B::nf] -= -2.0 * kw::betaStar * s[iw] * vol * invScaling;
+      dblk[B::nf + NT * NT - 1] -= -2.0 * beta * s[iw] * vol * invScaling;
+    }
+  }
 #pragma unroll
   for (int e = NS; e < E::neq; ++e) b.resid[e * b.fs + idx] = a.r[e];
   b.specRad[idx] = a.sr;
   b.specRad[b.fs + idx] = a.srT;
   if (implicitScalar) {
     b.diag[idx] = a.dg;
-    b.diag[b.fs + idx] = a.dgT;
+    if (NT > 0) b.diag[b.fs + idx] = a.dgT;
   }
-  b.eddyVisc[idx] = a.mut;
-  b.f1[idx] = a.f1;
-  b.f2[idx] = a.f2;
+  if (BLOCK) {
+#pragma unroll
+    for (int q = 0; q < B::n; ++q) b.diag[q * b.fs + idx] = dblk[q];
+  }
+  if (NT > 0) {
+    b.eddyVisc[idx] = a.mut;
+    b.f1[idx] = a.f1;
+    b.f2[idx] = a.f2;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      b.tkeGrad[q * b.fs + idx] = a.kg[q];
+      b.omegaGrad[q * b.fs + idx] = a.wg[q];
+    }
+  }
 #pragma unroll
   for (int q = 0; q < 9; ++q) b.velGrad[q * b.fs + idx] = a.vg[q];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    b.tkeGrad[q * b.fs + idx] = a.kg[q];
-    b.omegaGrad[q * b.fs + idx] = a.wg[q];
-  }
 }
 
 }  // namespace aither

@@ -16,7 +16,9 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_v
                 # laminar Navier-Stokes (viscous fluxes, viscous-wall / edge ghosts, Sutherland)
                 "viscousFlatPlate", "box_visc4", "box_visc_iso",
                 # RANS: k-omega Wilcox 2006 (reference regression case + AUSM box) and SST 2003
-                "turbFlatPlate", "box_sst", "box_kw"]
+                "turbFlatPlate", "box_sst", "box_kw",
+                # block-matrix solvers (bdplur, blusgs laminar / SST) and the approximateRoe Jacobian
+                "box_bdplur", "box_blusgs_visc", "box_sst_blusgs", "box_roe_jac"]
 
 
 def make_gpu_level(prob):
@@ -50,7 +52,9 @@ def test_gpu_phases_match_reference(name):
                                         ("box_dplur", 30), ("box_lusgs_va", 20),
                                         ("box_weno", 12), ("viscousFlatPlate", 100),
                                         ("box_visc4", 12), ("box_visc_iso", 12),
-                                        ("turbFlatPlate", 20), ("box_sst", 12), ("box_kw", 12)])
+                                        ("turbFlatPlate", 20), ("box_sst", 12), ("box_kw", 12),
+                                        ("box_bdplur", 12), ("box_blusgs_visc", 12),
+                                        ("box_sst_blusgs", 12), ("box_roe_jac", 12)])
 def test_gpu_history_matches_reference(name, iters):
     d = gc.load(name)
     worst = gc.check_history(make_gpu_level, d, iters, 1e-9, name=name)
