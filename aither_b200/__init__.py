@@ -24,7 +24,8 @@ ABI_SYMBOLS = (
     "aither_gpu_get_boundary_conditions", "aither_gpu_calc_residual", "aither_gpu_calc_time_step",
     "aither_gpu_invert_diagonal", "aither_gpu_initialize_matrix_update", "aither_gpu_relax",
     "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
-    "aither_gpu_upload_state", "aither_gpu_download_state", "aither_gpu_download_field",
+    "aither_gpu_upload_state", "aither_gpu_upload_state_async", "aither_gpu_upload_state_commit",
+    "aither_gpu_download_state", "aither_gpu_download_field",
     "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
     "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
@@ -65,6 +66,8 @@ def load_library():
     L.aither_gpu_update_blocks.argtypes = [vp, C.c_int, pd, C.POINTER(abi.Linf)]
     L.aither_gpu_run.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, pd]
     L.aither_gpu_upload_state.argtypes = [vp, C.c_int, pd]
+    L.aither_gpu_upload_state_async.argtypes = [vp, C.c_int, pd]
+    L.aither_gpu_upload_state_commit.argtypes = [vp]
     L.aither_gpu_download_state.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
@@ -204,6 +207,15 @@ class GridLevel:
     def upload_state(self, blk, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
         self._check(self._lib.aither_gpu_upload_state(self._h, blk, _ptr(state)))
+
+    def upload_state_async(self, blk, state):
+        """start the host-to-device copy of `state` (page-locked, C-contiguous float64; it must
+        stay alive and unchanged until `upload_state_commit`) on the copy stream"""
+        assert state.flags["C_CONTIGUOUS"] and state.dtype == np.float64
+        self._check(self._lib.aither_gpu_upload_state_async(self._h, blk, _ptr(state)))
+
+    def upload_state_commit(self):
+        self._check(self._lib.aither_gpu_upload_state_commit(self._h))
 
     def download_state_into(self, blk, out):
         self._check(self._lib.aither_gpu_download_state(self._h, blk, _ptr(out)))

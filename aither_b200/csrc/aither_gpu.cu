@@ -102,9 +102,18 @@ struct aither_gpu {
   int resultsCap = 0;
   double *dStage = nullptr;        // layout-conversion staging
   size_t stageBytes = 0;
+  // pipelined state upload (aither_gpu_upload_state_async / _commit): its own staging buffer,
+  // a copy stream, and the two events that order copy -> conversion -> next copy
+  cudaStream_t copyStream = nullptr;
+  double *dStage2 = nullptr;
+  size_t stage2Bytes = 0;
+  cudaEvent_t evCopied = nullptr, evConverted = nullptr;
+  int pendingBlk = -1;
   long long launches = 0;
   bool keepMatrixResid = false;
   int jac = kJacScalar;            // JacKind of the implicit matrix
+  bool consNStale = false;         // U^n not materialised (Params::timeTermsVanish)
+  bool stateMovedSinceStore = false;
   int *dFlag = nullptr;            // set by PrepBlockKernel on a singular diagonal block
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
   bool tmaImplicit = true;         // AITHER_B200_KERNELS=march: register-fed implicit sweep
@@ -156,6 +165,10 @@ void DrainProfile(aither_gpu *h) {
 int EnsureStage(aither_gpu *h, size_t bytes) {
   if (bytes <= h->stageBytes) return 0;
   if (h->dStage) cudaFree(h->dStage);
+  if (h->dStage2) cudaFree(h->dStage2);
+  if (h->evCopied) cudaEventDestroy(h->evCopied);
+  if (h->evConverted) cudaEventDestroy(h->evConverted);
+  if (h->copyStream) cudaStreamDestroy(h->copyStream);
   h->dStage = nullptr;
   h->stageBytes = 0;
   CK(cudaMalloc(&h->dStage, bytes));
@@ -241,6 +254,13 @@ void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fus
   }
 #endif
   using S = ResSmem<NS, NT, RC>;
+  if constexpr (S::bytes > 227 * 1024) {
+    // 7 equations x WENO's 7-plane ring does not fit the 227 KB of shared memory: this one
+    // combination takes the gather kernel (thread per cell, face fluxes shared per tile)
+    ResidualKernel<NS, NT, RC, LM, FX><<<hb.resGrid, hb.resBlock, 0, h->stream>>>(
+        hb.dev, h->params, implicitScalar);
+    return;
+  } else {
   auto kern = ResidualMarchKernel<NS, NT, RC, LM, FX>;
   static bool configured = false;  // per template instantiation
   if (!configured) {
@@ -250,6 +270,7 @@ void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fus
   }
   kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), S::bytes, h->stream>>>(hb.dev, h->params, hb.kChunk,
                                                                  implicitScalar, fusePrep, cfl);
+  }
 }
 
 template <int NS, int NT>
@@ -621,7 +642,10 @@ int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
 }
 int PhasePrep(aither_gpu *h, double cfl, int bits) { return EQ_DISPATCH(h, PhasePrepT, h, cfl, bits); }
 int PhaseRelax(aither_gpu *h, int sweeps, int slot) { return EQ_DISPATCH(h, PhaseRelaxT, h, sweeps, slot); }
-int PhaseUpdate(aither_gpu *h, int slot, int mm) { return EQ_DISPATCH(h, PhaseUpdateT, h, slot, mm); }
+int PhaseUpdate(aither_gpu *h, int slot, int mm) {
+  h->stateMovedSinceStore = true;
+  return EQ_DISPATCH(h, PhaseUpdateT, h, slot, mm);
+}
 
 template <int NS, int NT>
 int StoreOldT(aither_gpu *h, int copyNm1) {
@@ -696,6 +720,10 @@ void FreeAll(aither_gpu *h) {
   if (h->dResults) cudaFree(h->dResults);
   if (h->hResults) cudaFreeHost(h->hResults);
   if (h->dStage) cudaFree(h->dStage);
+  if (h->dStage2) cudaFree(h->dStage2);
+  if (h->evCopied) cudaEventDestroy(h->evCopied);
+  if (h->evConverted) cudaEventDestroy(h->evConverted);
+  if (h->copyStream) cudaStreamDestroy(h->copyStream);
   if (h->evStart) cudaEventDestroy(h->evStart);
   if (h->evStop) cudaEventDestroy(h->evStop);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -752,6 +780,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.matrixRequiresInit = cfg->matrixRequiresInit;
   p.wenoZ = cfg->recon == AITHER_RECON_WENOZ;
   p.isViscous = cfg->isViscous;
+  {
+    const char *tv = getenv("AITHER_B200_KEEP_TIME_N");  // A/B switch: always store / read U^n
+    p.timeTermsVanish = !cfg->isMultilevelTime && cfg->nonlinearIterations <= 1 &&
+                        !(tv != nullptr && std::string(tv) == "1");
+  }
   p.viscRecon = cfg->viscRecon;
   p.viscCFLCoeff = cfg->viscousCFLCoeff;
   p.tr.tRef = cfg->tRef;
@@ -1073,6 +1106,13 @@ int aither_gpu_store_old_solution(aither_gpu *h, int iter) {
   if (!h) return Fail("null handle");
   CK(cudaSetDevice(h->device));
   const int copyNm1 = (h->cfg.isMultilevelTime && iter == 0) ? 1 : 0;
+  if (h->params.timeTermsVanish) {
+    // U^n is not needed by the iteration; it is materialised only if someone asks for it
+    // (aither_gpu_download_field(AITHER_FIELD_CONS_N)) before the state moves on
+    h->consNStale = true;
+    h->stateMovedSinceStore = false;
+    return 0;
+  }
   EQ_DISPATCH(h, StoreOldT, h, copyNm1);
   CK(cudaGetLastError());
   return 0;
@@ -1248,6 +1288,14 @@ long long aither_gpu_field_size(aither_gpu *h, int blk, int field) {
 int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst) {
   if (!h || !dst) return Fail("null argument");
   CK(cudaSetDevice(h->device));
+  if (field == AITHER_FIELD_CONS_N && h->consNStale) {
+    if (h->stateMovedSinceStore)
+      return Fail("U^n was not stored: with one nonlinear iteration per step of a single-level "
+                  "scheme the iteration does not need it (set AITHER_B200_KEEP_TIME_N=1 to keep it)");
+    EQ_DISPATCH(h, StoreOldT, h, 0);
+    CK(cudaGetLastError());
+    h->consNStale = false;
+  }
   const double *ptr; int nc; bool padded;
   if (FieldInfo(h, blk, field, &ptr, &nc, &padded)) return 1;
   const HostBlock &hb = h->blocks[blk];
@@ -1269,6 +1317,61 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
                 -g))
     return 1;
   if (h->nt > 0) {  // the wall omega BC reads the stored viscosity: make it the new state's
+    EQ_DISPATCH(h, InitAuxT, h, blk);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS) {
+  if (!h || !stateAoS) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  if (h->pendingBlk >= 0) return Fail("an asynchronous upload is already pending: commit it first");
+  const BlockDev &b = h->blocks[blk].dev;
+  const size_t n = static_cast<size_t>(b.ni + 2 * b.g) * (b.nj + 2 * b.g) * (b.nk + 2 * b.g) * h->neq;
+  if (!h->copyStream) {
+    CK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->evCopied, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evConverted, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->evConverted, h->stream));
+  }
+  if (n * sizeof(double) > h->stage2Bytes) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->dStage2) cudaFree(h->dStage2);
+    h->dStage2 = nullptr;
+    h->stage2Bytes = 0;
+    CK(cudaMalloc(&h->dStage2, n * sizeof(double)));
+    h->stage2Bytes = n * sizeof(double);
+  }
+  // the previous conversion must have finished reading the staging buffer
+  CK(cudaStreamWaitEvent(h->copyStream, h->evConverted, 0));
+  CK(cudaMemcpyAsync(h->dStage2, stateAoS, n * sizeof(double), cudaMemcpyHostToDevice,
+                     h->copyStream));
+  CK(cudaEventRecord(h->evCopied, h->copyStream));
+  h->pendingBlk = blk;
+  return 0;
+}
+int aither_gpu_upload_state_commit(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  if (h->pendingBlk < 0) return Fail("no asynchronous upload is pending");
+  const int blk = h->pendingBlk;
+  h->pendingBlk = -1;
+  const HostBlock &hb = h->blocks[blk];
+  const BlockDev &b = hb.dev;
+  const int g = b.g, SI = b.ni + 2 * g, SJ = b.nj + 2 * g, SK = b.nk + 2 * g;
+  CK(cudaStreamWaitEvent(h->stream, h->evCopied, 0));
+  const long long cells = static_cast<long long>(SI) * SJ * SK;
+  const int grid = static_cast<int>(std::min<long long>((cells + 255) / 256, 148 * 16));
+  {
+    ScopedLaunch sl(h, kFamLayout);
+    AosToSoaKernel<<<grid, 256, 0, h->stream>>>(h->dStage2, SI, SJ, SK, h->neq, b.state, b.fs,
+                                                -g + b.lp, 0, 0, b.sj, b.sk);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->evConverted, h->stream));
+  if (h->nt > 0) {
     EQ_DISPATCH(h, InitAuxT, h, blk);
     CK(cudaGetLastError());
   }

@@ -34,6 +34,9 @@ struct Params {
   int wenoZ;
   int isViscous;
   int viscRecon;   // 0 central, 1 centralFourth
+  // one nonlinear iteration per step of a single-level scheme: U^m = U^n at the only iteration,
+  // so the time terms of b vanish identically and U^n is never read (nor stored)
+  int timeTermsVanish;
 };
 
 // per-iteration reduction results (device + pinned host mirror)
@@ -223,7 +226,7 @@ __device__ __forceinline__ void ResidualPass(const BlockDev &b, const Params &p,
                                              double (*sflux)[kFaceMax], int i0, int j0, int k0,
                                              int tx, int ty, int tz, int tid, bool cellValid,
                                              long long idx, const double *s, double sos,
-                                             double *res, double &specRad) {
+                                             double *res, double &specRad, double &specRadT) {
   using E = Eq<NS, NT>;
   const int nd[3] = {b.ni, b.nj, b.nk};
   {
@@ -282,7 +285,9 @@ __device__ __forceinline__ void ResidualPass(const BlockDev &b, const Params &p,
       fL[q] = __ldg(b.fA[D] + q * b.fs + idx);
       fR[q] = __ldg(b.fA[D] + q * b.fs + idx + st);
     }
-    specRad += InvCellSpectralRadius<NS>(s, sos, fL, fR);  // ref: :468-488
+    double srT = 0.0;
+    specRad += InvCellSpectralRadii<NS>(s, sos, fL, fR, &srT);  // ref: :468-488
+    specRadT += srT;
   }
   __syncthreads();
 }
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(kResThreads)
   const bool cellValid = i < b.ni && j < b.nj && k < b.nk;
   const long long idx = CellIdx(b, i, j, k);
   double res[E::neq], s[E::neq];
-  double specRad = 0.0, sos = 0.0;
+  double specRad = 0.0, specRadT = 0.0, sos = 0.0;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) res[e] = 0.0;
   if (cellValid) {
@@ -307,18 +312,21 @@ __global__ void __launch_bounds__(kResThreads)
     sos = SoS<NS>(p.gas, s);
   }
   ResidualPass<NS, NT, RECON, LIM, FLUX, 0>(b, p, sflux, i0, j0, k0, tx, ty, tz, tid, cellValid,
-                                            idx, s, sos, res, specRad);
+                                            idx, s, sos, res, specRad, specRadT);
   ResidualPass<NS, NT, RECON, LIM, FLUX, 1>(b, p, sflux, i0, j0, k0, tx, ty, tz, tid, cellValid,
-                                            idx, s, sos, res, specRad);
+                                            idx, s, sos, res, specRad, specRadT);
   ResidualPass<NS, NT, RECON, LIM, FLUX, 2>(b, p, sflux, i0, j0, k0, tx, ty, tz, tid, cellValid,
-                                            idx, s, sos, res, specRad);
+                                            idx, s, sos, res, specRad, specRadT);
   if (cellValid) {
     StoreCell<E::neq>(b.resid, b.fs, idx, res);
     b.specRad[idx] = specRad;
-    b.specRad[b.fs + idx] = 0.0;
+    b.specRad[b.fs + idx] = NT > 0 ? specRadT : 0.0;
     // scalar implicit diagonal accumulates the same spectral radii (ref: :485-488); the
     // diagonal was zeroed by ResetDiagonal, so the sum starts from 0 exactly as specRadius_
-    if (implicitScalar) b.diag[idx] = specRad;
+    if (implicitScalar) {
+      b.diag[idx] = specRad;
+      if (NT > 0) b.diag[b.fs + idx] = specRadT;
+    }
   }
 }
 
@@ -333,9 +341,16 @@ __device__ __forceinline__ void RhsB(const BlockDev &b, const Params &p, long lo
   // b = -R/theta + SolDeltaNm1 - SolDeltaMmN; ref: src/procBlock.cpp:1010-1034,
   // src/linearSolver.cpp:124-129
   using E = Eq<NS, NT>;
+  const double thetaInv = 1.0 / p.theta;
+  if (p.timeTermsVanish) {
+    // SolDeltaMmN = coeff (U^m - U^n) = 0 exactly and there is no U^(n-1) term
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e)
+      out[e] = -thetaInv * (LOCAL_RES ? resLocal[e] : __ldg(b.resid + e * b.fs + idx));
+    return;
+  }
   double cons[E::neq];
   PrimToCons<NS, NT>(p.gas, s, cons);
-  const double thetaInv = 1.0 / p.theta;
   const double coeff = (vol * (1.0 + p.zeta)) / (dt * p.theta);
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) {

@@ -75,18 +75,22 @@ def viscous_terms(fluid, recon_kappa, visc_recon="central", sutherland=AIR_SUTHE
 
 def euler_cfg(fluid, *, g=2, solver="dplur", sweeps=4, limiter="none", flux="roe",
               recon="thirdOrder", relaxation=1.0, bc_states=(), viscous=False,
-              visc_recon="central"):
-    """`aither_cfg` for `equationSet: euler`, `timeIntegration: implicitEuler` (theta=1, zeta=0;
-    src/input.cpp:256-270), scalar diagonal (lusgs / dplur)."""
+              visc_recon="central", turb=None, jac="rusanov"):
+    """`aither_cfg` for `equationSet: euler | navierStokes | rans`, `timeIntegration:
+    implicitEuler` (theta=1, zeta=0; src/input.cpp:256-270); `solver`: lusgs / dplur (scalar
+    diagonal) or blusgs / bdplur (block matrices); `turb`: None, "kOmegaWilcox2006", "sst2003"."""
     rc, kappa = _RECON[recon]
+    viscous = viscous or turb is not None
+    turb_id = {None: abi.TURB_NONE, "kOmegaWilcox2006": abi.TURB_KW_WILCOX,
+               "sst2003": abi.TURB_SST}[turb]
     is_dplur = solver in ("dplur", "bdplur")
     extra = viscous_terms(fluid, kappa, visc_recon) if viscous else dict(isViscous=0, viscRecon=0,
                                                                          viscousCFLCoeff=1.0)
     return make_cfg(
-        numSpecies=1, numTurb=0, numGhosts=g, isRANS=0,
+        numSpecies=1, numTurb=2 if turb else 0, numGhosts=g, isRANS=int(turb is not None),
         isBlockMatrix=int(solver in ("blusgs", "bdplur")), isMultilevelTime=0,
         recon=rc, limiter=_LIMITER[limiter], invFlux=abi.FLUX_ROE if flux == "roe" else abi.FLUX_AUSM,
-        invFluxJac=abi.JAC_RUSANOV, turbModel=abi.TURB_NONE,
+        invFluxJac=abi.JAC_RUSANOV if jac == "rusanov" else abi.JAC_APPROX_ROE, turbModel=turb_id,
         solver=abi.SOLVER_DPLUR if is_dplur else abi.SOLVER_LUSGS,
         matrixSweeps=sweeps, matrixRequiresInit=int(is_dplur or sweeps > 1),  # input.cpp:1120
         nonlinearIterations=1,

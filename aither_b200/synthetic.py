@@ -177,16 +177,18 @@ def perturbed_state(shape_kji, neq_state, seed=0, amplitude=0.01):
 
 def box_problem(ni, nj, nk, *, solver="dplur", sweeps=4, limiter="none", flux="roe",
                 recon="thirdOrder", seed=0, amplitude=0.01, viscous=False, visc_recon="central",
-                wall=None, size=1.0):
+                wall=None, size=1.0, turb=None, jac="rusanov"):
     """The synthetic single-block case as a `Problem` (product-side set-up, no reference): Euler,
     or with `viscous` laminar Navier-Stokes with a viscous wall on the j-lo face (`wall`: None =
     adiabatic, ("isothermal", T [K]), ("heatFlux", q)) on a box `size` metres wide."""
+    viscous = viscous or turb is not None
     g = {"constant": 1, "weno": 3, "wenoZ": 3}.get(recon, 2)  # input.cpp:1127-1144
     m = block_metrics(box_nodes(ni, nj, nk, lengths=(size,) * 3, warp=0.02 * size, period=size), g)
     fluid = nondim.air(REF_RHO, REF_T)
     free = nondim.nondim_primitive(IC["density"], IC["velocity"], IC["pressure"], REF_RHO, REF_T)
     bc_states = [dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
-                      velocity=list(free[1:4]), pressure=free[4], massFractions=[1.0])]
+                      velocity=list(free[1:4]), pressure=free[4], massFractions=[1.0],
+                      turbulenceIntensity=0.01, eddyViscosityRatio=10.0)]
     if viscous:
         ws = dict(tag=2, type=abi.BC_VISCOUS_WALL, velocity=[0.0, 0.0, 0.0], massFractions=[1.0])
         if wall is not None and wall[0] == "isothermal":
@@ -196,8 +198,27 @@ def box_problem(ni, nj, nk, *, solver="dplur", sweeps=4, limiter="none", flux="r
         bc_states.append(ws)
     cfg = nondim.euler_cfg(fluid, g=g, solver=solver, sweeps=sweeps, limiter=limiter, flux=flux,
                            recon=recon, bc_states=bc_states, viscous=viscous,
-                           visc_recon=visc_recon)
+                           visc_recon=visc_recon, turb=turb, jac=jac)
     state = perturbed_state((nk + 2 * g, nj + 2 * g, ni + 2 * g), 5, seed, amplitude)
+    wall_dist = None
+    if turb is not None:
+        # farfield-like turbulence (k = 1.5 (0.01 |v|)^2, omega = rho k / (10 mu)), nondimensional
+        # as the reference's cloud reader does (src/utility.cpp:575-578), with the same noise
+        rng = np.random.default_rng(seed + 7919)
+        vmag = np.linalg.norm(IC["velocity"])
+        k0 = 1.5 * (0.01 * vmag) ** 2
+        mu0 = nondim.AIR_SUTHERLAND[0] * REF_T ** 1.5 / (REF_T + nondim.AIR_SUTHERLAND[1])
+        w0 = IC["density"] * k0 / (10.0 * mu0)
+        kw = np.array([k0 / fluid.a_ref ** 2, w0 * mu0 / (REF_RHO * fluid.a_ref ** 2)])
+        noise = 1.0 + amplitude * (2.0 * rng.random(state.shape[:3] + (2,)) - 1.0)
+        state = np.concatenate([state, kw[None, None, None, :] * noise], axis=-1)
+        # wall distance: to the centre of the j-lo wall face of the same (i, k) column -- an
+        # approximation of the reference's nearest-wall-face search (src/procBlock.cpp:6030-6107;
+        # set-up code outside the hot path) that is good enough for timing runs; parity tests take
+        # the wall distance from reference dumps
+        cen = m["center"]
+        face = 0.5 * (cen[:, g - 1:g, :, :] + cen[:, g:g + 1, :, :])
+        wall_dist = np.ascontiguousarray(np.linalg.norm(cen - face, axis=-1)[..., None])
     surfaces = [
         (abi.BC_CHARACTERISTIC, 0, 0, 0, nj, 0, nk, 1),
         (abi.BC_CHARACTERISTIC, ni, ni, 0, nj, 0, nk, 1),
@@ -210,7 +231,7 @@ def box_problem(ni, nj, nk, *, solver="dplur", sweeps=4, limiter="none", flux="r
     arrays = {k: m[k] for k in ("vol", "fAreaI", "fAreaJ", "fAreaK", "center", "cellWidthI",
                                 "cellWidthJ", "cellWidthK")}
     arrays["state"] = state
-    arrays["wallDist"] = None
+    arrays["wallDist"] = wall_dist
     return Problem(cfg, [Block(ni, nj, nk, surfaces, arrays)])
 
 

@@ -245,6 +245,13 @@ int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep,
  * (procBlock::States(), include/procBlock.hpp:506). */
 int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS);
 int aither_gpu_download_state(aither_gpu *h, int blk, double *stateAoS);
+/* Pipelined variant for a host that owns the state and hands a fresh copy over every step:
+ * _async starts the host-to-device copy (from page-locked memory) on the library's copy stream
+ * and returns at once, so the copy overlaps the iteration in flight; _commit makes the compute
+ * stream wait for the copy and converts it into the device layout in front of the next
+ * aither_gpu_iterate. One upload may be pending per handle. */
+int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS);
+int aither_gpu_upload_state_commit(aither_gpu *h);
 int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst);
 /* number of doubles aither_gpu_download_field writes for `field` */
 long long aither_gpu_field_size(aither_gpu *h, int blk, int field);
