@@ -215,6 +215,27 @@ int DownloadAos(aither_gpu *h, const HostBlock &hb, double *dst, int SI, int SJ,
   return 0;
 }
 
+// Chunk length along k for a plane-marching kernel: every (column, chunk) pair is one thread
+// block, `slots` blocks are resident at a time and a block's time is ~ its planes plus `overhead`
+// prologue planes. The time of the launch is (number of waves) x (chunk + overhead): with 256
+// planes, 128 columns and 148 slots a 52-plane chunk gives 4.3 -> 5 waves (270 units) where a
+// 32-plane chunk gives 6.9 -> 7 waves (238 units): measured 1.22 -> 1.10 ms per DPLUR sweep.
+int PickChunk(int nk, int cols, int slots, int overhead) {
+  int best = std::max(1, std::min(nk, 8));
+  double bestCost = 1e300;
+  for (int c = std::min(nk, 8); c <= std::min(nk, 64); ++c) {
+    const long long blocks = static_cast<long long>(cols) * ((nk + c - 1) / c);
+    const long long waves = (blocks + slots - 1) / slots;
+    // partially filled last wave still costs a full block; mild preference for longer chunks
+    const double cost = static_cast<double>(waves) * (c + overhead) * (1.0 + 0.02 / c);
+    if (cost < bestCost) {
+      bestCost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
 int SurfaceType(const aither_surface &s) {
   // ref: src/boundaryConditions.cpp:2424-2452
   if (s.imin == s.imax) return s.imax == 0 ? 1 : 2;
@@ -1038,12 +1059,12 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.resGrid = dim3((d.ni + 1 + kTI - 1) / kTI, (d.nj + 1 + kTJ - 1) / kTJ,
                       (d.nk + 1 + kTK - 1) / kTK);
     {
-      // k-chunks of the marching kernels: enough blocks to fill 148 SMs x 2 resident blocks a few
-      // times over, but chunks of at least 8 planes so the per-chunk prologue stays small
+      // k-chunks of the marching kernels: 148 SMs x 2 resident blocks; the chunk length that
+      // minimises (waves of blocks) x (planes per chunk + prologue), see PickChunk
       const int cols = ((d.ni + kMI - 1) / kMI) * ((d.nj + kMJ - 1) / kMJ);
-      int nChunks = std::max(1, (148 * 2 * 4 + cols - 1) / cols);
-      int chunk = std::max(std::min(8, d.nk), (d.nk + nChunks - 1) / nChunks);
-      chunk = std::min(chunk, 64);
+      int chunk = PickChunk(d.nk, cols, 148 * 2, 4);
+      int nChunks;
+      if (const char *ev = getenv("AITHER_B200_RES_CHUNK")) chunk = std::max(1, atoi(ev));
       nChunks = (d.nk + chunk - 1) / chunk;
       hb.kChunk = chunk;
       hb.marchGrid = dim3((d.ni + kMI - 1) / kMI, (d.nj + kMJ - 1) / kMJ, nChunks);
@@ -1052,9 +1073,9 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     {
       // TMA-fed implicit sweep: 32 x 16 columns, chunks of ~32 planes (2 extra end planes each)
       const int cols = ((d.ni + kQI - 1) / kQI) * ((d.nj + kQJ - 1) / kQJ);
-      int nChunks = std::max(1, (148 * 4 + cols - 1) / cols);
-      int chunk = std::max(std::min(16, d.nk), (d.nk + nChunks - 1) / nChunks);
-      chunk = std::min(chunk, 64);
+      int chunk = PickChunk(d.nk, cols, 148, 2);
+      int nChunks;
+      if (const char *ev = getenv("AITHER_B200_TMA_CHUNK")) chunk = std::max(1, atoi(ev));
       nChunks = (d.nk + chunk - 1) / chunk;
       hb.tmaChunk = chunk;
       hb.tmaGrid = dim3((d.ni + kQI - 1) / kQI, (d.nj + kQJ - 1) / kQJ, nChunks);

@@ -585,15 +585,15 @@ static void extrapolate_hold_mixture(const orc_level *h, const double *bnd,
 }
 
 /* ref: src/ghostStates.cpp:62-689 (GetGhostState), inviscid / low-Re subset */
-static double eff_conductivity(const orc_level *h, double t);
-static double viscosity_of(const orc_level *h, double t);
+static double eff_conductivity(const orc_level *h, double t, const double *s);
+static double viscosity_of(const orc_level *h, double t, const double *s);
 /* primitive::ApplyFarfieldTurbBC; ref: src/primitive.cpp:83-98 */
 static void apply_farfield_turb(const orc_level *h, double *s, const double vel[3],
                                 double turbInten, double viscRatio) {
   const int it = h->ns + 4;
   const double vmag = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
   s[it] = 1.5 * pow(turbInten * vmag, 2.0);
-  s[it + 1] = rho_of(h, s) * s[it] / (viscRatio * viscosity_of(h, temperature_of(h, s)));
+  s[it + 1] = rho_of(h, s) * s[it] / (viscRatio * viscosity_of(h, temperature_of(h, s), s));
   for (int tt = 0; tt < h->nt; ++tt)
     s[it + tt] = s[it + tt] > 1.0e-20 ? s[it + tt] : 1.0e-20;
 }
@@ -629,7 +629,7 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
         tGhost = 2.0 * bc->temperature - temperature_of(h, interior);
       } else { /* ref: :226-236 */
         const double t = temperature_of(h, interior);
-        const double kappa = eff_conductivity(h, t);
+        const double kappa = eff_conductivity(h, t, interior);
         tGhost = temperature_of(h, interior) -
                  bc->heatFlux / kappa * 2.0 * wallDist;
       }
@@ -1009,21 +1009,57 @@ static double species_viscosity(const orc_level *h, double t, int ss) {
       (h->cfg.suthViscC1[ss] * pow(temp, 1.5)) / (temp + h->cfg.suthViscS[ss]);
   return mu / h->cfg.muMixRef;
 }
-static double viscosity_of(const orc_level *h, double t) {
-  if (h->ns != 1) {
-    fprintf(stderr, "oracle: Wilke mixing rule is not restated (ns > 1)\n");
-    abort();
+/* sutherland::MoleFractions; ref: src/transport.cpp:133-146 */
+static void mole_fractions(const orc_level *h, const double *mf, double *x) {
+  double sum = 0.0;
+  for (int ii = 0; ii < h->ns; ++ii) {
+    x[ii] = mf[ii] / h->cfg.molarMass[ii];
+    sum += x[ii];
   }
-  return species_viscosity(h, t, 0);
+  for (int ii = 0; ii < h->ns; ++ii) x[ii] /= sum;
 }
-static double conductivity_of(const orc_level *h, double t) {
+/* sutherland::Viscosity with Wilke's mixing rule; ref: src/transport.cpp:70-96,148-162 */
+static double viscosity_of(const orc_level *h, double t, const double *s) {
+  if (h->ns == 1) return species_viscosity(h, t, 0);
+  double mf[AITHER_MAX_SPECIES], x[AITHER_MAX_SPECIES], sv[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  mole_fractions(h, mf, x);
+  for (int ii = 0; ii < h->ns; ++ii) sv[ii] = species_viscosity(h, t, ii);
+  const double *mm = h->cfg.molarMass;
+  double mixtureVisc = 0.0;
+  for (int ii = 0; ii < h->ns; ++ii) {
+    const double moleVisc = x[ii] * sv[ii];
+    double denom = 0.0;
+    for (int jj = 0; jj < h->ns; ++jj)
+      denom += x[jj] / sqrt(1.0 + mm[ii] / mm[jj]) *
+               pow(1.0 + sqrt(sv[ii] / sv[jj]) * pow(mm[jj] / mm[ii], 0.25), 2.0);
+    mixtureVisc += moleVisc / denom;
+  }
+  return 4.0 / sqrt(2.0) * mixtureVisc;
+}
+static double species_conductivity(const orc_level *h, double t, int ss) {
   const double temp = t * h->cfg.tRef;
   const double k =
-      (h->cfg.suthCondC1[0] * pow(temp, 1.5)) / (temp + h->cfg.suthCondS[0]);
+      (h->cfg.suthCondC1[ss] * pow(temp, 1.5)) / (temp + h->cfg.suthCondS[ss]);
   return k / h->cfg.kMixRef;
 }
-static double eff_conductivity(const orc_level *h, double t) {
-  return conductivity_of(h, t) * h->cfg.nondimScaling;
+/* sutherland::Conductivity; ref: src/transport.cpp:97-110,178-192 (WilkesCond) */
+static double conductivity_of(const orc_level *h, double t, const double *s) {
+  if (h->ns == 1) return species_conductivity(h, t, 0);
+  double mf[AITHER_MAX_SPECIES], x[AITHER_MAX_SPECIES];
+  mass_fractions(h, s, mf);
+  mole_fractions(h, mf, x);
+  double weightedAvg = 0.0, harmonicAvg = 0.0;
+  for (int ii = 0; ii < h->ns; ++ii) {
+    const double sc = species_conductivity(h, t, ii);
+    weightedAvg += x[ii] * sc;
+    harmonicAvg += x[ii] / sc;
+  }
+  harmonicAvg = 1.0 / harmonicAvg;
+  return 0.5 * (weightedAvg + harmonicAvg);
+}
+static double eff_conductivity(const orc_level *h, double t, const double *s) {
+  return conductivity_of(h, t, s) * h->cfg.nondimScaling;
 }
 /* ref: include/thermodynamic.hpp:61-64 */
 static double prandtl_of(double gamma) {
@@ -1041,7 +1077,7 @@ static void update_aux(orc_level *h, orc_block *b) {
         const long c = cidx(b, ii, jj, kk);
         b->temperature[c] = temperature_of(h, b->state + h->neq * c);
         if (h->cfg.isViscous)
-          b->viscosity[c] = viscosity_of(h, b->temperature[c]);
+          b->viscosity[c] = viscosity_of(h, b->temperature[c], b->state + h->neq * c);
       }
 }
 
@@ -1580,7 +1616,7 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         flux[ns + 1] = tau[1];
         flux[ns + 2] = tau[2];
         const double t = temperature_of(h, state);
-        const double kcond = eff_conductivity(h, t);
+        const double kcond = eff_conductivity(h, t, state);
         double kt = 0.0;
         if (rans) { /* sutherland::TurbConductivity: mut cp / Prt, include/transport.hpp:132-137 */
           double mf[AITHER_MAX_SPECIES];
@@ -2149,7 +2185,7 @@ static void approx_tsl_jacobian(const orc_level *h, const double *s, double lamV
   double mf[AITHER_MAX_SPECIES];
   mass_fractions(h, s, mf);
   const double rho = rho_of(h, s);
-  const double k = eff_conductivity(h, t);
+  const double k = eff_conductivity(h, t, s);
   const double kt = mut * cp_mix(h, mf) / turb_prandtl(h);
   double tauNorm[3];
   tau_normal(vGrad, n, mu, mut, tauNorm);
@@ -2644,7 +2680,8 @@ static void init_aux(orc_level *h, orc_block *b) {
       for (int ii = 0; ii < b->ni; ++ii) {
         const long c = cidx(b, ii, jj, kk);
         b->temperature[c] = temperature_of(h, b->state + h->neq * c);
-        if (h->cfg.isViscous) b->viscosity[c] = viscosity_of(h, b->temperature[c]);
+        if (h->cfg.isViscous)
+          b->viscosity[c] = viscosity_of(h, b->temperature[c], b->state + h->neq * c);
       }
 }
 
