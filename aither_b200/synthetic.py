@@ -45,13 +45,17 @@ def write_plot3d(path, blocks_nodes):
 
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
-             visc_recon="central", wall=None, turb=None, jac="rusanov"):
-    """`viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
+             visc_recon="central", wall=None, turb=None, jac="rusanov", species=None):
+    """`species`: None (air) or a dict name -> reference mass fraction (multi-species mixture with
+    Schmidt-number diffusion, e.g. {"H2O": 0.233, "H2": 0.001, "N2": 0.766}).
+    `viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
     ("isothermal", T) or ("heatFlux", q)). `turb`: None, "kOmegaWilcox2006" or "sst2003" (RANS,
     implies viscous; farfield turbulence intensity 1 %, eddy viscosity ratio 10)."""
     viscous = viscous or turb is not None
     vel = "[%g, %g, %g]" % IC["velocity"]
     state = "pressure=%g; density=%g; velocity=%s" % (IC["pressure"], IC["density"], vel)
+    if species:
+        state += "; massFractions=[%s]" % ", ".join("%s=%g" % kv for kv in species.items())
     if turb is not None:
         state += "; turbulenceIntensity=0.01; eddyViscosityRatio=10"
     ic = "icState(tag=-1; %s)" % state if ic_file is None else "icState(tag=-1; file=%s)" % ic_file
@@ -75,6 +79,9 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "outputVariables: <density, vel_x, vel_y, vel_z, pressure>",
         "referenceTemperature: %g" % REF_T,
         "referenceDensity: %g" % REF_RHO,
+        *(["fluids: <%s>" % ", ".join("fluid(name=%s; referenceMassFraction=%g)" % kv
+                                      for kv in species.items()),
+           "diffusionModel: schmidt"] if species else []),
         "initialConditions: <%s>" % ic,
         "matrixSolver: %s" % solver,
         "matrixSweeps: %d" % sweeps,
@@ -137,7 +144,7 @@ def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air", turb=No
             f.write(" ".join("%.17g" % x for x in (*c, *v, *t, 1.0)) + "\n")
 
 
-def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None):
+def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None, mix=None):
     """Initial-condition cloud file (reference src/utility.cpp:513-520: `numberOfPoints`, species
     line, then `x y z rho u v w p tke omega mf...` per point), one point per cell centroid, with
     seed-fixed +-amplitude noise on rho, u, v, w, p. The reference assigns each cell the state of
@@ -146,10 +153,17 @@ def write_cloud(path, nodes, seed=0, amplitude=0.01, species="air", turb=None):
     cen = 0.125 * (x[:-1, :-1, :-1] + x[:-1, :-1, 1:] + x[:-1, 1:, :-1] + x[:-1, 1:, 1:] +
                    x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:]).reshape(-1, 3)
     vals, kw = _cloud_values(cen.shape[0], seed, amplitude, turb)
+    mfs = np.ones((cen.shape[0], 1))
+    if mix:  # perturbed mass fractions (10x the state noise, so that diffusion is visible)
+        species = " ".join(mix)
+        rng = np.random.default_rng(seed + 104729)
+        mfs = np.array(list(mix.values()))[None, :] * (
+            1.0 + 10.0 * amplitude * (2.0 * rng.random((cen.shape[0], len(mix))) - 1.0))
+        mfs /= mfs.sum(axis=1, keepdims=True)
     with open(path, "w") as f:
         f.write("%d\n%s\n" % (cen.shape[0], species))
-        for c, v, t in zip(cen, vals, kw):
-            f.write(" ".join("%.17g" % x for x in (*c, *v, *t, 1.0)) + "\n")
+        for c, v, t, m in zip(cen, vals, kw, mfs):
+            f.write(" ".join("%.17g" % x for x in (*c, *v, *t, *m)) + "\n")
 
 
 def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
@@ -160,7 +174,8 @@ def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
     nodes = box_nodes(ni, nj, nk, lengths=(size, size, size), warp=0.02 * size, period=size)
     write_plot3d(os.path.join(case_dir, name + ".xyz"), [nodes])
     if perturb is not None:
-        write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb, turb=kw.get("turb"))
+        write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb, turb=kw.get("turb"),
+                    mix=kw.get("species"))
         kw["ic_file"] = "ic.dat"
     with open(os.path.join(case_dir, name + ".inp"), "w") as f:
         f.write(inp_text(name, ni, nj, nk, **kw))

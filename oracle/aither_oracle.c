@@ -1268,7 +1268,7 @@ static const double *farea(const orc_block *b, int d, int i, int j, int k) {
  * (I), :5378-5508 (J), :5584-5714 (K); src/utility.cpp:59-175 */
 static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
                            int j, int k, double vg[9], double tg[3],
-                           double kg[3], double wg[3]) {
+                           double kg[3], double wg[3], double (*mg)[3]) {
   const int ns = h->ns, neq = h->neq;
   const int e3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   const int *ed = e3[d];
@@ -1345,6 +1345,33 @@ static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
   }
   if (nval == 4) {
     for (int r = 0; r < 3; ++r) kg[r] = wg[r] = 0.0;
+  }
+  /* mass-fraction gradients (multi-species; ref: src/procBlock.cpp:5347-5376) */
+  if (ns > 1 && mg) {
+    for (int ss = 0; ss < ns; ++ss) {
+      double ml[3], mu_[3];
+#define MFV(cell) (b->state[neq * (cell) + ss] / rho_of(h, b->state + neq * (cell)))
+      for (int q = 0; q < 3; ++q) {
+        if (q == d) {
+          ml[q] = MFV(cLo);
+          mu_[q] = MFV(cHi);
+        } else {
+          const int *eq = e3[q];
+          const long up0 = cidx(b, i + eq[0], j + eq[1], k + eq[2]);
+          const long up1 = cidx(b, i + eq[0] - ed[0], j + eq[1] - ed[1], k + eq[2] - ed[2]);
+          const long lo0 = cidx(b, i - eq[0], j - eq[1], k - eq[2]);
+          const long lo1 = cidx(b, i - eq[0] - ed[0], j - eq[1] - ed[1], k - eq[2] - ed[2]);
+          mu_[q] = 0.25 * (MFV(cLo) + MFV(cHi) + MFV(up0) + MFV(up1));
+          ml[q] = 0.25 * (MFV(cLo) + MFV(cHi) + MFV(lo0) + MFV(lo1));
+        }
+      }
+#undef MFV
+      for (int r = 0; r < 3; ++r) {
+        const double t = mu_[0] * au[0][r] - ml[0] * al[0][r] + mu_[1] * au[1][r] -
+                         ml[1] * al[1][r] + mu_[2] * au[2][r] - ml[2] * al[2][r];
+        mg[ss][r] = t * invVol;
+      }
+    }
   }
 }
 
@@ -1572,8 +1599,8 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
     for (int jj = 0; jj < b->nj + dj; ++jj)
       for (int ii = 0; ii < b->ni + di; ++ii) {
         const int fi = d == 0 ? ii : (d == 1 ? jj : kk);
-        double vg[9], tg[3], kg[3], wg[3];
-        face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg);
+        double vg[9], tg[3], kg[3], wg[3], mg[AITHER_MAX_SPECIES][3];
+        face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg, mg);
         double state[MAXEQ], mu, wDist = 0.0;
 #define CL(o) cidx(b, ii + (o)*di, jj + (o)*dj, kk + (o)*dk)
         if (h->cfg.viscRecon == 0) { /* central; ref: :1305-1321 */
@@ -1623,8 +1650,40 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           mass_fractions(h, state, mf);
           kt = muts * cp_mix(h, mf) / turb_prandtl(h);
         }
+        /* species diffusion with the zero-net-mass-flux rescale; not at low-Re wall faces,
+         * whose CalcWallFlux has no species terms (ref: src/viscousFlux.cpp:84-105,137-196) */
+        double speciesEnthalpyTerm = 0.0;
+        int isLowReWall = 0;
+        if (fi == 0 || fi == nd[d]) {
+          const aither_surface *sf = find_surface(b, ii, jj, kk, 2 * d + (fi == 0 ? 1 : 2));
+          isLowReWall = sf->type == AITHER_BC_VISCOUS_WALL;
+        }
+        if (ns > 1 && !isLowReWall) {
+          /* schmidt::DiffCoeff (include/diffusion.hpp:100-105; Sc_t = 0.7, turbulence.hpp:71);
+           * diffusionModel none: 0 */
+          const double dc =
+              h->cfg.schmidt > 0.0 ? mus / h->cfg.schmidt + muts / 0.7 : 0.0;
+          double posDiff = 0.0, negDiff = 0.0;
+          for (int ss = 0; ss < ns; ++ss) {
+            flux[ss] = dc * dot3(mg[ss], fa);
+            negDiff -= flux[ss] < 0.0 ? flux[ss] : 0.0;
+            posDiff += flux[ss] > 0.0 ? flux[ss] : 0.0;
+          }
+          const double posDiffFac = posDiff > negDiff ? negDiff / posDiff : 1.0;
+          const double negDiffFac = negDiff > posDiff ? posDiff / negDiff : 1.0;
+          const double tf = temperature_of(h, state);
+          const double vel = vel_mag(h, state);
+          for (int ss = 0; ss < ns; ++ss) {
+            flux[ss] *= flux[ss] > 0.0 ? posDiffFac : negDiffFac;
+            const double hs = (h->cfg.hf[ss] +
+                               h->cfg.gasConstant[ss] * (h->cfg.n[ss] + 1.0) * tf) +
+                              0.5 * vel * vel;
+            speciesEnthalpyTerm += flux[ss] * hs;
+          }
+        }
         flux[ns + 3] = (tau[0] * state[ns] + tau[1] * state[ns + 1] + tau[2] * state[ns + 2]) +
-                       (kcond + kt) * (tg[0] * fa[0] + tg[1] * fa[1] + tg[2] * fa[2]) + 0.0;
+                       (kcond + kt) * (tg[0] * fa[0] + tg[1] * fa[1] + tg[2] * fa[2]) +
+                       speciesEnthalpyTerm;
         if (rans) {
           const double mutt = is_sst(h) ? muts
                                         : h->cfg.nondimScaling * eddy_visc_no_lim(h, state);

@@ -227,7 +227,8 @@ void DumpConfig(Dump &d, const input &inp, const physics &phys) {
     d.vec("cfg/suthCondS", ks);
     d.vec("cfg/molarMass", mm);
   }
-  d.scalar("cfg/schmidt", inp.SchmidtNumber());
+  // diffusionModel: none -> no species diffusion (reference src/input.cpp:810-823)
+  d.scalar("cfg/schmidt", inp.DiffusionModel() == "schmidt" ? inp.SchmidtNumber() : -1.0);
   // boundary-condition state table (already nondimensional)
   const int nb = inp.bcStates_.size();
   d.iscalar("cfg/numBCStates", nb);

@@ -27,7 +27,10 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_v
                 "turbFlatPlate", "box_sst", "box_kw",
                 # block-matrix solvers (bdplur / blusgs: Rusanov + thin-shear-layer flux Jacobians,
                 # turbulence source Jacobian, Gauss-Jordan inverse) and the approximateRoe Jacobian
-                "box_bdplur", "box_blusgs_visc", "box_sst_blusgs", "box_roe_jac"]
+                "box_bdplur", "box_blusgs_visc", "box_sst_blusgs", "box_roe_jac",
+                # three species: Wilke mixing, Schmidt-number diffusion with the zero-net-flux
+                # rescale, species enthalpy transport; laminar / SST / inviscid, AUSMPW+ and Roe
+                "box_mix3_visc", "box_mix3_sst", "box_mix3_euler", "box_mix3_roe"]
 
 
 # viscousFlatPlate runs at CFL 1e4 from a uniform start: the implicit update is the solution of a
@@ -50,9 +53,23 @@ def test_oracle_phases_match_reference(name):
                                         ("box_visc4", 12), ("box_visc_iso", 12),
                                         ("turbFlatPlate", 20), ("box_sst", 12), ("box_kw", 12),
                                         ("box_bdplur", 12), ("box_blusgs_visc", 12),
-                                        ("box_sst_blusgs", 12), ("box_roe_jac", 12)])
+                                        ("box_sst_blusgs", 12), ("box_roe_jac", 12),
+                                        ("box_mix3_visc", 12), ("box_mix3_sst", 12),
+                                        ("box_mix3_euler", 12), ("box_mix3_roe", 3)])
 def test_oracle_history_matches_reference(name, iters):
     """L2 history within 1e-9 relative (north_star bar) + the reference's regression goldens."""
     d = gc.load(name)
     worst = gc.check_history(oracle.OracleLevel, d, iters, 1e-9, name=name)
     assert worst <= 1e-9
+
+
+def test_oracle_supersonic_mixing():
+    """testCases/supersonicMixing as shipped (BASELINE configs[4]'s base; regressionTests.py:515-540):
+    H2O / H2 / N2, Schmidt diffusion, SST 2003, AUSMPW+, minmod, 4th-order viscous reconstruction,
+    LU-SGS x2, 5 blocks. The fixture (26 MB: ghost-padded metrics of five 2-D blocks) is not
+    committed; `python tests/golden/make_golden.py supersonicMixing` regenerates it."""
+    import os
+    if not os.path.exists(os.path.join(gc.GOLDEN_DIR, "supersonicMixing.npz")):
+        pytest.skip("tests/golden/supersonicMixing.npz has not been generated")
+    d = gc.load("supersonicMixing")
+    assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
