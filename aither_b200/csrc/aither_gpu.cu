@@ -244,7 +244,8 @@ int SurfaceType(const aither_surface &s) {
 }
 
 bool Supported(const aither_cfg &c, std::string *why) {
-  if (c.numSpecies != 1) { *why = "only single-species gas is built in this round"; return false; }
+  if (c.numSpecies != 1 && c.numSpecies != 3) { *why = "numSpecies must be 1 or 3 (kernels are instantiated for these counts)"; return false; }
+  if (c.numSpecies > 1 && c.isBlockMatrix) { *why = "block-matrix solvers are built for one species (species rows of the thin-shear-layer Jacobian)"; return false; }
   if (c.numTurb != 0 || c.isRANS) {
     if (c.numTurb != 2 || !c.isRANS || !c.isViscous) { *why = "RANS needs numTurb = 2 and isViscous"; return false; }
     if (c.turbModel != AITHER_TURB_KW_WILCOX && c.turbModel != AITHER_TURB_SST) {
@@ -356,12 +357,15 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
 }
 
 template <int NS, int NT>
-void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t stream, bool block) {
+void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t stream, bool block,
+                    const EdgeSurf *surfs, int nsurf) {
   if (block) {
-    RansCellKernel<NS, NT, true><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 0);
+    if constexpr (NS == 1) {
+      RansCellKernel<NS, NT, true><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 0, surfs, nsurf);
+    }
   } else {
-    if constexpr (NT > 0) {
-      RansCellKernel<NS, NT, false><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1);
+    if constexpr (NT > 0 || NS > 1) {
+      RansCellKernel<NS, NT, false><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1, surfs, nsurf);
     }
   }
 }
@@ -456,9 +460,11 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
   const bool block = h->jac == kJacBlock;
   for (auto &hb : h->blocks) {
     LaunchResidual<NS, NT>(h, hb, fusePrep, cfl);
-    if (block) {
-      ScopedLaunch sl(h, kFamResidual);
-      LaunchBlockDiagInv<NS, NT>(h, hb);
+    if constexpr (NS == 1) {
+      if (block) {
+        ScopedLaunch sl(h, kFamResidual);
+        LaunchBlockDiagInv<NS, NT>(h, hb);
+      }
     }
   }
   CK(cudaGetLastError());
@@ -483,12 +489,12 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
       const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
       AuxKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
     }
-    if (NT > 0 || block) {
-      // RANS and / or block matrix: viscous (+ turbulent) fluxes, cell averages, spectral radii,
+    if (NT > 0 || block || NS > 1) {
+      // RANS, multi-species and / or block matrix: viscous (+ turbulent) fluxes, cell averages, spectral radii,
       // source terms and the thin-shear-layer Jacobians, per cell
       ScopedLaunch sl(h, kFamViscFlux);
       const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
-      LaunchRansCell<NS, NT>(b, h->params, grid, h->stream, block);
+      LaunchRansCell<NS, NT>(b, h->params, grid, h->stream, block, hb.dEdgeSurfs, hb.nEdgeSurfs);
       continue;
     }
     {
@@ -515,11 +521,13 @@ template <int NS, int NT>
 int PhasePrepT(aither_gpu *h, double cfl, int bits) {
   for (auto &hb : h->blocks) {
     ScopedLaunch sl(h, kFamPrep);
-    if (h->jac == kJacBlock) {
-      const BlockDev &b = hb.dev;
-      const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
-      PrepBlockKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, h->params, cfl, bits,
-                                                                     h->dFlag);
+    if (NS == 1 && h->jac == kJacBlock) {
+      if constexpr (NS == 1) {
+        const BlockDev &b = hb.dev;
+        const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
+        PrepBlockKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, h->params, cfl, bits,
+                                                                       h->dFlag);
+      }
     } else {
       PrepKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, cfl, bits);
     }
@@ -535,7 +543,7 @@ int SwapUpdate(aither_gpu *h) {
 
 template <int NS, int NT, int JAC>
 int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
-  constexpr bool kCell = NT > 0 || JAC != kJacScalar;  // cell-parallel implicit kernels
+  constexpr bool kCell = NT > 0 || JAC != kJacScalar || NS > 1;  // cell-parallel implicit kernels
   const bool fullGSAlways = h->cfg.matrixRequiresInit != 0;
   for (int s = 0; s < sweeps; ++s) {
     if (SwapUpdate(h)) return 1;
@@ -550,10 +558,9 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
             else
               DplurKernel<NS, NT, JAC><<<hb.cell128Grid, dim3(32, 4, 1), 0, h->stream>>>(
                   hb.dev, h->params, hb.dev.x, hb.dev.xalt);
-          } else if (h->tmaImplicit) {
-            LaunchImplicitTma<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
-          } else {
-            LaunchImplicitMarch<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
+          } else if constexpr (!kCell) {
+            if (h->tmaImplicit) LaunchImplicitTma<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
+            else LaunchImplicitMarch<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0);
           }
         }
         std::swap(hb.dev.x, hb.dev.xalt);
@@ -597,12 +604,15 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
               hb.dev, h->params, h->dPartials, h->keepMatrixResid ? 1 : 0);
           nPartials = hb.cell128Grid.x * hb.cell128Grid.y * hb.cell128Grid.z;
         }
-      } else if (h->tmaImplicit) {
-        LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
-        nPartials = hb.nTmaBlocks;
-      } else {
-        LaunchImplicitMarch<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
-        nPartials = hb.nMarchBlocks;
+      } else if constexpr (!kCell) {
+        if (h->tmaImplicit) {
+          LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+          nPartials = hb.nTmaBlocks;
+        } else {
+          LaunchImplicitMarch<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr,
+                                                 h->keepMatrixResid ? 1 : 0);
+          nPartials = hb.nMarchBlocks;
+        }
       }
     }
     {
@@ -617,7 +627,9 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
 
 template <int NS, int NT>
 int PhaseRelaxT(aither_gpu *h, int sweeps, int slot) {
-  if (h->jac == kJacBlock) return PhaseRelaxJ<NS, NT, kJacBlock>(h, sweeps, slot);
+  if constexpr (NS == 1) {
+    if (h->jac == kJacBlock) return PhaseRelaxJ<NS, NT, kJacBlock>(h, sweeps, slot);
+  }
   if constexpr (NT == 0) {
     if (h->jac == kJacRoe) return PhaseRelaxJ<NS, NT, kJacRoe>(h, sweeps, slot);
   }
@@ -655,8 +667,10 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
   return 0;
 }
 
-// equation-set dispatch: one species, laminar / Euler (NT = 0) or two-equation RANS (NT = 2)
-#define EQ_DISPATCH(h, FN, ...) ((h)->nt == 0 ? FN<1, 0>(__VA_ARGS__) : FN<1, 2>(__VA_ARGS__))
+// equation-set dispatch: one or three species, laminar / Euler (NT = 0) or two-equation RANS (NT = 2)
+#define EQ_DISPATCH(h, FN, ...)                                                            \
+  ((h)->ns == 1 ? ((h)->nt == 0 ? FN<1, 0>(__VA_ARGS__) : FN<1, 2>(__VA_ARGS__))           \
+                : ((h)->nt == 0 ? FN<3, 0>(__VA_ARGS__) : FN<3, 2>(__VA_ARGS__)))
 int PhaseBoundaryConditions(aither_gpu *h) { return EQ_DISPATCH(h, PhaseBoundaryConditionsT, h); }
 int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
   return EQ_DISPATCH(h, PhaseResidualT, h, fusePrep, cfl);
@@ -809,11 +823,15 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.viscRecon = cfg->viscRecon;
   p.viscCFLCoeff = cfg->viscousCFLCoeff;
   p.tr.tRef = cfg->tRef;
-  p.tr.viscC1 = cfg->suthViscC1[0];
-  p.tr.viscS = cfg->suthViscS[0];
+  for (int q = 0; q < AITHER_MAX_SPECIES; ++q) {
+    p.tr.viscC1[q] = cfg->suthViscC1[q];
+    p.tr.viscS[q] = cfg->suthViscS[q];
+    p.tr.condC1[q] = cfg->suthCondC1[q];
+    p.tr.condS[q] = cfg->suthCondS[q];
+    p.tr.molarMass[q] = cfg->molarMass[q];
+  }
+  p.tr.schmidt = cfg->schmidt;
   p.tr.muRef = cfg->muMixRef;
-  p.tr.condC1 = cfg->suthCondC1[0];
-  p.tr.condS = cfg->suthCondS[0];
   p.tr.kRef = cfg->kMixRef;
   p.tr.scaling = cfg->nondimScaling;
   p.tr.turbModel = cfg->turbModel;
@@ -827,7 +845,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     const char *kv = getenv("AITHER_B200_KERNELS");
     h->legacyKernels = kv != nullptr && std::string(kv) == "legacy";
     // the TMA-fed sweep is inviscid-only so far; viscous runs take the register-fed march kernel
-    h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march") && !cfg->isViscous;
+    h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march") && !cfg->isViscous &&
+                     cfg->numSpecies == 1;
     const char *fp = getenv("AITHER_B200_FUSE_PREP");
     h->fusePrep = !(fp != nullptr && std::string(fp) == "0");
   }
@@ -883,7 +902,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
-                        (h->nt > 0 ? 18 : ((cfg->isViscous && cfg->isBlockMatrix) ? 9 : 0));
+                        (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) ? 9 : 0));
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
@@ -913,7 +932,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
     }
-    if (h->nt == 0 && cfg->isViscous && cfg->isBlockMatrix) b.velGrad = take(9);
+    if (h->nt == 0 && cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) b.velGrad = take(9);
     if (h->nt > 0) {
       b.eddyVisc = take(1);
       b.f1 = take(1);
@@ -1081,7 +1100,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       hb.tmaGrid = dim3((d.ni + kQI - 1) / kQI, (d.nj + kQJ - 1) / kQJ, nChunks);
       hb.nTmaBlocks = hb.tmaGrid.x * hb.tmaGrid.y * hb.tmaGrid.z;
       std::string err;
-      if (h->tmaImplicit && h->nt == 0 &&
+      if (h->tmaImplicit && h->nt == 0 && h->ns == 1 &&
           (EncodeBlockMap(&hb.tmaMaps.cell, b, hb.alloc, nFields, kQPI, kQPJ, neq, &err) ||
           EncodeBlockMap(&hb.tmaMaps.faceI, b, hb.alloc, nFields, kQAI, kQJ, 4, &err) ||
           EncodeBlockMap(&hb.tmaMaps.faceJ, b, hb.alloc, nFields, kQI, kQJ + 1, 4, &err))) {

@@ -128,7 +128,7 @@ AITHER_HD void ApproxTslJacobian(const Gas &g, const Transport &tr, const double
   const double u = s[ns], v = s[ns + 1], w = s[ns + 2];
   const double velNorm = u * n[0] + v * n[1] + w * n[2];
   const double rho = SpeciesSum<NS>(s);
-  const double k = EffectiveConductivity(tr, t);
+  const double k = MixtureEffConductivity<NS>(tr, t, s);
   const double kt = mut * Mixture<NS>(g, s).cp / TurbPrandtl(tr.turbModel);
   double tauNorm[3];
   TauNormalVg(vGrad, n, mu, mut, tauNorm);

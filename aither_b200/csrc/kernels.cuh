@@ -457,7 +457,7 @@ __device__ __forceinline__ void OffDiagOne(const BlockDev &b, const Params &p, c
                                            bool positive, long long nidx, double dist,
                                            double *od) {
   using E = Eq<NS, NT>;
-  if (JAC == kJacBlock) {
+  if constexpr (JAC == kJacBlock) {
     // RusanovBlockOffDiagonal; ref: src/fluxJacobian.cpp:164-194
     double J[Blk<NS, NT>::n];
     RusanovFluxJacobian<NS, NT>(p.gas, sn, fa, positive, J);
@@ -473,7 +473,7 @@ __device__ __forceinline__ void OffDiagOne(const BlockDev &b, const Params &p, c
       for (int q = 0; q < Blk<NS, NT>::n; ++q) J[q] = positive ? J[q] - V[q] : J[q] + V[q];
     }
     BlockMult<NS, NT>(J, dun, od);
-  } else if (JAC == kJacRoe) {
+  } else if constexpr (JAC == kJacRoe) {
     // RoeOffDiagonal; ref: src/fluxJacobian.cpp:240-296. Its caller passes (.., f1, dist, ..) into
     // parameters declared (.., dist, f1, ..), so for viscous flow the reference divides by f1 = 0;
     // only the inviscid use is built (aither_gpu_create refuses approximateRoe + viscous).

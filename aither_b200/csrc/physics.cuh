@@ -29,19 +29,82 @@ constexpr double kTurbMin = 1.0e-20;    // ref: include/turbulence.hpp:72-73
 // Gas model constants for <= AITHER_MAX_SPECIES calorically perfect species (nondimensional).
 // Sutherland transport of the (single) species; ref: src/transport.cpp:50-68,113-131
 struct Transport {
-  double tRef, viscC1, viscS, muRef, condC1, condS, kRef, scaling;
-  int turbModel;  // aither_turb
+  double tRef, muRef, kRef, scaling;
+  // Sutherland coefficients and molar mass per species (src/transport.cpp:32-68)
+  double viscC1[AITHER_MAX_SPECIES], viscS[AITHER_MAX_SPECIES];
+  double condC1[AITHER_MAX_SPECIES], condS[AITHER_MAX_SPECIES];
+  double molarMass[AITHER_MAX_SPECIES];
+  double schmidt;  // species diffusion: Schmidt number, <= 0 for `diffusionModel: none`
+  int turbModel;   // aither_turb
 };
-// ref: src/transport.cpp:113-131,173-196
-AITHER_HD double SutherlandViscosity(const Transport &tr, double t) {
+// ref: src/transport.cpp:113-131 (species), :70-110,148-192 (Wilke's mixing rule)
+AITHER_HD double SpeciesViscosity(const Transport &tr, double t, int ss) {
   const double temp = t * tr.tRef;
-  const double mu = (tr.viscC1 * (temp * sqrt(temp))) / (temp + tr.viscS);
+  const double mu = (tr.viscC1[ss] * (temp * sqrt(temp))) / (temp + tr.viscS[ss]);
   return mu / tr.muRef;
 }
-AITHER_HD double EffectiveConductivity(const Transport &tr, double t) {
+AITHER_HD double SpeciesConductivity(const Transport &tr, double t, int ss) {
   const double temp = t * tr.tRef;
-  const double k = (tr.condC1 * (temp * sqrt(temp))) / (temp + tr.condS);
-  return (k / tr.kRef) * tr.scaling;
+  const double k = (tr.condC1[ss] * (temp * sqrt(temp))) / (temp + tr.condS[ss]);
+  return k / tr.kRef;
+}
+// mixture viscosity of primitive state s (densities s[0..NS)) at temperature t
+template <int NS>
+AITHER_HD double MixtureViscosity(const Transport &tr, double t, const double *s) {
+  if (NS == 1) return SpeciesViscosity(tr, t, 0);
+  double x[NS], sv[NS], sum = 0.0, rho = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) rho += s[q];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    x[q] = (s[q] / rho) / tr.molarMass[q];
+    sum += x[q];
+    sv[q] = SpeciesViscosity(tr, t, q);
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) x[q] /= sum;
+  double mixtureVisc = 0.0;
+#pragma unroll
+  for (int ii = 0; ii < NS; ++ii) {
+    double denom = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < NS; ++jj) {
+      const double f = 1.0 + sqrt(sv[ii] / sv[jj]) * sqrt(sqrt(tr.molarMass[jj] / tr.molarMass[ii]));
+      denom += x[jj] / sqrt(1.0 + tr.molarMass[ii] / tr.molarMass[jj]) * (f * f);
+    }
+    mixtureVisc += (x[ii] * sv[ii]) / denom;
+  }
+  return 4.0 / sqrt(2.0) * mixtureVisc;
+}
+// k_eff = scaling * k_mix, k_mix = (sum x_i k_i + 1 / sum (x_i / k_i)) / 2
+template <int NS>
+AITHER_HD double MixtureEffConductivity(const Transport &tr, double t, const double *s) {
+  if (NS == 1) return SpeciesConductivity(tr, t, 0) * tr.scaling;
+  double x[NS], sum = 0.0, rho = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) rho += s[q];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    x[q] = (s[q] / rho) / tr.molarMass[q];
+    sum += x[q];
+  }
+  double weightedAvg = 0.0, harmonicAvg = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    const double xq = x[q] / sum;
+    const double sc = SpeciesConductivity(tr, t, q);
+    weightedAvg += xq * sc;
+    harmonicAvg += xq / sc;
+  }
+  harmonicAvg = 1.0 / harmonicAvg;
+  return (0.5 * (weightedAvg + harmonicAvg)) * tr.scaling;
+}
+// single-species forms (the laminar scalar path)
+AITHER_HD double SutherlandViscosity(const Transport &tr, double t) {
+  return SpeciesViscosity(tr, t, 0);
+}
+AITHER_HD double EffectiveConductivity(const Transport &tr, double t) {
+  return SpeciesConductivity(tr, t, 0) * tr.scaling;
 }
 // turbulent Prandtl number: 0.9 (include/turbulence.hpp:70), k-omega 2006 8/9 (:398), SST 0.9 (:500)
 AITHER_HD double TurbPrandtl(int turbModel) {
@@ -975,7 +1038,7 @@ AITHER_HD void ApplyFarfieldTurb(const Gas &g, const Transport *tr, double *s, d
   const double vmag = sqrt(vx * vx + vy * vy + vz * vz);
   const double tv = bc.turbulenceIntensity * vmag;
   s[E::it] = 1.5 * (tv * tv);
-  const double mu = SutherlandViscosity(*tr, Temperature<NS>(g, s));
+  const double mu = MixtureViscosity<NS>(*tr, Temperature<NS>(g, s), s);
   s[E::it + (NT > 1 ? 1 : 0)] = SpeciesSum<NS>(s) * s[E::it] / (bc.eddyViscosityRatio * mu);
 #pragma unroll
   for (int t = 0; t < NT; ++t) s[E::it + t] = fmax(s[E::it + t], kTurbMin);

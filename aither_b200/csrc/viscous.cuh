@@ -40,7 +40,7 @@ AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double 
     if (bc.isIsothermal) {
       tGhost = 2.0 * bc.temperature - tInt;
     } else {
-      const double kappa = EffectiveConductivity(tr, tInt);
+      const double kappa = MixtureEffConductivity<NS>(tr, tInt, interior);
       tGhost = tInt - bc.heatFlux / kappa * 2.0 * wallDist;
     }
     const double rhoInt = SpeciesSum<NS>(interior);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) AuxKernel(BlockDev b, Params p) {
   LoadCell<NS + 4 + NT>(b.state, b.fs, idx, s);
   const double t = Temperature<NS>(p.gas, s);
   b.temperature[idx] = t;
-  b.viscosity[idx] = SutherlandViscosity(p.tr, t);
+  b.viscosity[idx] = MixtureViscosity<NS>(p.tr, t, s);
 }
 
 // projected centre-to-centre distance across every face (geometry only; built once):
@@ -489,7 +489,7 @@ struct FaceOut {
 
 template <int NS, int NT, int D>
 __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, long long idx,
-                                         FaceOut<NS + 4 + NT> &o) {
+                                         FaceOut<NS + 4 + NT> &o, bool lowReWall = false) {
   using E = Eq<NS, NT>;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
   constexpr int NG = NT > 0 ? 6 : 4;
@@ -612,15 +612,64 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
     tau[r] = lambda * trace * n[r] + (mus + muts) * mm;
   }
   const double t = Temperature<NS>(p.gas, fs_);
-  const double kcond = EffectiveConductivity(p.tr, t);
+  const double kcond = MixtureEffConductivity<NS>(p.tr, t, fs_);
   // sutherland::TurbConductivity: mu_t cp / Pr_t (include/transport.hpp:132-137)
   const double kt = muts * Mixture<NS>(p.gas, fs_).cp / TurbPrandtl(p.tr.turbModel);
-  const double fe = (tau[0] * fs_[E::imx] + tau[1] * fs_[E::imy] + tau[2] * fs_[E::imz]) +
-                    (kcond + kt) * (grad[3][0] * n[0] + grad[3][1] * n[1] + grad[3][2] * n[2]) + 0.0;
-  // k and omega diffusion; k-omega 2006 uses the unlimited eddy viscosity here
-  // (ref: src/viscousFlux.cpp:117-134, include/turbulence.hpp:439)
 #pragma unroll
   for (int q = 0; q < NS; ++q) o.flux[q] = 0.0;
+  double speciesEnthalpyTerm = 0.0;
+  if (NS > 1 && !lowReWall) {
+    // species diffusion D grad(Y_s).n with D = mu / Sc + mu_t / Sc_t (Sc_t = 0.7), rescaled so
+    // that the positive and negative fluxes cancel, and the enthalpy it carries; a low-Re wall
+    // face has none (ref: src/viscousFlux.cpp:84-105 vs :137-196; procBlock.cpp:5347-5376)
+    const double dc = p.tr.schmidt > 0.0 ? mus / p.tr.schmidt + muts / 0.7 : 0.0;
+    double fl[NS], posDiff = 0.0, negDiff = 0.0;
+#pragma unroll
+    for (int ss = 0; ss < NS; ++ss) {
+      auto Y = [&](long long c) {
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) r += __ldg(b.state + q * b.fs + c);
+        return __ldg(b.state + ss * b.fs + c) / r;
+      };
+      const double lo = Y(idx - sd), hi = Y(idx);
+      double g3[3], vl[3], vu[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (q == D) {
+          vl[q] = lo;
+          vu[q] = hi;
+        } else {
+          vu[q] = 0.25 * (lo + hi + Y(idx + st[q]) + Y(idx + st[q] - sd));
+          vl[q] = 0.25 * (lo + hi + Y(idx - st[q]) + Y(idx - st[q] - sd));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double tt = vu[0] * au[0][r] - vl[0] * al[0][r] + vu[1] * au[1][r] - vl[1] * al[1][r] +
+                          vu[2] * au[2][r] - vl[2] * al[2][r];
+        g3[r] = tt * invVol;
+      }
+      fl[ss] = dc * Dot3(g3, n);
+      negDiff -= fmin(fl[ss], 0.0);
+      posDiff += fmax(fl[ss], 0.0);
+    }
+    const double posFac = posDiff > negDiff ? negDiff / posDiff : 1.0;
+    const double negFac = negDiff > posDiff ? posDiff / negDiff : 1.0;
+    const double vmag = sqrt(VelMagSq<NS>(fs_));
+#pragma unroll
+    for (int ss = 0; ss < NS; ++ss) {
+      fl[ss] *= fl[ss] > 0.0 ? posFac : negFac;
+      const double hs = (p.gas.hf[ss] + (p.gas.R[ss] * (p.gas.n[ss] + 1.0)) * t) + 0.5 * vmag * vmag;
+      speciesEnthalpyTerm += fl[ss] * hs;
+      o.flux[ss] = fl[ss] * mag;
+    }
+  }
+  const double fe = (tau[0] * fs_[E::imx] + tau[1] * fs_[E::imy] + tau[2] * fs_[E::imz]) +
+                    (kcond + kt) * (grad[3][0] * n[0] + grad[3][1] * n[1] + grad[3][2] * n[2]) +
+                    speciesEnthalpyTerm;
+  // k and omega diffusion; k-omega 2006 uses the unlimited eddy viscosity here
+  // (ref: src/viscousFlux.cpp:117-134, include/turbulence.hpp:439)
   o.flux[E::imx] = tau[0] * mag;
   o.flux[E::imy] = tau[1] * mag;
   o.flux[E::imz] = tau[2] * mag;
@@ -644,16 +693,17 @@ struct RansAcc {
 template <int NS, int NT, int D, bool BLOCK>
 __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Params &p, long long idx,
                                                   const double *s, double visc, double vol,
-                                                  RansAcc<NS, NT> &a, double *dblk) {
+                                                  RansAcc<NS, NT> &a, double *dblk, bool wallLo,
+                                                  bool wallHi) {
   using E = Eq<NS, NT>;
   constexpr double sixth = 1.0 / 6.0;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
   const long long sd = Stride(b, D);
   FaceOut<E::neq> f;
   // lower face: this cell is the face's upper cell (ref: :1432-1493)
-  RansFace<NS, NT, D>(b, p, idx, f);
+  RansFace<NS, NT, D>(b, p, idx, f, wallLo);
 #pragma unroll
-  for (int e = NS; e < E::neq; ++e) a.r[e] += f.flux[e];
+  for (int e = (NS > 1 ? 0 : NS); e < E::neq; ++e) a.r[e] += f.flux[e];
   const double mutLo = f.mut, f1Lo = f.f1;
 #pragma unroll
   for (int q = 0; q < 9; ++q) a.vg[q] += sixth * f.vg[q];
@@ -678,7 +728,7 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
     a.dg += 2.0 * vsr;
     a.dgT += 2.0 * tvsr;
   }
-  if (BLOCK) {  // + dFv/dU of the lower face (left = false); ref: src/procBlock.cpp:1481-1489
+  if constexpr (BLOCK) {  // + dFv/dU of the lower face (left = false); ref: src/procBlock.cpp:1481-1489
     double fa[4], J[Blk<NS, NT>::n];
 #pragma unroll
     for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[D] + q * b.fs + idx);
@@ -688,10 +738,10 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
     for (int q = 0; q < Blk<NS, NT>::n; ++q) dblk[q] += J[q];
   }
   // upper face: this cell is the face's lower cell (ref: :1392-1429)
-  RansFace<NS, NT, D>(b, p, idx + sd, f);
+  RansFace<NS, NT, D>(b, p, idx + sd, f, wallHi);
 #pragma unroll
-  for (int e = NS; e < E::neq; ++e) a.r[e] -= f.flux[e];
-  if (BLOCK) {  // - dFv/dU of the upper face (left = true); ref: src/procBlock.cpp:1420-1428
+  for (int e = (NS > 1 ? 0 : NS); e < E::neq; ++e) a.r[e] -= f.flux[e];
+  if constexpr (BLOCK) {  // - dFv/dU of the upper face (left = true); ref: src/procBlock.cpp:1420-1428
     double fa[4], J[Blk<NS, NT>::n];
 #pragma unroll
     for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[D] + q * b.fs + idx + sd);
@@ -714,7 +764,8 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
 
 template <int NS, int NT, bool BLOCK>
 __global__ void __launch_bounds__(128)
-    RansCellKernel(BlockDev b, Params p, int implicitScalar) {
+    RansCellKernel(BlockDev b, Params p, int implicitScalar, const EdgeSurf *__restrict__ surfs,
+                   int nsurf) {
   using E = Eq<NS, NT>;
   using B = Blk<NS, NT>;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
@@ -744,9 +795,27 @@ __global__ void __launch_bounds__(128)
   for (int q = 0; q < 9; ++q) a.vg[q] = 0.0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) a.kg[q] = a.wg[q] = 0.0;
-  RansAccumulateDir<NS, NT, 0, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
-  RansAccumulateDir<NS, NT, 1, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
-  RansAccumulateDir<NS, NT, 2, BLOCK>(b, p, idx, s, visc, vol, a, dblk);
+  // multi-species: boundary faces on a viscous wall carry no species diffusion
+  bool wl[3] = {false, false, false}, wh[3] = {false, false, false};
+  if (NS > 1) {
+    const int c[3] = {i, j, k}, nd[3] = {b.ni, b.nj, b.nk};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (c[d] == 0) {
+        const int sf = FindSurface(surfs, nsurf, c, 2 * d + 1);
+        wl[d] = sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL;
+      }
+      if (c[d] == nd[d] - 1) {
+        int cu[3] = {i, j, k};
+        cu[d] += 1;
+        const int sf = FindSurface(surfs, nsurf, cu, 2 * d + 2);
+        wh[d] = sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL;
+      }
+    }
+  }
+  RansAccumulateDir<NS, NT, 0, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[0], wh[0]);
+  RansAccumulateDir<NS, NT, 1, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[1], wh[1]);
+  RansAccumulateDir<NS, NT, 2, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[2], wh[2]);
   if (NT > 0) {
     // source terms (ref: src/procBlock.cpp:5956-6025, src/source.cpp:64-82)
     double src[2], beta = 0.0;
@@ -765,7 +834,7 @@ __global__ void __launch_bounds__(128)
     }
   }
 #pragma unroll
-  for (int e = NS; e < E::neq; ++e) b.resid[e * b.fs + idx] = a.r[e];
+  for (int e = (NS > 1 ? 0 : NS); e < E::neq; ++e) b.resid[e * b.fs + idx] = a.r[e];
   b.specRad[idx] = a.sr;
   b.specRad[b.fs + idx] = a.srT;
   if (implicitScalar) {

@@ -86,8 +86,13 @@ void hs_offdiag_fast(const aither_cfg *c, const double *s, const double *du, con
 // ---- RANS point functions (turbulence.cuh) and the NT = 2 variants ---------------------------
 static Transport TransportFromCfg(const aither_cfg *c) {
   Transport t;
-  t.tRef = c->tRef; t.viscC1 = c->suthViscC1[0]; t.viscS = c->suthViscS[0]; t.muRef = c->muMixRef;
-  t.condC1 = c->suthCondC1[0]; t.condS = c->suthCondS[0]; t.kRef = c->kMixRef;
+  t.tRef = c->tRef; t.muRef = c->muMixRef; t.kRef = c->kMixRef;
+  for (int q = 0; q < AITHER_MAX_SPECIES; ++q) {
+    t.viscC1[q] = c->suthViscC1[q]; t.viscS[q] = c->suthViscS[q];
+    t.condC1[q] = c->suthCondC1[q]; t.condS[q] = c->suthCondS[q];
+    t.molarMass[q] = c->molarMass[q];
+  }
+  t.schmidt = c->schmidt;
   t.scaling = c->nondimScaling; t.turbModel = c->turbModel;
   return t;
 }

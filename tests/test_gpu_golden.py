@@ -18,7 +18,9 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_v
                 # RANS: k-omega Wilcox 2006 (reference regression case + AUSM box) and SST 2003
                 "turbFlatPlate", "box_sst", "box_kw",
                 # block-matrix solvers (bdplur, blusgs laminar / SST) and the approximateRoe Jacobian
-                "box_bdplur", "box_blusgs_visc", "box_sst_blusgs", "box_roe_jac"]
+                "box_bdplur", "box_blusgs_visc", "box_sst_blusgs", "box_roe_jac",
+                # three species (H2O / H2 / N2): Wilke mixing, Schmidt diffusion, species enthalpy
+                "box_mix3_visc", "box_mix3_sst", "box_mix3_euler", "box_mix3_roe"]
 
 
 def make_gpu_level(prob):
@@ -54,7 +56,9 @@ def test_gpu_phases_match_reference(name):
                                         ("box_visc4", 12), ("box_visc_iso", 12),
                                         ("turbFlatPlate", 20), ("box_sst", 12), ("box_kw", 12),
                                         ("box_bdplur", 12), ("box_blusgs_visc", 12),
-                                        ("box_sst_blusgs", 12), ("box_roe_jac", 12)])
+                                        ("box_sst_blusgs", 12), ("box_roe_jac", 12),
+                                        ("box_mix3_visc", 12), ("box_mix3_sst", 12),
+                                        ("box_mix3_euler", 12), ("box_mix3_roe", 3)])
 def test_gpu_history_matches_reference(name, iters):
     d = gc.load(name)
     worst = gc.check_history(make_gpu_level, d, iters, 1e-9, name=name)
