@@ -92,7 +92,9 @@ struct aither_gpu {
   cudaStream_t stream = nullptr;
   std::vector<HostBlock> blocks;
   std::vector<aither_conn> conns;
-  HaloPlan halo;
+  HaloPlan halo;      // every connection with its tangential extension (the reference's swap)
+  HaloPlan haloFace;  // ghost cells straight behind the patches only: one level
+  bool stateNeedsEdges = false;  // viscous stencils read the edge ghost cells of the state
   aither_bc_state *dBcStates = nullptr;
   double *dPartials = nullptr;    // per-thread-block partial sums
   LinfCand *dLinfPartials = nullptr;
@@ -408,6 +410,9 @@ int Exchange(aither_gpu *h, int which) {
   // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update),
   // src/procBlock.cpp:3064-3085 (eddy viscosity + f1 + f2: three contiguous fields; velocity gradient)
   if (h->halo.nConn == 0) return 0;
+  // only the state of viscous runs needs the edge ghost cells (Green-Gauss stencils); everything
+  // else is read face-normal and takes the single-level plan
+  HaloPlan &plan = (which == kHaloState && h->stateNeedsEdges) ? h->halo : h->haloFace;
   const int total = which == kHaloTurb ? 3 : (which == kHaloVelGrad ? 9 : h->neq);
   for (int done = 0; done < total;) {
     const int nc = std::min(total - done, h->neq);  // the plan's buffers hold neq components
@@ -423,7 +428,7 @@ int Exchange(aither_gpu *h, int which) {
     ScopedLaunch sl(h, kFamHalo);
     h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
     h->famLaunches[kFamHalo]--;
-    if (HaloExchange(h->halo, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
+    if (HaloExchange(plan, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
       return Fail(HaloError());
     done += nc;
   }
@@ -748,6 +753,7 @@ void FreeAll(aither_gpu *h) {
       if (p) cudaFree(p);
   }
   HaloDestroy(h->halo);
+  HaloDestroy(h->haloFace);
   if (h->dBcStates) cudaFree(h->dBcStates);
   if (h->dFlag) cudaFree(h->dFlag);
   if (h->dPartials) cudaFree(h->dPartials);
@@ -1123,7 +1129,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     std::vector<const BlockDev *> devs;
     std::vector<int> gpos;
     for (auto &hb : h->blocks) { devs.push_back(&hb.dev); gpos.push_back(hb.globalPos); }
-    if (HaloBuild(h->halo, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm)) {
+    const char *he = getenv("AITHER_B200_HALO_EDGES");  // A/B switch: 1 = always the full plan
+    h->stateNeedsEdges = cfg->isViscous != 0 || (he != nullptr && std::string(he) == "1");
+    if (HaloBuild(h->halo, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm) ||
+        HaloBuild(h->haloFace, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm,
+                  !(he != nullptr && std::string(he) == "1"))) {
       Fail(HaloError());
       FreeAll(h);
       return 1;
@@ -1459,7 +1469,7 @@ int aither_gpu_comm_destroy(void *comm) {
 }
 int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells) {
   if (!h) return Fail("null handle");
-  if (levels) *levels = static_cast<int>(h->halo.levels.size());
+  if (levels) *levels = static_cast<int>(h->halo.levels.size());  // the reference-order plan
   if (remoteCells) *remoteCells = h->halo.bytesPerExchangeRemote;
   return 0;
 }

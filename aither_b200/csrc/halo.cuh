@@ -323,9 +323,16 @@ inline int HaloUpload(HaloPlan &plan, const std::vector<T> &v, T **out) {
 
 // Compile the connections this rank takes part in. `conns` is the full (global) list in the
 // reference's order; every rank derives the same levels from it.
+// `faceOnly`: keep only the ghost cells straight behind each patch (no tangential extension into
+// the edge ghost cells). Those are all that the inviscid stencils, the implicit off-diagonals and
+// the turbulence / gradient exchanges read; without the extension no two connections touch the
+// same cell, every connection lands in ONE level (one pack + one NCCL group + one unpack per
+// exchange instead of three for a Cartesian decomposition), and what is written there is
+// bit-identical to the full plan's.
 inline int HaloBuild(HaloPlan &plan, const std::vector<aither_conn> &conns,
                      const std::vector<const BlockDev *> &devs, const std::vector<int> &globalPos,
-                     int maxComp, int g, int rank, int nRanks, void *ncclComm) {
+                     int maxComp, int g, int rank, int nRanks, void *ncclComm,
+                     bool faceOnly = false) {
   (void)globalPos;
   plan.nConn = static_cast<int>(conns.size());
   plan.rank = rank;
@@ -340,6 +347,7 @@ inline int HaloBuild(HaloPlan &plan, const std::vector<aither_conn> &conns,
   struct RW { int rk[2], lb[2]; Box rd[2], wr[2]; };
   std::vector<RW> rw(nc);
   std::vector<AcceptorMap> maps(2 * static_cast<size_t>(nc));
+  std::vector<Box> faceRead(2 * static_cast<size_t>(nc));
   for (int c = 0; c < nc; ++c) {
     const ConnView v = ViewOf(conns[c]);
     if (conns[c].orientation < 1 || conns[c].orientation > 8)
@@ -352,8 +360,50 @@ inline int HaloBuild(HaloPlan &plan, const std::vector<aither_conn> &conns,
       if (maps[2 * c + s].slice.size() == 1 && maps[2 * c + s].slice[0] < 0)
         return HaloFail("halo: connection " + std::to_string(c) + " patches do not match in size");
       rw[c].wr[s] = maps[2 * c + s].written;
+      if (faceOnly) {
+        // drop the pairs whose target lies outside the patch's own tangential range, then take
+        // the bounding boxes of what is still written and of the donor cells still read
+        AcceptorMap &m = maps[2 * c + s];
+        int d3, d1, d2;
+        Dirs(v.boundary[s], &d3, &d1, &d2);
+        const Box don = DonorBox(v, 1 - s, g);
+        const int sn0 = don.hi[0] - don.lo[0], sn1 = don.hi[1] - don.lo[1];
+        AcceptorMap f;
+        Box wr = {{1 << 30, 1 << 30, 1 << 30}, {-(1 << 30), -(1 << 30), -(1 << 30)}};
+        Box rd = wr;
+        std::vector<int> donorCell;
+        for (size_t n = 0; n < m.slice.size(); ++n) {
+          const int *cc = &m.cell[3 * n];
+          if (cc[d1] < v.d1s[s] || cc[d1] >= v.d1e[s] || cc[d2] < v.d2s[s] || cc[d2] >= v.d2e[s])
+            continue;
+          f.cell.insert(f.cell.end(), cc, cc + 3);
+          const int sp = m.slice[n];
+          const int dc[3] = {don.lo[0] + sp % sn0, don.lo[1] + (sp / sn0) % sn1,
+                             don.lo[2] + sp / (sn0 * sn1)};
+          donorCell.insert(donorCell.end(), dc, dc + 3);
+          for (int q = 0; q < 3; ++q) {
+            wr.lo[q] = std::min(wr.lo[q], cc[q]);
+            wr.hi[q] = std::max(wr.hi[q], cc[q] + 1);
+            rd.lo[q] = std::min(rd.lo[q], dc[q]);
+            rd.hi[q] = std::max(rd.hi[q], dc[q] + 1);
+          }
+        }
+        // slice positions inside the clipped donor box (the slice that is packed and sent)
+        const int rn0 = rd.hi[0] - rd.lo[0], rn1 = rd.hi[1] - rd.lo[1];
+        for (size_t n = 0; n < donorCell.size() / 3; ++n) {
+          const int *dc = &donorCell[3 * n];
+          f.slice.push_back((dc[0] - rd.lo[0]) + rn0 * ((dc[1] - rd.lo[1]) + rn1 * (dc[2] - rd.lo[2])));
+        }
+        f.written = wr;
+        m = f;
+        rw[c].wr[s] = wr;
+        faceRead[2 * c + (1 - s)] = rd;  // what the donor side (1 - s) must provide
+      }
     }
   }
+  if (faceOnly)
+    for (int c = 0; c < nc; ++c)
+      for (int s = 0; s < 2; ++s) rw[c].rd[s] = faceRead[2 * c + s];
   std::vector<int> level(nc, 0);
   int nLevels = 0;
   for (int c = 0; c < nc; ++c) {
