@@ -83,7 +83,7 @@ typedef struct aither_bc_state {
 /* POD snapshot of the reference's `input` + `physics` objects: only what the
  * hot path branches on (src/input.cpp:674-721,1110-1144) or evaluates. */
 typedef struct aither_cfg {
-  int numSpecies;                /* ns; neq = ns + 4 + numTurb */
+  int numSpecies;                /* ns; neq = ns + 4 + numTurb (kernels exist for ns = 1 and 3) */
   int numTurb;                   /* 0, or 2 for RANS */
   int numGhosts;                 /* input::NumberGhostLayers */
   int isViscous;
@@ -116,9 +116,12 @@ typedef struct aither_cfg {
   double nondimScaling;                   /* mu_ref / (rho_ref a_ref l_ref) */
   double suthViscC1[AITHER_MAX_SPECIES], suthViscS[AITHER_MAX_SPECIES];
   double suthCondC1[AITHER_MAX_SPECIES], suthCondS[AITHER_MAX_SPECIES];
-  double molarMass[AITHER_MAX_SPECIES];
+  double molarMass[AITHER_MAX_SPECIES];   /* Wilke's mixing rule (any consistent unit) */
   double tRef, muMixRef, kMixRef;
-  double schmidt, turbPrandtl;
+  double schmidt;                /* species diffusion (`diffusionModel: schmidt`): Schmidt number;
+                                    <= 0 for `diffusionModel: none`. The turbulent Schmidt number
+                                    is the reference's constant 0.7 (include/turbulence.hpp:71) */
+  double turbPrandtl;            /* unused: Pr_t follows the turbulence model (0.9; k-omega 2006 8/9) */
   int numBCStates;
   aither_bc_state bcStates[AITHER_MAX_BC_STATES];
 } aither_cfg;

@@ -2960,3 +2960,12 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
   level_from_cfg(&h, cfg);
   ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, wallDist, nuW, ghost);
 }
+
+/* transport of a mixture state (tests/test_physics_host.py): {viscosity, effective conductivity} */
+void orc_mixture_transport(const aither_cfg *cfg, const double *state, double out[2]) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  const double t = temperature_of(&h, state);
+  out[0] = viscosity_of(&h, t, state);
+  out[1] = eff_conductivity(&h, t, state);
+}

@@ -77,6 +77,8 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
                           const double areaUnit[3], int surfType, int tag, int layer,
                           double wallDist, double nuW, double *ghost);
 
+void orc_mixture_transport(const aither_cfg *cfg, const double *state, double out[2]);
+
 #ifdef __cplusplus
 }
 #endif

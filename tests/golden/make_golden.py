@@ -122,6 +122,18 @@ CASES = {
                              drop=("diagRaw@", "temperature@", "state@it0.start", "x0@",
                                    "velocityGrad@", "tkeGrad@", "omegaGrad@", "f2@", "diagInv@",
                                    "matrixResid@", "dt@", "state@it0.bc")),
+    # BASELINE configs[2] on the shipped grid: turbFlatPlate with `turbulenceModel: sst2003` and
+    # `matrixSolver: blusgs` (the config string differs from the shipped .inp)
+    "turbFlatPlate_sst_blusgs": dict(src="turbFlatPlate", iters=20, full=(), 
+                                     edits={"turbulenceModel": "sst2003", "matrixSolver": "blusgs"},
+                                     drop=("state@",)),
+    # BASELINE configs[4] on the shipped grid: supersonicMixing with BDF2 dual time stepping
+    # (3 nonlinear iterations per step)
+    "supersonicMixing_bdf2": dict(src="supersonicMixing", iters=8, full=(),
+                                  fluids=("H2O", "H2", "N2"),
+                                  edits={"timeIntegration": "bdf2", "timeStep": "1.0e-7",
+                                         "dualTimeCFL": "100", "nonlinearIterations": "3"},
+                                  drop=("state@",)),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
     # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,

@@ -135,3 +135,34 @@ void hs_inviscid_flux_rans(const aither_cfg *c, const double *l, const double *r
   }
 }
 }
+
+// ---- three-species variants --------------------------------------------------------------------
+extern "C" {
+void hs_mixture_transport3(const aither_cfg *c, const double *s, double *out) {
+  const Gas g = GasFromCfg(c);
+  const Transport tr = TransportFromCfg(c);
+  const double t = Temperature<3>(g, s);
+  out[0] = MixtureViscosity<3>(tr, t, s);
+  out[1] = MixtureEffConductivity<3>(tr, t, s);
+}
+void hs_inviscid_flux3(const aither_cfg *c, const double *l, const double *r, const double *n,
+                       int fast, double *f) {
+  const Gas g = GasFromCfg(c);
+  if (c->invFlux == AITHER_FLUX_ROE) {
+    if (fast) RoeFluxFast<3, 0>(g, l, r, n, f);
+    else RoeFlux<3, 0>(g, l, r, n, f);
+  } else {
+    if (fast) InviscidFluxFast<3, 0, AITHER_FLUX_AUSM>(g, l, r, n, f);
+    else AusmFlux<3, 0>(g, l, r, n, f);
+  }
+}
+void hs_update_prim3(const aither_cfg *c, const double *s, const double *du, double *out) {
+  const Gas g = GasFromCfg(c);
+  UpdatePrimWithCons<3, 0>(g, s, du, out);
+}
+void hs_offdiag_scalar3(const aither_cfg *c, const double *s, const double *du, const double *fa,
+                        int positive, double *out) {
+  const Gas g = GasFromCfg(c);
+  OffDiagScalar<3, 0>(g, s, du, fa, positive != 0, out);
+}
+}

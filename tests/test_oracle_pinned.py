@@ -73,3 +73,20 @@ def test_oracle_supersonic_mixing():
         pytest.skip("tests/golden/supersonicMixing.npz has not been generated")
     d = gc.load("supersonicMixing")
     assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
+
+
+def test_oracle_baseline_config_turb_flat_plate_sst_blusgs():
+    """BASELINE configs[2] on the shipped grid: testCases/turbFlatPlate edited to
+    `turbulenceModel: sst2003` + `matrixSolver: blusgs`, 20 iterations at CFL 1e5."""
+    d = gc.load("turbFlatPlate_sst_blusgs")
+    assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
+
+
+def test_oracle_baseline_config_supersonic_mixing_bdf2():
+    """BASELINE configs[4] on the shipped grid: supersonicMixing edited to BDF2 with dual time
+    stepping, 3 nonlinear iterations per step. Fixture not committed (7.6 MB)."""
+    import os
+    if not os.path.exists(os.path.join(gc.GOLDEN_DIR, "supersonicMixing_bdf2.npz")):
+        pytest.skip("tests/golden/supersonicMixing_bdf2.npz has not been generated")
+    d = gc.load("supersonicMixing_bdf2")
+    assert gc.check_history(oracle.OracleLevel, d, 24, 1e-9) <= 1e-9

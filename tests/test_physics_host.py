@@ -305,3 +305,66 @@ def test_inviscid_flux_rans(hs, flux, fast):
         assert np.all(np.abs(a[:5] - b[:5]) <= 3e-14 * np.abs(a[:5]).max()), (a, b)
         tscale = np.maximum(np.abs(a[5:]), np.abs(a[0]) * np.maximum(l[5:], r[5:]))
         assert np.all(np.abs(a[5:] - b[5:]) <= 1e-12 * tscale), (a, b)
+
+
+# ---- three species ------------------------------------------------------------------------------
+def mix3_cfg(flux="ausm"):
+    import goldencheck as gc
+    import refcase
+    cfg = refcase.cfg_from_dump(gc.load("box_mix3_euler"))
+    cfg.invFlux = abi.FLUX_ROE if flux == "roe" else abi.FLUX_AUSM
+    return cfg
+
+
+def rand_mix3_state(rng, mach=0.3):
+    s = np.empty(7)
+    rho = rng.uniform(0.5, 1.5)
+    y = rng.dirichlet([2.0, 0.3, 5.0])
+    s[:3] = rho * y
+    s[3:6] = rng.uniform(-1, 1, 3) * mach
+    s[6] = rng.uniform(0.4, 1.0)
+    return s
+
+
+def test_mixture_transport(hs):
+    """Wilke's mixing rule for viscosity and conductivity (src/transport.cpp:70-110)."""
+    rng = np.random.default_rng(53)
+    cfg = mix3_cfg()
+    L = oracle.lib()
+    for _ in range(500):
+        s = rand_mix3_state(rng)
+        a, b = np.empty(2), np.empty(2)
+        L.orc_mixture_transport(C.byref(cfg), ptr(s), ptr(a))
+        hs.hs_mixture_transport3(C.byref(cfg), ptr(s), ptr(b))
+        assert np.all(np.abs(a - b) <= 1e-13 * np.abs(a)), (a, b)
+
+
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_inviscid_flux_three_species(hs, flux, fast):
+    rng = np.random.default_rng(59)
+    cfg = mix3_cfg(flux)
+    L = oracle.lib()
+    for trial in range(300):
+        mach = 0.3 if trial % 2 == 0 else 1.5
+        l, r, n = rand_mix3_state(rng, mach), rand_mix3_state(rng, mach), unit(rng)
+        a, b = np.empty(7), np.empty(7)
+        L.orc_inviscid_flux(C.byref(cfg), ptr(l), ptr(r), ptr(n), ptr(a))
+        hs.hs_inviscid_flux3(C.byref(cfg), ptr(l), ptr(r), ptr(n), fast, ptr(b))
+        # the energy flux carries the heats of formation (|hf| ~ 100): compare against it
+        assert np.all(np.abs(a - b) <= 1e-13 * np.abs(a).max()), (a, b)
+
+
+def test_offdiag_three_species(hs):
+    rng = np.random.default_rng(61)
+    cfg = mix3_cfg()
+    L = oracle.lib()
+    for _ in range(300):
+        s, n = rand_mix3_state(rng), unit(rng)
+        du = rng.normal(size=7) * 1e-3
+        fa = np.concatenate([n, [rng.uniform(0.1, 2.0)]])
+        for pos in (0, 1):
+            a, b = np.empty(7), np.empty(7)
+            L.orc_offdiag_scalar(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(a))
+            hs.hs_offdiag_scalar3(C.byref(cfg), ptr(s), ptr(du), ptr(fa), pos, ptr(b))
+            assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a).max() + 1e-13), (a, b)
