@@ -25,33 +25,34 @@
 
 using namespace aither;
 
-namespace {
+struct aither_gpu;
+struct AitherEqOps {
+  int (*PhaseBoundaryConditionsT)(aither_gpu *);
+  int (*PhaseResidualT)(aither_gpu *, int, double);
+  int (*PhasePrepT)(aither_gpu *, double, int);
+  int (*PhaseRelaxT)(aither_gpu *, int, int);
+  int (*PhaseUpdateT)(aither_gpu *, int, int);
+  int (*StoreOldT)(aither_gpu *, int);
+  int (*InitAuxT)(aither_gpu *, int);
+};
+const AitherEqOps *AitherEqOps_1_0();
+const AitherEqOps *AitherEqOps_1_2();
+const AitherEqOps *AitherEqOps_3_0();
+const AitherEqOps *AitherEqOps_3_2();
 
-thread_local std::string g_lastError;
-
-int Fail(const std::string &msg) {
-  g_lastError = msg;
-  return 1;
+// one last-error string per thread for the whole library (the equation-set translation units
+// below share it: inline function, one instance after linking)
+inline std::string &AitherLastError() {
+  static thread_local std::string e;
+  return e;
 }
+#define g_lastError AitherLastError()
 
-#define CK(call)                                                                       \
-  do {                                                                                 \
-    cudaError_t e_ = (call);                                                           \
-    if (e_ != cudaSuccess) {                                                           \
-      return Fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
-                  ":" + std::to_string(__LINE__) + ")");                               \
-    }                                                                                  \
-  } while (0)
-
+namespace aither_host {  // host-side types shared by every translation unit of the library
 enum Family {
   kFamBc = 0, kFamResidual, kFamPrep, kFamDplur, kFamLusgs, kFamAxmb, kFamUpdate, kFamStore,
   kFamReduce, kFamHalo, kFamLayout, kFamViscGhost, kFamViscFlux, kNumFamilies
 };
-const char *kFamilyNames[kNumFamilies] = {"bc_ghost_fill", "residual", "dt_diag_init", "dplur_sweep",
-                                          "lusgs_plane", "matrix_residual", "update_norms",
-                                          "store_time_n", "reduce_finalize", "halo_pack_unpack",
-                                          "layout_convert", "viscous_ghosts_aux", "viscous_flux"};
-
 struct HostBlock {
   BlockDev dev;
   void *alloc = nullptr;          // one allocation holding every field
@@ -80,6 +81,30 @@ struct HostBlock {
   int nTmaBlocks = 0;
   int nFields = 0;
 };
+
+}  // namespace aither_host
+using namespace aither_host;
+
+namespace {
+
+const char *kFamilyNames[kNumFamilies] = {"bc_ghost_fill", "residual", "dt_diag_init", "dplur_sweep",
+                                          "lusgs_plane", "matrix_residual", "update_norms",
+                                          "store_time_n", "reduce_finalize", "halo_pack_unpack",
+                                          "layout_convert", "viscous_ghosts_aux", "viscous_flux"};
+
+int Fail(const std::string &msg) {
+  g_lastError = msg;
+  return 1;
+}
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      return Fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                  ":" + std::to_string(__LINE__) + ")");                               \
+    }                                                                                  \
+  } while (0)
 
 }  // namespace
 
@@ -672,10 +697,13 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
   return 0;
 }
 
-// equation-set dispatch: one or three species, laminar / Euler (NT = 0) or two-equation RANS (NT = 2)
-#define EQ_DISPATCH(h, FN, ...)                                                            \
-  ((h)->ns == 1 ? ((h)->nt == 0 ? FN<1, 0>(__VA_ARGS__) : FN<1, 2>(__VA_ARGS__))           \
-                : ((h)->nt == 0 ? FN<3, 0>(__VA_ARGS__) : FN<3, 2>(__VA_ARGS__)))
+// Equation-set dispatch: one or three species, laminar / Euler (NT = 0) or two-equation RANS
+// (NT = 2). The phase templates of one equation set are instantiated in their own translation
+// unit -- this same file compiled with -DAITHER_EQ_TU=<10|12|30|32> -- and reached through a
+// table, so the library builds in parallel (__graft_entry__.build); with neither AITHER_EQ_TU nor
+// AITHER_MAIN_TU defined the file is the whole library (one slow translation unit).
+const AitherEqOps *EqOpsFor(const aither_gpu *h);
+#define EQ_DISPATCH(h, FN, ...) (EqOpsFor(h)->FN(__VA_ARGS__))
 int PhaseBoundaryConditions(aither_gpu *h) { return EQ_DISPATCH(h, PhaseBoundaryConditionsT, h); }
 int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
   return EQ_DISPATCH(h, PhaseResidualT, h, fusePrep, cfl);
@@ -771,8 +799,41 @@ void FreeAll(aither_gpu *h) {
   delete h;
 }
 
+const AitherEqOps *EqOpsFor(const aither_gpu *h) {
+  if (h->ns == 1) return h->nt == 0 ? AitherEqOps_1_0() : AitherEqOps_1_2();
+  return h->nt == 0 ? AitherEqOps_3_0() : AitherEqOps_3_2();
+}
+
 }  // namespace
 
+#define AITHER_DEFINE_EQ_OPS(NS, NT)                                                          \
+  const AitherEqOps *AitherEqOps_##NS##_##NT() {                                              \
+    static const AitherEqOps ops = {PhaseBoundaryConditionsT<NS, NT>, PhaseResidualT<NS, NT>, \
+                                    PhasePrepT<NS, NT>,               PhaseRelaxT<NS, NT>,    \
+                                    PhaseUpdateT<NS, NT>,             StoreOldT<NS, NT>,      \
+                                    InitAuxT<NS, NT>};                                        \
+    return &ops;                                                                              \
+  }
+#if defined(AITHER_EQ_TU)
+#if AITHER_EQ_TU == 10
+AITHER_DEFINE_EQ_OPS(1, 0)
+#elif AITHER_EQ_TU == 12
+AITHER_DEFINE_EQ_OPS(1, 2)
+#elif AITHER_EQ_TU == 30
+AITHER_DEFINE_EQ_OPS(3, 0)
+#elif AITHER_EQ_TU == 32
+AITHER_DEFINE_EQ_OPS(3, 2)
+#else
+#error "AITHER_EQ_TU must be 10, 12, 30 or 32"
+#endif
+#elif !defined(AITHER_MAIN_TU)
+AITHER_DEFINE_EQ_OPS(1, 0)
+AITHER_DEFINE_EQ_OPS(1, 2)
+AITHER_DEFINE_EQ_OPS(3, 0)
+AITHER_DEFINE_EQ_OPS(3, 2)
+#endif
+
+#if !defined(AITHER_EQ_TU)  // the C ABI lives in the main translation unit only
 // =================================================================================================
 extern "C" {
 
@@ -1519,3 +1580,4 @@ int aither_gpu_profile_get(aither_gpu *h, int family, double *ms, long long *lau
 }
 
 }  // extern "C"
+#endif  // !AITHER_EQ_TU

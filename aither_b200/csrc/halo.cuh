@@ -259,7 +259,7 @@ struct HaloFields {
   long long fs[kHaloMaxBlocks];
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     HaloPackKernel(const HaloJob *__restrict__ jobs, HaloFields f, int nc) {
   const HaloJob j = jobs[blockIdx.y];
   const double *__restrict__ src = f.base[j.block];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256)
     for (int e = 0; e < nc; ++e) j.buf[static_cast<long long>(e) * j.sliceCells + n] = src[e * fs + c];
   }
 }
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     HaloUnpackKernel(const HaloJob *__restrict__ jobs, HaloFields f, int nc) {
   const HaloJob j = jobs[blockIdx.y];
   double *__restrict__ dst = f.base[j.block];

@@ -65,7 +65,7 @@ __device__ __forceinline__ void StoreCell(double *__restrict__ f, long long fs, 
 // layout conversion: reference array-of-structs (host order) <-> device structure-of-arrays
 // src extents (SI,SJ,SK) with `nc` doubles per entry; entry (ii,jj,kk) maps to device index
 // (ii+oi) + (jj+oj)*sj + (kk+ok)*sk
-__global__ void AosToSoaKernel(const double *__restrict__ src, int SI, int SJ, int SK, int nc,
+static __global__ void AosToSoaKernel(const double *__restrict__ src, int SI, int SJ, int SK, int nc,
                                double *__restrict__ dst, long long fs, int oi, int oj, int ok,
                                int sj, long long sk) {
   const long long n = static_cast<long long>(SI) * SJ * SK;
@@ -78,7 +78,7 @@ __global__ void AosToSoaKernel(const double *__restrict__ src, int SI, int SJ, i
     for (int c = 0; c < nc; ++c) dst[c * fs + d] = src[t * nc + c];
   }
 }
-__global__ void SoaToAosKernel(double *__restrict__ dstAos, int SI, int SJ, int SK, int nc,
+static __global__ void SoaToAosKernel(double *__restrict__ dstAos, int SI, int SJ, int SK, int nc,
                                const double *__restrict__ src, long long fs, int oi, int oj,
                                int ok, int sj, long long sk) {
   const long long n = static_cast<long long>(SI) * SJ * SK;
@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(256)
 // final pass over the per-block partials of one procBlock, accumulating into the iteration's
 // result record in a fixed order (deterministic run to run)
 constexpr int kFinalThreads = 512;
-__global__ void __launch_bounds__(kFinalThreads)
+static __global__ void __launch_bounds__(kFinalThreads)
     FinalizeSumKernel(const double *__restrict__ partials, int nPartials, int nv,
                       double *__restrict__ out) {
   // one block per value; each thread strides the partial list, then a fixed shuffle/shared tree
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(kFinalThreads)
     if (threadIdx.x == 0) out[v] += w;
   }
 }
-__global__ void __launch_bounds__(kFinalThreads)
+static __global__ void __launch_bounds__(kFinalThreads)
     FinalizeLinfKernel(const LinfCand *__restrict__ cands, int n, BlockDev b, int neq,
                        IterResult *__restrict__ res) {
   __shared__ LinfCand sh[kFinalThreads / 32];
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(256) StoreOldKernel(BlockDev b, Params p, int 
   if (copyToNm1) StoreCell<E::neq>(b.consNm1, b.fs, idx, c);
 }
 
-__global__ void FillKernel(double *__restrict__ p, long long n, double v) {
+static __global__ void FillKernel(double *__restrict__ p, long long n, double v) {
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n;
        t += static_cast<long long>(gridDim.x) * blockDim.x)
     p[t] = v;

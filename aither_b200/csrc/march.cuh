@@ -41,7 +41,7 @@ __device__ __forceinline__ void MusclC(const double *u2, const double *u1, const
 //   mc[0] = (w + w) / (w + w_lower)   mc[1] = (w + w) / (w + w_upper)
 // (the exact expressions of reconstruction.hpp:133-134, so the values are bit-identical to the
 // ones the reference forms per face)
-__global__ void MusclCoefKernel(BlockDev b, int d) {
+static __global__ void MusclCoefKernel(BlockDev b, int d) {
   const int NI = b.ni + 2 * b.g, NJ = b.nj + 2 * b.g, NK = b.nk + 2 * b.g;
   const long long n = static_cast<long long>(NI) * NJ * NK;
   const int nd[3] = {NI, NJ, NK};

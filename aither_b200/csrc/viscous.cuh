@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) AuxKernel(BlockDev b, Params p) {
 
 // projected centre-to-centre distance across every face (geometry only; built once):
 // ref: src/procBlock.cpp:6316-6341 (ProjC2CDist)
-__global__ void DistKernel(BlockDev b) {
+static __global__ void DistKernel(BlockDev b) {
   const int NI = b.ni + 2 * b.g, NJ = b.nj + 2 * b.g, NK = b.nk + 2 * b.g;
   const long long n = static_cast<long long>(NI) * NJ * NK;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n;
