@@ -37,6 +37,8 @@ struct AitherEqOps {
 };
 const AitherEqOps *AitherEqOps_1_0();
 const AitherEqOps *AitherEqOps_1_2();
+const AitherEqOps *AitherEqOps_2_0();
+const AitherEqOps *AitherEqOps_2_2();
 const AitherEqOps *AitherEqOps_3_0();
 const AitherEqOps *AitherEqOps_3_2();
 
@@ -271,7 +273,7 @@ int SurfaceType(const aither_surface &s) {
 }
 
 bool Supported(const aither_cfg &c, std::string *why) {
-  if (c.numSpecies != 1 && c.numSpecies != 3) { *why = "numSpecies must be 1 or 3 (kernels are instantiated for these counts)"; return false; }
+  if (c.numSpecies < 1 || c.numSpecies > 3) { *why = "numSpecies must be 1, 2 or 3 (kernels are instantiated for these counts)"; return false; }
   if (c.numSpecies > 1 && c.isBlockMatrix) { *why = "block-matrix solvers are built for one species (species rows of the thin-shear-layer Jacobian)"; return false; }
   if (c.numTurb != 0 || c.isRANS) {
     if (c.numTurb != 2 || !c.isRANS || !c.isViscous) { *why = "RANS needs numTurb = 2 and isViscous"; return false; }
@@ -699,7 +701,7 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
 
 // Equation-set dispatch: one or three species, laminar / Euler (NT = 0) or two-equation RANS
 // (NT = 2). The phase templates of one equation set are instantiated in their own translation
-// unit -- this same file compiled with -DAITHER_EQ_TU=<10|12|30|32> -- and reached through a
+// unit -- this same file compiled with -DAITHER_EQ_TU=<10|12|20|22|30|32> -- and reached through a
 // table, so the library builds in parallel (__graft_entry__.build); with neither AITHER_EQ_TU nor
 // AITHER_MAIN_TU defined the file is the whole library (one slow translation unit).
 const AitherEqOps *EqOpsFor(const aither_gpu *h);
@@ -801,6 +803,7 @@ void FreeAll(aither_gpu *h) {
 
 const AitherEqOps *EqOpsFor(const aither_gpu *h) {
   if (h->ns == 1) return h->nt == 0 ? AitherEqOps_1_0() : AitherEqOps_1_2();
+  if (h->ns == 2) return h->nt == 0 ? AitherEqOps_2_0() : AitherEqOps_2_2();
   return h->nt == 0 ? AitherEqOps_3_0() : AitherEqOps_3_2();
 }
 
@@ -819,16 +822,22 @@ const AitherEqOps *EqOpsFor(const aither_gpu *h) {
 AITHER_DEFINE_EQ_OPS(1, 0)
 #elif AITHER_EQ_TU == 12
 AITHER_DEFINE_EQ_OPS(1, 2)
+#elif AITHER_EQ_TU == 20
+AITHER_DEFINE_EQ_OPS(2, 0)
+#elif AITHER_EQ_TU == 22
+AITHER_DEFINE_EQ_OPS(2, 2)
 #elif AITHER_EQ_TU == 30
 AITHER_DEFINE_EQ_OPS(3, 0)
 #elif AITHER_EQ_TU == 32
 AITHER_DEFINE_EQ_OPS(3, 2)
 #else
-#error "AITHER_EQ_TU must be 10, 12, 30 or 32"
+#error "AITHER_EQ_TU must be 10, 12, 20, 22, 30 or 32"
 #endif
 #elif !defined(AITHER_MAIN_TU)
 AITHER_DEFINE_EQ_OPS(1, 0)
 AITHER_DEFINE_EQ_OPS(1, 2)
+AITHER_DEFINE_EQ_OPS(2, 0)
+AITHER_DEFINE_EQ_OPS(2, 2)
 AITHER_DEFINE_EQ_OPS(3, 0)
 AITHER_DEFINE_EQ_OPS(3, 2)
 #endif

@@ -83,7 +83,7 @@ typedef struct aither_bc_state {
 /* POD snapshot of the reference's `input` + `physics` objects: only what the
  * hot path branches on (src/input.cpp:674-721,1110-1144) or evaluates. */
 typedef struct aither_cfg {
-  int numSpecies;                /* ns; neq = ns + 4 + numTurb (kernels exist for ns = 1 and 3) */
+  int numSpecies;                /* ns; neq = ns + 4 + numTurb (kernels exist for ns = 1, 2, 3) */
   int numTurb;                   /* 0, or 2 for RANS */
   int numGhosts;                 /* input::NumberGhostLayers */
   int isViscous;

@@ -108,6 +108,11 @@ CASES = {
                                           flux="ausm", limiter="minmod",
                                           species={"H2O": 0.233, "H2": 0.001, "N2": 0.766}),
                            iters=12, full=(0, 4)),
+    # two species (H2 / N2), laminar, AUSMPW+, DPLUR
+    "box_mix2_visc": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="dplur", sweeps=3, flux="ausm",
+                                         limiter="vanAlbada", viscous=True, size=2e-5, cfl=5.0,
+                                         species={"H2": 0.05, "N2": 0.95}),
+                          iters=12, full=(0,)),
     # the Roe flux with three species (the reference's Roe scheme is not stable for this mixture
     # beyond a few iterations, the heats of formation being large: 3 iterations of the laminar box)
     "box_mix3_roe": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2, cfl=5.0,
