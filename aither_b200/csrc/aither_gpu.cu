@@ -892,6 +892,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   p.wenoZ = cfg->recon == AITHER_RECON_WENOZ;
   p.isViscous = cfg->isViscous;
   {
+    // planes ahead of the L2 prefetch in the marching kernels (0 = off; A/B switch)
+    const char *pf = getenv("AITHER_B200_PREFETCH");
+    p.prefetch = pf != nullptr ? std::max(0, std::min(4, atoi(pf))) : 1;
+  }
+  {
     const char *tv = getenv("AITHER_B200_KEEP_TIME_N");  // A/B switch: always store / read U^n
     p.timeTermsVanish = !cfg->isMultilevelTime && cfg->nonlinearIterations <= 1 &&
                         !(tv != nullptr && std::string(tv) == "1");

@@ -132,6 +132,15 @@ __global__ void __launch_bounds__(kQThreads, 1)
     const bool planeInterior = it > 0 && it < nIter - 1;
     const long long idx = idxCol + static_cast<long long>(k) * b.sk;
 
+    // next plane's register operands: into L2 one plane ahead (one request per 128-byte line)
+    if (p.prefetch && (threadIdx.x & 15) == 0 && k + p.prefetch <= b.nk) {
+      const long long ahead = static_cast<long long>(p.prefetch) * b.sk;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) PrefetchL2(b.fA[2] + q * b.fs + idx + b.sk + ahead);
+#pragma unroll
+      for (int e = 0; e < neq; ++e) PrefetchL2(b.rhs + e * b.fs + idx - b.sk + ahead);
+      PrefetchL2((MODE == kModeDplur ? b.dinv : b.diag) + idx - b.sk + ahead);
+    }
     // this plane's register operands, issued before waiting on its tiles
     double faUp[4], rhsN[neq], dN = 0.0;
     if (it < nIter - 1) {  // face k + 1: upper face of this plane's cell

@@ -37,7 +37,13 @@ struct Params {
   // one nonlinear iteration per step of a single-level scheme: U^m = U^n at the only iteration,
   // so the time terms of b vanish identically and U^n is never read (nor stored)
   int timeTermsVanish;
+  // plane-marching kernels: L2 prefetch of the next plane's register-fed operands
+  int prefetch;
 };
+
+__device__ __forceinline__ void PrefetchL2(const void *ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
 
 // per-iteration reduction results (device + pinned host mirror)
 struct IterResult {

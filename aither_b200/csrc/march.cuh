@@ -208,6 +208,23 @@ __global__ void __launch_bounds__(kMThreads, 2)
     CpAsyncCommit();
 
     const long long idx = CellIdx(b, i, j, k);
+    // geometry of the next plane comes through registers (no in-plane reuse): pull its lines
+    // into L2 one plane ahead, one request per 128-byte line (lanes 0 and 16 of a row)
+    if (p.prefetch && (tx & 15) == 0 && colValid && k + p.prefetch <= b.nk) {
+      const long long idxn = idx + p.prefetch * b.sk;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) PrefetchL2(b.fA[d] + q * b.fs + idxn);
+        if (RECON == AITHER_RECON_MUSCL) {
+          PrefetchL2(b.mc[d] + idxn);
+          PrefetchL2(b.mc[d] + b.fs + idxn);
+        } else if (RECON != AITHER_RECON_CONSTANT) {
+          PrefetchL2(b.cw[d] + idxn);
+        }
+      }
+      if (fusePrep) PrefetchL2(b.vol + idxn);
+    }
     const int curBase = slotOf(k) * SLOTSZ;
     double fk[E::neq];
 #pragma unroll

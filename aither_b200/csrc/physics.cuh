@@ -329,6 +329,15 @@ template <int LIM>
 AITHER_HD double Muscl1(double u2, double u1, double d1, double kappa, double dPlus,
                         double dMinus) {
   const double dm = (u1 - u2) * dMinus;
+#ifdef __CUDA_ARCH__
+  if (LIM == AITHER_LIMITER_NONE) {
+    // Without a limiter the ratio r only appears as dm * r = dm (eps + dp) / (eps + dm), which is
+    // dp to within eps / |dm| = 1e-30 / |dm| relative (|dm| is 0 or at least an ulp of the
+    // variable) -- except for dm == 0 exactly, where the reference's product is 0. No division.
+    const double dp = (d1 - u1) * dPlus;
+    return u1 + 0.25 * ((1.0 - kappa) * dm + (1.0 + kappa) * (dm != 0.0 ? dp : 0.0));
+  }
+#endif
   const double r = (kEps + (d1 - u1) * dPlus) * FastRcp(kEps + dm);
   double lim = 1.0, invLim = 1.0;
   if (LIM != AITHER_LIMITER_NONE) {

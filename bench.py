@@ -370,6 +370,7 @@ def run_gpu_arm(args):
     total_cells = cells * world
     value = total_cells * args.steps / (ms * 1e-3) / 1e6
     e2e = total_cells * args.steps / (ms_e2e * 1e-3) / 1e6
+    e2e_sync = total_cells * args.steps / (ms_e2e_sync * 1e-3) / 1e6
     peak, peak_src = peaks()
     # dominant kernel family of the timed region
     alg = dict(ALG_DOUBLES)
@@ -396,12 +397,18 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, gpus=world, recon=args.recon, viscous=args.viscous,
                                   turb=args.turb, solver=args.solver),
-        "e2e": {"value": e2e, "unit": "Mcell-iter/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                "what": "per step: aither_gpu_upload_state_async (next step's state from pinned "
-                        "host memory, overlapping this step) + _commit + store_old_solution + "
-                        "aither_gpu_iterate (norms copied back)",
-                "value_without_overlap": total_cells * args.steps / (ms_e2e_sync * 1e-3) / 1e6},
+        "e2e": {"value": max(e2e, e2e_sync), "unit": "Mcell-iter/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "ms_per_step": min(ms_e2e, ms_e2e_sync) / args.steps,
+                "what": "per step: the host hands over a fresh copy of the state from pinned memory "
+                        "(703 MB at 256^3), store_old_solution, aither_gpu_iterate, norms copied "
+                        "back. Two ways through the C ABI, both timed in full, the faster one is "
+                        "`value`: `overlapped` = aither_gpu_upload_state_async / _commit (the copy "
+                        "of the next step runs on the copy stream during this step's kernels), "
+                        "`synchronous` = aither_gpu_upload_state. Which one wins depends on the "
+                        "box: the DMA copy slows down when the kernels keep HBM busy.",
+                "mode": "overlapped" if e2e >= e2e_sync else "synchronous",
+                "value_overlapped": e2e, "value_synchronous": e2e_sync},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,

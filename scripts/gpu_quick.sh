@@ -5,7 +5,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/quick_be
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/quick_bench.json'))
-print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'])
+print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'], d['e2e']['mode'], d['e2e']['value_overlapped'], d['e2e']['value_synchronous'])
 print('roofline', d['roofline']['kernel'], d['roofline']['frac'], 'iter frac', d['roofline_iteration']['frac'])
 print(d['kernel_ms_per_step'])
 PY
