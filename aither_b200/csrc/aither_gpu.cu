@@ -70,6 +70,8 @@ struct HostBlock {
   long long paddedCells = 0;
   dim3 cellGrid, cellBlock;       // cell-parallel kernels (32 x 8 threads)
   dim3 cell128Grid;               // register-heavy cell-parallel kernels (32 x 4 threads)
+  dim3 updGrid;                   // update kernel: kUpdPlanes k-planes per block
+  int nUpdBlocks = 0;
   dim3 resGrid, resBlock;
   int nCellBlocks = 0;
   // plane-marching kernels (march.cuh)
@@ -674,18 +676,18 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
   for (auto &hb : h->blocks) {
     {
       ScopedLaunch sl(h, kFamUpdate);
-      UpdateKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
-                                                                       h->dPartials,
-                                                                       h->dLinfPartials);
+      UpdateKernel<NS, NT><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+                                                                      h->dPartials,
+                                                                      h->dLinfPartials);
     }
     {
       ScopedLaunch sl(h, kFamReduce);
-      FinalizeSumKernel<<<h->neq, kFinalThreads, 0, h->stream>>>(h->dPartials, hb.nCellBlocks,
+      FinalizeSumKernel<<<h->neq, kFinalThreads, 0, h->stream>>>(h->dPartials, hb.nUpdBlocks,
                                                                  h->neq, h->dResults[slot].l2);
     }
     {
       ScopedLaunch sl(h, kFamReduce);
-      FinalizeLinfKernel<<<1, kFinalThreads, 0, h->stream>>>(h->dLinfPartials, hb.nCellBlocks,
+      FinalizeLinfKernel<<<1, kFinalThreads, 0, h->stream>>>(h->dLinfPartials, hb.nUpdBlocks,
                                                              hb.dev, h->neq, &h->dResults[slot]);
     }
     // U^(n-1) <- U^n after the last nonlinear iteration of a multilevel scheme
@@ -895,6 +897,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // planes ahead of the L2 prefetch in the marching kernels (0 = off; A/B switch)
     const char *pf = getenv("AITHER_B200_PREFETCH");
     p.prefetch = pf != nullptr ? std::max(0, std::min(4, atoi(pf))) : 1;
+
   }
   {
     const char *tv = getenv("AITHER_B200_KEEP_TIME_N");  // A/B switch: always store / read U^n
@@ -1155,6 +1158,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.cellGrid = dim3((d.ni + 31) / 32, (d.nj + 7) / 8, d.nk);
     hb.nCellBlocks = hb.cellGrid.x * hb.cellGrid.y * hb.cellGrid.z;
     hb.cell128Grid = dim3((d.ni + 31) / 32, (d.nj + 3) / 4, d.nk);
+    hb.updGrid = dim3((d.ni + 31) / 32, (d.nj + 7) / 8, (d.nk + kUpdPlanes - 1) / kUpdPlanes);
+    hb.nUpdBlocks = hb.updGrid.x * hb.updGrid.y * hb.updGrid.z;
     hb.resBlock = dim3(kTI, kTJ, kTK);
     hb.resGrid = dim3((d.ni + 1 + kTI - 1) / kTI, (d.nj + 1 + kTJ - 1) / kTJ,
                       (d.nk + 1 + kTK - 1) / kTK);

@@ -838,6 +838,7 @@ __device__ __forceinline__ LinfCand LinfBetter(LinfCand a, LinfCand c) {
   return (c.v > a.v || (c.v == a.v && c.key < a.key)) ? c : a;
 }
 
+constexpr int kUpdPlanes = 4;  // k-planes per thread block: the block reductions are paid once
 template <int NS, int NT>
 __global__ void __launch_bounds__(256)
     UpdateKernel(BlockDev b, Params p, double *__restrict__ partials,
@@ -845,7 +846,6 @@ __global__ void __launch_bounds__(256)
   using E = Eq<NS, NT>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z;
   double sq[E::neq];
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) sq[e] = 0.0;
@@ -853,22 +853,25 @@ __global__ void __launch_bounds__(256)
   best.v = 0.0;  // the reference starts from linf = 0 and uses a strict '>' (resid.hpp:33)
   best.key = 0x7fffffffffffffffLL;
   if (i < b.ni && j < b.nj) {
-    const long long idx = CellIdx(b, i, j, k);
-    double s[E::neq], du[E::neq], sn[E::neq];
-    LoadCell<E::neq>(b.state, b.fs, idx, s);
-    LoadCell<E::neq>(b.x, b.fs, idx, du);
-    UpdatePrimWithCons<NS, NT>(p.gas, s, du, sn);
-    StoreCell<E::neq>(b.state, b.fs, idx, sn);
-    const long long cellKey =
-        ((static_cast<long long>(k) * b.nj + j) * b.ni + i) * static_cast<long long>(E::neq);
+    const int kEnd = min(b.nk, (static_cast<int>(blockIdx.z) + 1) * kUpdPlanes);
+    for (int k = blockIdx.z * kUpdPlanes; k < kEnd; ++k) {
+      const long long idx = CellIdx(b, i, j, k);
+      double s[E::neq], du[E::neq], sn[E::neq];
+      LoadCell<E::neq>(b.state, b.fs, idx, s);
+      LoadCell<E::neq>(b.x, b.fs, idx, du);
+      UpdatePrimWithCons<NS, NT>(p.gas, s, du, sn);
+      StoreCell<E::neq>(b.state, b.fs, idx, sn);
+      const long long cellKey =
+          ((static_cast<long long>(k) * b.nj + j) * b.ni + i) * static_cast<long long>(E::neq);
 #pragma unroll
-    for (int e = 0; e < E::neq; ++e) {
-      const double r = __ldg(b.resid + e * b.fs + idx);
-      sq[e] = r * r;
-      LinfCand c;
-      c.v = r;
-      c.key = cellKey + e;
-      if (r > best.v) best = c;  // increasing e: first maximum wins, like the reference loop
+      for (int e = 0; e < E::neq; ++e) {
+        const double r = __ldg(b.resid + e * b.fs + idx);
+        sq[e] += r * r;
+        LinfCand c;
+        c.v = r;
+        c.key = cellKey + e;
+        if (r > best.v) best = c;  // increasing k, e: first maximum wins, like the reference loop
+      }
     }
   }
   const int tid = threadIdx.x + blockDim.x * threadIdx.y;
