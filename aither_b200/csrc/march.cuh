@@ -440,6 +440,25 @@ __global__ void __launch_bounds__(kMThreads, 2)
     double *cur = smem + static_cast<size_t>((k - k0 + 1) & 1) * G::n * kIPC;
     const long long idx = CellIdx(b, i, j, k);
     const bool planeInterior = k >= k0 && k < k1;
+    // everything this kernel reads comes through registers: pull the next plane's lines into L2
+    // (one request per 128-byte line)
+    if (p.prefetch && (tx & 15) == 0 && colValid && k + 1 <= b.nk) {
+      const long long idxn = idx + b.sk;
+#pragma unroll
+      for (int e = 0; e < neq; ++e) {
+        PrefetchL2(b.state + e * b.fs + idxn);
+        PrefetchL2(xin + e * b.fs + idxn);
+        PrefetchL2(b.rhs + e * b.fs + idx);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) PrefetchL2(b.fA[d] + q * b.fs + idxn);
+        if (p.isViscous) PrefetchL2(b.dist[d] + idxn);
+      }
+      if (p.isViscous) PrefetchL2(b.viscosity + idxn);
+      PrefetchL2((MODE == kModeDplur ? b.dinv : b.diag) + idx);
+    }
     double newCarry[neq];
 #pragma unroll
     for (int e = 0; e < neq; ++e) newCarry[e] = 0.0;
