@@ -2432,9 +2432,6 @@ static double proj_c2c_dist(const orc_block *b, int d, int ii, int jj, int kk) {
                                       : b->fAK + 4 * fidxK(b, ii, jj, kk));
   return (cu[0] - cl[0]) * fa[0] + (cu[1] - cl[1]) * fa[1] + (cu[2] - cl[2]) * fa[2];
 }
-static double visc_at(const orc_level *h, const orc_block *b, int ii, int jj, int kk) {
-  return h->cfg.isViscous ? b->viscosity[cidx(b, ii, jj, kk)] : 0.0;
-}
 /* fluxJacobian.cpp OffDiagonal (:196-238): the product of one neighbour's off-diagonal block
  * with its update, by the configured method */
 static void roe_flux(const orc_level *h, const double *l, const double *r,

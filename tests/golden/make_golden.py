@@ -139,6 +139,12 @@ CASES = {
                                   edits={"timeIntegration": "bdf2", "timeStep": "1.0e-7",
                                          "dualTimeCFL": "100", "nonlinearIterations": "3"},
                                   drop=("state@",)),
+    # reference regression case transonicBump (regressionTests.py:325-337) on a single grid level:
+    # first-order-upwind-biased MUSCL (kappa = -1) + vanAlbada, DPLUR x4, CFL ramp 1000 -> 10000
+    # (cflStep), patched slip walls; the shipped case adds a 3-level W-cycle multigrid, which is a
+    # SURVEY 8(f) row, so `multigridLevels: 1` here
+    "transonicBump_sg": dict(src="transonicBump", iters=100, full=(0, 50),
+                             edits={"multigridLevels": "1"}),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
     # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,

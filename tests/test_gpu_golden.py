@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-13, dt=1e-13, diag=1e-13, x0=1e-12,
            x=1e-11, matrixResid=1e-9, state=1e-12, l2=1e-12, turb=1e-11)
 
-SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno",
+SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_dplur", "box_lusgs_va", "box_weno",
                 # laminar Navier-Stokes (viscous fluxes, viscous-wall / edge ghosts, Sutherland)
                 "viscousFlatPlate", "box_visc4", "box_visc_iso",
                 # RANS: k-omega Wilcox 2006 (reference regression case + AUSM box) and SST 2003
@@ -50,7 +50,7 @@ def test_gpu_phases_match_reference(name):
         gc.check_phases(make_gpu_level, d, it, CASE_TOL.get(name, TOL))
 
 
-@pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30),
+@pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30), ("transonicBump_sg", 100),
                                         ("box_dplur", 30), ("box_lusgs_va", 20),
                                         ("box_weno", 12), ("viscousFlatPlate", 100),
                                         ("box_visc4", 12), ("box_visc_iso", 12),

@@ -18,7 +18,7 @@ import oracle
 TOL = dict(ghosts=1e-12, residual=1e-12, specRadius=1e-14, dt=1e-14, diag=1e-13, x0=1e-13,
            x=1e-12, matrixResid=1e-10, state=1e-13, l2=1e-13, turb=1e-12)
 
-SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "box_dplur", "box_lusgs_va", "box_weno",
+SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_dplur", "box_lusgs_va", "box_weno",
                 # laminar Navier-Stokes: Green-Gauss face gradients, viscous fluxes, Sutherland,
                 # viscous-wall + edge ghost cells, viscous spectral radii (diagonal and faces)
                 "viscousFlatPlate", "box_visc4", "box_visc_iso",
@@ -47,7 +47,7 @@ def test_oracle_phases_match_reference(name):
         gc.check_phases(oracle.OracleLevel, d, it, CASE_TOL.get(name, TOL))
 
 
-@pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30),
+@pytest.mark.parametrize("name,iters", [("subsonicCylinder", 100), ("supersonicWedge", 30), ("transonicBump_sg", 100),
                                         ("box_dplur", 30), ("box_lusgs_va", 20),
                                         ("box_weno", 12), ("viscousFlatPlate", 100),
                                         ("box_visc4", 12), ("box_visc_iso", 12),
