@@ -368,23 +368,30 @@ def lattice_connections(dims, splits):
 
 
 def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="none", flux="roe",
-                    recon="thirdOrder", seed=0, amplitude=0.01):
+                    recon="thirdOrder", seed=0, amplitude=0.01, viscous=False,
+                    visc_recon="central", size=1.0):
     """A pi x pj x pk lattice of n^3-cell blocks (each a unit cube of the warped box, so every block
     is the benchmark's block) joined by `interblock` connections -- the weak-scaling workload.
     `only`: block ids to materialise (default all); the others are dimension-only placeholders so
     that a rank builds just the blocks it owns. Each block's ghost geometry on a joined face is its
     neighbour's real geometry: the block's nodes are generated g cells beyond those faces from the
-    same analytic node function, metrics computed, and the extra layers cropped."""
+    same analytic node function, metrics computed, and the extra layers cropped.
+    `viscous`: laminar Navier-Stokes with an adiabatic viscous wall on the lattice's j-lo side
+    (BASELINE configs[3]'s scheme with recon="weno", visc_recon="centralFourth"); `size`: edge
+    length of one block in metres."""
     pi, pj, pk = splits
     nb = pi * pj * pk
     g = {"constant": 1, "weno": 3, "wenoZ": 3}.get(recon, 2)
     fluid = nondim.air(REF_RHO, REF_T)
     free = nondim.nondim_primitive(IC["density"], IC["velocity"], IC["pressure"], REF_RHO, REF_T)
+    bc_states = [dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
+                      velocity=list(free[1:4]), pressure=free[4], massFractions=[1.0])]
+    if viscous:
+        bc_states.append(dict(tag=2, type=abi.BC_VISCOUS_WALL, velocity=[0.0, 0.0, 0.0],
+                              massFractions=[1.0]))
     cfg = nondim.euler_cfg(fluid, g=g, solver=solver, sweeps=sweeps, limiter=limiter, flux=flux,
-                           recon=recon,
-                           bc_states=[dict(tag=1, type=abi.BC_CHARACTERISTIC, density=free[0],
-                                           velocity=list(free[1:4]), pressure=free[4],
-                                           massFractions=[1.0])])
+                           recon=recon, bc_states=bc_states, viscous=viscous,
+                           visc_recon=visc_recon)
     want = set(range(nb) if only is None else only)
     blocks = []
     for bid in range(nb):
@@ -400,6 +407,8 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
                 at_edge = pos[d3] == (splits[d3] - 1 if upper else 0)
                 if at_edge:
                     t, tag = (abi.BC_CHARACTERISTIC, 1) if d3 == 0 else (abi.BC_SLIP_WALL, 0)
+                    if viscous and d3 == 1 and not upper:
+                        t, tag = abi.BC_VISCOUS_WALL, 2
                 else:
                     nbp = list(pos)
                     nbp[d3] += 1 if upper else -1
@@ -411,10 +420,11 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
         arrays = {"state": None}
         if bid in want:
             ne = [n + ext_lo[d] + ext_hi[d] for d in range(3)]
-            h = 1.0 / n
+            h = size / n
             nodes = box_nodes(ne[0], ne[1], ne[2],
                               lengths=tuple(ne[d] * h for d in range(3)),
-                              origin=tuple(pos[d] - ext_lo[d] * h for d in range(3)))
+                              origin=tuple(pos[d] * size - ext_lo[d] * h for d in range(3)),
+                              warp=0.02 * size, period=size)
             m = block_metrics(nodes, g)
             arrays = {}
             for name in ("vol", "fAreaI", "fAreaJ", "fAreaK", "center", "cellWidthI", "cellWidthJ",

@@ -258,10 +258,12 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = adist.make_comm(local)
         splits = LATTICE[world]
-        if args.viscous:
-            raise SystemExit("--viscous is a single-GPU workload in this round")
+        if args.turb or args.solver != "dplur":
+            raise SystemExit("--turb / --solver are single-GPU workloads in this round")
+        extra = (dict(viscous=True, visc_recon="centralFourth", size=n * 2e-6) if args.viscous
+                 else {})
         prob = synthetic.lattice_problem(n, splits, only=[rank], solver="dplur", sweeps=SWEEPS,
-                                         recon=args.recon)
+                                         recon=args.recon, **extra)
         synthetic.assign_ranks(prob, world)
         mine = rank
         lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world,
@@ -439,7 +441,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per side of the block (256)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=256,
+                    help="cells per side of the block (256); use --cells under torchrun, whose own "
+                         "parser treats --n as an abbreviation")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--recon", default="thirdOrder",
                     help="face reconstruction of the workload (default thirdOrder = the headline "
