@@ -84,6 +84,9 @@ struct HostBlock {
   int tmaChunk = 1;
   int nTmaBlocks = 0;
   int nFields = 0;
+  // LU-SGS: the plane launches of one half sweep, captured once as a CUDA graph
+  // [forward / backward][first sweep form / full Gauss-Seidel]
+  cudaGraphExec_t lusgsGraph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 }  // namespace aither_host
@@ -144,6 +147,8 @@ struct aither_gpu {
   bool keepMatrixResid = false;
   int jac = kJacScalar;            // JacKind of the implicit matrix
   bool consNStale = false;         // U^n not materialised (Params::timeTermsVanish)
+  bool lusgsGraphs = true;         // AITHER_B200_LUSGS_GRAPH=0: plain launches (A/B)
+  bool lusgsSplit = true;          // AITHER_B200_LUSGS_SPLIT=0: one thread per cell (A/B)
   bool stateMovedSinceStore = false;
   int *dFlag = nullptr;            // set by PrepBlockKernel on a singular diagonal block
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
@@ -601,25 +606,58 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
       }
     } else {
       const int fullGS = (s > 0 || fullGSAlways) ? 1 : 0;
-      for (auto &hb : h->blocks) {
+      // one launch per i + j + k hyperplane; the ~(ni + nj + nk) launches of a half sweep are
+      // captured once per block into a CUDA graph and replayed (launch-bound otherwise)
+      auto halfSweep = [&](HostBlock &hb, bool forward) -> int {
         const BlockDev &b = hb.dev;
         const dim3 blk(16, 8);
         const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
-        for (int pl = 0; pl <= b.ni + b.nj + b.nk - 3; ++pl) {
-          ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<NS, NT, true, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
+        const int last = b.ni + b.nj + b.nk - 3;
+        // eight lanes per cell (LusgsPlaneSplitKernel): 32 cells per 256-thread block
+        const int splitGrid = (b.nj * b.nk + 31) / 32;
+        auto launchAll = [&]() {
+          for (int n = 0; n <= last; ++n) {
+            const int pl = forward ? n : last - n;
+            if (h->lusgsSplit) {
+              if (forward)
+                LusgsPlaneSplitKernel<NS, NT, true, JAC><<<splitGrid, 256, 0, h->stream>>>(
+                    b, h->params, pl, fullGS);
+              else
+                LusgsPlaneSplitKernel<NS, NT, false, JAC><<<splitGrid, 256, 0, h->stream>>>(
+                    b, h->params, pl, fullGS);
+            } else if (forward) {
+              LusgsPlaneKernel<NS, NT, true, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl,
+                                                                              fullGS);
+            } else {
+              LusgsPlaneKernel<NS, NT, false, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl,
+                                                                               fullGS);
+            }
+          }
+        };
+        ScopedLaunch sl(h, kFamLusgs);  // one timing record per half sweep
+        h->launches += last;
+        h->famLaunches[kFamLusgs] += last;
+        if (!h->lusgsGraphs) {
+          launchAll();
+          return 0;
         }
-      }
+        cudaGraphExec_t &ex = hb.lusgsGraph[forward ? 0 : 1][fullGS];
+        if (!ex) {
+          cudaGraph_t graph = nullptr;
+          CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+          launchAll();
+          CK(cudaStreamEndCapture(h->stream, &graph));
+          CK(cudaGraphInstantiate(&ex, graph, 0));
+          CK(cudaGraphDestroy(graph));
+        }
+        CK(cudaGraphLaunch(ex, h->stream));
+        return 0;
+      };
+      for (auto &hb : h->blocks)
+        if (halfSweep(hb, true)) return 1;
       if (SwapUpdate(h)) return 1;
-      for (auto &hb : h->blocks) {
-        const BlockDev &b = hb.dev;
-        const dim3 blk(16, 8);
-        const dim3 grid((b.nj + 15) / 16, (b.nk + 7) / 8);
-        for (int pl = b.ni + b.nj + b.nk - 3; pl >= 0; --pl) {
-          ScopedLaunch sl(h, kFamLusgs);
-          LusgsPlaneKernel<NS, NT, false, JAC><<<grid, blk, 0, h->stream>>>(b, h->params, pl, fullGS);
-        }
-      }
+      for (auto &hb : h->blocks)
+        if (halfSweep(hb, false)) return 1;
     }
   }
   CK(cudaGetLastError());
@@ -779,6 +817,9 @@ void FreeAll(aither_gpu *h) {
   cudaSetDevice(h->device);
   for (auto &hb : h->blocks) {
     if (hb.alloc) cudaFree(hb.alloc);
+    for (auto &row : hb.lusgsGraph)
+      for (auto &ex : row)
+        if (ex) cudaGraphExecDestroy(ex);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     for (auto &p : hb.dConnFace)
@@ -931,6 +972,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // the TMA-fed sweep is inviscid-only so far; viscous runs take the register-fed march kernel
     h->tmaImplicit = !(kv != nullptr && std::string(kv) == "march") && !cfg->isViscous &&
                      cfg->numSpecies == 1;
+    const char *lg = getenv("AITHER_B200_LUSGS_GRAPH");
+    h->lusgsGraphs = !(lg != nullptr && std::string(lg) == "0");
+    const char *ls = getenv("AITHER_B200_LUSGS_SPLIT");
+    h->lusgsSplit = !(ls != nullptr && std::string(ls) == "0");
     const char *fp = getenv("AITHER_B200_FUSE_PREP");
     h->fusePrep = !(fp != nullptr && std::string(fp) == "0");
   }

@@ -639,6 +639,88 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// K7, latency-split form: the plane kernels are bound by the dependent chain of ONE thread working
+// through its up to six neighbours (~2 us each: gathers, U + dU -> primitives, two fluxes), while a
+// hyperplane offers few cells. Here eight lanes share a cell -- lanes 0..2 take the lower
+// neighbours in i, j, k, lanes 3..5 the upper ones -- and lane 0 collects the six products with
+// shuffles in the reference's order (L: i, j, k; U: i, j, k; src/procBlock.cpp:1056-1170), so the
+// sums are the same expressions as in LusgsPlaneKernel.
+template <int NS, int NT, bool FORWARD, int JAC = kJacScalar>
+__global__ void __launch_bounds__(256)
+    LusgsPlaneSplitKernel(BlockDev b, Params p, int plane, int fullGS) {
+  using E = Eq<NS, NT>;
+  const int lane8 = threadIdx.x & 7;
+  const int cell = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int j = cell % b.nj, k = cell / b.nj;
+  const int i = plane - j - k;
+  const bool valid = k < b.nk && i >= 0 && i < b.ni;
+  const long long idx = valid ? CellIdx(b, i, j, k) : 0;
+  const bool doLower = FORWARD || fullGS != 0, doUpper = !FORWARD || fullGS != 0;
+  double od[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) od[e] = 0.0;
+  if (valid && lane8 < 6) {
+    const int d = lane8 % 3;
+    const bool upper = lane8 >= 3;
+    const int c[3] = {i, j, k}, nd[3] = {b.ni, b.nj, b.nk};
+    const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+    const long long st = Stride(b, d);
+    const bool wanted = upper ? doUpper : doLower;
+    const bool contributes =
+        upper ? (c[d] < nd[d] - 1 || ConnAcross(b, 2 * d + 2, c[d1], nd[d1], c[d2]))
+              : (c[d] > 0 || ConnAcross(b, 2 * d + 1, c[d1], nd[d1], c[d2]));
+    if (wanted && contributes) {
+      const long long nidx = upper ? idx + st : idx - st;
+      const long long fidx = upper ? idx + st : idx;  // the face between the two cells
+      double sn[E::neq], dun[E::neq], own[E::neq], fa[4];
+      LoadCell<E::neq>(b.state, b.fs, nidx, sn);
+#pragma unroll
+      for (int e = 0; e < E::neq; ++e) dun[e] = b.x[e * b.fs + nidx];
+      if (JAC == kJacRoe) LoadCell<E::neq>(b.state, b.fs, idx, own);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) fa[q] = __ldg(b.fA[d] + q * b.fs + fidx);
+      OffDiagOne<NS, NT, JAC>(b, p, sn, dun, own, fa, !upper, nidx,
+                              p.isViscous ? __ldg(b.dist[d] + fidx) : 1.0, od);
+    }
+  }
+  // lane 0 of the group: L = ((0 + od_i) + od_j) + od_k from lanes 0..2, U from lanes 3..5
+  const int base = (threadIdx.x & 31) & ~7;
+  double L[E::neq], U[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) {
+    double l = 0.0, u = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      l += __shfl_sync(0xffffffffu, od[e], base + q);
+      u += __shfl_sync(0xffffffffu, od[e], base + 3 + q);
+    }
+    L[e] = l;
+    U[e] = u;
+  }
+  if (!valid || lane8 != 0) return;
+  double rhs[E::neq], xn[E::neq];
+  if (FORWARD) {
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) rhs[e] = __ldg(b.rhs + e * b.fs + idx) + (L[e] - U[e]);
+    DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, rhs, xn);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = xn[e];
+  } else if (fullGS) {
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) rhs[e] = (__ldg(b.rhs + e * b.fs + idx) + L[e]) - U[e];
+    DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, rhs, xn);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) b.x[e * b.fs + idx] = xn[e];
+  } else {
+    DiagMult<NS, NT, JAC>(b.dinv, b.fs, idx, U, xn);
+#pragma unroll
+    for (int e = 0; e < E::neq; ++e) {
+      const double xo = b.x[e * b.fs + idx];
+      b.x[e * b.fs + idx] = xo - xn[e];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // block-matrix diagonal (blusgs / bdplur).
 // face state reconstructed from this cell's side towards its lower (UPPER_FACE = false: the
