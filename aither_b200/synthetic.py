@@ -45,8 +45,11 @@ def write_plot3d(path, blocks_nodes):
 
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
-             visc_recon="central", wall=None, turb=None, jac="rusanov", species=None):
-    """`species`: None (air) or a dict name -> reference mass fraction (multi-species mixture with
+             visc_recon="central", wall=None, turb=None, jac="rusanov", species=None,
+             periodic=None):
+    """`periodic`: None, or the box length: the two i-faces become a periodic pair (translation
+    [length, 0, 0]) instead of characteristic boundaries.
+    `species`: None (air) or a dict name -> reference mass fraction (multi-species mixture with
     Schmidt-number diffusion, e.g. {"H2O": 0.233, "H2": 0.001, "N2": 0.766}).
     `viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
     ("isothermal", T) or ("heatFlux", q)). `turb`: None, "kOmegaWilcox2006" or "sst2003" (RANS,
@@ -87,12 +90,16 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "matrixSweeps: %d" % sweeps,
         "matrixRelaxation: 1.0",
         "viscousFaceReconstruction: %s" % visc_recon,
-        ("boundaryStates: <characteristic(tag=1; %s), %s>" % (state, wall_state)) if viscous
-        else ("boundaryStates: <characteristic(tag=1; %s)>" % state),
+        "boundaryStates: <%s>" % ", ".join(
+            ["characteristic(tag=1; %s)" % state] + ([wall_state] if viscous else []) +
+            (["periodic(startTag=4; endTag=5; translation=[%.17g, 0, 0])" % periodic]
+             if periodic else [])),
         "boundaryConditions: 1",
         "2 2 2",
-        "characteristic %d %d %d %d %d %d 1" % (0, 0, 0, nj, 0, nk),
-        "characteristic %d %d %d %d %d %d 1" % (ni, ni, 0, nj, 0, nk),
+        ("periodic %d %d %d %d %d %d 4" if periodic else "characteristic %d %d %d %d %d %d 1")
+        % (0, 0, 0, nj, 0, nk),
+        ("periodic %d %d %d %d %d %d 5" if periodic else "characteristic %d %d %d %d %d %d 1")
+        % (ni, ni, 0, nj, 0, nk),
         ("viscousWall %d %d %d %d %d %d 2" if viscous else "slipWall %d %d %d %d %d %d 0")
         % (0, ni, 0, 0, 0, nk),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, nj, nj, 0, nk),
@@ -177,6 +184,8 @@ def write_case(case_dir, name, ni, nj, nk, perturb=None, size=1.0, **kw):
         write_cloud(os.path.join(case_dir, "ic.dat"), nodes, *perturb, turb=kw.get("turb"),
                     mix=kw.get("species"))
         kw["ic_file"] = "ic.dat"
+    if kw.get("periodic"):
+        kw["periodic"] = size  # the i-faces are one box length apart
     with open(os.path.join(case_dir, name + ".inp"), "w") as f:
         f.write(inp_text(name, ni, nj, nk, **kw))
     return name + ".inp"

@@ -108,6 +108,13 @@ CASES = {
                                           flux="ausm", limiter="minmod",
                                           species={"H2O": 0.233, "H2": 0.001, "N2": 0.766}),
                            iters=12, full=(0, 4)),
+    # periodic connection (the block's i-lo and i-hi faces, translation one box length): the ghost
+    # exchange of a block with itself; Euler + DPLUR and laminar + LU-SGS
+    "box_periodic": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="dplur", sweeps=3,
+                                        periodic=True), iters=12, full=(0, 4)),
+    "box_periodic_visc": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                             limiter="vanAlbada", viscous=True, size=2e-5,
+                                             periodic=True), iters=12, full=(0,)),
     # two species (H2 / N2), laminar, AUSMPW+, DPLUR
     "box_mix2_visc": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="dplur", sweeps=3, flux="ausm",
                                          limiter="vanAlbada", viscous=True, size=2e-5, cfl=5.0,

@@ -145,3 +145,14 @@ def test_run_with_nonlinear_iterations_equals_iterate():
             assert np.array_equal(hist[n * nl + mm, :-1], l2) and hist[n * nl + mm, -1] == mr
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("name", ["box_periodic", "box_periodic_visc"])
+def test_periodic_connection_matches_reference(name):
+    """Periodic pair on the block's own i-faces: the device ghost exchange of a block with itself
+    (same-GPU path, donor and acceptor in one block) against the reference's dumps."""
+    d = gc.load(name)
+    for it in gc.full_iterations(d):
+        out = gc.check_phases(make_gpu_level, d, it, TOL)
+        assert out["ghosts"] <= 1e-15
+    assert gc.check_history(make_gpu_level, d, 12, 1e-9) <= 1e-9

@@ -67,3 +67,16 @@ def test_oracle_uniform_flow_rans():
     d = gc.load("uniformFlow_rans")
     gc.check_phases(oracle.OracleLevel, d, 0, dict(TOL, turb=1e-12))
     assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
+
+
+def test_oracle_periodic_connection():
+    """A periodic pair (the block's own i-lo and i-hi faces, `periodic(startTag; endTag;
+    translation)`, reference src/boundaryConditions.cpp:2224-2300): the block exchanges ghost layers
+    with itself. Euler + DPLUR and laminar + LU-SGS, against the reference's dumps."""
+    for name in ("box_periodic", "box_periodic_visc"):
+        d = gc.load(name)
+        assert int(d["connections"][0][27]) == 0  # isInterblock = 0: periodic
+        for it in gc.full_iterations(d):
+            out = gc.check_phases(oracle.OracleLevel, d, it, dict(TOL, diag=1e-13))
+            assert out["ghosts"] == 0.0
+        assert gc.check_history(oracle.OracleLevel, d, 12, 1e-9) <= 1e-9
