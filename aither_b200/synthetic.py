@@ -46,9 +46,11 @@ def write_plot3d(path, blocks_nodes):
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
              visc_recon="central", wall=None, turb=None, jac="rusanov", species=None,
-             periodic=None):
+             periodic=None, overrides=None):
     """`periodic`: None, or the box length: the two i-faces become a periodic pair (translation
     [length, 0, 0]) instead of characteristic boundaries.
+    `overrides`: dict of `.inp` keys replacing (or adding to) the lines below, e.g.
+    {"timeIntegration": "crankNicholson", "timeStep": "1e-6", "matrixRelaxation": "1.1"}.
     `species`: None (air) or a dict name -> reference mass fraction (multi-species mixture with
     Schmidt-number diffusion, e.g. {"H2O": 0.233, "H2": 0.001, "N2": 0.766}).
     `viscous`: navierStokes with a viscousWall on the j-lo face (`wall`: None = adiabatic,
@@ -67,7 +69,7 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         wall_state = "viscousWall(tag=2; temperature=%g)" % wall[1]
     elif wall is not None and wall[0] == "heatFlux":
         wall_state = "viscousWall(tag=2; heatFlux=%g)" % wall[1]
-    return "\n".join([
+    lines = [
         "gridName: %s" % name,
         "equationSet: %s" % ("rans" if turb else ("navierStokes" if viscous else "euler")),
         "turbulenceModel: %s" % (turb or "none"),
@@ -105,7 +107,15 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "slipWall %d %d %d %d %d %d 0" % (0, ni, nj, nj, 0, nk),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, 0, nj, 0, 0),
         "slipWall %d %d %d %d %d %d 0" % (0, ni, 0, nj, nk, nk),
-        ""])
+        ""]
+    for key, val in (overrides or {}).items():
+        hit = [n for n, ln in enumerate(lines) if ln.split(":")[0] == key]
+        if hit:
+            lines[hit[0]] = "%s: %s" % (key, val)
+        else:  # new keys go in front of the boundary-state table
+            pos = [n for n, ln in enumerate(lines) if ln.startswith("boundaryStates")][0]
+            lines.insert(pos, "%s: %s" % (key, val))
+    return "\n".join(lines)
 
 
 def read_plot3d(path):

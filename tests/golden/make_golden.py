@@ -108,6 +108,18 @@ CASES = {
                                           flux="ausm", limiter="minmod",
                                           species={"H2O": 0.233, "H2": 0.001, "N2": 0.766}),
                            iters=12, full=(0, 4)),
+    # options no other fixture holds: WENO-Z + Crank-Nicolson with a global time step and
+    # matrixRelaxation 1.1; first-order (constant) reconstruction; constant-heat-flux wall
+    "box_wenoz_cn": dict(synthetic=dict(ni=12, nj=8, nk=8, solver="dplur", sweeps=3, recon="wenoZ",
+                                        overrides={"timeIntegration": "crankNicholson",
+                                                   "timeStep": "2.0e-5",
+                                                   "matrixRelaxation": "1.1"}),
+                         iters=10, full=(0, 4)),
+    "box_first_order": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                           recon="constant"), iters=10, full=(0, 4)),
+    "box_visc_heatflux": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="dplur", sweeps=3,
+                                             limiter="minmod", viscous=True, size=2e-5,
+                                             wall=("heatFlux", 2.0e5)), iters=10, full=(0, 4)),
     # periodic connection (the block's i-lo and i-hi faces, translation one box length): the ghost
     # exchange of a block with itself; Euler + DPLUR and laminar + LU-SGS
     "box_periodic": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="dplur", sweeps=3,
