@@ -46,9 +46,11 @@ def write_plot3d(path, blocks_nodes):
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
              visc_recon="central", wall=None, turb=None, jac="rusanov", species=None,
-             periodic=None, overrides=None):
+             periodic=None, overrides=None, inlet_outlet=False):
     """`periodic`: None, or the box length: the two i-faces become a periodic pair (translation
     [length, 0, 0]) instead of characteristic boundaries.
+    `inlet_outlet`: the i-lo face becomes an `inlet` and the i-hi face a `pressureOutlet`
+    (reflecting forms) instead of characteristic boundaries.
     `overrides`: dict of `.inp` keys replacing (or adding to) the lines below, e.g.
     {"timeIntegration": "crankNicholson", "timeStep": "1e-6", "matrixRelaxation": "1.1"}.
     `species`: None (air) or a dict name -> reference mass fraction (multi-species mixture with
@@ -93,14 +95,19 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "matrixRelaxation: 1.0",
         "viscousFaceReconstruction: %s" % visc_recon,
         "boundaryStates: <%s>" % ", ".join(
-            ["characteristic(tag=1; %s)" % state] + ([wall_state] if viscous else []) +
+            (["inlet(tag=1; %s; massFractions=[air=1.0])" % state,
+              "pressureOutlet(tag=3; pressure=%g)" % IC["pressure"]] if inlet_outlet
+             else ["characteristic(tag=1; %s)" % state]) + ([wall_state] if viscous else []) +
             (["periodic(startTag=4; endTag=5; translation=[%.17g, 0, 0])" % periodic]
              if periodic else [])),
         "boundaryConditions: 1",
         "2 2 2",
-        ("periodic %d %d %d %d %d %d 4" if periodic else "characteristic %d %d %d %d %d %d 1")
+        ("periodic %d %d %d %d %d %d 4" if periodic else
+         ("inlet %d %d %d %d %d %d 1" if inlet_outlet else "characteristic %d %d %d %d %d %d 1"))
         % (0, 0, 0, nj, 0, nk),
-        ("periodic %d %d %d %d %d %d 5" if periodic else "characteristic %d %d %d %d %d %d 1")
+        ("periodic %d %d %d %d %d %d 5" if periodic else
+         ("pressureOutlet %d %d %d %d %d %d 3" if inlet_outlet
+          else "characteristic %d %d %d %d %d %d 1"))
         % (ni, ni, 0, nj, 0, nk),
         ("viscousWall %d %d %d %d %d %d 2" if viscous else "slipWall %d %d %d %d %d %d 0")
         % (0, ni, 0, 0, 0, nk),

@@ -120,6 +120,10 @@ CASES = {
     "box_visc_heatflux": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="dplur", sweeps=3,
                                              limiter="minmod", viscous=True, size=2e-5,
                                              wall=("heatFlux", 2.0e5)), iters=10, full=(0, 4)),
+    # subsonic `inlet` / `pressureOutlet` pair (reflecting forms) with WENO and LU-SGS
+    "box_inlet_outlet": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                            recon="weno", inlet_outlet=True), iters=10,
+                             full=(0, 4)),
     # periodic connection (the block's i-lo and i-hi faces, translation one box length): the ghost
     # exchange of a block with itself; Euler + DPLUR and laminar + LU-SGS
     "box_periodic": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="dplur", sweeps=3,
