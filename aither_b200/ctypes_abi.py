@@ -49,6 +49,7 @@ class BCState(C.Structure):
         ("temperature", C.c_double), ("heatFlux", C.c_double),
         ("isIsothermal", C.c_int), ("isConstantHeatFlux", C.c_int),
         ("turbulenceIntensity", C.c_double), ("eddyViscosityRatio", C.c_double),
+        ("isWallLaw", C.c_int), ("vonKarmen", C.c_double), ("wallConstant", C.c_double),
     ]
 
 

@@ -46,8 +46,9 @@ def write_plot3d(path, blocks_nodes):
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
              visc_recon="central", wall=None, turb=None, jac="rusanov", species=None,
-             periodic=None, overrides=None, inlet_outlet=False):
-    """`periodic`: None, or the box length: the two i-faces become a periodic pair (translation
+             periodic=None, overrides=None, inlet_outlet=False, wall_law=False):
+    """`wall_law`: the viscous wall uses the wall law (`wallTreatment=wallLaw`).
+    `periodic`: None, or the box length: the two i-faces become a periodic pair (translation
     [length, 0, 0]) instead of characteristic boundaries.
     `inlet_outlet`: the i-lo face becomes an `inlet` and the i-hi face a `pressureOutlet`
     (reflecting forms) instead of characteristic boundaries.
@@ -71,6 +72,8 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         wall_state = "viscousWall(tag=2; temperature=%g)" % wall[1]
     elif wall is not None and wall[0] == "heatFlux":
         wall_state = "viscousWall(tag=2; heatFlux=%g)" % wall[1]
+    if wall_law:
+        wall_state = wall_state[:-1] + "; wallTreatment=wallLaw)"
     lines = [
         "gridName: %s" % name,
         "equationSet: %s" % ("rans" if turb else ("navierStokes" if viscous else "euler")),
@@ -143,10 +146,11 @@ def centroids(x):
                     x[1:, :-1, :-1] + x[1:, :-1, 1:] + x[1:, 1:, :-1] + x[1:, 1:, 1:])
 
 
-def _cloud_values(n, seed, amplitude, turb):
+def _cloud_values(n, seed, amplitude, turb, ic=None):
     """seed-fixed +-amplitude noise on rho, u, v, w, p (+ k, omega for RANS: farfield-like
     k = 1.5 (0.01 |v|)^2, omega = rho k / (10 mu))"""
     rng = np.random.default_rng(seed)
+    IC = ic or globals()["IC"]
     base = np.array([IC["density"], *IC["velocity"], IC["pressure"]])
     vals = base[None, :] * (1.0 + amplitude * (2.0 * rng.random((n, 5)) - 1.0))
     kw = np.zeros((n, 2))
@@ -159,9 +163,10 @@ def _cloud_values(n, seed, amplitude, turb):
     return vals, kw
 
 
-def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air", turb=None):
-    """cloud file with seed-fixed noise on the IC state at the given points (see write_cloud)"""
-    vals, kw = _cloud_values(cen.shape[0], seed, amplitude, turb)
+def write_cloud_points(path, cen, seed=0, amplitude=0.01, species="air", turb=None, ic=None):
+    """cloud file with seed-fixed noise on the IC state (`ic`: density / velocity / pressure,
+    default the synthetic box's) at the given points (see write_cloud)"""
+    vals, kw = _cloud_values(cen.shape[0], seed, amplitude, turb, ic)
     with open(path, "w") as f:
         f.write("%d\n%s\n" % (cen.shape[0], species))
         for c, v, t in zip(cen, vals, kw):

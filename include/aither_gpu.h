@@ -78,6 +78,9 @@ typedef struct aither_bc_state {
   int isConstantHeatFlux;
   double turbulenceIntensity;
   double eddyViscosityRatio;
+  int isWallLaw;                 /* viscousWall(wallTreatment=wallLaw): include/inputStates.hpp:343-369 */
+  double vonKarmen;              /* 0.41 unless given */
+  double wallConstant;           /* 5.5 unless given */
 } aither_bc_state;
 
 /* POD snapshot of the reference's `input` + `physics` objects: only what the

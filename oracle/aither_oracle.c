@@ -41,7 +41,16 @@ typedef struct {
   double *tkeGrad, *omegaGrad; /* ni nj nk 3 */
   const double *vol, *fAI, *fAJ, *fAK, *center, *cwI, *cwJ, *cwK, *wallDist;
   int *order; /* hyperplane ordering: 3 ints per cell */
+  /* wallData_: one record per face of every viscous-wall surface (NULL for
+   * other surfaces); ref: include/wallData.hpp:40-62, src/procBlock.cpp:6287-6290 */
+  struct orc_wall_vars **wall;
 } orc_block;
+
+/* wallVars; ref: include/wallData.hpp:40-57 */
+typedef struct orc_wall_vars {
+  double shearStress[3], heatFlux, yplus, temperature, turbEddyVisc, viscosity,
+      density, frictionVelocity, tke, sdr;
+} orc_wall_vars;
 
 struct orc_level {
   aither_cfg cfg;
@@ -597,9 +606,14 @@ static void apply_farfield_turb(const orc_level *h, double *s, const double vel[
   for (int tt = 0; tt < h->nt; ++tt)
     s[it + tt] = s[it + tt] > 1.0e-20 ? s[it + tt] : 1.0e-20;
 }
+static void wall_law_eval(const orc_level *h, const aither_bc_state *bc, int mode,
+                          const double *state, double wallDist, const double area[3],
+                          int isLower, orc_wall_vars *wv);
+static double cp_mix(const orc_level *h, const double *mf);
+static double turb_prandtl(const orc_level *h);
 static void ghost_state(const orc_level *h, const double *interior, int bcType,
                         const double areaVec[3], int surf, int tag, int layer,
-                        double wallDist, double nuW, double *ghost) {
+                        double wallDist, double nuW, double *ghost, orc_wall_vars *wvOut) {
   const int rans = h->nt > 0, it = h->ns + 4;
   const int ns = h->ns, neq = h->neq;
   const int imx = ns, imy = ns + 1, imz = ns + 2, ie = ns + 3;
@@ -621,24 +635,55 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     ghost[imx] = 2.0 * velWall[0] - interior[imx];
     ghost[imy] = 2.0 * velWall[1] - interior[imy];
     ghost[imz] = 2.0 * velWall[2] - interior[imz];
+    orc_wall_vars wv;
+    memset(&wv, 0, sizeof(wv));
+    const int wallLaw = bc && bc->isWallLaw;
+    int lowRe = 1; /* low-Re treatment, or the wall law handed over to it (y+ < 10) */
     if (bc && (bc->isIsothermal || bc->isConstantHeatFlux)) {
       double mf[AITHER_MAX_SPECIES];
       mass_fractions(h, interior, mf);
       double tGhost;
-      if (bc->isIsothermal) { /* ref: :183-189 */
-        tGhost = 2.0 * bc->temperature - temperature_of(h, interior);
-      } else { /* ref: :226-236 */
-        const double t = temperature_of(h, interior);
-        const double kappa = eff_conductivity(h, t, interior);
-        tGhost = temperature_of(h, interior) -
-                 bc->heatFlux / kappa * 2.0 * wallDist;
+      if (wallLaw) { /* ref: :149-181 (isothermal), :195-224 (heat flux) */
+        wall_law_eval(h, bc, bc->isIsothermal ? 2 : 1, interior, wallDist, nA, isLower, &wv);
+        lowRe = wv.yplus < 10.0; /* wallVars::SwitchToLowRe, include/wallData.hpp:57 */
+      }
+      if (bc->isIsothermal) {
+        if (!lowRe) { /* ref: :160-171 */
+          const double kappa =
+              eff_conductivity(h, wv.temperature, interior) +
+              wv.turbEddyVisc * cp_mix(h, mf) / turb_prandtl(h);
+          tGhost = bc->temperature - wv.heatFlux / kappa * 2.0 * wallDist;
+        } else { /* ref: :183-189 */
+          tGhost = 2.0 * bc->temperature - temperature_of(h, interior);
+        }
+      } else {
+        if (!lowRe) { /* ref: :212-219 */
+          tGhost = 2.0 * wv.temperature - temperature_of(h, interior);
+        } else { /* ref: :226-236 */
+          const double t = temperature_of(h, interior);
+          const double kappa = eff_conductivity(h, t, interior);
+          tGhost = temperature_of(h, interior) -
+                   bc->heatFlux / kappa * 2.0 * wallDist;
+        }
       }
       double R = 0.0; /* ref: src/eos.cpp:111-115 (DensityTP) */
       for (int ss = 0; ss < ns; ++ss) R += mf[ss] * h->cfg.gasConstant[ss];
       const double rho = ghost[ie] / (R * tGhost);
       for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * mf[ss];
+    } else if (wallLaw) { /* adiabatic; ref: :243-256 */
+      wall_law_eval(h, bc, 0, interior, wallDist, nA, isLower, &wv);
+      lowRe = wv.yplus < 10.0;
     }
-    if (rans) { /* ref: :262-281 (low-Re wall) */
+    if (rans && !lowRe) { /* wall-law k and omega; ref: :173-180, :221-228, :248-255 */
+      ghost[it] = 2.0 * wv.tke - interior[it];
+      ghost[it + 1] = 2.0 * wv.sdr - interior[it + 1];
+      if (layer > 1) {
+        ghost[it] = layer * ghost[it] - wv.tke;
+        ghost[it + 1] = layer * ghost[it + 1] - wv.sdr;
+      }
+    }
+    if (wvOut) *wvOut = wv;
+    if (rans && lowRe) { /* ref: :262-281 (low-Re wall) */
       ghost[it] = -1.0 * interior[it];
       const double scaling = h->cfg.nondimScaling;
       const double wWall = scaling * scaling * 60.0 * nuW /
@@ -895,7 +940,7 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
                                    : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
             double ghost[MAXEQ];
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]), bcType,
-                        fa, st, sf->tag, layer, 0.0, 0.0, ghost);
+                        fa, st, sf->tag, layer, 0.0, 0.0, ghost, NULL);
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -1172,10 +1217,10 @@ static void assign_ghost_edges(orc_level *h, orc_block *b, int viscous) {
              * never extended by this branch pair -- only the both-viscousWall
              * averaging below applies */
             if (bc2 == AITHER_BC_SLIP_WALL && bc3 != AITHER_BC_SLIP_WALL) {
-              ghost_state(h, from2, bc2, fArea2, surf2, s2->tag, layer2, wDist2, 0.0, ghost);
+              ghost_state(h, from2, bc2, fArea2, surf2, s2->tag, layer2, wDist2, 0.0, ghost, NULL);
               memcpy(dst, ghost, sizeof(double) * neq);
             } else if (bc2 != AITHER_BC_SLIP_WALL && bc3 == AITHER_BC_SLIP_WALL) {
-              ghost_state(h, from3, bc3, fArea3, surf3, s3->tag, layer3, wDist3, 0.0, ghost);
+              ghost_state(h, from3, bc3, fArea3, surf3, s3->tag, layer3, wDist3, 0.0, ghost, NULL);
               memcpy(dst, ghost, sizeof(double) * neq);
             } else if (!viscous || (bc2 == AITHER_BC_VISCOUS_WALL &&
                                     bc3 == AITHER_BC_VISCOUS_WALL)) {
@@ -1241,8 +1286,13 @@ static void assign_viscous_ghosts(orc_level *h, orc_block *b) {
             const long ac = cidx(b, ca[0], ca[1], ca[2]);
             const double nuW = b->viscosity[ac] / rho_of(h, b->state + neq * ac);
             double ghost[MAXEQ];
+            orc_wall_vars wv;
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]),
-                        AITHER_BC_VISCOUS_WALL, fa, st, sf->tag, layer, wd, nuW, ghost);
+                        AITHER_BC_VISCOUS_WALL, fa, st, sf->tag, layer, wd, nuW, ghost, &wv);
+            /* wallData_ keeps the first layer's record; ref: src/procBlock.cpp:6287-6290 */
+            if (layer == 1)
+              b->wall[s][(ii - lo[0]) + (long)(hi[0] - lo[0]) * ((jj - lo[1]) +
+                         (long)(hi[1] - lo[1]) * (kk - lo[2]))] = wv;
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -1421,6 +1471,161 @@ static double eddy_visc_no_lim(const orc_level *h, const double *s) {
   return rho_of(h, s) * tke_of(h, s) / omega_of(h, s);
 }
 /* primitive::LimitTurb; ref: src/primitive.cpp:100-106, turbulence.hpp:72-73 */
+/* ------------------------------------------------------------------------ */
+/* wall law (Nichols & Nelson 2004 with White & Christoph's compressible law
+ * of the wall); ref: src/wallLaw.cpp:31-289, include/wallLaw.hpp:36-95.
+ * mode 0 adiabatic, 1 constant heat flux, 2 isothermal. The members of the
+ * reference's wallLaw object after its last function evaluation are what the
+ * wall variables are built from, so the context keeps them the same way.   */
+typedef struct {
+  const orc_level *h;
+  const double *state;
+  double mf[AITHER_MAX_SPECIES];
+  double wallDist, vonKarmen, yplus0, velTanMag, tInt, cp;
+  double beta, gamma, q, phi, yplusWhite, uStar, uplus, tW, rhoW, muW, mutW, kW, recovery;
+  int mode;
+  double heatFlux, yplus, temperature;
+} wl_ctx;
+static void wl_set_wall_vars(wl_ctx *c, double tW) { /* ref: src/wallLaw.cpp:229-237 */
+  const orc_level *h = c->h;
+  c->tW = tW;
+  double R = 0.0; /* eos DensityTP, src/eos.cpp:111-115 */
+  for (int ss = 0; ss < h->ns; ++ss) R += c->mf[ss] * h->cfg.gasConstant[ss];
+  c->rhoW = c->state[h->ns + 3] / (R * tW);
+  c->muW = viscosity_of(h, tW, c->state) * h->cfg.nondimScaling;
+  c->kW = eff_conductivity(h, tW, c->state);
+}
+static double wl_func(wl_ctx *c, double yplus) {
+  const orc_level *h = c->h;
+  /* CalcVelocities; ref: :264-268 */
+  c->uplus = (c->wallDist * c->rhoW * c->velTanMag) / (c->muW * yplus);
+  c->uStar = c->velTanMag / c->uplus;
+  if (c->mode == 1) { /* CalcWallTemperature; ref: :220-227, then SetWallVars */
+    c->temperature = c->tInt + c->recovery * c->uStar * c->uStar * c->uplus * c->uplus /
+                                   (2.0 * c->cp + c->heatFlux * c->muW / (c->rhoW * c->kW * c->uStar));
+    wl_set_wall_vars(c, c->temperature);
+  }
+  /* UpdateGamma; ref: :186-191 */
+  c->gamma = c->recovery * c->uStar * c->uStar / (2.0 * c->cp * c->tW);
+  if (c->mode == 2) { /* CalcHeatFlux; ref: :211-218 */
+    const double tmp = (c->tInt / c->tW - 1.0 + c->gamma * c->uplus * c->uplus) / c->uplus;
+    c->heatFlux = tmp * (c->rhoW * c->tW * c->kW * c->uStar) / c->muW;
+  }
+  /* UpdateConstants; ref: :193-198 */
+  c->beta = c->heatFlux * c->muW / (c->rhoW * c->tW * c->kW * c->uStar);
+  c->q = sqrt(c->beta * c->beta + 4.0 * c->gamma);
+  c->phi = asin(-c->beta / c->q);
+  /* CalcYplusWhite; ref: :200-205 */
+  c->yplusWhite = exp((c->vonKarmen / sqrt(c->gamma)) *
+                      (asin((2.0 * c->gamma * c->uplus - c->beta) / c->q) - c->phi)) *
+                  c->yplus0;
+  c->yplus = yplus;
+  /* CalcYplusRoot; ref: :239-244 */
+  const double sixth = 1.0 / 6.0;
+  const double ku = c->vonKarmen * c->uplus;
+  (void)h;
+  return yplus - (c->uplus + c->yplusWhite -
+                  c->yplus0 * (1.0 + ku + 0.5 * ku * ku + sixth * pow(ku, 3.0)));
+}
+/* Ridder's method; ref: include/utility.hpp:130-184 */
+static double wl_find_root(wl_ctx *c, double x1, double x2, double tol) {
+  double f1 = wl_func(c, x1);
+  double f2 = wl_func(c, x2);
+  if (sign_of(f1) == sign_of(f2) && sign_of(f1) != 0.0) return 0.5 * (x1 + x2);
+  double x4 = x1;
+  for (int ii = 0; ii < 100; ++ii) {
+    const double x3 = 0.5 * (x1 + x2);
+    const double f3 = wl_func(c, x3);
+    if (f3 == 0.0) return x3;
+    const double denom = sqrt(fabs(f3 * f3 - f1 * f2));
+    if (denom == 0.0) return x3;
+    const double fac = sign_of(f1 - f2);
+    x4 = x3 + (x3 - x1) * (fac * f3) / denom;
+    const double f4 = wl_func(c, x4);
+    if (f4 == 0.0) return x4;
+    if (sign_of(f4) != sign_of(f3)) {
+      x1 = x3;
+      f1 = f3;
+      x2 = x4;
+      f2 = f4;
+    } else if (sign_of(f4) != sign_of(f1)) {
+      x2 = x4;
+      f2 = f4;
+    } else {
+      x1 = x4;
+      f1 = f4;
+    }
+    if (fabs(x2 - x1) <= tol) return x4;
+  }
+  return x4;
+}
+static void wall_law_eval(const orc_level *h, const aither_bc_state *bc, int mode,
+                          const double *state, double wallDist, const double area[3],
+                          int isLower, orc_wall_vars *wv) {
+  const int ns = h->ns;
+  wl_ctx c;
+  memset(&c, 0, sizeof(c));
+  c.h = h;
+  c.state = state;
+  c.mode = mode;
+  c.wallDist = wallDist;
+  c.vonKarmen = bc->vonKarmen;
+  c.yplus0 = exp(-bc->vonKarmen * bc->wallConstant);
+  mass_fractions(h, state, c.mf);
+  /* tangential velocity relative to the wall; ref: :41-44 */
+  double vel[3], velTan[3];
+  for (int d = 0; d < 3; ++d) vel[d] = state[ns + d] - bc->velocity[d];
+  const double vn = vel[0] * area[0] + vel[1] * area[1] + vel[2] * area[2];
+  for (int d = 0; d < 3; ++d) velTan[d] = vel[d] - vn * area[d];
+  c.velTanMag = sqrt(velTan[0] * velTan[0] + velTan[1] * velTan[1] + velTan[2] * velTan[2]);
+  c.tInt = temperature_of(h, state);
+  c.cp = cp_mix(h, c.mf);
+  /* CalcRecoveryFactor; ref: :286-289 */
+  c.recovery = pow(prandtl_of(c.cp / cv_mix(h, c.mf)), 1.0 / 3.0);
+  if (mode == 0) { /* Crocco-Busemann wall temperature; ref: :46-52 */
+    const double tW = c.tInt + 0.5 * c.recovery * c.velTanMag * c.velTanMag / c.cp;
+    wl_set_wall_vars(&c, tW);
+    c.heatFlux = 0.0;
+  } else if (mode == 1) { /* ref: :96-105 */
+    c.heatFlux = bc->heatFlux;
+    c.temperature = c.tInt;
+    wl_set_wall_vars(&c, c.tInt);
+  } else { /* ref: :148-160 */
+    c.temperature = bc->temperature;
+    wl_set_wall_vars(&c, bc->temperature);
+  }
+  wl_find_root(&c, 1.0e1, 1.0e4, 1.0e-8);
+  wv->tke = 0.0;
+  wv->sdr = 0.0;
+  if (h->nt > 0) { /* CalcTurbVars, EddyVisc; ref: :246-262, :270-284 */
+    const double dYplusWhite =
+        2.0 * c.yplusWhite * c.vonKarmen * sqrt(c.gamma) / c.q *
+        sqrt(fmax(1.0 - pow(2.0 * c.gamma * c.uplus - c.beta, 2.0) / (c.q * c.q), 0.0));
+    const double ku = c.vonKarmen * c.uplus;
+    c.mutW = c.muW * (1.0 + dYplusWhite - c.vonKarmen * c.yplus0 * (1.0 + ku + 0.5 * ku * ku)) -
+             viscosity_of(h, c.tInt, state) * h->cfg.nondimScaling;
+    c.mutW = fmax(c.mutW, 0.0);
+    double wi = 6.0 * c.muW / (wall_beta(h) * c.rhoW * wallDist * wallDist);
+    wi *= h->cfg.nondimScaling;
+    double wo = c.uStar / (sqrt(0.09) * c.vonKarmen * wallDist);
+    wo *= h->cfg.nondimScaling;
+    wv->sdr = sqrt(wi * wi + wo * wo);
+    wv->tke = wv->sdr * c.mutW / rho_of(h, state) * (1.0 / h->cfg.nondimScaling);
+  }
+  wv->heatFlux = c.heatFlux;
+  wv->yplus = c.yplus;
+  wv->density = c.rhoW;
+  wv->temperature = mode == 0 ? c.tW : c.temperature;
+  wv->viscosity = c.muW;
+  wv->turbEddyVisc = c.mutW;
+  wv->frictionVelocity = c.uStar;
+  const double tauMag = c.uStar * c.uStar * c.rhoW; /* ShearStressMag */
+  for (int d = 0; d < 3; ++d) {
+    wv->shearStress[d] = tauMag * velTan[d] / c.velTanMag;
+    if (!isLower) wv->shearStress[d] *= -1.0;
+  }
+}
+
 static void limit_turb(const orc_level *h, double *s) {
   for (int tt = 0; tt < h->nt; ++tt)
     s[h->ns + 4 + tt] = s[h->ns + 4 + tt] > 1.0e-20 ? s[h->ns + 4 + tt] : 1.0e-20;
@@ -1603,6 +1808,66 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg, mg);
         double state[MAXEQ], mu, wDist = 0.0;
 #define CL(o) cidx(b, ii + (o)*di, jj + (o)*dj, kk + (o)*dk)
+        double mut = 0.0, f1 = 0.0, f2 = 0.0, flux[MAXEQ];
+        const double *fa = farea(b, d, ii, jj, kk);
+        for (int e = 0; e < neq; ++e) flux[e] = 0.0;
+        /* boundary face on a viscous wall: low-Re treatment, or the wall law where its
+         * y+ stayed >= 10 (ref: src/procBlock.cpp:1269-1300) */
+        int isLowReWall = 0, isWallLawFace = 0;
+        const orc_wall_vars *wvp = NULL;
+        const aither_bc_state *wbc = NULL;
+        if (fi == 0 || fi == nd[d]) {
+          const aither_surface *sf = find_surface(b, ii, jj, kk, 2 * d + (fi == 0 ? 1 : 2));
+          if (sf->type == AITHER_BC_VISCOUS_WALL) {
+            wbc = bc_data(h, sf->tag);
+            if (wbc && wbc->isWallLaw) {
+              int lo[3] = {sf->imin, sf->jmin, sf->kmin}, hi[3] = {sf->imax, sf->jmax, sf->kmax};
+              int c3[3] = {ii, jj, kk};
+              lo[d] = 0;
+              hi[d] = 1;
+              c3[d] = 0;
+              wvp = &b->wall[sf - b->surf][(c3[0] - lo[0]) + (long)(hi[0] - lo[0]) *
+                                           ((c3[1] - lo[1]) + (long)(hi[1] - lo[1]) * (c3[2] - lo[2]))];
+              isWallLawFace = !(wvp->yplus < 10.0);
+            }
+            isLowReWall = !isWallLawFace;
+          }
+        }
+        if (isWallLawFace) {
+          /* wall state, wall viscosities, prescribed stress and heat flux
+           * (ref: src/procBlock.cpp:1286-1300, src/wallData.cpp:299-313,
+           * viscousFlux::CalcWallLawFlux src/viscousFlux.cpp:213-249) */
+          const double invScaling = 1.0 / h->cfg.nondimScaling;
+          f1 = 1.0;
+          f2 = 1.0;
+          mu = wvp->viscosity * invScaling;
+          mut = wvp->turbEddyVisc * invScaling;
+          double mfw[AITHER_MAX_SPECIES], pW = 0.0;
+          /* wall mass fractions are the adjacent cell's (ref: src/ghostStates.cpp:146) */
+          mass_fractions(h, b->state + neq * (fi == 0 ? CL(0) : CL(-1)), mfw);
+          for (int ss = 0; ss < ns; ++ss) {
+            state[ss] = mfw[ss] * wvp->density;
+            pW += state[ss] * h->cfg.gasConstant[ss]; /* eos PressureRT */
+          }
+          state[ns] = wbc->velocity[0];
+          state[ns + 1] = wbc->velocity[1];
+          state[ns + 2] = wbc->velocity[2];
+          state[ns + 3] = pW * wvp->temperature;
+          if (rans) {
+            state[ns + 4] = wvp->tke;
+            state[ns + 5] = wvp->sdr;
+          }
+          flux[ns] = wvp->shearStress[0];
+          flux[ns + 1] = wvp->shearStress[1];
+          flux[ns + 2] = wvp->shearStress[2];
+          flux[ns + 3] = (wvp->shearStress[0] * wbc->velocity[0] + wvp->shearStress[1] * wbc->velocity[1] +
+                          wvp->shearStress[2] * wbc->velocity[2]) + wvp->heatFlux;
+          if (rans) { /* WallSigmaK / WallSigmaW: include/turbulence.hpp:478-479, :605-606 */
+            const double sk = is_sst(h) ? 0.85 : 0.6, sw = 0.5;
+            flux[ns + 4] = (wvp->viscosity + sk * wvp->turbEddyVisc) * dot3(kg, fa);
+            flux[ns + 5] = (wvp->viscosity + sw * wvp->turbEddyVisc) * dot3(wg, fa);
+          }
+        } else {
         if (h->cfg.viscRecon == 0) { /* central; ref: :1305-1321 */
           const double w[2] = {cw[CL(-1)], cw[CL(0)]};
           double c[2];
@@ -1630,14 +1895,11 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         }
         limit_turb(h, state);
         if (wDist < 0.0 && wDist > -1.0e-10) wDist = 0.0; /* WALL_DIST_NEG_TOL, :1349-1351 */
-        double mut = 0.0, f1 = 0.0, f2 = 0.0;
         if (rans) eddy_visc_and_blending(h, state, vg, kg, wg, mu, wDist, &mut, &f1, &f2);
         /* viscousFlux::CalcFlux / CalcWallFlux; ref: src/viscousFlux.cpp:58-135,137-196 */
-        const double *fa = farea(b, d, ii, jj, kk);
         const double mus = h->cfg.nondimScaling * mu;
         const double muts = h->cfg.nondimScaling * mut;
-        double tau[3], flux[MAXEQ];
-        for (int e = 0; e < neq; ++e) flux[e] = 0.0;
+        double tau[3];
         tau_normal(vg, fa, mus, muts, tau);
         flux[ns] = tau[0];
         flux[ns + 1] = tau[1];
@@ -1653,11 +1915,6 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         /* species diffusion with the zero-net-mass-flux rescale; not at low-Re wall faces,
          * whose CalcWallFlux has no species terms (ref: src/viscousFlux.cpp:84-105,137-196) */
         double speciesEnthalpyTerm = 0.0;
-        int isLowReWall = 0;
-        if (fi == 0 || fi == nd[d]) {
-          const aither_surface *sf = find_surface(b, ii, jj, kk, 2 * d + (fi == 0 ? 1 : 2));
-          isLowReWall = sf->type == AITHER_BC_VISCOUS_WALL;
-        }
         if (ns > 1 && !isLowReWall) {
           /* schmidt::DiffCoeff (include/diffusion.hpp:100-105; Sc_t = 0.7, turbulence.hpp:71);
            * diffusionModel none: 0 */
@@ -1690,6 +1947,7 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           flux[ns + 4] = (mus + sigma_k(h, f1) * mutt) * dot3(kg, fa);
           flux[ns + 5] = (mus + sigma_w(h, f1) * mutt) * dot3(wg, fa);
         }
+        } /* not a wall-law face */
         /* residual: opposite sign to the inviscid flux; ref: :1392-1429 */
         if (fi > 0) {
           double *r = b->residual + neq * pidx(b, ii - di, jj - dj, kk - dk);
@@ -2805,6 +3063,15 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
     b->wallDist = d->wallDist;
     /* ref: src/utility.cpp:377-398 (HyperplaneReorder) */
     b->order = (int *)malloc(sizeof(int) * 3 * nc);
+    b->wall = (orc_wall_vars **)calloc(b->nsurf > 0 ? b->nsurf : 1, sizeof(orc_wall_vars *));
+    for (int s = 0; s < b->nsurf; ++s) {
+      const aither_surface *sf = &b->surf[s];
+      if (sf->type != AITHER_BC_VISCOUS_WALL) continue;
+      long n = 1;
+      const int ext[3] = {sf->imax - sf->imin, sf->jmax - sf->jmin, sf->kmax - sf->kmin};
+      for (int q = 0; q < 3; ++q) n *= ext[q] > 0 ? ext[q] : 1;
+      b->wall[s] = (orc_wall_vars *)calloc(n, sizeof(orc_wall_vars));
+    }
     long q = 0;
     for (int kk = 0; kk < b->nk; ++kk)
       for (int jj = 0; jj < b->nj; ++jj)
@@ -2830,6 +3097,10 @@ void orc_destroy(orc_level *h) {
     free(b->viscosity); free(b->order);
     free(b->eddyVisc); free(b->f1); free(b->f2); free(b->velGrad);
     free(b->tkeGrad); free(b->omegaGrad);
+    if (b->wall) {
+      for (int s = 0; s < b->nsurf; ++s) free(b->wall[s]);
+      free(b->wall);
+    }
   }
   free(h->blk);
   free(h->conn);
@@ -2917,7 +3188,7 @@ void orc_ghost_state(const aither_cfg *cfg, const double *interior, int bcType,
                      double *ghost) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, 0.0, ghost);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, 0.0, ghost, NULL);
 }
 void orc_offdiag_scalar(const aither_cfg *cfg, const double *stateNb,
                         const double *duNb, const double fArea[4], int positive,
@@ -2955,7 +3226,7 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
                           double wallDist, double nuW, double *ghost) {
   orc_level h;
   level_from_cfg(&h, cfg);
-  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, wallDist, nuW, ghost);
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, wallDist, nuW, ghost, NULL);
 }
 
 /* transport of a mixture state (tests/test_physics_host.py): {viscosity, effective conductivity} */

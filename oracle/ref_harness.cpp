@@ -252,6 +252,8 @@ void DumpConfig(Dump &d, const input &inp, const physics &phys) {
     d.iscalar(p + "isAdiabatic", st->IsAdiabatic());
     d.iscalar(p + "isConstantHeatFlux", st->IsConstantHeatFlux());
     d.iscalar(p + "isWallLaw", st->IsWallLaw());
+    d.scalar(p + "vonKarmen", st->IsWallLaw() ? st->VonKarmen() : 0.41);
+    d.scalar(p + "wallConstant", st->IsWallLaw() ? st->WallConstant() : 5.5);
     d.iscalar(p + "isNonreflecting", st->IsNonreflecting());
     d.scalar(p + "lengthScale", st->LengthScale());
     d.scalar(p + "turbulenceIntensity", st->TurbulenceIntensity());

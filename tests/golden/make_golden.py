@@ -176,6 +176,28 @@ CASES = {
     # viscosity stored by the previous evaluation, which a restart cannot reproduce
     "turbFlatPlate": dict(src="turbFlatPlate", iters=20, full=(0,), edits={},
                           drop=("diagRaw@", "temperature@", "state@it0.start", "x0@")),
+    # reference regression case wallLaw (regressionTests.py:430-446): SST 2003 + BLU-SGS, two
+    # blocks, adiabatic viscous wall with the wall law (y+ root by Ridder's method per wall face,
+    # prescribed wall stress, k and omega from the law); phases at iteration 0 only
+    "wallLaw": dict(src="wallLaw", iters=20, full=(), edits={}, drop=("state@",)),
+    # the same case from a perturbed state (1 % noise about the shipped initial condition), so
+    # that the phase-by-phase dump of iteration 0 is not a uniform flow
+    "wallLaw_cloud": dict(src="wallLaw", iters=6, full=(0,), cloud=(23, 0.01), turb="sst2003",
+                          ic=dict(density=1.2256, velocity=[0.0, 0.0, 75.0], pressure=101325.0),
+                          edits={"initialConditions": "<icState(tag=-1; file=ic.dat)>"},
+                          drop=("diagRaw@", "temperature@", "state@it0.start", "x0@",
+                                "velocityGrad@", "f2@")),
+    # synthetic SST boxes (1 cm: y+ of the wall cells ~ 50) with the wall law on an isothermal
+    # and on a constant-heat-flux wall (wallLaw::IsothermalBCs / HeatFluxBCs; the shipped case is
+    # adiabatic), DPLUR and BLU-SGS
+    "box_walllaw_isothermal": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="dplur", sweeps=3,
+                                                  turb="sst2003", limiter="vanAlbada", size=1e-2,
+                                                  cfl=5.0, wall=("isothermal", 320.0),
+                                                  wall_law=True), iters=10, full=(0,)),
+    "box_walllaw_heatflux": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="blusgs", sweeps=2,
+                                                turb="sst2003", limiter="vanAlbada", size=1e-2,
+                                                cfl=5.0, wall=("heatFlux", 2.0e4),
+                                                wall_law=True), iters=10, full=(0,)),
     # synthetic RANS boxes (1 mm, viscous wall on j-lo): SST 2003 + DPLUR + 4th-order
     # viscous reconstruction, and k-omega Wilcox 2006 + LU-SGS + AUSMPW+ + minmod at CFL 5
     "box_sst": dict(synthetic=dict(ni=12, nj=10, nk=8, solver="dplur", sweeps=3, turb="sst2003",
@@ -213,7 +235,7 @@ def generate(name):
                 blocks = synthetic.read_plot3d(os.path.join(tmp, inp[:-4] + ".xyz"))
                 nodes = np.concatenate([synthetic.centroids(b).reshape(-1, 3) for b in blocks])
                 synthetic.write_cloud_points(os.path.join(tmp, "ic.dat"), nodes, *spec["cloud"],
-                                             turb=spec.get("turb"))
+                                             turb=spec.get("turb"), ic=spec.get("ic"))
         d = refcase.run_harness(tmp, inp, spec["iters"], full=spec["full"], geom=True)
     out = {k: np.asarray(v) for k, v in d.items()
            if not k.startswith("__") and k.split("/")[-1] not in DROP and k != "hist/time" and

@@ -21,6 +21,9 @@ REGRESSION_GOLDENS = {
     # :379-380 (k-omega Wilcox 2006, 20 iterations)
     "turbFlatPlate": (20, [2.2309e-01, 2.9862e-01, None, 3.2376e-01, 2.1910e-01, 2.5208e-07,
                            3.3009e-06]),
+    # :444-445 (SST 2003 + BLU-SGS + wall law, 20 iterations)
+    "wallLaw": (20, [7.4098e-01, None, 3.1463e-01, 9.2837e-01, 7.2133e-01, 2.6860e-02,
+                     2.6250e-07]),
 }
 
 

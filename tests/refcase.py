@@ -75,7 +75,11 @@ def cfg_from_dump(d):
             heatFlux=float(g(p + "heatFlux")[0]), isIsothermal=int(g(p + "isIsothermal")[0]),
             isConstantHeatFlux=int(g(p + "isConstantHeatFlux")[0]),
             turbulenceIntensity=float(g(p + "turbulenceIntensity")[0]),
-            eddyViscosityRatio=float(g(p + "eddyViscosityRatio")[0])))
+            eddyViscosityRatio=float(g(p + "eddyViscosityRatio")[0]),
+            isWallLaw=int(g(p + "isWallLaw")[0]) if ("cfg/" + p + "isWallLaw") in d else 0,
+            vonKarmen=float(g(p + "vonKarmen")[0]) if ("cfg/" + p + "vonKarmen") in d else 0.41,
+            wallConstant=float(g(p + "wallConstant")[0]) if ("cfg/" + p + "wallConstant") in d
+            else 5.5))
     return make_cfg(
         numSpecies=ns, numTurb=int(g("numTurb")[0]), numGhosts=int(g("numGhosts")[0]),
         isViscous=int(g("isViscous")[0]), isRANS=int(g("isRANS")[0]),

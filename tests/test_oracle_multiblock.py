@@ -69,6 +69,19 @@ def test_oracle_uniform_flow_rans():
     assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9) <= 1e-9
 
 
+def test_oracle_wall_law():
+    """testCases/wallLaw (regressionTests.py:430-446): SST 2003 + BLU-SGS, two blocks, adiabatic
+    viscous wall with the wall law -- y+ by Ridder's method per wall face, prescribed wall shear
+    stress, k and omega ghost cells from the law. The shipped uniform start for 20 iterations
+    (with the reference's own regression golden), and the same case from a perturbed state phase
+    by phase."""
+    d = gc.load("wallLaw_cloud")
+    gc.check_phases(oracle.OracleLevel, d, 0, dict(TOL, turb=1e-12, diag=1e-13))
+    assert gc.check_history(oracle.OracleLevel, d, 6, 1e-9) <= 1e-9
+    d = gc.load("wallLaw")
+    assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9, name="wallLaw") <= 1e-9
+
+
 def test_oracle_periodic_connection():
     """A periodic pair (the block's own i-lo and i-hi faces, `periodic(startTag; endTag;
     translation)`, reference src/boundaryConditions.cpp:2224-2300): the block exchanges ghost layers

@@ -33,7 +33,11 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_
                 "box_mix3_visc", "box_mix3_sst", "box_mix3_euler", "box_mix3_roe", "box_mix2_visc",
                 # WENO-Z + Crank-Nicolson + global time step + relaxation 1.1; first-order
                 # reconstruction (one ghost layer); constant-heat-flux viscous wall
-                "box_wenoz_cn", "box_first_order", "box_visc_heatflux", "box_inlet_outlet"]
+                "box_wenoz_cn", "box_first_order", "box_visc_heatflux", "box_inlet_outlet",
+                # wall law (White & Christoph / Nichols & Nelson) on an isothermal and on a
+                # constant-heat-flux wall; the adiabatic one is the reference's wallLaw case
+                # (two blocks: test_oracle_multiblock.py)
+                "box_walllaw_isothermal", "box_walllaw_heatflux"]
 
 
 # viscousFlatPlate runs at CFL 1e4 from a uniform start: the implicit update is the solution of a
@@ -60,7 +64,9 @@ def test_oracle_phases_match_reference(name):
                                         ("box_mix3_visc", 12), ("box_mix3_sst", 12),
                                         ("box_mix3_euler", 12), ("box_mix3_roe", 3), ("box_mix2_visc", 12),
                                         ("box_wenoz_cn", 10), ("box_first_order", 10),
-                                        ("box_visc_heatflux", 10), ("box_inlet_outlet", 10)])
+                                        ("box_visc_heatflux", 10), ("box_inlet_outlet", 10),
+                                        ("box_walllaw_isothermal", 10),
+                                        ("box_walllaw_heatflux", 10)])
 def test_oracle_history_matches_reference(name, iters):
     """L2 history within 1e-9 relative (north_star bar) + the reference's regression goldens."""
     d = gc.load(name)
