@@ -63,6 +63,7 @@ struct HostBlock {
   SurfDev *dSurfs = nullptr;
   int nBcSurfs = 0;
   EdgeSurf *dEdgeSurfs = nullptr;  // every surface of the block, connections included
+  double *dWallVars = nullptr;     // wall-law records (walllaw.cuh), null without wall-law walls
   int nEdgeSurfs = 0;
   long long bcThreads = 0;
   uint8_t *dConnFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -299,6 +300,12 @@ bool Supported(const aither_cfg &c, std::string *why) {
     return false;
   }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
+  for (int q = 0; q < c.numBCStates; ++q) {
+    if (c.bcStates[q].isWallLaw && !c.isRANS) {
+      *why = "the wall law (wallTreatment=wallLaw) is built for RANS runs";
+      return false;
+    }
+  }
   return true;
 }
 
@@ -822,6 +829,7 @@ void FreeAll(aither_gpu *h) {
         if (ex) cudaGraphExecDestroy(ex);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
+    if (hb.dWallVars) cudaFree(hb.dWallVars);
     for (auto &p : hb.dConnFace)
       if (p) cudaFree(p);
   }
@@ -1166,8 +1174,20 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     }
     {
       std::vector<EdgeSurf> es;
+      long long faceBase = 0;  // SurfDev::faceOffset / g of the same surface
       for (const auto &sf : hb.surfaces) {
         EdgeSurf e;
+        {
+          const int st = SurfaceType(sf);
+          const int d3 = (st - 1) / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+          const int lo[3] = {sf.imin, sf.jmin, sf.kmin}, hi[3] = {sf.imax, sf.jmax, sf.kmax};
+          if (sf.type == AITHER_BC_INTERBLOCK || sf.type == AITHER_BC_PERIODIC) {
+            e.faceBase = -1;
+          } else {
+            e.faceBase = static_cast<int>(faceBase);
+            faceBase += static_cast<long long>(hi[d1] - lo[d1]) * (hi[d2] - lo[d2]);
+          }
+        }
         e.type = sf.type;
         e.surfType = SurfaceType(sf);
         e.tag = sf.tag;
@@ -1187,6 +1207,19 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     }
     hb.nBcSurfs = static_cast<int>(sd.size());
     hb.bcThreads = off;
+    {
+      // wall-law walls: one record per boundary face of the block (walllaw.cuh)
+      bool wallLaw = false;
+      for (const auto &v : sd)
+        wallLaw = wallLaw || (v.type == AITHER_BC_VISCOUS_WALL && cfg->isViscous &&
+                              cfg->bcStates[v.bcIndex].isWallLaw);
+      if (wallLaw && off > 0) {
+        const size_t bytes = sizeof(double) * kWallVarsStride * static_cast<size_t>(off / g);
+        CKC(cudaMalloc(&hb.dWallVars, bytes));
+        CKC(cudaMemset(hb.dWallVars, 0, bytes));
+        b.wallVars = hb.dWallVars;
+      }
+    }
     if (!sd.empty()) {
       CKC(cudaMalloc(&hb.dSurfs, sizeof(SurfDev) * sd.size()));
       CKC(cudaMemcpy(hb.dSurfs, sd.data(), sizeof(SurfDev) * sd.size(), cudaMemcpyHostToDevice));

@@ -52,6 +52,9 @@ struct BlockDev {
   double *velGrad;      // 9   velGrad[3 r + c] = d u_c / d x_r
   double *tkeGrad;      // 3
   double *omegaGrad;    // 3
+  // wall-law runs only (else null): kWallVarsStride doubles per boundary face of the block
+  // (walllaw.cuh), face index = SurfDev::faceOffset / g + d1 + n1 * d2
+  double *wallVars;
   // per boundary face: 1 if the neighbour across that block face contributes to the implicit
   // off-diagonals, i.e. the face belongs to a connection (interblock / periodic) boundary
   // (ref: src/procBlock.cpp:1064,1115; include/boundaryConditions.hpp:287-293).

@@ -18,30 +18,56 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "walllaw.cuh"
 
 namespace aither {
 
-// viscous-wall ghost state, low-Re treatment (ref: src/ghostStates.cpp:134-258): velocity
-// mirrored about the wall velocity; adiabatic keeps rho and p, isothermal / heat-flux walls set
-// the ghost temperature and take rho from p = rho R T
+// viscous-wall ghost state (ref: src/ghostStates.cpp:134-281): velocity mirrored about the wall
+// velocity; adiabatic keeps rho and p, isothermal / heat-flux walls set the ghost temperature and
+// take rho from p = rho R T. Low-Re treatment: k = 0 and the omega wall value; with the wall law
+// (bc.isWallLaw, `nA` = unit normal out of the domain) the ghost temperature, k and omega come
+// from the law unless its y+ fell below 10 (wallVars::SwitchToLowRe). `wvOut`: the wall variables
+// of this face, y+ = 0 when the wall has no wall law.
 template <int NS, int NT>
 AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double *interior,
                                 const aither_bc_state &bc, double wallDist, double *ghost,
-                                double nuW = 0.0, int layer = 1) {
+                                double nuW = 0.0, int layer = 1, const double *nA = nullptr,
+                                bool isLower = false, WallVars *wvOut = nullptr) {
   using E = Eq<NS, NT>;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
   ghost[E::imx] = 2.0 * bc.velocity[0] - interior[E::imx];
   ghost[E::imy] = 2.0 * bc.velocity[1] - interior[E::imy];
   ghost[E::imz] = 2.0 * bc.velocity[2] - interior[E::imz];
+  WallVars wv;
+  wv.yplus = 0.0;
+  const bool wallLaw = bc.isWallLaw && nA != nullptr;
+  bool lowRe = true;
+  if (wallLaw) {
+    WallLawEval<NS, NT>(g, tr, bc,
+                        bc.isIsothermal ? kWallIsothermal
+                                        : (bc.isConstantHeatFlux ? kWallHeatFlux : kWallAdiabatic),
+                        interior, wallDist, nA, isLower, wv);
+    lowRe = wv.SwitchToLowRe();
+  }
   if (bc.isIsothermal || bc.isConstantHeatFlux) {
     const double tInt = Temperature<NS>(g, interior);
     double tGhost;
     if (bc.isIsothermal) {
-      tGhost = 2.0 * bc.temperature - tInt;
+      if (!lowRe) {  // wall-law heat flux through laminar + turbulent conductivity (:160-171)
+        const double kappa = MixtureEffConductivity<NS>(tr, wv.t, interior) +
+                             wv.mut * Mixture<NS>(g, interior).cp / TurbPrandtl(tr.turbModel);
+        tGhost = bc.temperature - wv.heatFlux / kappa * 2.0 * wallDist;
+      } else {
+        tGhost = 2.0 * bc.temperature - tInt;
+      }
     } else {
-      const double kappa = MixtureEffConductivity<NS>(tr, tInt, interior);
-      tGhost = tInt - bc.heatFlux / kappa * 2.0 * wallDist;
+      if (!lowRe) {  // wall-law wall temperature (:212-219)
+        tGhost = 2.0 * wv.t - tInt;
+      } else {
+        const double kappa = MixtureEffConductivity<NS>(tr, tInt, interior);
+        tGhost = tInt - bc.heatFlux / kappa * 2.0 * wallDist;
+      }
     }
     const double rhoInt = SpeciesSum<NS>(interior);
     double R = 0.0;
@@ -52,14 +78,24 @@ AITHER_HD void ViscousWallGhost(const Gas &g, const Transport &tr, const double 
     for (int q = 0; q < NS; ++q) ghost[q] = rho * (interior[q] / rhoInt);
   }
   if (NT > 1) {
-    // k = 0 at the wall; omega_wall = scaling^2 60 nu_w / (beta d^2) (ref: :262-281)
-    ghost[E::it] = -1.0 * interior[E::it];
-    const double wWall = tr.scaling * tr.scaling * 60.0 * nuW /
-                         (wallDist * wallDist * TurbWallBeta(tr.turbModel));
     constexpr int iw = E::it + (NT > 1 ? 1 : 0);
-    ghost[iw] = 2.0 * wWall - interior[iw];
-    if (layer > 1) ghost[iw] = layer * ghost[iw] - wWall;
+    if (!lowRe) {  // k and omega of the law at the wall (:173-180, :221-228, :248-255)
+      ghost[E::it] = 2.0 * wv.tke - interior[E::it];
+      ghost[iw] = 2.0 * wv.sdr - interior[iw];
+      if (layer > 1) {
+        ghost[E::it] = layer * ghost[E::it] - wv.tke;
+        ghost[iw] = layer * ghost[iw] - wv.sdr;
+      }
+    } else {
+      // k = 0 at the wall; omega_wall = scaling^2 60 nu_w / (beta d^2) (ref: :262-281)
+      ghost[E::it] = -1.0 * interior[E::it];
+      const double wWall = tr.scaling * tr.scaling * 60.0 * nuW /
+                           (wallDist * wallDist * TurbWallBeta(tr.turbModel));
+      ghost[iw] = 2.0 * wWall - interior[iw];
+      if (layer > 1) ghost[iw] = layer * ghost[iw] - wWall;
+    }
   }
+  if (wvOut) *wvOut = wv;
 }
 
 // ---- K11b: viscous-wall ghost cells (ref: src/procBlock.cpp:2760-2833) -------------------------
@@ -111,7 +147,41 @@ __global__ void ViscousWallKernel(BlockDev b, Params p, const SurfDev *__restric
     for (int q = 0; q < NS; ++q) rhoA += __ldg(b.state + q * b.fs + aidx);
     nuW = b.viscosity[aidx] / rhoA;
   }
-  ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bcs[sf.bcIndex], wd, ghost, nuW, layer);
+  const aither_bc_state &bc = bcs[sf.bcIndex];
+  if (bc.isWallLaw) {
+    // unit normal out of the domain and the record of this face (first layer only;
+    // ref: src/procBlock.cpp:6287-6290)
+    c[d3] = r3;
+    const long long fidx = CellIdx(b, c[0], c[1], c[2]);
+    const bool isLower = sf.surfType % 2 == 1;
+    double nA[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double a = __ldg(b.fA[d3] + q * b.fs + fidx);
+      nA[q] = isLower ? -1.0 * a : a;
+    }
+    WallVars wv;
+    ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bc, wd, ghost, nuW, layer, nA, isLower, &wv);
+    if (layer == 1 && b.wallVars) {
+      double *w = b.wallVars + kWallVarsStride * (sf.faceOffset / b.g + a1 + static_cast<long long>(n1) * a2);
+      w[kWvYplus] = wv.yplus;
+      w[kWvTau] = wv.tau[0];
+      w[kWvTau + 1] = wv.tau[1];
+      w[kWvTau + 2] = wv.tau[2];
+      w[kWvHeatFlux] = wv.heatFlux;
+      w[kWvMu] = wv.mu;
+      w[kWvMut] = wv.mut;
+      w[kWvRho] = wv.rho;
+      w[kWvT] = wv.t;
+      w[kWvTke] = wv.tke;
+      w[kWvSdr] = wv.sdr;
+      w[kWvVelWall] = bc.velocity[0];
+      w[kWvVelWall + 1] = bc.velocity[1];
+      w[kWvVelWall + 2] = bc.velocity[2];
+    }
+  } else {
+    ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bc, wd, ghost, nuW, layer);
+  }
   c[d3] = gCell;
   StoreCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), ghost);
 }
@@ -123,6 +193,7 @@ __global__ void ViscousWallKernel(BlockDev b, Params p, const SurfDev *__restric
 // reference's layer order because later layers read earlier ones.
 struct EdgeSurf {
   int type, surfType, tag, bcIndex;
+  int faceBase;      // first boundary-face record of the surface in BlockDev::wallVars (-1: connection)
   int lo[3], hi[3];  // node-index ranges of the surface as given (imin..kmax)
 };
 __device__ __forceinline__ void DirIjk(int dd, int d1, int d2, int d3, int *c) {
@@ -489,7 +560,8 @@ struct FaceOut {
 
 template <int NS, int NT, int D>
 __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, long long idx,
-                                         FaceOut<NS + 4 + NT> &o, bool lowReWall = false) {
+                                         FaceOut<NS + 4 + NT> &o, bool lowReWall = false,
+                                         const double *wlv = nullptr, bool wallUpper = false) {
   using E = Eq<NS, NT>;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
   constexpr int NG = NT > 0 ? 6 : 4;
@@ -681,6 +753,44 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
     o.flux[E::it] = fk * mag;
     o.flux[iw] = fw * mag;
   }
+  if (wlv != nullptr) {
+    // boundary face on a wall-law wall: the gradients stand, everything else is prescribed by the
+    // law -- wall state (src/wallData.cpp:299-313), wall viscosities, f1 = f2 = 1
+    // (src/procBlock.cpp:1286-1300) and viscousFlux::CalcWallLawFlux (src/viscousFlux.cpp:213-249)
+    const double invScaling = 1.0 / p.tr.scaling;
+    o.f1 = 1.0;
+    o.f2 = 1.0;
+    o.mu = wlv[kWvMu] * invScaling;
+    o.mut = wlv[kWvMut] * invScaling;
+    const long long ca = wallUpper ? idx - sd : idx;  // wall mass fractions: the adjacent cell's
+    double rhoA = 0.0, pW = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) rhoA += __ldg(b.state + q * b.fs + ca);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      o.st[q] = (__ldg(b.state + q * b.fs + ca) / rhoA) * wlv[kWvRho];
+      pW += o.st[q] * p.gas.R[q];
+      o.flux[q] = 0.0;
+    }
+    const double vw[3] = {wlv[kWvVelWall], wlv[kWvVelWall + 1], wlv[kWvVelWall + 2]};
+    o.st[E::imx] = vw[0];
+    o.st[E::imy] = vw[1];
+    o.st[E::imz] = vw[2];
+    o.st[E::ie] = pW * wlv[kWvT];
+    const double tw[3] = {wlv[kWvTau], wlv[kWvTau + 1], wlv[kWvTau + 2]};
+    o.flux[E::imx] = tw[0] * mag;
+    o.flux[E::imy] = tw[1] * mag;
+    o.flux[E::imz] = tw[2] * mag;
+    o.flux[E::ie] = ((tw[0] * vw[0] + tw[1] * vw[1] + tw[2] * vw[2]) + wlv[kWvHeatFlux]) * mag;
+    if (NT > 0) {
+      o.st[E::it] = wlv[kWvTke];
+      o.st[iw] = wlv[kWvSdr];
+      const double fk = (wlv[kWvMu] + TurbSigmaK(p.tr.turbModel, 1.0) * wlv[kWvMut]) * Dot3(o.kg, n);
+      const double fw = (wlv[kWvMu] + TurbSigmaW(p.tr.turbModel, 1.0) * wlv[kWvMut]) * Dot3(o.wg, n);
+      o.flux[E::it] = fk * mag;
+      o.flux[iw] = fw * mag;
+    }
+  }
 }
 
 template <int NS, int NT>
@@ -694,14 +804,15 @@ template <int NS, int NT, int D, bool BLOCK>
 __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Params &p, long long idx,
                                                   const double *s, double visc, double vol,
                                                   RansAcc<NS, NT> &a, double *dblk, bool wallLo,
-                                                  bool wallHi) {
+                                                  bool wallHi, const double *wlvLo = nullptr,
+                                                  const double *wlvHi = nullptr) {
   using E = Eq<NS, NT>;
   constexpr double sixth = 1.0 / 6.0;
   constexpr int iw = E::it + (NT > 1 ? 1 : 0);
   const long long sd = Stride(b, D);
   FaceOut<E::neq> f;
   // lower face: this cell is the face's upper cell (ref: :1432-1493)
-  RansFace<NS, NT, D>(b, p, idx, f, wallLo);
+  RansFace<NS, NT, D>(b, p, idx, f, wallLo, wlvLo, false);
 #pragma unroll
   for (int e = (NS > 1 ? 0 : NS); e < E::neq; ++e) a.r[e] += f.flux[e];
   const double mutLo = f.mut, f1Lo = f.f1;
@@ -738,7 +849,7 @@ __device__ __forceinline__ void RansAccumulateDir(const BlockDev &b, const Param
     for (int q = 0; q < Blk<NS, NT>::n; ++q) dblk[q] += J[q];
   }
   // upper face: this cell is the face's lower cell (ref: :1392-1429)
-  RansFace<NS, NT, D>(b, p, idx + sd, f, wallHi);
+  RansFace<NS, NT, D>(b, p, idx + sd, f, wallHi, wlvHi, true);
 #pragma unroll
   for (int e = (NS > 1 ? 0 : NS); e < E::neq; ++e) a.r[e] -= f.flux[e];
   if constexpr (BLOCK) {  // - dFv/dU of the upper face (left = true); ref: src/procBlock.cpp:1420-1428
@@ -796,26 +907,45 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
   for (int q = 0; q < 3; ++q) a.kg[q] = a.wg[q] = 0.0;
   // multi-species: boundary faces on a viscous wall carry no species diffusion
+  // and a wall-law wall whose y+ stayed >= 10 prescribes the whole flux of its faces
   bool wl[3] = {false, false, false}, wh[3] = {false, false, false};
-  if (NS > 1) {
+  const double *vl[3] = {nullptr, nullptr, nullptr}, *vh[3] = {nullptr, nullptr, nullptr};
+  if (NS > 1 || b.wallVars != nullptr) {
     const int c[3] = {i, j, k}, nd[3] = {b.ni, b.nj, b.nk};
+    auto wallRecord = [&](int sf, int d) -> const double * {
+      // record index as written by ViscousWallKernel: d1 + n1 * d2 with the reference's
+      // direction cycling
+      if (b.wallVars == nullptr || surfs[sf].faceBase < 0) return nullptr;
+      const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+      const int n1 = surfs[sf].hi[d1] - surfs[sf].lo[d1];
+      const double *w = b.wallVars + kWallVarsStride * (static_cast<long long>(surfs[sf].faceBase) +
+                                                        (c[d1] - surfs[sf].lo[d1]) +
+                                                        static_cast<long long>(n1) * (c[d2] - surfs[sf].lo[d2]));
+      return w[kWvYplus] < 10.0 ? nullptr : w;
+    };
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (c[d] == 0) {
         const int sf = FindSurface(surfs, nsurf, c, 2 * d + 1);
-        wl[d] = sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL;
+        if (sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL) {
+          vl[d] = wallRecord(sf, d);
+          wl[d] = vl[d] == nullptr;
+        }
       }
       if (c[d] == nd[d] - 1) {
         int cu[3] = {i, j, k};
         cu[d] += 1;
         const int sf = FindSurface(surfs, nsurf, cu, 2 * d + 2);
-        wh[d] = sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL;
+        if (sf >= 0 && surfs[sf].type == AITHER_BC_VISCOUS_WALL) {
+          vh[d] = wallRecord(sf, d);
+          wh[d] = vh[d] == nullptr;
+        }
       }
     }
   }
-  RansAccumulateDir<NS, NT, 0, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[0], wh[0]);
-  RansAccumulateDir<NS, NT, 1, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[1], wh[1]);
-  RansAccumulateDir<NS, NT, 2, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[2], wh[2]);
+  RansAccumulateDir<NS, NT, 0, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[0], wh[0], vl[0], vh[0]);
+  RansAccumulateDir<NS, NT, 1, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[1], wh[1], vl[1], vh[1]);
+  RansAccumulateDir<NS, NT, 2, BLOCK>(b, p, idx, s, visc, vol, a, dblk, wl[2], wh[2], vl[2], vh[2]);
   if (NT > 0) {
     // source terms (ref: src/procBlock.cpp:5956-6025, src/source.cpp:64-82)
     double src[2], beta = 0.0;

@@ -3230,6 +3230,29 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
 }
 
 /* transport of a mixture state (tests/test_physics_host.py): {viscosity, effective conductivity} */
+/* wallLaw::AdiabaticBCs (mode 0) / HeatFluxBCs (1) / IsothermalBCs (2) for the boundary state
+ * `tag`; out = {yplus, tau x y z, heatFlux, viscosity, eddy viscosity, density, temperature,
+ * tke, sdr} (tests/test_physics_host.py) */
+void orc_wall_law(const aither_cfg *cfg, int mode, int tag, const double *state,
+                  double wallDist, const double area[3], int isLower, double out[11]) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  orc_wall_vars wv;
+  memset(&wv, 0, sizeof(wv));
+  wall_law_eval(&h, bc_data(&h, tag), mode, state, wallDist, area, isLower, &wv);
+  out[0] = wv.yplus;
+  out[1] = wv.shearStress[0];
+  out[2] = wv.shearStress[1];
+  out[3] = wv.shearStress[2];
+  out[4] = wv.heatFlux;
+  out[5] = wv.viscosity;
+  out[6] = wv.turbEddyVisc;
+  out[7] = wv.density;
+  out[8] = wv.temperature;
+  out[9] = wv.tke;
+  out[10] = wv.sdr;
+}
+
 void orc_mixture_transport(const aither_cfg *cfg, const double *state, double out[2]) {
   orc_level h;
   level_from_cfg(&h, cfg);

@@ -77,6 +77,9 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
                           const double areaUnit[3], int surfType, int tag, int layer,
                           double wallDist, double nuW, double *ghost);
 
+void orc_wall_law(const aither_cfg *cfg, int mode, int tag, const double *state,
+                  double wallDist, const double area[3], int isLower, double out[11]);
+
 void orc_mixture_transport(const aither_cfg *cfg, const double *state, double out[2]);
 
 #ifdef __cplusplus

@@ -3,6 +3,7 @@
 // GPU. Never part of libaither_b200.so; built on demand by tests/test_physics_host.py.
 #include "../../aither_b200/csrc/physics.cuh"
 #include "../../aither_b200/csrc/turbulence.cuh"
+#include "../../aither_b200/csrc/walllaw.cuh"
 
 using namespace aither;
 
@@ -122,6 +123,24 @@ void hs_ghost_state_rans(const aither_cfg *c, const double *interior, int bcType
   const Gas g = GasFromCfg(c);
   const Transport tr = TransportFromCfg(c);
   GhostState<1, 2>(g, interior, bcType, area, surf, *Find(c, tag), layer, ghost, &tr);
+}
+void hs_wall_law(const aither_cfg *c, int mode, int tag, const double *state, double wallDist,
+                 const double *area, int isLower, double *out) {
+  const Gas g = GasFromCfg(c);
+  const Transport tr = TransportFromCfg(c);
+  WallVars wv;
+  WallLawEval<1, 2>(g, tr, *Find(c, tag), mode, state, wallDist, area, isLower != 0, wv);
+  out[0] = wv.yplus;
+  out[1] = wv.tau[0];
+  out[2] = wv.tau[1];
+  out[3] = wv.tau[2];
+  out[4] = wv.heatFlux;
+  out[5] = wv.mu;
+  out[6] = wv.mut;
+  out[7] = wv.rho;
+  out[8] = wv.t;
+  out[9] = wv.tke;
+  out[10] = wv.sdr;
 }
 void hs_inviscid_flux_rans(const aither_cfg *c, const double *l, const double *r, const double *n,
                            int fast, double *f) {

@@ -23,7 +23,9 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_
                 "box_mix3_visc", "box_mix3_sst", "box_mix3_euler", "box_mix3_roe", "box_mix2_visc",
                 # WENO-Z + Crank-Nicolson + global time step + relaxation 1.1; first-order
                 # reconstruction (one ghost layer); constant-heat-flux viscous wall
-                "box_wenoz_cn", "box_first_order", "box_visc_heatflux", "box_inlet_outlet"]
+                "box_wenoz_cn", "box_first_order", "box_visc_heatflux", "box_inlet_outlet",
+                # SST with the wall law on an isothermal / constant-heat-flux wall
+                "box_walllaw_isothermal", "box_walllaw_heatflux"]
 
 
 def make_gpu_level(prob):
@@ -63,7 +65,9 @@ def test_gpu_phases_match_reference(name):
                                         ("box_mix3_visc", 12), ("box_mix3_sst", 12),
                                         ("box_mix3_euler", 12), ("box_mix3_roe", 3), ("box_mix2_visc", 12),
                                         ("box_wenoz_cn", 10), ("box_first_order", 10),
-                                        ("box_visc_heatflux", 10), ("box_inlet_outlet", 10)])
+                                        ("box_visc_heatflux", 10), ("box_inlet_outlet", 10),
+                                        ("box_walllaw_isothermal", 10),
+                                        ("box_walllaw_heatflux", 10)])
 def test_gpu_history_matches_reference(name, iters):
     d = gc.load(name)
     worst = gc.check_history(make_gpu_level, d, iters, 1e-9, name=name)

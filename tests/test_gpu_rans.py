@@ -37,6 +37,39 @@ def test_uniform_flow_rans_matches_reference():
     assert gc.check_history(make_gpu_level, d, 20, 1e-9) <= 1e-9
 
 
+def test_wall_law_matches_reference():
+    """testCases/wallLaw (regressionTests.py:430-446): SST 2003 + BLU-SGS, two blocks, adiabatic
+    wall with the wall law. Phase by phase from a perturbed state, and the shipped uniform start
+    for 20 iterations with the reference's own regression golden. The y+ root comes out of
+    Ridder's method with transcendental functions (asin, exp, pow) of another libm; measured on
+    B200 (profiles/r01n_walllaw_errors.txt): residual 1.6e-13, turbulence fields 8.7e-13, history
+    2.9e-13 (perturbed start) and 9.2e-11 (uniform start; the CPU oracle itself: 1.05e-10)."""
+    d = gc.load("wallLaw_cloud")
+    gc.check_phases(make_gpu_level, d, 0, TOL)
+    assert gc.check_history(make_gpu_level, d, 6, 1e-9) <= 1e-9
+    d = gc.load("wallLaw")
+    assert gc.check_history(make_gpu_level, d, 20, 1e-9, name="wallLaw") <= 1e-9
+
+
+def test_wall_law_records_on_device():
+    """the wall-law runs above really take the wall-law branch: switching the law off in the
+    boundary state changes the turbulence residuals of the first iteration"""
+    d = gc.load("wallLaw_cloud")
+    cfl = float(d["hist/cfl"][0])
+    out = []
+    for law in (1, 0):
+        prob = refcase.problem_from_dump(d, state_key="state0")
+        for q in range(prob.cfg.numBCStates):
+            if prob.cfg.bcStates[q].isWallLaw:
+                prob.cfg.bcStates[q].isWallLaw = law
+        lvl = make_gpu_level(prob)
+        lvl.store_old_solution(0)
+        out.append(np.asarray(lvl.iterate(cfl)[0]))
+        lvl.close()
+    assert abs(out[0][5] / out[1][5] - 1.0) > 0.1
+    assert np.allclose(out[0], d["hist/residL2"][0], rtol=1e-9)
+
+
 @pytest.mark.parametrize("name", ["box_sst", "box_kw", "box_sst_blusgs", "box_blusgs_visc"])
 def test_rans_split_box_matches_oracle(name):
     d = gc.load(name)

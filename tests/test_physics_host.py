@@ -289,6 +289,41 @@ def test_ghost_state_rans(hs, bc, tag):
                 assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a) + 1e-14 * np.abs(a[:5]).max()), (a, b)
 
 
+@pytest.mark.parametrize("mode,fixture", [(0, "wallLaw"), (1, "box_walllaw_heatflux"),
+                                          (2, "box_walllaw_isothermal")])
+def test_wall_law(hs, mode, fixture):
+    """wall law (walllaw.cuh WallLawEval vs the oracle's restatement of src/wallLaw.cpp): y+ root,
+    wall shear stress, heat flux / wall temperature, wall eddy viscosity, k and omega, for random
+    wall-adjacent states at wall distances on both sides of the root bracket [10, 1e4] (without a
+    root in the bracket the reference keeps the values of its last evaluation, y+ = 1e4)."""
+    import goldencheck as gc
+    import refcase
+    d = gc.load(fixture)
+    cfg = refcase.cfg_from_dump(d)
+    tag = [cfg.bcStates[q].tag for q in range(cfg.numBCStates) if cfg.bcStates[q].isWallLaw][0]
+    L = oracle.lib()
+    D = C.c_double
+    for f in (L.orc_wall_law, hs.hs_wall_law):
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, PD, D, PD, C.c_int, PD]
+        f.restype = None
+    rng = np.random.default_rng(59 + mode)
+    unbracketed, bracketed = 0, 0
+    for trial in range(300):
+        s, n = rand_rans_state(rng, 0.25), unit(rng)
+        wd = 10.0 ** rng.uniform(-6.5, -2.5)
+        a, b = np.empty(11), np.empty(11)
+        L.orc_wall_law(C.byref(cfg), mode, tag, ptr(s), wd, ptr(n), trial % 2, ptr(a))
+        hs.hs_wall_law(C.byref(cfg), mode, tag, ptr(s), wd, ptr(n), trial % 2, ptr(b))
+        if not np.isfinite(a).all():
+            continue
+        unbracketed += a[0] == 1.0e4
+        bracketed += 10.0 <= a[0] < 1.0e4
+        scale = np.abs(a)
+        scale[1:4] = np.abs(a[1:4]).max()
+        assert np.all(np.abs(a - b) <= 1e-11 * scale + 1e-300), (trial, a, b)
+    assert unbracketed > 10 and bracketed > 50
+
+
 @pytest.mark.parametrize("flux", ["roe", "ausm"])
 @pytest.mark.parametrize("fast", [0, 1])
 def test_inviscid_flux_rans(hs, flux, fast):
