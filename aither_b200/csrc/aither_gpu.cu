@@ -64,6 +64,7 @@ struct HostBlock {
   int nBcSurfs = 0;
   EdgeSurf *dEdgeSurfs = nullptr;  // every surface of the block, connections included
   double *dWallVars = nullptr;     // wall-law records (walllaw.cuh), null without wall-law walls
+  double *dPatchMach = nullptr;    // {average, maximum} Mach number per BC surface (non-reflecting BCs)
   int nEdgeSurfs = 0;
   long long bcThreads = 0;
   uint8_t *dConnFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -148,6 +149,7 @@ struct aither_gpu {
   bool keepMatrixResid = false;
   int jac = kJacScalar;            // JacKind of the implicit matrix
   bool consNStale = false;         // U^n not materialised (Params::timeTermsVanish)
+  bool nonreflecting = false;      // some inlet / pressure outlet is non-reflecting
   bool lusgsGraphs = true;         // AITHER_B200_LUSGS_GRAPH=0: plain launches (A/B)
   bool lusgsSplit = true;          // AITHER_B200_LUSGS_SPLIT=0: one thread per cell (A/B)
   bool stateMovedSinceStore = false;
@@ -301,6 +303,11 @@ bool Supported(const aither_cfg &c, std::string *why) {
   }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
   for (int q = 0; q < c.numBCStates; ++q) {
+    if (c.bcStates[q].isNonreflecting && !c.isViscous) {
+      *why = "non-reflecting boundary conditions are built for viscous runs (they read the "
+             "pressure / velocity gradients the viscous fluxes leave behind)";
+      return false;
+    }
     if (c.bcStates[q].isWallLaw && !c.isRANS) {
       *why = "the wall law (wallTreatment=wallLaw) is built for RANS runs";
       return false;
@@ -483,8 +490,11 @@ int PhaseBoundaryConditionsT(aither_gpu *h) {
     if (hb.bcThreads == 0) continue;
     ScopedLaunch sl(h, kFamBc);
     const int grid = static_cast<int>((hb.bcThreads + 127) / 128);
+    if (hb.dPatchMach)
+      PatchMachKernel<NS, NT><<<hb.nBcSurfs, 256, 0, h->stream>>>(hb.dev, h->params, hb.dSurfs,
+                                                                  h->dBcStates, hb.dPatchMach);
     BcKernel<NS, NT><<<grid, 128, 0, h->stream>>>(hb.dev, h->params, hb.dSurfs, hb.nBcSurfs,
-                                               h->dBcStates, hb.bcThreads);
+                                               h->dBcStates, hb.bcThreads, hb.dPatchMach);
   }
   CK(cudaGetLastError());
   if (Exchange(h, kHaloState)) return 1;
@@ -541,6 +551,8 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
       ScopedLaunch sl(h, kFamViscFlux);
       const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
       LaunchRansCell<NS, NT>(b, h->params, grid, h->stream, block, hb.dEdgeSurfs, hb.nEdgeSurfs);
+      if (b.pressGrad)  // non-reflecting BCs of the next iteration read the pressure gradient
+        CellGradKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, 0);
       continue;
     }
     {
@@ -552,6 +564,11 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
       ScopedLaunch sl(h, kFamViscFlux);
       ViscAccumKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(b, h->params, b.xalt, b.x,
                                                                          1);
+    }
+    if (b.pressGrad) {  // ... and the velocity gradient, which this path does not keep
+      ScopedLaunch sl(h, kFamViscFlux);
+      const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
+      CellGradKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, 1);
     }
   }
   CK(cudaGetLastError());
@@ -830,6 +847,7 @@ void FreeAll(aither_gpu *h) {
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     if (hb.dWallVars) cudaFree(hb.dWallVars);
+    if (hb.dPatchMach) cudaFree(hb.dPatchMach);
     for (auto &p : hb.dConnFace)
       if (p) cudaFree(p);
   }
@@ -921,6 +939,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   h->nRanks = nRanks;
   h->ns = cfg->numSpecies;
   h->nt = cfg->numTurb;
+  for (int q = 0; q < cfg->numBCStates; ++q)
+    h->nonreflecting = h->nonreflecting || cfg->bcStates[q].isNonreflecting != 0;
   h->neq = h->ns + 4 + h->nt;
   h->jac = cfg->isBlockMatrix ? kJacBlock
                               : (cfg->invFluxJac == AITHER_JAC_APPROX_ROE ? kJacRoe : kJacScalar);
@@ -950,8 +970,11 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   }
   {
     const char *tv = getenv("AITHER_B200_KEEP_TIME_N");  // A/B switch: always store / read U^n
+    bool nonreflecting = false;  // reads U^n in the boundary-adjacent cells
+    for (int q = 0; q < cfg->numBCStates; ++q)
+      nonreflecting = nonreflecting || cfg->bcStates[q].isNonreflecting != 0;
     p.timeTermsVanish = !cfg->isMultilevelTime && cfg->nonlinearIterations <= 1 &&
-                        !(tv != nullptr && std::string(tv) == "1");
+                        !(tv != nullptr && std::string(tv) == "1") && !nonreflecting;
   }
   p.viscRecon = cfg->viscRecon;
   p.viscCFLCoeff = cfg->viscousCFLCoeff;
@@ -1039,7 +1062,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
-                        (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) ? 9 : 0));
+                        (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) ? 9 : 0)) +
+                        (h->nonreflecting ? 12 : 0);
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
     CKC(cudaMalloc(&hb.alloc, hb.allocBytes));
@@ -1070,6 +1094,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
     }
     if (h->nt == 0 && cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) b.velGrad = take(9);
+    if (h->nonreflecting) {
+      b.pressGrad = take(3);
+      if (h->nt == 0 && b.velGrad == nullptr) b.velGrad = take(9);
+    }
     if (h->nt > 0) {
       b.eddyVisc = take(1);
       b.f1 = take(1);
@@ -1207,6 +1235,10 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     }
     hb.nBcSurfs = static_cast<int>(sd.size());
     hb.bcThreads = off;
+    if (h->nonreflecting && !sd.empty()) {
+      CKC(cudaMalloc(&hb.dPatchMach, sizeof(double) * 2 * sd.size()));
+      CKC(cudaMemset(hb.dPatchMach, 0, sizeof(double) * 2 * sd.size()));
+    }
     {
       // wall-law walls: one record per boundary face of the block (walllaw.cuh)
       bool wallLaw = false;

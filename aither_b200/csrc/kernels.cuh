@@ -106,9 +106,66 @@ struct SurfDev {
   long long faceOffset;  // prefix sum of faces * layers over the surfaces of the block
 };
 
+// average and maximum outward Mach number of the boundary-adjacent cells of every non-reflecting
+// inlet / outlet patch (ref: src/procBlock.cpp:6235-6261): one thread block per surface,
+// fixed-order tree reduction (run-to-run identical); out[2 s] = average, out[2 s + 1] = maximum
+template <int NS, int NT>
+__global__ void __launch_bounds__(256) PatchMachKernel(BlockDev b, Params p,
+                                                       const SurfDev *__restrict__ surfs,
+                                                       const aither_bc_state *__restrict__ bcs,
+                                                       double *__restrict__ out) {
+  using E = Eq<NS, NT>;
+  const SurfDev sf = surfs[blockIdx.x];
+  if (!(sf.type == AITHER_BC_INLET || sf.type == AITHER_BC_PRESSURE_OUTLET) ||
+      !bcs[sf.bcIndex].isNonreflecting)
+    return;
+  const int d3 = (sf.surfType - 1) / 2;
+  const int d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+  const int n1 = sf.hi[d1] - sf.lo[d1], n2 = sf.hi[d2] - sf.lo[d2];
+  const int r3 = sf.lo[d3];
+  const bool isLower = sf.surfType % 2 == 1;
+  const int aCell = isLower ? r3 : r3 - 1;
+  double sum = 0.0, mx = -1.7976931348623157e308;
+  for (int t = threadIdx.x; t < n1 * n2; t += blockDim.x) {
+    int c[3];
+    c[d1] = sf.lo[d1] + t % n1;
+    c[d2] = sf.lo[d2] + t / n1;
+    c[d3] = aCell;
+    double s[E::neq];
+    LoadCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), s);
+    c[d3] = r3;
+    const long long fidx = CellIdx(b, c[0], c[1], c[2]);
+    double vn = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double a = __ldg(b.fA[d3] + q * b.fs + fidx);
+      vn += s[E::imx + q] * (isLower ? -1.0 * a : a);
+    }
+    const double mach = vn / SoS<NS>(p.gas, s);
+    sum += mach;
+    mx = fmax(mx, mach);
+  }
+  __shared__ double ssum[256], smax[256];
+  ssum[threadIdx.x] = sum;
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + w];
+      smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + w]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = ssum[0] / static_cast<double>(n1 * n2);
+    out[2 * blockIdx.x + 1] = smax[0];
+  }
+}
+
 template <int NS, int NT>
 __global__ void BcKernel(BlockDev b, Params p, const SurfDev *__restrict__ surfs, int nsurf,
-                         const aither_bc_state *__restrict__ bcs, long long total) {
+                         const aither_bc_state *__restrict__ bcs, long long total,
+                         const double *__restrict__ patchMach = nullptr) {
   using E = Eq<NS, NT>;
   const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
@@ -148,8 +205,29 @@ __global__ void BcKernel(BlockDev b, Params p, const SurfDev *__restrict__ surfs
   const long long fidx = CellIdx(b, c[0], c[1], c[2]);
 #pragma unroll
   for (int q = 0; q < 3; ++q) area[q] = __ldg(b.fA[d3] + q * b.fs + fidx);
-  GhostState<NS, NT>(p.gas, interior, bcType, area, sf.surfType, bcs[sf.bcIndex], layer, ghost,
-                     &p.tr);
+  if (patchMach != nullptr && (bcType == AITHER_BC_INLET || bcType == AITHER_BC_PRESSURE_OUTLET) &&
+      bcs[sf.bcIndex].isNonreflecting) {
+    // state at time n, time step and gradients of the boundary-adjacent cell as the previous
+    // evaluation left them (ref: src/procBlock.cpp:2506-2517)
+    BcExtra ex;
+    c[d3] = aCell;
+    const long long aidx = CellIdx(b, c[0], c[1], c[2]);
+    ex.dt = b.dt[aidx];
+    double cn[E::neq];
+    LoadCell<E::neq>(b.consN, b.fs, aidx, cn);
+    ConsToPrim<NS, NT>(p.gas, cn, ex.stateN);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) ex.pressGrad[q] = b.pressGrad[q * b.fs + aidx];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) ex.velGrad[q] = b.velGrad[q * b.fs + aidx];
+    ex.avgMach = patchMach[2 * s];
+    ex.maxMach = patchMach[2 * s + 1];
+    GhostState<NS, NT>(p.gas, interior, bcType, area, sf.surfType, bcs[sf.bcIndex], layer, ghost,
+                       &p.tr, &ex);
+  } else {
+    GhostState<NS, NT>(p.gas, interior, bcType, area, sf.surfType, bcs[sf.bcIndex], layer, ghost,
+                       &p.tr);
+  }
   c[d3] = gCell;
   StoreCell<E::neq>(b.state, b.fs, CellIdx(b, c[0], c[1], c[2]), ghost);
 }

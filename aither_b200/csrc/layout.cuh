@@ -52,6 +52,8 @@ struct BlockDev {
   double *velGrad;      // 9   velGrad[3 r + c] = d u_c / d x_r
   double *tkeGrad;      // 3
   double *omegaGrad;    // 3
+  // runs with non-reflecting BCs only (else null): cell average of the six face pressure gradients
+  double *pressGrad;    // 3
   // wall-law runs only (else null): kWallVarsStride doubles per boundary face of the block
   // (walllaw.cuh), face index = SurfDev::faceOffset / g + d1 + n1 * d2
   double *wallVars;

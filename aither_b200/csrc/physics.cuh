@@ -1053,10 +1053,19 @@ AITHER_HD void ApplyFarfieldTurb(const Gas &g, const Transport *tr, double *s, d
   for (int t = 0; t < NT; ++t) s[E::it + t] = fmax(s[E::it + t], kTurbMin);
 }
 
+// what a non-reflecting inlet / pressure outlet reads besides the interior state (the implicit
+// integrators' extra GetGhostState arguments; ref: src/procBlock.cpp:2506-2522, :6235-6285): time
+// step, state at time n and the gradients the previous evaluation left in the boundary-adjacent
+// cell, average / maximum outward Mach number of the surface patch
+struct BcExtra {
+  double dt, stateN[AITHER_MAX_SPECIES + 4 + 2], pressGrad[3], velGrad[9], avgMach, maxMach;
+};
+
 template <int NS, int NT>
 AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
                           const double *areaVec, int surf, const aither_bc_state &bc, int layer,
-                          double *ghost, const Transport *tr = nullptr) {
+                          double *ghost, const Transport *tr = nullptr,
+                          const BcExtra *ex = nullptr) {
   using E = Eq<NS, NT>;
 #pragma unroll
   for (int e = 0; e < E::neq; ++e) ghost[e] = interior[e];
@@ -1090,14 +1099,36 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
                    vd2 = fs[E::imz] - interior[E::imz];
       ghost[E::ie] = 0.5 * (fs[E::ie] + interior[E::ie] -
                             rhoSoSInt * (nA[0] * vd0 + nA[1] * vd1 + nA[2] * vd2));
-      const double deltaPressure = fs[E::ie] - ghost[E::ie];
       const double fsRho = SpeciesSum<NS>(fs);
-      const double rho = fsRho - deltaPressure / (SoSInt * SoSInt);
+      if (isInlet && bc.isNonreflecting && ex != nullptr) {
+        // LODI relaxation of density and velocity towards the boundary state (ref: :435-466)
+        const double *sN = ex->stateN;
+        constexpr double sigma = 0.25;
+        const double dt = ex->dt;
+        const double rhoN = SpeciesSum<NS>(sN);
+        const double sosN = SoS<NS>(g, sN);
+        const double rhoSoSN = rhoN * sosN;
+        const double deltaPressure = ghost[E::ie] - sN[E::ie];
+        const double alpha = sigma * sosN / bc.lengthScale;
+        const double rhoNp1 =
+            (rhoN + dt * alpha * fsRho + deltaPressure / (sosN * sosN)) / (1.0 + dt * alpha);
 #pragma unroll
-      for (int q = 0; q < NS; ++q) ghost[q] = rho * (fs[q] / fsRho);
-      ghost[E::imx] = fs[E::imx] - nA[0] * deltaPressure / rhoSoSInt;
-      ghost[E::imy] = fs[E::imy] - nA[1] * deltaPressure / rhoSoSInt;
-      ghost[E::imz] = fs[E::imz] - nA[2] * deltaPressure / rhoSoSInt;
+        for (int q = 0; q < NS; ++q) ghost[q] = rhoNp1 * (fs[q] / fsRho);
+        const double k = alpha * (1.0 - ex->maxMach * ex->maxMach);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          ghost[E::imx + d] = (sN[E::imx + d] + dt * k * fs[E::imx + d] -
+                               nA[d] * deltaPressure / rhoSoSN) /
+                              (1.0 + dt * k);
+      } else {
+        const double deltaPressure = fs[E::ie] - ghost[E::ie];
+        const double rho = fsRho - deltaPressure / (SoSInt * SoSInt);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) ghost[q] = rho * (fs[q] / fsRho);
+        ghost[E::imx] = fs[E::imx] - nA[0] * deltaPressure / rhoSoSInt;
+        ghost[E::imy] = fs[E::imy] - nA[1] * deltaPressure / rhoSoSInt;
+        ghost[E::imz] = fs[E::imz] - nA[2] * deltaPressure / rhoSoSInt;
+      }
       ApplyFarfieldTurb<NS, NT>(g, tr, ghost, bc.velocity[0], bc.velocity[1], bc.velocity[2], bc);
     } else {  // subsonic outflow
       const double intRho = SpeciesSum<NS>(interior);
@@ -1163,11 +1194,63 @@ AITHER_HD void GhostState(const Gas &g, const double *interior, int bcType,
       ExtrapolateHoldMixture<NS, NT>(ghost, static_cast<double>(layer), interior, ghost);
       ApplyFarfieldTurb<NS, NT>(g, tr, ghost, ghost[E::imx], ghost[E::imy], ghost[E::imz], bc);
     }
-  } else if (bcType == AITHER_BC_PRESSURE_OUTLET) {  // ref: :604-664 (reflecting form)
+  } else if (bcType == AITHER_BC_PRESSURE_OUTLET) {  // ref: :604-664
     const double SoSInt = SoS<NS>(g, interior);
     const double intRho = SpeciesSum<NS>(interior);
     const double rhoSoSInt = intRho * SoSInt;
     ghost[E::ie] = bc.pressure;
+    if (bc.isNonreflecting && ex != nullptr) {
+      // LODI relaxation of the pressure with transverse terms (ref: :614-643)
+      const double *sN = ex->stateN;
+      const double dt = ex->dt;
+      const double deltaVel = (interior[E::imx] - sN[E::imx]) * nA[0] +
+                              (interior[E::imy] - sN[E::imy]) * nA[1] +
+                              (interior[E::imz] - sN[E::imz]) * nA[2];
+      constexpr double sigma = 0.25;
+      const double rhoN = SpeciesSum<NS>(sN);
+      const double sosN = SoS<NS>(g, sN);
+      const double rhoSoSN = rhoN * sosN;
+      const double k = sigma * sosN * (1.0 - ex->maxMach * ex->maxMach) / bc.lengthScale;
+      const double beta = ex->avgMach;
+      const double pgn = ex->pressGrad[0] * nA[0] + ex->pressGrad[1] * nA[1] + ex->pressGrad[2] * nA[2];
+      const double vnN = sN[E::imx] * nA[0] + sN[E::imy] * nA[1] + sN[E::imz] * nA[2];
+      double pGradT[3], velT[3], vgT[9], dVelN[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        pGradT[d] = ex->pressGrad[d] - pgn * nA[d];
+        velT[d] = sN[E::imx + d] - vnN * nA[d];
+      }
+      // tensor::RemoveComponent (include/tensor.hpp:371-379): every row loses its normal part
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double *row = ex->velGrad + 3 * r;
+        const double rn = row[0] * nA[0] + row[1] * nA[1] + row[2] * nA[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vgT[3 * r + c] = row[c] - rn * nA[c];
+      }
+      // tensor::LinearCombination (:384-389): rows scaled by the normal and summed
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double comb = vgT[c] * nA[0];
+        comb += vgT[3 + c] * nA[1];
+        comb += vgT[6 + c] * nA[2];
+        dVelN[c] = comb;
+      }
+      double vgSum = 0.0;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) vgSum += vgT[q];
+      double dnSum = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dnSum += dVelN[c];
+      const double dVelT_dTrans = vgSum - dnSum;
+      const double gam = Gamma<NS>(g, sN);
+      const double dotT = velT[0] * (pGradT[0] - rhoSoSN * dVelN[0]) +
+                          velT[1] * (pGradT[1] - rhoSoSN * dVelN[1]) +
+                          velT[2] * (pGradT[2] - rhoSoSN * dVelN[2]);
+      const double trans = -0.5 * (dotT + gam * sN[E::ie] * dVelT_dTrans);
+      ghost[E::ie] = (sN[E::ie] + rhoSoSN * deltaVel + dt * k * bc.pressure - dt * beta * trans) /
+                     (1.0 + dt * k);
+    }
     const double deltaPressure = interior[E::ie] - ghost[E::ie];
     const double rho = intRho - deltaPressure / (SoSInt * SoSInt);
 #pragma unroll

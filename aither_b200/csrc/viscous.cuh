@@ -793,6 +793,111 @@ __device__ __forceinline__ void RansFace(const BlockDev &b, const Params &p, lon
   }
 }
 
+// ---- cell averages of the face pressure (and velocity) gradients for the non-reflecting BCs ----
+// The reference's viscous flux loops leave pressureGrad_ / velocityGrad_ behind as 1/6 of the six
+// face gradients of every cell (src/procBlock.cpp:1396-1452), and the non-reflecting inlet /
+// outlet of the NEXT iteration reads them in the boundary-adjacent cells (:2513-2514). Runs
+// without such a BC never launch this kernel. Same Green-Gauss control volume and summation
+// order as RansFace; `withVel`: also the velocity gradient (the laminar scalar path does not
+// produce it otherwise).
+template <int D>
+__device__ __forceinline__ void FaceControlVolume(const BlockDev &b, long long idx, double al[3][3],
+                                                  double au[3][3], double *invVol) {
+  const long long sd = Stride(b, D);
+  const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double a0[3], a1[3];
+    if (q == D) {
+      AreaVec(b, D, idx, a0);
+      AreaVec(b, D, idx + sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, D, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    } else {
+      AreaVec(b, q, idx + st[q], a0);
+      AreaVec(b, q, idx + st[q] - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) au[q][c] = 0.5 * (a0[c] + a1[c]);
+      AreaVec(b, q, idx, a0);
+      AreaVec(b, q, idx - sd, a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) al[q][c] = 0.5 * (a0[c] + a1[c]);
+    }
+  }
+  *invVol = 1.0 / (0.5 * (__ldg(b.vol + idx - sd) + __ldg(b.vol + idx)));
+}
+template <int D>
+__device__ __forceinline__ void FaceGreenGauss(const BlockDev &b, const double *f, long long idx,
+                                               const double al[3][3], const double au[3][3],
+                                               double invVol, double *g3) {
+  const long long sd = Stride(b, D);
+  const long long st[3] = {1LL, static_cast<long long>(b.sj), b.sk};
+  const double lo = f[idx - sd], hi = f[idx];
+  double vl[3], vu[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (q == D) {
+      vl[q] = lo;
+      vu[q] = hi;
+    } else {
+      vu[q] = 0.25 * (lo + hi + f[idx + st[q]] + f[idx + st[q] - sd]);
+      vl[q] = 0.25 * (lo + hi + f[idx - st[q]] + f[idx - st[q] - sd]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double t = vu[0] * au[0][r] - vl[0] * al[0][r] + vu[1] * au[1][r] - vl[1] * al[1][r] +
+                     vu[2] * au[2][r] - vl[2] * al[2][r];
+    g3[r] = t * invVol;
+  }
+}
+template <int NS, int D>
+__device__ __forceinline__ void CellGradDir(const BlockDev &b, long long idx, bool withVel,
+                                            double *pg, double *vg) {
+  constexpr double sixth = 1.0 / 6.0;
+  const long long sd = Stride(b, D);
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {  // lower face, then upper face (reference order)
+    const long long fidx = idx + side * sd;
+    double al[3][3], au[3][3], invVol, g3[3];
+    FaceControlVolume<D>(b, fidx, al, au, &invVol);
+    FaceGreenGauss<D>(b, b.state + (NS + 3) * b.fs, fidx, al, au, invVol, g3);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) pg[r] += sixth * g3[r];
+    if (withVel) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        FaceGreenGauss<D>(b, b.state + (NS + c) * b.fs, fidx, al, au, invVol, g3);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) vg[3 * r + c] += sixth * g3[r];
+      }
+    }
+  }
+}
+template <int NS, int NT>
+__global__ void __launch_bounds__(128) CellGradKernel(BlockDev b, int withVel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double pg[3] = {0.0, 0.0, 0.0}, vg[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) vg[q] = 0.0;
+  CellGradDir<NS, 0>(b, idx, withVel != 0, pg, vg);
+  CellGradDir<NS, 1>(b, idx, withVel != 0, pg, vg);
+  CellGradDir<NS, 2>(b, idx, withVel != 0, pg, vg);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) b.pressGrad[q * b.fs + idx] = pg[q];
+  if (withVel) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) b.velGrad[q * b.fs + idx] = vg[q];
+  }
+}
+
 template <int NS, int NT>
 struct RansAcc {
   double r[NS + 4 + NT];

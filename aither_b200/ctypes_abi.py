@@ -50,6 +50,7 @@ class BCState(C.Structure):
         ("isIsothermal", C.c_int), ("isConstantHeatFlux", C.c_int),
         ("turbulenceIntensity", C.c_double), ("eddyViscosityRatio", C.c_double),
         ("isWallLaw", C.c_int), ("vonKarmen", C.c_double), ("wallConstant", C.c_double),
+        ("isNonreflecting", C.c_int), ("lengthScale", C.c_double),
     ]
 
 

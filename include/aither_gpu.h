@@ -81,6 +81,9 @@ typedef struct aither_bc_state {
   int isWallLaw;                 /* viscousWall(wallTreatment=wallLaw): include/inputStates.hpp:343-369 */
   double vonKarmen;              /* 0.41 unless given */
   double wallConstant;           /* 5.5 unless given */
+  int isNonreflecting;           /* inlet / pressureOutlet(nonreflecting=true): LODI relaxation,
+                                    src/ghostStates.cpp:435-466, :614-643 */
+  double lengthScale;            /* its relaxation length */
 } aither_bc_state;
 
 /* POD snapshot of the reference's `input` + `physics` objects: only what the

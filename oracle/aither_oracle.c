@@ -6,6 +6,7 @@
  */
 #include "aither_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,6 +40,7 @@ typedef struct {
   double *eddyVisc, *f1, *f2; /* padded; ghosts only across connections */
   double *velGrad;            /* padded, 9: velGrad(r,c) = d u_c / d x_r */
   double *tkeGrad, *omegaGrad; /* ni nj nk 3 */
+  double *pressGrad;           /* ni nj nk 3: cell average of the face pressure gradients */
   const double *vol, *fAI, *fAJ, *fAK, *center, *cwI, *cwJ, *cwK, *wallDist;
   int *order; /* hyperplane ordering: 3 ints per cell */
   /* wallData_: one record per face of every viscous-wall surface (NULL for
@@ -606,6 +608,14 @@ static void apply_farfield_turb(const orc_level *h, double *s, const double vel[
   for (int tt = 0; tt < h->nt; ++tt)
     s[it + tt] = s[it + tt] > 1.0e-20 ? s[it + tt] : 1.0e-20;
 }
+/* what the implicit time integrators hand to GetGhostState besides the interior state
+ * (ref: src/procBlock.cpp:2506-2522, :6272-6285): time step, state at time n and gradients of
+ * the boundary-adjacent cell, average / maximum normal Mach number of the surface patch. Set by
+ * assign_inviscid_ghosts around its ghost_state calls; read by the non-reflecting branches. */
+typedef struct {
+  double dt, stateN[16], pressGrad[3], velGrad[9], avgMach, maxMach;
+} orc_bc_extra;
+static const orc_bc_extra *g_bc_extra = NULL;
 static void wall_law_eval(const orc_level *h, const aither_bc_state *bc, int mode,
                           const double *state, double wallDist, const double area[3],
                           int isLower, orc_wall_vars *wv);
@@ -751,7 +761,7 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
       if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
                                     bc->eddyViscosityRatio);
     }
-  } else if (bcType == AITHER_BC_INLET) { /* ref: :391-484, reflecting */
+  } else if (bcType == AITHER_BC_INLET) { /* ref: :391-484 */
     const aither_bc_state *bc = bc_data(h, tag);
     double freeState[MAXEQ];
     for (int e = 0; e < neq; ++e) freeState[e] = 0.0;
@@ -777,14 +787,35 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
       ghost[ie] = 0.5 * (freeState[ie] + interior[ie] -
                          rhoSoSInt * (nA[0] * vd[0] + nA[1] * vd[1] +
                                       nA[2] * vd[2]));
-      const double deltaPressure = freeState[ie] - ghost[ie];
-      const double rho = rho_of(h, freeState) - deltaPressure / (SoSInt * SoSInt);
       double fmf[AITHER_MAX_SPECIES];
       mass_fractions(h, freeState, fmf);
+      if (bc->isNonreflecting && g_bc_extra) { /* LODI relaxation; ref: :435-466 */
+        const orc_bc_extra *ex = g_bc_extra;
+        const double *stateN = ex->stateN;
+        const double sigma = 0.25, dt = ex->dt;
+        const double rhoN = rho_of(h, stateN);
+        const double sosN = sos_of(h, stateN);
+        const double rhoSoSN = rhoN * sosN;
+        const double deltaPressure = ghost[ie] - stateN[ie];
+        const double length = bc->lengthScale;
+        const double alpha = sigma * sosN / length;
+        const double rhoNp1 = (rhoN + dt * alpha * rho_of(h, freeState) +
+                               deltaPressure / (sosN * sosN)) /
+                              (1.0 + dt * alpha);
+        for (int ss = 0; ss < ns; ++ss) ghost[ss] = rhoNp1 * fmf[ss];
+        const double k = alpha * (1.0 - ex->maxMach * ex->maxMach);
+        for (int dd = 0; dd < 3; ++dd)
+          ghost[imx + dd] = (stateN[imx + dd] + dt * k * freeState[imx + dd] -
+                             nA[dd] * deltaPressure / rhoSoSN) /
+                            (1.0 + dt * k);
+      } else {
+      const double deltaPressure = freeState[ie] - ghost[ie];
+      const double rho = rho_of(h, freeState) - deltaPressure / (SoSInt * SoSInt);
       for (int ss = 0; ss < ns; ++ss) ghost[ss] = rho * fmf[ss];
       ghost[imx] = freeState[imx] - nA[0] * deltaPressure / rhoSoSInt;
       ghost[imy] = freeState[imy] - nA[1] * deltaPressure / rhoSoSInt;
       ghost[imz] = freeState[imz] - nA[2] * deltaPressure / rhoSoSInt;
+      }
       if (rans) apply_farfield_turb(h, ghost, bc->velocity, bc->turbulenceIntensity,
                                     bc->eddyViscosityRatio);
       double tmp[MAXEQ];
@@ -861,6 +892,55 @@ static void ghost_state(const orc_level *h, const double *interior, int bcType,
     const double SoSInt = sos_of(h, interior);
     const double rhoSoSInt = rho_of(h, interior) * SoSInt;
     ghost[ie] = pb;
+    if (bc->isNonreflecting && g_bc_extra) { /* LODI with transverse terms; ref: :614-643 */
+      const orc_bc_extra *ex = g_bc_extra;
+      const double *stateN = ex->stateN;
+      const double dt = ex->dt;
+      const double deltaVel = (interior[imx] - stateN[imx]) * nA[0] +
+                              (interior[imy] - stateN[imy]) * nA[1] +
+                              (interior[imz] - stateN[imz]) * nA[2];
+      const double sigma = 0.25;
+      const double rhoN = rho_of(h, stateN);
+      const double sosN = sos_of(h, stateN);
+      const double rhoSoSN = rhoN * sosN;
+      const double length = bc->lengthScale;
+      const double k = sigma * sosN * (1.0 - ex->maxMach * ex->maxMach) / length;
+      const double beta = ex->avgMach;
+      const double pgn = ex->pressGrad[0] * nA[0] + ex->pressGrad[1] * nA[1] +
+                         ex->pressGrad[2] * nA[2];
+      const double vnN = stateN[imx] * nA[0] + stateN[imy] * nA[1] + stateN[imz] * nA[2];
+      double pGradT[3], velT[3], vgT[9], dVelN[3];
+      for (int dd = 0; dd < 3; ++dd) {
+        pGradT[dd] = ex->pressGrad[dd] - pgn * nA[dd];
+        velT[dd] = stateN[imx + dd] - vnN * nA[dd];
+      }
+      /* tensor::RemoveComponent: every row loses its component along the normal
+       * (include/tensor.hpp:371-379) */
+      for (int r = 0; r < 3; ++r) {
+        const double *row = ex->velGrad + 3 * r;
+        const double rn = row[0] * nA[0] + row[1] * nA[1] + row[2] * nA[2];
+        for (int c = 0; c < 3; ++c) vgT[3 * r + c] = row[c] - rn * nA[c];
+      }
+      /* tensor::LinearCombination: rows scaled by the normal and summed (:384-389) */
+      for (int c = 0; c < 3; ++c) {
+        double comb = vgT[c] * nA[0];
+        comb += vgT[3 + c] * nA[1];
+        comb += vgT[6 + c] * nA[2];
+        dVelN[c] = comb;
+      }
+      double vgSum = 0.0;
+      for (int q = 0; q < 9; ++q) vgSum += vgT[q];
+      double dnSum = 0.0;
+      for (int c = 0; c < 3; ++c) dnSum += dVelN[c];
+      const double dVelT_dTrans = vgSum - dnSum;
+      const double gam = gamma_of(h, stateN);
+      const double dotT = velT[0] * (pGradT[0] - rhoSoSN * dVelN[0]) +
+                          velT[1] * (pGradT[1] - rhoSoSN * dVelN[1]) +
+                          velT[2] * (pGradT[2] - rhoSoSN * dVelN[2]);
+      const double trans = -0.5 * (dotT + gam * stateN[ie] * dVelT_dTrans);
+      ghost[ie] = (stateN[ie] + rhoSoSN * deltaVel + dt * k * pb - dt * beta * trans) /
+                  (1.0 + dt * k);
+    }
     const double deltaPressure = interior[ie] - ghost[ie];
     const double rho = rho_of(h, interior) - deltaPressure / (SoSInt * SoSInt);
     double imf[AITHER_MAX_SPECIES];
@@ -927,6 +1007,38 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
       int hi[3] = {sf->imax, sf->jmax, sf->kmax};
       lo[d3] = 0;
       hi[d3] = 1;
+      /* non-reflecting inlet / outlet: average and maximum outward Mach number of the
+       * boundary-adjacent cells of this patch (ref: src/procBlock.cpp:6235-6261) */
+      orc_bc_extra ex;
+      memset(&ex, 0, sizeof(ex));
+      const aither_bc_state *sbc =
+          (bcType == AITHER_BC_PRESSURE_OUTLET || bcType == AITHER_BC_INLET) ? bc_data(h, sf->tag)
+                                                                               : NULL;
+      const int nonRefl = sbc && sbc->isNonreflecting;
+      if (nonRefl) {
+        double avg = 0.0, mx = -DBL_MAX;
+        long cnt = 0;
+        for (int kk = lo[2]; kk < hi[2]; ++kk)
+          for (int jj = lo[1]; jj < hi[1]; ++jj)
+            for (int ii = lo[0]; ii < hi[0]; ++ii) {
+              int ca[3] = {ii, jj, kk}, cf[3] = {ii, jj, kk};
+              ca[d3] = src;
+              cf[d3] = bnd;
+              const double *fa =
+                  d3 == 0 ? b->fAI + 4 * fidxI(b, cf[0], cf[1], cf[2])
+                          : (d3 == 1 ? b->fAJ + 4 * fidxJ(b, cf[0], cf[1], cf[2])
+                                     : b->fAK + 4 * fidxK(b, cf[0], cf[1], cf[2]));
+              const double sg = st % 2 == 1 ? -1.0 : 1.0;
+              const double *bs = b->state + neq * cidx(b, ca[0], ca[1], ca[2]);
+              const double mach = (bs[h->ns] * (sg * fa[0]) + bs[h->ns + 1] * (sg * fa[1]) +
+                                   bs[h->ns + 2] * (sg * fa[2])) / sos_of(h, bs);
+              mx = mach > mx ? mach : mx;
+              avg += mach;
+              ++cnt;
+            }
+        ex.avgMach = avg / (double)cnt;
+        ex.maxMach = mx;
+      }
       for (int kk = lo[2]; kk < hi[2]; ++kk) {
         for (int jj = lo[1]; jj < hi[1]; ++jj) {
           for (int ii = lo[0]; ii < hi[0]; ++ii) {
@@ -934,6 +1046,17 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
             ci[d3] = src;
             cg[d3] = gCell;
             cf[d3] = bnd;
+            if (nonRefl) { /* ref: src/procBlock.cpp:2506-2517 */
+              int ca[3] = {ii, jj, kk};
+              ca[d3] = aCell;
+              const long pa = pidx(b, ca[0], ca[1], ca[2]);
+              ex.dt = b->dt[pa];
+              cons_to_prim(h, b->consN + neq * pa, ex.stateN);
+              for (int q = 0; q < 3; ++q) ex.pressGrad[q] = b->pressGrad[3 * pa + q];
+              for (int q = 0; q < 9; ++q)
+                ex.velGrad[q] = b->velGrad[9 * cidx(b, ca[0], ca[1], ca[2]) + q];
+              g_bc_extra = &ex;
+            }
             const double *fa =
                 d3 == 0 ? b->fAI + 4 * fidxI(b, cf[0], cf[1], cf[2])
                         : (d3 == 1 ? b->fAJ + 4 * fidxJ(b, cf[0], cf[1], cf[2])
@@ -941,6 +1064,7 @@ static void assign_inviscid_ghosts(orc_level *h, orc_block *b) {
             double ghost[MAXEQ];
             ghost_state(h, b->state + neq * cidx(b, ci[0], ci[1], ci[2]), bcType,
                         fa, st, sf->tag, layer, 0.0, 0.0, ghost, NULL);
+            g_bc_extra = NULL;
             memcpy(b->state + neq * cidx(b, cg[0], cg[1], cg[2]), ghost,
                    sizeof(double) * neq);
           }
@@ -1316,6 +1440,7 @@ static const double *farea(const orc_block *b, int d, int i, int j, int k) {
 /* Green-Gauss gradients of velocity and temperature on the control volume
  * centred on face (i,j,k) of direction d; ref: src/procBlock.cpp:5173-5303
  * (I), :5378-5508 (J), :5584-5714 (K); src/utility.cpp:59-175 */
+static double g_face_press_grad[3]; /* pressure gradient of the last face_gradients call */
 static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
                            int j, int k, double vg[9], double tg[3],
                            double kg[3], double wg[3], double (*mg)[3]) {
@@ -1383,6 +1508,31 @@ static void face_gradients(const orc_level *h, const orc_block *b, int d, int i,
                      vu[1][3] * au[1][r] - vl[1][3] * al[1][r] +
                      vu[2][3] * au[2][r] - vl[2][3] * al[2][r];
     tg[r] = t * invVol;
+  }
+  { /* pressure gradient of the same control volume (ref: src/procBlock.cpp:5319-5331;
+     * kept for the non-reflecting boundary conditions) */
+    double pl[3], pu[3];
+#define PV(cell) (b->state[neq * (cell) + ns + 3])
+    for (int q = 0; q < 3; ++q) {
+      if (q == d) {
+        pl[q] = PV(cLo);
+        pu[q] = PV(cHi);
+      } else {
+        const int *eq = e3[q];
+        const long up0 = cidx(b, i + eq[0], j + eq[1], k + eq[2]);
+        const long up1 = cidx(b, i + eq[0] - ed[0], j + eq[1] - ed[1], k + eq[2] - ed[2]);
+        const long lo0 = cidx(b, i - eq[0], j - eq[1], k - eq[2]);
+        const long lo1 = cidx(b, i - eq[0] - ed[0], j - eq[1] - ed[1], k - eq[2] - ed[2]);
+        pu[q] = 0.25 * (PV(cLo) + PV(cHi) + PV(up0) + PV(up1));
+        pl[q] = 0.25 * (PV(cLo) + PV(cHi) + PV(lo0) + PV(lo1));
+      }
+    }
+#undef PV
+    for (int r = 0; r < 3; ++r) {
+      const double t = pu[0] * au[0][r] - pl[0] * al[0][r] + pu[1] * au[1][r] - pl[1] * al[1][r] +
+                       pu[2] * au[2][r] - pl[2] * al[2][r];
+      g_face_press_grad[r] = t * invVol;
+    }
   }
   for (int c = 4; c < nval; ++c) {
     double *out = c == 4 ? kg : wg;
@@ -1806,6 +1956,7 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
         const int fi = d == 0 ? ii : (d == 1 ? jj : kk);
         double vg[9], tg[3], kg[3], wg[3], mg[AITHER_MAX_SPECIES][3];
         face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg, mg);
+        const double pg[3] = {g_face_press_grad[0], g_face_press_grad[1], g_face_press_grad[2]};
         double state[MAXEQ], mu, wDist = 0.0;
 #define CL(o) cidx(b, ii + (o)*di, jj + (o)*dj, kk + (o)*dk)
         double mut = 0.0, f1 = 0.0, f2 = 0.0, flux[MAXEQ];
@@ -1954,6 +2105,8 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           for (int e = 0; e < neq; ++e) r[e] -= flux[e] * fa[3];
           if (!rans)
             for (int q = 0; q < 9; ++q) b->velGrad[9 * CL(-1) + q] += sixth * vg[q];
+          for (int q = 0; q < 3; ++q)
+            b->pressGrad[3 * pidx(b, ii - di, jj - dj, kk - dk) + q] += sixth * pg[q];
           if (h->cfg.isBlockMatrix) { /* ref: src/procBlock.cpp:1420-1428 */
             double J[MAXJAC];
             approx_tsl_jacobian(h, state, mu, mut, f1, fa, proj_c2c_dist(b, d, ii, jj, kk), 1,
@@ -1978,6 +2131,7 @@ static void calc_visc_flux(orc_level *h, orc_block *b, int d) {
           for (int e = 0; e < neq; ++e) r[e] += flux[e] * fa[3];
           if (!rans)
             for (int q = 0; q < 9; ++q) b->velGrad[9 * CL(0) + q] += sixth * vg[q];
+          for (int q = 0; q < 3; ++q) b->pressGrad[3 * pidx(b, ii, jj, kk) + q] += sixth * pg[q];
           if (rans) {
             const long c = CL(0), pp = pidx(b, ii, jj, kk);
             for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
@@ -2260,6 +2414,7 @@ void orc_calc_residual(orc_level *h) {
     memset(b->residual, 0, sizeof(double) * nc * h->neq);
     memset(b->specRad, 0, sizeof(double) * nc * 2);
     if (h->cfg.isViscous) memset(b->velGrad, 0, sizeof(double) * np * 9);
+    memset(b->pressGrad, 0, sizeof(double) * nc * 3);
     if (is_rans(h)) { /* ResetGradients, ResetTurbVars; ref: src/procBlock.cpp:961-981 */
       memset(b->tkeGrad, 0, sizeof(double) * nc * 3);
       memset(b->omegaGrad, 0, sizeof(double) * nc * 3);
@@ -3052,6 +3207,7 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
     b->velGrad = (double *)calloc(np * 9, sizeof(double));
     b->tkeGrad = (double *)calloc(nc * 3, sizeof(double));
     b->omegaGrad = (double *)calloc(nc * 3, sizeof(double));
+    b->pressGrad = (double *)calloc(nc * 3, sizeof(double));
     b->vol = d->vol;
     b->fAI = d->fAreaI;
     b->fAJ = d->fAreaJ;
@@ -3096,7 +3252,7 @@ void orc_destroy(orc_level *h) {
     free(b->consN); free(b->consNm1); free(b->mresid); free(b->temperature);
     free(b->viscosity); free(b->order);
     free(b->eddyVisc); free(b->f1); free(b->f2); free(b->velGrad);
-    free(b->tkeGrad); free(b->omegaGrad);
+    free(b->tkeGrad); free(b->omegaGrad); free(b->pressGrad);
     if (b->wall) {
       for (int s = 0; s < b->nsurf; ++s) free(b->wall[s]);
       free(b->wall);
@@ -3230,6 +3386,26 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
 }
 
 /* transport of a mixture state (tests/test_physics_host.py): {viscosity, effective conductivity} */
+/* ghost state of a non-reflecting inlet / pressure outlet; extra = {dt, stateN[neq],
+ * pressGrad[3], velGrad[9], avgMach, maxMach} (tests/test_physics_host.py) */
+void orc_ghost_state_nonreflecting(const aither_cfg *cfg, const double *interior, int bcType,
+                                   const double areaUnit[3], int surfType, int tag, int layer,
+                                   const double *extra, double *ghost) {
+  orc_level h;
+  level_from_cfg(&h, cfg);
+  orc_bc_extra ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.dt = extra[0];
+  for (int e = 0; e < h.neq; ++e) ex.stateN[e] = extra[1 + e];
+  for (int q = 0; q < 3; ++q) ex.pressGrad[q] = extra[1 + h.neq + q];
+  for (int q = 0; q < 9; ++q) ex.velGrad[q] = extra[4 + h.neq + q];
+  ex.avgMach = extra[13 + h.neq];
+  ex.maxMach = extra[14 + h.neq];
+  g_bc_extra = &ex;
+  ghost_state(&h, interior, bcType, areaUnit, surfType, tag, layer, 0.0, 0.0, ghost, NULL);
+  g_bc_extra = NULL;
+}
+
 /* wallLaw::AdiabaticBCs (mode 0) / HeatFluxBCs (1) / IsothermalBCs (2) for the boundary state
  * `tag`; out = {yplus, tau x y z, heatFlux, viscosity, eddy viscosity, density, temperature,
  * tke, sdr} (tests/test_physics_host.py) */

@@ -77,6 +77,10 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
                           const double areaUnit[3], int surfType, int tag, int layer,
                           double wallDist, double nuW, double *ghost);
 
+void orc_ghost_state_nonreflecting(const aither_cfg *cfg, const double *interior, int bcType,
+                                   const double areaUnit[3], int surfType, int tag, int layer,
+                                   const double *extra, double *ghost);
+
 void orc_wall_law(const aither_cfg *cfg, int mode, int tag, const double *state,
                   double wallDist, const double area[3], int isLower, double out[11]);
 

@@ -187,6 +187,12 @@ CASES = {
                           edits={"initialConditions": "<icState(tag=-1; file=ic.dat)>"},
                           drop=("diagRaw@", "temperature@", "state@it0.start", "x0@",
                                 "velocityGrad@", "f2@")),
+    # reference regression case convectingVortex (regressionTests.py:498-514): laminar, BDF2 dual
+    # time stepping (10 nonlinear iterations per step), LU-SGS, periodic pair, non-reflecting
+    # inlet and pressure outlet (LODI relaxation with the state at time n, the time step, the
+    # pressure / velocity gradients of the previous evaluation and the patch Mach numbers)
+    "convectingVortex": dict(src="convectingVortex", iters=40, full=(0,), edits={}, fluids=("N2",),
+                             drop=("diagRaw@", "temperature@", "state@it0.start", "x0@")),
     # synthetic SST boxes (1 cm: y+ of the wall cells ~ 50) with the wall law on an isothermal
     # and on a constant-heat-flux wall (wallLaw::IsothermalBCs / HeatFluxBCs; the shipped case is
     # adiabatic), DPLUR and BLU-SGS

@@ -185,7 +185,9 @@ def check_history(make_level, d, n_iter, tol, name=None):
         worst = max(worst, err)
         assert err <= tol, "iteration %d: L2 rel err %.3e > %.1e\n%s\n%s" % (it, err, tol, l2,
                                                                             href[it])
-        assert abs(mr - mref[it]) <= max(tol, 1e-9) * abs(mref[it]), (it, mr, mref[it])
+        # (a matrix residual at rounding level -- converged dual time steps -- is noise)
+        assert abs(mr - mref[it]) <= max(tol, 1e-9) * abs(mref[it]) + 1e-12 * href[it].max(), \
+            (it, mr, mref[it])
     lvl.close()
     if name in REGRESSION_GOLDENS and n_iter >= REGRESSION_GOLDENS[name][0]:
         n, gold = REGRESSION_GOLDENS[name]

@@ -124,6 +124,19 @@ void hs_ghost_state_rans(const aither_cfg *c, const double *interior, int bcType
   const Transport tr = TransportFromCfg(c);
   GhostState<1, 2>(g, interior, bcType, area, surf, *Find(c, tag), layer, ghost, &tr);
 }
+void hs_ghost_state_nonreflecting(const aither_cfg *c, const double *interior, int bcType,
+                                  const double *area, int surf, int tag, int layer,
+                                  const double *extra, double *ghost) {
+  const Gas g = GasFromCfg(c);
+  BcExtra ex;
+  ex.dt = extra[0];
+  for (int e = 0; e < 5; ++e) ex.stateN[e] = extra[1 + e];
+  for (int q = 0; q < 3; ++q) ex.pressGrad[q] = extra[6 + q];
+  for (int q = 0; q < 9; ++q) ex.velGrad[q] = extra[9 + q];
+  ex.avgMach = extra[18];
+  ex.maxMach = extra[19];
+  GhostState<1, 0>(g, interior, bcType, area, surf, *Find(c, tag), layer, ghost, nullptr, &ex);
+}
 void hs_wall_law(const aither_cfg *c, int mode, int tag, const double *state, double wallDist,
                  const double *area, int isLower, double *out) {
   const Gas g = GasFromCfg(c);

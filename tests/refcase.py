@@ -79,7 +79,11 @@ def cfg_from_dump(d):
             isWallLaw=int(g(p + "isWallLaw")[0]) if ("cfg/" + p + "isWallLaw") in d else 0,
             vonKarmen=float(g(p + "vonKarmen")[0]) if ("cfg/" + p + "vonKarmen") in d else 0.41,
             wallConstant=float(g(p + "wallConstant")[0]) if ("cfg/" + p + "wallConstant") in d
-            else 5.5))
+            else 5.5,
+            isNonreflecting=int(g(p + "isNonreflecting")[0])
+            if ("cfg/" + p + "isNonreflecting") in d else 0,
+            lengthScale=float(g(p + "lengthScale")[0]) if ("cfg/" + p + "lengthScale") in d
+            else 0.0))
     return make_cfg(
         numSpecies=ns, numTurb=int(g("numTurb")[0]), numGhosts=int(g("numGhosts")[0]),
         isViscous=int(g("isViscous")[0]), isRANS=int(g("isRANS")[0]),

@@ -127,6 +127,17 @@ def test_shock_tube_bdf2_dual_time_matches_reference():
     assert gc.check_history(make_gpu_level, d, 200, 1e-9) <= 1e-9
 
 
+def test_convecting_vortex_nonreflecting_matches_reference():
+    """testCases/convectingVortex (regressionTests.py:498-514): laminar, BDF2 dual time stepping,
+    LU-SGS, periodic pair, non-reflecting inlet and pressure outlet -- the ghost-cell kernel reads
+    U^n, the time step and the pressure / velocity gradient cell averages of the previous
+    evaluation in the boundary-adjacent cells, and the patch Mach numbers. 4 time steps of 10
+    nonlinear iterations."""
+    d = gc.load("convectingVortex")
+    gc.check_phases(make_gpu_level, d, 0, TOL)
+    assert gc.check_history(make_gpu_level, d, 40, 1e-9) <= 1e-9
+
+
 def test_run_with_nonlinear_iterations_equals_iterate():
     """aither_gpu_run loops cfg.nonlinearIterations inside every time step."""
     import refcase

@@ -82,6 +82,19 @@ def test_oracle_wall_law():
     assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9, name="wallLaw") <= 1e-9
 
 
+def test_oracle_convecting_vortex_nonreflecting():
+    """testCases/convectingVortex (regressionTests.py:498-514): laminar, BDF2 dual time stepping
+    (10 nonlinear iterations per step), LU-SGS, periodic pair, non-reflecting `inlet` and
+    `pressureOutlet`: LODI relaxation towards the boundary state with the state at time n, the
+    time step and the pressure / velocity gradients of the boundary-adjacent cell from the
+    previous evaluation, and the average / maximum normal Mach number of the patch
+    (src/ghostStates.cpp:435-466, :614-643; src/procBlock.cpp:6235-6261). 4 time steps."""
+    d = gc.load("convectingVortex")
+    assert any(int(d["cfg/bc%d/isNonreflecting" % q][0]) for q in range(3))
+    gc.check_phases(oracle.OracleLevel, d, 0, TOL)
+    assert gc.check_history(oracle.OracleLevel, d, 40, 1e-9) <= 1e-9
+
+
 def test_oracle_periodic_connection():
     """A periodic pair (the block's own i-lo and i-hi faces, `periodic(startTag; endTag;
     translation)`, reference src/boundaryConditions.cpp:2224-2300): the block exchanges ghost layers

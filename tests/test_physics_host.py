@@ -289,6 +289,40 @@ def test_ghost_state_rans(hs, bc, tag):
                 assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a) + 1e-14 * np.abs(a[:5]).max()), (a, b)
 
 
+@pytest.mark.parametrize("bc,tag", [(abi.BC_INLET, 2), (abi.BC_PRESSURE_OUTLET, 3)])
+def test_ghost_state_nonreflecting(hs, bc, tag):
+    """non-reflecting inlet / pressure outlet (LODI relaxation with the state at time n, the time
+    step, pressure / velocity gradients and the patch Mach numbers): device point function vs
+    the oracle's restatement of src/ghostStates.cpp:435-466, :614-643, with the boundary states
+    of the reference's convectingVortex case."""
+    import goldencheck as gc
+    import refcase
+    cfg = refcase.cfg_from_dump(gc.load("convectingVortex"))
+    L = oracle.lib()
+    for f in (L.orc_ghost_state_nonreflecting, hs.hs_ghost_state_nonreflecting):
+        f.argtypes = [C.c_void_p, PD, C.c_int, PD, C.c_int, C.c_int, C.c_int, PD, PD]
+        f.restype = None
+    rng = np.random.default_rng(61)
+    for trial in range(300):
+        s, n = rand_state(rng, 0.3), unit(rng)
+        extra = np.empty(20)
+        extra[0] = 0.0 if trial % 5 == 0 else 10.0 ** rng.uniform(-4, 0)
+        extra[1:6] = s * (1.0 + 0.01 * rng.normal(size=5))
+        extra[6:9] = rng.normal(size=3)
+        extra[9:18] = rng.normal(size=9) * 5.0
+        extra[18], extra[19] = rng.uniform(0.0, 0.5), rng.uniform(0.3, 0.9)
+        for surf in (1, 4):
+            for layer in (1, 2):
+                a, b = np.empty(5), np.empty(5)
+                L.orc_ghost_state_nonreflecting(C.byref(cfg), ptr(s), bc, ptr(n), surf, tag, layer,
+                                                ptr(extra), ptr(a))
+                hs.hs_ghost_state_nonreflecting(C.byref(cfg), ptr(s), bc, ptr(n), surf, tag, layer,
+                                                ptr(extra), ptr(b))
+                if not np.isfinite(a).all():
+                    continue
+                assert np.all(np.abs(a - b) <= 1e-12 * np.abs(a) + 1e-13 * np.abs(a).max()), (a, b)
+
+
 @pytest.mark.parametrize("mode,fixture", [(0, "wallLaw"), (1, "box_walllaw_heatflux"),
                                           (2, "box_walllaw_isothermal")])
 def test_wall_law(hs, mode, fixture):
