@@ -150,6 +150,7 @@ struct aither_gpu {
   int jac = kJacScalar;            // JacKind of the implicit matrix
   bool consNStale = false;         // U^n not materialised (Params::timeTermsVanish)
   bool nonreflecting = false;      // some inlet / pressure outlet is non-reflecting
+  bool wallLaw = false;            // some viscous wall uses the wall law
   bool lusgsGraphs = true;         // AITHER_B200_LUSGS_GRAPH=0: plain launches (A/B)
   bool lusgsSplit = true;          // AITHER_B200_LUSGS_SPLIT=0: one thread per cell (A/B)
   bool stateMovedSinceStore = false;
@@ -303,13 +304,8 @@ bool Supported(const aither_cfg &c, std::string *why) {
   }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
   for (int q = 0; q < c.numBCStates; ++q) {
-    if (c.bcStates[q].isNonreflecting && !c.isViscous) {
-      *why = "non-reflecting boundary conditions are built for viscous runs (they read the "
-             "pressure / velocity gradients the viscous fluxes leave behind)";
-      return false;
-    }
-    if (c.bcStates[q].isWallLaw && !c.isRANS) {
-      *why = "the wall law (wallTreatment=wallLaw) is built for RANS runs";
+    if (c.bcStates[q].isWallLaw && c.isViscous && !c.isRANS && c.numSpecies > 1) {
+      *why = "the wall law in a laminar run is built for one species";
       return false;
     }
   }
@@ -414,9 +410,7 @@ void LaunchRansCell(const BlockDev &b, const Params &p, dim3 grid, cudaStream_t 
       RansCellKernel<NS, NT, true><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 0, surfs, nsurf);
     }
   } else {
-    if constexpr (NT > 0 || NS > 1) {
-      RansCellKernel<NS, NT, false><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1, surfs, nsurf);
-    }
+    RansCellKernel<NS, NT, false><<<grid, dim3(32, 4, 1), 0, stream>>>(b, p, 1, surfs, nsurf);
   }
 }
 
@@ -498,8 +492,9 @@ int PhaseBoundaryConditionsT(aither_gpu *h) {
   }
   CK(cudaGetLastError());
   if (Exchange(h, kHaloState)) return 1;
-  if (h->cfg.isViscous) {
-    // edge ghost cells: read by the viscous gradient stencils only (ref src/gridLevel.cpp:314-318)
+  if (h->cfg.isViscous || h->nonreflecting) {
+    // edge ghost cells: read by the gradient stencils only (viscous fluxes, or the gradient pass
+    // an Euler run makes for its non-reflecting BCs; ref src/gridLevel.cpp:314-318)
     for (auto &hb : h->blocks) {
       ScopedLaunch sl(h, kFamViscGhost);
       const int n = 4 * (hb.dev.ni + hb.dev.nj + hb.dev.nk);
@@ -524,7 +519,20 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
     }
   }
   CK(cudaGetLastError());
-  if (!h->cfg.isViscous) return 0;
+  if (!h->cfg.isViscous) {
+    // Euler run with a non-reflecting BC: the reference's gradient-only pass
+    // (CalcGradsI/J/K, src/procBlock.cpp:6138-6146, :5790-5945) leaves the same cell averages
+    if (h->nonreflecting) {
+      for (auto &hb : h->blocks) {
+        ScopedLaunch sl(h, kFamResidual);
+        const BlockDev &b = hb.dev;
+        const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
+        CellGradKernel<NS, NT><<<grid, dim3(32, 4, 1), 0, h->stream>>>(b, 1);
+      }
+      CK(cudaGetLastError());
+    }
+    return 0;
+  }
   // ref: src/procBlock.cpp:6125-6137
   for (auto &hb : h->blocks) {
     const BlockDev &b = hb.dev;
@@ -545,8 +553,8 @@ int PhaseResidualT(aither_gpu *h, int fusePrep, double cfl) {
       const dim3 grid((b.ni + 2 * b.g + 31) / 32, (b.nj + 2 * b.g + 7) / 8, b.nk + 2 * b.g);
       AuxKernel<NS, NT><<<grid, dim3(32, 8, 1), 0, h->stream>>>(b, h->params);
     }
-    if (NT > 0 || block || NS > 1) {
-      // RANS, multi-species and / or block matrix: viscous (+ turbulent) fluxes, cell averages, spectral radii,
+    if (NT > 0 || block || NS > 1 || b.wallVars != nullptr) {
+      // RANS, multi-species, block matrix and / or wall-law walls: viscous (+ turbulent) fluxes, cell averages, spectral radii,
       // source terms and the thin-shear-layer Jacobians, per cell
       ScopedLaunch sl(h, kFamViscFlux);
       const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk);
@@ -941,6 +949,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
   h->nt = cfg->numTurb;
   for (int q = 0; q < cfg->numBCStates; ++q)
     h->nonreflecting = h->nonreflecting || cfg->bcStates[q].isNonreflecting != 0;
+  for (int q = 0; q < cfg->numBCStates; ++q)
+    h->wallLaw = h->wallLaw || (cfg->bcStates[q].isWallLaw != 0 && cfg->isViscous);
   h->neq = h->ns + 4 + h->nt;
   h->jac = cfg->isBlockMatrix ? kJacBlock
                               : (cfg->invFluxJac == AITHER_JAC_APPROX_ROE ? kJacRoe : kJacScalar);
@@ -1062,7 +1072,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
     const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
-                        (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) ? 9 : 0)) +
+                        (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1 || h->wallLaw)) ? 9 : 0)) +
                         (h->nonreflecting ? 12 : 0);
     hb.allocBytes = static_cast<size_t>(nFields) * b.fs * sizeof(double);
     hb.nFields = nFields;
@@ -1093,7 +1103,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
     }
-    if (h->nt == 0 && cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1)) b.velGrad = take(9);
+    if (h->nt == 0 && cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1 || h->wallLaw))
+      b.velGrad = take(9);  // written by the per-cell viscous pass (RansCellKernel)
     if (h->nonreflecting) {
       b.pressGrad = take(3);
       if (h->nt == 0 && b.velGrad == nullptr) b.velGrad = take(9);
@@ -1320,7 +1331,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     std::vector<int> gpos;
     for (auto &hb : h->blocks) { devs.push_back(&hb.dev); gpos.push_back(hb.globalPos); }
     const char *he = getenv("AITHER_B200_HALO_EDGES");  // A/B switch: 1 = always the full plan
-    h->stateNeedsEdges = cfg->isViscous != 0 || (he != nullptr && std::string(he) == "1");
+    h->stateNeedsEdges = cfg->isViscous != 0 || h->nonreflecting ||
+                         (he != nullptr && std::string(he) == "1");
     if (HaloBuild(h->halo, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm) ||
         HaloBuild(h->haloFace, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm,
                   !(he != nullptr && std::string(he) == "1"))) {
@@ -1500,8 +1512,14 @@ static int FieldInfo(aither_gpu *h, int blk, int field, const double **ptr, int 
     case AITHER_FIELD_VISCOSITY:
       if (!b.viscosity) return Fail("viscosity is only stored for viscous runs");
       *ptr = b.viscosity; *nc = 1; *padded = true; break;
+    case AITHER_FIELD_PRESSURE_GRAD:
+      if (!b.pressGrad) return Fail("the pressure gradient is only kept for runs with non-reflecting BCs");
+      *ptr = b.pressGrad; *nc = 3; *padded = false; break;
+    case AITHER_FIELD_VELOCITY_GRAD:
+      if (!b.velGrad) return Fail("the velocity gradient is not kept by this configuration");
+      *ptr = b.velGrad; *nc = 9; *padded = true; break;
     case AITHER_FIELD_EDDY_VISCOSITY: case AITHER_FIELD_F1: case AITHER_FIELD_F2:
-    case AITHER_FIELD_VELOCITY_GRAD: case AITHER_FIELD_TKE_GRAD: case AITHER_FIELD_OMEGA_GRAD:
+    case AITHER_FIELD_TKE_GRAD: case AITHER_FIELD_OMEGA_GRAD:
       if (!b.eddyVisc) return Fail("turbulence fields are only stored for RANS runs");
       *padded = field != AITHER_FIELD_TKE_GRAD && field != AITHER_FIELD_OMEGA_GRAD;
       *nc = field == AITHER_FIELD_VELOCITY_GRAD ? 9 : (*padded ? 1 : 3);

@@ -46,8 +46,11 @@ def write_plot3d(path, blocks_nodes):
 def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="none",
              recon="thirdOrder", flux="roe", iterations=10, ic_file=None, viscous=False,
              visc_recon="central", wall=None, turb=None, jac="rusanov", species=None,
-             periodic=None, overrides=None, inlet_outlet=False, wall_law=False):
+             periodic=None, overrides=None, inlet_outlet=False, wall_law=False,
+             nonreflecting=None):
     """`wall_law`: the viscous wall uses the wall law (`wallTreatment=wallLaw`).
+    `nonreflecting`: None, or the length scale [m] of non-reflecting `inlet` / `pressureOutlet`
+    states (with `inlet_outlet`).
     `periodic`: None, or the box length: the two i-faces become a periodic pair (translation
     [length, 0, 0]) instead of characteristic boundaries.
     `inlet_outlet`: the i-lo face becomes an `inlet` and the i-hi face a `pressureOutlet`
@@ -74,6 +77,7 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         wall_state = "viscousWall(tag=2; heatFlux=%g)" % wall[1]
     if wall_law:
         wall_state = wall_state[:-1] + "; wallTreatment=wallLaw)"
+    nr = "; nonreflecting=true; lengthScale=%g" % nonreflecting if nonreflecting else ""
     lines = [
         "gridName: %s" % name,
         "equationSet: %s" % ("rans" if turb else ("navierStokes" if viscous else "euler")),
@@ -98,8 +102,8 @@ def inp_text(name, ni, nj, nk, *, solver="dplur", sweeps=4, cfl=50.0, limiter="n
         "matrixRelaxation: 1.0",
         "viscousFaceReconstruction: %s" % visc_recon,
         "boundaryStates: <%s>" % ", ".join(
-            (["inlet(tag=1; %s; massFractions=[air=1.0])" % state,
-              "pressureOutlet(tag=3; pressure=%g)" % IC["pressure"]] if inlet_outlet
+            (["inlet(tag=1; %s; massFractions=[air=1.0]%s)" % (state, nr),
+              "pressureOutlet(tag=3; pressure=%g%s)" % (IC["pressure"], nr)] if inlet_outlet
              else ["characteristic(tag=1; %s)" % state]) + ([wall_state] if viscous else []) +
             (["periodic(startTag=4; endTag=5; translation=[%.17g, 0, 0])" % periodic]
              if periodic else [])),

@@ -204,7 +204,9 @@ enum aither_field {
   AITHER_FIELD_F2 = 14,          /* ghost padded, 1 */
   AITHER_FIELD_VELOCITY_GRAD = 15, /* ghost padded, 9: (r,c) = d u_c / d x_r */
   AITHER_FIELD_TKE_GRAD = 16,    /* no ghosts, 3 */
-  AITHER_FIELD_OMEGA_GRAD = 17   /* no ghosts, 3 */
+  AITHER_FIELD_OMEGA_GRAD = 17,  /* no ghosts, 3 */
+  AITHER_FIELD_PRESSURE_GRAD = 18 /* no ghosts, 3: cell average of the face pressure gradients
+                                     (kept for runs with non-reflecting BCs only) */
 };
 
 typedef struct aither_gpu aither_gpu;   /* opaque handle */

@@ -2433,6 +2433,37 @@ void orc_calc_residual(orc_level *h) {
       calc_visc_flux(h, b, 2);
     } else {
       update_aux(h, b);
+      /* gradient-only pass of Euler runs (CalcGradsI/J/K; ref: src/procBlock.cpp:6138-6146,
+       * :5790-5945): the cell averages are read by the non-reflecting BCs only, so the pass
+       * is skipped when there is none */
+      int nonRefl = 0;
+      for (int q = 0; q < h->cfg.numBCStates; ++q) nonRefl |= h->cfg.bcStates[q].isNonreflecting;
+      if (nonRefl) {
+        memset(b->velGrad, 0, sizeof(double) * np * 9);
+        const int nd[3] = {b->ni, b->nj, b->nk};
+        const double sixth = 1.0 / 6.0;
+        for (int d = 0; d < 3; ++d) {
+          const int di = d == 0, dj = d == 1, dk = d == 2;
+          for (int kk = 0; kk < b->nk + dk; ++kk)
+            for (int jj = 0; jj < b->nj + dj; ++jj)
+              for (int ii = 0; ii < b->ni + di; ++ii) {
+                const int fi = d == 0 ? ii : (d == 1 ? jj : kk);
+                double vg[9], tg[3], kg[3], wg[3], mg[AITHER_MAX_SPECIES][3];
+                face_gradients(h, b, d, ii, jj, kk, vg, tg, kg, wg, mg);
+                if (fi > 0) {
+                  const long c = cidx(b, ii - di, jj - dj, kk - dk);
+                  const long pp = pidx(b, ii - di, jj - dj, kk - dk);
+                  for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
+                  for (int q = 0; q < 3; ++q) b->pressGrad[3 * pp + q] += sixth * g_face_press_grad[q];
+                }
+                if (fi < nd[d]) {
+                  const long c = cidx(b, ii, jj, kk), pp = pidx(b, ii, jj, kk);
+                  for (int q = 0; q < 9; ++q) b->velGrad[9 * c + q] += sixth * vg[q];
+                  for (int q = 0; q < 3; ++q) b->pressGrad[3 * pp + q] += sixth * g_face_press_grad[q];
+                }
+              }
+        }
+      }
     }
   }
   if (h->cfg.isViscous && !is_rans(h)) swap_connections(h, 5);
@@ -3286,6 +3317,7 @@ long long orc_field_size(orc_level *h, int blk, int field) {
     case AITHER_FIELD_VELOCITY_GRAD: return np * 9;
     case AITHER_FIELD_TKE_GRAD: return nc * 3;
     case AITHER_FIELD_OMEGA_GRAD: return nc * 3;
+    case AITHER_FIELD_PRESSURE_GRAD: return nc * 3;
   }
   return 0;
 }
@@ -3312,6 +3344,7 @@ void orc_get_field(orc_level *h, int blk, int field, double *dst) {
     case AITHER_FIELD_VELOCITY_GRAD: src = b->velGrad; break;
     case AITHER_FIELD_TKE_GRAD: src = b->tkeGrad; break;
     case AITHER_FIELD_OMEGA_GRAD: src = b->omegaGrad; break;
+    case AITHER_FIELD_PRESSURE_GRAD: src = b->pressGrad; break;
   }
   if (src) memcpy(dst, src, sizeof(double) * orc_field_size(h, blk, field));
 }

@@ -193,6 +193,17 @@ CASES = {
     # pressure / velocity gradients of the previous evaluation and the patch Mach numbers)
     "convectingVortex": dict(src="convectingVortex", iters=40, full=(0,), edits={}, fluids=("N2",),
                              drop=("diagRaw@", "temperature@", "state@it0.start", "x0@")),
+    # Euler box with non-reflecting inlet / outlet: the gradients come from the reference's
+    # gradient-only pass (CalcGradsI/J/K); and a laminar box with the wall law (1 cm).
+    # (vanAlbada: at iteration 0 the time step is 0 and the outlet ghost cells equal the interior
+    # cell to the last bit, where the unlimited eps-regularised MUSCL ratio is discontinuous)
+    "box_nonrefl_euler": dict(synthetic=dict(ni=12, nj=9, nk=8, solver="dplur", sweeps=3,
+                                             limiter="vanAlbada", inlet_outlet=True,
+                                             nonreflecting=1.0), iters=10,
+                              full=(0,)),
+    "box_walllaw_laminar": dict(synthetic=dict(ni=10, nj=9, nk=8, solver="lusgs", sweeps=2,
+                                               limiter="vanAlbada", viscous=True, size=1e-2,
+                                               wall_law=True), iters=10, full=(0,)),
     # synthetic SST boxes (1 cm: y+ of the wall cells ~ 50) with the wall law on an isothermal
     # and on a constant-heat-flux wall (wallLaw::IsothermalBCs / HeatFluxBCs; the shipped case is
     # adiabatic), DPLUR and BLU-SGS

@@ -25,7 +25,9 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_
                 # reconstruction (one ghost layer); constant-heat-flux viscous wall
                 "box_wenoz_cn", "box_first_order", "box_visc_heatflux", "box_inlet_outlet",
                 # SST with the wall law on an isothermal / constant-heat-flux wall
-                "box_walllaw_isothermal", "box_walllaw_heatflux"]
+                "box_walllaw_isothermal", "box_walllaw_heatflux", "box_walllaw_laminar",
+                # Euler run with non-reflecting inlet / outlet (gradient-only pass)
+                "box_nonrefl_euler"]
 
 
 def make_gpu_level(prob):
@@ -67,7 +69,8 @@ def test_gpu_phases_match_reference(name):
                                         ("box_wenoz_cn", 10), ("box_first_order", 10),
                                         ("box_visc_heatflux", 10), ("box_inlet_outlet", 10),
                                         ("box_walllaw_isothermal", 10),
-                                        ("box_walllaw_heatflux", 10)])
+                                        ("box_walllaw_heatflux", 10),
+                                        ("box_walllaw_laminar", 10), ("box_nonrefl_euler", 10)])
 def test_gpu_history_matches_reference(name, iters):
     d = gc.load(name)
     worst = gc.check_history(make_gpu_level, d, iters, 1e-9, name=name)

@@ -37,7 +37,9 @@ SINGLE_BLOCK = ["subsonicCylinder", "supersonicWedge", "transonicBump_sg", "box_
                 # wall law (White & Christoph / Nichols & Nelson) on an isothermal and on a
                 # constant-heat-flux wall; the adiabatic one is the reference's wallLaw case
                 # (two blocks: test_oracle_multiblock.py)
-                "box_walllaw_isothermal", "box_walllaw_heatflux"]
+                "box_walllaw_isothermal", "box_walllaw_heatflux", "box_walllaw_laminar",
+                # Euler run with non-reflecting inlet / outlet (gradient-only pass)
+                "box_nonrefl_euler"]
 
 
 # viscousFlatPlate runs at CFL 1e4 from a uniform start: the implicit update is the solution of a
@@ -66,7 +68,8 @@ def test_oracle_phases_match_reference(name):
                                         ("box_wenoz_cn", 10), ("box_first_order", 10),
                                         ("box_visc_heatflux", 10), ("box_inlet_outlet", 10),
                                         ("box_walllaw_isothermal", 10),
-                                        ("box_walllaw_heatflux", 10)])
+                                        ("box_walllaw_heatflux", 10),
+                                        ("box_walllaw_laminar", 10), ("box_nonrefl_euler", 10)])
 def test_oracle_history_matches_reference(name, iters):
     """L2 history within 1e-9 relative (north_star bar) + the reference's regression goldens."""
     d = gc.load(name)
