@@ -187,6 +187,13 @@ CASES = {
                           edits={"initialConditions": "<icState(tag=-1; file=ic.dat)>"},
                           drop=("diagRaw@", "temperature@", "state@it0.start", "x0@",
                                 "velocityGrad@", "f2@")),
+    # shipped case couette: laminar, LU-SGS at CFL 1e5, periodic pair in j, isothermal walls, the
+    # upper one moving (viscousWall with a velocity)
+    "couette": dict(src="couette", iters=30, full=(0,), edits={},
+                    drop=("diagRaw@", "temperature@", "state@it0.start", "x0@")),
+    # shipped case rae2822: SST 2003, LU-SGS, C-mesh whose wake cut is an interblock connection of
+    # the block with itself, referenceLength 0.3048
+    "rae2822": dict(src="rae2822", iters=10, full=(), edits={}, drop=("state@",)),
     # reference regression case convectingVortex (regressionTests.py:498-514): laminar, BDF2 dual
     # time stepping (10 nonlinear iterations per step), LU-SGS, periodic pair, non-reflecting
     # inlet and pressure outlet (LODI relaxation with the state at time n, the time step, the

@@ -138,6 +138,24 @@ def test_convecting_vortex_nonreflecting_matches_reference():
     assert gc.check_history(make_gpu_level, d, 40, 1e-9) <= 1e-9
 
 
+def test_couette_matches_reference():
+    """The shipped testCases/couette (laminar, LU-SGS at CFL 1e5, periodic pair, moving isothermal
+    wall); bars as viscousFlatPlate's (nearly singular implicit system at CFL 1e5)."""
+    d = gc.load("couette")
+    gc.check_phases(make_gpu_level, d, 0, dict(TOL, x=1e-9, x0=1e-11, state=1e-11, matrixResid=1e-7))
+    assert gc.check_history(make_gpu_level, d, 30, 1e-9) <= 1e-9
+
+
+def test_rae2822_matches_reference():
+    """The shipped testCases/rae2822 (SST 2003, LU-SGS, C-mesh with a self-connected wake cut);
+    fixture generated on demand (tests/golden/make_golden.py rae2822)."""
+    import os
+    if not os.path.exists(os.path.join(gc.GOLDEN_DIR, "rae2822.npz")):
+        pytest.skip("tests/golden/rae2822.npz has not been generated")
+    d = gc.load("rae2822")
+    assert gc.check_history(make_gpu_level, d, 10, 1e-9) <= 1e-9
+
+
 def test_run_with_nonlinear_iterations_equals_iterate():
     """aither_gpu_run loops cfg.nonlinearIterations inside every time step."""
     import refcase

@@ -95,6 +95,27 @@ def test_oracle_convecting_vortex_nonreflecting():
     assert gc.check_history(oracle.OracleLevel, d, 40, 1e-9) <= 1e-9
 
 
+def test_oracle_couette():
+    """The shipped testCases/couette: laminar, LU-SGS at CFL 1e5, periodic pair in j, isothermal
+    walls with the upper one moving (viscousWall with a velocity). CFL 1e5 from a uniform start:
+    a nearly singular implicit system, as viscousFlatPlate."""
+    d = gc.load("couette")
+    gc.check_phases(oracle.OracleLevel, d, 0, dict(TOL, x=1e-10, matrixResid=1e-9))
+    assert gc.check_history(oracle.OracleLevel, d, 30, 1e-9) <= 1e-9
+
+
+def test_oracle_rae2822():
+    """The shipped testCases/rae2822: SST 2003, LU-SGS, C-mesh (368 x 64 cells) whose wake cut is
+    an interblock connection of the block with itself; referenceLength 0.3048. The fixture
+    (14 MB) is not committed: `python tests/golden/make_golden.py rae2822` regenerates it."""
+    import os
+    import pytest
+    if not os.path.exists(os.path.join(gc.GOLDEN_DIR, "rae2822.npz")):
+        pytest.skip("tests/golden/rae2822.npz has not been generated")
+    d = gc.load("rae2822")
+    assert gc.check_history(oracle.OracleLevel, d, 10, 1e-9) <= 1e-9
+
+
 def test_oracle_periodic_connection():
     """A periodic pair (the block's own i-lo and i-hi faces, `periodic(startTag; endTag;
     translation)`, reference src/boundaryConditions.cpp:2224-2300): the block exchanges ghost layers
