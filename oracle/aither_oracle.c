@@ -46,6 +46,13 @@ typedef struct {
   /* wallData_: one record per face of every viscous-wall surface (NULL for
    * other surfaces); ref: include/wallData.hpp:40-62, src/procBlock.cpp:6287-6290 */
   struct orc_wall_vars **wall;
+  /* multigrid (ref: include/gridLevel.hpp:56-59): forcing term of this level (ni nj nk neq,
+   * zero on the finest level), update saved before the coarse cycles, and -- kept by the FINE
+   * block of a level pair -- coarse cell of every cell (3 ints), its volume weight, the seven
+   * trilinear coefficients of its centre in that coarse cell */
+  double *forcing, *savedX;
+  int *toCoarse;
+  double *volFac, *prolong;
 } orc_block;
 
 /* wallVars; ref: include/wallData.hpp:40-57 */
@@ -2988,8 +2995,9 @@ static void dplur_sweep(orc_level *h, orc_block *b) {
         implicit_lower(h, b, ii, jj, kk, b->xold, L);
         implicit_upper(h, b, ii, jj, kk, b->xold, U);
         rhs_b(h, b, ii, jj, kk, rb);
-        /* b + forcing(=0) + offDiagonal, offDiagonal = L - U */
-        for (int e = 0; e < neq; ++e) rhs[e] = rb[e] + 0.0 + (L[e] - U[e]);
+        /* b + forcing + offDiagonal, offDiagonal = L - U (forcing = 0 on the finest level) */
+        const double *fc = b->forcing + neq * pidx(b, ii, jj, kk);
+        for (int e = 0; e < neq; ++e) rhs[e] = rb[e] + fc[e] + (L[e] - U[e]);
         diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs,
                   b->x + neq * cidx(b, ii, jj, kk));
       }
@@ -3009,8 +3017,10 @@ static void lusgs_forward(orc_level *h, orc_block *b, int sweep) {
       for (int e = 0; e < neq; ++e) L[e] -= U[e];
     }
     rhs_b(h, b, ii, jj, kk, rb);
-    /* b = -R/theta + forcing + nm1 - mmn ; forcing = 0 */
-    for (int e = 0; e < neq; ++e) rhs[e] = rb[e] + L[e];
+    /* b = -R/theta + forcing + nm1 - mmn (forcing = 0 on the finest level; with forcing AND
+     * time terms the reference adds in that order, here the time terms come first) */
+    const double *fc = b->forcing + neq * pidx(b, ii, jj, kk);
+    for (int e = 0; e < neq; ++e) rhs[e] = (rb[e] + fc[e]) + L[e];
     diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs,
               b->x + neq * cidx(b, ii, jj, kk));
   }
@@ -3028,7 +3038,8 @@ static void lusgs_backward(orc_level *h, orc_block *b, int sweep) {
     if (sweep > 0 || h->cfg.matrixRequiresInit) {
       implicit_lower(h, b, ii, jj, kk, b->x, L);
       rhs_b(h, b, ii, jj, kk, rb);
-      for (int e = 0; e < neq; ++e) rhs[e] = (rb[e] + L[e]) - U[e];
+      const double *fc = b->forcing + neq * pidx(b, ii, jj, kk);
+      for (int e = 0; e < neq; ++e) rhs[e] = ((rb[e] + fc[e]) + L[e]) - U[e];
       diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), rhs, xc);
     } else {
       diag_mult(h, b->ainv + h->asz * pidx(b, ii, jj, kk), U, tmp);
@@ -3051,7 +3062,7 @@ static void matrix_residual(orc_level *h, orc_block *b) {
                   b->x + neq * cidx(b, ii, jj, kk), ax);
         double *mr = b->mresid + neq * pidx(b, ii, jj, kk);
         for (int e = 0; e < neq; ++e)
-          mr[e] = 0.0 - ((ax[e] - (L[e] - U[e])) - rb[e]);
+          mr[e] = b->forcing[neq * pidx(b, ii, jj, kk) + e] - ((ax[e] - (L[e] - U[e])) - rb[e]);
       }
 }
 
@@ -3239,6 +3250,8 @@ orc_level *orc_create(const aither_cfg *cfg, int nBlocks,
     b->tkeGrad = (double *)calloc(nc * 3, sizeof(double));
     b->omegaGrad = (double *)calloc(nc * 3, sizeof(double));
     b->pressGrad = (double *)calloc(nc * 3, sizeof(double));
+    b->forcing = (double *)calloc(nc * h->neq, sizeof(double));
+    b->savedX = (double *)calloc(np * h->neq, sizeof(double));
     b->vol = d->vol;
     b->fAI = d->fAreaI;
     b->fAJ = d->fAreaJ;
@@ -3284,6 +3297,7 @@ void orc_destroy(orc_level *h) {
     free(b->viscosity); free(b->order);
     free(b->eddyVisc); free(b->f1); free(b->f2); free(b->velGrad);
     free(b->tkeGrad); free(b->omegaGrad); free(b->pressGrad);
+    free(b->forcing); free(b->savedX); free(b->toCoarse); free(b->volFac); free(b->prolong);
     if (b->wall) {
       for (int s = 0; s < b->nsurf; ++s) free(b->wall[s]);
       free(b->wall);
@@ -3419,6 +3433,168 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
 }
 
 /* transport of a mixture state (tests/test_physics_host.py): {viscosity, effective conductivity} */
+/* ------------------------------------------------------------------------ */
+/* multigrid transfer operators between two levels (each an orc_level of its own;
+ * ref: src/gridLevel.cpp:538-611, include/procBlock.hpp:637-690,
+ * include/gridLevel.hpp:159-214, include/utility.hpp:186-372). The cycle itself
+ * (mgSolution::CycleAtLevel, src/mgSolution.cpp:160-207) is composed from these and
+ * the per-level phases by the caller (tests/oracle.py).                      */
+void orc_set_transfer(orc_level *h, int blk, const int *toCoarse, const double *volFac,
+                      const double *prolong) {
+  orc_block *b = &h->blk[blk];
+  const long nc = (long)b->ni * b->nj * b->nk;
+  free(b->toCoarse); free(b->volFac); free(b->prolong);
+  b->toCoarse = (int *)malloc(sizeof(int) * 3 * nc);
+  b->volFac = (double *)malloc(sizeof(double) * nc);
+  b->prolong = (double *)malloc(sizeof(double) * 7 * nc);
+  memcpy(b->toCoarse, toCoarse, sizeof(int) * 3 * nc);
+  memcpy(b->volFac, volFac, sizeof(double) * nc);
+  memcpy(b->prolong, prolong, sizeof(double) * 7 * nc);
+}
+
+/* gridLevel::Restriction; `cfl` = inp.CFL() of the current iteration */
+void orc_mg_restrict(orc_level *fine, orc_level *coarse, int mm, double cfl) {
+  const int neq = fine->neq;
+  for (int bb = 0; bb < fine->nblk; ++bb) {
+    const orc_block *f = &fine->blk[bb];
+    orc_block *c = &coarse->blk[bb];
+    /* volume-weighted state (BlockRestriction zeroes the coarse array, ghosts included) */
+    memset(c->state, 0, sizeof(double) * (long)c->NI * c->NJ * c->NK * neq);
+    for (int kk = 0; kk < f->nk; ++kk)
+      for (int jj = 0; jj < f->nj; ++jj)
+        for (int ii = 0; ii < f->ni; ++ii) {
+          const long pf = pidx(f, ii, jj, kk);
+          const int *ci = f->toCoarse + 3 * pf;
+          double *cs = c->state + neq * cidx(c, ci[0], ci[1], ci[2]);
+          const double *fs = f->state + neq * cidx(f, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) cs[e] = cs[e] + f->volFac[pf] * fs[e];
+        }
+    if (mm == 0) orc_store_old_solution(coarse, 1);
+  }
+  orc_get_boundary_conditions(coarse);
+  orc_calc_residual(coarse);
+  orc_calc_time_step(coarse, cfl);
+  orc_invert_diagonal(coarse);
+  /* linearSolver::Restriction: volume-weighted update, then its ghost swap */
+  for (int bb = 0; bb < fine->nblk; ++bb) {
+    const orc_block *f = &fine->blk[bb];
+    orc_block *c = &coarse->blk[bb];
+    memset(c->x, 0, sizeof(double) * (long)c->NI * c->NJ * c->NK * neq);
+    for (int kk = 0; kk < f->nk; ++kk)
+      for (int jj = 0; jj < f->nj; ++jj)
+        for (int ii = 0; ii < f->ni; ++ii) {
+          const long pf = pidx(f, ii, jj, kk);
+          const int *ci = f->toCoarse + 3 * pf;
+          double *cx = c->x + neq * cidx(c, ci[0], ci[1], ci[2]);
+          const double *fx = f->x + neq * cidx(f, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) cx[e] = cx[e] + f->volFac[pf] * fx[e];
+        }
+  }
+  swap_connections(coarse, 1);
+  /* forcing = (A x - b) of the coarse level with the restricted update and state + the fine
+   * level's matrix residual summed over the fine cells of every coarse cell */
+  for (int bb = 0; bb < fine->nblk; ++bb) {
+    const orc_block *f = &fine->blk[bb];
+    orc_block *c = &coarse->blk[bb];
+    const long ncc = (long)c->ni * c->nj * c->nk;
+    memset(c->forcing, 0, sizeof(double) * ncc * neq);
+    for (int kk = 0; kk < f->nk; ++kk)
+      for (int jj = 0; jj < f->nj; ++jj)
+        for (int ii = 0; ii < f->ni; ++ii) {
+          const long pf = pidx(f, ii, jj, kk);
+          const int *ci = f->toCoarse + 3 * pf;
+          double *cf = c->forcing + neq * pidx(c, ci[0], ci[1], ci[2]);
+          for (int e = 0; e < neq; ++e) cf[e] = cf[e] + f->mresid[neq * pf + e];
+        }
+    for (int kk = 0; kk < c->nk; ++kk)
+      for (int jj = 0; jj < c->nj; ++jj)
+        for (int ii = 0; ii < c->ni; ++ii) {
+          double L[MAXEQ], U[MAXEQ], rb[MAXEQ], ax[MAXEQ];
+          implicit_lower(coarse, c, ii, jj, kk, c->x, L);
+          implicit_upper(coarse, c, ii, jj, kk, c->x, U);
+          rhs_b(coarse, c, ii, jj, kk, rb);
+          diag_mult(coarse, c->a + coarse->asz * pidx(c, ii, jj, kk),
+                    c->x + neq * cidx(c, ii, jj, kk), ax);
+          double *cf = c->forcing + neq * pidx(c, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) cf[e] = ((ax[e] - (L[e] - U[e])) - rb[e]) + cf[e];
+        }
+  }
+}
+
+void orc_mg_save_update(orc_level *h) {
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    memcpy(b->savedX, b->x, sizeof(double) * (long)b->NI * b->NJ * b->NK * h->neq);
+  }
+}
+void orc_mg_subtract_saved(orc_level *h) { /* linearSolver::SubtractFromUpdate */
+  for (int bb = 0; bb < h->nblk; ++bb) {
+    orc_block *b = &h->blk[bb];
+    const long n = (long)b->NI * b->NJ * b->NK * h->neq;
+    for (long q = 0; q < n; ++q) b->x[q] -= b->savedX[q];
+  }
+}
+
+/* gridLevel::Prolongation: coarse update -> node values of the coarse block
+ * (ConvertCellToNode(coarse, ignoreEdge = true, ignoreGhosts = true)) -> trilinear
+ * interpolation at every fine cell centre -> added to the fine update */
+void orc_mg_prolong(orc_level *coarse, orc_level *fine) {
+  const int neq = fine->neq;
+  for (int bb = 0; bb < fine->nblk; ++bb) {
+    const orc_block *c = &coarse->blk[bb];
+    orc_block *f = &fine->blk[bb];
+    const int n0 = c->ni + 1, n1 = c->nj + 1, n2 = c->nk + 1;
+    double *node = (double *)calloc((size_t)n0 * n1 * n2 * neq, sizeof(double));
+#define ND(i, j, k) (node + neq * ((long)(i) + (long)n0 * ((j) + (long)n1 * (k))))
+    const int off[8][3] = {{0, 0, 0}, {0, 1, 0}, {0, 1, 1}, {0, 0, 1},
+                           {1, 0, 0}, {1, 1, 0}, {1, 1, 1}, {1, 0, 1}};
+    for (int kk = 0; kk < c->nk; ++kk)
+      for (int jj = 0; jj < c->nj; ++jj)
+        for (int ii = 0; ii < c->ni; ++ii) {
+          const double *cx = c->x + neq * cidx(c, ii, jj, kk);
+          for (int q = 0; q < 8; ++q) {
+            double *nd = ND(ii + off[q][0], jj + off[q][1], kk + off[q][2]);
+            for (int e = 0; e < neq; ++e) nd[e] += cx[e];
+          }
+        }
+    for (int kk = 0; kk < n2; ++kk)
+      for (int jj = 0; jj < n1; ++jj)
+        for (int ii = 0; ii < n0; ++ii) {
+          const int ei = ii == 0 || ii == n0 - 1, ej = jj == 0 || jj == n1 - 1,
+                    ek = kk == 0 || kk == n2 - 1;
+          /* AtInteriorCorner: 1; AtInteriorEdge: 1/2; else 1/8 (no ghost layers) */
+          const double fac = (ei && ej && ek) ? 1.0 : ((ei + ej + ek == 2) ? 1.0 / 2.0 : 1.0 / 8.0);
+          double *nd = ND(ii, jj, kk);
+          for (int e = 0; e < neq; ++e) nd[e] *= fac;
+        }
+    for (int kk = 0; kk < f->nk; ++kk)
+      for (int jj = 0; jj < f->nj; ++jj)
+        for (int ii = 0; ii < f->ni; ++ii) {
+          const long pf = pidx(f, ii, jj, kk);
+          const int *ci = f->toCoarse + 3 * pf;
+          const double *co = f->prolong + 7 * pf;
+          const double *d0 = ND(ci[0], ci[1], ci[2]), *d1 = ND(ci[0] + 1, ci[1], ci[2]),
+                       *d2 = ND(ci[0], ci[1] + 1, ci[2]), *d3 = ND(ci[0] + 1, ci[1] + 1, ci[2]),
+                       *d4 = ND(ci[0], ci[1], ci[2] + 1), *d5 = ND(ci[0] + 1, ci[1], ci[2] + 1),
+                       *d6 = ND(ci[0], ci[1] + 1, ci[2] + 1),
+                       *d7 = ND(ci[0] + 1, ci[1] + 1, ci[2] + 1);
+          double *fx = f->x + neq * cidx(f, ii, jj, kk);
+          for (int e = 0; e < neq; ++e) {
+            /* TrilinearInterp: LinearInterp(a, b, c) = (1 - c) a + c b */
+            const double d04 = (1.0 - co[0]) * d0[e] + co[0] * d4[e];
+            const double d15 = (1.0 - co[1]) * d1[e] + co[1] * d5[e];
+            const double d26 = (1.0 - co[2]) * d2[e] + co[2] * d6[e];
+            const double d37 = (1.0 - co[3]) * d3[e] + co[3] * d7[e];
+            const double d0415 = (1.0 - co[4]) * d04 + co[4] * d15;
+            const double d2637 = (1.0 - co[5]) * d26 + co[5] * d37;
+            fx[e] += (1.0 - co[6]) * d0415 + co[6] * d2637;
+          }
+        }
+#undef ND
+    free(node);
+  }
+}
+
 /* ghost state of a non-reflecting inlet / pressure outlet; extra = {dt, stateN[neq],
  * pressGrad[3], velGrad[9], avgMach, maxMach} (tests/test_physics_host.py) */
 void orc_ghost_state_nonreflecting(const aither_cfg *cfg, const double *interior, int bcType,

@@ -77,6 +77,15 @@ void orc_ghost_state_visc(const aither_cfg *cfg, const double *interior, int bcT
                           const double areaUnit[3], int surfType, int tag, int layer,
                           double wallDist, double nuW, double *ghost);
 
+/* multigrid transfer operators between two levels (gridLevel::Restriction / Prolongation,
+ * linearSolver::SubtractFromUpdate); the cycle is composed by the caller (tests/oracle.py) */
+void orc_set_transfer(orc_level *h, int blk, const int *toCoarse, const double *volFac,
+                      const double *prolong);
+void orc_mg_restrict(orc_level *fine, orc_level *coarse, int mm, double cfl);
+void orc_mg_save_update(orc_level *h);
+void orc_mg_subtract_saved(orc_level *h);
+void orc_mg_prolong(orc_level *coarse, orc_level *fine);
+
 void orc_ghost_state_nonreflecting(const aither_cfg *cfg, const double *interior, int bcType,
                                    const double areaUnit[3], int surfType, int tag, int layer,
                                    const double *extra, double *ghost);

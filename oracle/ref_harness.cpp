@@ -266,11 +266,11 @@ void DumpConfig(Dump &d, const input &inp, const physics &phys) {
   }
 }
 
-void DumpBlockSetup(Dump &d, const gridLevel &lvl) {
-  d.iscalar("numBlocks", lvl.NumBlocks());
+void DumpBlockSetup(Dump &d, const gridLevel &lvl, const std::string &pre = "") {
+  d.iscalar(pre + "numBlocks", lvl.NumBlocks());
   for (int bb = 0; bb < lvl.NumBlocks(); ++bb) {
     const auto &blk = lvl.Block(bb);
-    const std::string p = "b" + std::to_string(bb) + "/";
+    const std::string p = pre + "b" + std::to_string(bb) + "/";
     d.ivec(p + "dims", {blk.NumI(), blk.NumJ(), blk.NumK(), blk.NumGhosts(),
                         blk.ParentBlock(), blk.Rank(), blk.LocalPosition(),
                         blk.GlobalPos()});
@@ -317,7 +317,25 @@ void DumpBlockSetup(Dump &d, const gridLevel &lvl) {
     c.push_back(cn.orientation_);
     c.push_back(cn.isInterblock_ ? 1 : 0);
   }
-  d.ints("connections", c.data(), {static_cast<int64_t>(conns.size()), 28});
+  d.ints(pre + "connections", c.data(), {static_cast<int64_t>(conns.size()), 28});
+}
+
+// multigrid transfer maps between level `fl` and the next coarser one: fine cell -> coarse cell,
+// volume weight of the fine cell in it (both kept by the fine level) and the seven trilinear
+// coefficients of the fine cell centre in the coarse cell (kept by the coarse level)
+void DumpTransfer(Dump &d, const gridLevel &fine, const gridLevel &coarse, int fl) {
+  for (int bb = 0; bb < fine.NumBlocks(); ++bb) {
+    const std::string p = "L" + std::to_string(fl) + "/b" + std::to_string(bb) + "/";
+    const auto &tc = fine.toCoarse_[bb];
+    std::vector<int> flat;
+    for (const auto &v : tc.data_) flat.insert(flat.end(), {v.X(), v.Y(), v.Z()});
+    d.ints(p + "toCoarse", flat.data(), {tc.NumK(), tc.NumJ(), tc.NumI(), 3});
+    d.field(p + "volWeightFactor", fine.volWeightFactor_[bb]);
+    const auto &pc = coarse.prolongCoeffs_[bb];
+    std::vector<double> co;
+    for (const auto &a : pc.data_) co.insert(co.end(), a.begin(), a.end());
+    d.doubles(p + "prolongCoeffs", co.data(), {pc.NumK(), pc.NumJ(), pc.NumI(), 7});
+  }
 }
 
 void DumpStates(Dump &d, const gridLevel &lvl, const std::string &tag) {
@@ -397,6 +415,14 @@ int main(int argc, char *argv[]) {
   DumpConfig(d, inp, phys);
   auto &lvl = local[local.FinestIndex()];
   if (geom) DumpBlockSetup(d, lvl);
+  d.iscalar("cfg/multigridLevels", local.NumGridLevels());
+  d.iscalar("cfg/mgCycleIndex", inp.MultigridCycleIndex());
+  if (geom) {  // coarse levels (prefix L<level>/) and the transfer maps between levels
+    for (int ll = 1; ll < local.NumGridLevels(); ++ll) {
+      DumpBlockSetup(d, local[ll], "L" + std::to_string(ll) + "/");
+      DumpTransfer(d, local[ll - 1], local[ll], ll - 1);
+    }
+  }
 
   const int neq = inp.NumEquations();
   std::vector<double> histL2, histLinf, histMat, histCfl, histTime;

@@ -168,6 +168,10 @@ CASES = {
     # SURVEY 8(f) row, so `multigridLevels: 1` here
     "transonicBump_sg": dict(src="transonicBump", iters=100, full=(0, 50),
                              edits={"multigridLevels": "1"}),
+    # the shipped transonicBump itself: 3-level W-cycle multigrid (full-approximation-storage
+    # coarse grid correction: volume-weighted restriction of state and update, summed matrix
+    # residual as forcing, trilinear prolongation); regressionTests.py:325-337
+    "transonicBump": dict(src="transonicBump", iters=100, full=(), edits={}, drop=("state@",)),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
     # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,

@@ -48,6 +48,14 @@ def lib():
         L.orc_ghost_state.argtypes = [C.POINTER(abi.Cfg), pd, C.c_int, pd, C.c_int, C.c_int,
                                       C.c_int, pd]
         L.orc_offdiag_scalar.argtypes = [C.POINTER(abi.Cfg), pd, pd, pd, C.c_int, pd]
+        L.orc_set_transfer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), pd, pd]
+        L.orc_mg_restrict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.orc_mg_prolong.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_mg_save_update.argtypes = [C.c_void_p]
+        L.orc_mg_subtract_saved.argtypes = [C.c_void_p]
+        for name in ("orc_set_transfer", "orc_mg_restrict", "orc_mg_prolong", "orc_mg_save_update",
+                     "orc_mg_subtract_saved"):
+            getattr(L, name).restype = None
         _LIB = L
     return _LIB
 
@@ -122,3 +130,62 @@ class OracleLevel:
                          abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
+
+
+class OracleMultigrid:
+    """The oracle's mgSolution: one OracleLevel per grid level (finest first) plus the transfer
+    maps of every level pair, and the full-approximation-storage cycle of the reference
+    (mgSolution::Iterate / ImplicitUpdate / CycleAtLevel, src/mgSolution.cpp:160-269) composed
+    from the per-level phases and the oracle's transfer operators.
+
+    `problems`: one Problem per level; `transfers[l]`: per block of level l a tuple
+    (toCoarse int32 [nk, nj, ni, 3], volWeightFactor [nk, nj, ni], prolongCoeffs [nk, nj, ni, 7])
+    onto level l + 1; `cycle_index`: 1 = V cycle, 2 = W cycle."""
+
+    def __init__(self, problems, transfers, cycle_index):
+        self.levels = [OracleLevel(p) for p in problems]
+        self.cycle_index = cycle_index
+        self.neq = problems[0].neq
+        pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        for l, per_block in enumerate(transfers):
+            for bb, (tc, vf, pc) in enumerate(per_block):
+                tc = np.ascontiguousarray(tc, dtype=np.int32)
+                vf = np.ascontiguousarray(vf, dtype=np.float64)
+                pc = np.ascontiguousarray(pc, dtype=np.float64)
+                lib().orc_set_transfer(self.levels[l]._h, bb, tc.ctypes.data_as(pi),
+                                       vf.ctypes.data_as(pd), pc.ctypes.data_as(pd))
+
+    def close(self):
+        for l in self.levels:
+            l.close()
+
+    def store_old_solution(self, it=0):
+        self.levels[0].store_old_solution(it)
+
+    def _cycle(self, fl, mm, cfl):
+        lv = self.levels
+        sweeps = lv[0].problem.cfg.matrixSweeps
+        if fl == len(lv) - 1:
+            return lv[fl].relax(sweeps)
+        half = max(sweeps // 2, 1)
+        lv[fl].relax(half)
+        lib().orc_mg_restrict(lv[fl]._h, lv[fl + 1]._h, mm, cfl)
+        lib().orc_mg_save_update(lv[fl + 1]._h)
+        for _ in range(self.cycle_index):
+            self._cycle(fl + 1, mm, cfl)
+        lib().orc_mg_subtract_saved(lv[fl + 1]._h)
+        lib().orc_mg_prolong(lv[fl + 1]._h, lv[fl]._h)
+        return lv[fl].relax(half)
+
+    def iterate(self, cfl, mm=0):
+        f = self.levels[0]
+        f.get_boundary_conditions()
+        f.calc_residual()
+        lib().orc_calc_time_step(f._h, cfl)
+        lib().orc_invert_diagonal(f._h)
+        lib().orc_initialize_matrix_update(f._h)
+        mr = self._cycle(0, mm, cfl)
+        l2, linf = f.update_blocks(mm)
+        for l in self.levels:
+            l.reset_diagonal()
+        return l2, linf, mr

@@ -108,9 +108,9 @@ def cfg_from_dump(d):
         bcStates=bcs)
 
 
-def conns_from_dump(d):
+def conns_from_dump(d, prefix=""):
     out = []
-    for row in d.get("connections", np.zeros((0, 28), dtype=np.int32)):
+    for row in d.get(prefix + "connections", np.zeros((0, 28), dtype=np.int32)):
         c = abi.Conn()
         r = [int(v) for v in row]
         for n, name in enumerate(("rank", "block", "localBlock", "boundary", "d1Start", "d1End",
@@ -124,11 +124,28 @@ def conns_from_dump(d):
     return out
 
 
-def problem_from_dump(d, state_key="state0"):
+def multigrid_from_dump(d):
+    """(problems, transfers, cycle index) of a multi-level dump: the finest level and every
+    coarse level `L<l>/` as a Problem of its own, plus the transfer maps between level pairs
+    (oracle.OracleMultigrid)."""
+    nl = int(d["cfg/multigridLevels"][0])
+    problems = [problem_from_dump(d)] + [problem_from_dump(d, prefix="L%d/" % l)
+                                         for l in range(1, nl)]
+    transfers = []
+    for l in range(nl - 1):
+        per_block = []
+        for bb in range(len(problems[l].blocks)):
+            p = "L%d/b%d/" % (l, bb)
+            per_block.append((d[p + "toCoarse"], d[p + "volWeightFactor"], d[p + "prolongCoeffs"]))
+        transfers.append(per_block)
+    return problems, transfers, int(d["cfg/mgCycleIndex"][0])
+
+
+def problem_from_dump(d, state_key="state0", prefix=""):
     cfg = cfg_from_dump(d)
     blocks = []
-    for bb in range(int(d["numBlocks"][0])):
-        p = "b%d/" % bb
+    for bb in range(int(d[prefix + "numBlocks"][0])):
+        p = prefix + "b%d/" % bb
         ni, nj, nk, g, parent, rank, lpos, gpos = [int(v) for v in d[p + "dims"]]
         surfaces = [tuple(int(v) for v in row[:8]) for row in d[p + "surfaces"]]
         arrays = {k: np.array(d[p + k]) for k in ("vol", "fAreaI", "fAreaJ", "fAreaK", "center",
@@ -136,7 +153,7 @@ def problem_from_dump(d, state_key="state0"):
                                                  "wallDist")}
         arrays["state"] = np.array(d[p + state_key])
         blocks.append(Block(ni, nj, nk, surfaces, arrays, parent_block=parent, global_pos=gpos))
-    return Problem(cfg, blocks, conns_from_dump(d))
+    return Problem(cfg, blocks, conns_from_dump(d, prefix))
 
 
 def stage_case(src_dir, dst_dir, edits=None, iterations=None):
