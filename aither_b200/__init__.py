@@ -33,6 +33,8 @@ ABI_SYMBOLS = (
     "aither_gpu_alloc_host", "aither_gpu_free_host",
     "aither_gpu_comm_unique_id", "aither_gpu_comm_create", "aither_gpu_comm_destroy",
     "aither_gpu_halo_info",
+    "aither_gpu_set_transfer", "aither_gpu_mg_restrict", "aither_gpu_mg_save_update",
+    "aither_gpu_mg_subtract_saved", "aither_gpu_mg_prolong",
 )
 
 
@@ -54,6 +56,11 @@ def load_library():
     L.aither_gpu_create.argtypes = [C.POINTER(abi.Cfg), C.c_int, C.POINTER(abi.BlockDesc), C.c_int,
                                     C.POINTER(abi.Conn), C.c_int, C.c_int, vp, C.c_int,
                                     C.POINTER(vp)]
+    L.aither_gpu_set_transfer.argtypes = [vp, C.c_int, C.POINTER(C.c_int), pd, pd]
+    L.aither_gpu_mg_restrict.argtypes = [vp, vp, C.c_int, C.c_double]
+    L.aither_gpu_mg_save_update.argtypes = [vp]
+    L.aither_gpu_mg_subtract_saved.argtypes = [vp]
+    L.aither_gpu_mg_prolong.argtypes = [vp, vp]
     L.aither_gpu_store_old_solution.argtypes = [vp, C.c_int]
     L.aither_gpu_iterate.argtypes = [vp, C.c_double, C.c_int, pd, C.POINTER(abi.Linf), pd]
     for name in ("aither_gpu_get_boundary_conditions", "aither_gpu_calc_residual",
@@ -247,3 +254,65 @@ class GridLevel:
             self._check(self._lib.aither_gpu_profile_get(self._h, f, C.byref(ms), C.byref(n)))
             out[self._lib.aither_gpu_kernel_family_name(f).decode()] = (ms.value, n.value)
         return out
+
+
+class Multigrid:
+    """Device-resident multigrid solution: one GridLevel per grid level (finest first) and the
+    reference's full-approximation-storage cycle (mgSolution::Iterate / ImplicitUpdate /
+    CycleAtLevel, src/mgSolution.cpp:160-269) composed from the per-level phase calls and the
+    transfer operators of the C ABI (aither_gpu_mg_*).
+
+    `problems`: one Problem per level (the coarse blocks are built once by the caller, as the
+    reference's gridLevel::Coarsen does at set-up); `transfers[l]`: per block of level l the maps
+    onto level l + 1 -- (toCoarse int32 [nk, nj, ni, 3], volWeightFactor [nk, nj, ni],
+    prolongCoeffs [nk, nj, ni, 7]); `cycle_index`: 1 = V cycle, 2 = W cycle."""
+
+    def __init__(self, problems, transfers, cycle_index, device=0):
+        self.levels = [GridLevel(p, device=device) for p in problems]
+        self.cycle_index = int(cycle_index)
+        self.neq = problems[0].neq
+        self._lib = load_library()
+        self._keep = []
+        for l, per_block in enumerate(transfers):
+            for bb, (tc, vf, pc) in enumerate(per_block):
+                tc = np.ascontiguousarray(tc, dtype=np.int32)
+                vf = np.ascontiguousarray(vf, dtype=np.float64)
+                pc = np.ascontiguousarray(pc, dtype=np.float64)
+                lv = self.levels[l]
+                lv._check(self._lib.aither_gpu_set_transfer(
+                    lv._h, bb, tc.ctypes.data_as(C.POINTER(C.c_int)), _ptr(vf), _ptr(pc)))
+
+    def close(self):
+        for lv in self.levels:
+            lv.close()
+
+    def store_old_solution(self, it=0):
+        self.levels[0].store_old_solution(it)
+
+    def _cycle(self, fl, mm, cfl):
+        lv = self.levels
+        sweeps = lv[0].problem.cfg.matrixSweeps
+        if fl == len(lv) - 1:
+            return lv[fl].relax(sweeps)
+        half = max(sweeps // 2, 1)
+        lv[fl].relax(half)
+        lv[fl]._check(self._lib.aither_gpu_mg_restrict(lv[fl]._h, lv[fl + 1]._h, mm, cfl))
+        lv[fl + 1]._check(self._lib.aither_gpu_mg_save_update(lv[fl + 1]._h))
+        for _ in range(self.cycle_index):
+            self._cycle(fl + 1, mm, cfl)
+        lv[fl + 1]._check(self._lib.aither_gpu_mg_subtract_saved(lv[fl + 1]._h))
+        lv[fl]._check(self._lib.aither_gpu_mg_prolong(lv[fl + 1]._h, lv[fl]._h))
+        return lv[fl].relax(half)
+
+    def iterate(self, cfl, mm=0):
+        f = self.levels[0]
+        f.get_boundary_conditions()
+        f.calc_residual()
+        f.calc_time_step(cfl)
+        f.invert_diagonal()
+        f.initialize_matrix_update()
+        mr = self._cycle(0, mm, cfl)
+        l2, linf = f.update_blocks(mm)
+        for lv in self.levels:
+            lv.reset_diagonal()
+        return l2, linf, mr

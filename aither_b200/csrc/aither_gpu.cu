@@ -65,6 +65,13 @@ struct HostBlock {
   EdgeSurf *dEdgeSurfs = nullptr;  // every surface of the block, connections included
   double *dWallVars = nullptr;     // wall-law records (walllaw.cuh), null without wall-law walls
   double *dPatchMach = nullptr;    // {average, maximum} Mach number per BC surface (non-reflecting BCs)
+  // multigrid (multigrid.cuh): transfer maps onto the next coarser level (kept by the fine block),
+  // child list per coarse cell (built on first use), saved update, node scratch of this block
+  std::vector<int> toCoarseHost;
+  int *dToCoarse = nullptr, *dChildren = nullptr;
+  long long childrenFor = 0;       // coarse cell count the child list was built for
+  double *dVolFac = nullptr, *dProlong = nullptr, *dSavedX = nullptr, *dNodes = nullptr;
+  double *dSavedDiag = nullptr;    // diagonal of the previous restriction of this iteration
   int nEdgeSurfs = 0;
   long long bcThreads = 0;
   uint8_t *dConnFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -856,6 +863,13 @@ void FreeAll(aither_gpu *h) {
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     if (hb.dWallVars) cudaFree(hb.dWallVars);
     if (hb.dPatchMach) cudaFree(hb.dPatchMach);
+    if (hb.dToCoarse) cudaFree(hb.dToCoarse);
+    if (hb.dChildren) cudaFree(hb.dChildren);
+    if (hb.dVolFac) cudaFree(hb.dVolFac);
+    if (hb.dProlong) cudaFree(hb.dProlong);
+    if (hb.dSavedX) cudaFree(hb.dSavedX);
+    if (hb.dNodes) cudaFree(hb.dNodes);
+    if (hb.dSavedDiag) cudaFree(hb.dSavedDiag);
     for (auto &p : hb.dConnFace)
       if (p) cudaFree(p);
   }
@@ -920,6 +934,7 @@ AITHER_DEFINE_EQ_OPS(3, 2)
 #endif
 
 #if !defined(AITHER_EQ_TU)  // the C ABI lives in the main translation unit only
+#include "multigrid.cuh"
 // =================================================================================================
 extern "C" {
 
@@ -1345,6 +1360,171 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
 #undef CKH
 #undef CKC
   *out = h;
+  return 0;
+}
+
+// ---- multigrid transfer operators (multigrid.cuh) ------------------------------
+int aither_gpu_set_transfer(aither_gpu *h, int blk, const int *toCoarse, const double *volFac,
+                            const double *prolong) {
+  if (!h || !toCoarse || !volFac || !prolong) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  HostBlock &hb = h->blocks[blk];
+  const BlockDev &b = hb.dev;
+  const size_t nc = static_cast<size_t>(b.ni) * b.nj * b.nk;
+  hb.toCoarseHost.assign(toCoarse, toCoarse + 3 * nc);
+  if (!hb.dToCoarse) {
+    CK(cudaMalloc(&hb.dToCoarse, sizeof(int) * 3 * nc));
+    CK(cudaMalloc(&hb.dVolFac, sizeof(double) * nc));
+    CK(cudaMalloc(&hb.dProlong, sizeof(double) * 7 * nc));
+  }
+  CK(cudaMemcpy(hb.dToCoarse, toCoarse, sizeof(int) * 3 * nc, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(hb.dVolFac, volFac, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(hb.dProlong, prolong, sizeof(double) * 7 * nc, cudaMemcpyHostToDevice));
+  hb.childrenFor = 0;
+  return 0;
+}
+
+namespace {
+int MgCheckPair(aither_gpu *fine, aither_gpu *coarse) {
+  if (!fine || !coarse) return Fail("null handle");
+  if (fine->device != coarse->device) return Fail("multigrid levels must live on one device");
+  if (fine->blocks.size() != coarse->blocks.size() || fine->neq != coarse->neq)
+    return Fail("multigrid levels must have the same blocks and equations");
+  for (auto &hb : fine->blocks)
+    if (!hb.dToCoarse) return Fail("aither_gpu_set_transfer has not been called for the fine level");
+  return 0;
+}
+// children of every coarse cell in the reference's visiting order (fine k, j, i ascending)
+int MgChildren(HostBlock &f, const HostBlock &c) {
+  const long long ncc = static_cast<long long>(c.dev.ni) * c.dev.nj * c.dev.nk;
+  if (f.dChildren && f.childrenFor == ncc) return 0;
+  std::vector<int> ch(static_cast<size_t>(ncc) * kMaxChildren, -1);
+  std::vector<int> cnt(static_cast<size_t>(ncc), 0);
+  const long long nfc = static_cast<long long>(f.dev.ni) * f.dev.nj * f.dev.nk;
+  for (long long pf = 0; pf < nfc; ++pf) {
+    const int *ci = &f.toCoarseHost[3 * pf];
+    if (ci[0] < 0 || ci[0] >= c.dev.ni || ci[1] < 0 || ci[1] >= c.dev.nj || ci[2] < 0 ||
+        ci[2] >= c.dev.nk)
+      return Fail("multigrid transfer map points outside the coarse block");
+    const long long pc = ci[0] + static_cast<long long>(c.dev.ni) * (ci[1] + static_cast<long long>(c.dev.nj) * ci[2]);
+    if (cnt[pc] >= kMaxChildren) return Fail("a coarse cell has more than 8 fine cells");
+    ch[pc * kMaxChildren + cnt[pc]++] = static_cast<int>(pf);
+  }
+  if (f.dChildren) cudaFree(f.dChildren);
+  f.dChildren = nullptr;
+  CK(cudaMalloc(&f.dChildren, sizeof(int) * ch.size()));
+  CK(cudaMemcpy(f.dChildren, ch.data(), sizeof(int) * ch.size(), cudaMemcpyHostToDevice));
+  f.childrenFor = ncc;
+  return 0;
+}
+}  // namespace
+
+int aither_gpu_mg_restrict(aither_gpu *fine, aither_gpu *coarse, int mm, double cfl) {
+  // gridLevel::Restriction (ref: src/gridLevel.cpp:538-588)
+  if (MgCheckPair(fine, coarse)) return 1;
+  CK(cudaSetDevice(fine->device));
+  CK(cudaStreamSynchronize(fine->stream));
+  const int neq = fine->neq;
+  const dim3 blk(32, 4, 1);
+  for (size_t bb = 0; bb < fine->blocks.size(); ++bb) {
+    HostBlock &f = fine->blocks[bb];
+    HostBlock &c = coarse->blocks[bb];
+    if (MgChildren(f, c)) return 1;
+    const dim3 grid((c.dev.ni + 31) / 32, (c.dev.nj + 3) / 4, c.dev.nk);
+    RestrictKernel<<<grid, blk, 0, coarse->stream>>>(f.dev, c.dev, f.dChildren, f.dVolFac,
+                                                     f.dev.state, c.dev.state, neq, false);
+  }
+  CK(cudaGetLastError());
+  coarse->stateMovedSinceStore = true;
+  if (mm == 0 && aither_gpu_store_old_solution(coarse, 1)) return 1;
+  // The reference's residual loops ADD the spectral radii / flux Jacobians to the main diagonal,
+  // which is only zeroed by ResetDiagonal at the end of the iteration (src/mgSolution.cpp:262-265):
+  // a level that is restricted to more than once per iteration (W cycle) keeps the inverted-
+  // diagonal terms of its previous visit underneath the new ones. The residual kernels here
+  // assign the diagonal, so the previous one is saved and added back.
+  const long long nDiag = static_cast<long long>(coarse->asz);
+  for (auto &c : coarse->blocks) {
+    const size_t bytes = sizeof(double) * c.dev.fs * nDiag;
+    if (!c.dSavedDiag) CK(cudaMalloc(&c.dSavedDiag, bytes));
+    CK(cudaMemcpyAsync(c.dSavedDiag, c.dev.diag, bytes, cudaMemcpyDeviceToDevice, coarse->stream));
+  }
+  if (aither_gpu_get_boundary_conditions(coarse) || aither_gpu_calc_residual(coarse)) return 1;
+  for (auto &c : coarse->blocks)
+    AxpyFieldKernel<<<148 * 4, 256, 0, coarse->stream>>>(c.dev.diag, c.dSavedDiag, 1.0,
+                                                       static_cast<long long>(c.dev.fs) * nDiag);
+  CK(cudaGetLastError());
+  if (aither_gpu_calc_time_step(coarse, cfl) || aither_gpu_invert_diagonal(coarse) ||
+      aither_gpu_initialize_matrix_update(coarse))  // right-hand side b; x is replaced below
+    return 1;
+  // linearSolver::Restriction: volume-weighted update (ghosts zero), then its ghost swap
+  for (size_t bb = 0; bb < fine->blocks.size(); ++bb) {
+    HostBlock &f = fine->blocks[bb];
+    HostBlock &c = coarse->blocks[bb];
+    CK(cudaMemsetAsync(c.dev.x, 0, sizeof(double) * c.dev.fs * neq, coarse->stream));
+    const dim3 grid((c.dev.ni + 31) / 32, (c.dev.nj + 3) / 4, c.dev.nk);
+    RestrictKernel<<<grid, blk, 0, coarse->stream>>>(f.dev, c.dev, f.dChildren, f.dVolFac, f.dev.x,
+                                                     c.dev.x, neq, false);
+  }
+  CK(cudaGetLastError());
+  // A x - b of the coarse level with the restricted update (no sweeps: swap + matrix residual)
+  double unused = 0.0;
+  if (aither_gpu_relax(coarse, 0, &unused)) return 1;
+  for (size_t bb = 0; bb < fine->blocks.size(); ++bb) {
+    HostBlock &f = fine->blocks[bb];
+    HostBlock &c = coarse->blocks[bb];
+    const dim3 grid((c.dev.ni + 31) / 32, (c.dev.nj + 3) / 4, c.dev.nk);
+    ForcingKernel<<<grid, blk, 0, coarse->stream>>>(f.dev, c.dev, f.dChildren, neq);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(coarse->stream));
+  return 0;
+}
+
+int aither_gpu_mg_save_update(aither_gpu *h) {
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  for (auto &hb : h->blocks) {
+    const size_t bytes = sizeof(double) * hb.dev.fs * h->neq;
+    if (!hb.dSavedX) CK(cudaMalloc(&hb.dSavedX, bytes));
+    CK(cudaMemcpyAsync(hb.dSavedX, hb.dev.x, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return 0;
+}
+
+int aither_gpu_mg_subtract_saved(aither_gpu *h) {
+  // linearSolver::SubtractFromUpdate (ref: src/linearSolver.cpp:195-201)
+  if (!h) return Fail("null handle");
+  CK(cudaSetDevice(h->device));
+  for (auto &hb : h->blocks) {
+    if (!hb.dSavedX) return Fail("aither_gpu_mg_save_update has not been called");
+    AxpyFieldKernel<<<148 * 4, 256, 0, h->stream>>>(hb.dev.x, hb.dSavedX, -1.0,
+                                                   static_cast<long long>(hb.dev.fs) * h->neq);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int aither_gpu_mg_prolong(aither_gpu *coarse, aither_gpu *fine) {
+  // gridLevel::Prolongation (ref: src/gridLevel.cpp:594-611)
+  if (MgCheckPair(fine, coarse)) return 1;
+  CK(cudaSetDevice(fine->device));
+  CK(cudaStreamSynchronize(coarse->stream));
+  const int neq = fine->neq;
+  for (size_t bb = 0; bb < fine->blocks.size(); ++bb) {
+    HostBlock &f = fine->blocks[bb];
+    HostBlock &c = coarse->blocks[bb];
+    const long long nn = static_cast<long long>(c.dev.ni + 1) * (c.dev.nj + 1) * (c.dev.nk + 1);
+    if (!c.dNodes) CK(cudaMalloc(&c.dNodes, sizeof(double) * nn * neq));
+    const dim3 blk(32, 4, 1);
+    const dim3 gridN((c.dev.ni + 1 + 31) / 32, (c.dev.nj + 1 + 3) / 4, c.dev.nk + 1);
+    NodeKernel<<<gridN, blk, 0, fine->stream>>>(c.dev, c.dev.x, c.dNodes, neq);
+    const dim3 gridF((f.dev.ni + 31) / 32, (f.dev.nj + 3) / 4, f.dev.nk);
+    ProlongKernel<<<gridF, blk, 0, fine->stream>>>(f.dev, c.dev, f.dToCoarse, f.dProlong, c.dNodes,
+                                                   f.dev.x, neq);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(fine->stream));
   return 0;
 }
 

@@ -303,6 +303,28 @@ int aither_gpu_comm_destroy(void *comm);
  * rank sends to other ranks per component per exchange; for reports and tests */
 int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells);
 
+/* ---- multigrid transfer operators between two levels ----------------------
+ * Every grid level is a handle of its own, created from the coarse blocks the reference builds
+ * once (gridLevel::Coarsen, setup). These calls replace gridLevel::Restriction / Prolongation
+ * (src/gridLevel.cpp:538-611) and linearSolver::SubtractFromUpdate (src/linearSolver.cpp:195-201);
+ * the cycle (mgSolution::CycleAtLevel, src/mgSolution.cpp:160-207) is composed by the caller from
+ * them and the per-level phase calls above, as the reference composes it from gridLevel methods.
+ *   set_transfer : maps of one block of the FINE level onto the next coarser level, in the
+ *                  reference's layouts -- toCoarse_ (nk nj ni 3 ints), volWeightFactor_ (nk nj ni),
+ *                  prolongCoeffs_ (nk nj ni 7) (include/gridLevel.hpp:56-58)
+ *   mg_restrict  : volume-weighted state -> coarse; coarse BCs, residual, time step, diagonal;
+ *                  volume-weighted update -> coarse; forcing = (A x - b) + summed fine matrix
+ *                  residual (of the fine level's last aither_gpu_relax), folded into the coarse
+ *                  right-hand side
+ *   mg_save_update / mg_subtract_saved : coarseDu = x before the coarse cycles, x -= coarseDu after
+ *   mg_prolong   : node-averaged trilinear interpolation of the coarse update, added to the fine */
+int aither_gpu_set_transfer(aither_gpu *fine, int blk, const int *toCoarse, const double *volFac,
+                            const double *prolongCoeffs);
+int aither_gpu_mg_restrict(aither_gpu *fine, aither_gpu *coarse, int mm, double cfl);
+int aither_gpu_mg_save_update(aither_gpu *h);
+int aither_gpu_mg_subtract_saved(aither_gpu *h);
+int aither_gpu_mg_prolong(aither_gpu *coarse, aither_gpu *fine);
+
 int aither_gpu_destroy(aither_gpu *h);
 const char *aither_gpu_last_error(void);
 const char *aither_gpu_version(void);
