@@ -172,6 +172,15 @@ CASES = {
     # coarse grid correction: volume-weighted restriction of state and update, summed matrix
     # residual as forcing, trilinear prolongation); regressionTests.py:325-337
     "transonicBump": dict(src="transonicBump", iters=100, full=(), edits={}, drop=("state@",)),
+    # multigrid beyond the shipped case: two blocks with an interblock connection on every level
+    # (AUSMPW+, LU-SGS, 2-level V cycle) and laminar viscous terms on the coarse level
+    # (viscousFlatPlate, LU-SGS, 2 levels)
+    "multiblockCylinder_mg2": dict(src="multiblockCylinder", iters=30, full=(),
+                                   edits={"multigridLevels": "2", "multigridCycle": "V"},
+                                   drop=("state@",)),
+    "viscousFlatPlate_mg2": dict(src="viscousFlatPlate", iters=30, full=(),
+                                 edits={"multigridLevels": "2", "multigridCycle": "V"},
+                                 drop=("state@",)),
     # two-block cylinder with interblock halo, AUSMPW+ (regressionTests.py:252-268)
     "multiblockCylinder": dict(src="multiblockCylinder", iters=100, full=(0, 1), edits={}),
     # RANS, reference regression case (regressionTests.py:364-381): k-omega Wilcox 2006, LU-SGS,

@@ -40,3 +40,24 @@ def test_gpu_transonic_bump_three_level_w_cycle():
     for e, gv in enumerate([2.6152e-02, 1.5984e-02, 9.6803e-03, None, 1.9215e-02]):
         if gv is not None:
             assert abs(norm[e] - gv) <= 0.01 * gv, (e, norm[e], gv)
+
+
+@pytest.mark.xfail(strict=False, reason="multigrid on the GPU has not been re-run on a B200 in its "
+                                        "final form (see profiles/r01r_multigrid_gpu.md)")
+@pytest.mark.parametrize("name", ["multiblockCylinder_mg2", "viscousFlatPlate_mg2"])
+def test_gpu_two_level_v_cycle(name):
+    """two-level V cycles: two blocks with an interblock connection on every level (LU-SGS),
+    and laminar viscous terms on the coarse level"""
+    import aither_b200
+    d = gc.load(name)
+    probs, transfers, cycle = refcase.multigrid_from_dump(d)
+    mg = aither_b200.Multigrid(probs, transfers, cycle)
+    href, mref, cfl = d["hist/residL2"], d["hist/matrixResid"], d["hist/cfl"]
+    for it in range(30):
+        mg.store_old_solution(it)
+        l2, _, mr = mg.iterate(float(cfl[it]))
+        scale = np.where(href[it] > 1e-20 * href[it].max(), href[it], np.inf)
+        err = float(np.max(np.abs(l2 - href[it]) / scale))
+        assert err <= 1e-9, (it, err, l2, href[it])
+        assert abs(mr - mref[it]) <= 1e-9 * abs(mref[it]) + 1e-12 * href[it].max(), (it, mr, mref[it])
+    mg.close()

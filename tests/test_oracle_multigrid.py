@@ -7,6 +7,7 @@ operators (volume-weighted restriction of state and update, summed matrix residu
 forcing term, node-averaged trilinear prolongation) and tests/oracle.py composes the
 full-approximation-storage cycle from them and the per-level phases."""
 import numpy as np
+import pytest
 
 import goldencheck as gc
 import oracle
@@ -40,6 +41,18 @@ def test_oracle_transonic_bump_three_level_w_cycle():
     for e, gv in enumerate([2.6152e-02, 1.5984e-02, 9.6803e-03, None, 1.9215e-02]):
         if gv is not None:
             assert abs(norm[e] - gv) <= 0.01 * gv, (e, norm[e], gv)
+
+
+@pytest.mark.parametrize("name", ["multiblockCylinder_mg2", "viscousFlatPlate_mg2"])
+def test_oracle_two_level_v_cycle(name):
+    """Multigrid beyond the shipped case (`multigridLevels: 2`, `multigridCycle: V` edits): two
+    blocks with an interblock connection on every level (AUSMPW+, LU-SGS: forcing term in the
+    forward / backward sweeps, ghost swap of the restricted update), and laminar viscous terms on
+    the coarse level (viscousFlatPlate, CFL 1e4)."""
+    d = gc.load(name)
+    assert int(d["cfg/multigridLevels"][0]) == 2 and int(d["cfg/mgCycleIndex"][0]) == 1
+    _, worst, worst_mr = run_multigrid(d, 30)
+    assert worst <= 1e-9 and worst_mr <= 1e-9, (worst, worst_mr)
 
 
 def test_multigrid_differs_from_single_grid():
