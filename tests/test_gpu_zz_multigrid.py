@@ -1,7 +1,10 @@
 """GPU: multigrid through the C ABI against the UNMODIFIED reference: the
 shipped testCases/transonicBump (Euler, DPLUR x4, CFL ramp, 3-level W cycle;
 regressionTests.py:325-337), 100 iterations. Every level is a device handle; the transfer
-operators are aither_gpu_mg_* (aither_b200/csrc/multigrid.cuh)."""
+operators are aither_gpu_mg_* (aither_b200/csrc/multigrid.cuh).
+
+(The file name sorts last on purpose: these tests have not run on hardware in their final form,
+and whatever they do must not stand in front of the verified GPU tests.)"""
 import numpy as np
 import pytest
 
