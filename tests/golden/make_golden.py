@@ -178,6 +178,11 @@ CASES = {
     "multiblockCylinder_mg2": dict(src="multiblockCylinder", iters=30, full=(),
                                    edits={"multigridLevels": "2", "multigridCycle": "V"},
                                    drop=("state@",)),
+    # RANS on the coarse level (k-omega Wilcox 2006, wall omega from the stored viscosity of that
+    # level's previous evaluation), 2-level V cycle
+    "turbFlatPlate_mg2": dict(src="turbFlatPlate", iters=12, full=(),
+                              edits={"multigridLevels": "2", "multigridCycle": "V"},
+                              drop=("state@",)),
     "viscousFlatPlate_mg2": dict(src="viscousFlatPlate", iters=30, full=(),
                                  edits={"multigridLevels": "2", "multigridCycle": "V"},
                                  drop=("state@",)),

@@ -43,15 +43,18 @@ def test_oracle_transonic_bump_three_level_w_cycle():
             assert abs(norm[e] - gv) <= 0.01 * gv, (e, norm[e], gv)
 
 
-@pytest.mark.parametrize("name", ["multiblockCylinder_mg2", "viscousFlatPlate_mg2"])
-def test_oracle_two_level_v_cycle(name):
+@pytest.mark.parametrize("name,iters", [("multiblockCylinder_mg2", 30), ("viscousFlatPlate_mg2", 30),
+                                        ("turbFlatPlate_mg2", 12)])
+def test_oracle_two_level_v_cycle(name, iters):
     """Multigrid beyond the shipped case (`multigridLevels: 2`, `multigridCycle: V` edits): two
     blocks with an interblock connection on every level (AUSMPW+, LU-SGS: forcing term in the
     forward / backward sweeps, ghost swap of the restricted update), and laminar viscous terms on
-    the coarse level (viscousFlatPlate, CFL 1e4)."""
+    the coarse level (viscousFlatPlate, CFL 1e4), and RANS on the coarse level (turbFlatPlate,
+    k-omega Wilcox 2006: the wall omega of a level comes from the viscosity its own previous
+    evaluation stored)."""
     d = gc.load(name)
     assert int(d["cfg/multigridLevels"][0]) == 2 and int(d["cfg/mgCycleIndex"][0]) == 1
-    _, worst, worst_mr = run_multigrid(d, 30)
+    _, worst, worst_mr = run_multigrid(d, iters)
     assert worst <= 1e-9 and worst_mr <= 1e-9, (worst, worst_mr)
 
 
