@@ -21,6 +21,8 @@
 #include "kernels.cuh"
 #include "march.cuh"
 #include "implicit_tma.cuh"
+#include "lusgs_wave.cuh"
+#include "lusgs_pencil.cuh"
 #include "viscous.cuh"
 
 using namespace aither;
@@ -96,6 +98,16 @@ struct HostBlock {
   // LU-SGS: the plane launches of one half sweep, captured once as a CUDA graph
   // [forward / backward][first sweep form / full Gauss-Seidel]
   cudaGraphExec_t lusgsGraph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  // LU-SGS as a persistent wavefront (lusgs_wave.cuh): pencil order (anti-diagonals of the
+  // (j, k) pencil lattice, sweep space) and the ticket + progress counters, built on first use
+  int2 *dWaveOrder = nullptr;
+  WaveSync *dWaveSync = nullptr;
+  int waveTJ = 0, waveTK = 0, waveNbJ = 0, wavePencils = 0;
+  size_t waveSyncBytes = 0;
+  // scalar LU-SGS (lusgs_pencil.cuh): array-of-structs workspaces, one ghost layer included --
+  // behind-side face areas for the forward / backward sweep (built once) and the per-iteration
+  // record of what does not depend on the update
+  double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr;
 };
 
 }  // namespace aither_host
@@ -160,6 +172,7 @@ struct aither_gpu {
   bool wallLaw = false;            // some viscous wall uses the wall law
   bool lusgsGraphs = true;         // AITHER_B200_LUSGS_GRAPH=0: plain launches (A/B)
   bool lusgsSplit = true;          // AITHER_B200_LUSGS_SPLIT=0: one thread per cell (A/B)
+  bool lusgsWave = true;           // AITHER_B200_LUSGS=planes: one launch per hyperplane (A/B)
   bool stateMovedSinceStore = false;
   int *dFlag = nullptr;            // set by PrepBlockKernel on a singular diagonal block
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
@@ -437,6 +450,95 @@ void LaunchBlockDiagInv(aither_gpu *h, HostBlock &hb) {
 #undef BDI
 }
 
+// pencil lattice of a block for the LU-SGS wavefront kernels: ticket order along anti-diagonals
+// and the ticket / progress counters
+int EnsureWaveLattice(aither_gpu *h, HostBlock &hb, int TJ, int TK) {
+  if (hb.waveTJ == TJ && hb.waveTK == TK) return 0;
+  const BlockDev &b = hb.dev;
+  const int nbJ = (b.nj + TJ - 1) / TJ, nbK = (b.nk + TK - 1) / TK;
+  std::vector<int2> order;
+  order.reserve(static_cast<size_t>(nbJ) * nbK);
+  for (int s = 0; s <= nbJ + nbK - 2; ++s)
+    for (int bk = std::max(0, s - (nbJ - 1)); bk <= std::min(s, nbK - 1); ++bk)
+      order.push_back(make_int2(s - bk, bk));
+  if (hb.dWaveOrder) cudaFree(hb.dWaveOrder);
+  if (hb.dWaveSync) cudaFree(hb.dWaveSync);
+  hb.dWaveOrder = nullptr;
+  hb.dWaveSync = nullptr;
+  hb.waveSyncBytes = sizeof(WaveSync) + sizeof(int) * order.size();
+  CK(cudaMalloc(&hb.dWaveOrder, sizeof(int2) * order.size()));
+  CK(cudaMalloc(&hb.dWaveSync, hb.waveSyncBytes));
+  CK(cudaMemcpyAsync(hb.dWaveOrder, order.data(), sizeof(int2) * order.size(),
+                     cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // `order` leaves scope
+  hb.waveTJ = TJ;
+  hb.waveTK = TK;
+  hb.waveNbJ = nbJ;
+  hb.wavePencils = static_cast<int>(order.size());
+  return 0;
+}
+
+// LU-SGS half sweep as one persistent wavefront launch, eight lanes per cell (lusgs_wave.cuh):
+// block matrices and approximateRoe off-diagonals
+template <int NS, int NT, int JAC>
+int LaunchLusgsWave(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
+  // 7 x 4 pencils: 224 + 32 = 256 threads, 255 registers
+  constexpr int TJ = 7, TK = 4;
+  const BlockDev &b = hb.dev;
+  if (EnsureWaveLattice(h, hb, TJ, TK)) return 1;
+  CK(cudaMemsetAsync(hb.dWaveSync, 0, hb.waveSyncBytes, h->stream));
+  const int grid = std::min(hb.wavePencils, 148);
+  if (forward)
+    LusgsWaveKernel<NS, NT, true, JAC, TJ, TK><<<grid, TJ * TK * 8 + 32, 0, h->stream>>>(
+        b, h->params, fullGS, hb.dWaveOrder, hb.wavePencils, hb.waveNbJ, hb.dWaveSync);
+  else
+    LusgsWaveKernel<NS, NT, false, JAC, TJ, TK><<<grid, TJ * TK * 8 + 32, 0, h->stream>>>(
+        b, h->params, fullGS, hb.dWaveOrder, hb.wavePencils, hb.waveNbJ, hb.dWaveSync);
+  return 0;
+}
+
+// scalar-diagonal LU-SGS (lusgs_pencil.cuh): per-iteration pack of the update-independent record,
+// then one persistent launch per half sweep
+template <int NS, int NT>
+struct PencilTile {
+  static constexpr int TJ = 8, TK = NS + 4 + NT > 7 ? 4 : 8;  // shared memory: 3 neq + 5 doubles per record
+};
+template <int NS, int NT>
+int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
+  using R = PencilRec<NS, NT>;
+  const BlockDev &b = hb.dev;
+  const long long n = static_cast<long long>(b.ni + 2) * (b.nj + 2) * (b.nk + 2);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  if (!hb.dWaveDyn) {
+    CK(cudaMalloc(&hb.dWaveGeoLo, sizeof(double) * R::GN * n));
+    CK(cudaMalloc(&hb.dWaveGeoHi, sizeof(double) * R::GN * n));
+    CK(cudaMalloc(&hb.dWaveDyn, sizeof(double) * R::DN * n));
+    ScopedLaunch sl(h, kFamLayout);
+    WaveGeoKernel<<<grid, 256, 0, h->stream>>>(b, h->cfg.isViscous, hb.dWaveGeoLo, hb.dWaveGeoHi);
+  }
+  ScopedLaunch sl(h, kFamLusgs);
+  WaveDynKernel<NS, NT><<<grid, 256, 0, h->stream>>>(b, h->params, hb.dWaveDyn);
+  return 0;
+}
+template <int NS, int NT>
+int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
+  constexpr int TJ = PencilTile<NS, NT>::TJ, TK = PencilTile<NS, NT>::TK;
+  constexpr int threads = ((TJ * TK + 2 * (TJ + TK) + 31) / 32) * 32 + 32;
+  const BlockDev &b = hb.dev;
+  if (EnsureWaveLattice(h, hb, TJ, TK)) return 1;
+  CK(cudaMemsetAsync(hb.dWaveSync, 0, hb.waveSyncBytes, h->stream));
+  const int grid = std::min(hb.wavePencils, 148 * 2);
+  if (forward)
+    LusgsPencilKernel<NS, NT, true, TJ, TK><<<grid, threads, 0, h->stream>>>(
+        b, h->params, fullGS, hb.dWaveDyn, hb.dWaveGeoLo, hb.dWaveOrder, hb.wavePencils,
+        hb.waveNbJ, hb.dWaveSync);
+  else
+    LusgsPencilKernel<NS, NT, false, TJ, TK><<<grid, threads, 0, h->stream>>>(
+        b, h->params, fullGS, hb.dWaveDyn, hb.dWaveGeoHi, hb.dWaveOrder, hb.wavePencils,
+        hb.waveNbJ, hb.dWaveSync);
+  return 0;
+}
+
 int ZeroResult(aither_gpu *h, int slot) {
   CK(cudaMemsetAsync(h->dResults + slot, 0, sizeof(IterResult), h->stream));
   return 0;
@@ -623,6 +725,11 @@ template <int NS, int NT, int JAC>
 int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
   constexpr bool kCell = NT > 0 || JAC != kJacScalar || NS > 1;  // cell-parallel implicit kernels
   const bool fullGSAlways = h->cfg.matrixRequiresInit != 0;
+  if constexpr (JAC == kJacScalar) {
+    if (h->cfg.solver != AITHER_SOLVER_DPLUR && h->lusgsWave && sweeps > 0)
+      for (auto &hb : h->blocks)
+        if (PackLusgsPencil<NS, NT>(h, hb)) return 1;
+  }
   for (int s = 0; s < sweeps; ++s) {
     if (SwapUpdate(h)) return 1;
     if (h->cfg.solver == AITHER_SOLVER_DPLUR) {
@@ -674,6 +781,10 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
           }
         };
         ScopedLaunch sl(h, kFamLusgs);  // one timing record per half sweep
+        if (h->lusgsWave) {
+          if constexpr (JAC == kJacScalar) return LaunchLusgsPencil<NS, NT>(h, hb, forward, fullGS);
+          else return LaunchLusgsWave<NS, NT, JAC>(h, hb, forward, fullGS);
+        }
         h->launches += last;
         h->famLaunches[kFamLusgs] += last;
         if (!h->lusgsGraphs) {
@@ -859,6 +970,11 @@ void FreeAll(aither_gpu *h) {
     for (auto &row : hb.lusgsGraph)
       for (auto &ex : row)
         if (ex) cudaGraphExecDestroy(ex);
+    if (hb.dWaveOrder) cudaFree(hb.dWaveOrder);
+    if (hb.dWaveSync) cudaFree(hb.dWaveSync);
+    if (hb.dWaveGeoLo) cudaFree(hb.dWaveGeoLo);
+    if (hb.dWaveGeoHi) cudaFree(hb.dWaveGeoHi);
+    if (hb.dWaveDyn) cudaFree(hb.dWaveDyn);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     if (hb.dWallVars) cudaFree(hb.dWallVars);
@@ -1032,6 +1148,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     h->lusgsGraphs = !(lg != nullptr && std::string(lg) == "0");
     const char *ls = getenv("AITHER_B200_LUSGS_SPLIT");
     h->lusgsSplit = !(ls != nullptr && std::string(ls) == "0");
+    const char *lw = getenv("AITHER_B200_LUSGS");
+    h->lusgsWave = !(lw != nullptr && std::string(lw) == "planes");
     const char *fp = getenv("AITHER_B200_FUSE_PREP");
     h->fusePrep = !(fp != nullptr && std::string(fp) == "0");
   }

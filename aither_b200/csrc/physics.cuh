@@ -290,6 +290,27 @@ AITHER_HD void ConsToPrim(const Gas &g, const double *c, double *s) {
 
 // state + conserved update -> new primitive state, with the reference's mass-fraction clip and
 // renormalisation; ref: include/primitive.hpp:206-231
+// second half of UpdatePrimWithCons: `c0` = PrimToCons of the old state (independent of the update,
+// so a wavefront sweep can form it before the neighbour's new update is known)
+template <int NS, int NT>
+AITHER_HD void UpdatePrimFromCons(const Gas &g, const double *c0, const double *du, double *out) {
+  using E = Eq<NS, NT>;
+  double c[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) c[e] = c0[e] + du[e];
+  const double rho = SpeciesSum<NS>(c);
+  double mf[NS];
+  double total = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    mf[q] = fmax(c[q] / rho, 0.0);
+    total += mf[q];
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) c[q] = rho * (mf[q] / total);
+  ConsToPrim<NS, NT>(g, c, out);
+}
+
 template <int NS, int NT>
 AITHER_HD void UpdatePrimWithCons(const Gas &g, const double *s, const double *du, double *out) {
   using E = Eq<NS, NT>;
@@ -950,9 +971,12 @@ AITHER_HD void MakeIngr(const Gas &g, const double *s, const double *du,
 // off-diagonal product of one neighbour from its ingredients and the shared face's area
 // `srExtra`: viscous part of the face spectral radius, |A| / dist * max(4/(3 rho), gamma/rho) *
 // scaling * mu / Pr of the neighbour (ref include/spectralRadius.hpp:126-151,180-200)
+// `srExtraT`: the same for the turbulence equations (turbModel::ViscousFaceSpectralRadius,
+// src/turbulence.cpp:513-527,796-808)
 template <int NS, int NT, typename LD>
 AITHER_HD void OffDiagFromIngr(LD ld, const double *fA, bool positive,
-                                                double *acc, double srExtra = 0.0) {
+                                                double *acc, double srExtra = 0.0,
+                                                double srExtraT = 0.0) {
   using E = Eq<NS, NT>;
   constexpr int neq = E::neq;
   // layout: [0,neq) s | neq H | neq+1 a | [neq+2, 2neq+2) du | [2neq+2, 3neq+2) sn | 3neq+2 Hn
@@ -994,8 +1018,25 @@ AITHER_HD void OffDiagFromIngr(LD ld, const double *fA, bool positive,
     const double srd = sr * ld(neq + 2 + E::ie);
     acc[E::ie] += positive ? fc + srd : fc - srd;
   }
-  // turbulence rows: flux change zeroed and the flow spectral radius does not act on them
-  // (ref src/fluxJacobian.cpp:146-149; the turbulence spectral radius is 0 for inviscid flow)
+  // turbulence rows: flux change zeroed (ref src/fluxJacobian.cpp:146-149); their own spectral
+  // radius 0.5 |A| |vn +- |vn|| + viscous part (src/turbulence.cpp:162-171,
+  // include/turbulence.hpp:308-329), as OffDiagScalar above
+  if (NT > 0) {
+    const double srT = (positive ? half * fabs(vo + fabs(vo)) : half * fabs(vo - fabs(vo))) + srExtraT;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const double srd = srT * ld(neq + 2 + E::it + t);
+      acc[E::it + t] += positive ? srd : 0.0 - srd;
+    }
+  }
+}
+
+// the update-dependent ingredients alone (updated primitive state and its enthalpy)
+template <int NS, int NT>
+AITHER_HD void MakeIngrDyn(const Gas &g, const double *s, const double *du, double *sn,
+                           double *Hn) {
+  double H, a;
+  MakeIngr<NS, NT>(g, s, du, &H, &a, sn, Hn);
 }
 
 // ---------------------------------------------------------------------------------------------
