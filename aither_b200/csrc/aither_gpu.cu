@@ -55,7 +55,7 @@ inline std::string &AitherLastError() {
 namespace aither_host {  // host-side types shared by every translation unit of the library
 enum Family {
   kFamBc = 0, kFamResidual, kFamPrep, kFamDplur, kFamLusgs, kFamAxmb, kFamUpdate, kFamStore,
-  kFamReduce, kFamHalo, kFamLayout, kFamViscGhost, kFamViscFlux, kNumFamilies
+  kFamReduce, kFamHalo, kFamLayout, kFamViscGhost, kFamViscFlux, kFamLusgsPack, kFamLusgsAhead, kNumFamilies
 };
 struct HostBlock {
   BlockDev dev;
@@ -107,7 +107,7 @@ struct HostBlock {
   // scalar LU-SGS (lusgs_pencil.cuh): array-of-structs workspaces, one ghost layer included --
   // behind-side face areas for the forward / backward sweep (built once) and the per-iteration
   // record of what does not depend on the update
-  double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr;
+  double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr, *dWaveAhead = nullptr;
 };
 
 }  // namespace aither_host
@@ -118,7 +118,8 @@ namespace {
 const char *kFamilyNames[kNumFamilies] = {"bc_ghost_fill", "residual", "dt_diag_init", "dplur_sweep",
                                           "lusgs_plane", "matrix_residual", "update_norms",
                                           "store_time_n", "reduce_finalize", "halo_pack_unpack",
-                                          "layout_convert", "viscous_ghosts_aux", "viscous_flux"};
+                                          "layout_convert", "viscous_ghosts_aux", "viscous_flux",
+                                          "lusgs_pack", "lusgs_ahead"};
 
 int Fail(const std::string &msg) {
   g_lastError = msg;
@@ -497,45 +498,94 @@ int LaunchLusgsWave(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   return 0;
 }
 
-// scalar-diagonal LU-SGS (lusgs_pencil.cuh): per-iteration pack of the update-independent record,
-// then one persistent launch per half sweep
-template <int NS, int NT>
-struct PencilTile {
-  static constexpr int TJ = 8, TK = NS + 4 + NT > 7 ? 4 : 8;  // shared memory: 3 neq + 5 doubles per record
-};
+// scalar-diagonal LU-SGS (lusgs_pencil.cuh): per-iteration pack of the update-independent record
+// into the plane-major workspace, then per half sweep the parallel ahead-sum pass and one
+// persistent wavefront launch
+PencilLattice LatticeOf(const HostBlock &hb) {
+  PencilLattice L;
+  L.nbJ = (hb.dev.nj + kPTJ - 1) / kPTJ;
+  L.nbK = (hb.dev.nk + kPTK - 1) / kPTK;
+  L.planesPer = hb.dev.ni + kPTJ + kPTK - 2;
+  return L;
+}
 template <int NS, int NT>
 int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
   using R = PencilRec<NS, NT>;
   const BlockDev &b = hb.dev;
-  const long long n = static_cast<long long>(b.ni + 2) * (b.nj + 2) * (b.nk + 2);
-  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  const PencilLattice L = LatticeOf(hb);
+  const long long slots = static_cast<long long>(L.nbJ) * L.nbK * L.planesPer * kPCells;
+  const dim3 grid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk), blk(32, 4, 1);
   if (!hb.dWaveDyn) {
-    CK(cudaMalloc(&hb.dWaveGeoLo, sizeof(double) * R::GN * n));
-    CK(cudaMalloc(&hb.dWaveGeoHi, sizeof(double) * R::GN * n));
-    CK(cudaMalloc(&hb.dWaveDyn, sizeof(double) * R::DN * n));
+    CK(cudaMalloc(&hb.dWaveGeoLo, sizeof(double) * R::GN * slots));
+    CK(cudaMalloc(&hb.dWaveGeoHi, sizeof(double) * R::GN * slots));
+    CK(cudaMalloc(&hb.dWaveDyn, sizeof(double) * R::DN * slots));
+    CK(cudaMalloc(&hb.dWaveAhead, sizeof(double) * R::AN * slots));
+    // slots of clipped pencils / fill planes are copied with their plane: keep them finite
+    CK(cudaMemsetAsync(hb.dWaveGeoLo, 0, sizeof(double) * R::GN * slots, h->stream));
+    CK(cudaMemsetAsync(hb.dWaveGeoHi, 0, sizeof(double) * R::GN * slots, h->stream));
+    CK(cudaMemsetAsync(hb.dWaveDyn, 0, sizeof(double) * R::DN * slots, h->stream));
+    CK(cudaMemsetAsync(hb.dWaveAhead, 0, sizeof(double) * R::AN * slots, h->stream));
     ScopedLaunch sl(h, kFamLayout);
-    WaveGeoKernel<<<grid, 256, 0, h->stream>>>(b, h->cfg.isViscous, hb.dWaveGeoLo, hb.dWaveGeoHi);
+    WaveGeoKernel<<<grid, blk, 0, h->stream>>>(b, L, h->cfg.isViscous, hb.dWaveGeoLo,
+                                               hb.dWaveGeoHi);
   }
-  ScopedLaunch sl(h, kFamLusgs);
-  WaveDynKernel<NS, NT><<<grid, 256, 0, h->stream>>>(b, h->params, hb.dWaveDyn);
+  ScopedLaunch sl(h, kFamLusgsPack);
+  WaveDynKernel<NS, NT><<<grid, blk, 0, h->stream>>>(b, h->params, L, hb.dWaveDyn);
   return 0;
 }
 template <int NS, int NT>
 int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
-  constexpr int TJ = PencilTile<NS, NT>::TJ, TK = PencilTile<NS, NT>::TK;
-  constexpr int threads = ((TJ * TK + 2 * (TJ + TK) + 31) / 32) * 32 + 32;
+  using C = PencilCfg<NS, NT>;
   const BlockDev &b = hb.dev;
-  if (EnsureWaveLattice(h, hb, TJ, TK)) return 1;
+  const PencilLattice L = LatticeOf(hb);
+  if (EnsureWaveLattice(h, hb, kPTJ, kPTK)) return 1;
   CK(cudaMemsetAsync(hb.dWaveSync, 0, hb.waveSyncBytes, h->stream));
-  const int grid = std::min(hb.wavePencils, 148 * 2);
+  const int grid = std::min(hb.wavePencils, 148);
+  auto fwd = LusgsPencilKernel<NS, NT, true>;
+  auto bwd = LusgsPencilKernel<NS, NT, false>;
+  static bool configured[16] = {false};  // per device and template instantiation
+  if (h->device < 16 && !configured[h->device]) {
+    CK(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            static_cast<int>(C::smemBytes)));
+    CK(cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            static_cast<int>(C::smemBytes)));
+    configured[h->device] = true;
+  }
+  static long long *dbg = nullptr;  // AITHER_B200_LUSGS_DBG=1: clock64 stamps of one thread block
+  static int dbgCount = 0;
+  if (getenv("AITHER_B200_LUSGS_DBG") && !dbg) cudaMalloc(&dbg, 8 * 8 * 32);
+  if (forward) {
+    fwd<<<grid, C::threads, C::smemBytes, h->stream>>>(b, h->params, L, fullGS, hb.dWaveDyn,
+                                                        hb.dWaveGeoLo, hb.dWaveAhead, hb.dWaveOrder,
+                                                        hb.wavePencils, hb.dWaveSync, dbg);
+    if (dbg && ++dbgCount == 6) {
+      long long hbuf[8 * 32];
+      cudaStreamSynchronize(h->stream);
+      cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+      for (int q = 0; q < 32; ++q)
+        fprintf(stderr, "plane %d: wait %lld compute %lld tail %lld barrier %lld period %lld\n", q + 64,
+                hbuf[q * 8 + 1] - hbuf[q * 8], hbuf[q * 8 + 2] - hbuf[q * 8 + 1],
+                hbuf[q * 8 + 3] - hbuf[q * 8 + 2], hbuf[q * 8 + 4] - hbuf[q * 8 + 3],
+                q > 0 ? hbuf[q * 8] - hbuf[(q - 1) * 8] : 0LL);
+    }
+  } else {
+    bwd<<<grid, C::threads, C::smemBytes, h->stream>>>(b, h->params, L, fullGS, hb.dWaveDyn,
+                                                        hb.dWaveGeoHi, hb.dWaveAhead, hb.dWaveOrder,
+                                                        hb.wavePencils, hb.dWaveSync, nullptr);
+  }
+  return 0;
+}
+// the ahead-side sums (old update) of a half sweep in one parallel pass, before the wavefront
+template <int NS, int NT>
+int LaunchLusgsAhead(aither_gpu *h, HostBlock &hb, bool forward) {
+  const BlockDev &b = hb.dev;
+  const PencilLattice L = LatticeOf(hb);
+  const dim3 agrid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk), ablk(32, 4, 1);
+  ScopedLaunch sa(h, kFamLusgsAhead);
   if (forward)
-    LusgsPencilKernel<NS, NT, true, TJ, TK><<<grid, threads, 0, h->stream>>>(
-        b, h->params, fullGS, hb.dWaveDyn, hb.dWaveGeoLo, hb.dWaveOrder, hb.wavePencils,
-        hb.waveNbJ, hb.dWaveSync);
+    LusgsAheadKernel<NS, NT, true><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
   else
-    LusgsPencilKernel<NS, NT, false, TJ, TK><<<grid, threads, 0, h->stream>>>(
-        b, h->params, fullGS, hb.dWaveDyn, hb.dWaveGeoHi, hb.dWaveOrder, hb.wavePencils,
-        hb.waveNbJ, hb.dWaveSync);
+    LusgsAheadKernel<NS, NT, false><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
   return 0;
 }
 
@@ -780,6 +830,9 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
             }
           }
         };
+        if constexpr (JAC == kJacScalar) {
+          if (h->lusgsWave && fullGS && LaunchLusgsAhead<NS, NT>(h, hb, forward)) return 1;
+        }
         ScopedLaunch sl(h, kFamLusgs);  // one timing record per half sweep
         if (h->lusgsWave) {
           if constexpr (JAC == kJacScalar) return LaunchLusgsPencil<NS, NT>(h, hb, forward, fullGS);
@@ -975,6 +1028,7 @@ void FreeAll(aither_gpu *h) {
     if (hb.dWaveGeoLo) cudaFree(hb.dWaveGeoLo);
     if (hb.dWaveGeoHi) cudaFree(hb.dWaveGeoHi);
     if (hb.dWaveDyn) cudaFree(hb.dWaveDyn);
+    if (hb.dWaveAhead) cudaFree(hb.dWaveAhead);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     if (hb.dWallVars) cudaFree(hb.dWallVars);
