@@ -52,6 +52,26 @@ inline std::string &AitherLastError() {
 }
 #define g_lastError AitherLastError()
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per device and
+// kernel (one slot array per call site / template instantiation), under a lock -- handles on
+// different GPUs may be created and driven from different host threads
+#include <mutex>
+inline std::mutex &AitherAttrMutex() {
+  static std::mutex m;
+  return m;
+}
+template <typename K>
+int EnsureSmemOptIn(K kern, size_t bytes, int device, bool (&done)[64]) {
+  std::lock_guard<std::mutex> lock(AitherAttrMutex());
+  if (device < 0 || device >= 64) return 1;
+  if (done[device]) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(bytes)) != cudaSuccess)
+    return 1;
+  done[device] = true;
+  return 0;
+}
+
 namespace aither_host {  // host-side types shared by every translation unit of the library
 enum Family {
   kFamBc = 0, kFamResidual, kFamPrep, kFamDplur, kFamLusgs, kFamAxmb, kFamUpdate, kFamStore,
@@ -324,6 +344,12 @@ bool Supported(const aither_cfg &c, std::string *why) {
     return false;
   }
   if (c.numGhosts < 1 || c.numGhosts > 3) { *why = "numGhosts must be 1..3"; return false; }
+  {
+    // the reconstruction stencil must fit the ghost shell (ref: src/input.cpp:1127-1144)
+    const int need = c.recon == AITHER_RECON_CONSTANT ? 1 : (c.recon == AITHER_RECON_MUSCL ? 2 : 3);
+    if (c.numGhosts < need) { *why = "numGhosts is smaller than the stencil of the face reconstruction (constant 1, MUSCL 2, WENO 3)"; return false; }
+  }
+  if (c.numBCStates < 0 || c.numBCStates > AITHER_MAX_BC_STATES) { *why = "numBCStates must be 0.." + std::to_string(AITHER_MAX_BC_STATES); return false; }
   for (int q = 0; q < c.numBCStates; ++q) {
     if (c.bcStates[q].isWallLaw && c.isViscous && !c.isRANS && c.numSpecies > 1) {
       *why = "the wall law in a laminar run is built for one species";
@@ -351,12 +377,8 @@ void LaunchResidualOne(aither_gpu *h, HostBlock &hb, int implicitScalar, int fus
     return;
   } else {
   auto kern = ResidualMarchKernel<NS, NT, RC, LM, FX>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(S::bytes));
-    configured = true;
-  }
+  static bool configured[64] = {false};  // per template instantiation and device
+  EnsureSmemOptIn(kern, S::bytes, h->device, configured);
   kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), S::bytes, h->stream>>>(hb.dev, h->params, hb.kChunk,
                                                                  implicitScalar, fusePrep, cfl);
   }
@@ -393,12 +415,8 @@ void LaunchImplicitMarch(aither_gpu *h, HostBlock &hb, const double *xin, double
                          int storeField) {
   constexpr size_t bytes = sizeof(double) * 2 * Ingr<NS, NT>::n * kIPC;
   auto kern = ImplicitMarchKernel<NS, NT, MODE>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(bytes));
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  EnsureSmemOptIn(kern, bytes, h->device, configured);
   kern<<<hb.marchGrid, dim3(kMI, kMJ, 1), bytes, h->stream>>>(hb.dev, h->params, xin, xout,
                                                              hb.kChunk, h->dPartials, storeField);
 }
@@ -408,12 +426,8 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
                        int storeField) {
   using T = ImplTma<NS, NT>;
   auto kern = ImplicitTmaKernel<NS, NT, MODE>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(T::bytes));
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  EnsureSmemOptIn(kern, T::bytes, h->device, configured);
   const BlockDev &b = hb.dev;
   const double *base = static_cast<const double *>(hb.alloc);
   const int fX = static_cast<int>((xin - base) / b.fs);
@@ -543,14 +557,10 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   const int grid = std::min(hb.wavePencils, 148);
   auto fwd = LusgsPencilKernel<NS, NT, true>;
   auto bwd = LusgsPencilKernel<NS, NT, false>;
-  static bool configured[16] = {false};  // per device and template instantiation
-  if (h->device < 16 && !configured[h->device]) {
-    CK(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            static_cast<int>(C::smemBytes)));
-    CK(cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            static_cast<int>(C::smemBytes)));
-    configured[h->device] = true;
-  }
+  static bool cfgF[64] = {false}, cfgB[64] = {false};  // per device and template instantiation
+  if (EnsureSmemOptIn(fwd, C::smemBytes, h->device, cfgF) ||
+      EnsureSmemOptIn(bwd, C::smemBytes, h->device, cfgB))
+    return Fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the LU-SGS wavefront");
   static long long *dbg = nullptr;  // AITHER_B200_LUSGS_DBG=1: clock64 stamps of one thread block
   static int dbgCount = 0;
   if (getenv("AITHER_B200_LUSGS_DBG") && !dbg) cudaMalloc(&dbg, 8 * 8 * 32);
@@ -1926,6 +1936,7 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   if (UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g, -g,
                 -g))
     return 1;
+  h->stateMovedSinceStore = true;  // a U^n that was not materialised can no longer be
   if (h->nt > 0) {  // the wall omega BC reads the stored viscosity: make it the new state's
     EQ_DISPATCH(h, InitAuxT, h, blk);
     CK(cudaGetLastError());
@@ -1981,6 +1992,7 @@ int aither_gpu_upload_state_commit(aither_gpu *h) {
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->evConverted, h->stream));
+  h->stateMovedSinceStore = true;
   if (h->nt > 0) {
     EQ_DISPATCH(h, InitAuxT, h, blk);
     CK(cudaGetLastError());

@@ -35,16 +35,49 @@ def full_iterations(d):
     return sorted(int(k[2:].split("/")[0]) for k in d if k.startswith("it") and k.endswith("/cfl"))
 
 
-def rel(a, b):
-    """max |a-b| per trailing component relative to that component's max |b| over the block."""
+# Components that are rounding noise in a fixture (named explicitly, as the reference's own
+# regression suite does with SetIgnoreIndices, testCases/regressionTests.py): the out-of-plane
+# momentum of the 2-D cases -- every term of it is a difference of O(1) fluxes that cancel to the
+# last bit, so its value is 1e-16 of the other equations' and carries no information. They are
+# measured against the largest component's scale instead of their own. Everything else is held
+# to the bar relative to ITS OWN block maximum.
+def noise_equations(d, it=None):
+    """Equations of a fixture whose residual is rounding noise in the reference's own run: sum(R^2)
+    below 1e-20 of the largest equation's (amplitude 1e-10) -- at iteration `it`, or over the whole
+    dumped history. Every term of such an equation is a difference of O(1) fluxes that cancel to
+    the last bit (the out-of-plane momentum of a 2-D case; every equation but the wall-driven ones
+    at the first evaluation from a uniform state), so its value carries no information. For the
+    shipped cases the history-wide set is exactly what the reference's regression suite ignores
+    (REGRESSION_GOLDENS' None entries; tests/test_oracle_pinned.py::test_noise_equations...)."""
+    h = np.asarray(d["hist/residL2"], dtype=np.float64)
+    if it is not None:
+        h = h[it:it + 1]
+    top = h.max()
+    return tuple(int(e) for e in range(h.shape[1]) if h[:, e].max() <= 1e-20 * top)
+
+
+def rel(a, b, noise=(), scale=None, whole_field=False, groups=()):
+    """max |a-b| per trailing component relative to that component's OWN max |b| over the block
+    (or to `scale`, one value per component). Components listed in `noise` -- and every component
+    when `whole_field` (components of one vector / tensor: same units) -- are measured against the
+    largest component's scale; the components of each index list in `groups` (the velocity vector
+    inside the state) against the largest of the group."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64).reshape(a.shape)
     ax = tuple(range(a.ndim - 1))
-    scale = np.abs(b).max(axis=ax)
-    # a component that is rounding noise next to the others (the out-of-plane momentum of a 2-D
-    # case: 1e-22 noise against 1e-7; the reference's regression suite ignores that index too,
-    # testCases/regressionTests.py SetIgnoreIndices) is measured against the field's scale
-    scale = np.maximum(scale, 1e-2 * scale.max()) if scale.size else scale
+    own = np.abs(b).max(axis=ax)
+    scale = own if scale is None else np.maximum(own, np.asarray(scale, dtype=np.float64))
+    scale = np.array(scale, dtype=np.float64, copy=True)
+    if scale.size:
+        if whole_field:
+            scale[:] = scale.max()
+        for grp in groups:
+            grp = [c for c in grp if c < scale.size]
+            if grp:
+                scale[grp] = scale[grp].max()
+        for c in noise:
+            if c < scale.size:
+                scale[c] = scale.max()
     scale = np.where(scale > 0, scale, 1.0)
     return float((np.abs(a - b).max(axis=ax) / scale).max())
 
@@ -93,8 +126,20 @@ def check_phases(make_level, d, it, tol):
     out = {}
 
     viscous = bool(prob.cfg.isViscous)
+    # equations that are rounding noise at this iteration (named from the reference's own norms)
+    noise = noise_equations(d, it)
+    per_equation = (abi.FIELD_RESIDUAL, abi.FIELD_UPDATE, abi.FIELD_MATRIX_RESID)
+    # components of one vector / tensor share their units: measured against the field's magnitude
+    vector_fields = (abi.FIELD_VELOCITY_GRAD, abi.FIELD_TKE_GRAD, abi.FIELD_OMEGA_GRAD)
 
-    def cmp(field, key, what, mask_edges=False, inner=False, comps=None):
+    # the largest (root-mean-square) magnitude the residual of every equation reaches in the run:
+    # where an equation's residual is the rounding remainder of cancelling fluxes at this
+    # evaluation (first evaluation from a uniform state: turbFlatPlate's energy equation,
+    # sum R^2 = 7e-16 against 2e-7 five iterations later), its own maximum is not a scale
+    ncells = sum(int(np.prod(d["b%d/residual@%s" % (bb, tag)].shape[:3])) for bb in range(nb))
+    resid_scale = np.sqrt(np.asarray(d["hist/residL2"], dtype=np.float64).max(axis=0) / ncells)
+
+    def cmp(field, key, what, mask_edges=False, inner=False, comps=None, scale_key=None):
         worst = 0.0
         for bb in range(nb):
             a = lvl.field(bb, field)
@@ -110,7 +155,21 @@ def check_phases(make_level, d, it, tol):
                 a, b = a[m], b[m]
             if inner:
                 a, b = interior(a, g), interior(b, g)
-            worst = max(worst, rel(a, b))
+            scale = resid_scale if field == abi.FIELD_RESIDUAL else None
+            if scale_key is not None:  # per-equation scale of another dumped field of the block
+                sb = d["b%d/%s" % (bb, scale_key)]
+                scale = np.abs(sb.reshape(-1, sb.shape[-1])).max(axis=0)
+            # the three velocity components of the state are one vector (a 2-D case carries
+            # 1e-24 noise in the out-of-plane one)
+            ns = int(prob.cfg.numSpecies)
+            groups = ([ns, ns + 1, ns + 2],) if field == abi.FIELD_STATE and comps is None else ()
+            if field in (abi.FIELD_DIAG, abi.FIELD_DIAG_INV) and a.shape[-1] > 2:
+                # block matrices: the flow block and the turbulence block are each one operator,
+                # an entry is measured against the largest entry of its block
+                nfl = (ns + 4) * (ns + 4)
+                groups = (list(range(nfl)), list(range(nfl, a.shape[-1])))
+            worst = max(worst, rel(a, b, noise if field in per_equation else (), scale,
+                                   whole_field=field in vector_fields, groups=groups))
         out[what] = worst
         assert worst <= tol[what], "%s %s: rel err %.3e > %.1e" % (tag, what, worst, tol[what])
 
@@ -141,7 +200,9 @@ def check_phases(make_level, d, it, tol):
         cmp(abi.FIELD_UPDATE, "x0@" + tag, "x0", inner=True)
     lvl.relax()
     cmp(abi.FIELD_UPDATE, "x@" + tag, "x", inner=True)
-    cmp(abi.FIELD_MATRIX_RESID, "matrixResid@" + tag, "matrixResid")
+    # A x - b is a difference of terms of the size of b = -R / theta + ...: its rounding error
+    # scales with the residual of that equation, not with what is left of it after the sweeps
+    cmp(abi.FIELD_MATRIX_RESID, "matrixResid@" + tag, "matrixResid", scale_key="residual@" + tag)
     l2, linf = lvl.update_blocks()
     lvl.reset_diagonal()
     cmp(abi.FIELD_STATE, "state@%s.end" % tag, "state", inner=True)

@@ -56,3 +56,18 @@ def test_no_cpu_fallback_without_device():
     prob = synthetic.box_problem(8, 6, 4)
     with pytest.raises(aither_b200.AitherGpuError):
         aither_b200.GridLevel(prob)
+
+
+@pytest.mark.parametrize("field, value, needle", [
+    ("numBCStates", 33, "numBCStates"),       # bcStates[] holds AITHER_MAX_BC_STATES = 32 entries
+    ("numBCStates", -1, "numBCStates"),
+    ("numGhosts", 1, "stencil"),              # MUSCL needs two ghost layers (ref src/input.cpp:1127-1144)
+    ("numSpecies", 4, "numSpecies"),
+])
+def test_create_rejects_unsupported_configurations(field, value, needle):
+    """aither_gpu_create validates the configuration before it touches a device, so this runs on a
+    machine without a GPU: nothing unsupported is silently approximated or read out of bounds."""
+    prob = synthetic.box_problem(8, 6, 4)
+    setattr(prob.cfg, field, value)
+    with pytest.raises(aither_b200.AitherGpuError, match=needle):
+        aither_b200.GridLevel(prob)

@@ -28,13 +28,9 @@ def make_gpu_level(prob):
 
 
 def test_multiblock_cylinder_phases_match_reference():
-    # thin O-grid around the cylinder with strong stretching: the residual is a sum of cancelling
-    # fluxes and the CPU oracle, which follows the reference operation for operation, is itself
-    # 2.9e-13 from the reference here (tests/test_oracle_multiblock.py); the restructured device
-    # maths lands at 1.3e-12, so this one case is held to 2.5e-12 like subsonicCylinder
     d = gc.load("multiblockCylinder")
     for it in gc.full_iterations(d):
-        gc.check_phases(make_gpu_level, d, it, dict(TOL, residual=2.5e-12, ghosts=2.5e-12))
+        gc.check_phases(make_gpu_level, d, it, TOL)
 
 
 def test_multiblock_cylinder_history_matches_reference():

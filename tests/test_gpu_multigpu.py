@@ -17,7 +17,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("solver", ["dplur", "lusgs"])
+@pytest.mark.parametrize("solver", ["dplur", "lusgs", "viscous"])
 def test_two_ranks_match_one_rank_and_oracle(solver):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")

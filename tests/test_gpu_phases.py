@@ -50,6 +50,25 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(v) for v in c.values()))
 @pytest.mark.parametrize("dims", [(33, 9, 7), (16, 12, 10)], ids=lambda d: "x".join(map(str, d)))
 def test_phases_match_oracle(case, dims):
+    check_phases_against_oracle(case, dims)
+
+
+# 100 x 40 x 70: four 32 x 8 (residual march) / 32 x 16 (TMA sweep) tiles in i, three to five in
+# j, several k-chunks of both marching kernels, 13 x 10 LU-SGS pencils -- every tile / chunk /
+# pencil seam of the kernels against the oracle, not only against another GPU decomposition
+MULTI_TILE_CASES = [
+    dict(solver="dplur", sweeps=4, limiter="none", flux="roe", recon="thirdOrder"),
+    dict(solver="lusgs", sweeps=2, limiter="none", flux="roe", recon="thirdOrder"),
+    dict(solver="dplur", sweeps=2, limiter="vanAlbada", flux="ausm", recon="weno"),
+]
+
+
+@pytest.mark.parametrize("case", MULTI_TILE_CASES, ids=lambda c: "-".join(str(v) for v in c.values()))
+def test_phases_match_oracle_multi_tile(case):
+    check_phases_against_oracle(case, (100, 40, 70))
+
+
+def check_phases_against_oracle(case, dims):
     import aither_b200
     ni, nj, nk = dims
     prob = synthetic.box_problem(ni, nj, nk, seed=3, amplitude=0.02, **case)

@@ -28,8 +28,19 @@ def rel(a, b):
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(v) for v in c.values()))
 def test_viscous_phases_match_oracle(case):
+    check_viscous_phases(case, (18, 11, 9), 2e-5)
+
+
+def test_viscous_phases_match_oracle_multi_tile():
+    """BASELINE configs[3]'s scheme (WENO5 + 4th-order central viscous fluxes, DPLUR) on a
+    70 x 40 x 40 block: three tiles in i, five in j, several k-chunks of every kernel."""
+    check_viscous_phases(dict(solver="dplur", sweeps=2, recon="weno", limiter="none",
+                              visc_recon="centralFourth"), (70, 40, 40), 70 * 2e-6)
+
+
+def check_viscous_phases(case, dims, size):
     import aither_b200
-    prob = synthetic.box_problem(18, 11, 9, seed=21, amplitude=0.02, viscous=True, size=2e-5,
+    prob = synthetic.box_problem(*dims, seed=21, amplitude=0.02, viscous=True, size=size,
                                  **case)
     g = prob.cfg.numGhosts
     gpu, ref = aither_b200.GridLevel(prob), oracle.OracleLevel(prob)

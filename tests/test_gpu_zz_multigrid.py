@@ -3,8 +3,8 @@ shipped testCases/transonicBump (Euler, DPLUR x4, CFL ramp, 3-level W cycle;
 regressionTests.py:325-337), 100 iterations. Every level is a device handle; the transfer
 operators are aither_gpu_mg_* (aither_b200/csrc/multigrid.cuh).
 
-(The file name sorts last on purpose: these tests have not run on hardware in their final form,
-and whatever they do must not stand in front of the verified GPU tests.)"""
+Run on a B200 by the driver at the end of round 1 (GPUTEST_r01.json: all three passed) and
+again in round 2; a regression in aither_gpu_mg_* turns the suite red."""
 import numpy as np
 import pytest
 
@@ -14,15 +14,6 @@ import refcase
 pytestmark = pytest.mark.gpu
 
 
-# State of the evidence (profiles/r01r_multigrid_gpu.md): the one B200 run of this round, made
-# BEFORE the coarse levels accumulated their diagonal over the restrictions of one W cycle
-# (aither_gpu_mg_restrict, the reference's quirk), returned a first-iteration matrix residual of
-# 4.097511605788737e-06; the CPU oracle with that accumulation switched off returns
-# 4.097511605788731e-06 (the reference, and the oracle as committed: 4.0939659881952944e-06). The
-# accumulation was added after the GPU budget of the round was spent, so this test has not run
-# on hardware in its final form: non-strict xfail keeps the suite going either way.
-@pytest.mark.xfail(strict=False, reason="diagonal accumulation of the coarse levels not yet "
-                                        "re-run on a B200 (see profiles/r01r_multigrid_gpu.md)")
 def test_gpu_transonic_bump_three_level_w_cycle():
     import aither_b200
     d = gc.load("transonicBump")
@@ -45,18 +36,18 @@ def test_gpu_transonic_bump_three_level_w_cycle():
             assert abs(norm[e] - gv) <= 0.01 * gv, (e, norm[e], gv)
 
 
-@pytest.mark.xfail(strict=False, reason="multigrid on the GPU has not been re-run on a B200 in its "
-                                        "final form (see profiles/r01r_multigrid_gpu.md)")
-@pytest.mark.parametrize("name", ["multiblockCylinder_mg2", "viscousFlatPlate_mg2"])
-def test_gpu_two_level_v_cycle(name):
+@pytest.mark.parametrize("name,iters", [("multiblockCylinder_mg2", 30), ("viscousFlatPlate_mg2", 30),
+                                        ("turbFlatPlate_mg2", 12)])
+def test_gpu_two_level_v_cycle(name, iters):
     """two-level V cycles: two blocks with an interblock connection on every level (LU-SGS),
-    and laminar viscous terms on the coarse level"""
+    laminar viscous terms on the coarse level, and RANS on the coarse level (k-omega Wilcox 2006:
+    the wall omega of a level comes from the viscosity its own previous evaluation stored)"""
     import aither_b200
     d = gc.load(name)
     probs, transfers, cycle = refcase.multigrid_from_dump(d)
     mg = aither_b200.Multigrid(probs, transfers, cycle)
     href, mref, cfl = d["hist/residL2"], d["hist/matrixResid"], d["hist/cfl"]
-    for it in range(30):
+    for it in range(iters):
         mg.store_old_solution(it)
         l2, _, mr = mg.iterate(float(cfl[it]))
         scale = np.where(href[it] > 1e-20 * href[it].max(), href[it], np.inf)
