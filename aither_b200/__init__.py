@@ -15,7 +15,8 @@ from . import ctypes_abi as abi
 from .problem import Block, Problem, make_cfg  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaither_b200.so")
+# AITHER_B200_LIB: another build of the same library (bisect builds of scripts/build_bisect.sh)
+LIB_PATH = os.environ.get("AITHER_B200_LIB") or os.path.join(_HERE, "lib", "libaither_b200.so")
 _LIB = None
 
 # every symbol include/aither_gpu.h declares

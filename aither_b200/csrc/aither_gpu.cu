@@ -52,6 +52,21 @@ inline std::string &AitherLastError() {
 }
 #define g_lastError AitherLastError()
 
+// cuStreamWaitValue32 through the runtime's driver entry point (no link-time libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+inline StreamWaitValue32Fn StreamWaitValueFn() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    fn = reinterpret_cast<StreamWaitValue32Fn>(p);
+  return fn;
+}
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per device and
 // kernel (one slot array per call site / template instantiation), under a lock -- handles on
 // different GPUs may be created and driven from different host threads
@@ -114,6 +129,9 @@ struct HostBlock {
   dim3 tmaGrid;
   int tmaChunk = 1;
   int nTmaBlocks = 0;
+  // every tile id of the TMA sweep, the tiles next to a block face with a connection first
+  int *dTmaTiles = nullptr;
+  int nTmaBoundaryTiles = 0;
   int nFields = 0;
   // LU-SGS: the plane launches of one half sweep, captured once as a CUDA graph
   // [forward / backward][first sweep form / full Gauss-Seidel]
@@ -168,6 +186,11 @@ struct aither_gpu {
   std::vector<aither_conn> conns;
   HaloPlan halo;      // every connection with its tangential extension (the reference's swap)
   HaloPlan haloFace;  // ghost cells straight behind the patches only: one level
+  // ... and only the FIRST ghost layer: all that the implicit off-diagonals read of the update
+  // (nearest neighbours; ref src/procBlock.cpp:1056-1170). Half the bytes of haloFace for MUSCL,
+  // a third for WENO, on sweeps + 1 of the sweeps + 2 exchanges of an iteration.
+  HaloPlan haloUpdate;
+  bool updateOneLayer = true;  // AITHER_B200_HALO_LAYERS=all: exchange every ghost layer of the update (A/B)
   bool stateNeedsEdges = false;  // viscous stencils read the edge ghost cells of the state
   aither_bc_state *dBcStates = nullptr;
   double *dPartials = nullptr;    // per-thread-block partial sums
@@ -194,6 +217,16 @@ struct aither_gpu {
   bool lusgsGraphs = true;         // AITHER_B200_LUSGS_GRAPH=0: plain launches (A/B)
   bool lusgsSplit = true;          // AITHER_B200_LUSGS_SPLIT=0: one thread per cell (A/B)
   bool lusgsWave = true;           // AITHER_B200_LUSGS=planes: one launch per hyperplane (A/B)
+  // ghost exchanges run on their own high-priority stream, ordered against the compute stream with
+  // events; AITHER_B200_HALO_OVERLAP=1: the exchange of a DPLUR sweep's update runs beside the
+  // sweep's interior tiles (A/B; default: every exchange in program order of the compute stream)
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t evCompute = nullptr, evExchanged = nullptr;
+  bool haloOverlap = true;
+  // boundary tiles of the sweeps in flight bump this counter; the communication stream waits for
+  // it with a stream memory operation (cuStreamWaitValue32: no SM is held while waiting)
+  unsigned int *dHaloSignal = nullptr;
+  unsigned int haloTarget = 0;
   bool stateMovedSinceStore = false;
   int *dFlag = nullptr;            // set by PrepBlockKernel on a singular diagonal block
   bool legacyKernels = false;      // AITHER_B200_KERNELS=legacy: the first-generation kernels
@@ -214,18 +247,20 @@ struct ScopedLaunch {
   aither_gpu *h;
   int fam;
   cudaEvent_t a = nullptr, b = nullptr;
-  ScopedLaunch(aither_gpu *h_, int fam_) : h(h_), fam(fam_) {
+  cudaStream_t st;
+  ScopedLaunch(aither_gpu *h_, int fam_, cudaStream_t st_ = nullptr)
+      : h(h_), fam(fam_), st(st_ ? st_ : h_->stream) {
     h->launches++;
     h->famLaunches[fam]++;
     if (h->profile) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, h->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~ScopedLaunch() {
     if (h->profile) {
-      cudaEventRecord(b, h->stream);
+      cudaEventRecord(b, st);
       h->evs.push_back({a, b, fam});
     }
   }
@@ -421,9 +456,11 @@ void LaunchImplicitMarch(aither_gpu *h, HostBlock &hb, const double *xin, double
                                                              hb.kChunk, h->dPartials, storeField);
 }
 
+// `ordered`: one launch over the block's tile list (tiles next to a connected face first, each
+// signalling h->dHaloSignal when done) instead of the plain 3-D grid
 template <int NS, int NT, int MODE>
 void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *xout,
-                       int storeField) {
+                       int storeField, bool ordered = false) {
   using T = ImplTma<NS, NT>;
   auto kern = ImplicitTmaKernel<NS, NT, MODE>;
   static bool configured[64] = {false};
@@ -433,8 +470,15 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
   const int fX = static_cast<int>((xin - base) / b.fs);
   const int fAi = static_cast<int>((b.fA[0] - base) / b.fs);
   const int fAj = static_cast<int>((b.fA[1] - base) / b.fs);
-  kern<<<hb.tmaGrid, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
-      hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField);
+  if (!ordered) {
+    kern<<<hb.tmaGrid, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
+        hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField,
+        nullptr, 0, 0, 0, nullptr);
+    return;
+  }
+  kern<<<hb.nTmaBlocks, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
+      hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField,
+      hb.dTmaTiles, hb.tmaGrid.x, hb.tmaGrid.y, hb.nTmaBoundaryTiles, h->dHaloSignal);
 }
 
 template <int NS, int NT>
@@ -617,13 +661,16 @@ int EnsureResults(aither_gpu *h, int n) {
 }
 
 // ---- phases (all asynchronous on h->stream) ---------------------------------------------------
-int Exchange(aither_gpu *h, int which) {
+// The exchange itself, issued on the communication stream; the caller orders it against the
+// compute stream (ExchangeBegin / ExchangeEnd below).
+int ExchangeOnComm(aither_gpu *h, int which) {
   // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update),
   // src/procBlock.cpp:3064-3085 (eddy viscosity + f1 + f2: three contiguous fields; velocity gradient)
-  if (h->halo.nConn == 0) return 0;
   // only the state of viscous runs needs the edge ghost cells (Green-Gauss stencils); everything
   // else is read face-normal and takes the single-level plan
-  HaloPlan &plan = (which == kHaloState && h->stateNeedsEdges) ? h->halo : h->haloFace;
+  HaloPlan &plan = (which == kHaloState && h->stateNeedsEdges)
+                       ? h->halo
+                       : ((which == kHaloUpdate && h->updateOneLayer) ? h->haloUpdate : h->haloFace);
   const int total = which == kHaloTurb ? 3 : (which == kHaloVelGrad ? 9 : h->neq);
   for (int done = 0; done < total;) {
     const int nc = std::min(total - done, h->neq);  // the plan's buffers hold neq components
@@ -636,14 +683,32 @@ int Exchange(aither_gpu *h, int which) {
       f.base[bb] = base + static_cast<long long>(done) * b.fs;
       f.fs[bb] = b.fs;
     }
-    ScopedLaunch sl(h, kFamHalo);
+    ScopedLaunch sl(h, kFamHalo, h->commStream);
     h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
     h->famLaunches[kFamHalo]--;
-    if (HaloExchange(plan, f, nc, h->stream, &h->launches, &h->famLaunches[kFamHalo]))
+    if (HaloExchange(plan, f, nc, h->commStream, &h->launches, &h->famLaunches[kFamHalo]))
       return Fail(HaloError());
     done += nc;
   }
   return 0;
+}
+// what the exchange packs has been written by everything issued on the compute stream so far
+int ExchangeBegin(aither_gpu *h) {
+  CK(cudaEventRecord(h->evCompute, h->stream));
+  CK(cudaStreamWaitEvent(h->commStream, h->evCompute, 0));
+  return 0;
+}
+// ... and what is issued on the compute stream from here on sees the ghost cells it wrote
+int ExchangeEnd(aither_gpu *h) {
+  CK(cudaEventRecord(h->evExchanged, h->commStream));
+  CK(cudaStreamWaitEvent(h->stream, h->evExchanged, 0));
+  return 0;
+}
+// a ghost exchange in program order of the compute stream
+int Exchange(aither_gpu *h, int which) {
+  if (h->halo.nConn == 0) return 0;
+  if (ExchangeBegin(h) || ExchangeOnComm(h, which)) return 1;
+  return ExchangeEnd(h);
 }
 
 template <int NS, int NT>
@@ -790,7 +855,37 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
       for (auto &hb : h->blocks)
         if (PackLusgsPencil<NS, NT>(h, hb)) return 1;
   }
-  for (int s = 0; s < sweeps; ++s) {
+  // DPLUR with the TMA sweep and connections: every sweep runs the tiles next to a connected block
+  // face first; their part of the new update is then exchanged on the communication stream while
+  // the interior tiles are computed. The exchange after the last sweep is the one the matrix
+  // residual needs. (ref: the reference swaps, blocking, before every sweep: src/linearSolver.cpp:
+  // 190-193, src/utility.cpp:400-423 -- same data, same order, the wait is what moves.)
+  bool overlapped = false;
+  if constexpr (!kCell) {
+    overlapped = h->cfg.solver == AITHER_SOLVER_DPLUR && h->haloOverlap && h->tmaImplicit &&
+                 !h->legacyKernels && h->halo.nConn > 0 && sweeps > 0;
+    for (auto &hb : h->blocks) overlapped = overlapped && hb.dTmaTiles != nullptr;
+    if (overlapped) {
+      if (SwapUpdate(h)) return 1;  // ghost cells of x0
+      for (int s = 0; s < sweeps; ++s) {
+        for (auto &hb : h->blocks) {
+          ScopedLaunch sl(h, kFamDplur);
+          LaunchImplicitTma<NS, NT, kModeDplur>(h, hb, hb.dev.x, hb.dev.xalt, 0, true);
+          h->haloTarget += static_cast<unsigned int>(hb.nTmaBoundaryTiles);
+          std::swap(hb.dev.x, hb.dev.xalt);
+        }
+        // the exchange of the new update starts when every boundary tile of this sweep has
+        // signalled (the counter only grows: no reset, no ambiguity between sweeps) ...
+        if (StreamWaitValueFn()(h->commStream, reinterpret_cast<CUdeviceptr>(h->dHaloSignal),
+                                h->haloTarget, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+          return Fail("cuStreamWaitValue32 failed");
+        if (ExchangeOnComm(h, kHaloUpdate)) return 1;
+        if (ExchangeEnd(h)) return 1;  // ... and the next kernel on the compute stream waits for it
+      }
+      CK(cudaGetLastError());
+    }
+  }
+  for (int s = 0; s < sweeps && !overlapped; ++s) {
     if (SwapUpdate(h)) return 1;
     if (h->cfg.solver == AITHER_SOLVER_DPLUR) {
       for (auto &hb : h->blocks) {
@@ -874,7 +969,7 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
     }
   }
   CK(cudaGetLastError());
-  if (SwapUpdate(h)) return 1;
+  if (!overlapped && SwapUpdate(h)) return 1;
   // matrix residual and its norm (ref: src/linearSolver.cpp:92-109, src/mgSolution.cpp:198-206)
   for (auto &hb : h->blocks) {
     int nPartials = hb.nCellBlocks;
@@ -1033,6 +1128,7 @@ void FreeAll(aither_gpu *h) {
     for (auto &row : hb.lusgsGraph)
       for (auto &ex : row)
         if (ex) cudaGraphExecDestroy(ex);
+    if (hb.dTmaTiles) cudaFree(hb.dTmaTiles);
     if (hb.dWaveOrder) cudaFree(hb.dWaveOrder);
     if (hb.dWaveSync) cudaFree(hb.dWaveSync);
     if (hb.dWaveGeoLo) cudaFree(hb.dWaveGeoLo);
@@ -1055,6 +1151,7 @@ void FreeAll(aither_gpu *h) {
   }
   HaloDestroy(h->halo);
   HaloDestroy(h->haloFace);
+  HaloDestroy(h->haloUpdate);
   if (h->dBcStates) cudaFree(h->dBcStates);
   if (h->dFlag) cudaFree(h->dFlag);
   if (h->dPartials) cudaFree(h->dPartials);
@@ -1066,6 +1163,10 @@ void FreeAll(aither_gpu *h) {
   if (h->evCopied) cudaEventDestroy(h->evCopied);
   if (h->evConverted) cudaEventDestroy(h->evConverted);
   if (h->copyStream) cudaStreamDestroy(h->copyStream);
+  if (h->dHaloSignal) cudaFree(h->dHaloSignal);
+  if (h->evCompute) cudaEventDestroy(h->evCompute);
+  if (h->evExchanged) cudaEventDestroy(h->evExchanged);
+  if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->evStart) cudaEventDestroy(h->evStart);
   if (h->evStop) cudaEventDestroy(h->evStop);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1234,6 +1335,19 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     }                                                                  \
   } while (0)
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int prLow = 0, prHigh = 0;
+    CKC(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+    CKC(cudaStreamCreateWithPriority(&h->commStream, cudaStreamNonBlocking, prHigh));
+    CKC(cudaEventCreateWithFlags(&h->evCompute, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->evExchanged, cudaEventDisableTiming));
+    const char *ho = getenv("AITHER_B200_HALO_OVERLAP");
+    // opt-in: measured SLOWER on B200 (profiles/r02q): the sweep's 1024 tiles are 6.92 waves of
+    // 148 thread blocks, and every SM lent to the pack / NCCL / unpack kernels costs an eighth wave
+    h->haloOverlap = ho != nullptr && std::string(ho) == "1" && StreamWaitValueFn() != nullptr;
+    CKC(cudaMalloc(&h->dHaloSignal, sizeof(unsigned int)));
+    CKC(cudaMemset(h->dHaloSignal, 0, sizeof(unsigned int)));
+  }
   CKC(cudaEventCreate(&h->evStart));
   CKC(cudaEventCreate(&h->evStop));
   CKC(cudaMalloc(&h->dFlag, sizeof(int)));
@@ -1513,6 +1627,34 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
         return 1;
       }
     }
+    if (anyConn && h->tmaImplicit) {
+      // tiles of the TMA sweep that hold cells a connection donates (the g layers next to a block
+      // face with a connection patch; a face with any patch counts as a whole) -- computed first,
+      // so that their exchange overlaps with the remaining tiles
+      bool faceConn[6];
+      for (int sf = 0; sf < 6; ++sf)
+        faceConn[sf] = std::find(connMask[sf].begin(), connMask[sf].end(), 1) != connMask[sf].end();
+      const int ext[3] = {kQI, kQJ, hb.tmaChunk};
+      const int nt[3] = {static_cast<int>(hb.tmaGrid.x), static_cast<int>(hb.tmaGrid.y),
+                         static_cast<int>(hb.tmaGrid.z)};
+      std::vector<int> bnd, inner;
+      for (int tz = 0; tz < nt[2]; ++tz)
+        for (int ty = 0; ty < nt[1]; ++ty)
+          for (int tx = 0; tx < nt[0]; ++tx) {
+            const int t3[3] = {tx, ty, tz};
+            bool touches = false;
+            for (int q = 0; q < 3; ++q) {
+              const int lo = t3[q] * ext[q], hi = std::min(nd[q], lo + ext[q]);  // cells [lo, hi)
+              if (faceConn[2 * q] && lo < g) touches = true;
+              if (faceConn[2 * q + 1] && hi > nd[q] - g) touches = true;
+            }
+            (touches ? bnd : inner).push_back(tx + nt[0] * (ty + nt[1] * tz));
+          }
+      hb.nTmaBoundaryTiles = static_cast<int>(bnd.size());
+      bnd.insert(bnd.end(), inner.begin(), inner.end());
+      CKC(cudaMalloc(&hb.dTmaTiles, sizeof(int) * bnd.size()));
+      CKC(cudaMemcpy(hb.dTmaTiles, bnd.data(), sizeof(int) * bnd.size(), cudaMemcpyHostToDevice));
+    }
     maxCellBlocks = std::max<size_t>(
         maxCellBlocks, std::max<size_t>(std::max(hb.nCellBlocks, hb.nTmaBlocks),
                                         static_cast<size_t>(hb.cell128Grid.x) * hb.cell128Grid.y *
@@ -1530,9 +1672,14 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     const char *he = getenv("AITHER_B200_HALO_EDGES");  // A/B switch: 1 = always the full plan
     h->stateNeedsEdges = cfg->isViscous != 0 || h->nonreflecting ||
                          (he != nullptr && std::string(he) == "1");
+    const char *hl = getenv("AITHER_B200_HALO_LAYERS");
+    h->updateOneLayer = !(hl != nullptr && std::string(hl) == "all") &&
+                        !(he != nullptr && std::string(he) == "1");
     if (HaloBuild(h->halo, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm) ||
         HaloBuild(h->haloFace, h->conns, devs, gpos, neq, g, rank, nRanks, ncclComm,
-                  !(he != nullptr && std::string(he) == "1"))) {
+                  !(he != nullptr && std::string(he) == "1")) ||
+        (h->updateOneLayer &&
+         HaloBuild(h->haloUpdate, h->conns, devs, gpos, neq, 1, rank, nRanks, ncclComm, true))) {
       Fail(HaloError());
       FreeAll(h);
       return 1;

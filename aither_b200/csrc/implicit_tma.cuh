@@ -57,7 +57,9 @@ template <int NS, int NT, int MODE>
 __global__ void __launch_bounds__(kQThreads, 1)
     ImplicitTmaKernel(const __grid_constant__ ImplMaps maps, BlockDev b, Params p,
                       const double *__restrict__ xin, double *__restrict__ xout, int fX, int fAi,
-                      int fAj, int kChunk, double *__restrict__ partials, int storeField) {
+                      int fAj, int kChunk, double *__restrict__ partials, int storeField,
+                      const int *__restrict__ tiles = nullptr, int tilesX = 0, int tilesY = 0,
+                      int nSignal = 0, unsigned int *__restrict__ signal = nullptr) {
   using E = Eq<NS, NT>;
   using T = ImplTma<NS, NT>;
   constexpr int neq = E::neq;
@@ -67,8 +69,22 @@ __global__ void __launch_bounds__(kQThreads, 1)
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = tx + kQI * ty;
-  const int i0 = blockIdx.x * kQI, j0 = blockIdx.y * kQJ;
-  const int k0 = blockIdx.z * kChunk;
+  // which (column, k-chunk) this thread block works on: its own grid position, or an entry of a
+  // tile list (linear tile id = x + X (y + Y z)). The list puts the tiles next to a connected
+  // block face first; each of those first `nSignal` thread blocks bumps `signal` when its part of
+  // the new update is in memory, and the ghost exchange -- waiting on that counter on another
+  // stream -- runs while the remaining tiles are computed.
+  int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, gx = gridDim.x, gy = gridDim.y;
+  if (tiles != nullptr) {
+    const int t = __ldg(tiles + blockIdx.x);
+    gx = tilesX;
+    gy = tilesY;
+    bx = t % gx;
+    by = (t / gx) % gy;
+    bz = t / (gx * gy);
+  }
+  const int i0 = bx * kQI, j0 = by * kQJ;
+  const int k0 = bz * kChunk;
   const int k1 = min(k0 + kChunk, b.nk);
   const int i = i0 + tx, j = j0 + ty;
   const bool colValid = i < b.ni && j < b.nj;
@@ -294,8 +310,15 @@ __global__ void __launch_bounds__(kQThreads, 1)
     if (tid == 0 && it + 2 < nIter) issue(it + 2);
   }
   if (MODE == kModeAxmb) {
-    const int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int blockLinear = bx + gx * (by + gy * bz);
     BlockSumToPartials<1>(&sq, partials, blockLinear, tid, kQThreads);
+  }
+  if (signal != nullptr && static_cast<int>(blockIdx.x) < nSignal) {
+    __syncthreads();  // every thread's stores of this tile are issued
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(signal, 1u);
+    }
   }
 }
 

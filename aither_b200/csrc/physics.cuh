@@ -140,8 +140,11 @@ inline void GasFinalize(Gas *g) {
 // samples, profiles/r01c_*); this is the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton
 // steps: 5 instructions, no branch, <= 1 ulp for normal-range arguments (all we feed it:
 // densities, 1 + sqrt(rho_R / rho_L), a^2, eps + slope). Host builds (tests/hostsim) divide.
+// Bisect builds (scripts/build_bisect.sh; never shipped): AITHER_BISECT_EXACT_RCP = IEEE division
+// here, AITHER_BISECT_REF_ROE = the reference-order Roe flux in the marching residual kernel,
+// AITHER_BISECT_MUSCL_DIV = MUSCL through the ratio r as the reference forms it.
 AITHER_HD double FastRcp(double x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(AITHER_BISECT_EXACT_RCP)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   y = fma(y, fma(-x, y, 1.0), y);
@@ -350,7 +353,7 @@ template <int LIM>
 AITHER_HD double Muscl1(double u2, double u1, double d1, double kappa, double dPlus,
                         double dMinus) {
   const double dm = (u1 - u2) * dMinus;
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(AITHER_BISECT_MUSCL_DIV)
   if (LIM == AITHER_LIMITER_NONE) {
     // Without a limiter the ratio r only appears as dm * r = dm (eps + dp) / (eps + dm), which is
     // dp to within eps / |dm| = 1e-30 / |dm| relative (|dm| is 0 or at least an ulp of the
@@ -903,7 +906,11 @@ AITHER_HD void RoeFluxFast(const Gas &g, const double *l, const double *r,
 template <int NS, int NT, int FLUX>
 AITHER_HD void InviscidFluxFast(const Gas &g, const double *l, const double *r,
                                                  const double *n, double *f) {
+#ifdef AITHER_BISECT_REF_ROE
+  if (FLUX == AITHER_FLUX_ROE) RoeFlux<NS, NT>(g, l, r, n, f);
+#else
   if (FLUX == AITHER_FLUX_ROE) RoeFluxFast<NS, NT>(g, l, r, n, f);
+#endif
   else AusmFlux<NS, NT>(g, l, r, n, f);
 }
 

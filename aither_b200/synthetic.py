@@ -405,17 +405,19 @@ def lattice_connections(dims, splits):
 def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="none", flux="roe",
                     recon="thirdOrder", seed=0, amplitude=0.01, viscous=False,
                     visc_recon="central", size=1.0):
-    """A pi x pj x pk lattice of n^3-cell blocks (each a unit cube of the warped box, so every block
-    is the benchmark's block) joined by `interblock` connections -- the weak-scaling workload.
+    """A pi x pj x pk lattice of blocks of n^3 cells (or n = (ni, nj, nk) cells; each block is one
+    period of the warped box, so every block is the benchmark's block) joined by `interblock`
+    connections -- the weak-scaling workload.
     `only`: block ids to materialise (default all); the others are dimension-only placeholders so
     that a rank builds just the blocks it owns. Each block's ghost geometry on a joined face is its
     neighbour's real geometry: the block's nodes are generated g cells beyond those faces from the
     same analytic node function, metrics computed, and the extra layers cropped.
     `viscous`: laminar Navier-Stokes with an adiabatic viscous wall on the lattice's j-lo side
     (BASELINE configs[3]'s scheme with recon="weno", visc_recon="centralFourth"); `size`: edge
-    length of one block in metres."""
+    length of one block along i in metres (cells are cubes of size / ni)."""
     pi, pj, pk = splits
     nb = pi * pj * pk
+    nn = (n, n, n) if np.isscalar(n) else tuple(int(v) for v in n)
     g = {"constant": 1, "weno": 3, "wenoZ": 3}.get(recon, 2)
     fluid = nondim.air(REF_RHO, REF_T)
     free = nondim.nondim_primitive(IC["density"], IC["velocity"], IC["pressure"], REF_RHO, REF_T)
@@ -428,6 +430,7 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
                            recon=recon, bc_states=bc_states, viscous=viscous,
                            visc_recon=visc_recon)
     want = set(range(nb) if only is None else only)
+    h = size / nn[0]
     blocks = []
     for bid in range(nb):
         a, b, c = bid % pi, (bid // pi) % pj, bid // (pi * pj)
@@ -437,8 +440,8 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
         for d3 in range(3):
             for upper in (0, 1):
                 st = 2 * d3 + 1 + upper
-                rng = [[0, n], [0, n], [0, n]]
-                rng[d3] = [n, n] if upper else [0, 0]
+                rng = [[0, nn[0]], [0, nn[1]], [0, nn[2]]]
+                rng[d3] = [nn[d3], nn[d3]] if upper else [0, 0]
                 at_edge = pos[d3] == (splits[d3] - 1 if upper else 0)
                 if at_edge:
                     t, tag = (abi.BC_CHARACTERISTIC, 1) if d3 == 0 else (abi.BC_SLIP_WALL, 0)
@@ -454,11 +457,10 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
                                  rng[2][1], tag))
         arrays = {"state": None}
         if bid in want:
-            ne = [n + ext_lo[d] + ext_hi[d] for d in range(3)]
-            h = size / n
+            ne = [nn[d] + ext_lo[d] + ext_hi[d] for d in range(3)]
             nodes = box_nodes(ne[0], ne[1], ne[2],
                               lengths=tuple(ne[d] * h for d in range(3)),
-                              origin=tuple(pos[d] * size - ext_lo[d] * h for d in range(3)),
+                              origin=tuple(pos[d] * nn[d] * h - ext_lo[d] * h for d in range(3)),
                               warp=0.02 * size, period=size)
             m = block_metrics(nodes, g)
             arrays = {}
@@ -468,12 +470,14 @@ def lattice_problem(n, splits, *, only=None, solver="dplur", sweeps=4, limiter="
                 sl = []
                 for ax, d in ((0, 2), (1, 1), (2, 0)):
                     extra = 1 if name == "fArea" + "IJK"[d] else 0
-                    sl.append(slice(ext_lo[d], ext_lo[d] + n + 2 * g + extra))
+                    sl.append(slice(ext_lo[d], ext_lo[d] + nn[d] + 2 * g + extra))
                 arrays[name] = np.ascontiguousarray(arr[tuple(sl)])
-            arrays["state"] = perturbed_state((n + 2 * g,) * 3, 5, seed + bid, amplitude)
+            del m
+            arrays["state"] = perturbed_state((nn[2] + 2 * g, nn[1] + 2 * g, nn[0] + 2 * g), 5,
+                                              seed + bid, amplitude)
             arrays["wallDist"] = None
-        blocks.append(Block(n, n, n, surfaces, arrays, parent_block=bid, global_pos=bid))
-    conns = lattice_connections([(n, n, n)] * nb, splits)
+        blocks.append(Block(nn[0], nn[1], nn[2], surfaces, arrays, parent_block=bid, global_pos=bid))
+    conns = lattice_connections([nn] * nb, splits)
     return Problem(cfg, blocks, conns)
 
 

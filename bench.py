@@ -234,6 +234,74 @@ def workload_config(n=256, n_cells_note=None, gpus=1, recon="thirdOrder", viscou
     return cfg
 
 
+def measure_configs3(args, rank, world, local, comm, dist):
+    """BASELINE configs[3]'s block and scheme on every GPU of the run: one 512 x 256 x 256 block per
+    GPU (the config's 1024 x 512 x 512 grid is eight of them), WENO5 + 4th-order central viscous
+    fluxes, DPLUR, ghost layers exchanged over NCCL with the reference-order (multi-level) plan for
+    the state; and the same block alone on this GPU (its joined faces turned into slip walls) as
+    the 1-GPU time of the same run. Device time, max over ranks. AITHER_BENCH_CONFIGS3_DIMS=ni,nj,nk
+    overrides the block size (tests)."""
+    import aither_b200
+    from aither_b200 import ctypes_abi as abi
+    from aither_b200 import synthetic
+    from aither_b200.problem import Block, Problem
+    dims = tuple(int(v) for v in os.environ.get("AITHER_BENCH_CONFIGS3_DIMS", "512,256,256").split(","))
+    splits = LATTICE[world]
+    t0 = time.perf_counter()
+    prob = synthetic.lattice_problem(dims, splits, only=[rank], solver="dplur", sweeps=SWEEPS,
+                                     recon="weno", viscous=True, visc_recon="centralFourth",
+                                     size=dims[0] * 2e-6)
+    synthetic.assign_ranks(prob, world)
+    setup_s = time.perf_counter() - t0
+    cells = dims[0] * dims[1] * dims[2]
+
+    def timed(lvl):
+        def barrier():
+            lvl.synchronize()
+            dist.barrier()
+            lvl.synchronize()
+        lvl.run(args.warmup, CFL)
+        lvl.profile_enable(True)
+        barrier()
+        lvl.timer_start()
+        hist = lvl.run(args.steps, CFL)
+        ms = lvl.timer_stop()
+        barrier()
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        prof = lvl.profile()
+        lvl.profile_enable(False)
+        assert np.isfinite(hist).all(), "non-finite residual history (configs3)"
+        return float(t.item()) / args.steps, prof
+
+    lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world, block_ids=[rank],
+                                nccl_comm=comm)
+    ms_n, prof_n = timed(lvl)
+    lvl.close()
+    mine = prob.blocks[rank]
+    alone = [(abi.BC_SLIP_WALL, *sf[1:7], 0) if sf[0] == abi.BC_INTERBLOCK else sf
+             for sf in mine.surfaces]
+    prob1 = Problem(prob.cfg, [Block(mine.ni, mine.nj, mine.nk, alone, mine.arrays,
+                                     parent_block=0, global_pos=0)], [])
+    lvl1 = aither_b200.GridLevel(prob1, device=local)
+    ms_1, prof_1 = timed(lvl1)
+    lvl1.close()
+    return {
+        "workload": "one %d x %d x %d block per GPU (BASELINE configs[3]: 1024 x 512 x 512 = 8 of "
+                    "them), laminar viscous (centralFourth) Roe+WENO5, implicit Euler, DPLUR x%d, "
+                    "CFL %g; %dx%dx%d lattice, state exchanged with the reference-order multi-level "
+                    "plan" % (*dims, SWEEPS, CFL, *splits),
+        "cells_per_gpu": cells, "n_gpus": world,
+        "ms_per_step": ms_n, "value": cells * world / (ms_n * 1e-3) / 1e6, "unit": "Mcell-iter/s",
+        "ms_per_step_1gpu_same_run": ms_1, "value_1gpu_same_run": cells / (ms_1 * 1e-3) / 1e6,
+        "exchange_ms_per_step": prof_n.get("halo_pack_unpack", (0.0, 0))[0] / args.steps,
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof_n.items() if v[1]},
+        "kernel_ms_per_step_1gpu": {k: round(v[0] / args.steps, 4) for k, v in prof_1.items() if v[1]},
+        "setup_s": round(setup_s, 1),
+    }
+
+
 # ------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
     import aither_b200
@@ -357,8 +425,12 @@ def run_gpu_arm(args):
     # a round trip that also brings the state back to the host (output / restart iterations)
     lvl.download_state_into(0, host_state)
 
+    lvl.close()
+    configs3 = None
+    if world > 1 and args.recon == "thirdOrder" and not args.viscous and not args.no_configs3:
+        configs3 = measure_configs3(args, rank, world, local, comm, dist)
+
     def shutdown():
-        lvl.close()
         if comm is not None:
             from aither_b200 import distributed as adist
             adist.destroy_comm(comm)
@@ -422,8 +494,12 @@ def run_gpu_arm(args):
         "roofline_iteration": {"bytes_per_cell_iter": bpc, "achieved": iter_gbs,
                                "frac": iter_gbs / peak, "unit": "GB/s"},
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]},
+        # ghost-layer exchanges of one iteration (pack + ncclSend/ncclRecv + unpack, device time)
+        "exchange_ms_per_step": round(prof.get("halo_pack_unpack", (0.0, 0))[0] / args.steps, 4),
         "setup_s": round(t_setup, 1),
     }
+    if configs3 is not None:
+        line["configs3"] = configs3
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
@@ -445,6 +521,9 @@ def main():
                     help="cells per side of the block (256); use --cells under torchrun, whose own "
                          "parser treats --n as an abbreviation")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-configs3", action="store_true",
+                    help="N > 1: skip the BASELINE configs[3] block (512 x 256 x 256 WENO5 + viscous "
+                         "per GPU) that is measured after the headline workload")
     ap.add_argument("--recon", default="thirdOrder",
                     help="face reconstruction of the workload (default thirdOrder = the headline "
                          "config; weno = the inviscid half of BASELINE configs[3])")
