@@ -663,7 +663,8 @@ int EnsureResults(aither_gpu *h, int n) {
 // ---- phases (all asynchronous on h->stream) ---------------------------------------------------
 // The exchange itself, issued on the communication stream; the caller orders it against the
 // compute stream (ExchangeBegin / ExchangeEnd below).
-int ExchangeOnComm(aither_gpu *h, int which) {
+int ExchangeOnComm(aither_gpu *h, int which, cudaStream_t st = nullptr) {
+  if (st == nullptr) st = h->commStream;
   // ref: src/gridLevel.cpp:297-312 (state), src/utility.cpp:400-423 (implicit update),
   // src/procBlock.cpp:3064-3085 (eddy viscosity + f1 + f2: three contiguous fields; velocity gradient)
   // only the state of viscous runs needs the edge ghost cells (Green-Gauss stencils); everything
@@ -683,10 +684,10 @@ int ExchangeOnComm(aither_gpu *h, int which) {
       f.base[bb] = base + static_cast<long long>(done) * b.fs;
       f.fs[bb] = b.fs;
     }
-    ScopedLaunch sl(h, kFamHalo, h->commStream);
+    ScopedLaunch sl(h, kFamHalo, st);
     h->launches--;  // ScopedLaunch counts one; the exchange counts its own kernels below
     h->famLaunches[kFamHalo]--;
-    if (HaloExchange(plan, f, nc, h->commStream, &h->launches, &h->famLaunches[kFamHalo]))
+    if (HaloExchange(plan, f, nc, st, &h->launches, &h->famLaunches[kFamHalo]))
       return Fail(HaloError());
     done += nc;
   }
@@ -704,9 +705,11 @@ int ExchangeEnd(aither_gpu *h) {
   CK(cudaStreamWaitEvent(h->stream, h->evExchanged, 0));
   return 0;
 }
-// a ghost exchange in program order of the compute stream
+// a ghost exchange in program order of the compute stream (on the compute stream itself unless
+// the overlapped sweeps use the communication stream: NCCL wants one stream per communicator)
 int Exchange(aither_gpu *h, int which) {
   if (h->halo.nConn == 0) return 0;
+  if (!h->haloOverlap) return ExchangeOnComm(h, which, h->stream);
   if (ExchangeBegin(h) || ExchangeOnComm(h, which)) return 1;
   return ExchangeEnd(h);
 }
