@@ -210,6 +210,9 @@ struct aither_gpu {
   int pendingBlk = -1;
   long long launches = 0;
   bool keepMatrixResid = false;
+  // aither_gpu_iterate / _run: the matrix-residual pass also advances the state into the
+  // alternate buffer (fuseUpdate: requested for this iteration; stateFused: done by PhaseRelax)
+  bool fuseUpdate = false, stateFused = false;
   int jac = kJacScalar;            // JacKind of the implicit matrix
   bool consNStale = false;         // U^n not materialised (Params::timeTermsVanish)
   bool nonreflecting = false;      // some inlet / pressure outlet is non-reflecting
@@ -460,7 +463,7 @@ void LaunchImplicitMarch(aither_gpu *h, HostBlock &hb, const double *xin, double
 // signalling h->dHaloSignal when done) instead of the plain 3-D grid
 template <int NS, int NT, int MODE>
 void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *xout,
-                       int storeField, bool ordered = false) {
+                       int storeField, bool ordered = false, double *stateOut = nullptr) {
   using T = ImplTma<NS, NT>;
   auto kern = ImplicitTmaKernel<NS, NT, MODE>;
   static bool configured[64] = {false};
@@ -470,15 +473,17 @@ void LaunchImplicitTma(aither_gpu *h, HostBlock &hb, const double *xin, double *
   const int fX = static_cast<int>((xin - base) / b.fs);
   const int fAi = static_cast<int>((b.fA[0] - base) / b.fs);
   const int fAj = static_cast<int>((b.fA[1] - base) / b.fs);
+  const int fState = static_cast<int>((b.state - base) / b.fs);
   if (!ordered) {
     kern<<<hb.tmaGrid, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
         hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField,
-        nullptr, 0, 0, 0, nullptr);
+        nullptr, 0, 0, 0, nullptr, fState, stateOut);
     return;
   }
   kern<<<hb.nTmaBlocks, dim3(kQI, kQJ, 1), T::bytes, h->stream>>>(
       hb.tmaMaps, b, h->params, xin, xout, fX, fAi, fAj, hb.tmaChunk, h->dPartials, storeField,
-      hb.dTmaTiles, hb.tmaGrid.x, hb.tmaGrid.y, hb.nTmaBoundaryTiles, h->dHaloSignal);
+      hb.dTmaTiles, hb.tmaGrid.x, hb.tmaGrid.y, hb.nTmaBoundaryTiles, h->dHaloSignal, fState,
+      nullptr);
 }
 
 template <int NS, int NT>
@@ -989,7 +994,10 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
         }
       } else if constexpr (!kCell) {
         if (h->tmaImplicit) {
-          LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0);
+          double *stateOut = h->fuseUpdate ? hb.dev.stateAlt : nullptr;
+          LaunchImplicitTma<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr, h->keepMatrixResid ? 1 : 0,
+                                               false, stateOut);
+          if (stateOut) h->stateFused = true;
           nPartials = hb.nTmaBlocks;
         } else {
           LaunchImplicitMarch<NS, NT, kModeAxmb>(h, hb, hb.dev.x, nullptr,
@@ -1025,9 +1033,17 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
   for (auto &hb : h->blocks) {
     {
       ScopedLaunch sl(h, kFamUpdate);
-      UpdateKernel<NS, NT><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
-                                                                      h->dPartials,
-                                                                      h->dLinfPartials);
+      if (h->stateFused) {
+        // the matrix-residual pass has advanced the state into the alternate buffer: residual
+        // norms only, then the two buffers change roles
+        UpdateKernel<NS, NT, true, false><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(
+            hb.dev, h->params, h->dPartials, h->dLinfPartials);
+        std::swap(hb.dev.state, hb.dev.stateAlt);
+      } else {
+        UpdateKernel<NS, NT><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
+                                                                        h->dPartials,
+                                                                        h->dLinfPartials);
+      }
     }
     {
       ScopedLaunch sl(h, kFamReduce);
@@ -1101,9 +1117,16 @@ int IterateAsync(aither_gpu *h, double cfl, int slot, int mm) {
   const bool fuse = !h->legacyKernels && h->fusePrep && !h->cfg.isViscous && h->jac != kJacBlock;
   if (PhaseResidual(h, fuse ? 1 : 0, cfl)) return 1;
   if (!fuse && PhasePrep(h, cfl, kPrepDt | kPrepDiag | kPrepInit)) return 1;
-  if (PhaseRelax(h, h->cfg.matrixSweeps, slot)) return 1;
-  if (PhaseUpdate(h, slot, mm)) return 1;
-  return 0;
+  // the matrix-residual pass of the TMA path advances the state as well (A/B:
+  // AITHER_B200_FUSE_UPDATE=0 leaves it to the update kernel)
+  h->fuseUpdate = h->tmaImplicit && !h->legacyKernels && getenv("AITHER_B200_FUSE_UPDATE") == nullptr;
+  h->stateFused = false;
+  const int rcRelax = PhaseRelax(h, h->cfg.matrixSweeps, slot);
+  h->fuseUpdate = false;
+  if (rcRelax) return 1;
+  const int rcUpd = PhaseUpdate(h, slot, mm);
+  h->stateFused = false;
+  return rcUpd;
 }
 
 int CheckFlag(aither_gpu *h) {
@@ -1384,7 +1407,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     hb.paddedCells = static_cast<long long>(d.ni + 2 * g) * (d.nj + 2 * g) * (d.nk + 2 * g);
     // field budget (doubles per cell): state, consN, [consNm1], resid, rhs, x, xalt, [mres],
     // specRad 2, dt, diag, dinv, vol, cw 3, fA 12, center 3
-    const int nFields = neq * 7 + (cfg->isMultilevelTime ? neq : 0) + 2 + 1 + 1 + 1 + 1 + 3 + 6 +
+    const int nFields = neq * 7 + (h->tmaImplicit ? neq : 0) + (cfg->isMultilevelTime ? neq : 0) +
+                        2 + 1 + 1 + 1 + 1 + 3 + 6 +
                         12 + 3 + (cfg->isViscous ? 6 : 0) + 2 * (h->asz - 1) +
                         (h->nt > 0 ? 18 : ((cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1 || h->wallLaw)) ? 9 : 0)) +
                         (h->nonreflecting ? 12 : 0);
@@ -1395,6 +1419,7 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     double *cur = static_cast<double *>(hb.alloc);
     auto take = [&](int n) { double *r = cur; cur += static_cast<size_t>(n) * b.fs; return r; };
     b.state = take(neq);
+    b.stateAlt = h->tmaImplicit ? take(neq) : nullptr;
     b.consN = take(neq);
     b.consNm1 = cfg->isMultilevelTime ? take(neq) : nullptr;
     b.resid = take(neq);

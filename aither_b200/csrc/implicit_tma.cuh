@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(kQThreads, 1)
                       const double *__restrict__ xin, double *__restrict__ xout, int fX, int fAi,
                       int fAj, int kChunk, double *__restrict__ partials, int storeField,
                       const int *__restrict__ tiles = nullptr, int tilesX = 0, int tilesY = 0,
-                      int nSignal = 0, unsigned int *__restrict__ signal = nullptr) {
+                      int nSignal = 0, unsigned int *__restrict__ signal = nullptr, int fState = 0,
+                      double *__restrict__ stateOut = nullptr) {
   using E = Eq<NS, NT>;
   using T = ImplTma<NS, NT>;
   constexpr int neq = E::neq;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kQThreads, 1)
     uint64_t *bar = full + (it & 1);
     const bool interior = it > 0 && it < nIter - 1;
     MbarExpectTx(bar, T::txState + (interior ? T::txFaces : 0u));
-    TmaLoad4D(st, &maps.cell, i0 - kQL + b.lp, j0 - 1 + b.g, k + b.g, 0, bar);
+    TmaLoad4D(st, &maps.cell, i0 - kQL + b.lp, j0 - 1 + b.g, k + b.g, fState, bar);
     TmaLoad4D(st + T::szS, &maps.cell, i0 - kQL + b.lp, j0 - 1 + b.g, k + b.g, fX, bar);
     if (interior) {
       TmaLoad4D(st + 2 * T::szS, &maps.faceI, i0 + b.lp, j0 + b.g, k + b.g, fAi, bar);
@@ -185,6 +186,14 @@ __global__ void __launch_bounds__(kQThreads, 1)
       du[e] = sX[e * kQPC + pc];
     }
     MakeIngr<NS, NT>(p.gas, s, du, &H, &a, sn, &Hn);
+    if (MODE == kModeAxmb && stateOut != nullptr && colValid && planeInterior) {
+      // the updated primitive state (U + dU -> primitives; ref src/procBlock.cpp:902-915,
+      // include/primitive.hpp:206-231) is what MakeIngr has just formed for the off-diagonals:
+      // the state is advanced here, into the alternate buffer (the neighbours' old state is
+      // still being read), and the update kernel is left with the residual norms
+#pragma unroll
+      for (int e = 0; e < neq; ++e) stateOut[e * b.fs + idx] = sn[e];
+    }
     if (it < nIter - 1) {  // every plane that has a cell above it in the chunk
       sG[pc] = H;
       sG[kQPC + pc] = a;

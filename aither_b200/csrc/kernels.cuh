@@ -176,10 +176,21 @@ __global__ void BcKernel(BlockDev b, Params p, const SurfDev *__restrict__ surfs
   const int d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
   const int n1 = sf.hi[d1] - sf.lo[d1], n2 = sf.hi[d2] - sf.lo[d2];
   long long r = t - sf.faceOffset;
-  const int a1 = static_cast<int>(r % n1);
-  r /= n1;
-  const int a2 = static_cast<int>(r % n2);
-  const int layer = static_cast<int>(r / n2) + 1;
+  // consecutive threads along i wherever the surface has an i extent (j-surfaces: direction 2 is
+  // i, k-surfaces: direction 1): their loads and stores then fall on consecutive addresses
+  int a1, a2;
+  if (d3 == 1) {
+    a2 = static_cast<int>(r % n2);
+    r /= n2;
+    a1 = static_cast<int>(r % n1);
+    r /= n1;
+  } else {
+    a1 = static_cast<int>(r % n1);
+    r /= n1;
+    a2 = static_cast<int>(r % n2);
+    r /= n2;
+  }
+  const int layer = static_cast<int>(r) + 1;
   const int nd[3] = {b.ni, b.nj, b.nk};
   const int r3 = sf.lo[d3];
   // ref: src/procBlock.cpp:2470-2486
@@ -998,47 +1009,9 @@ __device__ __forceinline__ LinfCand LinfBetter(LinfCand a, LinfCand c) {
   return (c.v > a.v || (c.v == a.v && c.key < a.key)) ? c : a;
 }
 
-constexpr int kUpdPlanes = 4;  // k-planes per thread block: the block reductions are paid once
-template <int NS, int NT>
-__global__ void __launch_bounds__(256)
-    UpdateKernel(BlockDev b, Params p, double *__restrict__ partials,
-                 LinfCand *__restrict__ linfPartials) {
-  using E = Eq<NS, NT>;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  double sq[E::neq];
-#pragma unroll
-  for (int e = 0; e < E::neq; ++e) sq[e] = 0.0;
-  LinfCand best;
-  best.v = 0.0;  // the reference starts from linf = 0 and uses a strict '>' (resid.hpp:33)
-  best.key = 0x7fffffffffffffffLL;
-  if (i < b.ni && j < b.nj) {
-    const int kEnd = min(b.nk, (static_cast<int>(blockIdx.z) + 1) * kUpdPlanes);
-    for (int k = blockIdx.z * kUpdPlanes; k < kEnd; ++k) {
-      const long long idx = CellIdx(b, i, j, k);
-      double s[E::neq], du[E::neq], sn[E::neq];
-      LoadCell<E::neq>(b.state, b.fs, idx, s);
-      LoadCell<E::neq>(b.x, b.fs, idx, du);
-      UpdatePrimWithCons<NS, NT>(p.gas, s, du, sn);
-      StoreCell<E::neq>(b.state, b.fs, idx, sn);
-      const long long cellKey =
-          ((static_cast<long long>(k) * b.nj + j) * b.ni + i) * static_cast<long long>(E::neq);
-#pragma unroll
-      for (int e = 0; e < E::neq; ++e) {
-        const double r = __ldg(b.resid + e * b.fs + idx);
-        sq[e] += r * r;
-        LinfCand c;
-        c.v = r;
-        c.key = cellKey + e;
-        if (r > best.v) best = c;  // increasing k, e: first maximum wins, like the reference loop
-      }
-    }
-  }
-  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
-  const int nthreads = blockDim.x * blockDim.y;
-  const int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  BlockSumToPartials<E::neq>(sq, partials, blockLinear, tid, nthreads);
-  // arg-max
+// arg-max over a thread block, one candidate per block (deterministic: ties by traversal key)
+__device__ __forceinline__ void BlockLinfToPartials(LinfCand best, LinfCand *linfPartials,
+                                                    int blockLinear, int tid, int nthreads) {
   __shared__ LinfCand shc[32];
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -1055,6 +1028,57 @@ __global__ void __launch_bounds__(256)
     for (int w = 1; w < (nthreads + 31) / 32; ++w) r = LinfBetter(r, shc[w]);
     linfPartials[blockLinear] = r;
   }
+}
+
+constexpr int kUpdPlanes = 4;  // k-planes per thread block: the block reductions are paid once
+// MOVE = false: the state has already been advanced by the matrix-residual pass
+// (implicit_tma.cuh: every cell's updated primitive state is in registers there and is written to
+// the alternate state buffer); what is left is the residual norms
+template <int NS, int NT, bool NORMS = true, bool MOVE = true>
+__global__ void __launch_bounds__(256)
+    UpdateKernel(BlockDev b, Params p, double *__restrict__ partials,
+                 LinfCand *__restrict__ linfPartials) {
+  using E = Eq<NS, NT>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  double sq[E::neq];
+#pragma unroll
+  for (int e = 0; e < E::neq; ++e) sq[e] = 0.0;
+  LinfCand best;
+  best.v = 0.0;  // the reference starts from linf = 0 and uses a strict '>' (resid.hpp:33)
+  best.key = 0x7fffffffffffffffLL;
+  if (i < b.ni && j < b.nj) {
+    const int kEnd = min(b.nk, (static_cast<int>(blockIdx.z) + 1) * kUpdPlanes);
+    for (int k = blockIdx.z * kUpdPlanes; k < kEnd; ++k) {
+      const long long idx = CellIdx(b, i, j, k);
+      if (MOVE) {
+        double s[E::neq], du[E::neq], sn[E::neq];
+        LoadCell<E::neq>(b.state, b.fs, idx, s);
+        LoadCell<E::neq>(b.x, b.fs, idx, du);
+        UpdatePrimWithCons<NS, NT>(p.gas, s, du, sn);
+        StoreCell<E::neq>(b.state, b.fs, idx, sn);
+      }
+      if (NORMS) {
+        const long long cellKey =
+            ((static_cast<long long>(k) * b.nj + j) * b.ni + i) * static_cast<long long>(E::neq);
+#pragma unroll
+        for (int e = 0; e < E::neq; ++e) {
+          const double r = __ldg(b.resid + e * b.fs + idx);
+          sq[e] += r * r;
+          LinfCand c;
+          c.v = r;
+          c.key = cellKey + e;
+          if (r > best.v) best = c;  // increasing k, e: first maximum wins, like the reference loop
+        }
+      }
+    }
+  }
+  if (!NORMS) return;
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  BlockSumToPartials<E::neq>(sq, partials, blockLinear, tid, nthreads);
+  BlockLinfToPartials(best, linfPartials, blockLinear, tid, nthreads);
 }
 
 // final pass over the per-block partials of one procBlock, accumulating into the iteration's

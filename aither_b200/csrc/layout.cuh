@@ -24,6 +24,8 @@ struct BlockDev {
   int parentBlock;
   // fields (each `fs` doubles per component)
   double *state;     // neq   primitive, ghosts valid
+  double *stateAlt;  // neq   the state the fused matrix-residual pass advances into (inviscid
+                     //       one-species scalar-diagonal runs, else null); swapped with `state`
   double *consN;     // neq   U^n
   double *consNm1;   // neq   U^(n-1) (bdf2 only, else null)
   double *resid;     // neq   residual R
