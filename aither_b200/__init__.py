@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "aither_gpu_invert_diagonal", "aither_gpu_initialize_matrix_update", "aither_gpu_relax",
     "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
     "aither_gpu_upload_state", "aither_gpu_upload_state_async", "aither_gpu_upload_state_commit",
-    "aither_gpu_download_state", "aither_gpu_download_field",
+    "aither_gpu_download_state", "aither_gpu_download_field", "aither_gpu_download_wall_data",
     "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
     "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
@@ -78,6 +78,7 @@ def load_library():
     L.aither_gpu_upload_state_commit.argtypes = [vp]
     L.aither_gpu_download_state.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
+    L.aither_gpu_download_wall_data.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
     L.aither_gpu_field_size.restype = C.c_longlong
     L.aither_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -211,6 +212,15 @@ class GridLevel:
                          abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
+
+    def wall_data(self, blk, surface):
+        """wall variables (y+, shear stress, heat flux, T, mu_t, mu, rho, u_tau, k, omega) of a
+        wall-law surface of block `blk`, shape (nk, nj, ni, 12) over the surface's cell range"""
+        sf = self.problem.blocks[self.block_ids[blk]].surfaces[surface]
+        shp = (max(sf[6] - sf[5], 1), max(sf[4] - sf[3], 1), max(sf[2] - sf[1], 1))
+        out = np.empty(shp + (12,))
+        self._check(self._lib.aither_gpu_download_wall_data(self._h, blk, surface, _ptr(out)))
+        return out
 
     def upload_state(self, blk, state):
         state = np.ascontiguousarray(state, dtype=np.float64)

@@ -97,6 +97,7 @@ struct HostBlock {
   void *alloc = nullptr;          // one allocation holding every field
   size_t allocBytes = 0;
   std::vector<aither_surface> surfaces;
+  std::vector<long long> surfFaceOffset;  // per surface: first boundary-face record, -1 for connections
   SurfDev *dSurfs = nullptr;
   int nBcSurfs = 0;
   EdgeSurf *dEdgeSurfs = nullptr;  // every surface of the block, connections included
@@ -1512,6 +1513,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
       const int st = SurfaceType(sf);
       const int d3 = (st - 1) / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
       int lo[3] = {sf.imin, sf.jmin, sf.kmin}, hi[3] = {sf.imax, sf.jmax, sf.kmax};
+      hb.surfFaceOffset.push_back(
+          (sf.type == AITHER_BC_INTERBLOCK || sf.type == AITHER_BC_PERIODIC) ? -1 : off / g);
       if (sf.type == AITHER_BC_INTERBLOCK || sf.type == AITHER_BC_PERIODIC) {
         anyConn = true;
         for (int c2 = lo[d2]; c2 < hi[d2]; ++c2)
@@ -2100,6 +2103,55 @@ int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst) {
 }
 int aither_gpu_download_state(aither_gpu *h, int blk, double *stateAoS) {
   return aither_gpu_download_field(h, blk, AITHER_FIELD_STATE, stateAoS);
+}
+int aither_gpu_download_wall_data(aither_gpu *h, int blk, int surface, double *dst) {
+  // ref: include/wallData.hpp:40-57, src/procBlock.cpp:6287-6290 (records of wall-law walls)
+  if (!h || !dst) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  const HostBlock &hb = h->blocks[blk];
+  if (surface < 0 || surface >= static_cast<int>(hb.surfaces.size())) return Fail("bad surface index");
+  const aither_surface &sf = hb.surfaces[surface];
+  bool wallLaw = false;
+  if (sf.type == AITHER_BC_VISCOUS_WALL && h->cfg.isViscous)
+    for (int q = 0; q < h->cfg.numBCStates; ++q)
+      if (h->cfg.bcStates[q].tag == sf.tag) { wallLaw = h->cfg.bcStates[q].isWallLaw != 0; break; }
+  if (!wallLaw || !hb.dWallVars || hb.surfFaceOffset[surface] < 0)
+    return Fail("wall data is kept for viscous walls with the wall law only (surface " +
+                std::to_string(surface) + " is not one)");
+  const int st = SurfaceType(sf);
+  const int d3 = (st - 1) / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+  const int lo[3] = {sf.imin, sf.jmin, sf.kmin}, hi[3] = {sf.imax, sf.jmax, sf.kmax};
+  const int n1 = hi[d1] - lo[d1], n2 = hi[d2] - lo[d2];
+  std::vector<double> raw(static_cast<size_t>(n1) * n2 * kWallVarsStride);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(raw.data(), hb.dWallVars + hb.surfFaceOffset[surface] * kWallVarsStride,
+                sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
+  // device order: direction 1 fastest (i-surface: j, k; j-surface: k, i; k-surface: i, j);
+  // reference order: i fastest, then j, then k
+  int ext[3] = {1, 1, 1};
+  ext[d1] = n1;
+  ext[d2] = n2;
+  for (int a2 = 0; a2 < n2; ++a2)
+    for (int a1 = 0; a1 < n1; ++a1) {
+      int c[3] = {0, 0, 0};
+      c[d1] = a1;
+      c[d2] = a2;
+      const double *w = &raw[(static_cast<size_t>(a2) * n1 + a1) * kWallVarsStride];
+      double *o = dst + (static_cast<size_t>(c[2]) * ext[1] * ext[0] + static_cast<size_t>(c[1]) * ext[0] + c[0]) *
+                            AITHER_WALL_VARS;
+      o[0] = w[kWvYplus];
+      o[1] = w[kWvTau]; o[2] = w[kWvTau + 1]; o[3] = w[kWvTau + 2];
+      o[4] = w[kWvHeatFlux];
+      o[5] = w[kWvT];
+      o[6] = w[kWvMut];
+      o[7] = w[kWvMu];
+      o[8] = w[kWvRho];
+      o[9] = w[kWvUtau];
+      o[10] = w[kWvTke];
+      o[11] = w[kWvSdr];
+    }
+  return 0;
 }
 int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   if (!h || !stateAoS) return Fail("null argument");

@@ -178,6 +178,7 @@ __global__ void ViscousWallKernel(BlockDev b, Params p, const SurfDev *__restric
       w[kWvVelWall] = bc.velocity[0];
       w[kWvVelWall + 1] = bc.velocity[1];
       w[kWvVelWall + 2] = bc.velocity[2];
+      w[kWvUtau] = wv.utau;
     }
   } else {
     ViscousWallGhost<NS, NT>(p.gas, p.tr, interior, bc, wd, ghost, nuW, layer);

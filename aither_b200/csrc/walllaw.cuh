@@ -19,10 +19,10 @@ namespace aither {
 // (ref: src/procBlock.cpp:6287-6290, :1286-1300)
 constexpr int kWallVarsStride = 16;
 enum WallVarSlot { kWvYplus = 0, kWvTau = 1, kWvHeatFlux = 4, kWvMu = 5, kWvMut = 6, kWvRho = 7,
-                   kWvT = 8, kWvTke = 9, kWvSdr = 10, kWvVelWall = 11 };
+                   kWvT = 8, kWvTke = 9, kWvSdr = 10, kWvVelWall = 11, kWvUtau = 14 };
 
 struct WallVars {
-  double yplus, tau[3], heatFlux, mu, mut, rho, t, tke, sdr;
+  double yplus, tau[3], heatFlux, mu, mut, rho, t, tke, sdr, utau;
   AITHER_HD bool SwitchToLowRe() const { return yplus < 10.0; }  // include/wallData.hpp:57
 };
 
@@ -170,6 +170,7 @@ AITHER_HD void WallLawEval(const Gas &g, const Transport &tr, const aither_bc_st
   wv.t = mode == kWallAdiabatic ? c.tW : c.temperature;
   wv.mu = c.muW;
   wv.mut = mutW;
+  wv.utau = c.uStar;  // wallVars::frictionVelocity_ (src/wallLaw.cpp:81,139,194)
   const double tauMag = c.uStar * c.uStar * c.rhoW;  // ShearStressMag
 #pragma unroll
   for (int d = 0; d < 3; ++d) {

@@ -252,6 +252,17 @@ int aither_gpu_reset_diagonal(aither_gpu *h);
 int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep,
                    double cflMax, double *hist);
 
+/* Wall variables of one viscous-wall surface (reference `wallData` / `wallVars`,
+ * include/wallData.hpp:40-57; what WriteWallFunFile reads, src/output.cpp:440-588): for every face
+ * of surface `surface` (index into the block's surface list as given to aither_gpu_create) the
+ * AITHER_WALL_VARS doubles {y+, shear stress x/y/z, heat flux, wall temperature, wall eddy
+ * viscosity, wall viscosity, wall density, friction velocity, k, omega}, in the reference's face
+ * order (i fastest, then j, then k over the surface's cell range), as the last residual
+ * evaluation left them. Kept on the device for walls with `wallTreatment: wallLaw`; any other
+ * surface is refused. */
+#define AITHER_WALL_VARS 12
+int aither_gpu_download_wall_data(aither_gpu *h, int blk, int surface, double *dst);
+
 /* host <-> device state transfer in the reference's layout
  * (procBlock::States(), include/procBlock.hpp:506). */
 int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS);

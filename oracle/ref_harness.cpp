@@ -471,6 +471,24 @@ int main(int argc, char *argv[]) {
             d.field(p + "omegaGrad@" + it, lvl.Block(bb).omegaGrad_);
           }
           d.field(p + "diagRaw@" + it, lvl.solver_->a_[bb]);
+          // wall variables of every viscous-wall surface (include/wallData.hpp:40-57), as the
+          // viscous fluxes of this evaluation left them: 12 doubles per wall face
+          for (int ww = 0; ww < static_cast<int>(lvl.Block(bb).wallData_.size()); ++ww) {
+            const auto &wd = lvl.Block(bb).wallData_[ww];
+            const auto &sf = wd.surf_;
+            d.ivec(p + "wall" + std::to_string(ww) + "/surface",
+                   {sf.IMin(), sf.IMax(), sf.JMin(), sf.JMax(), sf.KMin(), sf.KMax(),
+                    sf.SurfaceType(), sf.Tag()});
+            std::vector<double> v;
+            for (const auto &w : wd.data_.data_) {
+              v.insert(v.end(), {w.yplus_, w.shearStress_.X(), w.shearStress_.Y(),
+                                 w.shearStress_.Z(), w.heatFlux_, w.temperature_,
+                                 w.turbEddyVisc_, w.viscosity_, w.density_,
+                                 w.frictionVelocity_, w.tke_, w.sdr_});
+            }
+            d.doubles(p + "wall" + std::to_string(ww) + "/vars@" + it, v.data(),
+                      {wd.NumK(), wd.NumJ(), wd.NumI(), 12});
+          }
         }
         lvl.CalcTimeStep(inp);
         for (int bb = 0; bb < lvl.NumBlocks(); ++bb) {

@@ -13,6 +13,7 @@ import pytest
 
 import goldencheck as gc
 import oracle
+import refcase
 from aither_b200 import ctypes_abi as abi
 from aither_b200 import synthetic
 
@@ -218,3 +219,38 @@ def test_full_size_block_is_decomposition_invariant():
     many.close()
     scale = np.abs(whole).max(axis=(0, 1, 2))
     assert (np.abs(whole - parts).max(axis=(0, 1, 2)) / scale).max() <= 1e-12
+
+
+def test_wall_data_matches_reference():
+    """aither_gpu_download_wall_data against the reference's wallData of testCases/wallLaw (SST,
+    wall law; perturbed start): y+, wall shear stress, heat flux, wall temperature / viscosities /
+    density, friction velocity, k and omega of every wall face after the first residual
+    evaluation (include/wallData.hpp:40-57; what WriteWallFunFile writes, src/output.cpp:440-588)."""
+    import aither_b200
+    d = gc.load("wallLaw_cloud")
+    prob = refcase.problem_from_dump(d, state_key="state0")
+    gpu = aither_b200.GridLevel(prob)
+    gpu.store_old_solution(0)
+    gpu.get_boundary_conditions()
+    gpu.calc_residual()
+    seen = 0
+    for bb, blk in enumerate(prob.blocks):
+        ww = 0
+        while "b%d/wall%d/surface" % (bb, ww) in d:
+            sf = [int(v) for v in d["b%d/wall%d/surface" % (bb, ww)]]
+            ref = d["b%d/wall%d/vars@it0" % (bb, ww)]
+            idx = [n for n, s in enumerate(blk.surfaces) if list(s[1:7]) == sf[:6]]
+            assert len(idx) == 1, (sf, blk.surfaces)
+            mine = gpu.wall_data(bb, idx[0])
+            assert mine.shape == ref.shape, (mine.shape, ref.shape)
+            # the three shear-stress components are one vector
+            err = gc.rel(mine, ref, groups=([1, 2, 3],))
+            assert err <= 1e-11, (bb, ww, err)
+            seen += 1
+            ww += 1
+    assert seen >= 1
+    # a surface without the wall law is refused
+    with pytest.raises(aither_b200.AitherGpuError):
+        other = [n for n, s in enumerate(prob.blocks[0].surfaces) if s[0] != abi.BC_VISCOUS_WALL]
+        gpu.wall_data(0, other[0])
+    gpu.close()
