@@ -27,6 +27,7 @@ ABI_SYMBOLS = (
     "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
     "aither_gpu_upload_state", "aither_gpu_upload_state_async", "aither_gpu_upload_state_commit",
     "aither_gpu_download_state", "aither_gpu_download_field", "aither_gpu_download_wall_data",
+    "aither_gpu_download_output",
     "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
     "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
@@ -79,6 +80,7 @@ def load_library():
     L.aither_gpu_download_state.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_download_wall_data.argtypes = [vp, C.c_int, C.c_int, pd]
+    L.aither_gpu_download_output.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, pd]
     L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
     L.aither_gpu_field_size.restype = C.c_longlong
     L.aither_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -212,6 +214,15 @@ class GridLevel:
                          abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
+
+    def output(self, blk, var, scale=1.0, species=0):
+        """one function-file variable (abi.OUT_*) of block `blk`, derived on the device, physical
+        cells only: shape (nk, nj, ni)"""
+        b = self.problem.blocks[self.block_ids[blk]]
+        out = np.empty((b.nk, b.nj, b.ni))
+        self._check(self._lib.aither_gpu_download_output(self._h, blk, var, species, scale,
+                                                         _ptr(out)))
+        return out
 
     def wall_data(self, blk, surface):
         """wall variables (y+, shear stress, heat flux, T, mu_t, mu, rho, u_tau, k, omega) of a

@@ -36,6 +36,7 @@ struct AitherEqOps {
   int (*PhaseUpdateT)(aither_gpu *, int, int);
   int (*StoreOldT)(aither_gpu *, int);
   int (*InitAuxT)(aither_gpu *, int);
+  int (*OutputVarT)(aither_gpu *, int, int, int, double, double *);
 };
 const AitherEqOps *AitherEqOps_1_0();
 const AitherEqOps *AitherEqOps_1_2();
@@ -1105,6 +1106,16 @@ int InitAuxT(aither_gpu *h, int blk) {
   return 0;
 }
 
+// one function-file variable of block `blk` into the staging buffer (device), physical cells
+template <int NS, int NT>
+int OutputVarT(aither_gpu *h, int blk, int var, int species, double scale, double *dDst) {
+  HostBlock &hb = h->blocks[blk];
+  ScopedLaunch sl(h, kFamLayout);
+  OutputVarKernel<NS, NT><<<hb.cellGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params, var,
+                                                                      species, scale, dDst);
+  return 0;
+}
+
 long long TotalPaddedSize(const aither_gpu *h) {
   long long t = 0;
   for (auto &hb : h->blocks) t += hb.paddedCells * h->neq;
@@ -1213,7 +1224,7 @@ const AitherEqOps *EqOpsFor(const aither_gpu *h) {
     static const AitherEqOps ops = {PhaseBoundaryConditionsT<NS, NT>, PhaseResidualT<NS, NT>, \
                                     PhasePrepT<NS, NT>,               PhaseRelaxT<NS, NT>,    \
                                     PhaseUpdateT<NS, NT>,             StoreOldT<NS, NT>,      \
-                                    InitAuxT<NS, NT>};                                        \
+                                    InitAuxT<NS, NT>,                 OutputVarT<NS, NT>};    \
     return &ops;                                                                              \
   }
 #if defined(AITHER_EQ_TU)
@@ -2103,6 +2114,30 @@ int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst) {
 }
 int aither_gpu_download_state(aither_gpu *h, int blk, double *stateAoS) {
   return aither_gpu_download_field(h, blk, AITHER_FIELD_STATE, stateAoS);
+}
+int aither_gpu_download_output(aither_gpu *h, int blk, int var, int species, double scale,
+                               double *dst) {
+  // ref: WriteFunFile, src/output.cpp:209-437
+  if (!h || !dst) return Fail("null argument");
+  CK(cudaSetDevice(h->device));
+  if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
+  if (var < 0 || var >= AITHER_OUT_NUM_VARS) return Fail("unknown output variable " + std::to_string(var));
+  const BlockDev &b = h->blocks[blk].dev;
+  if ((var == AITHER_OUT_VISCOSITY || var == AITHER_OUT_VISCOSITY_RATIO) && !b.viscosity)
+    return Fail("viscosity is only kept for viscous runs");
+  if ((var == AITHER_OUT_TURBULENT_VISCOSITY || var == AITHER_OUT_F1 || var == AITHER_OUT_F2 ||
+       var == AITHER_OUT_TKE || var == AITHER_OUT_SDR) && h->nt == 0)
+    return Fail("turbulence variables are only kept for RANS runs");
+  if (var == AITHER_OUT_WALL_DISTANCE && !b.wallDist) return Fail("this run has no wall distance");
+  if (var == AITHER_OUT_MASS_FRACTION && (species < 0 || species >= h->ns))
+    return Fail("species index out of range");
+  const size_t n = static_cast<size_t>(b.ni) * b.nj * b.nk;
+  if (EnsureStage(h, n * sizeof(double))) return 1;
+  if (EQ_DISPATCH(h, OutputVarT, h, blk, var, species, scale, h->dStage)) return 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, h->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 int aither_gpu_download_wall_data(aither_gpu *h, int blk, int surface, double *dst) {
   // ref: include/wallData.hpp:40-57, src/procBlock.cpp:6287-6290 (records of wall-law walls)

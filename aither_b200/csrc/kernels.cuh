@@ -1152,6 +1152,54 @@ __global__ void __launch_bounds__(256) StoreOldKernel(BlockDev b, Params p, int 
   if (copyToNm1) StoreCell<E::neq>(b.consNm1, b.fs, idx, c);
 }
 
+// ---------------------------------------------------------------------------------------------
+// output staging: one function-file variable for the physical cells of a block, i fastest
+// (ref: WriteFunFile, src/output.cpp:229-330 -- each branch cited by its variable name there)
+template <int NS, int NT>
+__global__ void __launch_bounds__(256)
+    OutputVarKernel(BlockDev b, Params p, int var, int species, double scale,
+                    double *__restrict__ dst) {
+  using E = Eq<NS, NT>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= b.ni || j >= b.nj) return;
+  const long long idx = CellIdx(b, i, j, k);
+  double s[E::neq];
+  LoadCell<E::neq>(b.state, b.fs, idx, s);
+  double v = 0.0;
+  switch (var) {
+    case AITHER_OUT_DENSITY: v = SpeciesSum<NS>(s); break;
+    case AITHER_OUT_VEL_X: v = s[E::imx]; break;
+    case AITHER_OUT_VEL_Y: v = s[E::imy]; break;
+    case AITHER_OUT_VEL_Z: v = s[E::imz]; break;
+    case AITHER_OUT_PRESSURE: v = s[E::ie]; break;
+    case AITHER_OUT_MACH: v = sqrt(VelMagSq<NS>(s)) / SoS<NS>(p.gas, s); break;
+    case AITHER_OUT_SOS: v = SoS<NS>(p.gas, s); break;
+    case AITHER_OUT_DT: v = b.dt[idx]; break;
+    // the reference writes its stored temperature field (refreshed from the state every residual
+    // evaluation); for the current state that is T = p / sum(rho_s R_s)
+    case AITHER_OUT_TEMPERATURE: v = Temperature<NS>(p.gas, s); break;
+    case AITHER_OUT_ENERGY: v = Energy<NS>(p.gas, s); break;
+    case AITHER_OUT_ENTHALPY: v = Enthalpy<NS>(p.gas, s); break;
+    case AITHER_OUT_CP: v = Mixture<NS>(p.gas, s).cp; break;
+    case AITHER_OUT_CV: v = Mixture<NS>(p.gas, s).cv; break;
+    case AITHER_OUT_VISCOSITY_RATIO:
+      v = (NT > 0 && b.eddyVisc) ? b.eddyVisc[idx] / b.viscosity[idx] : 0.0;
+      break;
+    case AITHER_OUT_TURBULENT_VISCOSITY: v = b.eddyVisc ? b.eddyVisc[idx] : 0.0; break;
+    case AITHER_OUT_VISCOSITY: v = b.viscosity ? b.viscosity[idx] : 0.0; break;
+    case AITHER_OUT_TKE: v = NT > 0 ? s[E::it] : 0.0; break;
+    case AITHER_OUT_SDR: v = NT > 1 ? s[E::it + (NT > 1 ? 1 : 0)] : 0.0; break;
+    case AITHER_OUT_F1: v = b.f1 ? b.f1[idx] : 0.0; break;
+    case AITHER_OUT_F2: v = b.f2 ? b.f2[idx] : 0.0; break;
+    case AITHER_OUT_WALL_DISTANCE: v = b.wallDist ? b.wallDist[idx] : 0.0; break;
+    case AITHER_OUT_MASS_FRACTION: v = s[species < NS ? species : 0] / SpeciesSum<NS>(s); break;
+    default: break;
+  }
+  dst[(static_cast<long long>(k) * b.nj + j) * b.ni + i] = v * scale;
+}
+
 static __global__ void FillKernel(double *__restrict__ p, long long n, double v) {
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n;
        t += static_cast<long long>(gridDim.x) * blockDim.x)

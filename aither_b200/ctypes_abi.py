@@ -115,3 +115,9 @@ class Conn(C.Structure):
 class Linf(C.Structure):
     _fields_ = [("linf", C.c_double), ("block", C.c_int), ("i", C.c_int), ("j", C.c_int),
                 ("k", C.c_int), ("eqn", C.c_int)]
+
+# aither_output_var (include/aither_gpu.h)
+(OUT_DENSITY, OUT_VEL_X, OUT_VEL_Y, OUT_VEL_Z, OUT_PRESSURE, OUT_MACH, OUT_SOS, OUT_DT,
+ OUT_TEMPERATURE, OUT_ENERGY, OUT_ENTHALPY, OUT_CP, OUT_CV, OUT_VISCOSITY_RATIO,
+ OUT_TURBULENT_VISCOSITY, OUT_VISCOSITY, OUT_TKE, OUT_SDR, OUT_F1, OUT_F2, OUT_WALL_DISTANCE,
+ OUT_MASS_FRACTION) = range(22)

@@ -252,6 +252,24 @@ int aither_gpu_reset_diagonal(aither_gpu *h);
 int aither_gpu_run(aither_gpu *h, int nIter, double cflStart, double cflStep,
                    double cflMax, double *hist);
 
+/* Output staging: one variable of the reference's function file (`outputVariables`, WriteFunFile
+ * src/output.cpp:209-437) derived ON THE DEVICE for the physical cells of a block and copied to
+ * `dst` ((nk, nj, ni) doubles, i fastest: the order WriteFunFile writes), so that only what is
+ * asked for crosses PCIe instead of the ghost-padded state. `scale` is the dimensional factor the
+ * reference multiplies by (e.g. rRef * aRef * aRef for pressure); the value is formed with the
+ * reference's expression and then multiplied once. `species` selects the species for
+ * AITHER_OUT_MASS_FRACTION. Variables whose field the configuration does not keep are refused. */
+enum aither_output_var {
+  AITHER_OUT_DENSITY = 0, AITHER_OUT_VEL_X, AITHER_OUT_VEL_Y, AITHER_OUT_VEL_Z, AITHER_OUT_PRESSURE,
+  AITHER_OUT_MACH, AITHER_OUT_SOS, AITHER_OUT_DT, AITHER_OUT_TEMPERATURE, AITHER_OUT_ENERGY,
+  AITHER_OUT_ENTHALPY, AITHER_OUT_CP, AITHER_OUT_CV, AITHER_OUT_VISCOSITY_RATIO,
+  AITHER_OUT_TURBULENT_VISCOSITY, AITHER_OUT_VISCOSITY, AITHER_OUT_TKE, AITHER_OUT_SDR,
+  AITHER_OUT_F1, AITHER_OUT_F2, AITHER_OUT_WALL_DISTANCE, AITHER_OUT_MASS_FRACTION,
+  AITHER_OUT_NUM_VARS
+};
+int aither_gpu_download_output(aither_gpu *h, int blk, int var, int species, double scale,
+                               double *dst);
+
 /* Wall variables of one viscous-wall surface (reference `wallData` / `wallVars`,
  * include/wallData.hpp:40-57; what WriteWallFunFile reads, src/output.cpp:440-588): for every face
  * of surface `surface` (index into the block's surface list as given to aither_gpu_create) the
