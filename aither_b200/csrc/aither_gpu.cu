@@ -605,7 +605,7 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   const PencilLattice L = LatticeOf(hb);
   if (EnsureWaveLattice(h, hb, kPTJ, kPTK)) return 1;
   CK(cudaMemsetAsync(hb.dWaveSync, 0, hb.waveSyncBytes, h->stream));
-  const int grid = std::min(hb.wavePencils, 148);
+  const int grid = std::min(hb.wavePencils, 148 * kPencilCtasPerSm);
   auto fwd = LusgsPencilKernel<NS, NT, true>;
   auto bwd = LusgsPencilKernel<NS, NT, false>;
   static bool cfgF[64] = {false}, cfgB[64] = {false};  // per device and template instantiation

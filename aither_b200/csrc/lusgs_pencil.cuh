@@ -39,7 +39,20 @@
 
 namespace aither {
 
-constexpr int kPTJ = 8, kPTK = 7, kPCells = kPTJ * kPTK;  // 56 cells x 4 lanes + a service warp = 256 threads
+// pencil cross-section and resident thread blocks per SM (tunable at build time for A/B runs):
+// 8 x 8 = 64 cells x 4 lanes + a service warp = 288 threads, one thread block per SM (192^3 x4 sweeps:
+// 8x7 18.4 ms, 8x8 17.4, 4x8 and 8x4 with two blocks per SM 18.5 / 19.1)
+#ifndef AITHER_PENCIL_TJ
+#define AITHER_PENCIL_TJ 8
+#endif
+#ifndef AITHER_PENCIL_TK
+#define AITHER_PENCIL_TK 8
+#endif
+#ifndef AITHER_PENCIL_CTAS
+#define AITHER_PENCIL_CTAS 1
+#endif
+constexpr int kPTJ = AITHER_PENCIL_TJ, kPTK = AITHER_PENCIL_TK, kPCells = kPTJ * kPTK;
+constexpr int kPencilCtasPerSm = AITHER_PENCIL_CTAS;
 
 template <int NS, int NT>
 struct PencilRec {
@@ -232,7 +245,7 @@ struct PencilFetch {
 // equations l, l + 4, ... . The chain of a plane is
 //     shared memory -> ingredients -> product -> shuffles -> solve -> shared memory.
 template <int NS, int NT, bool FORWARD>
-__global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
+__global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, kPencilCtasPerSm)
     LusgsPencilKernel(BlockDev b, Params p, PencilLattice L, int fullGS,
                       const double *__restrict__ dyn, const double *__restrict__ geo,
                       const double *__restrict__ ahead, const int2 *__restrict__ order,
