@@ -148,6 +148,8 @@ struct HostBlock {
   // behind-side face areas for the forward / backward sweep (built once) and the per-iteration
   // record of what does not depend on the update
   double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr, *dWaveAhead = nullptr;
+  uint4 *dWaveMailJ = nullptr, *dWaveMailK = nullptr;  // hand-over between pencils (lusgs_pencil.cuh)
+  unsigned waveTag = 0;                                 // number of the half sweep
 };
 
 }  // namespace aither_host
@@ -612,27 +614,47 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   if (EnsureSmemOptIn(fwd, C::smemBytes, h->device, cfgF) ||
       EnsureSmemOptIn(bwd, C::smemBytes, h->device, cfgB))
     return Fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the LU-SGS wavefront");
-  static long long *dbg = nullptr;  // AITHER_B200_LUSGS_DBG=1: clock64 stamps of one thread block
+  if (!hb.dWaveMailJ) {
+    const size_t lines = static_cast<size_t>(hb.wavePencils) * L.planesPer;
+    const size_t bytesJ = lines * kPTK * C::NI * sizeof(uint4), bytesK = lines * kPTJ * C::NI * sizeof(uint4);
+    CK(cudaMalloc(&hb.dWaveMailJ, bytesJ));
+    CK(cudaMalloc(&hb.dWaveMailK, bytesK));
+    CK(cudaMemsetAsync(hb.dWaveMailJ, 0, bytesJ, h->stream));
+    CK(cudaMemsetAsync(hb.dWaveMailK, 0, bytesK, h->stream));
+  }
+  if (++hb.waveTag == 0) ++hb.waveTag;  // 0 is what an untouched mailbox holds
+  // AITHER_B200_LUSGS_DBG=<file>: the time line of the pencils of the 6th forward launch
+  static long long *dbg = nullptr;
   static int dbgCount = 0;
-  if (getenv("AITHER_B200_LUSGS_DBG") && !dbg) cudaMalloc(&dbg, 8 * 8 * 32);
-  if (forward) {
-    fwd<<<grid, C::threads, C::smemBytes, h->stream>>>(b, h->params, L, fullGS, hb.dWaveDyn,
-                                                        hb.dWaveGeoLo, hb.dWaveAhead, hb.dWaveOrder,
-                                                        hb.wavePencils, hb.dWaveSync, dbg);
-    if (dbg && ++dbgCount == 6) {
-      long long hbuf[8 * 32];
-      cudaStreamSynchronize(h->stream);
-      cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
-      for (int q = 0; q < 32; ++q)
-        fprintf(stderr, "plane %d: wait %lld compute %lld tail %lld barrier %lld period %lld\n", q + 64,
-                hbuf[q * 8 + 1] - hbuf[q * 8], hbuf[q * 8 + 2] - hbuf[q * 8 + 1],
-                hbuf[q * 8 + 3] - hbuf[q * 8 + 2], hbuf[q * 8 + 4] - hbuf[q * 8 + 3],
-                q > 0 ? hbuf[q * 8] - hbuf[(q - 1) * 8] : 0LL);
+  const char *dbgFile = getenv("AITHER_B200_LUSGS_DBG");
+  if (dbgFile && !dbg) {
+    cudaMalloc(&dbg, sizeof(long long) * 8 * hb.wavePencils);
+    cudaMemset(dbg, 0, sizeof(long long) * 8 * hb.wavePencils);
+  }
+  const bool record = dbg && forward && ++dbgCount == 6;
+  if (forward)
+    fwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
+        b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoLo, hb.dWaveAhead, hb.dWaveOrder,
+        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag,
+        record ? dbg : nullptr);
+  else
+    bwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
+        b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoHi, hb.dWaveAhead, hb.dWaveOrder,
+        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, nullptr);
+  if (record) {
+    std::vector<long long> hbuf(8 * hb.wavePencils);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(hbuf.data(), dbg, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost);
+    if (FILE *f = fopen(dbgFile, "w")) {
+      fprintf(f, "# ticket bJ bK smid | ns since the first ticket: drawn, plane 0, 32, 64, 96, 128 reached, last plane done\n");
+      for (int t = 0; t < hb.wavePencils; ++t) {
+        fprintf(f, "%d %lld %lld %lld |", t, hbuf[8 * t + 7] % 1000, hbuf[8 * t + 7] / 1000 % 1000,
+                hbuf[8 * t + 7] / 1000000);
+        for (int k = 0; k < 7; ++k) fprintf(f, " %lld", hbuf[8 * t + k] ? hbuf[8 * t + k] - hbuf[0] : -1LL);
+        fprintf(f, "\n");
+      }
+      fclose(f);
     }
-  } else {
-    bwd<<<grid, C::threads, C::smemBytes, h->stream>>>(b, h->params, L, fullGS, hb.dWaveDyn,
-                                                        hb.dWaveGeoHi, hb.dWaveAhead, hb.dWaveOrder,
-                                                        hb.wavePencils, hb.dWaveSync, nullptr);
   }
   return 0;
 }
@@ -1173,6 +1195,8 @@ void FreeAll(aither_gpu *h) {
     if (hb.dWaveGeoHi) cudaFree(hb.dWaveGeoHi);
     if (hb.dWaveDyn) cudaFree(hb.dWaveDyn);
     if (hb.dWaveAhead) cudaFree(hb.dWaveAhead);
+    if (hb.dWaveMailJ) cudaFree(hb.dWaveMailJ);
+    if (hb.dWaveMailK) cudaFree(hb.dWaveMailK);
     if (hb.dSurfs) cudaFree(hb.dSurfs);
     if (hb.dEdgeSurfs) cudaFree(hb.dEdgeSurfs);
     if (hb.dWallVars) cudaFree(hb.dWallVars);

@@ -43,7 +43,7 @@ namespace aither {
 // 8 x 8 = 64 cells x 4 lanes + a service warp = 288 threads, one thread block per SM (192^3 x4 sweeps:
 // 8x7 18.4 ms, 8x8 17.4, 4x8 and 8x4 with two blocks per SM 18.5 / 19.1)
 #ifndef AITHER_PENCIL_TJ
-#define AITHER_PENCIL_TJ 8
+#define AITHER_PENCIL_TJ 16
 #endif
 #ifndef AITHER_PENCIL_TK
 #define AITHER_PENCIL_TK 8
@@ -80,14 +80,14 @@ __host__ __device__ __forceinline__ long long PencilSlot(const PencilLattice &L,
          (jl + kPTJ * kl);
 }
 
-// record head of a cell from the block's fields: what WaveDynKernel packs for the cells of the
-// block, formed on the fly (same expressions) for ghost cells and cells of other pencils
+// record head of a cell: r[0, neq) holds its state on entry; what WaveDynKernel packs for the
+// cells of the block and the halo warp forms on the fly (same expressions) for ghost cells and
+// cells of other pencils
 template <int NS, int NT>
-__device__ __forceinline__ void MakeHead(const BlockDev &b, const Params &p, long long idx,
-                                         double *r) {
+__device__ __forceinline__ void HeadFromState(const Params &p, double *r, double mu, double mut,
+                                              double f1) {
   using E = Eq<NS, NT>;
   using R = PencilRec<NS, NT>;
-  LoadCell<E::neq>(b.state, b.fs, idx, r);
   const MixK<NS> m = MixOf<NS>(p.gas, r);
   const double t0 = r[E::ie] * m.tFac;
   r[R::iH] = m.hf + m.cp * t0 + 0.5 * VelMagSq<NS>(r);  // as MakeIngr
@@ -97,13 +97,26 @@ __device__ __forceinline__ void MakeHead(const BlockDev &b, const Params &p, lon
   if (p.isViscous) {
     // state-dependent factors of the viscous face spectral radii (NeighbourViscTerms)
     const double rho = SpeciesSum<NS>(r);
-    const double mu = __ldg(b.viscosity + idx);
-    const double mut = NT > 0 ? __ldg(b.eddyVisc + idx) : 0.0;
     r[R::iVt] = ViscSpecFactor(p.tr, rho, Gamma<NS>(p.gas, r), mu, mut);
     if (NT > 0)
       r[R::iVtT] = TurbViscSpecFactor(p.tr.turbModel, p.tr.scaling, rho, r[NS + 4],
-                                      r[NS + 4 + (NT > 1 ? 1 : 0)], mu, mut, __ldg(b.f1 + idx));
+                                      r[NS + 4 + (NT > 1 ? 1 : 0)], mu, mut, f1);
   }
+}
+template <int NS, int NT>
+__device__ __forceinline__ void MakeHead(const BlockDev &b, const Params &p, long long idx,
+                                         double *r) {
+  using E = Eq<NS, NT>;
+  LoadCell<E::neq>(b.state, b.fs, idx, r);
+  double mu = 0.0, mut = 0.0, f1 = 0.0;
+  if (p.isViscous) {
+    mu = __ldg(b.viscosity + idx);
+    if (NT > 0) {
+      mut = __ldg(b.eddyVisc + idx);
+      f1 = __ldg(b.f1 + idx);
+    }
+  }
+  HeadFromState<NS, NT>(p, r, mu, mut, f1);
 }
 
 // behind-side faces: lower faces for the forward sweep (geoLo), upper faces for the backward one
@@ -218,46 +231,105 @@ template <int NS, int NT>
 struct PencilCfg {
   using R = PencilRec<NS, NT>;
   static constexpr int neq = NS + 4 + NT;
-  static constexpr int NCOMP = kPCells * 4;   // four lanes per cell
-  static constexpr int threads = NCOMP + 32;  // + the service warp (poller, publisher, loader)
-  static constexpr int S = 6;                 // ring of plane stages: copies run S - 2 planes ahead
+  static constexpr int NCOMP = kPCells;  // one thread per grid line of the pencil
+  static_assert(NCOMP % 32 == 0, "the walkers fill whole warps");
+  // + three warps: loader (ring of plane stages; posts the boundary lines) and two halo warps
+  // (ingredients of the neighbours outside the pencil, even / odd planes)
+  static constexpr int threads = NCOMP + 96;
+  static constexpr int NH = kPTJ + 2 * kPTK;  // halo lanes: column behind in j, row behind in k, line starts
+  static_assert(NH <= 32, "one warp prepares the halo of a plane");
   static constexpr int dynB = kPCells * R::DN * 8, geoB = kPCells * R::GN * 8, ahB = kPCells * R::AN * 8;
   static constexpr int stageB = dynB + geoB + ahB;
   static_assert(dynB % 16 == 0 && geoB % 16 == 0 && ahB % 16 == 0, "bulk copies move 16-byte words");
-  static constexpr int sxB = 2 * neq * kPCells * 8;
-  static constexpr size_t smemBytes = static_cast<size_t>(S) * stageB + sxB + 8 * S + 16;
+  // update-dependent ingredients of the cells solved one plane ago: du | sn | Hn, component-major
+  // over the cross-section padded by one line behind in j and in k (filled by the halo warp)
+  static constexpr int PJ = kPTJ + 1, PCELLS = PJ * (kPTK + 1);
+  static constexpr int NI = 2 * neq + 1;
+  static constexpr int ingB = 2 * NI * PCELLS * 8;
+  static constexpr int haloB = 2 * NH * R::NST * 8;  // record heads of the halo cells
+  static constexpr int fixedB = ingB + haloB + 8 * 8 + 16;
+  static constexpr int kMaxSmem = 227 * 1024;
+  static constexpr int sFit = (kMaxSmem - fixedB) / stageB;
+  static constexpr int S = sFit > 6 ? 6 : sFit;  // ring of plane stages: copies run S - 2 planes ahead
+  static_assert(S >= 3, "the cross-section does not fit shared memory");
+  static constexpr size_t smemBytes = static_cast<size_t>(S) * stageB + fixedB;
 };
 
-// what a lane fetches from global memory one plane ahead of its use: only lanes whose
-// behind-neighbour is NOT in the pencil (cell of the pencil behind, ghost cell across a connection)
+__device__ __forceinline__ void NamedBarrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hand-over between pencils without fences: a MAILBOX entry is 16 bytes, two 8-byte words
+// {low half of the double, tag} {high half, tag}. Each 8-byte word is written atomically, so a
+// reader that finds the expected tag in both words holds the value -- no release / acquire pair,
+// no progress counter. (A gpu-scope release costs ~1 000 cycles on B200 and, announced every
+// plane by every pencil, slowed the whole sweep: profiles/r02y, 2.0 -> 1.5 ms per half sweep just
+// by announcing every 4th plane.) The tag is the number of the half sweep (never 0; the mailbox
+// is zeroed when it is allocated), so what an earlier half sweep left behind never matches.
+__device__ __forceinline__ void MailStore(uint4 *p, double v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+               "r"(static_cast<unsigned>(__double2loint(v))), "r"(tag),
+               "r"(static_cast<unsigned>(__double2hiint(v))), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 MailLoad(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+// what a halo lane loads one plane ahead of its use. Neighbour in another pencil: record head from
+// that pencil's workspace record, ingredients from the mailbox. Ghost cell: state (in hd), update
+// (in the first neq entries) and viscosities from the block's fields.
 template <int NS, int NT>
-struct PencilFetch {
+struct HaloRaw {
   static constexpr int neq = NS + 4 + NT;
-  double hd[PencilRec<NS, NT>::NST];  // record head of that neighbour
-  double du[neq];                     // its update
+  double hd[PencilRec<NS, NT>::NST];
+  uint4 ent[2 * neq + 1];
+  double mu, mut, f1;
+  const uint4 *mail;  // where the entries come from (re-read until their tags match)
+  int kind;           // 0 nothing, 1 mailbox, 2 ghost cell
 };
 
-// A cell (sweep coordinate I = q - jl - kl at plane q of its line) has FOUR lanes. Lane d = 0, 1, 2
-// owns the behind-neighbour in direction i, j, k: it takes that neighbour's NEW update (shared
-// memory, written one plane ago) and record head (the previous plane's stage), forms its new
-// ingredients and the product with the cell's own face; the three products are summed in the
-// reference's order with shuffles, the precomputed ahead-sum is added and lane l finishes
-// equations l, l + 4, ... . The chain of a plane is
-//     shared memory -> ingredients -> product -> shuffles -> solve -> shared memory.
+// ONE thread per cell. A cell (sweep coordinate I = q - jl - kl at plane q of its line) takes the
+// ingredients of its three behind-neighbours -- the one in i from its own registers (the same
+// thread solved it one plane ago), the ones in j and k from shared memory, where their threads
+// left them --, forms the three products side by side, sums them in the reference's order
+// ((0 + od_i) + od_j) + od_k, adds the precomputed ahead-sum, solves its equations, and leaves its
+// own new ingredients (MakeIngrDyn, once per cell instead of once per neighbour) for the next
+// plane. The chain of a plane is
+//     shared memory -> three products -> solve -> own ingredients -> shared memory -> barrier.
+// Neighbours that are not cells of the pencil are served by the HALO warp, one lane per line on
+// the pencil's two behind-sides: cells of the pencil behind arrive through the mailbox (written
+// by that pencil's boundary lines together with their shared-memory copy), ghost cells across a
+// connection and in front of a line are formed from the block's fields. The halo warp puts them
+// where the walkers look (cross-section padded by one line), so the walkers run one uniform path.
+// Pencils are handed out by an atomic ticket in anti-diagonal order: a pencil's predecessors are
+// always running or done, whatever the number of resident thread blocks.
+//
+// History (192^3, x4 sweeps, wavefront ms per iteration; profiles/r02*): four lanes per cell,
+// each forming its neighbour's ingredients, 8 x 7 / 8 x 8 cells: 18.4 / 17.4 -- fp64 ISSUE bound
+// (a warp instruction costs the same with 8 cells in it as with 32); one thread per cell with
+// progress counters (poller + publisher warp): 15.6, the pencils waiting on each other's
+// st.release.
 template <int NS, int NT, bool FORWARD>
-__global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, kPencilCtasPerSm)
+__global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
     LusgsPencilKernel(BlockDev b, Params p, PencilLattice L, int fullGS,
                       const double *__restrict__ dyn, const double *__restrict__ geo,
                       const double *__restrict__ ahead, const int2 *__restrict__ order,
-                      int nPencils, WaveSync *sync, long long *dbg = nullptr) {
+                      int nPencils, WaveSync *sync, uint4 *mailJ, uint4 *mailK, unsigned tag,
+                      long long *dbg = nullptr) {
   using E = Eq<NS, NT>;
   using R = PencilRec<NS, NT>;
   using C = PencilCfg<NS, NT>;
-  using F = PencilFetch<NS, NT>;
+  using HR = HaloRaw<NS, NT>;
   constexpr int neq = E::neq, nf = NS + 4, S = C::S;
-  constexpr int TJ = kPTJ, TK = kPTK, NCOMP = C::NCOMP;
-  constexpr int kPublish = 4;  // progress is announced every 4th plane (st.release ~1 000 cycles)
-  constexpr int NOWN = (neq + 3) / 4;  // equations finished by one lane
+  constexpr int TJ = kPTJ, TK = kPTK, NCOMP = C::NCOMP, PJ = C::PJ, PCELLS = C::PCELLS, NI = C::NI;
+  constexpr int NH = C::NH, NST = R::NST;
   extern __shared__ __align__(128) unsigned char smemRaw[];
   auto stDyn = [&](int s) { return reinterpret_cast<const double *>(smemRaw + s * C::stageB); };
   auto stGeo = [&](int s) {
@@ -266,23 +338,16 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, kPencilCtasPerSm)
   auto stAh = [&](int s) {
     return reinterpret_cast<const double *>(smemRaw + s * C::stageB + C::dynB + C::geoB);
   };
-  double *sxBase = reinterpret_cast<double *>(smemRaw + S * C::stageB);
-  auto sx = [&](int par, int e, int cell) -> double & {
-    return sxBase[(par * neq + e) * kPCells + cell];
-  };
-  uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + S * C::stageB + C::sxB);
+  double *ingBase = reinterpret_cast<double *>(smemRaw + S * C::stageB);
+  auto ing = [&](int par, int e, int P) -> double & { return ingBase[(par * NI + e) * PCELLS + P]; };
+  double *haloBase = reinterpret_cast<double *>(smemRaw + S * C::stageB + C::ingB);
+  auto haloHd = [&](int par, int h) { return haloBase + (par * NH + h) * NST; };
+  uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + S * C::stageB + C::ingB + C::haloB);
   __shared__ int sTicket;
 
   const int tid = threadIdx.x;
-  const bool isService = tid >= NCOMP;
-  const int lane = tid & 3, cellS = isService ? 0 : tid >> 2;  // cell in sweep space
-  const int jlS = cellS % TJ, klS = cellS / TJ;
-  const int d = lane % 3;  // lane 3 has no neighbour (it mirrors lane 0's direction, unused)
-  const int base = (tid & 31) & ~3;
-  const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+  const int role = tid < NCOMP ? 0 : (tid - NCOMP) / 32 + 1;  // 0 walker, 1 loader + post, 2 / 3 halo
   const int nd[3] = {b.ni, b.nj, b.nk};
-  const long long strideD = Stride(b, d);
-  int *done = sync->done;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) MbarInit(full + s, 1);
@@ -305,26 +370,13 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, kPencilCtasPerSm)
     const long long planeBase = static_cast<long long>(bJ + L.nbJ * bK) * L.planesPer;
     // sweep plane q -> plane of the workspace (geometric numbering)
     auto planeOf = [&](int q) { return FORWARD ? q : nSteps - 1 - q; };
+    // sweep coordinate I -> cell index along the line
+    auto iOf = [&](int I) { return FORWARD ? I : b.ni - 1 - I; };
+    // mailboxes are numbered in sweep space: [pencil][plane of the READER][line][entry]
+    const long long myMail = static_cast<long long>(bc.x + L.nbJ * bc.y) * L.planesPer;
 
-    if (isService) {
-      // ---- service warp. Lane 0 waits for the two pencils behind, lane 1 announces this pencil's
-      // progress (two threads, because st.release is a gpu-scope fence: issued by the polling
-      // thread it sat in series with the poll), lane 2 keeps the ring of plane stages filled.
-      int *myFlag = done + bc.x + L.nbJ * bc.y;
-      const int *flagJ = bc.x > 0 ? done + (bc.x - 1) + L.nbJ * bc.y : nullptr;
-      const int *flagK = bc.y > 0 ? done + bc.x + L.nbJ * (bc.y - 1) : nullptr;
-      // extents of the pencils behind (the clipped pencil is the first one of a backward sweep)
-      const int tjB = FORWARD ? TJ : min(TJ, b.nj - (bJ + 1) * TJ);
-      const int tkB = FORWARD ? TK : min(TK, b.nk - (bK + 1) * TK);
-      int seenJ = 0, seenK = 0;
-      // the foreign cell read at local plane q lies on plane q + tjB - 1 (k: q + tkB - 1) of the
-      // pencil behind
-      auto waitFor = [&](int q) {
-        if (flagJ)
-          while (seenJ < q + tjB) seenJ = LdAcquire(flagJ);
-        if (flagK)
-          while (seenK < q + tkB) seenK = LdAcquire(flagK);
-      };
+    if (role == 1) {
+      // ---- loader: lane 0 keeps the ring of plane stages filled ...
       auto load = [&](int q) {  // plane q of this pencil into its stage
         if (q >= nSteps) return;
         const int s = (fills + q) % S;
@@ -336,168 +388,318 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, kPencilCtasPerSm)
         if (fullGS)
           BulkLoad(smemRaw + s * C::stageB + C::dynB + C::geoB, ahead + slot0 * R::AN, C::ahB, bar);
       };
-      if (tid == NCOMP + 2)
+      // ... and hands the boundary lines of a finished plane to the pencils ahead (mailbox), off the
+      // walkers' chain: lane m < TK posts line (tj - 1, m) for the pencil ahead in j, lane
+      // TK <= m < TK + TJ line (m - TK, tk - 1) for the one ahead in k. Plane q of this pencil is
+      // plane q - (tj - 1) of the reader in j (its line 0 lies tj - 1 planes behind this pencil's
+      // last line), q - (tk - 1) in k.
+      const int m = tid - NCOMP;
+      const bool toJ = m < TK;
+      const int pjS = toJ ? tj - 1 : m - TK, pkS = toJ ? m : tk - 1;
+      const bool posts = m < TK + TJ && pjS < tj && pkS < tk &&
+                         (toJ ? bc.x + 1 < L.nbJ : bc.y + 1 < L.nbK);
+      const int postP = (pjS + 1) + PJ * (pkS + 1);
+      uint4 *out = toJ ? mailJ + ((myMail + L.planesPer - (tj - 1)) * TK + pkS) * NI
+                       : mailK + ((myMail + static_cast<long long>(L.nbJ) * L.planesPer - (tk - 1)) * TJ + pjS) * NI;
+      const int postStride = (toJ ? TK : TJ) * NI;
+      auto post = [&](int q) {
+        const int I = q - pjS - pkS;
+        if (!posts || I < 0 || I >= b.ni) return;
+        uint4 *o = out + static_cast<long long>(q) * postStride;
+#pragma unroll
+        for (int e = 0; e < NI; ++e) MailStore(o + e, ing(q & 1, e, postP), tag);
+      };
+      if (tid == NCOMP)
         for (int q = 0; q < S - 2; ++q) load(q);
-      if (tid == NCOMP) waitFor(1);
-      __syncthreads();
+      NamedBarrier(1, C::threads);
       for (int q = 0; q < nSteps; ++q) {
         // the stage of plane q + S - 2 held plane q - 2: its last readers finished with plane q - 1
-        if (tid == NCOMP + 2) load(q + S - 2);
-        // the lanes fetch the update of their NEXT plane's foreign neighbour at the top of a plane
-        if (tid == NCOMP) waitFor(q + 2);
-        // planes 0 .. q-1 are in global memory
-        if (tid == NCOMP + 1 && q > 0 && (q % kPublish) == 0) StRelease(myFlag, q);
-        __syncthreads();
+        if (tid == NCOMP) load(q + S - 2);
+        if (q > 0) post(q - 1);
+        NamedBarrier(1, C::threads);
       }
-      if (tid == NCOMP + 1) StRelease(myFlag, kWaveDone);
+      post(nSteps - 1);
       fills += nSteps;
       continue;
     }
 
-    // ---- compute threads ---------------------------------------------------------------------
+    if (role >= 2) {
+      // ---- halo warps (role 2: even planes, role 3: odd planes). Lane h < TK: the cell behind (in j) line (0, h); TK <= h < TK + TJ: the
+      // cell behind (in k) line (h - TK, 0); then TK lanes for the ghost cell in front of the line
+      // that starts at this plane (jl = q - kl, kl = h - TK - TJ)
+      const int h = (tid - NCOMP) & 31;
+      const int mine = role - 2;  // parity of the planes this warp serves
+      const int hd = h < TK ? 1 : (h < TK + TJ ? 2 : 0);
+      const long long strideH = Stride(b, hd);
+      const int hd1 = (hd + 1) % 3, hd2 = (hd + 2) % 3;
+      // sweep-space line of the cell this lane serves at plane q
+      auto lineOf = [&](int q, int *jS, int *kS) {
+        if (hd == 1) {
+          *jS = 0;
+          *kS = h;
+        } else if (hd == 2) {
+          *jS = h - TK;
+          *kS = 0;
+        } else {
+          *kS = h - TK - TJ;
+          *jS = q - *kS;
+        }
+        return h < NH && q < nSteps && *jS >= 0 && *jS < tj && *kS < tk;
+      };
+      // neighbour in the pencil behind (not at the block's face): mailbox of this pencil
+      const bool fromPencil = hd == 1 ? bc.x > 0 : (hd == 2 ? bc.y > 0 : false);
+      auto hfetch = [&](int q, HR &f) {
+        f.kind = 0;
+        int jS, kS;
+        if (!lineOf(q, &jS, &kS)) return;
+        const int I = q - jS - kS;
+        if (I < 0 || I >= b.ni) return;
+        const int j = j0 + (FORWARD ? jS : tj - 1 - jS), k = k0 + (FORWARD ? kS : tk - 1 - kS);
+        const int c[3] = {iOf(I), j, k};
+        if (fromPencil) {
+          int cn[3] = {c[0], c[1], c[2]};
+          cn[hd] += FORWARD ? -1 : 1;
+          const double2 *rec =
+              reinterpret_cast<const double2 *>(dyn + PencilSlot(L, cn[0], cn[1], cn[2]) * R::DN);
+#pragma unroll
+          for (int e = 0; e < NST / 2; ++e) {
+            const double2 v = __ldg(rec + e);
+            f.hd[2 * e] = v.x;
+            f.hd[2 * e + 1] = v.y;
+          }
+          if (NST & 1) f.hd[NST - 1] = __ldg(reinterpret_cast<const double *>(rec) + NST - 1);
+          f.mail = (hd == 1 ? mailJ + ((myMail + q) * TK + kS) * NI
+                            : mailK + ((myMail + q) * TJ + jS) * NI);
+#pragma unroll
+          for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e);
+          f.kind = 1;
+          return;
+        }
+        // ghost cell: does it contribute (across a connection; ref src/procBlock.cpp:1064,1115;
+        // behind = lower side in a forward sweep)?
+        if (!ConnAcross(b, FORWARD ? 2 * hd + 1 : 2 * hd + 2, c[hd1], nd[hd1], c[hd2])) return;
+        const long long idx = CellIdx(b, c[0], j, k);
+        const long long nidx = FORWARD ? idx - strideH : idx + strideH;
+        LoadCell<neq>(b.state, b.fs, nidx, f.hd);
+#pragma unroll
+        for (int e = 0; e < neq; ++e) {
+          const double v = __ldcg(b.x + e * b.fs + nidx);
+          f.ent[e] = make_uint4(__double2loint(v), tag, __double2hiint(v), tag);
+        }
+        f.mu = f.mut = f.f1 = 0.0;
+        if (p.isViscous) {
+          f.mu = __ldg(b.viscosity + nidx);
+          if (NT > 0) {
+            f.mut = __ldg(b.eddyVisc + nidx);
+            f.f1 = __ldg(b.f1 + nidx);
+          }
+        }
+        f.kind = 2;
+      };
+      auto hstore = [&](int q, HR &f) {
+        if (f.kind == 0) return;
+        int jS, kS;
+        lineOf(q, &jS, &kS);
+        double v[NI];
+        if (f.kind == 1) {
+          // The pencil behind may not be there yet. Pencils run at the same pace, so a pencil that
+          // has caught up waits here every plane: poll ONE entry, with a pause, and re-read the
+          // rest only when it has arrived -- a lane that re-reads everything back to back fills
+          // the SM's load / store queue and the walkers' shared-memory loads queue behind it
+          // (ncu, profiles/r02z: their loop body took twice as long under load as alone).
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int e = 0; e < NI; ++e) ok = ok && f.ent[e].y == tag && f.ent[e].w == tag;
+            if (ok) break;
+            for (;;) {
+              const uint4 w = MailLoad(f.mail + NI - 1);
+              if (w.y == tag && w.w == tag) break;
+              __nanosleep(200);
+            }
+#pragma unroll
+            for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e);
+          }
+#pragma unroll
+          for (int e = 0; e < NI; ++e) v[e] = __hiloint2double(f.ent[e].z, f.ent[e].x);
+        } else {
+#pragma unroll
+          for (int e = 0; e < neq; ++e) v[e] = __hiloint2double(f.ent[e].z, f.ent[e].x);
+          HeadFromState<NS, NT>(p, f.hd, f.mu, f.mut, f.f1);
+          MakeIngrDyn<NS, NT>(p.gas, f.hd, v, v + neq, v + 2 * neq);
+        }
+        double *o = haloHd(q & 1, h);
+#pragma unroll
+        for (int e = 0; e < NST; ++e) o[e] = f.hd[e];
+        // where the walker of plane q looks for this neighbour: one line behind in j / k, or (line
+        // start) at its own place
+        const int P = (hd == 1 ? 0 : jS + 1) + PJ * (hd == 2 ? 0 : kS + 1);
+        const int par = (q + 1) & 1;
+#pragma unroll
+        for (int e = 0; e < NI; ++e) ing(par, e, P) = v[e];
+      };
+      // The loads of plane q + 3 are issued during plane q, right after the halo of plane q + 1 has
+      // been put in place, and are used during plane q + 2: a whole plane in flight. (One warp
+      // doing every plane had either its loads or -- one scoreboard counts both -- the loads just
+      // issued in its way: 39 % of its time, profiles/r02x.)
+      HR hr;
+      if (mine == 0) {
+        hfetch(0, hr);
+        hstore(0, hr);
+        hfetch(2, hr);
+      } else {
+        hfetch(1, hr);
+      }
+      NamedBarrier(1, C::threads);
+      for (int q = 0; q < nSteps; ++q) {
+        if (((q + 1) & 1) == mine) {
+          hstore(q + 1, hr);
+          hfetch(q + 3, hr);
+        }
+        NamedBarrier(1, C::threads);
+      }
+      fills += nSteps;
+      continue;
+    }
+
+    // ---- walkers -------------------------------------------------------------------------------
+    const int jlS = tid % TJ, klS = tid / TJ;  // line in sweep space
+    const int P = (jlS + 1) + PJ * (klS + 1);
     // sweep-local line (jlS, klS) -> line of the block; the workspace numbers cells geometrically
     const bool lineValid = jlS < tj && klS < tk;
     const int jl = FORWARD ? jlS : tj - 1 - jlS, kl = FORWARD ? klS : tk - 1 - klS;
     const int j = j0 + jl, k = k0 + kl;
     const int cellG = lineValid ? jl + TJ * kl : 0;
-    // the behind-neighbour in this lane's direction: cell of the workspace plane, inside the pencil?
-    const int nbCellG = d == 0 ? cellG
-                               : (d == 1 ? (FORWARD ? cellG - 1 : cellG + 1)
-                                         : (FORWARD ? cellG - TJ : cellG + TJ));
-    const bool nbInside = d == 0 ? true : (d == 1 ? jlS > 0 : klS > 0);
+    const int nbG1 = FORWARD ? cellG - 1 : cellG + 1, nbG2 = FORWARD ? cellG - TJ : cellG + TJ;
     const long long idxRow = lineValid ? CellIdx(b, 0, j, k) : 0;
-    // sweep coordinate I -> cell index along the line
-    auto iOf = [&](int I) { return FORWARD ? I : b.ni - 1 - I; };
-
-    // Does the behind-neighbour of the cell solved at plane q contribute (physical cell, or across
-    // a connection: ref src/procBlock.cpp:1064,1115; behind = lower side in a forward sweep), and
-    // is it a cell of this pencil (else: record head formed on the fly, update read at L2)?
-    // Along a line both answers are constants except at the line's first cell (direction i) and
-    // on lines next to a block face with connection patches (the mask varies along i).
-    const bool lineActive = lineValid && lane != 3;
-    const bool onFace = d == 0 ? false : (FORWARD ? (d == 1 ? j == 0 : k == 0)
-                                                  : (d == 1 ? j == b.nj - 1 : k == b.nk - 1));
-    const bool faceHasConn = onFace && b.connFace[FORWARD ? 2 * d : 2 * d + 1] != nullptr;
-    auto classify = [&](int q, bool *use, bool *inside) {
-      const int I = q - jlS - klS;
-      *use = false;
-      *inside = false;
-      if (!lineActive || I < 0 || I >= b.ni) return;
-      if (d == 0) {
-        *inside = I > 0;
-        *use = I > 0 || ConnAcross(b, FORWARD ? 1 : 2, j, b.nj, k);
-      } else {
-        *inside = nbInside;
-        if (!onFace) *use = true;
-        else if (faceHasConn) {
-          const int c[3] = {iOf(I), j, k};
-          *use = ConnAcross(b, FORWARD ? 2 * d + 1 : 2 * d + 2, c[d1], nd[d1], c[d2]);
-        }
-      }
-    };
-    auto fetch = [&](int q, F &f) {
-      bool use, inside;
-      classify(q, &use, &inside);
-      if (!use || inside) return;
-      const long long idx = idxRow + iOf(q - jlS - klS);
-      const long long nidx = FORWARD ? idx - strideD : idx + strideD;
-      MakeHead<NS, NT>(b, p, nidx, f.hd);
-      // updates of other pencils are rewritten during the sweep: L2, never L1
+    // Does a behind-neighbour contribute (physical cell, or across a connection)? Along a line the
+    // answer is constant except at the line's first cell (direction i) and on lines next to a
+    // block face with connection patches (the mask varies along i).
+    const bool use0Start = lineValid && ConnAcross(b, FORWARD ? 1 : 2, j, b.nj, k);
+    const bool onFace1 = FORWARD ? j == 0 : j == b.nj - 1, onFace2 = FORWARD ? k == 0 : k == b.nk - 1;
+    const bool conn1 = onFace1 && b.connFace[FORWARD ? 2 : 3] != nullptr;
+    const bool conn2 = onFace2 && b.connFace[FORWARD ? 4 : 5] != nullptr;
+    // ingredients of this line's previous cell (the behind-neighbour in i), carried in registers
+    double pHd[NST], pDu[neq], pSn[neq], pHn = 0.0;
 #pragma unroll
-      for (int e = 0; e < neq; ++e) f.du[e] = __ldcg(b.x + e * b.fs + nidx);
-    };
+    for (int e = 0; e < NST; ++e) pHd[e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < neq; ++e) pDu[e] = pSn[e] = 0.0;
 
-    auto step = [&](int q, const F &f, F &fNext) {
-      fetch(q + 1, fNext);  // in flight during this plane
+    auto step = [&](int q) {
       const int I = q - jlS - klS;
       const bool active = lineValid && I >= 0 && I < b.ni;
-      bool use, inside;
-      classify(q, &use, &inside);
       const int g = fills + q;
       const int s = g % S, sPrev = (g + S - 1) % S;
-      const bool rec_ = dbg != nullptr && blockIdx.x == 0 && tid == 0 && fills == 0 && q >= 64 && q < 96;
-      if (rec_) dbg[(q - 64) * 8 + 0] = clock64();
       MbarWait(full + s, (g / S) & 1);
-      if (rec_) dbg[(q - 64) * 8 + 1] = clock64();
-      const double *myDyn = stDyn(s) + cellG * R::DN;
-      // this lane's equations: right-hand side, D^-1, ahead-sum -- read before the product starts
-      double ownB[NOWN], ownD[NOWN], ownA[NOWN];
-#pragma unroll
-      for (int hh = 0; hh < NOWN; ++hh) {
-        const int e = lane + 4 * hh;
-        if (e < neq) {
-          ownB[hh] = myDyn[R::iB + e];
-          ownD[hh] = myDyn[R::iD + (e < nf ? 0 : 1)];
-          ownA[hh] = fullGS ? stAh(s)[cellG * R::AN + e] : 0.0;
-        }
-      }
-      double od[neq];
-#pragma unroll
-      for (int e = 0; e < neq; ++e) od[e] = 0.0;
-      if (use) {
-        double hd[R::NST], du[neq], sn[neq], Hn;
-        if (inside) {
-          const double *nb = stDyn(sPrev) + nbCellG * R::DN;
-#pragma unroll
-          for (int e = 0; e < R::NST; ++e) hd[e] = nb[e];
-#pragma unroll
-          for (int e = 0; e < neq; ++e) du[e] = sx((q + 1) & 1, e, nbCellG);
-        } else {
-#pragma unroll
-          for (int e = 0; e < R::NST; ++e) hd[e] = f.hd[e];
-#pragma unroll
-          for (int e = 0; e < neq; ++e) du[e] = f.du[e];
-        }
+      if (active) {
+        const int ic = iOf(I);
+        const double *myDyn = stDyn(s) + cellG * R::DN;
         const double *gg = stGeo(s) + cellG * R::GN;
-        double fa[4];
+        const int parR = (q + 1) & 1;
+        if (I == 0) {  // line start: the ghost cell in front of the line, from the halo warp
+          const double *hp = haloHd(q & 1, TK + TJ + klS);
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) fa[qq] = gg[4 * d + qq];
-        const double len = gg[12 + d];
-        MakeIngrDyn<NS, NT>(p.gas, hd, du, sn, &Hn);
-        auto ld = [&](int cc) {
-          return cc < neq + 2 ? hd[cc]
-                              : (cc < 2 * neq + 2 ? du[cc - neq - 2]
-                                                  : (cc < 3 * neq + 2 ? sn[cc - 2 * neq - 2] : Hn));
+          for (int e = 0; e < NST; ++e) pHd[e] = hp[e];
+#pragma unroll
+          for (int e = 0; e < neq; ++e) {
+            pDu[e] = ing(parR, e, P);
+            pSn[e] = ing(parR, neq + e, P);
+          }
+          pHn = ing(parR, 2 * neq, P);
+        }
+        // The three products are formed unconditionally and side by side (independent chains); a
+        // neighbour that does not contribute (block face without connection) is dropped by a
+        // select, so whatever its slot holds never reaches the sum.
+        const bool use0 = I > 0 || use0Start;
+        const bool use1 = !onFace1 || (conn1 && ConnAcross(b, FORWARD ? 3 : 4, k, b.nk, ic));
+        const bool use2 = !onFace2 || (conn2 && ConnAcross(b, FORWARD ? 5 : 6, ic, b.ni, j));
+        auto product = [&](int d, const double *hd, const double *du, const double *sn,
+                           double Hn, double *od) {
+          double fa[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) fa[qq] = gg[4 * d + qq];
+          const double len = gg[12 + d];
+          auto ld = [&](int cc) {
+            return cc < neq + 2 ? hd[cc]
+                                : (cc < 2 * neq + 2 ? du[cc - neq - 2]
+                                                    : (cc < 3 * neq + 2 ? sn[cc - 2 * neq - 2] : Hn));
+          };
+#pragma unroll
+          for (int e = 0; e < neq; ++e) od[e] = 0.0;
+          OffDiagFromIngr<NS, NT>(ld, fa, FORWARD, od, len * hd[R::iVt], len * hd[R::iVtT]);
         };
-        OffDiagFromIngr<NS, NT>(ld, fa, FORWARD, od, len * hd[R::iVt], len * hd[R::iVtT]);
-      }
-      if (rec_) dbg[(q - 64) * 8 + 2] = clock64() + (od[0] == 1.2345e300);
-      // behind-sum (od_i + od_j) + od_k in every lane by a butterfly: lanes (0,1) and (2,3) swap,
-      // then the pairs swap; lane 3 holds zero and addition commutes, so each lane forms exactly
-      // the reference's ((0 + od_i) + od_j) + od_k. Then this lane's equations.
-      // forward: x = D^-1 (b + (L - U)); backward: D^-1 ((b + L) - U), or on the first sweep
-      // without initialisation x - D^-1 U (ref src/linearSolver.cpp:341-428)
+        auto fromSmem = [&](int d, const double *hdp, int Pn, double *od) {
+          double hd[NST], du[neq], sn[neq];
 #pragma unroll
-      for (int e = 0; e < neq; ++e) {
-        const double pr = od[e] + __shfl_xor_sync(0xffffffffu, od[e], 1);
-        const double other = __shfl_xor_sync(0xffffffffu, pr, 2);
-        const double bs = (lane & 2) ? other + pr : pr + other;
-        if ((e & 3) == lane && active) {
-          const double as = fullGS ? ownA[e >> 2] : 0.0;
-          const double rb = ownB[e >> 2];
+          for (int e = 0; e < NST; ++e) hd[e] = hdp[e];
+#pragma unroll
+          for (int e = 0; e < neq; ++e) {
+            du[e] = ing(parR, e, Pn);
+            sn[e] = ing(parR, neq + e, Pn);
+          }
+          product(d, hd, du, sn, ing(parR, 2 * neq, Pn), od);
+        };
+        double od0[neq], od1[neq], od2[neq];
+        product(0, pHd, pDu, pSn, pHn, od0);
+        fromSmem(1, jlS > 0 ? stDyn(sPrev) + nbG1 * R::DN : haloHd(q & 1, klS), P - 1, od1);
+        fromSmem(2, klS > 0 ? stDyn(sPrev) + nbG2 * R::DN : haloHd(q & 1, TK + jlS), P - PJ, od2);
+        // forward: x = D^-1 (b + (L - U)); backward: D^-1 ((b + L) - U), or on the first sweep
+        // without initialisation x - D^-1 U (ref src/linearSolver.cpp:341-428)
+#pragma unroll
+        for (int e = 0; e < NST; ++e) pHd[e] = myDyn[e];
+        const double *ah = stAh(s) + cellG * R::AN;
+#pragma unroll
+        for (int e = 0; e < neq; ++e) {
+          double bs = 0.0;
+          bs = use0 ? bs + od0[e] : bs;
+          bs = use1 ? bs + od1[e] : bs;
+          bs = use2 ? bs + od2[e] : bs;
+          const double as = fullGS ? ah[e] : 0.0;
+          const double rb = myDyn[R::iB + e];
           double r;
           if (FORWARD) r = rb + (bs - as);
           else if (fullGS) r = (rb + as) - bs;
           else r = bs;
-          r *= ownD[e >> 2];
-          const long long gi = e * b.fs + idxRow + iOf(I);
+          r *= myDyn[R::iD + (e < nf ? 0 : 1)];
+          const long long gi = e * b.fs + idxRow + ic;
           if (!FORWARD && !fullGS) r = b.x[gi] - r;
-          sx(q & 1, e, cellG) = r;
+          pDu[e] = r;
           __stcg(b.x + gi, r);
         }
+        MakeIngrDyn<NS, NT>(p.gas, pHd, pDu, pSn, &pHn);
+        const int parW = q & 1;
+#pragma unroll
+        for (int e = 0; e < neq; ++e) {
+          ing(parW, e, P) = pDu[e];
+          ing(parW, neq + e, P) = pSn[e];
+        }
+        ing(parW, 2 * neq, P) = pHn;
       }
-      if (rec_) dbg[(q - 64) * 8 + 3] = clock64();
-      __syncthreads();
-      if (rec_) dbg[(q - 64) * 8 + 4] = clock64();
+      NamedBarrier(1, C::threads);
     };
 
-    __syncthreads();  // the poller has seen what planes 0 and 1 read
-    F fa_, fb_;
-    fetch(0, fa_);
-    for (int q = 0; q < nSteps; q += 2) {
-      step(q, fa_, fb_);
-      if (q + 1 < nSteps) step(q + 1, fb_, fa_);
+    // AITHER_B200_LUSGS_DBG=<file>: time line of every pencil (ticket drawn, planes 0, 32, 64, 96,
+    // 128 reached, last plane done)
+    auto stamp = [&](int slot) {
+      if (dbg != nullptr && tid == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[ticket * 8 + slot] = t;
+        if (slot == 0) {
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          dbg[ticket * 8 + 7] = bc.x + 1000 * bc.y + 1000000LL * smid;
+        }
+      }
+    };
+    stamp(0);
+    NamedBarrier(1, C::threads);
+    for (int q = 0; q < nSteps; ++q) {
+      if ((q & 31) == 0 && q <= 128) stamp(1 + (q >> 5));
+      step(q);
     }
+    stamp(6);
     fills += nSteps;
   }
 }
