@@ -628,21 +628,22 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   static int dbgCount = 0;
   const char *dbgFile = getenv("AITHER_B200_LUSGS_DBG");
   if (dbgFile && !dbg) {
-    cudaMalloc(&dbg, sizeof(long long) * 8 * hb.wavePencils);
-    cudaMemset(dbg, 0, sizeof(long long) * 8 * hb.wavePencils);
+    cudaMalloc(&dbg, sizeof(long long) * (8 * hb.wavePencils + 512));
+    cudaMemset(dbg, 0, sizeof(long long) * (8 * hb.wavePencils + 512));
   }
   const bool record = dbg && forward && ++dbgCount == 6;
+  static const int dbgFlags = getenv("AITHER_B200_LUSGS_DBGFLAGS") ? atoi(getenv("AITHER_B200_LUSGS_DBGFLAGS")) : 0;
   if (forward)
     fwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
         b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoLo, hb.dWaveAhead, hb.dWaveOrder,
         hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag,
-        record ? dbg : nullptr);
+        record ? dbg : nullptr, dbgFlags);
   else
     bwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
         b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoHi, hb.dWaveAhead, hb.dWaveOrder,
-        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, nullptr);
+        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, nullptr, dbgFlags);
   if (record) {
-    std::vector<long long> hbuf(8 * hb.wavePencils);
+    std::vector<long long> hbuf(8 * hb.wavePencils + 512);
     cudaStreamSynchronize(h->stream);
     cudaMemcpy(hbuf.data(), dbg, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost);
     if (FILE *f = fopen(dbgFile, "w")) {

@@ -233,9 +233,9 @@ struct PencilCfg {
   static constexpr int neq = NS + 4 + NT;
   static constexpr int NCOMP = kPCells;  // one thread per grid line of the pencil
   static_assert(NCOMP % 32 == 0, "the walkers fill whole warps");
-  // + three warps: loader (ring of plane stages; posts the boundary lines) and two halo warps
-  // (ingredients of the neighbours outside the pencil, even / odd planes)
-  static constexpr int threads = NCOMP + 96;
+  // + four service warps taking turns as loader (ring of plane stages), mailbox writer (boundary
+  // lines for the pencils ahead) and halo (ingredients of the neighbours outside the pencil)
+  static constexpr int threads = NCOMP + 128;
   static constexpr int NH = kPTJ + 2 * kPTK;  // halo lanes: column behind in j, row behind in k, line starts
   static_assert(NH <= 32, "one warp prepares the halo of a plane");
   static constexpr int dynB = kPCells * R::DN * 8, geoB = kPCells * R::GN * 8, ahB = kPCells * R::AN * 8;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
                       const double *__restrict__ dyn, const double *__restrict__ geo,
                       const double *__restrict__ ahead, const int2 *__restrict__ order,
                       int nPencils, WaveSync *sync, uint4 *mailJ, uint4 *mailK, unsigned tag,
-                      long long *dbg = nullptr) {
+                      long long *dbg = nullptr, int dbgFlags = 0) {
   using E = Eq<NS, NT>;
   using R = PencilRec<NS, NT>;
   using C = PencilCfg<NS, NT>;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
   __shared__ int sTicket;
 
   const int tid = threadIdx.x;
-  const int role = tid < NCOMP ? 0 : (tid - NCOMP) / 32 + 1;  // 0 walker, 1 loader + post, 2 / 3 halo
+  const int role = tid < NCOMP ? 0 : (tid - NCOMP) / 32 + 1;  // 0 walker, 1 .. 4 service
   const int nd[3] = {b.ni, b.nj, b.nk};
 
   if (tid == 0) {
@@ -374,9 +374,17 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
     auto iOf = [&](int I) { return FORWARD ? I : b.ni - 1 - I; };
     // mailboxes are numbered in sweep space: [pencil][plane of the READER][line][entry]
     const long long myMail = static_cast<long long>(bc.x + L.nbJ * bc.y) * L.planesPer;
-
-    if (role == 1) {
-      // ---- loader: lane 0 keeps the ring of plane stages filled ...
+    if (role != 0) {
+      // ---- four service warps, taking turns: warp w serves the planes p = w (mod 4). During
+      // plane p - 3 it loads what the halo of plane p needs, during plane p - 1 it puts that halo in
+      // place; during plane p - 2 it is the loader (ring of plane stages) and hands the boundary
+      // lines of the plane just finished to the pencils ahead. Each of these is a few hundred
+      // dependent instructions of ONE warp -- about as long as the walkers' plane; taking turns
+      // keeps them off the plane's critical path (one halo warp: 0.94 -> 1.4 us per plane for a
+      // pencil with both neighbours behind, profiles/r02y).
+      const int w = role - 1;
+      const int h = tid & 31;
+      // -- loader
       auto load = [&](int q) {  // plane q of this pencil into its stage
         if (q >= nSteps) return;
         const int s = (fills + q) % S;
@@ -388,47 +396,31 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
         if (fullGS)
           BulkLoad(smemRaw + s * C::stageB + C::dynB + C::geoB, ahead + slot0 * R::AN, C::ahB, bar);
       };
-      // ... and hands the boundary lines of a finished plane to the pencils ahead (mailbox), off the
-      // walkers' chain: lane m < TK posts line (tj - 1, m) for the pencil ahead in j, lane
+      // -- mailbox out: lane m < TK posts line (tj - 1, m) for the pencil ahead in j, lane
       // TK <= m < TK + TJ line (m - TK, tk - 1) for the one ahead in k. Plane q of this pencil is
       // plane q - (tj - 1) of the reader in j (its line 0 lies tj - 1 planes behind this pencil's
       // last line), q - (tk - 1) in k.
-      const int m = tid - NCOMP;
-      const bool toJ = m < TK;
-      const int pjS = toJ ? tj - 1 : m - TK, pkS = toJ ? m : tk - 1;
-      const bool posts = m < TK + TJ && pjS < tj && pkS < tk &&
+      const bool toJ = h < TK;
+      const int pjS = toJ ? tj - 1 : h - TK, pkS = toJ ? h : tk - 1;
+      const bool posts = h < TK + TJ && pjS < tj && pkS < tk &&
                          (toJ ? bc.x + 1 < L.nbJ : bc.y + 1 < L.nbK);
       const int postP = (pjS + 1) + PJ * (pkS + 1);
-      uint4 *out = toJ ? mailJ + ((myMail + L.planesPer - (tj - 1)) * TK + pkS) * NI
-                       : mailK + ((myMail + static_cast<long long>(L.nbJ) * L.planesPer - (tk - 1)) * TJ + pjS) * NI;
-      const int postStride = (toJ ? TK : TJ) * NI;
+      // a mailbox plane is entry-major, [entry][line]: the lanes of one load / store instruction
+      // touch one or two 128-byte lines (line-major, every lane its own line: the load / store
+      // unit took them one line per cycle, in the way of the walkers' shared-memory traffic)
+      const int postLines = toJ ? TK : TJ;
+      uint4 *out = toJ ? mailJ + (myMail + L.planesPer - (tj - 1)) * (TK * NI) + pkS
+                       : mailK + (myMail + static_cast<long long>(L.nbJ) * L.planesPer - (tk - 1)) * (TJ * NI) + pjS;
       auto post = [&](int q) {
         const int I = q - pjS - pkS;
-        if (!posts || I < 0 || I >= b.ni) return;
-        uint4 *o = out + static_cast<long long>(q) * postStride;
+        if (!posts || I < 0 || I >= b.ni || (dbgFlags & 2)) return;
+        uint4 *o = out + static_cast<long long>(q) * (postLines * NI);
 #pragma unroll
-        for (int e = 0; e < NI; ++e) MailStore(o + e, ing(q & 1, e, postP), tag);
+        for (int e = 0; e < NI; ++e) MailStore(o + e * postLines, ing(q & 1, e, postP), tag);
       };
-      if (tid == NCOMP)
-        for (int q = 0; q < S - 2; ++q) load(q);
-      NamedBarrier(1, C::threads);
-      for (int q = 0; q < nSteps; ++q) {
-        // the stage of plane q + S - 2 held plane q - 2: its last readers finished with plane q - 1
-        if (tid == NCOMP) load(q + S - 2);
-        if (q > 0) post(q - 1);
-        NamedBarrier(1, C::threads);
-      }
-      post(nSteps - 1);
-      fills += nSteps;
-      continue;
-    }
-
-    if (role >= 2) {
-      // ---- halo warps (role 2: even planes, role 3: odd planes). Lane h < TK: the cell behind (in j) line (0, h); TK <= h < TK + TJ: the
-      // cell behind (in k) line (h - TK, 0); then TK lanes for the ghost cell in front of the line
-      // that starts at this plane (jl = q - kl, kl = h - TK - TJ)
-      const int h = (tid - NCOMP) & 31;
-      const int mine = role - 2;  // parity of the planes this warp serves
+      // -- halo in. Lane h < TK: the cell behind (in j) line (0, h); TK <= h < TK + TJ: the cell
+      // behind (in k) line (h - TK, 0); then TK lanes for the ghost cell in front of the line that
+      // starts at this plane (jl = q - kl, kl = h - TK - TJ)
       const int hd = h < TK ? 1 : (h < TK + TJ ? 2 : 0);
       const long long strideH = Stride(b, hd);
       const int hd1 = (hd + 1) % 3, hd2 = (hd + 2) % 3;
@@ -448,6 +440,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
       };
       // neighbour in the pencil behind (not at the block's face): mailbox of this pencil
       const bool fromPencil = hd == 1 ? bc.x > 0 : (hd == 2 ? bc.y > 0 : false);
+      const int mailLines = hd == 1 ? TK : TJ;
       auto hfetch = [&](int q, HR &f) {
         f.kind = 0;
         int jS, kS;
@@ -456,6 +449,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
         if (I < 0 || I >= b.ni) return;
         const int j = j0 + (FORWARD ? jS : tj - 1 - jS), k = k0 + (FORWARD ? kS : tk - 1 - kS);
         const int c[3] = {iOf(I), j, k};
+        if (fromPencil && (dbgFlags & 1)) return;
         if (fromPencil) {
           int cn[3] = {c[0], c[1], c[2]};
           cn[hd] += FORWARD ? -1 : 1;
@@ -468,10 +462,9 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
             f.hd[2 * e + 1] = v.y;
           }
           if (NST & 1) f.hd[NST - 1] = __ldg(reinterpret_cast<const double *>(rec) + NST - 1);
-          f.mail = (hd == 1 ? mailJ + ((myMail + q) * TK + kS) * NI
-                            : mailK + ((myMail + q) * TJ + jS) * NI);
+          f.mail = hd == 1 ? mailJ + (myMail + q) * (TK * NI) + kS : mailK + (myMail + q) * (TJ * NI) + jS;
 #pragma unroll
-          for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e);
+          for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e * mailLines);
           f.kind = 1;
           return;
         }
@@ -504,21 +497,19 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
         if (f.kind == 1) {
           // The pencil behind may not be there yet. Pencils run at the same pace, so a pencil that
           // has caught up waits here every plane: poll ONE entry, with a pause, and re-read the
-          // rest only when it has arrived -- a lane that re-reads everything back to back fills
-          // the SM's load / store queue and the walkers' shared-memory loads queue behind it
-          // (ncu, profiles/r02z: their loop body took twice as long under load as alone).
+          // rest only when it has arrived.
           for (;;) {
-            bool ok = true;
+            unsigned bad = 0;
 #pragma unroll
-            for (int e = 0; e < NI; ++e) ok = ok && f.ent[e].y == tag && f.ent[e].w == tag;
-            if (ok) break;
+            for (int e = 0; e < NI; ++e) bad |= (f.ent[e].y ^ tag) | (f.ent[e].w ^ tag);
+            if (bad == 0 || (dbgFlags & 4)) break;
             for (;;) {
-              const uint4 w = MailLoad(f.mail + NI - 1);
-              if (w.y == tag && w.w == tag) break;
+              const uint4 t = MailLoad(f.mail + (NI - 1) * mailLines);
+              if (t.y == tag && t.w == tag) break;
               __nanosleep(200);
             }
 #pragma unroll
-            for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e);
+            for (int e = 0; e < NI; ++e) f.ent[e] = MailLoad(f.mail + e * mailLines);
           }
 #pragma unroll
           for (int e = 0; e < NI; ++e) v[e] = __hiloint2double(f.ent[e].z, f.ent[e].x);
@@ -538,26 +529,31 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
 #pragma unroll
         for (int e = 0; e < NI; ++e) ing(par, e, P) = v[e];
       };
-      // The loads of plane q + 3 are issued during plane q, right after the halo of plane q + 1 has
-      // been put in place, and are used during plane q + 2: a whole plane in flight. (One warp
-      // doing every plane had either its loads or -- one scoreboard counts both -- the loads just
-      // issued in its way: 39 % of its time, profiles/r02x.)
       HR hr;
-      if (mine == 0) {
+      hr.kind = 0;
+      if (w == 0) {
         hfetch(0, hr);
         hstore(0, hr);
-        hfetch(2, hr);
-      } else {
-        hfetch(1, hr);
+      } else if (w < 3) {
+        hfetch(w, hr);
+      } else if (h == 0) {
+        for (int q = 0; q < S - 2; ++q) load(q);
       }
       NamedBarrier(1, C::threads);
       for (int q = 0; q < nSteps; ++q) {
-        if (((q + 1) & 1) == mine) {
-          hstore(q + 1, hr);
+        const int turn = (q - w) & 3;  // 0: idle, 1: fetch plane q + 3, 2: load + post, 3: halo of q + 1
+        if (turn == 1) {
           hfetch(q + 3, hr);
+        } else if (turn == 2) {
+          // the stage of plane q + S - 2 held plane q - 2: its last readers finished with plane q - 1
+          if (h == 0) load(q + S - 2);
+          if (q > 0) post(q - 1);
+        } else if (turn == 3) {
+          hstore(q + 1, hr);
         }
         NamedBarrier(1, C::threads);
       }
+      if (w == 0) post(nSteps - 1);
       fills += nSteps;
       continue;
     }
