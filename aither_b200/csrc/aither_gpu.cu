@@ -150,6 +150,7 @@ struct HostBlock {
   double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr, *dWaveAhead = nullptr;
   uint4 *dWaveMailJ = nullptr, *dWaveMailK = nullptr;  // hand-over between pencils (lusgs_pencil.cuh)
   unsigned waveTag = 0;                                 // number of the half sweep
+  bool waveCarries = false;  // no connections: a half sweep leaves the next one's ahead-sums behind
 };
 
 }  // namespace aither_host
@@ -596,6 +597,11 @@ int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
     WaveGeoKernel<<<grid, blk, 0, h->stream>>>(b, L, h->cfg.isViscous, hb.dWaveGeoLo,
                                                hb.dWaveGeoHi);
   }
+  // without connections the ghost cells of the update never change: half sweeps hand the next
+  // one's ahead-sums on (AITHER_B200_LUSGS_CARRY=0: always the parallel pass, for A/B runs)
+  static const bool carryOff = getenv("AITHER_B200_LUSGS_CARRY") && atoi(getenv("AITHER_B200_LUSGS_CARRY")) == 0;
+  hb.waveCarries = !carryOff;
+  for (int s = 0; s < 6; ++s) hb.waveCarries = hb.waveCarries && b.connFace[s] == nullptr;
   ScopedLaunch sl(h, kFamLusgsPack);
   WaveDynKernel<NS, NT><<<grid, blk, 0, h->stream>>>(b, h->params, L, hb.dWaveDyn);
   return 0;
@@ -623,6 +629,7 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
     CK(cudaMemsetAsync(hb.dWaveMailK, 0, bytesK, h->stream));
   }
   if (++hb.waveTag == 0) ++hb.waveTag;  // 0 is what an untouched mailbox holds
+  double *carry = hb.waveCarries ? hb.dWaveAhead : nullptr;
   // AITHER_B200_LUSGS_DBG=<file>: the time line of the pencils of the 6th forward launch
   static long long *dbg = nullptr;
   static int dbgCount = 0;
@@ -636,12 +643,12 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   if (forward)
     fwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
         b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoLo, hb.dWaveAhead, hb.dWaveOrder,
-        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag,
+        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, carry,
         record ? dbg : nullptr, dbgFlags);
   else
     bwd<<<grid, C::threads, C::smemBytes, h->stream>>>(
         b, h->params, L, fullGS, hb.dWaveDyn, hb.dWaveGeoHi, hb.dWaveAhead, hb.dWaveOrder,
-        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, nullptr, dbgFlags);
+        hb.wavePencils, hb.dWaveSync, hb.dWaveMailJ, hb.dWaveMailK, hb.waveTag, carry, nullptr, dbgFlags);
   if (record) {
     std::vector<long long> hbuf(8 * hb.wavePencils + 512);
     cudaStreamSynchronize(h->stream);
@@ -969,7 +976,10 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
           }
         };
         if constexpr (JAC == kJacScalar) {
-          if (h->lusgsWave && fullGS && LaunchLusgsAhead<NS, NT>(h, hb, forward)) return 1;
+          // the ahead-sums of this half sweep: left behind by the previous half sweep of this
+          // iteration, unless ghost cells changed in between (connections) or there was none
+          const bool carried = hb.waveCarries && !(s == 0 && forward);
+          if (h->lusgsWave && fullGS && !carried && LaunchLusgsAhead<NS, NT>(h, hb, forward)) return 1;
         }
         ScopedLaunch sl(h, kFamLusgs);  // one timing record per half sweep
         if (h->lusgsWave) {

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
                       const double *__restrict__ dyn, const double *__restrict__ geo,
                       const double *__restrict__ ahead, const int2 *__restrict__ order,
                       int nPencils, WaveSync *sync, uint4 *mailJ, uint4 *mailK, unsigned tag,
-                      long long *dbg = nullptr, int dbgFlags = 0) {
+                      double *__restrict__ carry, long long *dbg = nullptr, int dbgFlags = 0) {
   using E = Eq<NS, NT>;
   using R = PencilRec<NS, NT>;
   using C = PencilCfg<NS, NT>;
@@ -645,12 +645,16 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
 #pragma unroll
         for (int e = 0; e < NST; ++e) pHd[e] = myDyn[e];
         const double *ah = stAh(s) + cellG * R::AN;
+        double bsv[R::AN];
+#pragma unroll
+        for (int e = neq; e < R::AN; ++e) bsv[e] = 0.0;
 #pragma unroll
         for (int e = 0; e < neq; ++e) {
           double bs = 0.0;
           bs = use0 ? bs + od0[e] : bs;
           bs = use1 ? bs + od1[e] : bs;
           bs = use2 ? bs + od2[e] : bs;
+          bsv[e] = bs;
           const double as = fullGS ? ah[e] : 0.0;
           const double rb = myDyn[R::iB + e];
           double r;
@@ -662,6 +666,16 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
           if (!FORWARD && !fullGS) r = b.x[gi] - r;
           pDu[e] = r;
           __stcg(b.x + gi, r);
+        }
+        // The sum over this sweep's behind-neighbours with their NEW update is the next half
+        // sweep's sum over its ahead-neighbours with their OLD update (same neighbours, same
+        // update, same faces): it goes where this plane's ahead-sum came from, and the parallel
+        // ahead-sum pass (LusgsAheadKernel) is only needed before the first sweep of an iteration
+        // and for blocks whose ghost cells change between half sweeps (connections).
+        if (carry != nullptr) {
+          double2 *o = reinterpret_cast<double2 *>(carry + ((planeBase + planeOf(q)) * kPCells + cellG) * R::AN);
+#pragma unroll
+          for (int e = 0; e < R::AN / 2; ++e) __stcg(o + e, make_double2(bsv[2 * e], bsv[2 * e + 1]));
         }
         MakeIngrDyn<NS, NT>(p.gas, pHd, pDu, pSn, &pHn);
         const int parW = q & 1;
