@@ -67,7 +67,7 @@ struct PencilRec {
   static constexpr int NST = neq + 4;  // record head: s | H a vt vtT
   // per-block record: behind-side faces i, j, k {nx, ny, nz, |A|} | |A| / dist for i, j, k | pad
   static constexpr int GN = 18;
-  static constexpr int AN = (neq + 1) & ~1;  // ahead-sum, 16-byte words
+  static constexpr int AN = neq;  // ahead-sum: component-major within a plane, [plane][e][cell]
 };
 
 // plane-major slot of a cell: pencils tile (j, k) from 0; plane q = i + jl + kl of its pencil
@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(128)
     // the ahead-neighbour is the geometrically upper one in a forward sweep
     OffDiagFromIngr<NS, NT>(ld, g, !FORWARD, acc, len * hd[R::iVt], len * hd[R::iVtT]);
   }
-  double2 *o = reinterpret_cast<double2 *>(ahead + PencilSlot(L, i, j, k) * AN);
+  const long long t = PencilSlot(L, i, j, k);
+  double *o = ahead + (t / kPCells) * (AN * kPCells) + t % kPCells;
 #pragma unroll
-  for (int q = 0; q < AN / 2; ++q) o[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+  for (int e = 0; e < AN; ++e) o[e * kPCells] = acc[e];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -644,10 +645,8 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
         // without initialisation x - D^-1 U (ref src/linearSolver.cpp:341-428)
 #pragma unroll
         for (int e = 0; e < NST; ++e) pHd[e] = myDyn[e];
-        const double *ah = stAh(s) + cellG * R::AN;
-        double bsv[R::AN];
-#pragma unroll
-        for (int e = neq; e < R::AN; ++e) bsv[e] = 0.0;
+        const double *ah = stAh(s) + cellG;
+        double bsv[neq], xn[neq];
 #pragma unroll
         for (int e = 0; e < neq; ++e) {
           double bs = 0.0;
@@ -655,36 +654,52 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
           bs = use1 ? bs + od1[e] : bs;
           bs = use2 ? bs + od2[e] : bs;
           bsv[e] = bs;
-          const double as = fullGS ? ah[e] : 0.0;
+          const double as = fullGS ? ah[e * kPCells] : 0.0;
           const double rb = myDyn[R::iB + e];
           double r;
           if (FORWARD) r = rb + (bs - as);
           else if (fullGS) r = (rb + as) - bs;
           else r = bs;
           r *= myDyn[R::iD + (e < nf ? 0 : 1)];
-          const long long gi = e * b.fs + idxRow + ic;
-          if (!FORWARD && !fullGS) r = b.x[gi] - r;
-          pDu[e] = r;
-          __stcg(b.x + gi, r);
+          if (!FORWARD && !fullGS) r = b.x[e * b.fs + idxRow + ic] - r;
+          xn[e] = r;
         }
+        // the chain first: own new ingredients, handed on through shared memory
+        MakeIngrDyn<NS, NT>(p.gas, pHd, xn, pSn, &pHn);
+        const int parW = q & 1;
+#pragma unroll
+        for (int e = 0; e < neq; ++e) {
+          ing(parW, e, P) = xn[e];
+          ing(parW, neq + e, P) = pSn[e];
+        }
+        ing(parW, 2 * neq, P) = pHn;
+        // ... then what nobody waits for. The update goes to the block's field two cells of the
+        // line at a time (16-byte stores, half the store instructions and sectors): pDu still
+        // holds the update of the line's previous cell (ic - 1 forward, ic + 1 backward).
+        const bool pairHi = (ic & 1) != 0;  // the pair is (ic - 1, ic) or (ic, ic + 1)
+        const long long gi0 = idxRow + ic;
+        if (FORWARD ? pairHi : (!pairHi && I > 0)) {
+#pragma unroll
+          for (int e = 0; e < neq; ++e) {
+            if (FORWARD) __stcg(reinterpret_cast<double2 *>(b.x + e * b.fs + gi0 - 1), make_double2(pDu[e], xn[e]));
+            else __stcg(reinterpret_cast<double2 *>(b.x + e * b.fs + gi0), make_double2(xn[e], pDu[e]));
+          }
+        } else if (FORWARD ? ic == b.ni - 1 : !pairHi) {
+#pragma unroll
+          for (int e = 0; e < neq; ++e) __stcg(b.x + e * b.fs + gi0, xn[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < neq; ++e) pDu[e] = xn[e];
         // The sum over this sweep's behind-neighbours with their NEW update is the next half
         // sweep's sum over its ahead-neighbours with their OLD update (same neighbours, same
         // update, same faces): it goes where this plane's ahead-sum came from, and the parallel
         // ahead-sum pass (LusgsAheadKernel) is only needed before the first sweep of an iteration
         // and for blocks whose ghost cells change between half sweeps (connections).
         if (carry != nullptr) {
-          double2 *o = reinterpret_cast<double2 *>(carry + ((planeBase + planeOf(q)) * kPCells + cellG) * R::AN);
+          double *o = carry + (planeBase + planeOf(q)) * (R::AN * kPCells) + cellG;
 #pragma unroll
-          for (int e = 0; e < R::AN / 2; ++e) __stcg(o + e, make_double2(bsv[2 * e], bsv[2 * e + 1]));
+          for (int e = 0; e < neq; ++e) __stcg(o + e * kPCells, bsv[e]);
         }
-        MakeIngrDyn<NS, NT>(p.gas, pHd, pDu, pSn, &pHn);
-        const int parW = q & 1;
-#pragma unroll
-        for (int e = 0; e < neq; ++e) {
-          ing(parW, e, P) = pDu[e];
-          ing(parW, neq + e, P) = pSn[e];
-        }
-        ing(parW, 2 * neq, P) = pHn;
       }
       NamedBarrier(1, C::threads);
     };
