@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
     "aither_gpu_upload_state", "aither_gpu_upload_state_async", "aither_gpu_upload_state_commit",
     "aither_gpu_download_state", "aither_gpu_download_field", "aither_gpu_download_wall_data",
-    "aither_gpu_download_output",
+    "aither_gpu_download_output", "aither_gpu_compute_wall_distance",
     "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
     "aither_gpu_timer_stop", "aither_gpu_launch_count", "aither_gpu_profile_enable",
     "aither_gpu_profile_get", "aither_gpu_kernel_family_name", "aither_gpu_num_kernel_families",
@@ -81,6 +81,7 @@ def load_library():
     L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_download_wall_data.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_download_output.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, pd]
+    L.aither_gpu_compute_wall_distance.argtypes = [vp, pd, C.c_longlong]
     L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
     L.aither_gpu_field_size.restype = C.c_longlong
     L.aither_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -211,7 +212,7 @@ class GridLevel:
         g = self.problem.cfg.numGhosts
         padded = fld in (abi.FIELD_STATE, abi.FIELD_UPDATE, abi.FIELD_TEMPERATURE,
                          abi.FIELD_VISCOSITY, abi.FIELD_EDDY_VISCOSITY, abi.FIELD_F1,
-                         abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD)
+                         abi.FIELD_F2, abi.FIELD_VELOCITY_GRAD, abi.FIELD_WALL_DIST)
         shp = b.padded_shape(g) if padded else (b.nk, b.nj, b.ni)
         return out.reshape(shp + (-1,))
 
@@ -223,6 +224,12 @@ class GridLevel:
         self._check(self._lib.aither_gpu_download_output(self._h, blk, var, species, scale,
                                                          _ptr(out)))
         return out
+
+    def compute_wall_distance(self, wall_face_centers):
+        """wall distance of every block from the centres (n, 3) of all viscous-wall faces, on the
+        device (replaces the set-up's k-d tree search)"""
+        pts = np.ascontiguousarray(wall_face_centers, dtype=np.float64).reshape(-1, 3)
+        self._check(self._lib.aither_gpu_compute_wall_distance(self._h, _ptr(pts), pts.shape[0]))
 
     def wall_data(self, blk, surface):
         """wall variables (y+, shear stress, heat flux, T, mu_t, mu, rho, u_tau, k, omega) of a

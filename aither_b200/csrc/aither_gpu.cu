@@ -148,6 +148,7 @@ struct HostBlock {
   // behind-side face areas for the forward / backward sweep (built once) and the per-iteration
   // record of what does not depend on the update
   double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr, *dWaveAhead = nullptr;
+  double *wallDistSlot = nullptr;
   uint4 *dWaveMailJ = nullptr, *dWaveMailK = nullptr;  // hand-over between pencils (lusgs_pencil.cuh)
   unsigned waveTag = 0;                                 // number of the half sweep
   bool waveCarries = false;  // no connections: a half sweep leaves the next one's ahead-sums behind
@@ -706,10 +707,11 @@ int ExchangeOnComm(aither_gpu *h, int which, cudaStream_t st = nullptr) {
   // src/procBlock.cpp:3064-3085 (eddy viscosity + f1 + f2: three contiguous fields; velocity gradient)
   // only the state of viscous runs needs the edge ghost cells (Green-Gauss stencils); everything
   // else is read face-normal and takes the single-level plan
-  HaloPlan &plan = (which == kHaloState && h->stateNeedsEdges)
+  // (and the wall distance of the set-up, swapped like any slice: src/gridLevel.cpp:261-281)
+  HaloPlan &plan = ((which == kHaloState && h->stateNeedsEdges) || which == kHaloWallDist)
                        ? h->halo
                        : ((which == kHaloUpdate && h->updateOneLayer) ? h->haloUpdate : h->haloFace);
-  const int total = which == kHaloTurb ? 3 : (which == kHaloVelGrad ? 9 : h->neq);
+  const int total = which == kHaloTurb ? 3 : (which == kHaloVelGrad ? 9 : (which == kHaloWallDist ? 1 : h->neq));
   for (int done = 0; done < total;) {
     const int nc = std::min(total - done, h->neq);  // the plan's buffers hold neq components
     HaloFields f;
@@ -717,7 +719,8 @@ int ExchangeOnComm(aither_gpu *h, int which, cudaStream_t st = nullptr) {
       const BlockDev &b = h->blocks[bb].dev;
       double *base = which == kHaloState ? b.state
                      : which == kHaloUpdate ? b.x
-                     : which == kHaloTurb ? b.eddyVisc : b.velGrad;
+                     : which == kHaloTurb ? b.eddyVisc
+                     : which == kHaloWallDist ? b.wallDist : b.velGrad;
       f.base[bb] = base + static_cast<long long>(done) * b.fs;
       f.fs[bb] = b.fs;
     }
@@ -1289,6 +1292,7 @@ AITHER_DEFINE_EQ_OPS(3, 2)
 
 #if !defined(AITHER_EQ_TU)  // the C ABI lives in the main translation unit only
 #include "multigrid.cuh"
+#include "walldist.cuh"
 // =================================================================================================
 extern "C" {
 
@@ -1486,7 +1490,8 @@ int aither_gpu_create(const aither_cfg *cfg, int nLocalBlocks, const aither_bloc
     if (cfg->isViscous) {
       b.temperature = take(1);
       b.viscosity = take(1);
-      b.wallDist = d.wallDist ? take(1) : (take(1), nullptr);
+      hb.wallDistSlot = take(1);  // filled by the caller's array or by aither_gpu_compute_wall_distance
+      b.wallDist = d.wallDist ? hb.wallDistSlot : nullptr;
       for (int q = 0; q < 3; ++q) b.dist[q] = take(1);
     }
     if (h->nt == 0 && cfg->isViscous && (cfg->isBlockMatrix || h->ns > 1 || h->wallLaw))
@@ -2098,6 +2103,9 @@ static int FieldInfo(aither_gpu *h, int blk, int field, const double **ptr, int 
     case AITHER_FIELD_VISCOSITY:
       if (!b.viscosity) return Fail("viscosity is only stored for viscous runs");
       *ptr = b.viscosity; *nc = 1; *padded = true; break;
+    case AITHER_FIELD_WALL_DIST:
+      if (!b.wallDist) return Fail("this run has no wall distance");
+      *ptr = b.wallDist; *nc = 1; *padded = true; break;
     case AITHER_FIELD_PRESSURE_GRAD:
       if (!b.pressGrad) return Fail("the pressure gradient is only kept for runs with non-reflecting BCs");
       *ptr = b.pressGrad; *nc = 3; *padded = false; break;
@@ -2172,6 +2180,46 @@ int aither_gpu_download_output(aither_gpu *h, int blk, int var, int species, dou
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst, h->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int aither_gpu_compute_wall_distance(aither_gpu *h, const double *wallFaceCenters, long long n) {
+  // ref: src/main.cpp:144,191-201, src/procBlock.cpp:6030-6107, src/kdtree.cpp:211-225
+  if (!h) return Fail("null handle");
+  if (n < 0 || (n > 0 && !wallFaceCenters)) return Fail("aither_gpu_compute_wall_distance: bad point list");
+  if (n == 0 || !h->cfg.isViscous) return 0;  // the reference skips the search without viscous walls
+  CK(cudaSetDevice(h->device));
+  double *dPts = nullptr;
+  CK(cudaMalloc(&dPts, sizeof(double) * 3 * static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(dPts, wallFaceCenters, sizeof(double) * 3 * static_cast<size_t>(n),
+                     cudaMemcpyHostToDevice, h->stream));
+  for (auto &hb : h->blocks) {
+    BlockDev &b = hb.dev;
+    if (!hb.wallDistSlot) { cudaFree(dPts); return Fail("this handle keeps no wall-distance field"); }
+    if (!b.wallDist) {
+      // no array at create: the edge ghost cells, which the search does not touch, hold zero
+      b.wallDist = hb.wallDistSlot;
+      CK(cudaMemsetAsync(b.wallDist, 0, sizeof(double) * b.fs, h->stream));
+    }
+    const long long nCells = static_cast<long long>(b.ni) * b.nj * b.nk;
+    ScopedLaunch sl(h, kFamLayout);
+    WallDistKernel<<<static_cast<unsigned>((nCells + 255) / 256), 256, 0, h->stream>>>(b, dPts, n);
+    for (const aither_surface &sf : hb.surfaces) {
+      const int st = SurfaceType(sf);
+      const int d3 = (st - 1) / 2, d1 = (d3 + 1) % 3, d2 = (d3 + 2) % 3;
+      const int lo[3] = {sf.imin, sf.jmin, sf.kmin}, hi[3] = {sf.imax, sf.jmax, sf.kmax};
+      const int n1 = hi[d1] - lo[d1], n2 = hi[d2] - lo[d2];
+      if (n1 <= 0 || n2 <= 0) continue;
+      const int total = n1 * n2 * b.g;
+      WallDistGhostKernel<<<(total + 127) / 128, 128, 0, h->stream>>>(
+          b, d3, st % 2, sf.type == AITHER_BC_VISCOUS_WALL ? 1 : 0, lo[d1], n1, lo[d2], n2);
+    }
+  }
+  CK(cudaGetLastError());
+  // ghost cells across connections take the neighbour block's distance (mgSolution::SwapWallDist,
+  // src/main.cpp:202, src/gridLevel.cpp:261-281)
+  if (Exchange(h, kHaloWallDist)) { cudaFree(dPts); return 1; }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(dPts));
   return 0;
 }
 int aither_gpu_download_wall_data(aither_gpu *h, int blk, int surface, double *dst) {

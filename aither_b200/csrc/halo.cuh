@@ -36,7 +36,7 @@
 
 namespace aither {
 
-enum HaloField { kHaloState = 0, kHaloUpdate = 1, kHaloTurb = 2, kHaloVelGrad = 3, kHaloNumFields };
+enum HaloField { kHaloState = 0, kHaloUpdate = 1, kHaloTurb = 2, kHaloVelGrad = 3, kHaloWallDist = 4, kHaloNumFields };
 
 inline std::string &HaloErrorRef() {
   static thread_local std::string e;

@@ -34,6 +34,7 @@ FIELD_DIAG_INV, FIELD_UPDATE, FIELD_CONS_N, FIELD_MATRIX_RESID = 5, 6, 7, 8
 FIELD_TEMPERATURE, FIELD_CONS_NM1, FIELD_VISCOSITY = 9, 10, 11
 FIELD_EDDY_VISCOSITY, FIELD_F1, FIELD_F2, FIELD_VELOCITY_GRAD = 12, 13, 14, 15
 FIELD_TKE_GRAD, FIELD_OMEGA_GRAD, FIELD_PRESSURE_GRAD = 16, 17, 18
+FIELD_WALL_DIST = 19
 
 _dS = C.c_double * MAX_SPECIES
 _d3 = C.c_double * 3

@@ -205,8 +205,9 @@ enum aither_field {
   AITHER_FIELD_VELOCITY_GRAD = 15, /* ghost padded, 9: (r,c) = d u_c / d x_r */
   AITHER_FIELD_TKE_GRAD = 16,    /* no ghosts, 3 */
   AITHER_FIELD_OMEGA_GRAD = 17,  /* no ghosts, 3 */
-  AITHER_FIELD_PRESSURE_GRAD = 18 /* no ghosts, 3: cell average of the face pressure gradients
+  AITHER_FIELD_PRESSURE_GRAD = 18, /* no ghosts, 3: cell average of the face pressure gradients
                                      (kept for runs with non-reflecting BCs only) */
+  AITHER_FIELD_WALL_DIST = 19    /* ghost padded, 1 (viscous runs) */
 };
 
 typedef struct aither_gpu aither_gpu;   /* opaque handle */
@@ -269,6 +270,19 @@ enum aither_output_var {
 };
 int aither_gpu_download_output(aither_gpu *h, int blk, int var, int species, double scale,
                                double *dst);
+
+/* Wall distance on the device. Replaces the k-d tree search of the set-up:
+ * kdtree::NearestNeighbor (src/kdtree.cpp:123-225) called for every physical cell by
+ * procBlock::CalcWallDistance (src/procBlock.cpp:6030-6107) with the tree main.cpp builds from
+ * GetViscousFaceCenters (src/main.cpp:144,191-201; src/utility.cpp:310-368). `wallFaceCenters`
+ * holds the n centres (x, y, z) of ALL viscous-wall faces of the simulation -- every rank passes
+ * the same list, as the reference broadcasts it. For every block of the handle the distance of
+ * each physical cell centre to the nearest of them replaces the wall distance given at create,
+ * and the ghost cells (not the edge ghost cells, which keep what they held) follow the
+ * reference's rule: minus the mirrored interior value across a viscous wall, the value of the
+ * first interior cell elsewhere. Exhaustive search, tiled through shared memory: the minimum is
+ * the tree's minimum. n = 0 leaves everything as it is (the reference skips the call). */
+int aither_gpu_compute_wall_distance(aither_gpu *h, const double *wallFaceCenters, long long n);
 
 /* Wall variables of one viscous-wall surface (reference `wallData` / `wallVars`,
  * include/wallData.hpp:40-57; what WriteWallFunFile reads, src/output.cpp:440-588): for every face
