@@ -149,6 +149,7 @@ struct HostBlock {
   // record of what does not depend on the update
   double *dWaveGeoLo = nullptr, *dWaveGeoHi = nullptr, *dWaveDyn = nullptr, *dWaveAhead = nullptr;
   double *wallDistSlot = nullptr;
+  bool ghostsInAlt = false;  // fused update: the ghost cells of the last fill sit in dev.stateAlt
   uint4 *dWaveMailJ = nullptr, *dWaveMailK = nullptr;  // hand-over between pencils (lusgs_pencil.cuh)
   unsigned waveTag = 0;                                 // number of the half sweep
   bool waveCarries = false;  // no connections: a half sweep leaves the next one's ahead-sums behind
@@ -1077,6 +1078,7 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
         UpdateKernel<NS, NT, true, false><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(
             hb.dev, h->params, h->dPartials, h->dLinfPartials);
         std::swap(hb.dev.state, hb.dev.stateAlt);
+        hb.ghostsInAlt = true;
       } else {
         UpdateKernel<NS, NT><<<hb.updGrid, hb.cellBlock, 0, h->stream>>>(hb.dev, h->params,
                                                                         h->dPartials,
@@ -1111,7 +1113,10 @@ int PhaseUpdateT(aither_gpu *h, int slot, int mm) {
 // AITHER_MAIN_TU defined the file is the whole library (one slow translation unit).
 const AitherEqOps *EqOpsFor(const aither_gpu *h);
 #define EQ_DISPATCH(h, FN, ...) (EqOpsFor(h)->FN(__VA_ARGS__))
-int PhaseBoundaryConditions(aither_gpu *h) { return EQ_DISPATCH(h, PhaseBoundaryConditionsT, h); }
+int PhaseBoundaryConditions(aither_gpu *h) {
+  for (auto &hb : h->blocks) hb.ghostsInAlt = false;  // the fill writes the current buffer's ghost cells
+  return EQ_DISPATCH(h, PhaseBoundaryConditionsT, h);
+}
 int PhaseResidual(aither_gpu *h, int fusePrep = 0, double cfl = 0.0) {
   return EQ_DISPATCH(h, PhaseResidualT, h, fusePrep, cfl);
 }
@@ -2150,8 +2155,16 @@ int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst) {
   }
   const double *ptr; int nc; bool padded;
   if (FieldInfo(h, blk, field, &ptr, &nc, &padded)) return 1;
-  const HostBlock &hb = h->blocks[blk];
+  HostBlock &hb = h->blocks[blk];
   const BlockDev &b = hb.dev;
+  if (field == AITHER_FIELD_STATE && hb.ghostsInAlt && b.stateAlt) {
+    // the ghost cells of the last fill sit in the buffer the fused update left behind
+    const long long n = static_cast<long long>(b.ni + 2 * b.g) * (b.nj + 2 * b.g) * (b.nk + 2 * b.g);
+    GhostShellCopyKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(
+        b, b.stateAlt, b.state, h->neq);
+    CK(cudaGetLastError());
+    hb.ghostsInAlt = false;
+  }
   const int g = padded ? b.g : 0;
   return DownloadAos(h, hb, dst, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, nc, ptr, -g, -g, -g);
 }
@@ -2281,6 +2294,7 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   if (UploadAos(h, hb, stateAoS, b.ni + 2 * g, b.nj + 2 * g, b.nk + 2 * g, h->neq, b.state, -g, -g,
                 -g))
     return 1;
+  h->blocks[blk].ghostsInAlt = false;
   h->stateMovedSinceStore = true;  // a U^n that was not materialised can no longer be
   if (h->nt > 0) {  // the wall omega BC reads the stored viscosity: make it the new state's
     EQ_DISPATCH(h, InitAuxT, h, blk);
@@ -2337,6 +2351,7 @@ int aither_gpu_upload_state_commit(aither_gpu *h) {
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->evConverted, h->stream));
+  h->blocks[blk].ghostsInAlt = false;
   h->stateMovedSinceStore = true;
   if (h->nt > 0) {
     EQ_DISPATCH(h, InitAuxT, h, blk);

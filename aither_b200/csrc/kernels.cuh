@@ -98,6 +98,23 @@ static __global__ void SoaToAosKernel(double *__restrict__ dstAos, int SI, int S
   }
 }
 
+// ghost shell of `src` into `dst` (nc fields). With the state update fused into the matrix-residual
+// pass the two state buffers change roles every iteration; the ghost cells the reference's state_
+// holds after an iteration (filled at the START of that iteration, src/gridLevel.cpp:287-319) then
+// sit in the buffer that has just become the old one. Nothing on the path reads ghost cells before
+// the next fill, so they are only moved over when the state is downloaded.
+static __global__ void GhostShellCopyKernel(BlockDev b, const double *__restrict__ src,
+                                            double *__restrict__ dst, int nc) {
+  const int NI = b.ni + 2 * b.g, NJ = b.nj + 2 * b.g, NK = b.nk + 2 * b.g;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<long long>(NI) * NJ * NK) return;
+  const int i = static_cast<int>(t % NI) - b.g, j = static_cast<int>((t / NI) % NJ) - b.g;
+  const int k = static_cast<int>(t / (static_cast<long long>(NI) * NJ)) - b.g;
+  if (i >= 0 && i < b.ni && j >= 0 && j < b.nj && k >= 0 && k < b.nk) return;
+  const long long idx = CellIdx(b, i, j, k);
+  for (int e = 0; e < nc; ++e) dst[e * b.fs + idx] = src[e * b.fs + idx];
+}
+
 // ---------------------------------------------------------------------------------------------
 // K11 boundary-condition ghost fill. One thread per (boundary face, ghost layer).
 struct SurfDev {
