@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "aither_gpu_destroy", "aither_gpu_last_error", "aither_gpu_version",
     "aither_gpu_alloc_host", "aither_gpu_free_host",
     "aither_gpu_comm_unique_id", "aither_gpu_comm_create", "aither_gpu_comm_destroy",
-    "aither_gpu_halo_info",
+    "aither_gpu_halo_info", "aither_gpu_halo_p2p_export", "aither_gpu_halo_p2p_import",
     "aither_gpu_set_transfer", "aither_gpu_mg_restrict", "aither_gpu_mg_save_update",
     "aither_gpu_mg_subtract_saved", "aither_gpu_mg_prolong",
 )
@@ -82,6 +82,8 @@ def load_library():
     L.aither_gpu_download_wall_data.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_download_output.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, pd]
     L.aither_gpu_compute_wall_distance.argtypes = [vp, pd, C.c_longlong]
+    L.aither_gpu_halo_p2p_export.argtypes = [vp, C.c_char_p]
+    L.aither_gpu_halo_p2p_import.argtypes = [vp, C.c_char_p]
     L.aither_gpu_field_size.argtypes = [vp, C.c_int, C.c_int]
     L.aither_gpu_field_size.restype = C.c_longlong
     L.aither_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -224,6 +226,19 @@ class GridLevel:
         self._check(self._lib.aither_gpu_download_output(self._h, blk, var, species, scale,
                                                          _ptr(out)))
         return out
+
+    def enable_peer_exchange(self):
+        """ghost exchange over NVLink peer memory instead of NCCL send / recv (ranks of one node;
+        collective: every rank calls it). AITHER_B200_HALO_P2P=0 keeps NCCL."""
+        import os
+        from . import distributed as adist
+        if os.environ.get("AITHER_B200_HALO_P2P", "1") == "0":
+            return False
+        mine = C.create_string_buffer(64)
+        self._check(self._lib.aither_gpu_halo_p2p_export(self._h, mine))
+        everyone = adist.all_gather_bytes(mine.raw, 64)
+        self._check(self._lib.aither_gpu_halo_p2p_import(self._h, everyone))
+        return True
 
     def compute_wall_distance(self, wall_face_centers):
         """wall distance of every block from the centres (n, 3) of all viscous-wall faces, on the

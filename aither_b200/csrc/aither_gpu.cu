@@ -192,6 +192,10 @@ struct aither_gpu {
   std::vector<HostBlock> blocks;
   std::vector<aither_conn> conns;
   HaloPlan halo;      // every connection with its tangential extension (the reference's swap)
+  // direct exchange over peer memory: this rank's arena (receive buffers + flags) and the peers'
+  unsigned char *p2pArena = nullptr;
+  size_t p2pBytes = 0;
+  std::vector<unsigned char *> p2pPeers;  // IPC mappings (nullptr at this rank's own index)
   HaloPlan haloFace;  // ghost cells straight behind the patches only: one level
   // ... and only the FIRST ghost layer: all that the implicit off-diagonals read of the update
   // (nearest neighbours; ref src/procBlock.cpp:1056-1170). Half the bytes of haloFace for MUSCL,
@@ -1202,6 +1206,11 @@ int FetchResults(aither_gpu *h, int n) {
 void FreeAll(aither_gpu *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (unsigned char *p : h->p2pPeers)
+    if (p) cudaIpcCloseMemHandle(p);
+  h->p2pPeers.clear();
+  if (h->p2pArena) cudaFree(h->p2pArena);
+  h->p2pArena = nullptr;
   for (auto &hb : h->blocks) {
     if (hb.alloc) cudaFree(hb.alloc);
     for (auto &row : hb.lusgsGraph)
@@ -2397,6 +2406,49 @@ int aither_gpu_comm_destroy(void *comm) {
   if (!api) return Fail(HaloError());
   const int rc = api->CommDestroy(comm);
   if (rc != 0) return Fail(std::string("ncclCommDestroy: ") + api->GetErrorString(rc));
+  return 0;
+}
+int aither_gpu_halo_p2p_export(aither_gpu *h, void *handle) {
+  if (!h || !handle) return Fail("null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AITHER_P2P_HANDLE_BYTES, "IPC handle size");
+  CK(cudaSetDevice(h->device));
+  HaloPlan *plans[3] = {&h->halo, &h->haloFace, &h->haloUpdate};
+  if (!h->p2pArena) {
+    h->p2pBytes = P2POffset(plans, 3, h->rank, -1, 0, 0);
+    CK(cudaMalloc(&h->p2pArena, h->p2pBytes));
+    CK(cudaMemset(h->p2pArena, 0, h->p2pBytes));
+  }
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->p2pArena));
+  memcpy(handle, &ipc, sizeof(ipc));
+  return 0;
+}
+int aither_gpu_halo_p2p_import(aither_gpu *h, const void *handles) {
+  if (!h || !handles) return Fail("null argument");
+  if (!h->p2pArena) return Fail("aither_gpu_halo_p2p_import: call aither_gpu_halo_p2p_export first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<unsigned char *> arena(h->nRanks, nullptr);
+  h->p2pPeers.assign(h->nRanks, nullptr);
+  for (int r = 0; r < h->nRanks; ++r) {
+    if (r == h->rank) { arena[r] = h->p2pArena; continue; }
+    // only the ranks this one exchanges with are mapped
+    bool partner = false;
+    for (const aither_conn &c : h->conns)
+      partner = partner || (c.rank[0] == h->rank && c.rank[1] == r) || (c.rank[1] == h->rank && c.rank[0] == r);
+    if (!partner) continue;
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, static_cast<const unsigned char *>(handles) + static_cast<size_t>(r) * sizeof(ipc), sizeof(ipc));
+    void *ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return Fail(std::string("aither_gpu_halo_p2p_import: cudaIpcOpenMemHandle failed for rank ") +
+                  std::to_string(r) + ": " + cudaGetErrorString(e));
+    h->p2pPeers[r] = static_cast<unsigned char *>(ptr);
+    arena[r] = h->p2pPeers[r];
+  }
+  HaloPlan *plans[3] = {&h->halo, &h->haloFace, &h->haloUpdate};
+  if (HaloP2PEnable(plans, 3, arena)) return Fail(HaloError());
   return 0;
 }
 int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells) {

@@ -48,6 +48,17 @@ def broadcast_bytes(payload, n, src=0):
     return bytes(t.cpu().numpy().tobytes())
 
 
+def all_gather_bytes(payload, n):
+    """Every rank contributes `n` bytes; returns the world_size * n bytes in rank order."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    parts = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
 def make_comm(device):
     """NCCL communicator for the halo exchange, created through the library
     (aither_gpu_comm_unique_id on rank 0 -> broadcast -> aither_gpu_comm_create)."""

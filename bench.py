@@ -227,8 +227,10 @@ def workload_config(n=256, n_cells_note=None, gpus=1, recon="thirdOrder", viscou
            "parallelism": "blocks%d" % gpus}
     if gpus > 1 and gpus in LATTICE:
         cfg["parallelism"] = ("%dx%dx%d lattice of connected blocks, one per GPU; ghost layers of "
-                              "state and implicit update exchanged with ncclSend/ncclRecv "
-                              "(%d exchanges per iteration)" % (*LATTICE[gpus], SWEEPS + 2))
+                              "state and implicit update written straight into the neighbour's "
+                              "memory over NVLink (pack kernel -> peer buffer -> flag -> unpack; "
+                              "AITHER_B200_HALO_P2P=0: ncclSend/ncclRecv), %d exchanges per "
+                              "iteration" % (*LATTICE[gpus], SWEEPS + 2))
     if n_cells_note:
         cfg["sample"] = n_cells_note
     return cfg
@@ -277,6 +279,7 @@ def measure_configs3(args, rank, world, local, comm, dist):
 
     lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world, block_ids=[rank],
                                 nccl_comm=comm)
+    lvl.enable_peer_exchange()
     ms_n, prof_n = timed(lvl)
     lvl.close()
     mine = prob.blocks[rank]
@@ -336,6 +339,8 @@ def run_gpu_arm(args):
         mine = rank
         lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world,
                                     block_ids=[mine], nccl_comm=comm)
+        # ghost exchange over NVLink peer memory (AITHER_B200_HALO_P2P=0: ncclSend / ncclRecv)
+        peer_exchange = lvl.enable_peer_exchange()
     else:
         extra = dict(viscous=True, visc_recon="centralFourth", size=n * 2e-6) if args.viscous else {}
         if args.turb:

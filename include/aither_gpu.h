@@ -342,6 +342,18 @@ int aither_gpu_comm_unique_id(char id[128]);
 int aither_gpu_comm_create(const char id[128], int rank, int nRanks, int device,
                            void **comm);
 int aither_gpu_comm_destroy(void *comm);
+/* Direct ghost exchange over NVLink peer memory instead of ncclSend / ncclRecv (which cost ~95 us
+ * per exchange whatever the size): the donor rank's pack kernel writes a slice straight into the
+ * acceptor rank's receive buffer and raises a flag behind it; the acceptor's stream waits for the
+ * flag and unpacks. Replaces the MPI_Sendrecv of multiArray3d::SwapSliceMPI
+ * (include/multiArray3d.hpp:1440-1508) like the NCCL path, bit for bit the same ghost cells.
+ * Every rank (one process per GPU of ONE node) calls _export after aither_gpu_create, the host
+ * gathers the AITHER_P2P_HANDLE_BYTES-byte handles of all ranks in rank order with the transport
+ * it already has (MPI_Allgather), and every rank calls _import with the gathered block. Without
+ * these two calls the exchange stays on NCCL. */
+#define AITHER_P2P_HANDLE_BYTES 64
+int aither_gpu_halo_p2p_export(aither_gpu *h, void *handle);
+int aither_gpu_halo_p2p_import(aither_gpu *h, const void *handles);
 /* number of halo levels (pack/unpack launch pairs per exchange) and doubles this
  * rank sends to other ranks per component per exchange; for reports and tests */
 int aither_gpu_halo_info(aither_gpu *h, int *levels, long long *remoteCells);

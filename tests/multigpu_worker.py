@@ -48,6 +48,8 @@ def main():
     per = synthetic.assign_ranks(prob, world)
     lvl = aither_b200.GridLevel(prob, device=local, rank=rank, n_ranks=world, block_ids=per[rank],
                                 nccl_comm=comm)
+    # direct exchange over peer memory unless AITHER_B200_HALO_P2P=0 (then ncclSend / ncclRecv)
+    peer = lvl.enable_peer_exchange()
     hist = np.zeros((iters, prob.neq))
     for it in range(iters):
         lvl.store_old_solution(it)
@@ -85,7 +87,7 @@ def main():
                     np.abs(sr).max()
         one.close()
         ref.close()
-        print("MULTIGPU_OK world=%d solver=%s blocks=%d" % (world, solver, nblk), flush=True)
+        print("MULTIGPU_OK world=%d solver=%s blocks=%d exchange=%s" % (world, solver, nblk, "peer" if peer else "nccl"), flush=True)
     adist.destroy_comm(comm)
     dist.barrier()
     dist.destroy_process_group()
