@@ -1,7 +1,7 @@
 # round 2: N-GPU bench line (weak scaling, with configs3) -- N from the number of visible GPUs
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
-S=$SECONDS; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_scale_${N}gpu.json 2> gpurun_out/r02_scale_${N}gpu.err; echo "bench$N rc=$? $((SECONDS-S))s"
+S=$SECONDS; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 $BENCH_EXTRA > gpurun_out/r02_scale_${N}gpu.json 2> gpurun_out/r02_scale_${N}gpu.err; echo "bench$N rc=$? $((SECONDS-S))s"
 python - <<PY
 import json
 d=json.loads([l for l in open('gpurun_out/r02_scale_${N}gpu.json') if l.startswith('{')][-1])
