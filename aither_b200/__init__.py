@@ -26,6 +26,7 @@ ABI_SYMBOLS = (
     "aither_gpu_invert_diagonal", "aither_gpu_initialize_matrix_update", "aither_gpu_relax",
     "aither_gpu_update_blocks", "aither_gpu_reset_diagonal", "aither_gpu_run",
     "aither_gpu_upload_state", "aither_gpu_upload_state_async", "aither_gpu_upload_state_commit",
+    "aither_gpu_upload_interior_async",
     "aither_gpu_download_state", "aither_gpu_download_field", "aither_gpu_download_wall_data",
     "aither_gpu_download_output", "aither_gpu_compute_wall_distance",
     "aither_gpu_field_size", "aither_gpu_synchronize", "aither_gpu_timer_start",
@@ -77,6 +78,7 @@ def load_library():
     L.aither_gpu_upload_state.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_upload_state_async.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_upload_state_commit.argtypes = [vp]
+    L.aither_gpu_upload_interior_async.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_download_state.argtypes = [vp, C.c_int, pd]
     L.aither_gpu_download_field.argtypes = [vp, C.c_int, C.c_int, pd]
     L.aither_gpu_download_wall_data.argtypes = [vp, C.c_int, C.c_int, pd]
@@ -264,6 +266,13 @@ class GridLevel:
         stay alive and unchanged until `upload_state_commit`) on the copy stream"""
         assert state.flags["C_CONTIGUOUS"] and state.dtype == np.float64
         self._check(self._lib.aither_gpu_upload_state_async(self._h, blk, _ptr(state)))
+
+    def upload_interior_async(self, blk, interior):
+        """as upload_state_async for the physical cells only (nk, nj, ni, neq): the ghost cells are
+        filled at the start of every iteration and need not cross PCIe"""
+        if not interior.flags["C_CONTIGUOUS"] or interior.dtype != np.float64:
+            raise ValueError("upload_interior_async needs a C-contiguous float64 array")
+        self._check(self._lib.aither_gpu_upload_interior_async(self._h, blk, _ptr(interior)))
 
     def upload_state_commit(self):
         self._check(self._lib.aither_gpu_upload_state_commit(self._h))

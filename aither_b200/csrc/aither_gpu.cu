@@ -219,6 +219,7 @@ struct aither_gpu {
   size_t stage2Bytes = 0;
   cudaEvent_t evCopied = nullptr, evConverted = nullptr;
   int pendingBlk = -1;
+  bool pendingInterior = false;
   long long launches = 0;
   bool keepMatrixResid = false;
   // aither_gpu_iterate / _run: the matrix-residual pass also advances the state into the
@@ -2312,13 +2313,14 @@ int aither_gpu_upload_state(aither_gpu *h, int blk, const double *stateAoS) {
   return 0;
 }
 
-int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS) {
+static int UploadStateAsync(aither_gpu *h, int blk, const double *stateAoS, bool interior) {
   if (!h || !stateAoS) return Fail("null argument");
   CK(cudaSetDevice(h->device));
   if (blk < 0 || blk >= static_cast<int>(h->blocks.size())) return Fail("bad block index");
   if (h->pendingBlk >= 0) return Fail("an asynchronous upload is already pending: commit it first");
   const BlockDev &b = h->blocks[blk].dev;
-  const size_t n = static_cast<size_t>(b.ni + 2 * b.g) * (b.nj + 2 * b.g) * (b.nk + 2 * b.g) * h->neq;
+  const int gg = interior ? 0 : b.g;
+  const size_t n = static_cast<size_t>(b.ni + 2 * gg) * (b.nj + 2 * gg) * (b.nk + 2 * gg) * h->neq;
   if (!h->copyStream) {
     CK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->evCopied, cudaEventDisableTiming));
@@ -2339,7 +2341,14 @@ int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS
                      h->copyStream));
   CK(cudaEventRecord(h->evCopied, h->copyStream));
   h->pendingBlk = blk;
+  h->pendingInterior = interior;
   return 0;
+}
+int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS) {
+  return UploadStateAsync(h, blk, stateAoS, false);
+}
+int aither_gpu_upload_interior_async(aither_gpu *h, int blk, const double *interiorAoS) {
+  return UploadStateAsync(h, blk, interiorAoS, true);
 }
 int aither_gpu_upload_state_commit(aither_gpu *h) {
   if (!h) return Fail("null handle");
@@ -2349,14 +2358,16 @@ int aither_gpu_upload_state_commit(aither_gpu *h) {
   h->pendingBlk = -1;
   const HostBlock &hb = h->blocks[blk];
   const BlockDev &b = hb.dev;
-  const int g = b.g, SI = b.ni + 2 * g, SJ = b.nj + 2 * g, SK = b.nk + 2 * g;
+  // physical cells only: the ghost cells are filled at the start of every iteration anyway
+  const int g = h->pendingInterior ? 0 : b.g, SI = b.ni + 2 * g, SJ = b.nj + 2 * g, SK = b.nk + 2 * g;
   CK(cudaStreamWaitEvent(h->stream, h->evCopied, 0));
   const long long cells = static_cast<long long>(SI) * SJ * SK;
   const int grid = static_cast<int>(std::min<long long>((cells + 255) / 256, 148 * 16));
   {
     ScopedLaunch sl(h, kFamLayout);
+    const int off = b.g - g;  // rows / planes the source lacks in front (0 with ghost cells)
     AosToSoaKernel<<<grid, 256, 0, h->stream>>>(h->dStage2, SI, SJ, SK, h->neq, b.state, b.fs,
-                                                -g + b.lp, 0, 0, b.sj, b.sk);
+                                                -g + b.lp, off, off, b.sj, b.sk);
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->evConverted, h->stream));

@@ -355,6 +355,10 @@ def run_gpu_arm(args):
     state_shape = prob.blocks[mine].padded_shape(g) + (neq,)
     host_state = aither_b200.pinned_array(state_shape)
     host_state[...] = prob.blocks[mine].arrays["state"]
+    # the physical cells alone (what a host really has to hand over: the ghost shell is filled at
+    # the start of every iteration), for the overlapped upload
+    host_interior = aither_b200.pinned_array((n, n, n, neq))
+    host_interior[...] = host_state[g:g + n, g:g + n, g:g + n]
     for b in prob.blocks:          # host copies of the metrics are no longer needed
         b.arrays = {"state": None}
     t_setup = time.perf_counter() - t_setup
@@ -407,11 +411,11 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     lvl.timer_start()
-    lvl.upload_state_async(0, host_state)
+    lvl.upload_interior_async(0, host_interior)
     for it in range(args.steps):
         lvl.upload_state_commit()
         if it + 1 < args.steps:
-            lvl.upload_state_async(0, host_state)
+            lvl.upload_interior_async(0, host_interior)
         lvl.store_old_solution(it)
         l2, linf, mr = lvl.iterate(CFL)
     ms_e2e = lvl.timer_stop()
@@ -476,15 +480,18 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, gpus=world, recon=args.recon, viscous=args.viscous,
                                   turb=args.turb, solver=args.solver),
-        "e2e": {"value": max(e2e, e2e_sync), "unit": "Mcell-iter/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": max(e2e, e2e_sync), "unit": "Mcell-iter/s",
+                "h2d_bytes_per_step": host_interior.nbytes if e2e >= e2e_sync else h2d,
                 "d2h_bytes_per_step": d2h,
                 "ms_per_step": min(ms_e2e, ms_e2e_sync) / args.steps,
-                "what": "per step: the host hands over a fresh copy of the state from pinned memory "
-                        "(703 MB at 256^3), store_old_solution, aither_gpu_iterate, norms copied "
+                "what": "per step: the host hands over a fresh copy of the state from pinned memory, "
+                        "store_old_solution, aither_gpu_iterate, norms copied "
                         "back. Two ways through the C ABI, both timed in full, the faster one is "
-                        "`value`: `overlapped` = aither_gpu_upload_state_async / _commit (the copy "
-                        "of the next step runs on the copy stream during this step's kernels), "
-                        "`synchronous` = aither_gpu_upload_state. Which one wins depends on the "
+                        "`value`: `overlapped` = aither_gpu_upload_interior_async / _commit (the "
+                        "physical cells only, 671 MB at 256^3 -- the ghost shell is filled at the "
+                        "start of every iteration; the copy of the next step runs on the copy "
+                        "stream during this step's kernels), `synchronous` = aither_gpu_upload_state "
+                        "(ghost-padded state, 703 MB). Which one wins depends on the "
                         "box: the DMA copy slows down when the kernels keep HBM busy.",
                 "mode": "overlapped" if e2e >= e2e_sync else "synchronous",
                 "value_overlapped": e2e, "value_synchronous": e2e_sync},

@@ -306,6 +306,11 @@ int aither_gpu_download_state(aither_gpu *h, int blk, double *stateAoS);
  * aither_gpu_iterate. One upload may be pending per handle. */
 int aither_gpu_upload_state_async(aither_gpu *h, int blk, const double *stateAoS);
 int aither_gpu_upload_state_commit(aither_gpu *h);
+/* The same for a host that hands over the physical cells only (nk x nj x ni x neq, the
+ * reference's layout without the ghost shell): the ghost cells are filled at the start of every
+ * iteration (gridLevel::GetBoundaryConditions), so they need not cross PCIe. Committed with
+ * aither_gpu_upload_state_commit. */
+int aither_gpu_upload_interior_async(aither_gpu *h, int blk, const double *interiorAoS);
 int aither_gpu_download_field(aither_gpu *h, int blk, int field, double *dst);
 /* number of doubles aither_gpu_download_field writes for `field` */
 long long aither_gpu_field_size(aither_gpu *h, int blk, int field);
