@@ -18,12 +18,14 @@
 //      NEW update of its three neighbours behind it and the OLD update of the three ahead. The
 //      ahead-neighbours still hold their pre-sweep update when the cell is solved, so their sum
 //      does not depend on the sweep: LusgsAheadKernel forms it for all cells in parallel before
-//      the wavefront starts (U of the forward sweep, L of the backward one);
-//   3. the wavefront proper (LusgsPencilKernel): the block is cut into pencils of 8 x 7 grid
-//      lines; a thread block walks its pencil in local planes q = i + jl + kl, one __syncthreads
-//      per plane, the new update handed on through shared memory; pencils are ordered by atomic
-//      tickets along anti-diagonals and wait on the progress counters of the two pencils behind
-//      them (lusgs_wave.cuh), so a predecessor is always running or done;
+//      the first half sweep of an iteration, and every half sweep leaves the next one's sums behind
+//      (its behind-sums with the new update ARE the next sweep's ahead-sums with the old one);
+//   3. the wavefront proper (LusgsPencilKernel): the block is cut into pencils of 12 x 8 grid
+//      lines; a thread block walks its pencil in local planes q = i + jl + kl, one barrier per
+//      plane, one thread per cell, the new ingredients handed on through shared memory; pencils
+//      are ordered by atomic tickets along anti-diagonals, so a predecessor is always running or
+//      done, and take the boundary lines of the two pencils behind them from a mailbox of tagged
+//      16-byte entries (no fences, no progress counters);
 //   4. a PLANE-MAJOR workspace: the records of all cells of one plane of one pencil are contiguous
 //      in memory, so a plane arrives in shared memory by three bulk copies of the copy engine
 //      (cp.async.bulk, a ring of stages several planes ahead) and the walkers read shared memory
@@ -39,11 +41,13 @@
 
 namespace aither {
 
-// pencil cross-section and resident thread blocks per SM (tunable at build time for A/B runs):
-// 8 x 8 = 64 cells x 4 lanes + a service warp = 288 threads, one thread block per SM (192^3 x4 sweeps:
-// 8x7 18.4 ms, 8x8 17.4, 4x8 and 8x4 with two blocks per SM 18.5 / 19.1)
+// pencil cross-section (tunable at build time for A/B runs, scripts/build_pencil_variants.sh):
+// 12 x 8 = 96 grid lines, one thread each, + four service warps = 224 threads, one thread block
+// per SM. Measured with the one-thread-per-cell kernel (profiles/r02ad_pencil_cross_section.json;
+// LU-SGS x4 at 192^3 / SST + LU-SGS at 128^3, ms per iteration): 16x8 10.53 / 9.80, 12x8 10.27 /
+// 9.71, 16x6 10.22, 8x12 10.18, 8x8 10.84 / 9.21.
 #ifndef AITHER_PENCIL_TJ
-#define AITHER_PENCIL_TJ 16
+#define AITHER_PENCIL_TJ 12
 #endif
 #ifndef AITHER_PENCIL_TK
 #define AITHER_PENCIL_TK 8
