@@ -583,9 +583,9 @@ PencilLattice LatticeOf(const HostBlock &hb) {
   L.planesPer = hb.dev.ni + kPTJ + kPTK - 2;
   return L;
 }
-template <int NS, int NT>
-int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
-  using R = PencilRec<NS, NT>;
+template <int NS, int NT, bool VISC>
+int PackLusgsPencilV(aither_gpu *h, HostBlock &hb) {
+  using R = PencilRec<NS, NT, VISC>;
   const BlockDev &b = hb.dev;
   const PencilLattice L = LatticeOf(hb);
   const long long slots = static_cast<long long>(L.nbJ) * L.nbK * L.planesPer * kPCells;
@@ -601,7 +601,7 @@ int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
     CK(cudaMemsetAsync(hb.dWaveDyn, 0, sizeof(double) * R::DN * slots, h->stream));
     CK(cudaMemsetAsync(hb.dWaveAhead, 0, sizeof(double) * R::AN * slots, h->stream));
     ScopedLaunch sl(h, kFamLayout);
-    WaveGeoKernel<<<grid, blk, 0, h->stream>>>(b, L, h->cfg.isViscous, hb.dWaveGeoLo,
+    WaveGeoKernel<R::GN><<<grid, blk, 0, h->stream>>>(b, L, h->cfg.isViscous, hb.dWaveGeoLo,
                                                hb.dWaveGeoHi);
   }
   // without connections the ghost cells of the update never change: half sweeps hand the next
@@ -610,19 +610,27 @@ int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
   hb.waveCarries = !carryOff;
   for (int s = 0; s < 6; ++s) hb.waveCarries = hb.waveCarries && b.connFace[s] == nullptr;
   ScopedLaunch sl(h, kFamLusgsPack);
-  WaveDynKernel<NS, NT><<<grid, blk, 0, h->stream>>>(b, h->params, L, hb.dWaveDyn);
+  WaveDynKernel<NS, NT, VISC><<<grid, blk, 0, h->stream>>>(b, h->params, L, hb.dWaveDyn);
   return 0;
 }
+// Euler runs (no turbulence equations, inviscid) take the records without the viscous slots
 template <int NS, int NT>
-int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
-  using C = PencilCfg<NS, NT>;
+int PackLusgsPencil(aither_gpu *h, HostBlock &hb) {
+  if constexpr (NT == 0) {
+    if (!h->cfg.isViscous) return PackLusgsPencilV<NS, NT, false>(h, hb);
+  }
+  return PackLusgsPencilV<NS, NT, true>(h, hb);
+}
+template <int NS, int NT, bool VISC>
+int LaunchLusgsPencilV(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
+  using C = PencilCfg<NS, NT, VISC>;
   const BlockDev &b = hb.dev;
   const PencilLattice L = LatticeOf(hb);
   if (EnsureWaveLattice(h, hb, kPTJ, kPTK)) return 1;
   CK(cudaMemsetAsync(hb.dWaveSync, 0, hb.waveSyncBytes, h->stream));
   const int grid = std::min(hb.wavePencils, 148 * kPencilCtasPerSm);
-  auto fwd = LusgsPencilKernel<NS, NT, true>;
-  auto bwd = LusgsPencilKernel<NS, NT, false>;
+  auto fwd = LusgsPencilKernel<NS, NT, true, VISC>;
+  auto bwd = LusgsPencilKernel<NS, NT, false, VISC>;
   static bool cfgF[64] = {false}, cfgB[64] = {false};  // per device and template instantiation
   if (EnsureSmemOptIn(fwd, C::smemBytes, h->device, cfgF) ||
       EnsureSmemOptIn(bwd, C::smemBytes, h->device, cfgB))
@@ -673,18 +681,32 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   }
   return 0;
 }
-// the ahead-side sums (old update) of a half sweep in one parallel pass, before the wavefront
 template <int NS, int NT>
-int LaunchLusgsAhead(aither_gpu *h, HostBlock &hb, bool forward) {
+int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
+  if constexpr (NT == 0) {
+    if (!h->cfg.isViscous) return LaunchLusgsPencilV<NS, NT, false>(h, hb, forward, fullGS);
+  }
+  return LaunchLusgsPencilV<NS, NT, true>(h, hb, forward, fullGS);
+}
+// the ahead-side sums (old update) of a half sweep in one parallel pass, before the wavefront
+template <int NS, int NT, bool VISC>
+int LaunchLusgsAheadV(aither_gpu *h, HostBlock &hb, bool forward) {
   const BlockDev &b = hb.dev;
   const PencilLattice L = LatticeOf(hb);
   const dim3 agrid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk), ablk(32, 4, 1);
   ScopedLaunch sa(h, kFamLusgsAhead);
   if (forward)
-    LusgsAheadKernel<NS, NT, true><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
+    LusgsAheadKernel<NS, NT, true, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
   else
-    LusgsAheadKernel<NS, NT, false><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
+    LusgsAheadKernel<NS, NT, false, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
   return 0;
+}
+template <int NS, int NT>
+int LaunchLusgsAhead(aither_gpu *h, HostBlock &hb, bool forward) {
+  if constexpr (NT == 0) {
+    if (!h->cfg.isViscous) return LaunchLusgsAheadV<NS, NT, false>(h, hb, forward);
+  }
+  return LaunchLusgsAheadV<NS, NT, true>(h, hb, forward);
 }
 
 int ZeroResult(aither_gpu *h, int slot) {

@@ -58,19 +58,21 @@ namespace aither {
 constexpr int kPTJ = AITHER_PENCIL_TJ, kPTK = AITHER_PENCIL_TK, kPCells = kPTJ * kPTK;
 constexpr int kPencilCtasPerSm = AITHER_PENCIL_CTAS;
 
-template <int NS, int NT>
+// VISC = false (Euler runs): the records carry no viscous slots -- 14 + 14 doubles per cell and
+// plane instead of 18 + 18, a quarter of the workspace's bytes less and a deeper stage ring.
+template <int NS, int NT, bool VISC = true>
 struct PencilRec {
   static constexpr int neq = NS + 4 + NT;
-  // per-iteration record: s[neq] | H a vt vtT | b[neq] | dinv dinvT, padded to a stride that is a
+  // per-iteration record: s[neq] | H a (vt vtT) | b[neq] | dinv dinvT, padded to a stride that is a
   // multiple of 16 bytes and NOT of 128 (records of neighbouring cells in different banks)
-  static constexpr int nUsed = 2 * neq + 6;
+  static constexpr int NST = neq + (VISC ? 4 : 2);  // record head: s | H a (| vt vtT)
+  static constexpr int nUsed = NST + neq + 2;
   static constexpr int nEven = (nUsed + 1) & ~1;
   static constexpr int DN = nEven % 16 == 0 ? nEven + 2 : nEven;
-  static constexpr int iH = neq, iA = neq + 1, iVt = neq + 2, iVtT = neq + 3, iB = neq + 4,
-                       iD = 2 * neq + 4;
-  static constexpr int NST = neq + 4;  // record head: s | H a vt vtT
-  // per-block record: behind-side faces i, j, k {nx, ny, nz, |A|} | |A| / dist for i, j, k | pad
-  static constexpr int GN = 18;
+  static constexpr int iH = neq, iA = neq + 1, iVt = neq + 2, iVtT = neq + 3, iB = NST,
+                       iD = NST + neq;
+  // per-block record: behind-side faces i, j, k {nx, ny, nz, |A|} (| |A| / dist for i, j, k) | pad
+  static constexpr int GN = VISC ? 18 : 14;
   static constexpr int AN = neq;  // ahead-sum: component-major within a plane, [plane][e][cell]
 };
 
@@ -87,18 +89,20 @@ __host__ __device__ __forceinline__ long long PencilSlot(const PencilLattice &L,
 // record head of a cell: r[0, neq) holds its state on entry; what WaveDynKernel packs for the
 // cells of the block and the halo warp forms on the fly (same expressions) for ghost cells and
 // cells of other pencils
-template <int NS, int NT>
+template <int NS, int NT, bool VISC>
 __device__ __forceinline__ void HeadFromState(const Params &p, double *r, double mu, double mut,
                                               double f1) {
   using E = Eq<NS, NT>;
-  using R = PencilRec<NS, NT>;
+  using R = PencilRec<NS, NT, VISC>;
   const MixK<NS> m = MixOf<NS>(p.gas, r);
   const double t0 = r[E::ie] * m.tFac;
   r[R::iH] = m.hf + m.cp * t0 + 0.5 * VelMagSq<NS>(r);  // as MakeIngr
   r[R::iA] = sqrt(m.gamma * r[E::ie] * m.rhoInv);
-  r[R::iVt] = 0.0;
-  r[R::iVtT] = 0.0;
-  if (p.isViscous) {
+  if constexpr (VISC) {
+    r[R::iVt] = 0.0;
+    r[R::iVtT] = 0.0;
+  }
+  if (VISC && p.isViscous) {
     // state-dependent factors of the viscous face spectral radii (NeighbourViscTerms)
     const double rho = SpeciesSum<NS>(r);
     r[R::iVt] = ViscSpecFactor(p.tr, rho, Gamma<NS>(p.gas, r), mu, mut);
@@ -107,23 +111,24 @@ __device__ __forceinline__ void HeadFromState(const Params &p, double *r, double
                                       r[NS + 4 + (NT > 1 ? 1 : 0)], mu, mut, f1);
   }
 }
-template <int NS, int NT>
+template <int NS, int NT, bool VISC>
 __device__ __forceinline__ void MakeHead(const BlockDev &b, const Params &p, long long idx,
                                          double *r) {
   using E = Eq<NS, NT>;
   LoadCell<E::neq>(b.state, b.fs, idx, r);
   double mu = 0.0, mut = 0.0, f1 = 0.0;
-  if (p.isViscous) {
+  if (VISC && p.isViscous) {
     mu = __ldg(b.viscosity + idx);
     if (NT > 0) {
       mut = __ldg(b.eddyVisc + idx);
       f1 = __ldg(b.f1 + idx);
     }
   }
-  HeadFromState<NS, NT>(p, r, mu, mut, f1);
+  HeadFromState<NS, NT, VISC>(p, r, mu, mut, f1);
 }
 
 // behind-side faces: lower faces for the forward sweep (geoLo), upper faces for the backward one
+template <int GN>
 static __global__ void WaveGeoKernel(BlockDev b, PencilLattice L, int isViscous,
                                      double *__restrict__ geoLo, double *__restrict__ geoHi) {
   const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
@@ -138,31 +143,31 @@ static __global__ void WaveGeoKernel(BlockDev b, PencilLattice L, int isViscous,
       lo[4 * d + q] = b.fA[d][q * b.fs + idx];
       hi[4 * d + q] = b.fA[d][q * b.fs + idx + st];
     }
-    lo[12 + d] = isViscous ? lo[4 * d + 3] / b.dist[d][idx] : 0.0;
-    hi[12 + d] = isViscous ? hi[4 * d + 3] / b.dist[d][idx + st] : 0.0;
+    lo[12 + d] = (GN > 14 && isViscous) ? lo[4 * d + 3] / b.dist[d][idx] : 0.0;
+    hi[12 + d] = (GN > 14 && isViscous) ? hi[4 * d + 3] / b.dist[d][idx + st] : 0.0;
   }
   lo[15] = hi[15] = lo[16] = hi[16] = lo[17] = hi[17] = 0.0;
   const long long t = PencilSlot(L, i, j, k);
-  double2 *oLo = reinterpret_cast<double2 *>(geoLo + t * 18);
-  double2 *oHi = reinterpret_cast<double2 *>(geoHi + t * 18);
+  double2 *oLo = reinterpret_cast<double2 *>(geoLo + t * GN);
+  double2 *oHi = reinterpret_cast<double2 *>(geoHi + t * GN);
 #pragma unroll
-  for (int q = 0; q < 9; ++q) {
+  for (int q = 0; q < GN / 2; ++q) {
     oLo[q] = make_double2(lo[2 * q], lo[2 * q + 1]);
     oHi[q] = make_double2(hi[2 * q], hi[2 * q + 1]);
   }
 }
 
-template <int NS, int NT>
+template <int NS, int NT, bool VISC>
 __global__ void __launch_bounds__(128)
     WaveDynKernel(BlockDev b, Params p, PencilLattice L, double *__restrict__ dyn) {
   using E = Eq<NS, NT>;
-  using R = PencilRec<NS, NT>;
+  using R = PencilRec<NS, NT, VISC>;
   constexpr int neq = E::neq;
   const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
   if (i >= b.ni || j >= b.nj) return;
   const long long idx = CellIdx(b, i, j, k);
   double r[R::DN];
-  MakeHead<NS, NT>(b, p, idx, r);
+  MakeHead<NS, NT, VISC>(b, p, idx, r);
 #pragma unroll
   for (int e = 0; e < neq; ++e) r[R::iB + e] = __ldg(b.rhs + e * b.fs + idx);
   r[R::iD] = __ldg(b.dinv + idx);
@@ -178,11 +183,11 @@ __global__ void __launch_bounds__(128)
 // ((0 + od_i) + od_j) + od_k over the three neighbours AHEAD of every cell, with the update as it
 // is before the sweep (U of the forward sweep, L of the backward sweep; ref
 // src/procBlock.cpp:1056-1170). Fully parallel, all reads from the block's fields (coalesced).
-template <int NS, int NT, bool FORWARD>
+template <int NS, int NT, bool FORWARD, bool VISC>
 __global__ void __launch_bounds__(128)
     LusgsAheadKernel(BlockDev b, Params p, PencilLattice L, double *__restrict__ ahead) {
   using E = Eq<NS, NT>;
-  using R = PencilRec<NS, NT>;
+  using R = PencilRec<NS, NT, VISC>;
   constexpr int neq = E::neq, AN = R::AN;
   const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
   if (i >= b.ni || j >= b.nj) return;
@@ -201,10 +206,10 @@ __global__ void __launch_bounds__(128)
     const long long idxn = FORWARD ? idx + st : idx - st;
     const long long fidx = FORWARD ? idx + st : idx;  // the face between the two cells
     double hd[R::NST], g[4], du[neq], sn[neq], Hn;
-    MakeHead<NS, NT>(b, p, idxn, hd);
+    MakeHead<NS, NT, VISC>(b, p, idxn, hd);
 #pragma unroll
     for (int q = 0; q < 4; ++q) g[q] = __ldg(b.fA[d] + q * b.fs + fidx);
-    const double len = p.isViscous ? g[3] / __ldg(b.dist[d] + fidx) : 0.0;
+    const double len = (VISC && p.isViscous) ? g[3] / __ldg(b.dist[d] + fidx) : 0.0;
 #pragma unroll
     for (int e = 0; e < neq; ++e) du[e] = b.x[e * b.fs + idxn];
     MakeIngrDyn<NS, NT>(p.gas, hd, du, sn, &Hn);
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(128)
                                               : (cc < 3 * neq + 2 ? sn[cc - 2 * neq - 2] : Hn));
     };
     // the ahead-neighbour is the geometrically upper one in a forward sweep
-    OffDiagFromIngr<NS, NT>(ld, g, !FORWARD, acc, len * hd[R::iVt], len * hd[R::iVtT]);
+    OffDiagFromIngr<NS, NT>(ld, g, !FORWARD, acc, VISC ? len * hd[VISC ? R::iVt : 0] : 0.0,
+                            VISC ? len * hd[VISC ? R::iVtT : 0] : 0.0);
   }
   const long long t = PencilSlot(L, i, j, k);
   double *o = ahead + (t / kPCells) * (AN * kPCells) + t % kPCells;
@@ -232,9 +238,9 @@ __device__ __forceinline__ void BulkLoad(void *smemDst, const void *gsrc, unsign
       : "memory");
 }
 
-template <int NS, int NT>
+template <int NS, int NT, bool VISC = true>
 struct PencilCfg {
-  using R = PencilRec<NS, NT>;
+  using R = PencilRec<NS, NT, VISC>;
   static constexpr int neq = NS + 4 + NT;
   static constexpr int NCOMP = kPCells;  // one thread per grid line of the pencil
   static_assert(NCOMP % 32 == 0, "the walkers fill whole warps");
@@ -290,10 +296,10 @@ __device__ __forceinline__ uint4 MailLoad(const uint4 *p) {
 // what a halo lane loads one plane ahead of its use. Neighbour in another pencil: record head from
 // that pencil's workspace record, ingredients from the mailbox. Ghost cell: state (in hd), update
 // (in the first neq entries) and viscosities from the block's fields.
-template <int NS, int NT>
+template <int NS, int NT, bool VISC = true>
 struct HaloRaw {
   static constexpr int neq = NS + 4 + NT;
-  double hd[PencilRec<NS, NT>::NST];
+  double hd[PencilRec<NS, NT, VISC>::NST];
   uint4 ent[2 * neq + 1];
   double mu, mut, f1;
   const uint4 *mail;  // where the entries come from (re-read until their tags match)
@@ -321,17 +327,17 @@ struct HaloRaw {
 // (a warp instruction costs the same with 8 cells in it as with 32); one thread per cell with
 // progress counters (poller + publisher warp): 15.6, the pencils waiting on each other's
 // st.release.
-template <int NS, int NT, bool FORWARD>
-__global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
+template <int NS, int NT, bool FORWARD, bool VISC>
+__global__ void __launch_bounds__(PencilCfg<NS, NT, VISC>::threads, 1)
     LusgsPencilKernel(BlockDev b, Params p, PencilLattice L, int fullGS,
                       const double *__restrict__ dyn, const double *__restrict__ geo,
                       const double *__restrict__ ahead, const int2 *__restrict__ order,
                       int nPencils, WaveSync *sync, uint4 *mailJ, uint4 *mailK, unsigned tag,
                       double *__restrict__ carry, long long *dbg = nullptr, int dbgFlags = 0) {
   using E = Eq<NS, NT>;
-  using R = PencilRec<NS, NT>;
-  using C = PencilCfg<NS, NT>;
-  using HR = HaloRaw<NS, NT>;
+  using R = PencilRec<NS, NT, VISC>;
+  using C = PencilCfg<NS, NT, VISC>;
+  using HR = HaloRaw<NS, NT, VISC>;
   constexpr int neq = E::neq, nf = NS + 4, S = C::S;
   constexpr int TJ = kPTJ, TK = kPTK, NCOMP = C::NCOMP, PJ = C::PJ, PCELLS = C::PCELLS, NI = C::NI;
   constexpr int NH = C::NH, NST = R::NST;
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
           f.ent[e] = make_uint4(__double2loint(v), tag, __double2hiint(v), tag);
         }
         f.mu = f.mut = f.f1 = 0.0;
-        if (p.isViscous) {
+        if (VISC && p.isViscous) {
           f.mu = __ldg(b.viscosity + nidx);
           if (NT > 0) {
             f.mut = __ldg(b.eddyVisc + nidx);
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
         } else {
 #pragma unroll
           for (int e = 0; e < neq; ++e) v[e] = __hiloint2double(f.ent[e].z, f.ent[e].x);
-          HeadFromState<NS, NT>(p, f.hd, f.mu, f.mut, f.f1);
+          HeadFromState<NS, NT, VISC>(p, f.hd, f.mu, f.mut, f.f1);
           MakeIngrDyn<NS, NT>(p.gas, f.hd, v, v + neq, v + 2 * neq);
         }
         double *o = haloHd(q & 1, h);
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
           double fa[4];
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) fa[qq] = gg[4 * d + qq];
-          const double len = gg[12 + d];
+          const double len = VISC ? gg[VISC ? 12 + d : 0] : 0.0;
           auto ld = [&](int cc) {
             return cc < neq + 2 ? hd[cc]
                                 : (cc < 2 * neq + 2 ? du[cc - neq - 2]
@@ -628,7 +634,8 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT>::threads, 1)
           };
 #pragma unroll
           for (int e = 0; e < neq; ++e) od[e] = 0.0;
-          OffDiagFromIngr<NS, NT>(ld, fa, FORWARD, od, len * hd[R::iVt], len * hd[R::iVtT]);
+          OffDiagFromIngr<NS, NT>(ld, fa, FORWARD, od, VISC ? len * hd[VISC ? R::iVt : 0] : 0.0,
+                                  VISC ? len * hd[VISC ? R::iVtT : 0] : 0.0);
         };
         auto fromSmem = [&](int d, const double *hdp, int Pn, double *od) {
           double hd[NST], du[neq], sn[neq];
