@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT, VISC>::threads, 1)
     const long long myMail = static_cast<long long>(bc.x + L.nbJ * bc.y) * L.planesPer;
     if (role != 0) {
       // ---- four service warps, taking turns: warp w serves the planes p = w (mod 4). During
-      // plane p - 3 it loads what the halo of plane p needs, during plane p - 1 it puts that halo in
-      // place; during plane p - 2 it is the loader (ring of plane stages) and hands the boundary
+      // plane p - 2 it loads what the halo of plane p needs, during plane p - 1 it puts that halo in
+      // place; during plane p - 3 it is the loader (ring of plane stages) and hands the boundary
       // lines of the plane just finished to the pencils ahead. Each of these is a few hundred
       // dependent instructions of ONE warp -- about as long as the walkers' plane; taking turns
       // keeps them off the plane's critical path (one halo warp: 0.94 -> 1.4 us per plane for a
@@ -545,17 +545,19 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT, VISC>::threads, 1)
       if (w == 0) {
         hfetch(0, hr);
         hstore(0, hr);
-      } else if (w < 3) {
-        hfetch(w, hr);
-      } else if (h == 0) {
+      } else if (w == 1) {
+        hfetch(1, hr);
+      } else if (w == 3 && h == 0) {
         for (int q = 0; q < S - 2; ++q) load(q);
       }
       NamedBarrier(1, C::threads);
       for (int q = 0; q < nSteps; ++q) {
-        const int turn = (q - w) & 3;  // 0: idle, 1: fetch plane q + 3, 2: load + post, 3: halo of q + 1
-        if (turn == 1) {
-          hfetch(q + 3, hr);
-        } else if (turn == 2) {
+        // 0: idle, 1: load + post, 2: fetch plane q + 2, 3: halo of plane q + 1 in place. (Fetching
+        // three planes ahead kept every pencil one plane further behind the pencils it follows.)
+        const int turn = (q - w) & 3;
+        if (turn == 2) {
+          hfetch(q + 2, hr);
+        } else if (turn == 1) {
           // the stage of plane q + S - 2 held plane q - 2: its last readers finished with plane q - 1
           if (h == 0) load(q + S - 2);
           if (q > 0) post(q - 1);
