@@ -17,6 +17,8 @@ def run(prob, cfl=20.0, n=2):
     return out[0]
 print("euler dplur", run(synthetic.box_problem(40, 20, 18, sweeps=2)))
 print("euler weno lusgs", run(synthetic.box_problem(20, 12, 10, solver="lusgs", sweeps=2, recon="weno")))
+print("euler lusgs, 3 x 3 pencils", run(synthetic.box_problem(24, 30, 20, solver="lusgs", sweeps=2)))
+print("laminar lusgs, 2 x 2 pencils", run(synthetic.box_problem(16, 20, 12, solver="lusgs", viscous=True, size=2e-5, sweeps=2)))
 print("laminar", run(synthetic.box_problem(20, 12, 10, viscous=True, size=2e-5, sweeps=2)))
 print("sst", run(synthetic.box_problem(14, 10, 9, turb="sst2003", limiter="vanAlbada", size=1e-3, sweeps=2), 5.0))
 print("sst blusgs", run(synthetic.box_problem(12, 10, 9, turb="sst2003", solver="blusgs", limiter="vanAlbada", size=1e-3, sweeps=2), 5.0))
