@@ -22,6 +22,8 @@
 #include "boundaryConditions.hpp"
 #include "gridLevel.hpp"
 #include "input.hpp"
+#include <cstdlib>
+
 #include "kdtree.hpp"
 #include "logFileManager.hpp"
 #include "macros.hpp"
@@ -91,10 +93,15 @@ int main(int argc, char *argv[]) {
                                     MPI_vec3dMag);
   localSolution.AuxillaryAndWidths(phys);
   BroadcastViscFaces(MPI_vec3d, viscFaces);
-  kdtree tree(viscFaces);
-  if (tree.Size() > 0) {
-    localSolution.CalcWallDistance(tree);
-    localSolution.SwapWallDist(rank, inp.NumberGhostLayers());
+  // AITHER_GPU_WALLDIST set: the wall distance is computed on the device (gpuPath 1b below)
+  // instead of by the k-d tree search here
+  const bool gpuWallDist = std::getenv("AITHER_GPU_WALLDIST") != nullptr;
+  if (!gpuWallDist) {
+    kdtree tree(viscFaces);
+    if (tree.Size() > 0) {
+      localSolution.CalcWallDistance(tree);
+      localSolution.SwapWallDist(rank, inp.NumberGhostLayers());
+    }
   }
   solution.GetFinestGridLevel(localSolution, rank, MPI_uncoupledScalar, MPI_vec3d,
                               MPI_tensorDouble, inp);
@@ -105,6 +112,10 @@ int main(int argc, char *argv[]) {
 
   // <<< gpuPath 1: every grid level of this rank on the device
   gpuPath gpu(inp, phys, localSolution, rank, numProcs);
+  if (gpuWallDist) {  // <<< gpuPath 1b (was CalcWallDistance + SwapWallDist above)
+    gpu.ComputeWallDistance(viscFaces);
+    cout << "gpuPath: wall distance from " << viscFaces.size() << " wall faces on the device" << endl;
+  }
   cout << "gpuPath: " << aither_gpu_version() << ", " << localSolution.NumGridLevels()
        << " grid level(s), " << localSolution[0].NumBlocks() << " block(s)" << endl;
 

@@ -13,6 +13,8 @@
  *   gpuPath::StoreOldSolution   mgSolution::StoreOldSolution        src/mgSolution.cpp:103-114
  *   gpuPath::Iterate            mgSolution::Iterate / ImplicitUpdate / CycleAtLevel
  *                                                                   src/mgSolution.cpp:160-269
+ *   gpuPath::ComputeWallDistance mgSolution::CalcWallDistance + SwapWallDist (optional)
+ *                                                                   src/main.cpp:191-202
  *   gpuPath::DownloadStates     the state back into procBlock::state_ when main.cpp writes
  *                               output or a restart file            src/main.cpp:280-300
  *
@@ -318,6 +320,18 @@ class gpuPath {
     if (linf.linf > residLinf.Linf())
       residLinf = resid(linf.linf, linf.block, linf.i, linf.j, linf.k, linf.eqn);
     return mr;
+  }
+
+  // wall distance of every grid level on the device: replaces mgSolution::CalcWallDistance(tree)
+  // and SwapWallDist (src/main.cpp:191-202); `viscFaces` is what main.cpp broadcasts to every rank
+  // (GetViscousFaceCenters, src/utility.cpp:310-368). The procBlocks' own wallDist_ arrays are
+  // left as they are: nothing on the host reads them during the run.
+  void ComputeWallDistance(const std::vector<vector3d<double>> &viscFaces) {
+    static_assert(sizeof(vector3d<double>) == 3 * sizeof(double), "vector3d is three doubles");
+    for (aither_gpu *lv : levels_)
+      Check(aither_gpu_compute_wall_distance(lv, reinterpret_cast<const double *>(viscFaces.data()),
+                                             static_cast<long long>(viscFaces.size())),
+            "aither_gpu_compute_wall_distance");
   }
 
   // state of the finest level back into the procBlocks (main.cpp writes output / restart from it)

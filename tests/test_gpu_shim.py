@@ -30,8 +30,17 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("name,iters,gold", [c for c in CASES if c[0] in ("viscousFlatPlate", "turbFlatPlate")],
+                         ids=["viscousFlatPlate", "turbFlatPlate"])
+def test_shim_with_the_wall_distance_from_the_device(name, iters, gold):
+    """AITHER_GPU_WALLDIST=1: the shim skips the reference's k-d tree search and calls
+    aither_gpu_compute_wall_distance; the regression goldens are met all the same"""
+    test_shipped_case_through_the_shim(name, iters, gold, env_extra={"AITHER_GPU_WALLDIST": "1"},
+                                       expect="wall distance from")
+
+
 @pytest.mark.parametrize("name,iters,gold", CASES, ids=[c[0] for c in CASES])
-def test_shipped_case_through_the_shim(name, iters, gold):
+def test_shipped_case_through_the_shim(name, iters, gold, env_extra=None, expect=None):
     if not os.path.exists(BINARY):
         pytest.skip("oracle/_ref/aither_gpu_main has not been built (make -C oracle shim)")
     with tempfile.TemporaryDirectory() as tmp:
@@ -39,11 +48,12 @@ def test_shipped_case_through_the_shim(name, iters, gold):
                                  edits={"outputFrequency": str(iters)}, iterations=iters)
         with open(os.path.join(tmp, "air.dat"), "w") as f:
             f.write(refcase.AIR_DAT)
-        env = dict(os.environ, AITHER_INSTALL_DIRECTORY=tmp)
+        env = dict(os.environ, AITHER_INSTALL_DIRECTORY=tmp, **(env_extra or {}))
         res = subprocess.run([BINARY, inp], cwd=tmp, env=env, stdout=subprocess.PIPE,
                              stderr=subprocess.STDOUT, text=True, timeout=600)
         assert res.returncode == 0, res.stdout[-3000:]
         assert "gpuPath: aither_b200" in res.stdout and "Program Complete" in res.stdout
+        assert expect is None or expect in res.stdout, res.stdout[-3000:]
         last = open(os.path.join(tmp, name + ".resid")).readlines()[-1].split()
         # same columns as regressionTests.py GetTestCaseResiduals
         mine = [float(v) for v in last[3:3 + len(gold)]]
