@@ -152,7 +152,8 @@ struct HostBlock {
   bool ghostsInAlt = false;  // fused update: the ghost cells of the last fill sit in dev.stateAlt
   uint4 *dWaveMailJ = nullptr, *dWaveMailK = nullptr;  // hand-over between pencils (lusgs_pencil.cuh)
   unsigned waveTag = 0;                                 // number of the half sweep
-  bool waveCarries = false;  // no connections: a half sweep leaves the next one's ahead-sums behind
+  bool waveCarries = false;  // a half sweep leaves the next one's ahead-sums behind ...
+  bool waveFixup = false;    // ... except next to connected faces (ghost cells exchanged in between)
 };
 
 }  // namespace aither_host
@@ -604,11 +605,12 @@ int PackLusgsPencilV(aither_gpu *h, HostBlock &hb) {
     WaveGeoKernel<R::GN><<<grid, blk, 0, h->stream>>>(b, L, h->cfg.isViscous, hb.dWaveGeoLo,
                                                hb.dWaveGeoHi);
   }
-  // without connections the ghost cells of the update never change: half sweeps hand the next
-  // one's ahead-sums on (AITHER_B200_LUSGS_CARRY=0: always the parallel pass, for A/B runs)
+  // half sweeps hand the next one's ahead-sums on (AITHER_B200_LUSGS_CARRY=0: always the parallel
+  // pass, for A/B runs); next to connected faces they are formed again after the exchange
   static const bool carryOff = getenv("AITHER_B200_LUSGS_CARRY") && atoi(getenv("AITHER_B200_LUSGS_CARRY")) == 0;
   hb.waveCarries = !carryOff;
-  for (int s = 0; s < 6; ++s) hb.waveCarries = hb.waveCarries && b.connFace[s] == nullptr;
+  hb.waveFixup = false;
+  for (int s = 0; s < 6; ++s) hb.waveFixup = hb.waveFixup || b.connFace[s] != nullptr;
   ScopedLaunch sl(h, kFamLusgsPack);
   WaveDynKernel<NS, NT, VISC><<<grid, blk, 0, h->stream>>>(b, h->params, L, hb.dWaveDyn);
   return 0;
@@ -689,24 +691,39 @@ int LaunchLusgsPencil(aither_gpu *h, HostBlock &hb, bool forward, int fullGS) {
   return LaunchLusgsPencilV<NS, NT, true>(h, hb, forward, fullGS);
 }
 // the ahead-side sums (old update) of a half sweep in one parallel pass, before the wavefront
+// `fixupOnly`: the previous half sweep left this one's ahead-sums behind; only the cells whose
+// ahead-neighbour is a ghost cell across a connection (exchanged since) are formed again
 template <int NS, int NT, bool VISC>
-int LaunchLusgsAheadV(aither_gpu *h, HostBlock &hb, bool forward) {
+int LaunchLusgsAheadV(aither_gpu *h, HostBlock &hb, bool forward, bool fixupOnly) {
   const BlockDev &b = hb.dev;
   const PencilLattice L = LatticeOf(hb);
-  const dim3 agrid((b.ni + 31) / 32, (b.nj + 3) / 4, b.nk), ablk(32, 4, 1);
-  ScopedLaunch sa(h, kFamLusgsAhead);
-  if (forward)
-    LusgsAheadKernel<NS, NT, true, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
-  else
-    LusgsAheadKernel<NS, NT, false, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead);
+  const dim3 ablk(32, 4, 1);
+  auto launch = [&](int i0, int j0, int k0, int i1, int j1, int k1) {
+    const dim3 agrid((i1 - i0 + 31) / 32, (j1 - j0 + 3) / 4, k1 - k0);
+    ScopedLaunch sa(h, kFamLusgsAhead);
+    if (forward)
+      LusgsAheadKernel<NS, NT, true, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead,
+                                                                         i0, j0, k0, i1, j1);
+    else
+      LusgsAheadKernel<NS, NT, false, VISC><<<agrid, ablk, 0, h->stream>>>(b, h->params, L, hb.dWaveAhead,
+                                                                          i0, j0, k0, i1, j1);
+  };
+  if (!fixupOnly) {
+    launch(0, 0, 0, b.ni, b.nj, b.nk);
+    return 0;
+  }
+  // the ahead side of a forward sweep is the upper side (surfaces 2, 4, 6), of a backward one the lower
+  if (b.connFace[forward ? 1 : 0]) { const int i = forward ? b.ni - 1 : 0; launch(i, 0, 0, i + 1, b.nj, b.nk); }
+  if (b.connFace[forward ? 3 : 2]) { const int j = forward ? b.nj - 1 : 0; launch(0, j, 0, b.ni, j + 1, b.nk); }
+  if (b.connFace[forward ? 5 : 4]) { const int k = forward ? b.nk - 1 : 0; launch(0, 0, k, b.ni, b.nj, k + 1); }
   return 0;
 }
 template <int NS, int NT>
-int LaunchLusgsAhead(aither_gpu *h, HostBlock &hb, bool forward) {
+int LaunchLusgsAhead(aither_gpu *h, HostBlock &hb, bool forward, bool fixupOnly) {
   if constexpr (NT == 0) {
-    if (!h->cfg.isViscous) return LaunchLusgsAheadV<NS, NT, false>(h, hb, forward);
+    if (!h->cfg.isViscous) return LaunchLusgsAheadV<NS, NT, false>(h, hb, forward, fixupOnly);
   }
-  return LaunchLusgsAheadV<NS, NT, true>(h, hb, forward);
+  return LaunchLusgsAheadV<NS, NT, true>(h, hb, forward, fixupOnly);
 }
 
 int ZeroResult(aither_gpu *h, int slot) {
@@ -1009,8 +1026,12 @@ int PhaseRelaxJ(aither_gpu *h, int sweeps, int slot) {
         if constexpr (JAC == kJacScalar) {
           // the ahead-sums of this half sweep: left behind by the previous half sweep of this
           // iteration, unless ghost cells changed in between (connections) or there was none
+          // (blocks with connections: the cells next to a connected face on the ahead side are
+          // formed again, their ghost neighbours have been exchanged since)
           const bool carried = hb.waveCarries && !(s == 0 && forward);
-          if (h->lusgsWave && fullGS && !carried && LaunchLusgsAhead<NS, NT>(h, hb, forward)) return 1;
+          if (h->lusgsWave && fullGS && (!carried || hb.waveFixup) &&
+              LaunchLusgsAhead<NS, NT>(h, hb, forward, carried))
+            return 1;
         }
         ScopedLaunch sl(h, kFamLusgs);  // one timing record per half sweep
         if (h->lusgsWave) {

@@ -185,12 +185,16 @@ __global__ void __launch_bounds__(128)
 // src/procBlock.cpp:1056-1170). Fully parallel, all reads from the block's fields (coalesced).
 template <int NS, int NT, bool FORWARD, bool VISC>
 __global__ void __launch_bounds__(128)
-    LusgsAheadKernel(BlockDev b, Params p, PencilLattice L, double *__restrict__ ahead) {
+    LusgsAheadKernel(BlockDev b, Params p, PencilLattice L, double *__restrict__ ahead, int i0,
+                     int j0, int k0, int i1, int j1) {
+  // cells [i0, i1) x [j0, j1) x [k0, k0 + gridDim.z): the whole block, or the layer of cells next to
+  // a connected face (whose ghost cells changed since the previous half sweep left its sums)
   using E = Eq<NS, NT>;
   using R = PencilRec<NS, NT, VISC>;
   constexpr int neq = E::neq, AN = R::AN;
-  const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
-  if (i >= b.ni || j >= b.nj) return;
+  const int i = i0 + blockIdx.x * 32 + threadIdx.x, j = j0 + blockIdx.y * 4 + threadIdx.y,
+            k = k0 + blockIdx.z;
+  if (i >= i1 || j >= j1) return;
   const int c[3] = {i, j, k}, nd[3] = {b.ni, b.nj, b.nk};
   const long long idx = CellIdx(b, i, j, k);
   double acc[AN];
@@ -707,7 +711,8 @@ __global__ void __launch_bounds__(PencilCfg<NS, NT, VISC>::threads, 1)
         // sweep's sum over its ahead-neighbours with their OLD update (same neighbours, same
         // update, same faces): it goes where this plane's ahead-sum came from, and the parallel
         // ahead-sum pass (LusgsAheadKernel) is only needed before the first sweep of an iteration
-        // and for blocks whose ghost cells change between half sweeps (connections).
+        // and for the cells next to a connected face (their ghost neighbours are exchanged between
+        // half sweeps).
         if (carry != nullptr) {
           double *o = carry + (planeBase + planeOf(q)) * (R::AN * kPCells) + cellG;
 #pragma unroll
