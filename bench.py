@@ -465,6 +465,12 @@ def run_gpu_arm(args):
         # secondary workloads: SURVEY 8d's per-family table is for the headline (5 equations,
         # scalar diagonal); scale the state-sized entries by neq / 5 as a first-order figure
         alg = {k: int(round(v * neq / NEQ)) for k, v in alg.items()}
+    if args.solver == "lusgs":
+        # one launch = one half sweep of the pencil wavefront: per cell the packed
+        # record (2 neq + 4 doubles; + 2 viscous slots), the behind-side faces (14; 18 viscous),
+        # the ahead-sum read and the carried sum written (neq each), the update written (neq)
+        visc = bool(args.viscous or args.turb)
+        alg["lusgs_plane"] = (2 * neq + (6 if visc else 4)) + (18 if visc else 14) + 3 * neq
     fam = {k: v for k, v in prof.items() if v[1] > 0 and k in alg}
     top = max(fam, key=lambda k: fam[k][0])
     top_ms, top_n = fam[top]
