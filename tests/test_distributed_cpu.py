@@ -1,5 +1,6 @@
 """Host-side multi-rank logic on CPU (gloo, world_size 2): rank assignment of a connected lattice,
-the byte broadcast that carries the NCCL id, and the reduction of residual norms. The ghost-layer
+the byte broadcast that carries the NCCL id, the byte all-gather that carries the peer-memory
+handles of the direct ghost exchange, and the reduction of residual norms. The ghost-layer
 exchange itself is device code (tests/test_gpu_multigpu.py)."""
 import os
 import sys
@@ -22,6 +23,10 @@ def _worker(rank, world, port, out):
     ident = bytes(range(128)) if rank == 0 else bytes(128)
     got = adist.broadcast_bytes(ident, 128, src=0)
     assert got == bytes(range(128))
+    # the 64-byte peer-memory handles of all ranks, in rank order, on every rank
+    mine = bytes([rank + 1] * 64)
+    everyone = adist.all_gather_bytes(mine, 64)
+    assert everyone == b"".join(bytes([r + 1] * 64) for r in range(world))
     # every rank derives the same placement from the same connection list
     prob = synthetic.lattice_problem(4, (1, 2, 2), only=[])
     per = synthetic.assign_ranks(prob, world)
