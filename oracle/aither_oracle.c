@@ -3336,6 +3336,37 @@ long long orc_field_size(orc_level *h, int blk, int field) {
   return 0;
 }
 
+/* wallVars of one viscous-wall surface, 12 doubles per face in the order the reference's wall
+ * function file uses (y+, shear stress x / y / z, heat flux, wall temperature, wall eddy
+ * viscosity, wall viscosity, wall density, friction velocity, k, omega; include/wallData.hpp:40-57),
+ * faces i fastest, then j, then k over the surface's cell range. Returns the number of faces, 0 for
+ * a surface that keeps none. */
+long long orc_get_wall_data(orc_level *h, int blk, int surface, double *dst) {
+  const orc_block *b = &h->blk[blk];
+  if (surface < 0 || surface >= b->nsurf || !b->wall || !b->wall[surface]) return 0;
+  const aither_surface *sf = &b->surf[surface];
+  const int ext[3] = {sf->imax - sf->imin, sf->jmax - sf->jmin, sf->kmax - sf->kmin};
+  long n = 1;
+  for (int q = 0; q < 3; ++q) n *= ext[q] > 0 ? ext[q] : 1;
+  for (long f = 0; f < n && dst; ++f) {
+    const orc_wall_vars *w = &b->wall[surface][f];
+    double *o = dst + 12 * f;
+    o[0] = w->yplus;
+    o[1] = w->shearStress[0];
+    o[2] = w->shearStress[1];
+    o[3] = w->shearStress[2];
+    o[4] = w->heatFlux;
+    o[5] = w->temperature;
+    o[6] = w->turbEddyVisc;
+    o[7] = w->viscosity;
+    o[8] = w->density;
+    o[9] = w->frictionVelocity;
+    o[10] = w->tke;
+    o[11] = w->sdr;
+  }
+  return n;
+}
+
 void orc_get_field(orc_level *h, int blk, int field, double *dst) {
   const orc_block *b = &h->blk[blk];
   const double *src = NULL;

@@ -46,6 +46,9 @@ double orc_iterate(orc_level *h, double cfl, int mm, double *residL2,
 
 long long orc_field_size(orc_level *h, int blk, int field);
 void orc_get_field(orc_level *h, int blk, int field, double *dst);
+/* wallVars of a viscous-wall surface (12 doubles per face, the reference's wallData order);
+ * returns the number of faces (dst may be NULL to ask for it) */
+long long orc_get_wall_data(orc_level *h, int blk, int surface, double *dst);
 void orc_set_state(orc_level *h, int blk, const double *stateAoS);
 
 /* point functions, exported for unit tests against the device functions */

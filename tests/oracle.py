@@ -39,6 +39,8 @@ def lib():
         L.orc_field_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_field_size.restype = C.c_longlong
         L.orc_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.orc_get_wall_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.orc_get_wall_data.restype = C.c_longlong
         L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         pd = C.POINTER(C.c_double)
         L.orc_muscl.argtypes = [pd, pd, pd, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double,
@@ -118,6 +120,15 @@ class OracleLevel:
         mr = lib().orc_iterate(self._h, cfl, mm, l2.ctypes.data_as(C.POINTER(C.c_double)),
                                C.byref(linf))
         return l2, linf, mr
+
+    def wall_data(self, blk, surface):
+        """wall variables of a viscous-wall surface, shape (nk, nj, ni, 12) over its cell range"""
+        sf = self.problem.blocks[blk].surfaces[surface]
+        shp = (max(sf[6] - sf[5], 1), max(sf[4] - sf[3], 1), max(sf[2] - sf[1], 1))
+        out = np.zeros(shp + (12,))
+        n = lib().orc_get_wall_data(self._h, blk, surface, out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert n in (0, int(np.prod(shp))), (n, shp)
+        return out if n else None
 
     def field(self, blk, fld):
         n = lib().orc_field_size(self._h, blk, fld)

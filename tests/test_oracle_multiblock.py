@@ -3,6 +3,7 @@ and its decomposition invariance on a split synthetic box."""
 import numpy as np
 
 import goldencheck as gc
+import refcase
 import oracle
 from aither_b200 import ctypes_abi as abi
 from aither_b200 import synthetic
@@ -80,6 +81,37 @@ def test_oracle_wall_law():
     assert gc.check_history(oracle.OracleLevel, d, 6, 1e-9) <= 1e-9
     d = gc.load("wallLaw")
     assert gc.check_history(oracle.OracleLevel, d, 20, 1e-9, name="wallLaw") <= 1e-9
+
+
+def test_oracle_wall_data():
+    """The oracle's wall variables (y+, wall shear stress, heat flux, wall temperature /
+    viscosities / density, friction velocity, k, omega per wall face) after the first residual
+    evaluation of testCases/wallLaw from a perturbed state, against the reference's own wallData
+    (include/wallData.hpp:40-57) -- the CPU pin of what aither_gpu_download_wall_data returns
+    (tests/test_gpu_multiblock.py::test_wall_data_matches_reference)."""
+    d = gc.load("wallLaw_cloud")
+    prob = refcase.problem_from_dump(d, state_key="state0")
+    lvl = oracle.OracleLevel(prob)
+    lvl.store_old_solution(0)
+    lvl.get_boundary_conditions()
+    lvl.calc_residual()
+    seen = 0
+    for bb, blk in enumerate(prob.blocks):
+        ww = 0
+        while "b%d/wall%d/surface" % (bb, ww) in d:
+            sf = [int(v) for v in d["b%d/wall%d/surface" % (bb, ww)]]
+            ref = d["b%d/wall%d/vars@it0" % (bb, ww)]
+            idx = [n for n, s in enumerate(blk.surfaces) if list(s[1:7]) == sf[:6]]
+            assert len(idx) == 1, (sf, blk.surfaces)
+            mine = lvl.wall_data(bb, idx[0])
+            assert mine is not None and mine.shape == ref.shape, (None if mine is None else mine.shape, ref.shape)
+            # the three shear-stress components are one vector
+            err = gc.rel(mine, ref, groups=([1, 2, 3],))
+            assert err <= 1e-11, (bb, ww, err)
+            seen += 1
+            ww += 1
+    assert seen >= 1
+    lvl.close()
 
 
 def test_oracle_convecting_vortex_nonreflecting():
