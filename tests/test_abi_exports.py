@@ -71,3 +71,24 @@ def test_create_rejects_unsupported_configurations(field, value, needle):
     setattr(prob.cfg, field, value)
     with pytest.raises(aither_b200.AitherGpuError, match=needle):
         aither_b200.GridLevel(prob)
+
+
+def test_entry_points_refuse_a_null_handle():
+    """Every entry point that takes a handle reports an error for a null one (and says so in
+    aither_gpu_last_error) instead of touching a device: runs on a machine without a GPU."""
+    lib = aither_b200.load_library()
+    buf = (C.c_double * 16)()
+    raw = C.create_string_buffer(64 * 2)
+    calls = [
+        lambda: lib.aither_gpu_compute_wall_distance(None, buf, 1),
+        lambda: lib.aither_gpu_download_output(None, 0, 0, 0, 1.0, buf),
+        lambda: lib.aither_gpu_download_wall_data(None, 0, 0, buf),
+        lambda: lib.aither_gpu_upload_interior_async(None, 0, buf),
+        lambda: lib.aither_gpu_upload_state_async(None, 0, buf),
+        lambda: lib.aither_gpu_halo_p2p_export(None, raw),
+        lambda: lib.aither_gpu_halo_p2p_import(None, raw),
+        lambda: lib.aither_gpu_iterate(None, 1.0, 0, buf, None, None),
+    ]
+    for call in calls:
+        assert call() != 0
+        assert b"null" in lib.aither_gpu_last_error()
